@@ -1,0 +1,244 @@
+/*
+ * shineon_b200.h — C ABI of libshineon_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the per-frame try-on hot path of
+ * andrewjong/ShineOn-Virtual-Tryon.  Every entry point is `extern "C"`, takes
+ * plain device pointers + sizes + a cudaStream_t, never allocates, never
+ * synchronises, only enqueues on the given stream, and returns 0 on success or
+ * a negative shineon_status (the reference's extensions return `int 1` and
+ * swallow launch errors: correlation_cuda.cc:80-87, resample2d_cuda.cc:6-13;
+ * this ABI is stricter on purpose).  `shineon_last_error()` returns the text
+ * of the last failure on the calling thread.
+ *
+ * Reference interfaces each group replaces (paths relative to the reference
+ * checkout):
+ *   resample2d   models/flownet2_pytorch/networks/resample2d_package/resample2d_cuda.cc:6-31
+ *   channelnorm  models/flownet2_pytorch/networks/channelnorm_package/channelnorm_cuda.cc:6-30
+ *   correlation  models/flownet2_pytorch/networks/correlation_package/correlation_cuda.cc:10-172
+ *   tps / grid_sample   models/networks/cpvton/warp.py:116-318, models/warp_model.py:85-86,143-145
+ *   conv2d_igemm / pack / instnorm / prep / attention / compose
+ *                models/networks/cpvton/{warp,unet}.py, models/networks/attention/sagan.py,
+ *                models/unet_mask_model.py:64-135 (stock torch.nn ops there)
+ *
+ * Layout conventions
+ *   "NCHW f32"   : the reference's public tensor layout (contiguous).
+ *   "NHWC planes": internal activation layout of the tensor-core path:
+ *                  two bf16 tensors [N,H,W,Cpad] (hi, lo) with x ~= hi + lo
+ *                  (lo may be NULL in single-bf16 mode); Cpad % 64 == 0,
+ *                  channels >= C are zero.
+ */
+#ifndef SHINEON_B200_H_
+#define SHINEON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* shineon_stream_t; /* cudaStream_t */
+
+enum shineon_status {
+  SHINEON_OK = 0,
+  SHINEON_ERR_ARG = -1,         /* bad argument (shape, alignment, null pointer) */
+  SHINEON_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed */
+  SHINEON_ERR_UNSUPPORTED = -3, /* valid request this build has no kernel for */
+};
+
+enum shineon_act {
+  SHINEON_ACT_NONE = 0,
+  SHINEON_ACT_RELU = 1,
+  SHINEON_ACT_LEAKY = 2, /* slope in act_param */
+  SHINEON_ACT_GELU = 3,  /* exact erf form (nn.GELU()) */
+  SHINEON_ACT_SWISH = 4, /* x*sigmoid(x)  activation.py:13-18 */
+  SHINEON_ACT_SINE = 5,  /* sin(30x)      activation.py:4-11 */
+  SHINEON_ACT_TANH = 6,
+  SHINEON_ACT_SIGMOID = 7,
+};
+
+enum shineon_padding_mode { SHINEON_PAD_ZEROS = 0, SHINEON_PAD_BORDER = 1 };
+
+int shineon_version(void);
+const char* shineon_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t shineon_launch_count(void);
+
+/* ------------------------------------------------------------------ */
+/* G5/G6: thin-plate-spline grid + bilinear grid_sample                */
+/* ------------------------------------------------------------------ */
+
+/* Constant tables of TpsGridGen (all f32, device memory), built by the host exactly like the
+ * reference constructor does (warp.py:116-157): Li [(gs*gs+3)^2] = compute_L_inverse (warp.py:169-189),
+ * P_X/P_Y [gs*gs] control points, grid_X [W] / grid_Y [H] = float32(np.linspace(-1,1,.)). */
+typedef struct shineon_tps_tables {
+  const float* Li;
+  const float* P_X;
+  const float* P_Y;
+  const float* grid_X;
+  const float* grid_Y;
+  int grid_size;
+} shineon_tps_tables;
+
+/* TpsGridGen.forward (warp.py:159-318).  theta [B, 2*gs*gs] f32 -> grid [B,H,W,2] f32. */
+int shineon_tps_grid_fwd(const float* theta, const shineon_tps_tables* tps, float* grid, int B, int H, int W,
+                         shineon_stream_t stream);
+
+/* F.grid_sample(input, grid, mode="bilinear", padding_mode, align_corners=False)
+ * input [B,C,Hin,Win] f32 NCHW, grid [B,Hout,Wout,2], out [B,C,Hout,Wout]. */
+int shineon_grid_sample_fwd(const float* input, const float* grid, float* out, int B, int C, int Hin,
+                            int Win, int Hout, int Wout, int padding_mode, shineon_stream_t stream);
+
+/* Fused TPS + grid_sample: the grid is never materialised (warp_model.py:84-86 / 142-145).
+ * Up to 3 inputs sampled with the same grid; inputs[i] is [B,C_i,H,W] f32 or NULL.
+ * grid_out may be NULL. */
+int shineon_tps_grid_sample_fwd(const float* theta, const shineon_tps_tables* tps, int B, int H, int W,
+                                const float* in0, int C0, int pad0, float* out0,
+                                const float* in1, int C1, int pad1, float* out1,
+                                const float* in2, int C2, int pad2, float* out2,
+                                float* grid_out, shineon_stream_t stream);
+
+/* ------------------------------------------------------------------ */
+/* N1: Resample2d (resample2d_kernel.cu:16-72 fwd, :76-198 bwd)         */
+/* ------------------------------------------------------------------ */
+/* in1 [B,C,Hi,Wi], flow [B,2,H,W] (pixel units), out [B,C,H,W]; all f32 NCHW. */
+int shineon_resample2d_fwd(const float* in1, const float* flow, float* out, int B, int C, int Hi, int Wi,
+                           int H, int W, int kernel_size, int bilinear, shineon_stream_t stream);
+/* grad_in1 [B,C,Hi,Wi] must be zero-filled by the caller (resample2d.py:35); grad_flow [B,2,H,W]. */
+int shineon_resample2d_bwd(const float* in1, const float* flow, const float* grad_out, float* grad_in1,
+                           float* grad_flow, int B, int C, int Hi, int Wi, int H, int W, int kernel_size,
+                           int bilinear, shineon_stream_t stream);
+
+/* ------------------------------------------------------------------ */
+/* N3: ChannelNorm (channelnorm_kernel.cu:19-60 fwd, :64-96 bwd)         */
+/* ------------------------------------------------------------------ */
+int shineon_channelnorm_fwd(const float* in, float* out, int B, int C, int H, int W, int norm_deg,
+                            shineon_stream_t stream);
+int shineon_channelnorm_bwd(const float* in, const float* out, const float* grad_out, float* grad_in,
+                            int B, int C, int H, int W, int norm_deg, shineon_stream_t stream);
+
+/* ------------------------------------------------------------------ */
+/* N2: FlowNet Correlation (correlation_cuda_kernel.cu:47-147 fwd, :151-334 bwd) */
+/* ------------------------------------------------------------------ */
+/* Output geometry per correlation_cuda.cc:19-38. */
+int shineon_correlation_out_shape(int C, int H, int W, int pad_size, int kernel_size, int max_displacement,
+                                  int stride1, int stride2, int* out_c, int* out_h, int* out_w);
+/* in1,in2 [B,C,H,W] f32 NCHW -> out [B,out_c,out_h,out_w].  No padded NHWC scratch (rbot1/2) needed. */
+int shineon_correlation_fwd(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
+                            int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
+                            shineon_stream_t stream);
+int shineon_correlation_bwd(const float* in1, const float* in2, const float* grad_out, float* grad_in1,
+                            float* grad_in2, int B, int C, int H, int W, int pad_size, int kernel_size,
+                            int max_displacement, int stride1, int stride2, shineon_stream_t stream);
+
+/* ------------------------------------------------------------------ */
+/* Tensor-core convolution (tcgen05 implicit GEMM)                      */
+/* ------------------------------------------------------------------ */
+
+/* OIHW f32 -> [Cout][kh][kw][cin_pad] bf16 hi (+ lo).  chan_map (device, int32[cin_pad]) maps a padded
+ * input channel to the OIHW input channel or -1 (zero); NULL = identity for c<Cin, zero above.
+ * transpose_io != 0 reads a ConvTranspose2d weight [Cin][Cout][kh][kw] with the taps flipped. */
+int shineon_pack_conv_weight(const float* w, void* w_hi, void* w_lo, int Cout, int Cin, int kh, int kw,
+                             int cin_pad, const int32_t* chan_map, int transpose_io,
+                             shineon_stream_t stream);
+
+typedef struct shineon_conv2d_params {
+  /* input activation, NHWC planes [N,H,W,cin_pad] bf16 */
+  const void* x_hi;
+  const void* x_lo; /* NULL => single-bf16 products (fast mode) */
+  int N, H, W, cin_pad;
+  /* packed weights [Cout][kh*kw][cin_pad] bf16 */
+  const void* w_hi;
+  const void* w_lo; /* NULL unless x_lo given */
+  int Cout, kh, kw, stride;      /* stride 1 or 2 (stride 2 needs even H, W) */
+  int pad_h, pad_w;              /* zero padding before the first row / column */
+  int Ho, Wo;                    /* output size; rows/cols past the input read zeros, so any
+                                    Ho <= (H + pad_h)/stride is legal (asymmetric padding) */
+  /* epilogue: v = acc + bias; v = pre_act(v); v = v*scale + shift; v = post_act(v) */
+  const float* bias;  /* [Cout] or NULL */
+  const float* scale; /* [Cout] or NULL (with shift) */
+  const float* shift;
+  int pre_act, post_act;
+  float act_param;
+  /* outputs (any subset): f32 NHWC and/or bf16 planes NHWC, pixel (n, oh*oh_mul+oh_off, ow*ow_mul+ow_off)
+   * of a [N,out_H,out_W,out_cstride] tensor, channels written at out_coffset.. */
+  float* y_f32;
+  void* y_hi;
+  void* y_lo;
+  int out_H, out_W, out_cstride, out_coffset;
+  int oh_mul, oh_off, ow_mul, ow_off;
+  /* tuning overrides, 0 = auto */
+  int tile_n; /* 16,32,64,128,256 */
+  int stages;
+} shineon_conv2d_params;
+
+int shineon_conv2d_igemm_fwd(const shineon_conv2d_params* p, shineon_stream_t stream);
+/* CUDA-core fp32 direct convolution over the same operands: the on-GPU cross-check of the tcgen05
+ * kernel used by tests (not on the product path). */
+int shineon_conv2d_direct_fwd(const shineon_conv2d_params* p, shineon_stream_t stream);
+
+/* ------------------------------------------------------------------ */
+/* Layout / pointwise / normalisation                                   */
+/* ------------------------------------------------------------------ */
+
+/* NCHW f32 [N,C,H,W] (optionally a second tensor concatenated on C) -> NHWC planes [N,H,W,cpad],
+ * with activation applied (unet.py:132 down-activation on the block input). */
+int shineon_nchw_to_planes(const float* x0, int C0, const float* x1, int C1, void* y_hi, void* y_lo, int N,
+                           int H, int W, int cpad, int act, float act_param, shineon_stream_t stream);
+
+/* nn.InstanceNorm2d(affine=False, eps) over f32 NHWC x [N,H,W,C] (unet.py:133,135) followed by
+ * activation; writes any subset of: f32 NHWC y_f32 (may alias x), planes y_hi/y_lo [N,H,W,cpad].
+ * do_norm=0 skips the normalisation (innermost down block, unet.py:166-175).
+ * stats_ws: caller-owned scratch of 2*N*C doubles (sum, sum of squares); zeroed by the call. */
+int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, void* y_lo, double* stats_ws, int N, int H,
+                         int W, int C, int cpad, float eps, int do_norm, int act, float act_param,
+                         shineon_stream_t stream);
+
+/* Up-path input of a U-Net block (unet.py:138-146): up_act -> cat([skip, x'],C) -> bilinear x2
+ * (align_corners=False).  Sources are activated planes [N,H,W,c{0,1}pad]; the extra activation
+ * `act` (ReLU on the default path, where the skip already holds LeakyReLU'd values, unet.py:132,198)
+ * is applied before interpolation.  Output planes [N,2H,2W,c0pad+c1pad]. src1 may be NULL. */
+int shineon_upsample2x_cat(const void* s0_hi, const void* s0_lo, int c0pad, const void* s1_hi,
+                           const void* s1_lo, int c1pad, void* y_hi, void* y_lo, int N, int H, int W,
+                           int act, float act_param, shineon_stream_t stream);
+
+/* SAGAN self-attention core (sagan.py:29-53) given the fused 1x1 projection
+ * qkv f32 NHWC [N,HW,2*Cq+C] (q | k | v) and x f32 NHWC [N,HW,C]:
+ * out = act(gamma * (V . softmax(q^T k)^T) + x); writes f32 and/or planes. */
+int shineon_sagan_attention(const float* qkv, const float* x, const float* gamma, float* y_f32, void* y_hi,
+                            void* y_lo, int N, int HW, int C, int Cq, int cpad, int act, float act_param,
+                            shineon_stream_t stream);
+
+/* ------------------------------------------------------------------ */
+/* GMM glue                                                             */
+/* ------------------------------------------------------------------ */
+
+/* FeatureL2Norm x2 + FeatureCorrelation (warp.py:39-67) on f32 NHWC features [B,h*w,C]:
+ * out planes [B,h,w,cpad] with channel iA = wA*h + hA (warp.py:60), value = <A/|A|, B/|B|>.
+ * corr_f32 (optional) receives the same values as f32 NHWC [B,h,w,h*w]. */
+int shineon_l2norm_correlation(const float* featA, const float* featB, float* corr_f32, void* y_hi,
+                               void* y_lo, int B, int h, int w, int C, int cpad, shineon_stream_t stream);
+
+/* FeatureRegression tail (warp.py:94-99): x f32 NHWC [B,h,w,C] flattened in NCHW order ->
+ * Linear(C*h*w -> out_dim) -> tanh.  weight [out_dim, C*h*w], bias [out_dim]; theta [B,out_dim]. */
+int shineon_linear_tanh(const float* x, const float* weight, const float* bias, float* theta, int B, int h,
+                        int w, int C, int out_dim, shineon_stream_t stream);
+
+/* ------------------------------------------------------------------ */
+/* U5: try-on composition (unet_mask_model.py:74-135)                   */
+/* ------------------------------------------------------------------ */
+/* unet_out f32 NHWC [B,H,W,Cout] (post InstanceNorm), Cout = (4 or 5)*n_frames.  Per frame f:
+ *   rend = tanh(out[3f..3f+2]); mask = sigmoid(out[3n+f]); fmask = sigmoid(out[4n+f]) if flow_warp
+ *   if warped_prev != NULL (frame f>0 with flows): rend' = (1-fmask)*warped_prev + fmask*rend
+ *   tryon = (1-mask)*rend' + mask*cloth
+ * Writes NCHW f32 channel slices of p_rendereds [B,3n,H,W], tryon_masks [B,n,H,W],
+ * p_tryons [B,3n,H,W], flow_masks [B,n,H,W] (may be NULL) for frame index f.
+ * cloth is [B,3n,H,W]; warped_prev is [B,3,H,W] or NULL. */
+int shineon_tom_compose(const float* unet_out, int Cout, const float* cloth, const float* warped_prev,
+                        float* p_rendereds, float* tryon_masks, float* p_tryons, float* flow_masks, int B,
+                        int H, int W, int n_frames, int frame, int flow_warp, shineon_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHINEON_B200_H_ */

@@ -1,0 +1,98 @@
+"""ctypes binding of the C ABI declared in include/shineon_b200.h.
+
+There is no CPU or PyTorch fallback: if libshineon_b200.so is missing or does not load, every op raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libshineon_b200.so")
+
+c_p = C.c_void_p
+c_i = C.c_int
+c_f = C.c_float
+
+ACT = {None: 0, "none": 0, "relu": 1, "leaky": 2, "gelu": 3, "swish": 4, "sine": 5, "tanh": 6, "sigmoid": 7}
+PAD = {"zeros": 0, "border": 1}
+
+
+class TpsTables(C.Structure):
+    _fields_ = [("Li", c_p), ("P_X", c_p), ("P_Y", c_p), ("grid_X", c_p), ("grid_Y", c_p), ("grid_size", c_i)]
+
+
+class Conv2dParams(C.Structure):
+    _fields_ = [
+        ("x_hi", c_p), ("x_lo", c_p), ("N", c_i), ("H", c_i), ("W", c_i), ("cin_pad", c_i),
+        ("w_hi", c_p), ("w_lo", c_p), ("Cout", c_i), ("kh", c_i), ("kw", c_i), ("stride", c_i), ("pad_h", c_i), ("pad_w", c_i),
+        ("Ho", c_i), ("Wo", c_i),
+        ("bias", c_p), ("scale", c_p), ("shift", c_p), ("pre_act", c_i), ("post_act", c_i), ("act_param", c_f),
+        ("y_f32", c_p), ("y_hi", c_p), ("y_lo", c_p),
+        ("out_H", c_i), ("out_W", c_i), ("out_cstride", c_i), ("out_coffset", c_i),
+        ("oh_mul", c_i), ("oh_off", c_i), ("ow_mul", c_i), ("ow_off", c_i),
+        ("tile_n", c_i), ("stages", c_i),
+    ]
+
+
+# name -> argtypes (every function returns int status unless listed in _RESTYPES)
+SIGNATURES = {
+    "shineon_version": [],
+    "shineon_last_error": [],
+    "shineon_launch_count": [],
+    "shineon_tps_grid_fwd": [c_p, C.POINTER(TpsTables), c_p, c_i, c_i, c_i, c_p],
+    "shineon_grid_sample_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_tps_grid_sample_fwd": [c_p, C.POINTER(TpsTables), c_i, c_i, c_i,
+                                    c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
+    "shineon_resample2d_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_resample2d_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_channelnorm_fwd": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_channelnorm_bwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_correlation_out_shape": [c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
+                                      C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i)],
+    "shineon_correlation_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_correlation_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_pack_conv_weight": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p],
+    "shineon_conv2d_igemm_fwd": [C.POINTER(Conv2dParams), c_p],
+    "shineon_conv2d_direct_fwd": [C.POINTER(Conv2dParams), c_p],
+    "shineon_nchw_to_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
+    "shineon_instnorm_act": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_f, c_p],
+    "shineon_upsample2x_cat": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
+    "shineon_sagan_attention": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
+    "shineon_l2norm_correlation": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_linear_tanh": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_tom_compose": [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+}
+_RESTYPES = {"shineon_last_error": C.c_char_p, "shineon_launch_count": C.c_uint64}
+
+_lib = None
+
+
+class ShineonError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libshineon_b200.so (once) and attach prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ShineonError(
+            f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+            "There is no CPU/PyTorch fallback for the shineon ops.")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == symbol missing from the build
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_i)
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().shineon_last_error()
+        raise ShineonError(f"{what} failed with status {status}: {msg.decode() if msg else ''}")
+
+
+def launch_count():
+    return int(load().shineon_launch_count())

@@ -1,0 +1,621 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Replaces every nn.Conv2d / nn.ConvTranspose2d on the hot path (cuDNN calls in the reference):
+//   models/networks/cpvton/warp.py:14-28,74-84   (GMM 4x4 s2 / 3x3 s1)
+//   models/networks/cpvton/unet.py:129-174       (U-Net 4x4 s2 down, 3x3 s1 up)
+//   models/networks/attention/sagan.py:16-24     (1x1 q/k/v projections)
+//   models/flownet2_pytorch/networks/submodules.py:7-38 (FlowNet2 7x7/5x5/3x3/1x1, deconv 4x4 s2)
+//
+// GEMM view:  D[M = 128 output pixels, N = BN output channels] += A_tap[M, 64 ch] * W_tap[N, 64 ch]^T
+// over K-blocks kb = (tap, 64-channel slice).
+//   * A tiles come straight from the NHWC activation with one TMA box per K-block: a 4-D box
+//     {64 ch, bw, bh, nb} shifted by the filter tap for stride 1, and for stride 2 a 5-D box over the
+//     [N, H/2, 2, W/2, 2*C] view of the same tensor (row/column parity folded into the coordinates).
+//     Out-of-bounds box elements are zero-filled by TMA = the convolution's zero padding.
+//   * B tiles are {64, BN} boxes of the packed weight matrix [Cout][taps*Cin_pad].
+//   * Both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes.
+//   * One elected thread issues tcgen05.mma (M=128, N=BN, K=16, bf16 -> fp32 in TMEM); with hi/lo
+//     planes it issues hi*hi + hi*lo + lo*hi (bf16x3: fp32-grade products).
+//   * 4 epilogue warps read TMEM (tcgen05.ld 32x32b), apply bias / activation / per-channel affine
+//     (folded BatchNorm) and store fp32 NHWC and/or bf16 hi/lo planes for the next layer.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace shineon {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                 // bf16 elements = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+
+struct ConvArgs {
+  // tile geometry
+  int nb, bh, bw;
+  int tiles_w, tiles_h;
+  int N, Ho, Wo, Cout;
+  int kh, kw, stride, pad_h, pad_w;
+  int cin_pad, cin_blocks;
+  int num_kb, stages;
+  // epilogue
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  int pre_act, post_act;
+  float act_param;
+  float* y_f32;
+  __nv_bfloat16* y_hi;
+  __nv_bfloat16* y_lo;
+  int out_H, out_W, out_cstride, out_coffset;
+  int oh_mul, oh_off, ow_mul, ow_off;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 24)) {  // ~seconds: a protocol bug must fault, never hang the GPU
+      printf("shineon conv_igemm: mbarrier timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x,
+             blockIdx.y, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (= 1024 B: 8 rows)
+//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------- epilogue
+__device__ __forceinline__ float conv_epilogue_value(float acc, int c, const ConvArgs& a) {
+  float v = acc;
+  if (a.bias) v += __ldg(a.bias + c);
+  v = apply_act(v, a.pre_act, a.act_param);
+  if (a.scale) v = fmaf(v, __ldg(a.scale + c), __ldg(a.shift + c));
+  v = apply_act(v, a.post_act, a.act_param);
+  return v;
+}
+
+// Stores `cnt` (<= 32, multiple of 8 unless at the Cout edge) consecutive channels of one pixel.
+__device__ __forceinline__ void conv_store_row(const float* vals, int c_first, int cnt, long pix, const ConvArgs& a) {
+  const long base = pix * a.out_cstride + a.out_coffset + c_first;
+  if (a.y_f32) {
+    float* dst = a.y_f32 + base;
+    if ((cnt & 3) == 0 && (base & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        if (i < cnt) *reinterpret_cast<float4*>(dst + i) = make_float4(vals[i], vals[i + 1], vals[i + 2], vals[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < cnt) dst[i] = vals[i];
+    }
+  }
+  if (a.y_hi) {
+    const bool vec = (cnt & 7) == 0 && (base & 7) == 0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      if (i >= cnt) break;
+      __align__(16) __nv_bfloat16 hi[8];
+      __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_bf16(i + j < cnt ? vals[i + j] : 0.f, hi[j], lo[j]);
+      if (vec) {
+        *reinterpret_cast<uint4*>(a.y_hi + base + i) = *reinterpret_cast<const uint4*>(hi);
+        if (a.y_lo) *reinterpret_cast<uint4*>(a.y_lo + base + i) = *reinterpret_cast<const uint4*>(lo);
+      } else {
+        for (int j = 0; j < 8 && i + j < cnt; ++j) {
+          a.y_hi[base + i + j] = hi[j];
+          if (a.y_lo) a.y_lo[base + i + j] = lo[j];
+        }
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------- kernel
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+    conv_igemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                      const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                      const ConvArgs a) {
+  constexpr int kBBytes = BN * kBlockK * 2;
+  constexpr int kPlanes = SPLIT ? 2 : 1;
+  constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kIdesc = umma_idesc_bf16(kBlockM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = a.stages;
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]),
+                 bar_tmem = smem_u32(&bars[2 * kMaxStages]);
+
+  // tile coordinates
+  const int mt = blockIdx.x;
+  const int tw = mt % a.tiles_w;
+  const int th = (mt / a.tiles_w) % a.tiles_h;
+  const int tn = mt / (a.tiles_w * a.tiles_h);
+  const int n0 = tn * a.nb, h0 = th * a.bh, w0 = tw * a.bw;
+  const int cn0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmAh);
+    prefetch_tmap(&tmBh);
+    if (SPLIT) {
+      prefetch_tmap(&tmAl);
+      prefetch_tmap(&tmBl);
+    }
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_tmem, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      const uint32_t a_rows = a.nb * a.bh * a.bw;
+      const uint32_t tx = kPlanes * (a_rows * (kBlockK * 2) + kBBytes);
+      for (int kb = 0; kb < a.num_kb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t full = bar_full + 8 * s;
+        mbar_expect_tx(full, tx);
+        const uint32_t sA = tiles + s * kStageBytes;
+        const uint32_t sB = sA + kPlanes * kABytes;
+        const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks;
+        const int fy = tap / a.kw, fx = tap - fy * a.kw;
+        if (a.stride == 1) {
+          const int cx = w0 + fx - a.pad_w, cy = h0 + fy - a.pad_h;
+          tma_load_4d(sA, &tmAh, full, cb * kBlockK, cx, cy, n0);
+          if (SPLIT) tma_load_4d(sA + kABytes, &tmAl, full, cb * kBlockK, cx, cy, n0);
+        } else {
+          // input row 2*oh + fy - pad = 2*(oh + ay) + py ; same for columns
+          const int ty = fy - a.pad_h, tx_ = fx - a.pad_w;
+          const int py = ty & 1, px = tx_ & 1;
+          const int ay = (ty - py) >> 1, ax = (tx_ - px) >> 1;
+          const int cc = px * a.cin_pad + cb * kBlockK;
+          tma_load_5d(sA, &tmAh, full, cc, w0 + ax, py, h0 + ay, n0);
+          if (SPLIT) tma_load_5d(sA + kABytes, &tmAl, full, cc, w0 + ax, py, h0 + ay, n0);
+        }
+        tma_load_2d(sB, &tmBh, full, kb * kBlockK, cn0);
+        if (SPLIT) tma_load_2d(sB + kBBytes, &tmBl, full, kb * kBlockK, cn0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (single thread)
+    if (lane == 0) {
+      for (int kb = 0; kb < a.num_kb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sA = tiles + s * kStageBytes;
+        const uint32_t sB = sA + kPlanes * kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t dAh = umma_desc_sw128(sA + k * 32);
+          const uint64_t dBh = umma_desc_sw128(sB + k * 32);
+          umma_bf16(tmem_acc, dAh, dBh, kIdesc, (kb | k) != 0);
+          if (SPLIT) {
+            const uint64_t dAl = umma_desc_sw128(sA + kABytes + k * 32);
+            const uint64_t dBl = umma_desc_sw128(sB + kBBytes + k * 32);
+            umma_bf16(tmem_acc, dAh, dBl, kIdesc, 1);
+            umma_bf16(tmem_acc, dAl, dBh, kIdesc, 1);
+          }
+        }
+        umma_commit(bar_empty + 8 * s);  // frees the smem slot once these MMAs retire
+      }
+      umma_commit(bar_tmem);  // accumulator complete
+    }
+  } else {
+    // ===================================================== epilogue: TMEM -> registers -> global
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const int wi = r % a.bw, hi_ = (r / a.bw) % a.bh, ni = r / (a.bw * a.bh);
+    const int n = n0 + ni, oh = h0 + hi_, ow = w0 + wi;
+    const bool row_ok = ni < a.nb && n < a.N && oh < a.Ho && ow < a.Wo;
+    const long pix = ((long)n * a.out_H + (oh * a.oh_mul + a.oh_off)) * a.out_W + (ow * a.ow_mul + a.ow_off);
+    mbar_wait(bar_tmem, 0);
+    tc_fence_after();
+    constexpr int kChunk = BN < 32 ? BN : 32;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += kChunk) {
+      if (cn0 + c0 >= a.Cout) break;  // warp-uniform
+      uint32_t v[32];
+      const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      if (kChunk == 32)
+        tmem_ld32(taddr, v);
+      else
+        tmem_ld16(taddr, v);
+      tmem_ld_wait();
+      if (row_ok) {
+        const int cnt = min(kChunk, a.Cout - (cn0 + c0));
+        float vals[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          vals[i] = (i < cnt) ? conv_epilogue_value(__uint_as_float(v[i]), cn0 + c0 + i, a) : 0.f;
+        conv_store_row(vals, cn0 + c0, cnt, pix, a);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_acc);
+}
+
+// ---------------------------------------------------------------------------- CUDA-core cross-check
+// Same operands, same epilogue, plain fp32 FMAs.  Tests compare the tcgen05 kernel against this on
+// the GPU at sizes where the CPU oracle would take minutes.  Not on the product path.
+__global__ void __launch_bounds__(128)
+    conv_direct_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
+                       const __nv_bfloat16* __restrict__ wh, const __nv_bfloat16* __restrict__ wl, int H, int W,
+                       ConvArgs a) {
+  const long total = (long)a.N * a.Ho * a.Wo * a.Cout;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % a.Cout);
+    const long p = e / a.Cout;
+    const int ow = (int)(p % a.Wo), oh = (int)((p / a.Wo) % a.Ho), n = (int)(p / ((long)a.Wo * a.Ho));
+    float acc = 0.f;
+    for (int fy = 0; fy < a.kh; ++fy) {
+      const int iy = oh * a.stride + fy - a.pad_h;
+      if (iy < 0 || iy >= H) continue;
+      for (int fx = 0; fx < a.kw; ++fx) {
+        const int ix = ow * a.stride + fx - a.pad_w;
+        if (ix < 0 || ix >= W) continue;
+        const long xo = (((long)n * H + iy) * W + ix) * a.cin_pad;
+        const long wo = ((long)c * a.kh * a.kw + fy * a.kw + fx) * a.cin_pad;
+        for (int ci = 0; ci < a.cin_pad; ++ci) {
+          const float xhv = __bfloat162float(xh[xo + ci]), whv = __bfloat162float(wh[wo + ci]);
+          acc = fmaf(xhv, whv, acc);
+          if (xl) {
+            acc = fmaf(xhv, __bfloat162float(wl[wo + ci]), acc);
+            acc = fmaf(__bfloat162float(xl[xo + ci]), whv, acc);
+          }
+        }
+      }
+    }
+    float v = conv_epilogue_value(acc, c, a);
+    const long pix = ((long)n * a.out_H + (oh * a.oh_mul + a.oh_off)) * a.out_W + (ow * a.ow_mul + a.ow_off);
+    const long o = pix * a.out_cstride + a.out_coffset + c;
+    if (a.y_f32) a.y_f32[o] = v;
+    if (a.y_hi) {
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      a.y_hi[o] = h;
+      if (a.y_lo) a.y_lo[o] = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- weight packing
+__global__ void __launch_bounds__(256)
+    pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ whi,
+                            __nv_bfloat16* __restrict__ wlo, int Cout, int Cin, int kh, int kw, int cin_pad,
+                            const int32_t* __restrict__ chan_map, int transpose_io) {
+  const long total = (long)Cout * kh * kw * cin_pad;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int cp = (int)(e % cin_pad);
+    const int tap = (int)((e / cin_pad) % (kh * kw));
+    const int co = (int)(e / ((long)cin_pad * kh * kw));
+    const int ci = chan_map ? chan_map[cp] : (cp < Cin ? cp : -1);
+    float v = 0.f;
+    if (ci >= 0 && ci < Cin) {
+      const int fy = tap / kw, fx = tap - fy * kw;
+      if (!transpose_io)
+        v = w[(((long)co * Cin + ci) * kh + fy) * kw + fx];
+      else  // ConvTranspose2d weight [Cin][Cout][kh][kw], taps flipped
+        v = w[(((long)ci * Cout + co) * kh + (kh - 1 - fy)) * kw + (kw - 1 - fx)];
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    whi[e] = h;
+    if (wlo) wlo[e] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(SHINEON_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found (driver too old?)");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SHINEON_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed: CUresult %d", what, (int)r);
+  return SHINEON_OK;
+}
+
+// Picks the (nb, bh, bw) pixel tile with the fewest wasted accumulator rows.
+static void pick_tile(int N, int Ho, int Wo, int& nb, int& bh, int& bw) {
+  double best = -1.0;
+  nb = 1; bh = 1; bw = 1;
+  for (int w = 1; w <= Wo && w <= kBlockM; ++w) {
+    for (int h = 1; h <= Ho && h * w <= kBlockM; ++h) {
+      int n = kBlockM / (w * h);
+      if (n > N) n = N;
+      if (n < 1) n = 1;
+      long tiles = (long)cdiv(Wo, w) * cdiv(Ho, h) * cdiv(N, n);
+      double eff = (double)N * Ho * Wo / ((double)tiles * kBlockM);
+      // prefer wide tiles on ties (longer contiguous runs for TMA)
+      eff += 1e-6 * w;
+      if (eff > best) { best = eff; nb = n; bh = h; bw = w; }
+    }
+  }
+}
+
+template <int BN, bool SPLIT>
+static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUtensorMap& tBh, const CUtensorMap& tBl,
+                        ConvArgs& a, int m_tiles, int stages_req, cudaStream_t stream) {
+  constexpr int kBBytes = BN * kBlockK * 2;
+  constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
+  int stages = (200 * 1024) / kStageBytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages_req > 0 && stages_req < stages) stages = stages_req;
+  if (stages > a.num_kb) stages = a.num_kb;
+  if (stages < 1) stages = 1;
+  a.stages = stages;
+  const int smem = stages * kStageBytes + 1024;
+  static int configured_smem = 0;
+  if (smem > configured_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm): %s", cudaGetErrorString(e));
+    configured_smem = 227 * 1024;
+  }
+  dim3 grid(m_tiles, cdiv(a.Cout, BN));
+  conv_igemm_kernel<BN, SPLIT><<<grid, kThreads, smem, stream>>>(tAh, tAl, tBh, tBl, a);
+  return after_launch("conv_igemm_kernel");
+}
+
+static int fill_args(const shineon_conv2d_params* p, ConvArgs& a) {
+  SHINEON_REQUIRE(p != nullptr, "conv2d: null params");
+  SHINEON_REQUIRE(p->x_hi && p->w_hi, "conv2d: null operand");
+  SHINEON_REQUIRE((p->x_lo == nullptr) == (p->w_lo == nullptr), "conv2d: x_lo and w_lo must both be given or both NULL");
+  SHINEON_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0 && p->Cout > 0, "conv2d: bad shape");
+  SHINEON_REQUIRE(p->cin_pad > 0 && p->cin_pad % kBlockK == 0, "conv2d: cin_pad %d must be a multiple of 64", p->cin_pad);
+  SHINEON_REQUIRE(p->kh > 0 && p->kw > 0 && p->kh <= 7 && p->kw <= 7, "conv2d: kernel %dx%d unsupported", p->kh, p->kw);
+  SHINEON_REQUIRE(p->stride == 1 || p->stride == 2, "conv2d: stride %d unsupported", p->stride);
+  SHINEON_REQUIRE(p->pad_h >= 0 && p->pad_w >= 0 && p->pad_h < p->kh + p->stride && p->pad_w < p->kw + p->stride, "conv2d: pad");
+  SHINEON_REQUIRE(p->Ho > 0 && p->Wo > 0 && (p->Ho - 1) * p->stride - p->pad_h < p->H && (p->Wo - 1) * p->stride - p->pad_w < p->W,
+                  "conv2d: Ho/Wo (%d,%d) reach past the input", p->Ho, p->Wo);
+  SHINEON_REQUIRE(p->stride == 1 || (p->H % 2 == 0 && p->W % 2 == 0), "conv2d: stride 2 needs even H,W");
+  SHINEON_REQUIRE(p->y_f32 || p->y_hi, "conv2d: no output");
+  SHINEON_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), "conv2d: scale/shift");
+  SHINEON_REQUIRE((reinterpret_cast<uintptr_t>(p->x_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w_hi) & 15) == 0, "conv2d: operands must be 16-byte aligned");
+  a.N = p->N; a.Ho = p->Ho; a.Wo = p->Wo; a.Cout = p->Cout;
+  a.kh = p->kh; a.kw = p->kw; a.stride = p->stride; a.pad_h = p->pad_h; a.pad_w = p->pad_w;
+  a.cin_pad = p->cin_pad; a.cin_blocks = p->cin_pad / kBlockK;
+  a.num_kb = p->kh * p->kw * a.cin_blocks;
+  a.stages = 1;
+  a.bias = p->bias; a.scale = p->scale; a.shift = p->shift;
+  a.pre_act = p->pre_act; a.post_act = p->post_act; a.act_param = p->act_param;
+  a.y_f32 = p->y_f32; a.y_hi = (__nv_bfloat16*)p->y_hi; a.y_lo = (__nv_bfloat16*)p->y_lo;
+  a.oh_mul = p->oh_mul ? p->oh_mul : 1; a.ow_mul = p->ow_mul ? p->ow_mul : 1;
+  a.oh_off = p->oh_off; a.ow_off = p->ow_off;
+  a.out_H = p->out_H ? p->out_H : p->Ho; a.out_W = p->out_W ? p->out_W : p->Wo;
+  a.out_cstride = p->out_cstride ? p->out_cstride : p->Cout;
+  a.out_coffset = p->out_coffset;
+  SHINEON_REQUIRE(a.out_coffset >= 0 && a.out_coffset + a.Cout <= a.out_cstride, "conv2d: output channel window out of range");
+  SHINEON_REQUIRE((a.Ho - 1) * a.oh_mul + a.oh_off < a.out_H && (a.Wo - 1) * a.ow_mul + a.ow_off < a.out_W, "conv2d: output pixel window out of range");
+  pick_tile(a.N, a.Ho, a.Wo, a.nb, a.bh, a.bw);
+  a.tiles_w = cdiv(a.Wo, a.bw);
+  a.tiles_h = cdiv(a.Ho, a.bh);
+  return SHINEON_OK;
+}
+
+}  // namespace shineon
+
+using namespace shineon;
+
+extern "C" int shineon_conv2d_igemm_fwd(const shineon_conv2d_params* p, shineon_stream_t stream_) {
+  ConvArgs a;
+  int rc = fill_args(p, a);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const bool split = p->x_lo != nullptr;
+  const int m_tiles = a.tiles_w * a.tiles_h * cdiv(a.N, a.nb);
+  SHINEON_REQUIRE((long)m_tiles < (1l << 31), "conv2d: too many tiles");
+
+  int bn = p->tile_n;
+  if (bn == 0) bn = a.Cout <= 16 ? 16 : a.Cout <= 32 ? 32 : a.Cout <= 64 ? 64 : 128;
+  SHINEON_REQUIRE(bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256, "conv2d: tile_n %d", bn);
+
+  // ---- tensor maps
+  CUtensorMap tAh, tAl, tBh, tBl;
+  const cuuint64_t C = (cuuint64_t)p->cin_pad, H = (cuuint64_t)p->H, W = (cuuint64_t)p->W, N = (cuuint64_t)p->N;
+  if (p->stride == 1) {
+    cuuint64_t dims[4] = {C, W, H, N};
+    cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.nb};
+    if ((rc = encode_map(&tAh, p->x_hi, 4, dims, strides, box, "A hi"))) return rc;
+    if (split && (rc = encode_map(&tAl, p->x_lo, 4, dims, strides, box, "A lo"))) return rc;
+  } else {
+    cuuint64_t dims[5] = {2 * C, W / 2, 2, H / 2, N};
+    cuuint64_t strides[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
+    cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)a.bw, 1, (cuuint32_t)a.bh, (cuuint32_t)a.nb};
+    if ((rc = encode_map(&tAh, p->x_hi, 5, dims, strides, box, "A hi s2"))) return rc;
+    if (split && (rc = encode_map(&tAl, p->x_lo, 5, dims, strides, box, "A lo s2"))) return rc;
+  }
+  {
+    const cuuint64_t K = (cuuint64_t)p->kh * p->kw * C;
+    cuuint64_t dims[2] = {K, (cuuint64_t)p->Cout};
+    cuuint64_t strides[1] = {K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)bn};
+    if ((rc = encode_map(&tBh, p->w_hi, 2, dims, strides, box, "B hi"))) return rc;
+    if (split && (rc = encode_map(&tBl, p->w_lo, 2, dims, strides, box, "B lo"))) return rc;
+  }
+  if (!split) { tAl = tAh; tBl = tBh; }
+
+#define SHINEON_LAUNCH(BN_)                                                                            \
+  (split ? launch_igemm<BN_, true>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream)                  \
+         : launch_igemm<BN_, false>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream))
+  switch (bn) {
+    case 16: return SHINEON_LAUNCH(16);
+    case 32: return SHINEON_LAUNCH(32);
+    case 64: return SHINEON_LAUNCH(64);
+    case 128: return SHINEON_LAUNCH(128);
+    default: return SHINEON_LAUNCH(256);
+  }
+#undef SHINEON_LAUNCH
+}
+
+extern "C" int shineon_conv2d_direct_fwd(const shineon_conv2d_params* p, shineon_stream_t stream) {
+  ConvArgs a;
+  int rc = fill_args(p, a);
+  if (rc) return rc;
+  long total = (long)a.N * a.Ho * a.Wo * a.Cout;
+  long blocks = (total + 127) / 128;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  conv_direct_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)p->x_hi, (const __nv_bfloat16*)p->x_lo, (const __nv_bfloat16*)p->w_hi,
+      (const __nv_bfloat16*)p->w_lo, p->H, p->W, a);
+  return after_launch("conv_direct_kernel");
+}
+
+extern "C" int shineon_pack_conv_weight(const float* w, void* w_hi, void* w_lo, int Cout, int Cin, int kh, int kw,
+                                        int cin_pad, const int32_t* chan_map, int transpose_io,
+                                        shineon_stream_t stream) {
+  SHINEON_REQUIRE(w && w_hi, "pack_conv_weight: null pointer");
+  SHINEON_REQUIRE(Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && cin_pad >= 1, "pack_conv_weight: bad shape");
+  SHINEON_REQUIRE(chan_map != nullptr || cin_pad >= Cin, "pack_conv_weight: cin_pad < Cin");
+  long total = (long)Cout * kh * kw * cin_pad;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_conv_weight_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo,
+                                                                       Cout, Cin, kh, kw, cin_pad, chan_map, transpose_io);
+  return after_launch("pack_conv_weight_kernel");
+}

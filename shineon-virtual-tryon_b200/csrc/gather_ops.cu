@@ -1,0 +1,418 @@
+// Gather-type kernels of the try-on hot path (HBM/L2-bound, fp32):
+//   * TPS grid generation          — reference: models/networks/cpvton/warp.py:191-318
+//   * bilinear grid_sample         — reference: F.grid_sample call sites models/warp_model.py:85-86,143-145
+//   * fused TPS + grid_sample      — the grid is never written to HBM
+//   * Resample2d fwd/bwd           — reference: resample2d_kernel.cu:16-72, :76-125, :128-198
+//   * ChannelNorm fwd/bwd          — reference: channelnorm_kernel.cu:19-60, :64-96
+// All tensors here are the reference's public NCHW fp32 layout.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace shineon {
+
+constexpr int kMaxTpsN = 64;  // grid_size <= 8
+
+// ---------------------------------------------------------------------------------------------
+// TPS coefficients: W = Li[:N,:N] Q, A = Li[N:,:N] Q with Q = theta + P_base  (warp.py:207-249)
+// Computed redundantly by every CTA (56 dot products of length N) into shared memory.
+// ---------------------------------------------------------------------------------------------
+struct TpsTablesDev {
+  const float* Li;
+  const float* P_X;
+  const float* P_Y;
+  const float* grid_X;
+  const float* grid_Y;
+  int gs;
+};
+
+__device__ __forceinline__ void tps_coeffs(const float* __restrict__ theta_b, const TpsTablesDev& t,
+                                           float* sQ /*2N*/, float* sW /*2N*/, float* sA /*6*/,
+                                           float* sP /*2N*/) {
+  const int N = t.gs * t.gs;
+  const int L = N + 3;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float px = t.P_X[i], py = t.P_Y[i];
+    sP[i] = px;
+    sP[N + i] = py;
+    sQ[i] = theta_b[i] + px;          // Q_X = theta[:, :N] + P_X_base   (warp.py:207-210)
+    sQ[N + i] = theta_b[N + i] + py;  // Q_Y
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < 2 * L; r += blockDim.x) {
+    const int row = r % L;
+    const float* q = sQ + (r / L) * N;
+    const float* li = t.Li + row * L;
+    float acc = 0.f;
+    for (int k = 0; k < N; ++k) acc = fmaf(li[k], q[k], acc);
+    if (row < N)
+      sW[(r / L) * N + row] = acc;
+    else
+      sA[(r / L) * 3 + (row - N)] = acc;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void tps_point(float x, float y, int N, const float* sW, const float* sA,
+                                          const float* sP, float& xo, float& yo) {
+  float sx = 0.f, sy = 0.f;
+#pragma unroll 5
+  for (int n = 0; n < N; ++n) {
+    float dx = x - sP[n], dy = y - sP[N + n];
+    float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));  // torch.pow(.,2)+torch.pow(.,2)
+    if (d2 == 0.f) d2 = 1.f;                                     // warp.py:290
+    float U = d2 * logf(d2);
+    sx = fmaf(sW[n], U, sx);
+    sy = fmaf(sW[N + n], U, sy);
+  }
+  xo = sA[0] + sA[1] * x + sA[2] * y + sx;  // warp.py:303-316
+  yo = sA[3] + sA[4] * x + sA[5] * y + sy;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear sample of one NCHW channel plane; PyTorch grid_sampler semantics, align_corners=False
+// ---------------------------------------------------------------------------------------------
+struct BilinearTap {
+  int x0, y0;            // north-west corner
+  float wnw, wne, wsw, wse;
+  bool vx0, vx1, vy0, vy1;
+};
+
+__device__ __forceinline__ BilinearTap make_tap(float gx, float gy, int Hin, int Win, int padding_mode) {
+  float ix = ((gx + 1.f) * Win - 1.f) * 0.5f;
+  float iy = ((gy + 1.f) * Hin - 1.f) * 0.5f;
+  if (padding_mode == SHINEON_PAD_BORDER) {
+    ix = fminf(fmaxf(ix, 0.f), (float)(Win - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(Hin - 1));
+  }
+  float fx = floorf(ix), fy = floorf(iy);
+  BilinearTap t;
+  // weights exactly as ATen's grid_sampler: nw = (ix_se - ix) * (iy_se - iy) ... with ix_se = ix_nw + 1
+  float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+  float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+  t.wnw = wx0 * wy0;
+  t.wne = wx1 * wy0;
+  t.wsw = wx0 * wy1;
+  t.wse = wx1 * wy1;
+  // keep the int conversion defined for wild coordinates (all four taps are out of range there)
+  fx = fminf(fmaxf(fx, -2.f), (float)Win + 1.f);
+  fy = fminf(fmaxf(fy, -2.f), (float)Hin + 1.f);
+  t.x0 = (int)fx;
+  t.y0 = (int)fy;
+  t.vx0 = t.x0 >= 0 && t.x0 < Win;
+  t.vx1 = t.x0 + 1 >= 0 && t.x0 + 1 < Win;
+  t.vy0 = t.y0 >= 0 && t.y0 < Hin;
+  t.vy1 = t.y0 + 1 >= 0 && t.y0 + 1 < Hin;
+  return t;
+}
+
+__device__ __forceinline__ float sample_plane(const float* __restrict__ plane, int Win, const BilinearTap& t) {
+  float acc = 0.f;
+  const float* r0 = plane + (long)t.y0 * Win + t.x0;
+  const float* r1 = r0 + Win;
+  if (t.vy0 && t.vx0) acc += __ldg(r0) * t.wnw;
+  if (t.vy0 && t.vx1) acc += __ldg(r0 + 1) * t.wne;
+  if (t.vy1 && t.vx0) acc += __ldg(r1) * t.wsw;
+  if (t.vy1 && t.vx1) acc += __ldg(r1 + 1) * t.wse;
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) tps_grid_kernel(const float* __restrict__ theta, TpsTablesDev t,
+                                                       float* __restrict__ grid, int H, int W) {
+  __shared__ float sQ[2 * kMaxTpsN], sW[2 * kMaxTpsN], sP[2 * kMaxTpsN], sA[6];
+  const int b = blockIdx.y;
+  const int N = t.gs * t.gs;
+  tps_coeffs(theta + (long)b * 2 * N, t, sQ, sW, sA, sP);
+  const int HW = H * W;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    int y = p / W, x = p - y * W;
+    float xo, yo;
+    tps_point(t.grid_X[x], t.grid_Y[y], N, sW, sA, sP, xo, yo);
+    reinterpret_cast<float2*>(grid)[(long)b * HW + p] = make_float2(xo, yo);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    grid_sample_kernel(const float* __restrict__ in, const float* __restrict__ grid, float* __restrict__ out,
+                       int C, int Hin, int Win, int Hout, int Wout, int padding_mode) {
+  const int b = blockIdx.y;
+  const int HWo = Hout * Wout;
+  const long HWi = (long)Hin * Win;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HWo; p += gridDim.x * blockDim.x) {
+    float2 g = reinterpret_cast<const float2*>(grid)[(long)b * HWo + p];
+    BilinearTap t = make_tap(g.x, g.y, Hin, Win, padding_mode);
+    for (int c = 0; c < C; ++c)
+      out[((long)b * C + c) * HWo + p] = sample_plane(in + ((long)b * C + c) * HWi, Win, t);
+  }
+}
+
+struct FusedSampleArgs {
+  const float* in[3];
+  float* out[3];
+  int C[3];
+  int pad[3];
+};
+
+__global__ void __launch_bounds__(256)
+    tps_grid_sample_kernel(const float* __restrict__ theta, TpsTablesDev t, FusedSampleArgs a,
+                           float* __restrict__ grid_out, int H, int W) {
+  __shared__ float sQ[2 * kMaxTpsN], sW[2 * kMaxTpsN], sP[2 * kMaxTpsN], sA[6];
+  const int b = blockIdx.y;
+  const int N = t.gs * t.gs;
+  tps_coeffs(theta + (long)b * 2 * N, t, sQ, sW, sA, sP);
+  const int HW = H * W;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    int y = p / W, x = p - y * W;
+    float gx, gy;
+    tps_point(t.grid_X[x], t.grid_Y[y], N, sW, sA, sP, gx, gy);
+    if (grid_out) reinterpret_cast<float2*>(grid_out)[(long)b * HW + p] = make_float2(gx, gy);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (a.in[i] == nullptr) continue;
+      BilinearTap tap = make_tap(gx, gy, H, W, a.pad[i]);
+      for (int c = 0; c < a.C[i]; ++c)
+        a.out[i][((long)b * a.C[i] + c) * HW + p] = sample_plane(a.in[i] + ((long)b * a.C[i] + c) * HW, W, tap);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resample2d  (resample2d_kernel.cu).  kernel_size == 1 (the only value the reference uses).
+// One thread per output pixel; the flow is read once and reused for every channel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    resample2d_fwd_kernel(const float* __restrict__ in1, const float* __restrict__ flow,
+                          float* __restrict__ out, int C, int H, int W, int bilinear) {
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    int y = p / W, x = p - y * W;
+    float dx = flow[((long)b * 2 + 0) * HW + p];
+    float dy = flow[((long)b * 2 + 1) * HW + p];
+    float xf = (float)x + dx, yf = (float)y + dy;
+    if (bilinear) {
+      float fx = floorf(xf), fy = floorf(yf);
+      float alpha = xf - fx, beta = yf - fy;  // resample2d_kernel.cu:42-43
+      // int(floor(xf)) with a defined result for huge flows
+      float cfx = fminf(fmaxf(fx, -4.f), (float)W + 4.f), cfy = fminf(fmaxf(fy, -4.f), (float)H + 4.f);
+      int xL = max(min((int)cfx, W - 1), 0), xR = max(min((int)cfx + 1, W - 1), 0);
+      int yT = max(min((int)cfy, H - 1), 0), yB = max(min((int)cfy + 1, H - 1), 0);
+      float w00 = (1.f - alpha) * (1.f - beta), w01 = alpha * (1.f - beta);
+      float w10 = (1.f - alpha) * beta, w11 = alpha * beta;
+      for (int c = 0; c < C; ++c) {
+        const float* pl = in1 + ((long)b * C + c) * HW;
+        float v = 0.f;  // same accumulation order as resample2d_kernel.cu:56-59
+        v += w00 * __ldg(pl + yT * W + xL);
+        v += w01 * __ldg(pl + yT * W + xR);
+        v += w10 * __ldg(pl + yB * W + xL);
+        v += w11 * __ldg(pl + yB * W + xR);
+        out[((long)b * C + c) * HW + p] = v;
+      }
+    } else {
+      float nx = fminf(fmaxf(floorf(xf + 0.5f), -4.f), (float)W + 4.f);
+      float ny = fminf(fmaxf(floorf(yf + 0.5f), -4.f), (float)H + 4.f);
+      int xN = max(min((int)nx, W - 1), 0), yN = max(min((int)ny, H - 1), 0);
+      for (int c = 0; c < C; ++c)
+        out[((long)b * C + c) * HW + p] = __ldg(in1 + ((long)b * C + c) * HW + yN * W + xN);
+    }
+  }
+}
+
+// d/d in1: atomic scatter (resample2d_kernel.cu:76-125).  NB the reference takes alpha/beta from
+// `xf - int(xf)` (truncation, :105-106) here, unlike the forward's floor; reproduced on purpose.
+__global__ void __launch_bounds__(256)
+    resample2d_bwd_in1_kernel(const float* __restrict__ flow, const float* __restrict__ gout,
+                              float* __restrict__ gin1, int C, int H, int W) {
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    int y = p / W, x = p - y * W;
+    float dx = flow[((long)b * 2 + 0) * HW + p];
+    float dy = flow[((long)b * 2 + 1) * HW + p];
+    float xf = (float)x + dx, yf = (float)y + dy;
+    float cxf = fminf(fmaxf(xf, -1e9f), 1e9f), cyf = fminf(fmaxf(yf, -1e9f), 1e9f);
+    float alpha = xf - (float)(int)cxf, beta = yf - (float)(int)cyf;
+    float cfx = fminf(fmaxf(floorf(xf), -4.f), (float)W + 4.f), cfy = fminf(fmaxf(floorf(yf), -4.f), (float)H + 4.f);
+    int xL = max(min((int)cfx, W - 1), 0), xR = max(min((int)cfx + 1, W - 1), 0);
+    int yT = max(min((int)cfy, H - 1), 0), yB = max(min((int)cfy + 1, H - 1), 0);
+    for (int c = 0; c < C; ++c) {
+      float g = gout[((long)b * C + c) * HW + p];
+      float* pl = gin1 + ((long)b * C + c) * HW;
+      atomicAdd(pl + yT * W + xL, (1.f - alpha) * (1.f - beta) * g);
+      atomicAdd(pl + yT * W + xR, alpha * (1.f - beta) * g);
+      atomicAdd(pl + yB * W + xL, (1.f - alpha) * beta * g);
+      atomicAdd(pl + yB * W + xR, alpha * beta * g);
+    }
+  }
+}
+
+// d/d flow (resample2d_kernel.cu:128-198): channel 0 (even) = d/dx, channel 1 (odd) = d/dy.
+__global__ void __launch_bounds__(256)
+    resample2d_bwd_flow_kernel(const float* __restrict__ in1, const float* __restrict__ flow,
+                               const float* __restrict__ gout, float* __restrict__ gflow, int C, int H, int W) {
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    int y = p / W, x = p - y * W;
+    float dx = flow[((long)b * 2 + 0) * HW + p];
+    float dy = flow[((long)b * 2 + 1) * HW + p];
+    float xf = (float)x + dx, yf = (float)y + dy;
+    float fx = floorf(xf), fy = floorf(yf);
+    float cfx = fminf(fmaxf(fx, -4.f), (float)W + 4.f), cfy = fminf(fmaxf(fy, -4.f), (float)H + 4.f);
+    int xL = max(min((int)cfx, W - 1), 0), xR = max(min((int)cfx + 1, W - 1), 0);
+    int yT = max(min((int)cfy, H - 1), 0), yB = max(min((int)cfy + 1, H - 1), 0);
+    float gx_gamma = 1.f - (yf - fy);  // even channel (:181-192): weights along y, difference along x
+    float gy_gamma = 1.f - (xf - fx);  // odd channel  (:168-179): weights along x, difference along y
+    float ox = 0.f, oy = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float* pl = in1 + ((long)b * C + c) * HW;
+      float g = gout[((long)b * C + c) * HW + p];
+      float vTL = __ldg(pl + yT * W + xL), vTR = __ldg(pl + yT * W + xR);
+      float vBL = __ldg(pl + yB * W + xL), vBR = __ldg(pl + yB * W + xR);
+      ox += gx_gamma * g * vTR;
+      ox -= gx_gamma * g * vTL;
+      ox += (1.f - gx_gamma) * g * vBR;
+      ox -= (1.f - gx_gamma) * g * vBL;
+      oy += gy_gamma * g * vBL;
+      oy -= gy_gamma * g * vTL;
+      oy += (1.f - gy_gamma) * g * vBR;
+      oy -= (1.f - gy_gamma) * g * vTR;
+    }
+    gflow[((long)b * 2 + 0) * HW + p] = ox;
+    gflow[((long)b * 2 + 1) * HW + p] = oy;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ChannelNorm (channelnorm_kernel.cu): out = sqrt(sum_c x^2); norm_deg is ignored by the reference.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    channelnorm_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int C, long HW, long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long b = i / HW, p = i - b * HW;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float v = in[(b * C + c) * HW + p];
+      acc += v * v;
+    }
+    out[i] = sqrtf(acc);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    channelnorm_bwd_kernel(const float* __restrict__ in, const float* __restrict__ out,
+                           const float* __restrict__ gout, float* __restrict__ gin, int C, long HW, long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long b = i / (C * HW), p = i % HW;
+    long o = b * HW + p;
+    // channelnorm_kernel.cu:93: float*float / (float + 1e-9 (double))
+    double den = (double)out[o] + 1e-9;
+    gin[i] = (float)((double)(gout[o] * in[i]) / den);
+  }
+}
+
+static inline TpsTablesDev to_dev(const shineon_tps_tables* t) {
+  TpsTablesDev d{t->Li, t->P_X, t->P_Y, t->grid_X, t->grid_Y, t->grid_size};
+  return d;
+}
+
+static inline dim3 pixel_grid(int HW, int B) {
+  int bx = cdiv(HW, 256);
+  if (bx > 4096) bx = 4096;
+  return dim3(bx, B);
+}
+
+}  // namespace shineon
+
+using namespace shineon;
+
+extern "C" int shineon_tps_grid_fwd(const float* theta, const shineon_tps_tables* tps, float* grid, int B, int H,
+                                    int W, shineon_stream_t stream) {
+  SHINEON_REQUIRE(theta && tps && grid, "tps_grid: null pointer");
+  SHINEON_REQUIRE(tps->Li && tps->P_X && tps->P_Y && tps->grid_X && tps->grid_Y, "tps_grid: null table");
+  SHINEON_REQUIRE(tps->grid_size >= 2 && tps->grid_size * tps->grid_size <= kMaxTpsN, "tps_grid: grid_size %d unsupported", tps->grid_size);
+  SHINEON_REQUIRE(B >= 0 && H > 0 && W > 0 && B <= 65535, "tps_grid: bad shape");
+  if (B == 0) return SHINEON_OK;
+  tps_grid_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), grid, H, W);
+  return after_launch("tps_grid_kernel");
+}
+
+extern "C" int shineon_grid_sample_fwd(const float* input, const float* grid, float* out, int B, int C, int Hin,
+                                       int Win, int Hout, int Wout, int padding_mode, shineon_stream_t stream) {
+  SHINEON_REQUIRE(input && grid && out, "grid_sample: null pointer");
+  SHINEON_REQUIRE(padding_mode == SHINEON_PAD_ZEROS || padding_mode == SHINEON_PAD_BORDER, "grid_sample: padding_mode %d", padding_mode);
+  SHINEON_REQUIRE(B >= 0 && C > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && B <= 65535, "grid_sample: bad shape");
+  if (B == 0) return SHINEON_OK;
+  grid_sample_kernel<<<pixel_grid(Hout * Wout, B), 256, 0, (cudaStream_t)stream>>>(input, grid, out, C, Hin, Win,
+                                                                                  Hout, Wout, padding_mode);
+  return after_launch("grid_sample_kernel");
+}
+
+extern "C" int shineon_tps_grid_sample_fwd(const float* theta, const shineon_tps_tables* tps, int B, int H, int W,
+                                           const float* in0, int C0, int pad0, float* out0, const float* in1,
+                                           int C1, int pad1, float* out1, const float* in2, int C2, int pad2,
+                                           float* out2, float* grid_out, shineon_stream_t stream) {
+  SHINEON_REQUIRE(theta && tps, "tps_grid_sample: null pointer");
+  SHINEON_REQUIRE(tps->Li && tps->P_X && tps->P_Y && tps->grid_X && tps->grid_Y, "tps_grid_sample: null table");
+  SHINEON_REQUIRE(tps->grid_size >= 2 && tps->grid_size * tps->grid_size <= kMaxTpsN, "tps_grid_sample: grid_size %d unsupported", tps->grid_size);
+  SHINEON_REQUIRE(B >= 0 && H > 0 && W > 0 && B <= 65535, "tps_grid_sample: bad shape");
+  SHINEON_REQUIRE((in0 == nullptr) == (out0 == nullptr) && (in1 == nullptr) == (out1 == nullptr) && (in2 == nullptr) == (out2 == nullptr), "tps_grid_sample: in/out mismatch");
+  if (B == 0) return SHINEON_OK;
+  FusedSampleArgs a;
+  a.in[0] = in0; a.out[0] = out0; a.C[0] = C0; a.pad[0] = pad0;
+  a.in[1] = in1; a.out[1] = out1; a.C[1] = C1; a.pad[1] = pad1;
+  a.in[2] = in2; a.out[2] = out2; a.C[2] = C2; a.pad[2] = pad2;
+  tps_grid_sample_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid_out, H, W);
+  return after_launch("tps_grid_sample_kernel");
+}
+
+extern "C" int shineon_resample2d_fwd(const float* in1, const float* flow, float* out, int B, int C, int Hi, int Wi,
+                                      int H, int W, int kernel_size, int bilinear, shineon_stream_t stream) {
+  SHINEON_REQUIRE(in1 && flow && out, "resample2d_fwd: null pointer");
+  SHINEON_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && B <= 65535, "resample2d_fwd: bad shape");
+  if (kernel_size != 1) return fail(SHINEON_ERR_UNSUPPORTED, "resample2d: kernel_size %d (only 1, as the reference uses)", kernel_size);
+  if (Hi != H || Wi != W) return fail(SHINEON_ERR_UNSUPPORTED, "resample2d: input %dx%d != flow %dx%d", Hi, Wi, H, W);
+  if (B == 0) return SHINEON_OK;
+  resample2d_fwd_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(in1, flow, out, C, H, W, bilinear);
+  return after_launch("resample2d_fwd_kernel");
+}
+
+extern "C" int shineon_resample2d_bwd(const float* in1, const float* flow, const float* grad_out, float* grad_in1,
+                                      float* grad_flow, int B, int C, int Hi, int Wi, int H, int W, int kernel_size,
+                                      int bilinear, shineon_stream_t stream) {
+  SHINEON_REQUIRE(in1 && flow && grad_out && grad_in1 && grad_flow, "resample2d_bwd: null pointer");
+  SHINEON_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && B <= 65535, "resample2d_bwd: bad shape");
+  if (kernel_size != 1) return fail(SHINEON_ERR_UNSUPPORTED, "resample2d: kernel_size %d", kernel_size);
+  if (Hi != H || Wi != W) return fail(SHINEON_ERR_UNSUPPORTED, "resample2d: input %dx%d != flow %dx%d", Hi, Wi, H, W);
+  (void)bilinear;  // the reference's backward ignores the flag too (resample2d_kernel.cu:76-198)
+  if (B == 0) return SHINEON_OK;
+  resample2d_bwd_in1_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(flow, grad_out, grad_in1, C, H, W);
+  int rc = after_launch("resample2d_bwd_in1_kernel");
+  if (rc) return rc;
+  resample2d_bwd_flow_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(in1, flow, grad_out, grad_flow, C, H, W);
+  return after_launch("resample2d_bwd_flow_kernel");
+}
+
+extern "C" int shineon_channelnorm_fwd(const float* in, float* out, int B, int C, int H, int W, int norm_deg,
+                                       shineon_stream_t stream) {
+  SHINEON_REQUIRE(in && out, "channelnorm_fwd: null pointer");
+  SHINEON_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, "channelnorm_fwd: bad shape");
+  (void)norm_deg;
+  long total = (long)B * H * W;
+  if (total == 0) return SHINEON_OK;
+  int blocks = (int)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256);
+  channelnorm_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, C, (long)H * W, total);
+  return after_launch("channelnorm_fwd_kernel");
+}
+
+extern "C" int shineon_channelnorm_bwd(const float* in, const float* out, const float* grad_out, float* grad_in,
+                                       int B, int C, int H, int W, int norm_deg, shineon_stream_t stream) {
+  SHINEON_REQUIRE(in && out && grad_out && grad_in, "channelnorm_bwd: null pointer");
+  SHINEON_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, "channelnorm_bwd: bad shape");
+  (void)norm_deg;
+  long total = (long)B * C * H * W;
+  if (total == 0) return SHINEON_OK;
+  int blocks = (int)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256);
+  channelnorm_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, grad_out, grad_in, C, (long)H * W, total);
+  return after_launch("channelnorm_bwd_kernel");
+}

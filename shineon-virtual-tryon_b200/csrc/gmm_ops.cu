@@ -1,0 +1,127 @@
+// GMM glue between the conv stacks (reference: models/networks/cpvton/warp.py):
+//   * FeatureL2Norm x2 + FeatureCorrelation (warp.py:39-67) fused: an fp32 tiled GEMM per image
+//     out[b, pB, iA] = <A[pA], B[pB]> / (|A[pA]| |B[pB]|),  iA = wA*h + hA  (column-major A index, warp.py:60)
+//   * FeatureRegression tail: flatten (NCHW order) -> Linear -> tanh (warp.py:94-99)
+#include "common.cuh"
+
+namespace shineon {
+
+constexpr int kTA = 64;  // pA (output channel) tile
+constexpr int kTB = 32;  // pB (output pixel) tile
+constexpr int kTK = 32;
+
+__global__ void __launch_bounds__(256)
+    l2norm_corr_kernel(const float* __restrict__ fA, const float* __restrict__ fB, float* __restrict__ corr,
+                       __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int h, int w, int C, int cpad) {
+  __shared__ float sA[kTK][kTA + 4];
+  __shared__ float sB[kTK][kTB + 4];
+  const int P = h * w;
+  const int b = blockIdx.z;
+  const int a0 = blockIdx.x * kTA, b0 = blockIdx.y * kTB;
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;  // 4 pA x 2 pB per thread
+  const float* A = fA + (long)b * P * C;
+  const float* B = fB + (long)b * P * C;
+  float acc[2][4] = {};
+  float na[4] = {}, nb[2] = {};
+  for (int k0 = 0; k0 < C; k0 += kTK) {
+    // A tile: 64 rows x 32 k  (8 threads x float4 per row)
+    for (int idx = tid; idx < kTA * (kTK / 4); idx += 256) {
+      const int row = idx / (kTK / 4), kq = idx % (kTK / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a0 + row < P && k0 + kq * 4 < C) v = *reinterpret_cast<const float4*>(A + (long)(a0 + row) * C + k0 + kq * 4);
+      sA[kq * 4 + 0][row] = v.x; sA[kq * 4 + 1][row] = v.y; sA[kq * 4 + 2][row] = v.z; sA[kq * 4 + 3][row] = v.w;
+    }
+    for (int idx = tid; idx < kTB * (kTK / 4); idx += 256) {
+      const int row = idx / (kTK / 4), kq = idx % (kTK / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b0 + row < P && k0 + kq * 4 < C) v = *reinterpret_cast<const float4*>(B + (long)(b0 + row) * C + k0 + kq * 4);
+      sB[kq * 4 + 0][row] = v.x; sB[kq * 4 + 1][row] = v.y; sB[kq * 4 + 2][row] = v.z; sB[kq * 4 + 3][row] = v.w;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < kTK; ++k) {
+      float av[4], bv[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = sA[k][tx * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bv[j] = sB[k][ty * 2 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) na[i] = fmaf(av[i], av[i], na[i]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        nb[j] = fmaf(bv[j], bv[j], nb[j]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(av[i], bv[j], acc[j][i]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int pB = b0 + ty * 2 + j;
+    if (pB >= P) continue;
+    const float inb = 1.f / sqrtf(nb[j] + 1e-6f);  // warp.py:44-49
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pA = a0 + tx * 4 + i;
+      if (pA >= P) continue;
+      const float ina = 1.f / sqrtf(na[i] + 1e-6f);
+      const float v = acc[j][i] * ina * inb;
+      const int hA = pA / w, wA = pA - hA * w;
+      const int iA = wA * h + hA;  // feature_A.transpose(2,3) (warp.py:60)
+      if (corr) corr[((long)b * P + pB) * P + iA] = v;
+      if (yh) {
+        __nv_bfloat16 hh, ll;
+        split_bf16(v, hh, ll);
+        const long o = ((long)b * P + pB) * cpad + iA;
+        yh[o] = hh;
+        if (yl) yl[o] = ll;
+      }
+    }
+  }
+}
+
+// theta[b, o] = tanh(bias[o] + sum_{c,y,x} W[o, c*h*w + y*w + x] * x_nhwc[b, y, x, c]); one warp per output.
+__global__ void __launch_bounds__(256)
+    linear_tanh_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
+                       float* __restrict__ theta, int hw, int C, int out_dim) {
+  const int b = blockIdx.x;
+  const int K = hw * C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float* xb = x + (long)b * K;
+  for (int o = warp; o < out_dim; o += nw) {
+    const float* wr = wgt + (long)o * K;
+    float acc = 0.f;
+    for (int e = lane; e < K; e += 32) {  // e indexes the NHWC activation (coalesced); map to the NCHW weight column
+      const int c = e % C, p = e / C;
+      acc = fmaf(xb[e], __ldg(wr + (long)c * hw + p), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) theta[(long)b * out_dim + o] = tanhf(acc + (bias ? bias[o] : 0.f));
+  }
+}
+
+}  // namespace shineon
+
+using namespace shineon;
+
+extern "C" int shineon_l2norm_correlation(const float* featA, const float* featB, float* corr_f32, void* y_hi,
+                                          void* y_lo, int B, int h, int w, int C, int cpad, shineon_stream_t stream) {
+  SHINEON_REQUIRE(featA && featB && (corr_f32 || y_hi), "l2norm_correlation: null pointer");
+  SHINEON_REQUIRE(B > 0 && B <= 65535 && h > 0 && w > 0 && C > 0 && C % 4 == 0, "l2norm_correlation: bad shape (C %% 4)");
+  SHINEON_REQUIRE(!y_hi || cpad >= h * w, "l2norm_correlation: cpad < h*w");
+  const int P = h * w;
+  dim3 grid(cdiv(P, kTA), cdiv(P, kTB), B);
+  l2norm_corr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(featA, featB, corr_f32, (__nv_bfloat16*)y_hi,
+                                                           (__nv_bfloat16*)y_lo, h, w, C, cpad);
+  return after_launch("l2norm_corr_kernel");
+}
+
+extern "C" int shineon_linear_tanh(const float* x, const float* weight, const float* bias, float* theta, int B, int h,
+                                   int w, int C, int out_dim, shineon_stream_t stream) {
+  SHINEON_REQUIRE(x && weight && theta, "linear_tanh: null pointer");
+  SHINEON_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && out_dim > 0, "linear_tanh: bad shape");
+  linear_tanh_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, weight, bias, theta, h * w, C, out_dim);
+  return after_launch("linear_tanh_kernel");
+}

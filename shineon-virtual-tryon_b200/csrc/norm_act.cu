@@ -1,0 +1,323 @@
+// Memory-bound passes of the U-Net / TOM path, all NHWC:
+//   * nchw_to_planes   : reference-layout input -> activated bf16 hi/lo planes (unet.py:132 on the block input)
+//   * instnorm_act     : nn.InstanceNorm2d(affine=False) (unet.py:133,135) + following activation
+//   * upsample2x_cat   : up_act -> torch.cat([x, x'],1) -> nn.Upsample(2,"bilinear") (unet.py:138,155,166,198)
+//   * tom_compose      : tanh / sigmoid / mask compose of UnetMaskModel.forward (unet_mask_model.py:74-135)
+#include "common.cuh"
+
+namespace shineon {
+
+// ------------------------------------------------------------------------------ nchw -> planes
+__global__ void __launch_bounds__(256)
+    nchw_to_planes_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+                          __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int HW, int cpad,
+                          int act, float act_param) {
+  const int n = blockIdx.y;
+  const int groups = (C0 + C1 + 7) / 8;
+  const long total = (long)HW * groups;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int p = (int)(e % HW);  // pixel fastest: coalesced channel-plane reads
+    const int g = (int)(e / HW);
+    __align__(16) __nv_bfloat16 hi[8];
+    __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      float v = 0.f;
+      if (c < C0)
+        v = x0[((long)n * C0 + c) * HW + p];
+      else if (c < C0 + C1)
+        v = x1[((long)n * C1 + (c - C0)) * HW + p];
+      v = (c < C0 + C1) ? apply_act(v, act, act_param) : 0.f;
+      split_bf16(v, hi[j], lo[j]);
+    }
+    const long o = ((long)n * HW + p) * cpad + g * 8;
+    *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
+    if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+// ------------------------------------------------------------------------------ instance norm
+// Pass 1: per-(n,c) sum and sum of squares.  fp32 partials per CTA, fp64 atomics across CTAs
+// (E[x^2]-E[x]^2 is then evaluated in fp64, so cancellation is not an issue).
+template <int CB>  // channels per CTA (power of two <= 32)
+__global__ void __launch_bounds__(256)
+    instnorm_stats_kernel(const float* __restrict__ x, double* __restrict__ ws, int HW, int C, int pix_per_cta) {
+  constexpr int PP = 256 / CB;
+  __shared__ float s_sum[256], s_sq[256];
+  const int n = blockIdx.z;
+  const int c = blockIdx.y * CB + (threadIdx.x % CB);
+  const int pl = threadIdx.x / CB;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(p0 + pix_per_cta, HW);
+  float s = 0.f, q = 0.f;
+  if (c < C) {
+    const float* base = x + (long)n * HW * C + c;
+#pragma unroll 4
+    for (int p = p0 + pl; p < p1; p += PP) {
+      float v = __ldg(base + (long)p * C);
+      s += v;
+      q = fmaf(v, v, q);
+    }
+  }
+  s_sum[threadIdx.x] = s;
+  s_sq[threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.x < CB && c < C) {
+    float ts = 0.f, tq = 0.f;
+    for (int i = 0; i < PP; ++i) {
+      ts += s_sum[i * CB + threadIdx.x];
+      tq += s_sq[i * CB + threadIdx.x];
+    }
+    atomicAdd(ws + ((long)n * C + c) * 2 + 0, (double)ts);
+    atomicAdd(ws + ((long)n * C + c) * 2 + 1, (double)tq);
+  }
+}
+
+// Pass 2: y = act((x - mean) * rsqrt(var + eps)); 4 channels per thread when C % 4 == 0.
+__global__ void __launch_bounds__(256)
+    instnorm_apply_kernel(const float* __restrict__ x, const double* __restrict__ ws, float* __restrict__ yf,
+                          __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int HW, int C, int cpad,
+                          float eps, int do_norm, int act, float act_param) {
+  extern __shared__ float s_tab[];  // mean[C], rstd[C]
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean = 0.f, rstd = 1.f;
+    if (do_norm) {
+      double s = ws[((long)n * C + c) * 2], q = ws[((long)n * C + c) * 2 + 1];
+      double m = s / HW;
+      double var = q / HW - m * m;  // biased variance (F.instance_norm)
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    s_tab[c] = mean;
+    s_tab[C + c] = rstd;
+  }
+  __syncthreads();
+  const int vecC = (C % 4 == 0) ? 4 : 1;
+  const int cg = C / vecC;
+  const long total = (long)HW * cg;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(e % cg);
+    const long p = e / cg;
+    const long xi = ((long)n * HW + p) * C + g * vecC;
+    float v[4];
+    if (vecC == 4) {
+      float4 t = *reinterpret_cast<const float4*>(x + xi);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+      v[0] = x[xi];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < vecC) {
+        const int c = g * vecC + j;
+        v[j] = apply_act((v[j] - s_tab[c]) * s_tab[C + c], act, act_param);
+      }
+    if (yf) {
+      if (vecC == 4)
+        *reinterpret_cast<float4*>(yf + xi) = make_float4(v[0], v[1], v[2], v[3]);
+      else
+        yf[xi] = v[0];
+    }
+    if (yh) {
+      const long po = ((long)n * HW + p) * cpad + g * vecC;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < vecC) {
+          __nv_bfloat16 h, l;
+          split_bf16(v[j], h, l);
+          yh[po + j] = h;
+          if (yl) yl[po + j] = l;
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ upsample x2 + concat
+// PyTorch upsample_bilinear2d, align_corners=False, scale 2: src = max(0.5*(dst+0.5)-0.5, 0).
+__device__ __forceinline__ void up2_index(int d, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float src = 0.5f * ((float)d + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ l, long off,
+                                      int act, float act_param, float (&v)[8]) {
+  uint4 uh = *reinterpret_cast<const uint4*>(h + off);
+  const __nv_bfloat16* ph = reinterpret_cast<const __nv_bfloat16*>(&uh);
+  if (l) {
+    uint4 ul = *reinterpret_cast<const uint4*>(l + off);
+    const __nv_bfloat16* pl = reinterpret_cast<const __nv_bfloat16*>(&ul);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(join_bf16(ph[j], pl[j]), act, act_param);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(__bfloat162float(ph[j]), act, act_param);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    upsample2x_cat_kernel(const __nv_bfloat16* __restrict__ s0h, const __nv_bfloat16* __restrict__ s0l, int c0pad,
+                          const __nv_bfloat16* __restrict__ s1h, const __nv_bfloat16* __restrict__ s1l, int c1pad,
+                          __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int H, int W, int act,
+                          float act_param) {
+  const int n = blockIdx.y;
+  const int ctot = c0pad + c1pad;
+  const int groups = ctot / 8;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long total = (long)Ho * Wo * groups;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(e % groups);
+    const long p = e / groups;
+    const int ox = (int)(p % Wo), oy = (int)(p / Wo);
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    up2_index(oy, H, y0, y1, ly0, ly1);
+    up2_index(ox, W, x0, x1, lx0, lx1);
+    const int c = g * 8;
+    const __nv_bfloat16 *sh, *sl;
+    int cp, cc;
+    if (c < c0pad) { sh = s0h; sl = s0l; cp = c0pad; cc = c; } else { sh = s1h; sl = s1l; cp = c1pad; cc = c - c0pad; }
+    const long rb = (long)n * H * W;
+    float v00[8], v01[8], v10[8], v11[8];
+    load8(sh, sl, (rb + (long)y0 * W + x0) * cp + cc, act, act_param, v00);
+    load8(sh, sl, (rb + (long)y0 * W + x1) * cp + cc, act, act_param, v01);
+    load8(sh, sl, (rb + (long)y1 * W + x0) * cp + cc, act, act_param, v10);
+    load8(sh, sl, (rb + (long)y1 * W + x1) * cp + cc, act, act_param, v11);
+    __align__(16) __nv_bfloat16 hi[8];
+    __align__(16) __nv_bfloat16 lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // ATen: h0lambda*(w0lambda*p00 + w1lambda*p01) + h1lambda*(w0lambda*p10 + w1lambda*p11)
+      float v = ly0 * (lx0 * v00[j] + lx1 * v01[j]) + ly1 * (lx0 * v10[j] + lx1 * v11[j]);
+      split_bf16(v, hi[j], lo[j]);
+    }
+    const long o = ((long)n * Ho * Wo + p) * ctot + c;
+    *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
+    if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+// ------------------------------------------------------------------------------ TOM compose
+__global__ void __launch_bounds__(256)
+    tom_compose_kernel(const float* __restrict__ u, int Cout, const float* __restrict__ cloth,
+                       const float* __restrict__ warped_prev, float* __restrict__ p_rend, float* __restrict__ masks,
+                       float* __restrict__ p_tryon, float* __restrict__ fmasks, int HW, int nf, int f, int flow_warp) {
+  const int b = blockIdx.y;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+    const float* up = u + ((long)b * HW + p) * Cout;
+    const float m = 1.f / (1.f + expf(-up[3 * nf + f]));  // F.sigmoid (unet_mask_model.py:85)
+    float fm = 0.f;
+    if (flow_warp) fm = 1.f / (1.f + expf(-up[4 * nf + f]));
+    masks[((long)b * nf + f) * HW + p] = m;
+    if (flow_warp && fmasks) fmasks[((long)b * nf + f) * HW + p] = fm;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float r = tanhf(up[3 * f + k]);  // F.tanh (unet_mask_model.py:84)
+      const long o = ((long)b * 3 * nf + 3 * f + k) * HW + p;
+      p_rend[o] = r;
+      float rr = r;
+      if (warped_prev) {  // unet_mask_model.py:118-121
+        const float w = warped_prev[((long)b * 3 + k) * HW + p];
+        rr = (1.f - fm) * w + fm * r;
+      }
+      const float c = cloth[o];
+      p_tryon[o] = (1.f - m) * rr + m * c;  // unet_mask_model.py:126-129
+    }
+  }
+}
+
+static inline int grid_x(long total, int threads) {
+  long b = (total + threads - 1) / threads;
+  return (int)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
+}
+
+}  // namespace shineon
+
+using namespace shineon;
+
+extern "C" int shineon_nchw_to_planes(const float* x0, int C0, const float* x1, int C1, void* y_hi, void* y_lo,
+                                      int N, int H, int W, int cpad, int act, float act_param,
+                                      shineon_stream_t stream) {
+  SHINEON_REQUIRE(x0 && y_hi && C0 > 0, "nchw_to_planes: null pointer");
+  SHINEON_REQUIRE((x1 == nullptr) == (C1 == 0), "nchw_to_planes: x1/C1 mismatch");
+  SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "nchw_to_planes: bad shape");
+  SHINEON_REQUIRE(cpad % 8 == 0 && cpad >= C0 + C1, "nchw_to_planes: cpad %d too small / not a multiple of 8", cpad);
+  const int HW = H * W;
+  dim3 grid(grid_x((long)HW * ((C0 + C1 + 7) / 8), 256), N);
+  nchw_to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo,
+                                                               HW, cpad, act, act_param);
+  return after_launch("nchw_to_planes_kernel");
+}
+
+extern "C" int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, void* y_lo, double* stats_ws, int N,
+                                    int H, int W, int C, int cpad, float eps, int do_norm, int act, float act_param,
+                                    shineon_stream_t stream_) {
+  SHINEON_REQUIRE(x && (y_f32 || y_hi), "instnorm_act: null pointer");
+  SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && C > 0, "instnorm_act: bad shape");
+  SHINEON_REQUIRE(!do_norm || stats_ws, "instnorm_act: stats_ws required");
+  SHINEON_REQUIRE(!y_hi || cpad >= C, "instnorm_act: cpad < C");
+  SHINEON_REQUIRE(2 * C * sizeof(float) <= 48 * 1024, "instnorm_act: C too large");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int HW = H * W;
+  if (do_norm) {
+    cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * (size_t)N * C, stream);
+    if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "instnorm_act memset: %s", cudaGetErrorString(e));
+    int cb = 32;
+    while (cb > 1 && cb / 2 >= C) cb /= 2;
+    const int pp = 256 / cb;
+    int pix_per_cta = pp * 16;
+    dim3 grid(cdiv(HW, pix_per_cta), cdiv(C, cb), N);
+    switch (cb) {
+      case 32: instnorm_stats_kernel<32><<<grid, 256, 0, stream>>>(x, stats_ws, HW, C, pix_per_cta); break;
+      case 16: instnorm_stats_kernel<16><<<grid, 256, 0, stream>>>(x, stats_ws, HW, C, pix_per_cta); break;
+      case 8: instnorm_stats_kernel<8><<<grid, 256, 0, stream>>>(x, stats_ws, HW, C, pix_per_cta); break;
+      case 4: instnorm_stats_kernel<4><<<grid, 256, 0, stream>>>(x, stats_ws, HW, C, pix_per_cta); break;
+      case 2: instnorm_stats_kernel<2><<<grid, 256, 0, stream>>>(x, stats_ws, HW, C, pix_per_cta); break;
+      default: instnorm_stats_kernel<1><<<grid, 256, 0, stream>>>(x, stats_ws, HW, C, pix_per_cta); break;
+    }
+    int rc = after_launch("instnorm_stats_kernel");
+    if (rc) return rc;
+  }
+  const int vecC = (C % 4 == 0) ? 4 : 1;
+  dim3 grid(grid_x((long)HW * (C / vecC), 256), N);
+  instnorm_apply_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(x, stats_ws, y_f32, (__nv_bfloat16*)y_hi,
+                                                                     (__nv_bfloat16*)y_lo, HW, C, cpad, eps, do_norm,
+                                                                     act, act_param);
+  return after_launch("instnorm_apply_kernel");
+}
+
+extern "C" int shineon_upsample2x_cat(const void* s0_hi, const void* s0_lo, int c0pad, const void* s1_hi,
+                                      const void* s1_lo, int c1pad, void* y_hi, void* y_lo, int N, int H, int W,
+                                      int act, float act_param, shineon_stream_t stream) {
+  SHINEON_REQUIRE(s0_hi && y_hi, "upsample2x_cat: null pointer");
+  SHINEON_REQUIRE((s1_hi == nullptr) == (c1pad == 0), "upsample2x_cat: s1/c1pad mismatch");
+  SHINEON_REQUIRE((s0_lo == nullptr) == (y_lo == nullptr), "upsample2x_cat: lo planes must be all present or all absent");
+  SHINEON_REQUIRE(s1_hi == nullptr || (s1_lo == nullptr) == (s0_lo == nullptr), "upsample2x_cat: s1 lo mismatch");
+  SHINEON_REQUIRE(c0pad > 0 && c0pad % 8 == 0 && c1pad % 8 == 0, "upsample2x_cat: channel pads must be multiples of 8");
+  SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "upsample2x_cat: bad shape");
+  dim3 grid(grid_x((long)4 * H * W * ((c0pad + c1pad) / 8), 256), N);
+  upsample2x_cat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)s0_hi, (const __nv_bfloat16*)s0_lo, c0pad, (const __nv_bfloat16*)s1_hi,
+      (const __nv_bfloat16*)s1_lo, c1pad, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, H, W, act, act_param);
+  return after_launch("upsample2x_cat_kernel");
+}
+
+extern "C" int shineon_tom_compose(const float* unet_out, int Cout, const float* cloth, const float* warped_prev,
+                                   float* p_rendereds, float* tryon_masks, float* p_tryons, float* flow_masks, int B,
+                                   int H, int W, int n_frames, int frame, int flow_warp, shineon_stream_t stream) {
+  SHINEON_REQUIRE(unet_out && cloth && p_rendereds && tryon_masks && p_tryons, "tom_compose: null pointer");
+  SHINEON_REQUIRE(n_frames >= 1 && frame >= 0 && frame < n_frames, "tom_compose: frame %d of %d", frame, n_frames);
+  SHINEON_REQUIRE(Cout == (flow_warp ? 5 : 4) * n_frames, "tom_compose: Cout %d != %d*n_frames", Cout, flow_warp ? 5 : 4);
+  SHINEON_REQUIRE(!warped_prev || flow_warp, "tom_compose: warped_prev needs flow_warp");
+  SHINEON_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "tom_compose: bad shape");
+  dim3 grid(grid_x((long)H * W, 256), B);
+  tom_compose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(unet_out, Cout, cloth, warped_prev, p_rendereds, tryon_masks,
+                                                            p_tryons, flow_masks, H * W, n_frames, frame, flow_warp);
+  return after_launch("tom_compose_kernel");
+}

@@ -1,0 +1,345 @@
+"""Torch-tensor wrappers over the C ABI: allocation, argument checks and stream plumbing only.
+
+All compute happens in libshineon_b200.so; nothing here falls back to torch ops.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT, PAD, Conv2dParams, TpsTables, check
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _req(t, dtype=torch.float32, name="tensor"):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise _lib.ShineonError(f"{name}: expected a CUDA tensor (shineon ops have no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.ShineonError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.ShineonError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def cpad64(c):
+    return (c + 63) // 64 * 64
+
+
+class Planes:
+    """NHWC activation as bf16 hi (+ lo) planes [N,H,W,cpad]; x ~= hi + lo."""
+
+    def __init__(self, N, H, W, C, split=True, device="cuda", cpad=None):
+        self.N, self.H, self.W, self.C = N, H, W, C
+        self.cpad = cpad64(C) if cpad is None else cpad
+        self.hi = torch.zeros(N, H, W, self.cpad, dtype=torch.bfloat16, device=device)
+        self.lo = torch.zeros_like(self.hi) if split else None
+
+    def float(self):
+        """Reconstructed f32 NCHW tensor (debug / tests)."""
+        v = self.hi.float()
+        if self.lo is not None:
+            v = v + self.lo.float()
+        return v[..., : self.C].permute(0, 3, 1, 2).contiguous()
+
+
+# ----------------------------------------------------------------------------- TPS / grid sample
+class TpsTablesDev:
+    """Device copies of TpsGridGen's constants (built by the host module like warp.py:116-157)."""
+
+    def __init__(self, Li, P_X, P_Y, grid_X, grid_Y, grid_size, device):
+        f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous().view(-1)
+        self.Li, self.P_X, self.P_Y, self.grid_X, self.grid_Y = f(Li), f(P_X), f(P_Y), f(grid_X), f(grid_Y)
+        self.grid_size = int(grid_size)
+        self.struct = TpsTables(_p(self.Li), _p(self.P_X), _p(self.P_Y), _p(self.grid_X), _p(self.grid_Y),
+                                self.grid_size)
+
+
+def tps_grid(theta, tables, H, W):
+    theta = _req(theta, name="theta")
+    B = theta.shape[0]
+    grid = torch.empty(B, H, W, 2, dtype=torch.float32, device=theta.device)
+    check(_lib.load().shineon_tps_grid_fwd(_p(theta), C.byref(tables.struct), _p(grid), B, H, W, _stream()),
+          "shineon_tps_grid_fwd")
+    return grid
+
+
+def grid_sample(inp, grid, padding_mode="zeros"):
+    inp, grid = _req(inp, name="input"), _req(grid, name="grid")
+    B, Cc, Hin, Win = inp.shape
+    _, Hout, Wout, _ = grid.shape
+    out = torch.empty(B, Cc, Hout, Wout, dtype=torch.float32, device=inp.device)
+    check(_lib.load().shineon_grid_sample_fwd(_p(inp), _p(grid), _p(out), B, Cc, Hin, Win, Hout, Wout,
+                                              PAD[padding_mode], _stream()), "shineon_grid_sample_fwd")
+    return out
+
+
+def tps_grid_sample(theta, tables, H, W, inputs, want_grid=False):
+    """inputs: list of up to 3 (tensor [B,C,H,W], padding_mode).  Returns (outs, grid or None)."""
+    theta = _req(theta, name="theta")
+    B = theta.shape[0]
+    args, outs = [], []
+    for i in range(3):
+        if i < len(inputs):
+            t, mode = inputs[i]
+            t = _req(t, name=f"input{i}")
+            assert t.shape[0] == B and t.shape[2] == H and t.shape[3] == W
+            o = torch.empty_like(t)
+            outs.append(o)
+            args += [_p(t), t.shape[1], PAD[mode], _p(o)]
+        else:
+            args += [_p(None), 0, 0, _p(None)]
+    grid = torch.empty(B, H, W, 2, dtype=torch.float32, device=theta.device) if want_grid else None
+    check(_lib.load().shineon_tps_grid_sample_fwd(_p(theta), C.byref(tables.struct), B, H, W, *args, _p(grid),
+                                                  _stream()), "shineon_tps_grid_sample_fwd")
+    return outs, grid
+
+
+# ----------------------------------------------------------------------------- FlowNet2 native ops
+def resample2d_fwd(in1, flow, kernel_size=1, bilinear=True):
+    in1, flow = _req(in1, name="input1"), _req(flow, name="input2")
+    _, d, Hi, Wi = in1.shape
+    b, _, h, w = flow.shape
+    out = torch.empty(b, d, h, w, dtype=torch.float32, device=in1.device)
+    check(_lib.load().shineon_resample2d_fwd(_p(in1), _p(flow), _p(out), b, d, Hi, Wi, h, w, kernel_size,
+                                             int(bool(bilinear)), _stream()), "shineon_resample2d_fwd")
+    return out
+
+
+def resample2d_bwd(in1, flow, grad_out, kernel_size=1, bilinear=True):
+    in1, flow, grad_out = _req(in1), _req(flow), _req(grad_out.contiguous())
+    _, d, Hi, Wi = in1.shape
+    b, _, h, w = flow.shape
+    g1 = torch.zeros_like(in1)
+    g2 = torch.empty_like(flow)
+    check(_lib.load().shineon_resample2d_bwd(_p(in1), _p(flow), _p(grad_out), _p(g1), _p(g2), b, d, Hi, Wi, h, w,
+                                             kernel_size, int(bool(bilinear)), _stream()), "shineon_resample2d_bwd")
+    return g1, g2
+
+
+def channelnorm_fwd(x, norm_deg=2):
+    x = _req(x)
+    b, c, h, w = x.shape
+    out = torch.empty(b, 1, h, w, dtype=torch.float32, device=x.device)
+    check(_lib.load().shineon_channelnorm_fwd(_p(x), _p(out), b, c, h, w, norm_deg, _stream()),
+          "shineon_channelnorm_fwd")
+    return out
+
+
+def channelnorm_bwd(x, out, grad_out, norm_deg=2):
+    x, out, grad_out = _req(x), _req(out), _req(grad_out.contiguous())
+    b, c, h, w = x.shape
+    g = torch.empty_like(x)
+    check(_lib.load().shineon_channelnorm_bwd(_p(x), _p(out), _p(grad_out), _p(g), b, c, h, w, norm_deg, _stream()),
+          "shineon_channelnorm_bwd")
+    return g
+
+
+def correlation_out_shape(Cc, H, W, pad_size, kernel_size, max_displacement, stride1, stride2):
+    oc, oh, ow = C.c_int(), C.c_int(), C.c_int()
+    check(_lib.load().shineon_correlation_out_shape(Cc, H, W, pad_size, kernel_size, max_displacement, stride1,
+                                                    stride2, C.byref(oc), C.byref(oh), C.byref(ow)),
+          "shineon_correlation_out_shape")
+    return oc.value, oh.value, ow.value
+
+
+def correlation_fwd(in1, in2, pad_size, kernel_size, max_displacement, stride1, stride2):
+    in1, in2 = _req(in1), _req(in2)
+    b, c, h, w = in1.shape
+    oc, oh, ow = correlation_out_shape(c, h, w, pad_size, kernel_size, max_displacement, stride1, stride2)
+    out = torch.empty(b, oc, oh, ow, dtype=torch.float32, device=in1.device)
+    check(_lib.load().shineon_correlation_fwd(_p(in1), _p(in2), _p(out), b, c, h, w, pad_size, kernel_size,
+                                              max_displacement, stride1, stride2, _stream()),
+          "shineon_correlation_fwd")
+    return out
+
+
+def correlation_bwd(in1, in2, grad_out, pad_size, kernel_size, max_displacement, stride1, stride2):
+    in1, in2, grad_out = _req(in1), _req(in2), _req(grad_out.contiguous())
+    b, c, h, w = in1.shape
+    g1, g2 = torch.empty_like(in1), torch.empty_like(in2)
+    check(_lib.load().shineon_correlation_bwd(_p(in1), _p(in2), _p(grad_out), _p(g1), _p(g2), b, c, h, w, pad_size,
+                                              kernel_size, max_displacement, stride1, stride2, _stream()),
+          "shineon_correlation_bwd")
+    return g1, g2
+
+
+# ----------------------------------------------------------------------------- tensor-core conv
+class PackedConv:
+    """Conv2d / ConvTranspose2d weight repacked to [Cout][kh*kw][cin_pad] bf16 hi/lo on the device."""
+
+    def __init__(self, weight, bias=None, stride=1, pad=0, cin_pad=None, split=True, chan_map=None,
+                 transposed=False, pad_hw=None):
+        weight = _req(weight.detach().float().contiguous(), name="weight")
+        if transposed:
+            Cin, Cout, kh, kw = weight.shape
+        else:
+            Cout, Cin, kh, kw = weight.shape
+        self.Cout, self.Cin, self.kh, self.kw, self.stride = Cout, Cin, kh, kw, stride
+        self.pad_h, self.pad_w = pad_hw if pad_hw is not None else (pad, pad)
+        if cin_pad is None:
+            cin_pad = cpad64(Cin)
+        self.cin_pad = cin_pad
+        dev = weight.device
+        self.w_hi = torch.empty(Cout, kh * kw, cin_pad, dtype=torch.bfloat16, device=dev)
+        self.w_lo = torch.empty_like(self.w_hi) if split else None
+        cm = None
+        if chan_map is not None:
+            cm = torch.as_tensor(chan_map, dtype=torch.int32, device=dev).contiguous()
+            assert cm.numel() == cin_pad
+        check(_lib.load().shineon_pack_conv_weight(_p(weight), _p(self.w_hi), _p(self.w_lo), Cout, Cin, kh, kw,
+                                                   cin_pad, _p(cm), int(transposed), _stream()),
+              "shineon_pack_conv_weight")
+        self.bias = None if bias is None else _req(bias.detach().float().contiguous(), name="bias")
+        self.transposed = transposed
+
+
+def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_param=0.0, out_f32=None,
+           out_planes=None, out_coffset=0, want_f32=False, want_planes=False, direct=False, tile_n=0, stages=0,
+           out_geom=None, out_hw=None):
+    """Run one convolution layer on planes `x` with packed weights `pc`.
+
+    Outputs: f32 NHWC tensor [N,Ho,Wo,Cout] (want_f32 / out_f32) and/or Planes (want_planes / out_planes).
+    out_geom = (out_H, out_W, oh_mul, oh_off, ow_mul, ow_off) scatters into a larger output (deconv phases).
+    """
+    N, H, W = x.N, x.H, x.W
+    assert x.cpad == pc.cin_pad, f"activation cpad {x.cpad} != packed cin_pad {pc.cin_pad}"
+    assert (x.lo is None) == (pc.w_lo is None), "split mode of activation and weights must agree"
+    if out_hw is not None:
+        Ho, Wo = out_hw
+    else:
+        Ho = (H + 2 * pc.pad_h - pc.kh) // pc.stride + 1
+        Wo = (W + 2 * pc.pad_w - pc.kw) // pc.stride + 1
+    oH, oW, ohm, oho, owm, owo = out_geom if out_geom else (Ho, Wo, 1, 0, 1, 0)
+    dev = x.hi.device
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty(N, oH, oW, pc.Cout, dtype=torch.float32, device=dev)
+    if want_planes and out_planes is None:
+        out_planes = Planes(N, oH, oW, pc.Cout, split=x.lo is not None, device=dev)
+    p = Conv2dParams()
+    p.x_hi, p.x_lo = _p(x.hi), _p(x.lo)
+    p.N, p.H, p.W, p.cin_pad = N, H, W, x.cpad
+    p.w_hi, p.w_lo = _p(pc.w_hi), _p(pc.w_lo)
+    p.Cout, p.kh, p.kw, p.stride, p.pad_h, p.pad_w = pc.Cout, pc.kh, pc.kw, pc.stride, pc.pad_h, pc.pad_w
+    p.Ho, p.Wo = Ho, Wo
+    p.bias, p.scale, p.shift = _p(pc.bias), _p(scale), _p(shift)
+    p.pre_act, p.post_act, p.act_param = ACT[pre_act], ACT[post_act], float(act_param)
+    p.y_f32 = _p(out_f32)
+    p.y_hi = _p(out_planes.hi if out_planes is not None else None)
+    p.y_lo = _p(out_planes.lo if out_planes is not None else None)
+    p.out_H, p.out_W = oH, oW
+    if out_planes is not None:
+        p.out_cstride, p.out_coffset = out_planes.cpad, out_coffset
+        if out_f32 is not None:
+            assert out_f32.shape[-1] == out_planes.cpad, "f32 and planes outputs must share the channel stride"
+    else:
+        p.out_cstride, p.out_coffset = out_f32.shape[-1], out_coffset
+    p.oh_mul, p.oh_off, p.ow_mul, p.ow_off = ohm, oho, owm, owo
+    p.tile_n, p.stages = tile_n, stages
+    fn = _lib.load().shineon_conv2d_direct_fwd if direct else _lib.load().shineon_conv2d_igemm_fwd
+    check(fn(C.byref(p), _stream()), "shineon_conv2d_direct_fwd" if direct else "shineon_conv2d_igemm_fwd")
+    return out_f32, out_planes
+
+
+# ----------------------------------------------------------------------------- layout / norm / pointwise
+def nchw_to_planes(x0, x1=None, act=None, act_param=0.0, split=True, out=None):
+    x0 = _req(x0, name="x0")
+    N, C0, H, W = x0.shape
+    C1 = 0
+    if x1 is not None:
+        x1 = _req(x1, name="x1")
+        C1 = x1.shape[1]
+    if out is None:
+        out = Planes(N, H, W, C0 + C1, split=split, device=x0.device)
+    check(_lib.load().shineon_nchw_to_planes(_p(x0), C0, _p(x1), C1, _p(out.hi), _p(out.lo), N, H, W, out.cpad,
+                                             ACT[act], float(act_param), _stream()), "shineon_nchw_to_planes")
+    return out
+
+
+def instnorm_act(x, *, do_norm=True, act=None, act_param=0.0, eps=1e-5, want_f32=False, want_planes=True,
+                 split=True, out_f32=None, out_planes=None, ws=None):
+    """x: f32 NHWC [N,H,W,C]."""
+    x = _req(x, name="x")
+    N, H, W, Cc = x.shape
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty_like(x)
+    if want_planes and out_planes is None:
+        out_planes = Planes(N, H, W, Cc, split=split, device=x.device)
+    if ws is None and do_norm:
+        ws = torch.empty(N * Cc * 2, dtype=torch.float64, device=x.device)
+    check(_lib.load().shineon_instnorm_act(_p(x), _p(out_f32), _p(out_planes.hi if out_planes else None),
+                                           _p(out_planes.lo if out_planes else None), _p(ws), N, H, W, Cc,
+                                           out_planes.cpad if out_planes else Cc, float(eps), int(bool(do_norm)),
+                                           ACT[act], float(act_param), _stream()), "shineon_instnorm_act")
+    return out_f32, out_planes
+
+
+def upsample2x_cat(s0, s1=None, act=None, act_param=0.0, out=None):
+    N, H, W = s0.N, s0.H, s0.W
+    c1pad = s1.cpad if s1 is not None else 0
+    if out is None:
+        out = Planes(N, 2 * H, 2 * W, s0.cpad + c1pad, split=s0.lo is not None, device=s0.hi.device,
+                     cpad=s0.cpad + c1pad)
+    check(_lib.load().shineon_upsample2x_cat(_p(s0.hi), _p(s0.lo), s0.cpad, _p(s1.hi if s1 else None),
+                                             _p(s1.lo if s1 else None), c1pad, _p(out.hi), _p(out.lo), N, H, W,
+                                             ACT[act], float(act_param), _stream()), "shineon_upsample2x_cat")
+    return out
+
+
+def sagan_attention(qkv, x, gamma, Cq, *, act=None, act_param=0.0, want_f32=False, want_planes=True, split=True,
+                    out_f32=None, out_planes=None):
+    """qkv: f32 NHWC [N,H,W,2*Cq+C]; x: f32 NHWC [N,H,W,C]."""
+    qkv, x, gamma = _req(qkv), _req(x), _req(gamma)
+    N, H, W, Cc = x.shape
+    assert qkv.shape[-1] == 2 * Cq + Cc
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty_like(x)
+    if want_planes and out_planes is None:
+        out_planes = Planes(N, H, W, Cc, split=split, device=x.device)
+    check(_lib.load().shineon_sagan_attention(_p(qkv), _p(x), _p(gamma), _p(out_f32),
+                                              _p(out_planes.hi if out_planes else None),
+                                              _p(out_planes.lo if out_planes else None), N, H * W, Cc, Cq,
+                                              out_planes.cpad if out_planes else Cc, ACT[act], float(act_param),
+                                              _stream()), "shineon_sagan_attention")
+    return out_f32, out_planes
+
+
+def l2norm_correlation(featA, featB, *, want_f32=False, want_planes=True, split=True):
+    """featA/B: f32 NHWC [B,h,w,C] -> correlation [B,h,w,h*w] (channel = wA*h+hA)."""
+    featA, featB = _req(featA), _req(featB)
+    B, h, w, Cc = featA.shape
+    corr = torch.empty(B, h, w, h * w, dtype=torch.float32, device=featA.device) if want_f32 else None
+    planes = Planes(B, h, w, h * w, split=split, device=featA.device) if want_planes else None
+    check(_lib.load().shineon_l2norm_correlation(_p(featA), _p(featB), _p(corr), _p(planes.hi if planes else None),
+                                                 _p(planes.lo if planes else None), B, h, w, Cc,
+                                                 planes.cpad if planes else h * w, _stream()),
+          "shineon_l2norm_correlation")
+    return corr, planes
+
+
+def linear_tanh(x, weight, bias):
+    """x: f32 NHWC [B,h,w,C]; weight [out, C*h*w] over the NCHW-flattened input (warp.py:94-99)."""
+    x, weight = _req(x), _req(weight)
+    B, h, w, Cc = x.shape
+    out_dim = weight.shape[0]
+    assert weight.shape[1] == Cc * h * w
+    theta = torch.empty(B, out_dim, dtype=torch.float32, device=x.device)
+    check(_lib.load().shineon_linear_tanh(_p(x), _p(weight), _p(bias), _p(theta), B, h, w, Cc, out_dim, _stream()),
+          "shineon_linear_tanh")
+    return theta
+
+
+def tom_compose(unet_out, cloth, n_frames, flow_warp, outs, frame=0, warped_prev=None):
+    """unet_out f32 NHWC [B,H,W,Cout]; outs = (p_rendereds, tryon_masks, p_tryons, flow_masks|None) NCHW."""
+    unet_out, cloth = _req(unet_out), _req(cloth)
+    B, H, W, Cout = unet_out.shape
+    pr, tm, pt, fm = outs
+    check(_lib.load().shineon_tom_compose(_p(unet_out), Cout, _p(cloth), _p(warped_prev), _p(pr), _p(tm), _p(pt),
+                                          _p(fm), B, H, W, n_frames, frame, int(bool(flow_warp)), _stream()),
+          "shineon_tom_compose")

@@ -1,0 +1,288 @@
+"""Per-kernel parity: every C-ABI entry point on cuda:0 vs the CPU oracle on the same seeded inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import assert_close, nchw, nhwc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    from shineon_virtual_tryon_b200 import ops as _ops
+
+    return _ops
+
+
+def _planes_from(ops, x_nchw, split=True):
+    return ops.nchw_to_planes(x_nchw.cuda().contiguous(), split=split)
+
+
+# ------------------------------------------------------------------------------------------ conv
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, pad
+    (1, 8, 16, 64, 64, 1, 1, 0),
+    (2, 16, 12, 64, 128, 3, 1, 1),
+    (3, 32, 24, 22, 64, 4, 2, 1),
+    (2, 16, 12, 192, 512, 4, 2, 1),
+    (5, 4, 3, 512, 512, 3, 1, 1),
+    (2, 8, 6, 128, 640, 1, 1, 0),
+    (1, 64, 48, 128, 4, 3, 1, 1),
+    (2, 32, 32, 3, 64, 7, 2, 3),
+    (2, 16, 16, 64, 128, 5, 2, 2),
+    (1, 20, 12, 100, 70, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("split", [True, False])
+def test_conv2d_igemm(ops, case, split):
+    N, H, W, Cin, Cout, k, s, p = case
+    g = torch.Generator().manual_seed(1234 + Cin + Cout + k)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) * (1.0 / (Cin * k * k) ** 0.5)
+    b = torch.randn(Cout, generator=g) * 0.1
+    xp = _planes_from(ops, x, split)
+    pc = ops.PackedConv(w.cuda(), b.cuda(), stride=s, pad=p, split=split)
+    y, yp = ops.conv2d(xp, pc, want_f32=True, want_planes=True)
+    yd, _ = ops.conv2d(xp, pc, want_f32=True, direct=True)
+    torch.cuda.synchronize()
+    if split:
+        want = F.conv2d(x, w, b, stride=s, padding=p)
+        tol = dict(atol=2e-5, rtol=1e-4)
+    else:  # single-bf16 products: compare against the same rounding of the operands
+        want = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, stride=s, padding=p)
+        tol = dict(atol=2e-4, rtol=1e-3)
+    assert_close(nchw(yd), want, what="direct vs oracle", **tol)
+    assert_close(nchw(y), want, what="igemm vs oracle", **tol)
+    assert_close(yp.float(), want, what="igemm planes vs oracle", atol=max(tol["atol"], 1e-2 if not split else 0), rtol=1e-2 if not split else tol["rtol"])
+
+
+def test_conv2d_epilogue_and_window(ops):
+    """bias -> ReLU -> per-channel affine (folded BN) and writing into a channel window of a wider buffer."""
+    g = torch.Generator().manual_seed(7)
+    N, H, W, Cin, Cout = 2, 8, 6, 64, 64
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * 0.05
+    b = torch.randn(Cout, generator=g) * 0.1
+    sc = torch.rand(Cout, generator=g) + 0.5
+    sh = torch.randn(Cout, generator=g) * 0.1
+    xp = _planes_from(ops, x)
+    pc = ops.PackedConv(w.cuda(), b.cuda(), stride=1, pad=1)
+    out = ops.Planes(N, H, W, 192, device="cuda")
+    ops.conv2d(xp, pc, scale=sc.cuda(), shift=sh.cuda(), pre_act="relu", out_planes=out, out_coffset=64)
+    torch.cuda.synchronize()
+    want = F.relu(F.conv2d(x, w, b, padding=1)) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+    got = out.float()
+    assert_close(got[:, 64:128], want, atol=2e-5, rtol=1e-4, what="window")
+    assert got[:, :64].abs().max().item() == 0 and got[:, 128:].abs().max().item() == 0
+
+
+def test_deconv_as_phase_convs(ops):
+    """ConvTranspose2d(4,2,1) (submodules.py:34-38) = 4 phase-wise 2x2 convolutions scattered into the output."""
+    g = torch.Generator().manual_seed(11)
+    N, H, W, Cin, Cout = 2, 6, 8, 64, 32
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cin, Cout, 4, 4, generator=g) * 0.05
+    b = torch.randn(Cout, generator=g) * 0.1
+    want = F.conv_transpose2d(x, w, b, stride=2, padding=1)
+    from shineon_virtual_tryon_b200.networks.deconv import PackedDeconv4x4s2
+
+    xp = _planes_from(ops, x)
+    dc = PackedDeconv4x4s2(w.cuda(), b.cuda())
+    y = dc(xp, want_f32=True)[0]
+    torch.cuda.synchronize()
+    assert_close(nchw(y), want, atol=2e-5, rtol=1e-4, what="deconv")
+
+
+# ------------------------------------------------------------------------------------------ gather ops
+def _tps(ops, gs, H, W):
+    from oracle.gmm import TpsTables
+
+    t = TpsTables(H, W, gs)
+    dev = ops.TpsTablesDev(t.Li, t.P_X, t.P_Y, t.grid_X[0, :], t.grid_Y[:, 0], gs, "cuda")
+    return t, dev
+
+
+@pytest.mark.parametrize("gs,scale", [(5, 0.1), (3, 0.3), (5, 0.6)])
+def test_tps_grid_and_sample(ops, gs, scale):
+    from oracle import gmm
+
+    B, H, W = 3, 64, 48
+    g = torch.Generator().manual_seed(gs)
+    theta = (torch.rand(B, 2 * gs * gs, generator=g) * 2 - 1) * scale
+    cloth = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+    mask = (torch.rand(B, 1, H, W, generator=g) > 0.5).float()
+    t, dev = _tps(ops, gs, H, W)
+    want_grid = gmm.tps_grid(theta, t)
+    got_grid = ops.tps_grid(theta.cuda(), dev, H, W)
+    assert_close(got_grid, want_grid, atol=2e-5, rtol=1e-5, what="tps grid")
+    # grid_sample on the ORACLE grid (isolates the sampler)
+    for mode, src in (("border", cloth), ("zeros", mask)):
+        want = gmm.grid_sample(src, want_grid, mode)
+        got = ops.grid_sample(src.cuda(), want_grid.cuda(), mode)
+        assert_close(got, want, atol=1e-5, rtol=1e-5, what=f"grid_sample {mode}")
+    # fused path
+    outs, grid2 = ops.tps_grid_sample(theta.cuda(), dev, H, W, [(cloth.cuda(), "border"), (mask.cuda(), "zeros")], want_grid=True)
+    assert_close(grid2, want_grid, atol=2e-5, rtol=1e-5, what="fused grid")
+    assert_close(outs[0], gmm.grid_sample(cloth, want_grid, "border"), atol=2e-4, rtol=1e-3, what="fused cloth")
+    assert_close(outs[1], gmm.grid_sample(mask, want_grid, "zeros"), atol=2e-4, rtol=1e-3, what="fused mask")
+
+
+@pytest.mark.parametrize("bilinear", [True, False])
+def test_resample2d(ops, bilinear):
+    from oracle import flow_ops as fo
+
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 3, 3, 40, 28
+    img = torch.rand(B, C, H, W, generator=g)
+    flow = torch.randn(B, 2, H, W, generator=g) * 4
+    want = fo.resample2d_fwd(img, flow, 1, bilinear)
+    got = ops.resample2d_fwd(img.cuda(), flow.cuda(), 1, bilinear)
+    assert_close(got, want, atol=1e-6, rtol=1e-5, what="resample2d fwd")
+    if bilinear:
+        go = torch.randn(B, C, H, W, generator=g)
+        w1, w2 = fo.resample2d_bwd(img, flow, go)
+        g1, g2 = ops.resample2d_bwd(img.cuda(), flow.cuda(), go.cuda())
+        assert_close(g1, w1, atol=1e-5, rtol=1e-4, what="resample2d d_in1")
+        assert_close(g2, w2, atol=1e-5, rtol=1e-4, what="resample2d d_flow")
+
+
+def test_channelnorm(ops):
+    from oracle import flow_ops as fo
+
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(4, 3, 32, 24, generator=g)
+    want = fo.channelnorm_fwd(x)
+    got = ops.channelnorm_fwd(x.cuda())
+    assert_close(got, want, atol=1e-6, rtol=1e-6, what="channelnorm fwd")
+    go = torch.randn(4, 1, 32, 24, generator=g)
+    assert_close(ops.channelnorm_bwd(x.cuda(), got, go.cuda()), fo.channelnorm_bwd(x, want, go), atol=1e-6, rtol=1e-5,
+                 what="channelnorm bwd")
+
+
+@pytest.mark.parametrize("cfg", [(20, 1, 20, 1, 2, 32, 16, 12), (3, 3, 4, 1, 2, 6, 10, 9), (4, 1, 4, 2, 1, 5, 12, 10)])
+def test_correlation(ops, cfg):
+    from oracle import flow_ops as fo
+
+    pad, k, maxd, s1, s2, C, H, W = cfg
+    g = torch.Generator().manual_seed(C)
+    a = torch.randn(2, C, H, W, generator=g)
+    b = torch.randn(2, C, H, W, generator=g)
+    want = fo.correlation_fwd(a, b, pad, k, maxd, s1, s2)
+    got = ops.correlation_fwd(a.cuda(), b.cuda(), pad, k, maxd, s1, s2)
+    assert_close(got, want, atol=1e-5, rtol=1e-4, what="correlation fwd")
+    if H * W <= 120:
+        go = torch.randn(want.shape, generator=g)
+        w1, w2 = fo.correlation_bwd(a, b, go, pad, k, maxd, s1, s2)
+        g1, g2 = ops.correlation_bwd(a.cuda(), b.cuda(), go.cuda(), pad, k, maxd, s1, s2)
+        assert_close(g1, w1, atol=1e-5, rtol=1e-4, what="correlation d_in1")
+        assert_close(g2, w2, atol=1e-5, rtol=1e-4, what="correlation d_in2")
+
+
+# ------------------------------------------------------------------------------------------ norm / pointwise
+@pytest.mark.parametrize("shape", [(2, 64, 32, 24), (3, 512, 4, 3), (2, 4, 64, 48), (2, 5, 16, 12), (1, 167, 8, 6)])
+@pytest.mark.parametrize("act", [None, "gelu", "relu", "leaky", "swish", "sine"])
+def test_instnorm_act(ops, shape, act):
+    from oracle.unet import activation
+
+    g = torch.Generator().manual_seed(shape[1])
+    x = torch.randn(*shape, generator=g) * 2 + 0.7
+    yf, yp = ops.instnorm_act(nhwc(x).cuda(), act=act, act_param=0.2, want_f32=True, want_planes=True)
+    want = F.instance_norm(x, eps=1e-5)
+    if act == "leaky":
+        want = F.leaky_relu(want, 0.2)
+    elif act is not None:
+        want = activation(act, want, None)
+    tol = dict(atol=3e-5, rtol=1e-4) if act != "sine" else dict(atol=2e-4, rtol=1e-3)
+    assert_close(nchw(yf), want, what="instnorm f32", **tol)
+    assert_close(yp.float(), want, what="instnorm planes", **tol)
+
+
+def test_nchw_to_planes_and_upsample_cat(ops):
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(2, 70, 8, 6, generator=g)
+    b = torch.randn(2, 30, 8, 6, generator=g)
+    pa = ops.nchw_to_planes(a.cuda(), act="gelu")
+    pb = ops.nchw_to_planes(b.cuda(), act="gelu")
+    assert_close(pa.float(), F.gelu(a), atol=1e-5, rtol=1e-4, what="planes a")
+    cat = ops.nchw_to_planes(a.cuda(), b.cuda())
+    assert_close(cat.float(), torch.cat([a, b], 1), atol=1e-5, rtol=1e-4, what="planes cat")
+    up = ops.upsample2x_cat(pa, pb)
+    want = F.interpolate(torch.cat([F.gelu(a), F.pad(F.gelu(b), (0, 0, 0, 0, 0, 0))], 1), scale_factor=2, mode="bilinear",
+                         align_corners=False)
+    got = up.float()  # channels: [a (70) | pad to 128 | b (30) | pad]
+    assert_close(got[:, :70], want[:, :70], atol=1e-5, rtol=1e-4, what="upsample a")
+    assert_close(got[:, 128:158], want[:, 70:], atol=1e-5, rtol=1e-4, what="upsample b")
+    assert got[:, 70:128].abs().max().item() == 0
+    # extra ReLU on read (default-activation path)
+    up2 = ops.upsample2x_cat(pa, None, act="relu")
+    assert_close(up2.float()[:, :70], F.interpolate(F.relu(F.gelu(a)), scale_factor=2, mode="bilinear", align_corners=False),
+                 atol=1e-5, rtol=1e-4, what="upsample relu")
+
+
+@pytest.mark.parametrize("hw", [(4, 3), (8, 6), (16, 12)])
+def test_sagan_attention(ops, hw):
+    from oracle.unet import self_attention
+
+    H, W = hw
+    C, Cq, N = 64, 8, 3
+    g = torch.Generator().manual_seed(H)
+    x = torch.randn(N, C, H, W, generator=g)
+    sd = {"a.query_conv.weight": torch.randn(Cq, C, 1, 1, generator=g) * 0.2, "a.query_conv.bias": torch.randn(Cq, generator=g) * 0.1,
+          "a.key_conv.weight": torch.randn(Cq, C, 1, 1, generator=g) * 0.2, "a.key_conv.bias": torch.randn(Cq, generator=g) * 0.1,
+          "a.value_conv.weight": torch.randn(C, C, 1, 1, generator=g) * 0.1, "a.value_conv.bias": torch.randn(C, generator=g) * 0.1,
+          "a.gamma": torch.tensor([0.8])}
+    want = self_attention(sd, "a.", x)
+    q = F.conv2d(x, sd["a.query_conv.weight"], sd["a.query_conv.bias"])
+    k = F.conv2d(x, sd["a.key_conv.weight"], sd["a.key_conv.bias"])
+    v = F.conv2d(x, sd["a.value_conv.weight"], sd["a.value_conv.bias"])
+    qkv = nhwc(torch.cat([q, k, v], 1)).cuda()
+    yf, yp = ops.sagan_attention(qkv, nhwc(x).cuda(), sd["a.gamma"].cuda(), Cq, want_f32=True, want_planes=True)
+    assert_close(nchw(yf), want, atol=2e-5, rtol=1e-4, what="attention f32")
+    assert_close(yp.float(), want, atol=3e-5, rtol=1e-4, what="attention planes")
+
+
+def test_l2norm_correlation_and_linear(ops):
+    from oracle import gmm
+
+    g = torch.Generator().manual_seed(3)
+    B, C, h, w = 3, 512, 16, 12
+    fa = torch.randn(B, C, h, w, generator=g).abs()
+    fb = torch.randn(B, C, h, w, generator=g).abs()
+    want = gmm.feature_correlation(gmm.feature_l2norm(fa), gmm.feature_l2norm(fb))  # [B, h*w, h, w]
+    corr, planes = ops.l2norm_correlation(nhwc(fa).cuda(), nhwc(fb).cuda(), want_f32=True, want_planes=True)
+    assert_close(nchw(corr), want, atol=2e-6, rtol=1e-4, what="l2norm+corr f32")
+    assert_close(planes.float(), want, atol=1e-5, rtol=1e-4, what="l2norm+corr planes")
+    x = torch.randn(B, 64, 4, 3, generator=g)
+    wt = torch.randn(50, 768, generator=g) * 0.05
+    bs = torch.randn(50, generator=g) * 0.1
+    want_t = torch.tanh(F.linear(x.view(B, -1), wt, bs))
+    got_t = ops.linear_tanh(nhwc(x).cuda(), wt.cuda(), bs.cuda())
+    assert_close(got_t, want_t, atol=1e-5, rtol=1e-4, what="linear+tanh")
+
+
+@pytest.mark.parametrize("nf,flow", [(1, False), (2, True)])
+def test_tom_compose(ops, nf, flow):
+    g = torch.Generator().manual_seed(nf)
+    B, H, W = 2, 16, 12
+    cout = (5 if flow else 4) * nf
+    u = torch.randn(B, cout, H, W, generator=g)
+    cloth = torch.rand(B, 3 * nf, H, W, generator=g) * 2 - 1
+    prev = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+    pr = torch.empty(B, 3 * nf, H, W, device="cuda"); tm = torch.empty(B, nf, H, W, device="cuda")
+    pt = torch.empty(B, 3 * nf, H, W, device="cuda"); fm = torch.empty(B, nf, H, W, device="cuda") if flow else None
+    un = nhwc(u).cuda()
+    for f in range(nf):
+        ops.tom_compose(un, cloth.cuda(), nf, flow, (pr, tm, pt, fm), frame=f, warped_prev=prev.cuda() if (flow and f > 0) else None)
+    w_pr = torch.tanh(u[:, :3 * nf]); w_tm = torch.sigmoid(u[:, 3 * nf:4 * nf])
+    assert_close(pr, w_pr, atol=1e-6, rtol=1e-5, what="p_rendereds")
+    assert_close(tm, w_tm, atol=1e-6, rtol=1e-5, what="tryon_masks")
+    for f in range(nf):
+        r = w_pr[:, 3 * f:3 * f + 3]
+        if flow and f > 0:
+            wf = torch.sigmoid(u[:, 4 * nf + f:4 * nf + f + 1])
+            r = (1 - wf) * prev + wf * r
+        want = (1 - w_tm[:, f:f + 1]) * r + w_tm[:, f:f + 1] * cloth[:, 3 * f:3 * f + 3]
+        assert_close(pt[:, 3 * f:3 * f + 3], want, atol=2e-6, rtol=1e-5, what=f"p_tryon[{f}]")
