@@ -1,0 +1,47 @@
+"""Seeded parity cases shared by oracle/make_golden.py (reference side), the CPU tests (oracle side) and
+the GPU tests (CUDA side).  Inputs depend only on the case name, so all three regenerate identical tensors."""
+import torch
+
+TOM_CASES = {
+    # name: (hparams overrides, batch)
+    "tom_gelu_attn": (dict(self_attn=True, num_attn=2, activation="gelu", ngf=64), 1),       # BASELINE config 1
+    "tom_default_act": (dict(self_attn=False, num_attn=2, activation=None, ngf=64), 2),      # LeakyReLU-inplace quirk
+    "tom_swish_attn3": (dict(self_attn=True, num_attn=3, activation="swish", ngf=64), 1),
+    "tom_flow2": (dict(self_attn=True, num_attn=2, activation="gelu", n_frames_total=2, n_frames_now=2,
+                       flow_warp=True), 1),                                                  # ngf=int(64*(ln2+1))=108
+}
+GMM_CASES = {"gmm_b2": dict(batch=2, theta_scale=None), "gmm_stress": dict(batch=2, theta_scale=0.3)}
+
+
+def _g(name):
+    import zlib
+
+    return torch.Generator().manual_seed(zlib.crc32(name.encode()) % (2 ** 31))
+
+
+def tom_inputs(name, H=256, W=192):
+    over, B = TOM_CASES[name]
+    n = over.get("n_frames_total", 1)
+    g = _g(name)
+    person = torch.randn(B, 7 * n, H, W, generator=g)
+    cloth = torch.rand(B, 3 * n, H, W, generator=g) * 2 - 1
+    flows = torch.randn(B, 2 * n, H, W, generator=g) * 3 if over.get("flow_warp") else None
+    return person, cloth, flows
+
+
+def gmm_inputs(name, H=256, W=192):
+    cfg = GMM_CASES[name]
+    g = _g(name)
+    B = cfg["batch"]
+    A = torch.randn(B, 22, H, W, generator=g)
+    Bc = torch.randn(B, 3, H, W, generator=g)
+    cloth = torch.rand(B, 3, H, W, generator=g) * 2 - 1
+    mask = (torch.rand(B, 1, H, W, generator=g) > 0.5).float()
+    theta = None
+    if cfg["theta_scale"] is not None:
+        theta = (torch.rand(B, 50, generator=g) * 2 - 1) * cfg["theta_scale"]
+    return A, Bc, cloth, mask, theta
+
+
+def subsample(t, step=4):
+    return t[..., ::step, ::step].contiguous()

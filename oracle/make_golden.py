@@ -1,0 +1,66 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference classes (imported read-only through
+oracle/ref_shim.py) on the seeded cases of oracle/cases.py.  Build-container only.
+
+    python -m oracle.make_golden
+
+Each fixture stores the state_dict key/shape list (weights are regenerated from (seed, key, shape) by
+oracle/weights.py — `load_state_dict(strict=True)` into the reference module proves key compatibility),
+and spatially subsampled reference outputs (every 4th pixel) to keep the files small.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import cases, ref_shim, weights  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+SEED = 420  # the reference's own seed (train.py:29)
+
+
+def _save(name, shapes, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    meta = json.dumps({"seed": SEED, "shapes": {k: list(v) for k, v in shapes.items()}})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=np.frombuffer(meta.encode(), dtype=np.uint8),
+                        **{k: v.detach().numpy() for k, v in arrays.items()})
+    print("wrote", name, {k: tuple(v.shape) for k, v in arrays.items()})
+
+
+def main():
+    torch.manual_seed(SEED)
+    ref_shim.install()
+    ref_shim.patch_native_ops_with_oracle()  # Resample2d has no CPU path in the reference (tom_flow2 only)
+    with torch.no_grad():
+        for name, (over, _) in cases.TOM_CASES.items():
+            m = ref_shim.build_unet_mask_model(**over)
+            shapes = weights.shapes_of(m)
+            m.load_state_dict(weights.synth_state_dict(shapes, SEED), strict=True)
+            person, cloth, flows = cases.tom_inputs(name)
+            pr, tm, pt, fm = m.forward(person, cloth, flows)
+            arrs = dict(p_rendereds=cases.subsample(pr), tryon_masks=cases.subsample(tm), p_tryons=cases.subsample(pt))
+            if fm is not None:
+                arrs["flow_masks"] = cases.subsample(fm)
+            _save(name, shapes, **arrs)
+        import torch.nn.functional as F
+
+        for name in cases.GMM_CASES:
+            w = ref_shim.build_warp_model()
+            shapes = weights.shapes_of(w)
+            w.load_state_dict(weights.synth_state_dict(shapes, SEED), strict=True)
+            A, Bc, cloth, mask, theta = cases.gmm_inputs(name)
+            if theta is None:
+                grid, theta_out = w.forward(A, Bc)
+            else:  # stress the sampler with large offsets: gridGen + grid_sample only (warp_model.py:72,85-86)
+                grid, theta_out = w.gridGen(theta), theta
+            warped = F.grid_sample(cloth, grid, padding_mode="border")
+            wmask = F.grid_sample(mask, grid, padding_mode="zeros")
+            _save(name, shapes, theta=theta_out, grid=grid[:, ::4, ::4].contiguous(), warped_cloth=cases.subsample(warped),
+                  warped_mask=cases.subsample(wmask))
+
+
+if __name__ == "__main__":
+    main()

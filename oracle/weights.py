@@ -1,0 +1,51 @@
+"""Deterministic synthetic weights for the parity tests, golden fixtures and the benchmark.
+
+No checkpoint of the reference is available offline, so tests use seeded random weights with the
+reference's own init scales (models/networks/__init__.py:49-60: conv/linear N(0, 0.02), BN weight N(1, 0.02))
+plus non-trivial values for everything that would otherwise hide a kernel: attention gamma (zero-initialised,
+sagan.py:25), BatchNorm running statistics, biases.  A tensor's values depend only on (seed, key, shape),
+so any process can regenerate exactly the same state_dict from the key/shape list.
+"""
+import zlib
+
+import torch
+
+
+def _gen(seed, key):
+    return torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) % (2 ** 31))
+
+
+def synth_tensor(seed, key, shape, conv_std=None):
+    g = _gen(seed, key)
+    leaf = key.rsplit(".", 1)[-1]
+    if leaf == "num_batches_tracked":
+        return torch.zeros(shape, dtype=torch.long)
+    if leaf == "gamma":
+        return torch.rand(shape, generator=g) + 0.5
+    if leaf == "running_mean":
+        return torch.randn(shape, generator=g) * 0.1
+    if leaf == "running_var":
+        return torch.rand(shape, generator=g) + 0.5
+    if leaf == "weight" and len(shape) == 1:  # BatchNorm affine
+        return torch.rand(shape, generator=g) + 0.5
+    if leaf == "bias":
+        return torch.randn(shape, generator=g) * 0.05
+    if leaf == "weight" and len(shape) >= 2:
+        if conv_std is None:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            std = (1.0 / fan_in) ** 0.5  # keeps activations O(1) through the stack
+        else:
+            std = conv_std
+        return torch.randn(shape, generator=g) * std
+    return torch.randn(shape, generator=g) * 0.1
+
+
+def synth_state_dict(shapes, seed=420, conv_std=None):
+    """shapes: {key: shape}.  Returns {key: tensor}."""
+    return {k: synth_tensor(seed, k, tuple(s), conv_std) for k, s in shapes.items()}
+
+
+def shapes_of(module):
+    return {k: tuple(v.shape) for k, v in module.state_dict().items()}

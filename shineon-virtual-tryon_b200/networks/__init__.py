@@ -1,1 +1,41 @@
-"""Host-side mirrors of the reference nn.Modules on the hot path (same names, ctor args, state_dict keys)."""
+"""Host-side mirrors of the reference nn.Modules on the hot path (same names, ctor args, state_dict keys).
+
+`init_weights` mirrors models/networks/__init__.py:49-96 (CP-VTON initialisers).
+"""
+from torch.nn import init
+
+
+def weights_init_normal(m):
+    classname = m.__class__.__name__
+    if classname.find("Conv") != -1:
+        init.normal_(m.weight.data, 0.0, 0.02)
+    elif classname.find("Linear") != -1:
+        init.normal_(m.weight.data, 0.0, 0.02)
+    elif classname.find("BatchNorm2d") != -1:
+        init.normal_(m.weight.data, 1.0, 0.02)
+        init.constant_(m.bias.data, 0.0)
+
+
+def weights_init_xavier(m):
+    classname = m.__class__.__name__
+    if classname.find("Conv") != -1 or classname.find("Linear") != -1:
+        init.xavier_normal_(m.weight.data, gain=0.02)
+    elif classname.find("BatchNorm2d") != -1:
+        init.normal_(m.weight.data, 1.0, 0.02)
+        init.constant_(m.bias.data, 0.0)
+
+
+def weights_init_kaiming(m):
+    classname = m.__class__.__name__
+    if classname.find("Conv") != -1 or classname.find("Linear") != -1:
+        init.kaiming_normal_(m.weight.data, a=0, mode="fan_in")
+    elif classname.find("BatchNorm2d") != -1:
+        init.normal_(m.weight.data, 1.0, 0.02)
+        init.constant_(m.bias.data, 0.0)
+
+
+def init_weights(net, init_type="normal"):
+    fn = {"normal": weights_init_normal, "xavier": weights_init_xavier, "kaiming": weights_init_kaiming}.get(init_type)
+    if fn is None:
+        raise NotImplementedError("initialization method [%s] is not implemented" % init_type)
+    net.apply(fn)

@@ -1,0 +1,31 @@
+"""Shared helpers of the host-side engines: packed-weight cache invalidation and BN folding."""
+import torch
+from torch import nn
+
+
+def params_signature(module):
+    """Cheap change detector for a module's parameters/buffers: (data_ptr, _version) of every tensor."""
+    sig = []
+    for t in list(module.parameters()) + list(module.buffers()):
+        sig.append((t.data_ptr(), t._version, t.device.index))
+    return tuple(sig)
+
+
+def fold_bn(bn):
+    """Eval-mode BatchNorm2d as per-channel (scale, shift) for the conv epilogue."""
+    if bn.training:
+        raise NotImplementedError(
+            "BatchNorm2d in training mode (batch statistics) has no native kernel yet; call .eval() "
+            "(the try-on inference path, test.py, always does)")
+    w = bn.weight.detach().float() if bn.weight is not None else torch.ones_like(bn.running_var)
+    b = bn.bias.detach().float() if bn.bias is not None else torch.zeros_like(bn.running_var)
+    scale = w / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = b - bn.running_mean.detach().float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def require_cuda(module, what):
+    p = next(module.parameters(), None)
+    if p is None or not p.is_cuda:
+        raise RuntimeError(f"{what}: module is not on a CUDA device; the shineon B200 path has no CPU fallback")
+    return p.device

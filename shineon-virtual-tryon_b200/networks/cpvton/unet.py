@@ -1,0 +1,211 @@
+"""UnetGenerator / UnetSkipConnectionBlock (reference: models/networks/cpvton/unet.py:9-211).
+
+The module tree (and therefore every state_dict key, e.g. `model.model.1.model.3.model.1.weight`) is built
+exactly like the reference constructors do.  The forward pass does not run the nn.Sequential: it walks the
+tree once and drives the hand-written kernels, keeping activations as NHWC bf16 hi/lo planes between layers:
+
+  down:  conv4x4s2 (tcgen05, bias in epilogue) -> InstanceNorm(+next activation) -> [SelfAttention]
+  up:    upsample2x_cat (up_act, concat, bilinear x2) -> conv3x3 (tcgen05) -> InstanceNorm -> [SelfAttention]
+"""
+import torch
+from torch import nn
+
+from ... import ops
+from .._engine_util import fold_bn, params_signature, require_cuda
+from ..activation import Sine, Swish, act_name
+from ..attention.sagan import SelfAttention
+
+
+class UnetGenerator(nn.Module):
+    def __init__(self, input_nc, output_nc, num_downs, num_attention, ngf=64, norm_layer=nn.BatchNorm2d,
+                 use_dropout=False, use_self_attn=False, activation=None):
+        super().__init__()
+
+        def attn():
+            return use_self_attn if use_self_attn and num_attention > 0 else None
+
+        unet_block = UnetSkipConnectionBlock(ngf * 8, ngf * 8, input_nc=None, submodule=None, norm_layer=norm_layer,
+                                             innermost=True, self_attn=attn(), activation=activation)
+        num_attention -= 1
+        for _ in range(num_downs - 5):
+            unet_block = UnetSkipConnectionBlock(ngf * 8, ngf * 8, input_nc=None, submodule=unet_block,
+                                                 norm_layer=norm_layer, use_dropout=use_dropout, self_attn=attn(),
+                                                 activation=activation)
+            num_attention -= 1
+        for outer, inner in ((ngf * 4, ngf * 8), (ngf * 2, ngf * 4), (ngf, ngf * 2)):
+            unet_block = UnetSkipConnectionBlock(outer, inner, input_nc=None, submodule=unet_block,
+                                                 norm_layer=norm_layer, self_attn=attn(), activation=activation)
+            num_attention -= 1
+        unet_block = UnetSkipConnectionBlock(output_nc, ngf, input_nc=input_nc, submodule=unet_block, outermost=True,
+                                             norm_layer=norm_layer, self_attn=attn(), activation=activation)
+        self.model = unet_block
+        self.split_precision = True  # bf16x3 products (fp32-grade); False = single bf16 (fast mode)
+
+    def forward_nhwc(self, input):
+        """input: f32 NCHW CUDA tensor -> f32 NHWC [N,H,W,output_nc]."""
+        require_cuda(self, "UnetGenerator")
+        split = self.split_precision
+        blk = self.model
+        x = ops.nchw_to_planes(input.contiguous(), split=split)
+        return blk.run(x, split)
+
+    def forward(self, input):
+        return self.forward_nhwc(input).permute(0, 3, 1, 2).contiguous()
+
+
+class UnetSkipConnectionBlock(nn.Module):
+    def __init__(self, outer_nc, inner_nc, input_nc=None, submodule=None, outermost=False, innermost=False,
+                 norm_layer=nn.BatchNorm2d, self_attn=False, use_dropout=False, activation=None):
+        super().__init__()
+        self.outermost = outermost
+        self.innermost = innermost
+        use_bias = norm_layer == nn.InstanceNorm2d
+        if input_nc is None:
+            input_nc = outer_nc
+        downconv = nn.Conv2d(input_nc, inner_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+        down_activation = nn.LeakyReLU(0.2, True) if activation is None else _get_activation_fn(activation)
+        downnorm = norm_layer(inner_nc)
+        up_activation = nn.ReLU(True) if activation is None else _get_activation_fn(activation)
+        upnorm = norm_layer(outer_nc)
+        upsample = nn.Upsample(scale_factor=2, mode="bilinear")
+        if outermost:
+            upconv = nn.Conv2d(inner_nc * 2, outer_nc, kernel_size=3, stride=1, padding=1, bias=use_bias)
+            down = [downconv]
+            up = [up_activation, upsample, upconv, upnorm]
+            if self_attn:
+                down.append(SelfAttention(inner_nc, "relu"))
+                up.append(SelfAttention(outer_nc, "relu"))
+            model = down + [submodule] + up
+        elif innermost:
+            upconv = nn.Conv2d(inner_nc, outer_nc, kernel_size=3, stride=1, padding=1, bias=use_bias)
+            down = [down_activation, downconv]
+            up = [up_activation, upsample, upconv, upnorm]
+            if self_attn:
+                down.append(SelfAttention(inner_nc, "relu"))
+                up.append(SelfAttention(outer_nc, "relu"))
+            model = down + up
+        else:
+            upconv = nn.Conv2d(inner_nc * 2, outer_nc, kernel_size=3, stride=1, padding=1, bias=use_bias)
+            down = [down_activation, downconv, downnorm]
+            up = [up_activation, upsample, upconv, upnorm]
+            if self_attn:
+                down.append(SelfAttention(inner_nc, "relu"))
+                up.append(SelfAttention(outer_nc, "relu"))
+            model = down + [submodule] + up + ([nn.Dropout(0.5)] if use_dropout else [])
+        self.model = nn.Sequential(*model)
+        # structural view used by the engine (not registered twice: plain attributes to existing children)
+        self._parts = dict(
+            down_act=None if outermost else down_activation, downconv=downconv,
+            downnorm=None if (outermost or innermost) else downnorm,
+            attn_down=down[-1] if self_attn else None, sub=submodule, up_act=up_activation, upconv=upconv,
+            upnorm=upnorm, attn_up=up[-1] if self_attn else None, default_act=activation is None,
+            dropout=use_dropout and not (outermost or innermost))
+        self._packed = None
+
+    # ------------------------------------------------------------------ engine
+    def _pack(self, split):
+        sig = (params_signature(self._parts["downconv"]) + params_signature(self._parts["upconv"])
+               + params_signature(self._parts["upnorm"])
+               + (params_signature(self._parts["downnorm"]) if self._parts["downnorm"] is not None else ()), split)
+        if self._packed is not None and self._packed[0] == sig:
+            return self._packed[1]
+        pr = self._parts
+        dc, uc = pr["downconv"], pr["upconv"]
+        sub = pr["sub"]
+        d = {}
+        d["down"] = ops.PackedConv(dc.weight, dc.bias, stride=2, pad=1, split=split)
+        if sub is not None:
+            # up-conv input channels: [skip (sub input, padded to 64) | x' (sub output, padded to 64)]
+            c_skip = sub._parts["downconv"].in_channels
+            c_xp = sub._parts["upconv"].out_channels
+            p_skip, p_xp = ops.cpad64(c_skip), ops.cpad64(c_xp)
+            cmap = [-1] * (p_skip + p_xp)
+            for c in range(c_skip):
+                cmap[c] = c
+            for c in range(c_xp):
+                cmap[p_skip + c] = c_skip + c
+            d["up"] = ops.PackedConv(uc.weight, uc.bias, stride=1, pad=1, split=split, cin_pad=p_skip + p_xp,
+                                     chan_map=cmap)
+        else:
+            d["up"] = ops.PackedConv(uc.weight, uc.bias, stride=1, pad=1, split=split)
+        for key, norm in (("down_bn", pr["downnorm"]), ("up_bn", pr["upnorm"])):
+            d[key] = None
+            if isinstance(norm, nn.BatchNorm2d):
+                d[key] = fold_bn(norm)
+            elif norm is not None and not isinstance(norm, nn.InstanceNorm2d):
+                raise NotImplementedError(f"norm layer {type(norm).__name__} has no native kernel")
+            elif isinstance(norm, nn.InstanceNorm2d) and (norm.affine or norm.track_running_stats):
+                raise NotImplementedError("InstanceNorm2d with affine/running stats is not used by the reference")
+        self._packed = (sig, d)
+        return d
+
+    def _finish(self, conv_f32, norm, bn, attn, act, act_param, split, want_final_f32=False):
+        """conv output (f32 NHWC, bias [and folded BN] applied) -> [InstanceNorm] -> [SelfAttention] -> act.
+        Returns Planes of the activated value, or the final f32 tensor when want_final_f32."""
+        inorm = isinstance(norm, nn.InstanceNorm2d)
+        if attn is None:
+            if want_final_f32:
+                y, _ = ops.instnorm_act(conv_f32, do_norm=inorm, eps=norm.eps if inorm else 1e-5, act=None,
+                                        want_f32=True, want_planes=False, out_f32=conv_f32)
+                return y
+            _, p = ops.instnorm_act(conv_f32, do_norm=inorm, eps=norm.eps if inorm else 1e-5, act=act,
+                                    act_param=act_param, want_f32=False, want_planes=True, split=split)
+            return p
+        # attention works on the normalised, un-activated tensor: needs it as f32 (residual) and planes (qkv conv)
+        y, p = ops.instnorm_act(conv_f32, do_norm=inorm, eps=norm.eps if inorm else 1e-5, act=None, want_f32=True,
+                                want_planes=True, split=split, out_f32=conv_f32)
+        if want_final_f32:
+            return attn.run(y, p, want_f32=True, want_planes=False)[0]
+        return attn.run(y, p, act=act, act_param=act_param, want_f32=False, want_planes=True)[1]
+
+    def run(self, a_in, split):
+        """a_in: Planes holding this block's (already down-activated) input.
+        Outermost: returns f32 NHWC output.  Otherwise returns Planes of up_act(x') for the parent."""
+        pr = self._parts
+        if self.training and pr["dropout"]:
+            raise NotImplementedError("Dropout in training mode is not implemented in the native U-Net engine")
+        pk = self._pack(split)
+        sub = pr["sub"]
+        up_act, up_par = act_name(pr["up_act"])
+        # ---- down path: conv -> [norm] -> [attn] -> activation consumed next
+        if self.innermost:
+            next_act, next_par = up_act, up_par
+        else:
+            next_act, next_par = act_name(sub._parts["down_act"])
+        bn = pk["down_bn"]
+        sc, sh = bn if bn is not None else (None, None)
+        f32, _ = ops.conv2d(a_in, pk["down"], scale=sc, shift=sh, want_f32=True)
+        a_mid = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, split)
+        # ---- child + up-path input
+        if self.innermost:
+            u = ops.upsample2x_cat(a_mid, None)
+        else:
+            xp = sub.run(a_mid, split)
+            # default activation: the skip holds LeakyReLU'd values (in-place, unet.py:132) and the parent's
+            # ReLU is applied on top when reading it (relu(leaky(x)) == relu(x)); x' is already ReLU'd (idempotent)
+            extra = "relu" if pr["default_act"] else None
+            u = ops.upsample2x_cat(a_mid, xp, act=extra)
+        bn = pk["up_bn"]
+        sc, sh = bn if bn is not None else (None, None)
+        f32, _ = ops.conv2d(u, pk["up"], scale=sc, shift=sh, want_f32=True)
+        if self.outermost:
+            return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], None, 0.0, split, want_final_f32=True)
+        return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], up_act, up_par, split)
+
+    def forward(self, x):
+        raise NotImplementedError(
+            "UnetSkipConnectionBlock is driven by UnetGenerator.forward in the B200 build (activations stay in "
+            "NHWC planes between blocks); call the generator instead")
+
+
+def _get_activation_fn(activation):
+    if activation == "relu":
+        return nn.ReLU()
+    elif activation == "gelu":
+        return nn.GELU()
+    elif activation == "swish":
+        return Swish()
+    elif activation == "sine":
+        return Sine()
+    else:
+        raise RuntimeError(f"The selected activation should be relu/gelu/swish/sine, not {activation}")

@@ -1,0 +1,104 @@
+"""Pins the CPU oracle against the golden vectors produced by the reference's own classes
+(oracle/make_golden.py), and checks the oracle's internal consistency.  CPU only."""
+import pytest
+import torch
+
+from oracle import cases, flow_ops as fo, gmm, unet, weights
+from tests.golden_util import load_golden
+from tests.util import assert_close
+
+
+def _tom_kwargs(over):
+    return dict(n_frames=over.get("n_frames_total", 1), flow_warp=over.get("flow_warp", False), num_downs=6,
+                num_attention=over.get("num_attn", 2), use_self_attn=over.get("self_attn", True),
+                act=over.get("activation", "gelu"))
+
+
+@pytest.mark.parametrize("name", list(cases.TOM_CASES))
+def test_tom_oracle_matches_reference_golden(name):
+    seed, shapes, gold = load_golden(name)
+    sd = weights.synth_state_dict(shapes, seed)
+    person, cloth, flows = cases.tom_inputs(name)
+    with torch.no_grad():
+        pr, tm, pt, fm = unet.tom_forward(sd, person, cloth, flows=flows, resample=fo.resample2d_fwd,
+                                          **_tom_kwargs(cases.TOM_CASES[name][0]))
+    # same ATen kernels, same graph: expect bit-level agreement (tolerance only for thread-count effects)
+    assert_close(cases.subsample(pr), gold["p_rendereds"], atol=1e-5, rtol=1e-5, what="p_rendereds")
+    assert_close(cases.subsample(tm), gold["tryon_masks"], atol=1e-5, rtol=1e-5, what="tryon_masks")
+    assert_close(cases.subsample(pt), gold["p_tryons"], atol=1e-5, rtol=1e-5, what="p_tryons")
+    if fm is not None:
+        assert_close(cases.subsample(fm), gold["flow_masks"], atol=1e-5, rtol=1e-5, what="flow_masks")
+
+
+@pytest.mark.parametrize("name", list(cases.GMM_CASES))
+def test_gmm_oracle_matches_reference_golden(name):
+    seed, shapes, gold = load_golden(name)
+    sd = weights.synth_state_dict(shapes, seed)
+    A, Bc, cloth, mask, theta = cases.gmm_inputs(name)
+    t = gmm.TpsTables(256, 192, 5)
+    with torch.no_grad():
+        if theta is None:
+            grid, theta = gmm.gmm_forward(sd, A, Bc, t)
+        else:
+            grid = gmm.tps_grid(theta, t)
+    assert_close(theta, gold["theta"], atol=1e-5, rtol=1e-5, what="theta")
+    assert_close(grid[:, ::4, ::4], gold["grid"], atol=1e-5, rtol=1e-5, what="grid")
+    assert_close(cases.subsample(gmm.grid_sample(cloth, grid, "border")), gold["warped_cloth"], atol=1e-5, rtol=1e-5,
+                 what="warped cloth")
+    assert_close(cases.subsample(gmm.grid_sample(mask, grid, "zeros")), gold["warped_mask"], atol=1e-5, rtol=1e-5,
+                 what="warped mask")
+
+
+def test_attention_levels_follow_reference_countdown():
+    assert unet.attention_levels(6, 2, True) == {5, 4}
+    assert unet.attention_levels(6, 3, True) == {5, 4, 3}
+    assert unet.attention_levels(6, 2, False) == set()
+
+
+# ---- the three CUDA-only ops: consistency of the restatement (backward == autograd of forward where the
+# reference's backward is the exact gradient, i.e. away from its trunc-vs-floor quirk)
+def test_correlation_backward_is_gradient_of_forward():
+    g = torch.Generator().manual_seed(0)
+    for (pad, k, maxd, s1, s2, C, H, W) in [(4, 1, 4, 1, 2, 4, 6, 5), (3, 3, 2, 1, 1, 3, 8, 7)]:
+        a = torch.randn(1, C, H, W, generator=g, requires_grad=True)
+        b = torch.randn(1, C, H, W, generator=g, requires_grad=True)
+        o = fo.correlation_fwd(a, b, pad, k, maxd, s1, s2)
+        assert o.shape[1:] == fo.correlation_out_shape(C, H, W, pad, k, maxd, s1, s2)
+        go = torch.randn(o.shape, generator=g)
+        o.backward(go)
+        g1, g2 = fo.correlation_bwd(a.detach(), b.detach(), go, pad, k, maxd, s1, s2)
+        assert_close(g1, a.grad, atol=1e-5, rtol=1e-4, what="d_in1")
+        assert_close(g2, b.grad, atol=1e-5, rtol=1e-4, what="d_in2")
+
+
+def test_flownetc_correlation_shape():
+    # FlowNetC.py:31 config on the 256x192 path: 441 channels at 32x24
+    assert fo.correlation_out_shape(256, 32, 24, 20, 1, 20, 1, 2) == (441, 32, 24)
+
+
+def test_resample2d_properties():
+    g = torch.Generator().manual_seed(1)
+    img = torch.rand(2, 3, 12, 10, generator=g)
+    zero = torch.zeros(2, 2, 12, 10)
+    assert torch.equal(fo.resample2d_fwd(img, zero), img)  # identity flow
+    shift = zero.clone()
+    shift[:, 0] = 1.0  # sample one pixel to the right, clamped at the border
+    want = torch.cat([img[..., 1:], img[..., -1:]], -1)
+    assert torch.equal(fo.resample2d_fwd(img, shift), want)
+    # backward == autograd where xf, yf >= 0 (no trunc/floor discrepancy, resample2d_kernel.cu:105-106)
+    im = img.clone().requires_grad_()
+    fl = (torch.rand(2, 2, 12, 10, generator=g) * 3).requires_grad_()
+    o = fo.resample2d_fwd(im, fl)
+    go = torch.randn(o.shape, generator=g)
+    o.backward(go)
+    g1, g2 = fo.resample2d_bwd(im.detach(), fl.detach(), go)
+    assert_close(g1, im.grad, atol=1e-5, rtol=1e-4, what="d_img")
+    assert_close(g2, fl.grad, atol=1e-5, rtol=1e-4, what="d_flow")
+
+
+def test_channelnorm_backward_is_gradient():
+    x = torch.randn(2, 3, 4, 5, requires_grad=True)
+    o = fo.channelnorm_fwd(x)
+    go = torch.randn_like(o)
+    o.backward(go)
+    assert_close(fo.channelnorm_bwd(x.detach(), o.detach(), go), x.grad, atol=1e-6, rtol=1e-5, what="d_in")

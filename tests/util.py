@@ -27,3 +27,30 @@ def nhwc(t):
 
 def nchw(t):
     return t.permute(0, 3, 1, 2).contiguous()
+
+
+BASE_HPARAMS = dict(n_frames_total=1, n_frames_now=1, person_inputs=["agnostic", "densepose"], cloth_inputs=["cloth"],
+                    ngf=64, self_attn=True, num_attn=2, flow_warp=False, activation="gelu", is_train=False,
+                    grid_size=5, fine_height=256, fine_width=192)
+
+
+def make_hparams(**over):
+    import argparse
+
+    d = dict(BASE_HPARAMS)
+    d.update(over)
+    return argparse.Namespace(**d)
+
+
+def build_model(kind, seed=420, **over):
+    """Our nn.Module mirror with the deterministic synthetic weights (oracle/weights.py) loaded strictly."""
+    from oracle import weights
+    from shineon_virtual_tryon_b200.models import find_model_using_name
+
+    if kind == "warp":
+        over.setdefault("person_inputs", ["agnostic", "cocopose"])
+    m = find_model_using_name(kind)(make_hparams(**over))
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = weights.synth_state_dict(shapes, seed)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval(), sd
