@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — try-on frames/sec @256x192 (GMM warp + U-Net) on N B200s, next to the reference's CPU path.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run, one rank/GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], SURVEY.md §8d config 3, primary): 5-frame clips at 256x192; per clip the
+5 frames go as a batch through WarpModel.forward -> grid_sample(border) -> UnetMaskModel.forward
+(n_frames_total=1, --self_attn --activation gelu, the published ShineOn recipe docs/3_train.md:58-70).
+One step = `--clips` clips (default 16 = 80 frames) per GPU; frames are independent, so ranks shard clips
+with no data-path collective (weak scaling).  Synthetic inputs, seeded random weights (no checkpoints offline).
+
+Prints ONE JSON line (see the keys below).  `value` = frames/s with the step's inputs resident in HBM;
+`e2e` = the same work through the public host-buffer API (pinned host tensors -> H2D -> kernels -> D2H).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 256, 192
+FRAMES_PER_CLIP = 5
+# algorithmic conv FLOPs per try-on frame: GMM 9.295 + U-Net 16.731 GFLOP
+GFLOP_PER_FRAME = 9.295 + 16.731
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clips", type=int, default=16, help="5-frame clips per step per GPU")
+    ap.add_argument("--fast", action="store_true", help="also report the single-bf16 (serving) mode")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-clips", type=int, default=1, help="clips per CPU-baseline step (bounded sample)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- helpers
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # samples under load = upper half (idle samples at the edges would drag the median down)
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_models():
+    """WarpModel + UnetMaskModel mirrors on the CPU with the reference's own initialisation under the reference's
+    seed (train.py:29), then non-trivial attention gammas / BatchNorm statistics so no layer is a numerical no-op."""
+    import argparse
+
+    import torch
+    from torch import nn
+
+    from shineon_virtual_tryon_b200.models.unet_mask_model import UnetMaskModel
+    from shineon_virtual_tryon_b200.models.warp_model import WarpModel
+    from shineon_virtual_tryon_b200.networks.attention.sagan import SelfAttention
+
+    torch.manual_seed(420)
+    base = dict(n_frames_total=1, n_frames_now=1, cloth_inputs=["cloth"], ngf=64, self_attn=True, num_attn=2,
+                flow_warp=False, activation="gelu", is_train=False, grid_size=5, fine_height=H, fine_width=W)
+    warp = WarpModel(argparse.Namespace(person_inputs=["agnostic", "cocopose"], **base)).eval()
+    tom = UnetMaskModel(argparse.Namespace(person_inputs=["agnostic", "densepose"], **base)).eval()
+    with torch.no_grad():
+        for m in list(warp.modules()) + list(tom.modules()):
+            if isinstance(m, SelfAttention):
+                m.gamma.uniform_(0.5, 1.5)
+            elif isinstance(m, nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+    return warp, tom
+
+
+def synth_inputs(frames, seed, pinned=False):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(frames, 22, H, W, generator=g)
+    c = torch.rand(frames, 3, H, W, generator=g) * 2 - 1
+    p = torch.randn(frames, 7, H, W, generator=g)
+    if pinned:
+        a, c, p = a.pin_memory(), c.pin_memory(), p.pin_memory()
+    return a, c, p
+
+
+# ------------------------------------------------------------------------------------------- CPU baseline
+def cpu_tryon_fps(clips, min_seconds=10.0, max_iters=20):
+    """The oracle port of the reference path (oracle/gmm.py + oracle/unet.py == the reference modules' exact ATen
+    graph, pinned bit-for-bit by tests/test_oracle_cpu.py) timed on this box's host cores."""
+    import torch
+
+    from oracle import gmm, unet
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    warp, tom = build_models()
+    sdw = {k: v.detach() for k, v in warp.state_dict().items()}
+    sdt = {k: v.detach() for k, v in tom.state_dict().items()}
+    t = gmm.TpsTables(H, W, 5)
+    frames = clips * FRAMES_PER_CLIP
+    a, c, p = synth_inputs(frames, 7)
+
+    def step():
+        with torch.no_grad():
+            outs = []
+            for i in range(clips):  # one clip = a batch of 5 frames (the reference's inference batches frames too)
+                s = slice(i * FRAMES_PER_CLIP, (i + 1) * FRAMES_PER_CLIP)
+                grid, _ = gmm.gmm_forward(sdw, a[s], c[s], t)
+                wc = gmm.grid_sample(c[s], grid, "border")
+                outs.append(unet.tom_forward(sdt, p[s], wc, n_frames=1, flow_warp=False, num_downs=6, num_attention=2,
+                                             use_self_attn=True, act="gelu")[2])
+            return outs
+
+    step()  # warm-up
+    times = []
+    t_start = time.time()
+    while len(times) < 3 or (time.time() - t_start < min_seconds and len(times) < max_iters):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return frames / med, cores, f"{clips} clip(s) x {FRAMES_PER_CLIP} frames, {len(times)} timed iterations, median", med
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    fps, cores, sample, med = cpu_tryon_fps(args.cpu_clips, min_seconds=0.0, max_iters=max(args.steps, 3))
+    line = {
+        "impl": "reference", "metric": "try-on frames/sec @256x192 (GMM warp + U-Net)", "value": fps,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[2]: 5-frame clips 256x192, GMM -> grid_sample -> U-Net(self-attn, GELU), CPU oracle port",
+                   "clips_per_step": args.cpu_clips, "frames_per_clip": FRAMES_PER_CLIP},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from shineon_virtual_tryon_b200 import _lib, ops
+    from shineon_virtual_tryon_b200.pipeline import TryOnPipeline
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warp, tom = build_models()
+    pipe = TryOnPipeline(warp.to(dev), tom.to(dev))
+    frames = args.clips * FRAMES_PER_CLIP
+    a_h, c_h, p_h = synth_inputs(frames, 100 + rank, pinned=True)
+    a, c, p = a_h.to(dev), c_h.to(dev), p_h.to(dev)
+
+    def timed(fn, steps, sampler=None):
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), clocks
+
+    def run_mode(split):
+        pipe.set_precision(split)
+        for _ in range(args.warmup):
+            pipe(a, c, p)
+        l0 = _lib.launch_count()
+        prof = []
+        ops.PROFILE = prof
+        ms, clocks = timed(lambda: pipe(a, c, p), args.steps, ClockSampler(local) if rank == 0 else None)
+        ops.PROFILE = None
+        launches = _lib.launch_count() - l0
+        torch.cuda.synchronize()
+        conv_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in prof)
+        conv_flops = sum(f for f, _, _ in prof)
+        # end-to-end through the host-buffer API
+        for _ in range(max(1, args.warmup // 2)):
+            pipe.run_host(a_h, c_h, p_h)
+        ms_e2e, _ = timed(lambda: pipe.run_host(a_h, c_h, p_h), args.steps)
+        return dict(ms=ms, clocks=clocks, launches=launches, conv_ms=conv_ms, conv_flops=conv_flops,
+                    conv_launches=len(prof), ms_e2e=ms_e2e)
+
+    main = run_mode(True)
+    fast = run_mode(False) if args.fast else None
+
+    total_frames = frames * world * args.steps
+    value = total_frames / (main["ms"] * 1e-3)
+    e2e = total_frames / (main["ms_e2e"] * 1e-3)
+    peaks, peak_src = read_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    ach_tf = main["conv_flops"] / (main["conv_ms"] * 1e-3) / 1e12 if main["conv_ms"] > 0 else 0.0
+
+    line = {
+        "metric": "try-on frames/sec @256x192 (GMM warp + U-Net)", "value": value, "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (hi/lo-split bf16 tcgen05 products, fp32 accumulate; fp32-grade)", "data": "synthetic",
+        "config": {
+            "workload": "configs[2]: 5-frame clips 256x192, GMM(FeatureExtraction x2, correlation, regression, TPS) -> "
+                        "grid_sample(border) -> U-Net(num_downs 6, self-attn x4, GELU, InstanceNorm) -> tanh/sigmoid compose",
+            "clips_per_step_per_gpu": args.clips, "frames_per_clip": FRAMES_PER_CLIP, "frames_per_step": frames * world,
+            "parallelism": f"dp{world} (clips sharded, no collective)", "weights": "seeded random (no checkpoints offline)",
+            "l2": f"inputs per step {frames * 32 * H * W * 4 / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
+        },
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frames * 32 * H * W * 4,
+                "d2h_bytes_per_step": frames * 3 * H * W * 4, "ms_per_step": main["ms_e2e"] / args.steps},
+        "gpu_launches": main["launches"],
+        "clocks": main["clocks"],
+        "roofline": {
+            "kernel": "conv_igemm_kernel (tcgen05 implicit-GEMM conv, all conv launches of the step)",
+            "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+            "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
+            "algorithmic_gflop_per_frame": main["conv_flops"] / (frames * args.steps) / 1e9,
+            "conv_launches_per_step": main["conv_launches"] // args.steps,
+            "conv_share_of_step": main["conv_ms"] / main["ms"],
+            "whole_step_frac_of_tensor_peak": (GFLOP_PER_FRAME * 1e9 * frames * args.steps) / (main["ms"] * 1e-3) / 1e12 / peak_tf,
+            "traffic": None,
+        },
+    }
+    if fast is not None:
+        line["fast_bf16"] = {"value": total_frames / (fast["ms"] * 1e-3), "unit": "frames/s",
+                             "e2e": total_frames / (fast["ms_e2e"] * 1e-3),
+                             "conv_tflops": fast["conv_flops"] / (fast["conv_ms"] * 1e-3) / 1e12,
+                             "note": "single-bf16 products; parity bound 8e-2 abs (tests/test_e2e_gpu.py::test_fast_mode_single_bf16)"}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            fps, cores, sample, _ = cpu_tryon_fps(args.cpu_clips)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_b200(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -23,7 +23,7 @@
  * Layout conventions
  *   "NCHW f32"   : the reference's public tensor layout (contiguous).
  *   "NHWC planes": internal activation layout of the tensor-core path:
- *                  two bf16 tensors [N,H,W,Cpad] (hi, lo) with x ~= hi + lo
+ *                  two 16-bit tensors [N,H,W,Cpad] (hi, lo; bf16 or fp16, see shineon_plane_fmt) with x ~= hi + lo
  *                  (lo may be NULL in single-bf16 mode); Cpad % 64 == 0,
  *                  channels >= C are zero.
  */
@@ -58,6 +58,11 @@ enum shineon_act {
 };
 
 enum shineon_padding_mode { SHINEON_PAD_ZEROS = 0, SHINEON_PAD_BORDER = 1 };
+
+/* Encoding of the 16-bit hi/lo activation / weight planes (argument `plane_fmt`):
+ * BF16: range-safe, hi+lo = 16 mantissa bits;  FP16: hi+lo = 22 mantissa bits (fp32-grade products), values
+ * are clamped to +-65000 when written (weights are pre-scaled by a power of two, see acc_scale). */
+enum shineon_plane_fmt { SHINEON_FMT_BF16 = 0, SHINEON_FMT_FP16 = 1 };
 
 int shineon_version(void);
 const char* shineon_last_error(void);
@@ -139,7 +144,8 @@ int shineon_correlation_bwd(const float* in1, const float* in2, const float* gra
  * input channel to the OIHW input channel or -1 (zero); NULL = identity for c<Cin, zero above.
  * transpose_io != 0 reads a ConvTranspose2d weight [Cin][Cout][kh][kw] with the taps flipped. */
 int shineon_pack_conv_weight(const float* w, void* w_hi, void* w_lo, int Cout, int Cin, int kh, int kw,
-                             int cin_pad, const int32_t* chan_map, int transpose_io,
+                             int cin_pad, const int32_t* chan_map, int transpose_io, int plane_fmt,
+                             float w_scale /* packed = w * w_scale; pass 1/w_scale as acc_scale */,
                              shineon_stream_t stream);
 
 typedef struct shineon_conv2d_params {
@@ -160,6 +166,8 @@ typedef struct shineon_conv2d_params {
   const float* shift;
   int pre_act, post_act;
   float act_param;
+  float acc_scale; /* accumulator multiplier applied before the bias (0 = 1.0) */
+  int plane_fmt;   /* encoding of x/w/y planes (shineon_plane_fmt) */
   /* outputs (any subset): f32 NHWC and/or bf16 planes NHWC, pixel (n, oh*oh_mul+oh_off, ow*ow_mul+ow_off)
    * of a [N,out_H,out_W,out_cstride] tensor, channels written at out_coffset.. */
   float* y_f32;
@@ -184,7 +192,8 @@ int shineon_conv2d_direct_fwd(const shineon_conv2d_params* p, shineon_stream_t s
 /* NCHW f32 [N,C,H,W] (optionally a second tensor concatenated on C) -> NHWC planes [N,H,W,cpad],
  * with activation applied (unet.py:132 down-activation on the block input). */
 int shineon_nchw_to_planes(const float* x0, int C0, const float* x1, int C1, void* y_hi, void* y_lo, int N,
-                           int H, int W, int cpad, int act, float act_param, shineon_stream_t stream);
+                           int H, int W, int cpad, int act, float act_param, int plane_fmt,
+                           shineon_stream_t stream);
 
 /* nn.InstanceNorm2d(affine=False, eps) over f32 NHWC x [N,H,W,C] (unet.py:133,135) followed by
  * activation; writes any subset of: f32 NHWC y_f32 (may alias x), planes y_hi/y_lo [N,H,W,cpad].
@@ -192,7 +201,7 @@ int shineon_nchw_to_planes(const float* x0, int C0, const float* x1, int C1, voi
  * stats_ws: caller-owned scratch of 2*N*C doubles (sum, sum of squares); zeroed by the call. */
 int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, void* y_lo, double* stats_ws, int N, int H,
                          int W, int C, int cpad, float eps, int do_norm, int act, float act_param,
-                         shineon_stream_t stream);
+                         int plane_fmt, shineon_stream_t stream);
 
 /* Up-path input of a U-Net block (unet.py:138-146): up_act -> cat([skip, x'],C) -> bilinear x2
  * (align_corners=False).  Sources are activated planes [N,H,W,c{0,1}pad]; the extra activation
@@ -200,14 +209,14 @@ int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, void* y_lo, d
  * is applied before interpolation.  Output planes [N,2H,2W,c0pad+c1pad]. src1 may be NULL. */
 int shineon_upsample2x_cat(const void* s0_hi, const void* s0_lo, int c0pad, const void* s1_hi,
                            const void* s1_lo, int c1pad, void* y_hi, void* y_lo, int N, int H, int W,
-                           int act, float act_param, shineon_stream_t stream);
+                           int act, float act_param, int plane_fmt, shineon_stream_t stream);
 
 /* SAGAN self-attention core (sagan.py:29-53) given the fused 1x1 projection
  * qkv f32 NHWC [N,HW,2*Cq+C] (q | k | v) and x f32 NHWC [N,HW,C]:
  * out = act(gamma * (V . softmax(q^T k)^T) + x); writes f32 and/or planes. */
 int shineon_sagan_attention(const float* qkv, const float* x, const float* gamma, float* y_f32, void* y_hi,
                             void* y_lo, int N, int HW, int C, int Cq, int cpad, int act, float act_param,
-                            shineon_stream_t stream);
+                            int plane_fmt, shineon_stream_t stream);
 
 /* ------------------------------------------------------------------ */
 /* GMM glue                                                             */
@@ -217,7 +226,8 @@ int shineon_sagan_attention(const float* qkv, const float* x, const float* gamma
  * out planes [B,h,w,cpad] with channel iA = wA*h + hA (warp.py:60), value = <A/|A|, B/|B|>.
  * corr_f32 (optional) receives the same values as f32 NHWC [B,h,w,h*w]. */
 int shineon_l2norm_correlation(const float* featA, const float* featB, float* corr_f32, void* y_hi,
-                               void* y_lo, int B, int h, int w, int C, int cpad, shineon_stream_t stream);
+                               void* y_lo, int B, int h, int w, int C, int cpad, int plane_fmt,
+                               shineon_stream_t stream);
 
 /* FeatureRegression tail (warp.py:94-99): x f32 NHWC [B,h,w,C] flattened in NCHW order ->
  * Linear(C*h*w -> out_dim) -> tanh.  weight [out_dim, C*h*w], bias [out_dim]; theta [B,out_dim]. */

@@ -14,6 +14,7 @@ c_f = C.c_float
 
 ACT = {None: 0, "none": 0, "relu": 1, "leaky": 2, "gelu": 3, "swish": 4, "sine": 5, "tanh": 6, "sigmoid": 7}
 PAD = {"zeros": 0, "border": 1}
+FMT_BF16, FMT_FP16 = 0, 1
 
 
 class TpsTables(C.Structure):
@@ -26,6 +27,7 @@ class Conv2dParams(C.Structure):
         ("w_hi", c_p), ("w_lo", c_p), ("Cout", c_i), ("kh", c_i), ("kw", c_i), ("stride", c_i), ("pad_h", c_i), ("pad_w", c_i),
         ("Ho", c_i), ("Wo", c_i),
         ("bias", c_p), ("scale", c_p), ("shift", c_p), ("pre_act", c_i), ("post_act", c_i), ("act_param", c_f),
+        ("acc_scale", c_f), ("plane_fmt", c_i),
         ("y_f32", c_p), ("y_hi", c_p), ("y_lo", c_p),
         ("out_H", c_i), ("out_W", c_i), ("out_cstride", c_i), ("out_coffset", c_i),
         ("oh_mul", c_i), ("oh_off", c_i), ("ow_mul", c_i), ("ow_off", c_i),
@@ -50,14 +52,14 @@ SIGNATURES = {
                                       C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i)],
     "shineon_correlation_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_correlation_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
-    "shineon_pack_conv_weight": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p],
+    "shineon_pack_conv_weight": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_f, c_p],
     "shineon_conv2d_igemm_fwd": [C.POINTER(Conv2dParams), c_p],
     "shineon_conv2d_direct_fwd": [C.POINTER(Conv2dParams), c_p],
-    "shineon_nchw_to_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
-    "shineon_instnorm_act": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_f, c_p],
-    "shineon_upsample2x_cat": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
-    "shineon_sagan_attention": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
-    "shineon_l2norm_correlation": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_nchw_to_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
+    "shineon_instnorm_act": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_f, c_i, c_p],
+    "shineon_upsample2x_cat": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
+    "shineon_sagan_attention": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
+    "shineon_l2norm_correlation": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_linear_tanh": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_tom_compose": [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
 }

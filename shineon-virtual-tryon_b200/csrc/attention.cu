@@ -9,8 +9,8 @@ namespace shineon {
 
 __global__ void __launch_bounds__(128)
     sagan_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ x, const float* __restrict__ gamma,
-                           float* __restrict__ yf, __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl,
-                           int HW, int C, int Cq, int cpad, int act, float act_param) {
+                           float* __restrict__ yf, plane_t* __restrict__ yh, plane_t* __restrict__ yl,
+                           int HW, int C, int Cq, int cpad, int act, float act_param, int fmt) {
   extern __shared__ float sm[];  // q[Cq] | e[HW] | red[32]
   float* sq = sm;
   float* se = sm + Cq;
@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(128)
     const float v = apply_act(g * o + x[xi], act, act_param);  // sagan.py:53
     if (yf) yf[xi] = v;
     if (yh) {
-      __nv_bfloat16 h, l;
-      split_bf16(v, h, l);
+      plane_t h, l;
+      split16(v, fmt, h, l);
       const long po = ((long)n * HW + i) * cpad + c;
       yh[po] = h;
       if (yl) yl[po] = l;
@@ -92,7 +92,8 @@ using namespace shineon;
 
 extern "C" int shineon_sagan_attention(const float* qkv, const float* x, const float* gamma, float* y_f32, void* y_hi,
                                        void* y_lo, int N, int HW, int C, int Cq, int cpad, int act, float act_param,
-                                       shineon_stream_t stream) {
+                                       int plane_fmt, shineon_stream_t stream) {
+  SHINEON_REQUIRE(plane_fmt == SHINEON_FMT_BF16 || plane_fmt == SHINEON_FMT_FP16, "sagan_attention: plane_fmt %d", plane_fmt);
   SHINEON_REQUIRE(qkv && x && gamma && (y_f32 || y_hi), "sagan_attention: null pointer");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0 && Cq > 0, "sagan_attention: bad shape");
   SHINEON_REQUIRE(!y_hi || cpad >= C, "sagan_attention: cpad < C");
@@ -100,7 +101,7 @@ extern "C" int shineon_sagan_attention(const float* qkv, const float* x, const f
   if (smem > 48 * 1024) return fail(SHINEON_ERR_UNSUPPORTED, "sagan_attention: HW=%d too large for this kernel", HW);
   SHINEON_REQUIRE(((2 * Cq + C) & 3) == 0 || (Cq & 3) != 0, "sagan_attention: row stride must keep float4 alignment");
   dim3 grid(HW, N);
-  sagan_attention_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(qkv, x, gamma, y_f32, (__nv_bfloat16*)y_hi,
-                                                                   (__nv_bfloat16*)y_lo, HW, C, Cq, cpad, act, act_param);
+  sagan_attention_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(qkv, x, gamma, y_f32, (plane_t*)y_hi,
+                                                                   (plane_t*)y_lo, HW, C, Cq, cpad, act, act_param, plane_fmt);
   return after_launch("sagan_attention_kernel");
 }

@@ -1,6 +1,7 @@
 // Shared helpers for libshineon_b200 (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -56,16 +57,29 @@ __device__ __forceinline__ float apply_act(float v, int act, float param) {
   }
 }
 
-// ---------------------------------------------------------------- bf16 hi/lo planes
-// x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits, so three bf16 tensor-core
-// products (hi*hi + hi*lo + lo*hi) reproduce an fp32 product to ~2^-16 relative.
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+// ---------------------------------------------------------------- 16-bit hi/lo planes
+// x ~= hi + lo with hi = round16(x), lo = round16(x - hi).  Three tensor-core products
+// (hi*hi + hi*lo + lo*hi) then reproduce an fp32 product to ~2^-16 (bf16: 8+8 mantissa bits) or
+// ~2^-21 (fp16: 11+11 bits).  Planes are stored as raw 16-bit words; `fmt` selects the encoding.
+typedef uint16_t plane_t;
+__device__ __forceinline__ void split16(float x, int fmt, plane_t& hi, plane_t& lo) {
+  if (fmt == SHINEON_FMT_FP16) {
+    x = fminf(fmaxf(x, -65000.f), 65000.f);  // fp16 range guard (normalised activations never get close)
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+  }
 }
-__device__ __forceinline__ float join_bf16(__nv_bfloat16 hi, __nv_bfloat16 lo) {
-  return __bfloat162float(hi) + __bfloat162float(lo);
+__device__ __forceinline__ float load16(plane_t v, int fmt) {
+  return fmt == SHINEON_FMT_FP16 ? __half2float(__ushort_as_half(v)) : __bfloat162float(__ushort_as_bfloat16(v));
 }
+__device__ __forceinline__ float join16(plane_t hi, plane_t lo, int fmt) { return load16(hi, fmt) + load16(lo, fmt); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

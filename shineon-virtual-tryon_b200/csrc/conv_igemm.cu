@@ -47,9 +47,12 @@ struct ConvArgs {
   const float* shift;
   int pre_act, post_act;
   float act_param;
+  float acc_scale;   // multiplies the accumulator first (undoes the power-of-two weight scaling of fp16 planes)
+  int fmt;           // plane encoding (SHINEON_FMT_*)
+  uint32_t idesc;    // tcgen05 instruction descriptor for (fmt, BN)
   float* y_f32;
-  __nv_bfloat16* y_hi;
-  __nv_bfloat16* y_lo;
+  plane_t* y_hi;
+  plane_t* y_lo;
   int out_H, out_W, out_cstride, out_coffset;
   int oh_mul, oh_off, ow_mul, ow_off;
 };
@@ -118,12 +121,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A format [7,10), B format [10,13),
 // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// A/B format: 0 = f16, 1 = bf16.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int ab_fmt) {
+  return (1u << 4) | ((uint32_t)ab_fmt << 7) | ((uint32_t)ab_fmt << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -170,7 +175,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ------------------------------------------------------------------------------------- epilogue
 __device__ __forceinline__ float conv_epilogue_value(float acc, int c, const ConvArgs& a) {
-  float v = acc;
+  float v = acc * a.acc_scale;
   if (a.bias) v += __ldg(a.bias + c);
   v = apply_act(v, a.pre_act, a.act_param);
   if (a.scale) v = fmaf(v, __ldg(a.scale + c), __ldg(a.shift + c));
@@ -198,10 +203,10 @@ __device__ __forceinline__ void conv_store_row(const float* vals, int c_first, i
 #pragma unroll
     for (int i = 0; i < 32; i += 8) {
       if (i >= cnt) break;
-      __align__(16) __nv_bfloat16 hi[8];
-      __align__(16) __nv_bfloat16 lo[8];
+      __align__(16) plane_t hi[8];
+      __align__(16) plane_t lo[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) split_bf16(i + j < cnt ? vals[i + j] : 0.f, hi[j], lo[j]);
+      for (int j = 0; j < 8; ++j) split16(i + j < cnt ? vals[i + j] : 0.f, a.fmt, hi[j], lo[j]);
       if (vec) {
         *reinterpret_cast<uint4*>(a.y_hi + base + i) = *reinterpret_cast<const uint4*>(hi);
         if (a.y_lo) *reinterpret_cast<uint4*>(a.y_lo + base + i) = *reinterpret_cast<const uint4*>(lo);
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   constexpr int kPlanes = SPLIT ? 2 : 1;
   constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  constexpr uint32_t kIdesc = umma_idesc_bf16(kBlockM, BN);
+  const uint32_t kIdesc = a.idesc;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
@@ -311,12 +316,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int k = 0; k < kBlockK / 16; ++k) {
           const uint64_t dAh = umma_desc_sw128(sA + k * 32);
           const uint64_t dBh = umma_desc_sw128(sB + k * 32);
-          umma_bf16(tmem_acc, dAh, dBh, kIdesc, (kb | k) != 0);
+          umma_f16(tmem_acc, dAh, dBh, kIdesc, (kb | k) != 0);
           if (SPLIT) {
             const uint64_t dAl = umma_desc_sw128(sA + kABytes + k * 32);
             const uint64_t dBl = umma_desc_sw128(sB + kBBytes + k * 32);
-            umma_bf16(tmem_acc, dAh, dBl, kIdesc, 1);
-            umma_bf16(tmem_acc, dAl, dBh, kIdesc, 1);
+            umma_f16(tmem_acc, dAh, dBl, kIdesc, 1);
+            umma_f16(tmem_acc, dAl, dBh, kIdesc, 1);
           }
         }
         umma_commit(bar_empty + 8 * s);  // frees the smem slot once these MMAs retire
@@ -364,8 +369,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 // Same operands, same epilogue, plain fp32 FMAs.  Tests compare the tcgen05 kernel against this on
 // the GPU at sizes where the CPU oracle would take minutes.  Not on the product path.
 __global__ void __launch_bounds__(128)
-    conv_direct_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
-                       const __nv_bfloat16* __restrict__ wh, const __nv_bfloat16* __restrict__ wl, int H, int W,
+    conv_direct_kernel(const plane_t* __restrict__ xh, const plane_t* __restrict__ xl,
+                       const plane_t* __restrict__ wh, const plane_t* __restrict__ wl, int H, int W,
                        ConvArgs a) {
   const long total = (long)a.N * a.Ho * a.Wo * a.Cout;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
@@ -382,11 +387,11 @@ __global__ void __launch_bounds__(128)
         const long xo = (((long)n * H + iy) * W + ix) * a.cin_pad;
         const long wo = ((long)c * a.kh * a.kw + fy * a.kw + fx) * a.cin_pad;
         for (int ci = 0; ci < a.cin_pad; ++ci) {
-          const float xhv = __bfloat162float(xh[xo + ci]), whv = __bfloat162float(wh[wo + ci]);
+          const float xhv = load16(xh[xo + ci], a.fmt), whv = load16(wh[wo + ci], a.fmt);
           acc = fmaf(xhv, whv, acc);
           if (xl) {
-            acc = fmaf(xhv, __bfloat162float(wl[wo + ci]), acc);
-            acc = fmaf(__bfloat162float(xl[xo + ci]), whv, acc);
+            acc = fmaf(xhv, load16(wl[wo + ci], a.fmt), acc);
+            acc = fmaf(load16(xl[xo + ci], a.fmt), whv, acc);
           }
         }
       }
@@ -396,8 +401,8 @@ __global__ void __launch_bounds__(128)
     const long o = pix * a.out_cstride + a.out_coffset + c;
     if (a.y_f32) a.y_f32[o] = v;
     if (a.y_hi) {
-      __nv_bfloat16 h, l;
-      split_bf16(v, h, l);
+      plane_t h, l;
+      split16(v, a.fmt, h, l);
       a.y_hi[o] = h;
       if (a.y_lo) a.y_lo[o] = l;
     }
@@ -406,9 +411,9 @@ __global__ void __launch_bounds__(128)
 
 // ------------------------------------------------------------------------------- weight packing
 __global__ void __launch_bounds__(256)
-    pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ whi,
-                            __nv_bfloat16* __restrict__ wlo, int Cout, int Cin, int kh, int kw, int cin_pad,
-                            const int32_t* __restrict__ chan_map, int transpose_io) {
+    pack_conv_weight_kernel(const float* __restrict__ w, plane_t* __restrict__ whi,
+                            plane_t* __restrict__ wlo, int Cout, int Cin, int kh, int kw, int cin_pad,
+                            const int32_t* __restrict__ chan_map, int transpose_io, int fmt, float w_scale) {
   const long total = (long)Cout * kh * kw * cin_pad;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const int cp = (int)(e % cin_pad);
@@ -423,8 +428,8 @@ __global__ void __launch_bounds__(256)
       else  // ConvTranspose2d weight [Cin][Cout][kh][kw], taps flipped
         v = w[(((long)ci * Cout + co) * kh + (kh - 1 - fy)) * kw + (kw - 1 - fx)];
     }
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
+    plane_t h, l;
+    split16(v * w_scale, fmt, h, l);
     whi[e] = h;
     if (wlo) wlo[e] = l;
   }
@@ -449,11 +454,11 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box, const char* what) {
+                      const cuuint32_t* box, const char* what, int fmt) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(SHINEON_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found (driver too old?)");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes,
+  CUresult r = fn(tm, fmt == SHINEON_FMT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SHINEON_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed: CUresult %d", what, (int)r);
@@ -489,6 +494,7 @@ static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CU
   if (stages > a.num_kb) stages = a.num_kb;
   if (stages < 1) stages = 1;
   a.stages = stages;
+  a.idesc = umma_idesc_f16(kBlockM, BN, a.fmt == SHINEON_FMT_FP16 ? 0 : 1);
   const int smem = stages * kStageBytes + 1024;
   static int configured_smem = 0;
   if (smem > configured_smem) {
@@ -523,7 +529,11 @@ static int fill_args(const shineon_conv2d_params* p, ConvArgs& a) {
   a.stages = 1;
   a.bias = p->bias; a.scale = p->scale; a.shift = p->shift;
   a.pre_act = p->pre_act; a.post_act = p->post_act; a.act_param = p->act_param;
-  a.y_f32 = p->y_f32; a.y_hi = (__nv_bfloat16*)p->y_hi; a.y_lo = (__nv_bfloat16*)p->y_lo;
+  SHINEON_REQUIRE(p->plane_fmt == SHINEON_FMT_BF16 || p->plane_fmt == SHINEON_FMT_FP16, "conv2d: plane_fmt %d", p->plane_fmt);
+  a.fmt = p->plane_fmt;
+  a.acc_scale = p->acc_scale == 0.f ? 1.f : p->acc_scale;
+  a.idesc = 0;
+  a.y_f32 = p->y_f32; a.y_hi = (plane_t*)p->y_hi; a.y_lo = (plane_t*)p->y_lo;
   a.oh_mul = p->oh_mul ? p->oh_mul : 1; a.ow_mul = p->ow_mul ? p->ow_mul : 1;
   a.oh_off = p->oh_off; a.ow_off = p->ow_off;
   a.out_H = p->out_H ? p->out_H : p->Ho; a.out_W = p->out_W ? p->out_W : p->Wo;
@@ -561,22 +571,22 @@ extern "C" int shineon_conv2d_igemm_fwd(const shineon_conv2d_params* p, shineon_
     cuuint64_t dims[4] = {C, W, H, N};
     cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.nb};
-    if ((rc = encode_map(&tAh, p->x_hi, 4, dims, strides, box, "A hi"))) return rc;
-    if (split && (rc = encode_map(&tAl, p->x_lo, 4, dims, strides, box, "A lo"))) return rc;
+    if ((rc = encode_map(&tAh, p->x_hi, 4, dims, strides, box, "A hi", p->plane_fmt))) return rc;
+    if (split && (rc = encode_map(&tAl, p->x_lo, 4, dims, strides, box, "A lo", p->plane_fmt))) return rc;
   } else {
     cuuint64_t dims[5] = {2 * C, W / 2, 2, H / 2, N};
     cuuint64_t strides[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
     cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)a.bw, 1, (cuuint32_t)a.bh, (cuuint32_t)a.nb};
-    if ((rc = encode_map(&tAh, p->x_hi, 5, dims, strides, box, "A hi s2"))) return rc;
-    if (split && (rc = encode_map(&tAl, p->x_lo, 5, dims, strides, box, "A lo s2"))) return rc;
+    if ((rc = encode_map(&tAh, p->x_hi, 5, dims, strides, box, "A hi s2", p->plane_fmt))) return rc;
+    if (split && (rc = encode_map(&tAl, p->x_lo, 5, dims, strides, box, "A lo s2", p->plane_fmt))) return rc;
   }
   {
     const cuuint64_t K = (cuuint64_t)p->kh * p->kw * C;
     cuuint64_t dims[2] = {K, (cuuint64_t)p->Cout};
     cuuint64_t strides[1] = {K * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)bn};
-    if ((rc = encode_map(&tBh, p->w_hi, 2, dims, strides, box, "B hi"))) return rc;
-    if (split && (rc = encode_map(&tBl, p->w_lo, 2, dims, strides, box, "B lo"))) return rc;
+    if ((rc = encode_map(&tBh, p->w_hi, 2, dims, strides, box, "B hi", p->plane_fmt))) return rc;
+    if (split && (rc = encode_map(&tBl, p->w_lo, 2, dims, strides, box, "B lo", p->plane_fmt))) return rc;
   }
   if (!split) { tAl = tAh; tBl = tBh; }
 
@@ -601,21 +611,23 @@ extern "C" int shineon_conv2d_direct_fwd(const shineon_conv2d_params* p, shineon
   long blocks = (total + 127) / 128;
   if (blocks > 148 * 64) blocks = 148 * 64;
   conv_direct_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)p->x_hi, (const __nv_bfloat16*)p->x_lo, (const __nv_bfloat16*)p->w_hi,
-      (const __nv_bfloat16*)p->w_lo, p->H, p->W, a);
+      (const plane_t*)p->x_hi, (const plane_t*)p->x_lo, (const plane_t*)p->w_hi,
+      (const plane_t*)p->w_lo, p->H, p->W, a);
   return after_launch("conv_direct_kernel");
 }
 
 extern "C" int shineon_pack_conv_weight(const float* w, void* w_hi, void* w_lo, int Cout, int Cin, int kh, int kw,
-                                        int cin_pad, const int32_t* chan_map, int transpose_io,
-                                        shineon_stream_t stream) {
+                                        int cin_pad, const int32_t* chan_map, int transpose_io, int plane_fmt,
+                                        float w_scale, shineon_stream_t stream) {
+  SHINEON_REQUIRE(plane_fmt == SHINEON_FMT_BF16 || plane_fmt == SHINEON_FMT_FP16, "pack_conv_weight: plane_fmt %d", plane_fmt);
+  if (w_scale == 0.f) w_scale = 1.f;
   SHINEON_REQUIRE(w && w_hi, "pack_conv_weight: null pointer");
   SHINEON_REQUIRE(Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && cin_pad >= 1, "pack_conv_weight: bad shape");
   SHINEON_REQUIRE(chan_map != nullptr || cin_pad >= Cin, "pack_conv_weight: cin_pad < Cin");
   long total = (long)Cout * kh * kw * cin_pad;
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  pack_conv_weight_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo,
-                                                                       Cout, Cin, kh, kw, cin_pad, chan_map, transpose_io);
+  pack_conv_weight_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, (plane_t*)w_hi, (plane_t*)w_lo,
+                                                                       Cout, Cin, kh, kw, cin_pad, chan_map, transpose_io, plane_fmt, w_scale);
   return after_launch("pack_conv_weight_kernel");
 }

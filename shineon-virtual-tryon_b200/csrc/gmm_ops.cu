@@ -12,7 +12,7 @@ constexpr int kTK = 32;
 
 __global__ void __launch_bounds__(256)
     l2norm_corr_kernel(const float* __restrict__ fA, const float* __restrict__ fB, float* __restrict__ corr,
-                       __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int h, int w, int C, int cpad) {
+                       plane_t* __restrict__ yh, plane_t* __restrict__ yl, int h, int w, int C, int cpad, int fmt) {
   __shared__ float sA[kTK][kTA + 4];
   __shared__ float sB[kTK][kTB + 4];
   const int P = h * w;
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(256)
       const int iA = wA * h + hA;  // feature_A.transpose(2,3) (warp.py:60)
       if (corr) corr[((long)b * P + pB) * P + iA] = v;
       if (yh) {
-        __nv_bfloat16 hh, ll;
-        split_bf16(v, hh, ll);
+        plane_t hh, ll;
+        split16(v, fmt, hh, ll);
         const long o = ((long)b * P + pB) * cpad + iA;
         yh[o] = hh;
         if (yl) yl[o] = ll;
@@ -107,14 +107,16 @@ __global__ void __launch_bounds__(256)
 using namespace shineon;
 
 extern "C" int shineon_l2norm_correlation(const float* featA, const float* featB, float* corr_f32, void* y_hi,
-                                          void* y_lo, int B, int h, int w, int C, int cpad, shineon_stream_t stream) {
+                                          void* y_lo, int B, int h, int w, int C, int cpad, int plane_fmt,
+                                          shineon_stream_t stream) {
+  SHINEON_REQUIRE(plane_fmt == SHINEON_FMT_BF16 || plane_fmt == SHINEON_FMT_FP16, "l2norm_correlation: plane_fmt %d", plane_fmt);
   SHINEON_REQUIRE(featA && featB && (corr_f32 || y_hi), "l2norm_correlation: null pointer");
   SHINEON_REQUIRE(B > 0 && B <= 65535 && h > 0 && w > 0 && C > 0 && C % 4 == 0, "l2norm_correlation: bad shape (C %% 4)");
   SHINEON_REQUIRE(!y_hi || cpad >= h * w, "l2norm_correlation: cpad < h*w");
   const int P = h * w;
   dim3 grid(cdiv(P, kTA), cdiv(P, kTB), B);
-  l2norm_corr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(featA, featB, corr_f32, (__nv_bfloat16*)y_hi,
-                                                           (__nv_bfloat16*)y_lo, h, w, C, cpad);
+  l2norm_corr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(featA, featB, corr_f32, (plane_t*)y_hi,
+                                                           (plane_t*)y_lo, h, w, C, cpad, plane_fmt);
   return after_launch("l2norm_corr_kernel");
 }
 

@@ -10,16 +10,16 @@ namespace shineon {
 // ------------------------------------------------------------------------------ nchw -> planes
 __global__ void __launch_bounds__(256)
     nchw_to_planes_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
-                          __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int HW, int cpad,
-                          int act, float act_param) {
+                          plane_t* __restrict__ yh, plane_t* __restrict__ yl, int HW, int cpad,
+                          int act, float act_param, int fmt) {
   const int n = blockIdx.y;
   const int groups = (C0 + C1 + 7) / 8;
   const long total = (long)HW * groups;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const int p = (int)(e % HW);  // pixel fastest: coalesced channel-plane reads
     const int g = (int)(e / HW);
-    __align__(16) __nv_bfloat16 hi[8];
-    __align__(16) __nv_bfloat16 lo[8];
+    __align__(16) plane_t hi[8];
+    __align__(16) plane_t lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = g * 8 + j;
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256)
       else if (c < C0 + C1)
         v = x1[((long)n * C1 + (c - C0)) * HW + p];
       v = (c < C0 + C1) ? apply_act(v, act, act_param) : 0.f;
-      split_bf16(v, hi[j], lo[j]);
+      split16(v, fmt, hi[j], lo[j]);
     }
     const long o = ((long)n * HW + p) * cpad + g * 8;
     *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(256)
 // Pass 2: y = act((x - mean) * rsqrt(var + eps)); 4 channels per thread when C % 4 == 0.
 __global__ void __launch_bounds__(256)
     instnorm_apply_kernel(const float* __restrict__ x, const double* __restrict__ ws, float* __restrict__ yf,
-                          __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int HW, int C, int cpad,
-                          float eps, int do_norm, int act, float act_param) {
+                          plane_t* __restrict__ yh, plane_t* __restrict__ yl, int HW, int C, int cpad,
+                          float eps, int do_norm, int act, float act_param, int fmt) {
   extern __shared__ float s_tab[];  // mean[C], rstd[C]
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (j < vecC) {
-          __nv_bfloat16 h, l;
-          split_bf16(v[j], h, l);
+          plane_t h, l;
+          split16(v[j], fmt, h, l);
           yh[po + j] = h;
           if (yl) yl[po + j] = l;
         }
@@ -146,26 +146,26 @@ __device__ __forceinline__ void up2_index(int d, int in_size, int& i0, int& i1, 
   l0 = 1.f - l1;
 }
 
-__device__ __forceinline__ void load8(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ l, long off,
-                                      int act, float act_param, float (&v)[8]) {
+__device__ __forceinline__ void load8(const plane_t* __restrict__ h, const plane_t* __restrict__ l, long off,
+                                      int act, float act_param, int fmt, float (&v)[8]) {
   uint4 uh = *reinterpret_cast<const uint4*>(h + off);
-  const __nv_bfloat16* ph = reinterpret_cast<const __nv_bfloat16*>(&uh);
+  const plane_t* ph = reinterpret_cast<const plane_t*>(&uh);
   if (l) {
     uint4 ul = *reinterpret_cast<const uint4*>(l + off);
-    const __nv_bfloat16* pl = reinterpret_cast<const __nv_bfloat16*>(&ul);
+    const plane_t* pl = reinterpret_cast<const plane_t*>(&ul);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(join_bf16(ph[j], pl[j]), act, act_param);
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(join16(ph[j], pl[j], fmt), act, act_param);
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(__bfloat162float(ph[j]), act, act_param);
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(load16(ph[j], fmt), act, act_param);
   }
 }
 
 __global__ void __launch_bounds__(256)
-    upsample2x_cat_kernel(const __nv_bfloat16* __restrict__ s0h, const __nv_bfloat16* __restrict__ s0l, int c0pad,
-                          const __nv_bfloat16* __restrict__ s1h, const __nv_bfloat16* __restrict__ s1l, int c1pad,
-                          __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int H, int W, int act,
-                          float act_param) {
+    upsample2x_cat_kernel(const plane_t* __restrict__ s0h, const plane_t* __restrict__ s0l, int c0pad,
+                          const plane_t* __restrict__ s1h, const plane_t* __restrict__ s1l, int c1pad,
+                          plane_t* __restrict__ yh, plane_t* __restrict__ yl, int H, int W, int act,
+                          float act_param, int fmt) {
   const int n = blockIdx.y;
   const int ctot = c0pad + c1pad;
   const int groups = ctot / 8;
@@ -180,22 +180,22 @@ __global__ void __launch_bounds__(256)
     up2_index(oy, H, y0, y1, ly0, ly1);
     up2_index(ox, W, x0, x1, lx0, lx1);
     const int c = g * 8;
-    const __nv_bfloat16 *sh, *sl;
+    const plane_t *sh, *sl;
     int cp, cc;
     if (c < c0pad) { sh = s0h; sl = s0l; cp = c0pad; cc = c; } else { sh = s1h; sl = s1l; cp = c1pad; cc = c - c0pad; }
     const long rb = (long)n * H * W;
     float v00[8], v01[8], v10[8], v11[8];
-    load8(sh, sl, (rb + (long)y0 * W + x0) * cp + cc, act, act_param, v00);
-    load8(sh, sl, (rb + (long)y0 * W + x1) * cp + cc, act, act_param, v01);
-    load8(sh, sl, (rb + (long)y1 * W + x0) * cp + cc, act, act_param, v10);
-    load8(sh, sl, (rb + (long)y1 * W + x1) * cp + cc, act, act_param, v11);
-    __align__(16) __nv_bfloat16 hi[8];
-    __align__(16) __nv_bfloat16 lo[8];
+    load8(sh, sl, (rb + (long)y0 * W + x0) * cp + cc, act, act_param, fmt, v00);
+    load8(sh, sl, (rb + (long)y0 * W + x1) * cp + cc, act, act_param, fmt, v01);
+    load8(sh, sl, (rb + (long)y1 * W + x0) * cp + cc, act, act_param, fmt, v10);
+    load8(sh, sl, (rb + (long)y1 * W + x1) * cp + cc, act, act_param, fmt, v11);
+    __align__(16) plane_t hi[8];
+    __align__(16) plane_t lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       // ATen: h0lambda*(w0lambda*p00 + w1lambda*p01) + h1lambda*(w0lambda*p10 + w1lambda*p11)
       float v = ly0 * (lx0 * v00[j] + lx1 * v01[j]) + ly1 * (lx0 * v10[j] + lx1 * v11[j]);
-      split_bf16(v, hi[j], lo[j]);
+      split16(v, fmt, hi[j], lo[j]);
     }
     const long o = ((long)n * Ho * Wo + p) * ctot + c;
     *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
@@ -241,23 +241,27 @@ static inline int grid_x(long total, int threads) {
 
 using namespace shineon;
 
+#define SHINEON_REQUIRE_FMT(f, who) SHINEON_REQUIRE((f) == SHINEON_FMT_BF16 || (f) == SHINEON_FMT_FP16, who ": plane_fmt %d", (f))
+
 extern "C" int shineon_nchw_to_planes(const float* x0, int C0, const float* x1, int C1, void* y_hi, void* y_lo,
-                                      int N, int H, int W, int cpad, int act, float act_param,
+                                      int N, int H, int W, int cpad, int act, float act_param, int plane_fmt,
                                       shineon_stream_t stream) {
+  SHINEON_REQUIRE_FMT(plane_fmt, "nchw_to_planes");
   SHINEON_REQUIRE(x0 && y_hi && C0 > 0, "nchw_to_planes: null pointer");
   SHINEON_REQUIRE((x1 == nullptr) == (C1 == 0), "nchw_to_planes: x1/C1 mismatch");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "nchw_to_planes: bad shape");
   SHINEON_REQUIRE(cpad % 8 == 0 && cpad >= C0 + C1, "nchw_to_planes: cpad %d too small / not a multiple of 8", cpad);
   const int HW = H * W;
   dim3 grid(grid_x((long)HW * ((C0 + C1 + 7) / 8), 256), N);
-  nchw_to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo,
-                                                               HW, cpad, act, act_param);
+  nchw_to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo,
+                                                               HW, cpad, act, act_param, plane_fmt);
   return after_launch("nchw_to_planes_kernel");
 }
 
 extern "C" int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, void* y_lo, double* stats_ws, int N,
                                     int H, int W, int C, int cpad, float eps, int do_norm, int act, float act_param,
-                                    shineon_stream_t stream_) {
+                                    int plane_fmt, shineon_stream_t stream_) {
+  SHINEON_REQUIRE_FMT(plane_fmt, "instnorm_act");
   SHINEON_REQUIRE(x && (y_f32 || y_hi), "instnorm_act: null pointer");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && C > 0, "instnorm_act: bad shape");
   SHINEON_REQUIRE(!do_norm || stats_ws, "instnorm_act: stats_ws required");
@@ -286,15 +290,16 @@ extern "C" int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, vo
   }
   const int vecC = (C % 4 == 0) ? 4 : 1;
   dim3 grid(grid_x((long)HW * (C / vecC), 256), N);
-  instnorm_apply_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(x, stats_ws, y_f32, (__nv_bfloat16*)y_hi,
-                                                                     (__nv_bfloat16*)y_lo, HW, C, cpad, eps, do_norm,
-                                                                     act, act_param);
+  instnorm_apply_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(x, stats_ws, y_f32, (plane_t*)y_hi,
+                                                                     (plane_t*)y_lo, HW, C, cpad, eps, do_norm,
+                                                                     act, act_param, plane_fmt);
   return after_launch("instnorm_apply_kernel");
 }
 
 extern "C" int shineon_upsample2x_cat(const void* s0_hi, const void* s0_lo, int c0pad, const void* s1_hi,
                                       const void* s1_lo, int c1pad, void* y_hi, void* y_lo, int N, int H, int W,
-                                      int act, float act_param, shineon_stream_t stream) {
+                                      int act, float act_param, int plane_fmt, shineon_stream_t stream) {
+  SHINEON_REQUIRE_FMT(plane_fmt, "upsample2x_cat");
   SHINEON_REQUIRE(s0_hi && y_hi, "upsample2x_cat: null pointer");
   SHINEON_REQUIRE((s1_hi == nullptr) == (c1pad == 0), "upsample2x_cat: s1/c1pad mismatch");
   SHINEON_REQUIRE((s0_lo == nullptr) == (y_lo == nullptr), "upsample2x_cat: lo planes must be all present or all absent");
@@ -303,8 +308,8 @@ extern "C" int shineon_upsample2x_cat(const void* s0_hi, const void* s0_lo, int 
   SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "upsample2x_cat: bad shape");
   dim3 grid(grid_x((long)4 * H * W * ((c0pad + c1pad) / 8), 256), N);
   upsample2x_cat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)s0_hi, (const __nv_bfloat16*)s0_lo, c0pad, (const __nv_bfloat16*)s1_hi,
-      (const __nv_bfloat16*)s1_lo, c1pad, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, H, W, act, act_param);
+      (const plane_t*)s0_hi, (const plane_t*)s0_lo, c0pad, (const plane_t*)s1_hi,
+      (const plane_t*)s1_lo, c1pad, (plane_t*)y_hi, (plane_t*)y_lo, H, W, act, act_param, plane_fmt);
   return after_launch("upsample2x_cat_kernel");
 }
 

@@ -43,19 +43,20 @@ class UnetMaskModel(BaseModel):
         # VGGLoss (criterionVGG, unet_mask_model.py:61) is training-only and out of this build's scope
         init_weights(self.unet, init_type="normal")
 
-    def set_precision(self, split):
-        self.unet.split_precision = split
+    def set_precision(self, precision):
+        """One of ops.PRECISIONS: "fp16x3" (default, fp32-grade), "bf16x3", "fp16", "bf16" (fast modes)."""
+        self.unet.precision = precision
 
     def forward(self, person_representation, warped_cloths, flows=None, prev_im=None):
         """-> (p_rendereds, tryon_masks, p_tryons, flow_masks)  (unet_mask_model.py:64-135)."""
         n = self.hparams.n_frames_total
         flow_warp = bool(self.hparams.flow_warp)
-        split = self.unet.split_precision
+        prec = ops.resolve_precision(self.unet.precision)
         person_representation = person_representation.contiguous()
         warped_cloths = warped_cloths.contiguous()
         # torch.cat([person, cloth], 1) is fused into the NCHW -> NHWC-planes conversion
-        x = ops.nchw_to_planes(person_representation, warped_cloths, split=split)
-        out = self.unet.model.run(x, split)  # f32 NHWC [B,H,W,(4|5)n]
+        x = ops.nchw_to_planes(person_representation, warped_cloths, prec=prec)
+        out = self.unet.model.run(x, prec)  # f32 NHWC [B,H,W,(4|5)n]
         B, H, W, _ = out.shape
         dev = out.device
         p_rendereds = torch.empty(B, 3 * n, H, W, device=dev)

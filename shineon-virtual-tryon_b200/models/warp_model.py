@@ -33,19 +33,19 @@ class WarpModel(BaseModel):
         self.correlation = FeatureCorrelation()
         self.regression = FeatureRegression(input_nc=192, output_dim=2 * hparams.grid_size ** 2)
         self.gridGen = TpsGridGen(hparams.fine_height, hparams.fine_width, grid_size=hparams.grid_size)
-        self.split_precision = True
+        self.precision = None
 
-    def set_precision(self, split):
-        """True: bf16x3 products (fp32-grade, parity mode).  False: single bf16 products (fast mode)."""
-        self.split_precision = split
-        self.extractionA.split_precision = split
-        self.extractionB.split_precision = split
-        self.regression.split_precision = split
+    def set_precision(self, precision):
+        """One of ops.PRECISIONS: "fp16x3" (default, fp32-grade), "bf16x3", "fp16", "bf16" (fast modes)."""
+        self.precision = precision
+        self.extractionA.precision = precision
+        self.extractionB.precision = precision
+        self.regression.precision = precision
 
     def regress_theta(self, inputA, inputB):
         featureA = self.extractionA.forward_nhwc(inputA)
         featureB = self.extractionB.forward_nhwc(inputB)
-        _, corr = self.correlation.forward_fused(featureA, featureB, split=self.split_precision)
+        _, corr = self.correlation.forward_fused(featureA, featureB, prec=ops.resolve_precision(self.precision))
         return self.regression.forward_planes(corr)
 
     def forward(self, inputA, inputB):

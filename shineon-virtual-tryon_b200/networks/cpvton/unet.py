@@ -39,15 +39,14 @@ class UnetGenerator(nn.Module):
         unet_block = UnetSkipConnectionBlock(output_nc, ngf, input_nc=input_nc, submodule=unet_block, outermost=True,
                                              norm_layer=norm_layer, self_attn=attn(), activation=activation)
         self.model = unet_block
-        self.split_precision = True  # bf16x3 products (fp32-grade); False = single bf16 (fast mode)
+        self.precision = None  # ops.PRECISIONS name; None = default fp16x3 (fp32-grade products)
 
     def forward_nhwc(self, input):
         """input: f32 NCHW CUDA tensor -> f32 NHWC [N,H,W,output_nc]."""
         require_cuda(self, "UnetGenerator")
-        split = self.split_precision
-        blk = self.model
-        x = ops.nchw_to_planes(input.contiguous(), split=split)
-        return blk.run(x, split)
+        prec = ops.resolve_precision(self.precision)
+        x = ops.nchw_to_planes(input.contiguous(), prec=prec)
+        return self.model.run(x, prec)
 
     def forward(self, input):
         return self.forward_nhwc(input).permute(0, 3, 1, 2).contiguous()
@@ -103,17 +102,17 @@ class UnetSkipConnectionBlock(nn.Module):
         self._packed = None
 
     # ------------------------------------------------------------------ engine
-    def _pack(self, split):
+    def _pack(self, prec):
         sig = (params_signature(self._parts["downconv"]) + params_signature(self._parts["upconv"])
                + params_signature(self._parts["upnorm"])
-               + (params_signature(self._parts["downnorm"]) if self._parts["downnorm"] is not None else ()), split)
+               + (params_signature(self._parts["downnorm"]) if self._parts["downnorm"] is not None else ()), prec)
         if self._packed is not None and self._packed[0] == sig:
             return self._packed[1]
         pr = self._parts
         dc, uc = pr["downconv"], pr["upconv"]
         sub = pr["sub"]
         d = {}
-        d["down"] = ops.PackedConv(dc.weight, dc.bias, stride=2, pad=1, split=split)
+        d["down"] = ops.PackedConv(dc.weight, dc.bias, stride=2, pad=1, prec=prec)
         if sub is not None:
             # up-conv input channels: [skip (sub input, padded to 64) | x' (sub output, padded to 64)]
             c_skip = sub._parts["downconv"].in_channels
@@ -124,10 +123,10 @@ class UnetSkipConnectionBlock(nn.Module):
                 cmap[c] = c
             for c in range(c_xp):
                 cmap[p_skip + c] = c_skip + c
-            d["up"] = ops.PackedConv(uc.weight, uc.bias, stride=1, pad=1, split=split, cin_pad=p_skip + p_xp,
+            d["up"] = ops.PackedConv(uc.weight, uc.bias, stride=1, pad=1, prec=prec, cin_pad=p_skip + p_xp,
                                      chan_map=cmap)
         else:
-            d["up"] = ops.PackedConv(uc.weight, uc.bias, stride=1, pad=1, split=split)
+            d["up"] = ops.PackedConv(uc.weight, uc.bias, stride=1, pad=1, prec=prec)
         for key, norm in (("down_bn", pr["downnorm"]), ("up_bn", pr["upnorm"])):
             d[key] = None
             if isinstance(norm, nn.BatchNorm2d):
@@ -139,7 +138,7 @@ class UnetSkipConnectionBlock(nn.Module):
         self._packed = (sig, d)
         return d
 
-    def _finish(self, conv_f32, norm, bn, attn, act, act_param, split, want_final_f32=False):
+    def _finish(self, conv_f32, norm, bn, attn, act, act_param, prec, want_final_f32=False):
         """conv output (f32 NHWC, bias [and folded BN] applied) -> [InstanceNorm] -> [SelfAttention] -> act.
         Returns Planes of the activated value, or the final f32 tensor when want_final_f32."""
         inorm = isinstance(norm, nn.InstanceNorm2d)
@@ -149,22 +148,22 @@ class UnetSkipConnectionBlock(nn.Module):
                                         want_f32=True, want_planes=False, out_f32=conv_f32)
                 return y
             _, p = ops.instnorm_act(conv_f32, do_norm=inorm, eps=norm.eps if inorm else 1e-5, act=act,
-                                    act_param=act_param, want_f32=False, want_planes=True, split=split)
+                                    act_param=act_param, want_f32=False, want_planes=True, prec=prec)
             return p
         # attention works on the normalised, un-activated tensor: needs it as f32 (residual) and planes (qkv conv)
         y, p = ops.instnorm_act(conv_f32, do_norm=inorm, eps=norm.eps if inorm else 1e-5, act=None, want_f32=True,
-                                want_planes=True, split=split, out_f32=conv_f32)
+                                want_planes=True, prec=prec, out_f32=conv_f32)
         if want_final_f32:
             return attn.run(y, p, want_f32=True, want_planes=False)[0]
         return attn.run(y, p, act=act, act_param=act_param, want_f32=False, want_planes=True)[1]
 
-    def run(self, a_in, split):
+    def run(self, a_in, prec):
         """a_in: Planes holding this block's (already down-activated) input.
         Outermost: returns f32 NHWC output.  Otherwise returns Planes of up_act(x') for the parent."""
         pr = self._parts
         if self.training and pr["dropout"]:
             raise NotImplementedError("Dropout in training mode is not implemented in the native U-Net engine")
-        pk = self._pack(split)
+        pk = self._pack(prec)
         sub = pr["sub"]
         up_act, up_par = act_name(pr["up_act"])
         # ---- down path: conv -> [norm] -> [attn] -> activation consumed next
@@ -175,12 +174,12 @@ class UnetSkipConnectionBlock(nn.Module):
         bn = pk["down_bn"]
         sc, sh = bn if bn is not None else (None, None)
         f32, _ = ops.conv2d(a_in, pk["down"], scale=sc, shift=sh, want_f32=True)
-        a_mid = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, split)
+        a_mid = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, prec)
         # ---- child + up-path input
         if self.innermost:
             u = ops.upsample2x_cat(a_mid, None)
         else:
-            xp = sub.run(a_mid, split)
+            xp = sub.run(a_mid, prec)
             # default activation: the skip holds LeakyReLU'd values (in-place, unet.py:132) and the parent's
             # ReLU is applied on top when reading it (relu(leaky(x)) == relu(x)); x' is already ReLU'd (idempotent)
             extra = "relu" if pr["default_act"] else None
@@ -189,8 +188,8 @@ class UnetSkipConnectionBlock(nn.Module):
         sc, sh = bn if bn is not None else (None, None)
         f32, _ = ops.conv2d(u, pk["up"], scale=sc, shift=sh, want_f32=True)
         if self.outermost:
-            return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], None, 0.0, split, want_final_f32=True)
-        return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], up_act, up_par, split)
+            return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], None, 0.0, prec, want_final_f32=True)
+        return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], up_act, up_par, prec)
 
     def forward(self, x):
         raise NotImplementedError(

@@ -36,10 +36,10 @@ class FeatureExtraction(nn.Module):
         self.model = nn.Sequential(*model)
         init_weights(self.model, init_type="normal")
         self._packed = None
-        self.split_precision = True
+        self.precision = None
 
-    def _layers(self, split):
-        sig = (params_signature(self), split)
+    def _layers(self, prec):
+        sig = (params_signature(self), prec)
         if self._packed is not None and self._packed[0] == sig:
             return self._packed[1]
         require_cuda(self, "FeatureExtraction")
@@ -53,7 +53,7 @@ class FeatureExtraction(nn.Module):
             if bn is not None and not isinstance(bn, nn.BatchNorm2d):
                 raise NotImplementedError(f"FeatureExtraction norm {type(bn).__name__} has no native kernel")
             sc, sh = fold_bn(bn) if bn is not None else (None, None)
-            pc = ops.PackedConv(conv.weight, conv.bias, stride=conv.stride[0], pad=conv.padding[0], split=split)
+            pc = ops.PackedConv(conv.weight, conv.bias, stride=conv.stride[0], pad=conv.padding[0], prec=prec)
             layers.append((pc, sc, sh))
             i += 3
         self._packed = (sig, layers)
@@ -61,9 +61,9 @@ class FeatureExtraction(nn.Module):
 
     def forward_nhwc(self, x):
         """x f32 NCHW -> f32 NHWC features (conv -> ReLU -> BN ... conv -> ReLU, warp.py:13-31)."""
-        split = self.split_precision
-        layers = self._layers(split)
-        a = ops.nchw_to_planes(x.contiguous(), split=split)
+        prec = ops.resolve_precision(self.precision)
+        layers = self._layers(prec)
+        a = ops.nchw_to_planes(x.contiguous(), prec=prec)
         for li, (pc, sc, sh) in enumerate(layers):
             last = li == len(layers) - 1
             f32, a = ops.conv2d(a, pc, scale=sc, shift=sh, pre_act="relu", want_f32=last, want_planes=not last)
@@ -84,9 +84,9 @@ class FeatureL2Norm(nn.Module):
 
 
 class FeatureCorrelation(nn.Module):
-    def forward_fused(self, fa_nhwc, fb_nhwc, split=True, want_f32=False):
+    def forward_fused(self, fa_nhwc, fb_nhwc, prec=None, want_f32=False):
         """FeatureL2Norm x2 + FeatureCorrelation (warp.py:39-67) on f32 NHWC features."""
-        return ops.l2norm_correlation(fa_nhwc, fb_nhwc, want_f32=want_f32, want_planes=True, split=split)
+        return ops.l2norm_correlation(fa_nhwc, fb_nhwc, want_f32=want_f32, want_planes=True, prec=prec)
 
     def forward(self, feature_A, feature_B):
         raise NotImplementedError(
@@ -106,10 +106,10 @@ class FeatureRegression(nn.Module):
         self.linear = nn.Linear(64 * 4 * 3, output_dim)
         self.tanh = nn.Tanh()
         self._packed = None
-        self.split_precision = True
+        self.precision = None
 
-    def _layers(self, split):
-        sig = (params_signature(self), split)
+    def _layers(self, prec):
+        sig = (params_signature(self), prec)
         if self._packed is not None and self._packed[0] == sig:
             return self._packed[1]
         require_cuda(self, "FeatureRegression")
@@ -119,13 +119,13 @@ class FeatureRegression(nn.Module):
             conv, bn = mods[i], mods[i + 1]
             sc, sh = fold_bn(bn)
             layers.append((ops.PackedConv(conv.weight, conv.bias, stride=conv.stride[0], pad=conv.padding[0],
-                                          split=split), sc, sh))
+                                          prec=prec), sc, sh))
         self._packed = (sig, layers)
         return layers
 
     def forward_planes(self, corr_planes):
         """corr_planes: Planes [B,16,12,192] -> theta [B, output_dim] (warp.py:94-99)."""
-        layers = self._layers(corr_planes.lo is not None)
+        layers = self._layers(corr_planes.prec)
         a = corr_planes
         for li, (pc, sc, sh) in enumerate(layers):
             last = li == len(layers) - 1
@@ -133,7 +133,7 @@ class FeatureRegression(nn.Module):
         return ops.linear_tanh(f32, self.linear.weight.detach(), self.linear.bias.detach())
 
     def forward(self, x):
-        return self.forward_planes(ops.nchw_to_planes(x.contiguous(), split=self.split_precision))
+        return self.forward_planes(ops.nchw_to_planes(x.contiguous(), prec=ops.resolve_precision(self.precision)))
 
 
 class TpsGridGen(nn.Module):

@@ -13,7 +13,7 @@ _TAPS = {0: [3, 1], 1: [2, 0]}
 
 
 class PackedDeconv4x4s2:
-    def __init__(self, weight, bias=None, cin_pad=None, split=True, chan_map=None):
+    def __init__(self, weight, bias=None, cin_pad=None, prec=None, chan_map=None):
         # weight: [Cin, Cout, 4, 4] (nn.ConvTranspose2d layout)
         assert weight.shape[2] == 4 and weight.shape[3] == 4
         self.Cout = weight.shape[1]
@@ -22,7 +22,7 @@ class PackedDeconv4x4s2:
         for py in (0, 1):
             for px in (0, 1):
                 wk = w[:, :, _TAPS[py]][:, :, :, _TAPS[px]].contiguous()
-                pc = ops.PackedConv(wk, bias, stride=1, pad_hw=(1 - py, 1 - px), cin_pad=cin_pad, split=split,
+                pc = ops.PackedConv(wk, bias, stride=1, pad_hw=(1 - py, 1 - px), cin_pad=cin_pad, prec=prec,
                                     chan_map=chan_map)
                 self.phases.append((py, px, pc))
 
@@ -33,7 +33,7 @@ class PackedDeconv4x4s2:
         if want_f32 and out_f32 is None:
             out_f32 = torch.empty(N, 2 * H, 2 * W, self.Cout, dtype=torch.float32, device=dev)
         if want_planes and out_planes is None:
-            out_planes = ops.Planes(N, 2 * H, 2 * W, self.Cout, split=x.lo is not None, device=dev)
+            out_planes = ops.Planes(N, 2 * H, 2 * W, self.Cout, prec=x.prec, device=dev)
         for py, px, pc in self.phases:
             ops.conv2d(x, pc, post_act=post_act, act_param=act_param, out_f32=out_f32, out_planes=out_planes,
                        out_coffset=out_coffset, out_geom=(2 * H, 2 * W, 2, py, 2, px), out_hw=(H, W))

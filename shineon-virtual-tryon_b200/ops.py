@@ -10,6 +10,11 @@ from . import _lib
 from ._lib import ACT, PAD, Conv2dParams, TpsTables, check
 
 
+# When set to a list, conv2d() brackets every tensor-core conv launch with CUDA events on the launching stream
+# and appends (algorithmic_flops, start_event, end_event); bench.py uses it for the roofline of the dominant kernel.
+PROFILE = None
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -32,14 +37,44 @@ def cpad64(c):
     return (c + 63) // 64 * 64
 
 
-class Planes:
-    """NHWC activation as bf16 hi (+ lo) planes [N,H,W,cpad]; x ~= hi + lo."""
+# Numeric modes of the tensor-core path: name -> (plane format, hi/lo split)
+PRECISIONS = {
+    "fp16x3": (_lib.FMT_FP16, True),   # default: 22 mantissa bits per operand, 3 MMAs per K-slice (fp32-grade)
+    "bf16x3": (_lib.FMT_BF16, True),   # range-safe variant: 16 mantissa bits per operand
+    "fp16": (_lib.FMT_FP16, False),    # single products (fast modes)
+    "bf16": (_lib.FMT_BF16, False),
+}
+DEFAULT_PRECISION = "fp16x3"
 
-    def __init__(self, N, H, W, C, split=True, device="cuda", cpad=None):
+
+def resolve_precision(p):
+    """Accepts a mode name, a (fmt, split) pair, or the legacy bool (True = default split mode, False = bf16)."""
+    if p is None or p is True:
+        p = DEFAULT_PRECISION
+    elif p is False:
+        p = "bf16"
+    if isinstance(p, str):
+        return PRECISIONS[p]
+    return p
+
+
+_DTYPES = {_lib.FMT_BF16: torch.bfloat16, _lib.FMT_FP16: torch.float16}
+
+
+class Planes:
+    """NHWC activation as 16-bit hi (+ lo) planes [N,H,W,cpad]; x ~= hi + lo."""
+
+    def __init__(self, N, H, W, C, prec=None, device="cuda", cpad=None):
+        self.fmt, split = resolve_precision(prec)
         self.N, self.H, self.W, self.C = N, H, W, C
         self.cpad = cpad64(C) if cpad is None else cpad
-        self.hi = torch.zeros(N, H, W, self.cpad, dtype=torch.bfloat16, device=device)
-        self.lo = torch.zeros_like(self.hi) if split else None
+        alloc = torch.empty if self.cpad == C else torch.zeros  # padding channels must stay zero
+        self.hi = alloc(N, H, W, self.cpad, dtype=_DTYPES[self.fmt], device=device)
+        self.lo = alloc(N, H, W, self.cpad, dtype=_DTYPES[self.fmt], device=device) if split else None
+
+    @property
+    def prec(self):
+        return (self.fmt, self.lo is not None)
 
     def float(self):
         """Reconstructed f32 NCHW tensor (debug / tests)."""
@@ -174,8 +209,9 @@ def correlation_bwd(in1, in2, grad_out, pad_size, kernel_size, max_displacement,
 class PackedConv:
     """Conv2d / ConvTranspose2d weight repacked to [Cout][kh*kw][cin_pad] bf16 hi/lo on the device."""
 
-    def __init__(self, weight, bias=None, stride=1, pad=0, cin_pad=None, split=True, chan_map=None,
+    def __init__(self, weight, bias=None, stride=1, pad=0, cin_pad=None, prec=None, chan_map=None,
                  transposed=False, pad_hw=None):
+        self.fmt, split = resolve_precision(prec)
         weight = _req(weight.detach().float().contiguous(), name="weight")
         if transposed:
             Cin, Cout, kh, kw = weight.shape
@@ -187,14 +223,24 @@ class PackedConv:
             cin_pad = cpad64(Cin)
         self.cin_pad = cin_pad
         dev = weight.device
-        self.w_hi = torch.empty(Cout, kh * kw, cin_pad, dtype=torch.bfloat16, device=dev)
+        self.w_hi = torch.empty(Cout, kh * kw, cin_pad, dtype=_DTYPES[self.fmt], device=dev)
         self.w_lo = torch.empty_like(self.w_hi) if split else None
+        # fp16 planes: scale the weights by a power of two so hi/lo stay out of the fp16 subnormal range; the
+        # conv epilogue multiplies the accumulator by the exact inverse (acc_scale).
+        w_scale = 1.0
+        if self.fmt == _lib.FMT_FP16:
+            amax = float(weight.abs().max())
+            if amax > 0:
+                import math
+
+                w_scale = 2.0 ** math.floor(math.log2(16384.0 / amax))
+        self.acc_scale = 1.0 / w_scale
         cm = None
         if chan_map is not None:
             cm = torch.as_tensor(chan_map, dtype=torch.int32, device=dev).contiguous()
             assert cm.numel() == cin_pad
         check(_lib.load().shineon_pack_conv_weight(_p(weight), _p(self.w_hi), _p(self.w_lo), Cout, Cin, kh, kw,
-                                                   cin_pad, _p(cm), int(transposed), _stream()),
+                                                   cin_pad, _p(cm), int(transposed), self.fmt, w_scale, _stream()),
               "shineon_pack_conv_weight")
         self.bias = None if bias is None else _req(bias.detach().float().contiguous(), name="bias")
         self.transposed = transposed
@@ -210,7 +256,7 @@ def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_pa
     """
     N, H, W = x.N, x.H, x.W
     assert x.cpad == pc.cin_pad, f"activation cpad {x.cpad} != packed cin_pad {pc.cin_pad}"
-    assert (x.lo is None) == (pc.w_lo is None), "split mode of activation and weights must agree"
+    assert (x.lo is None) == (pc.w_lo is None) and x.fmt == pc.fmt, "precision of activation and weights must agree"
     if out_hw is not None:
         Ho, Wo = out_hw
     else:
@@ -221,7 +267,7 @@ def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_pa
     if want_f32 and out_f32 is None:
         out_f32 = torch.empty(N, oH, oW, pc.Cout, dtype=torch.float32, device=dev)
     if want_planes and out_planes is None:
-        out_planes = Planes(N, oH, oW, pc.Cout, split=x.lo is not None, device=dev)
+        out_planes = Planes(N, oH, oW, pc.Cout, prec=x.prec, device=dev)
     p = Conv2dParams()
     p.x_hi, p.x_lo = _p(x.hi), _p(x.lo)
     p.N, p.H, p.W, p.cin_pad = N, H, W, x.cpad
@@ -230,6 +276,7 @@ def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_pa
     p.Ho, p.Wo = Ho, Wo
     p.bias, p.scale, p.shift = _p(pc.bias), _p(scale), _p(shift)
     p.pre_act, p.post_act, p.act_param = ACT[pre_act], ACT[post_act], float(act_param)
+    p.acc_scale, p.plane_fmt = pc.acc_scale, pc.fmt
     p.y_f32 = _p(out_f32)
     p.y_hi = _p(out_planes.hi if out_planes is not None else None)
     p.y_lo = _p(out_planes.lo if out_planes is not None else None)
@@ -243,12 +290,19 @@ def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_pa
     p.oh_mul, p.oh_off, p.ow_mul, p.ow_off = ohm, oho, owm, owo
     p.tile_n, p.stages = tile_n, stages
     fn = _lib.load().shineon_conv2d_direct_fwd if direct else _lib.load().shineon_conv2d_igemm_fwd
+    prof = PROFILE
+    if prof is not None and not direct:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(fn(C.byref(p), _stream()), "shineon_conv2d_direct_fwd" if direct else "shineon_conv2d_igemm_fwd")
+    if prof is not None and not direct:
+        e1.record()
+        prof.append((2.0 * N * Ho * Wo * pc.Cout * pc.kh * pc.kw * pc.Cin, e0, e1))
     return out_f32, out_planes
 
 
 # ----------------------------------------------------------------------------- layout / norm / pointwise
-def nchw_to_planes(x0, x1=None, act=None, act_param=0.0, split=True, out=None):
+def nchw_to_planes(x0, x1=None, act=None, act_param=0.0, prec=None, out=None):
     x0 = _req(x0, name="x0")
     N, C0, H, W = x0.shape
     C1 = 0
@@ -256,27 +310,28 @@ def nchw_to_planes(x0, x1=None, act=None, act_param=0.0, split=True, out=None):
         x1 = _req(x1, name="x1")
         C1 = x1.shape[1]
     if out is None:
-        out = Planes(N, H, W, C0 + C1, split=split, device=x0.device)
+        out = Planes(N, H, W, C0 + C1, prec=prec, device=x0.device)
     check(_lib.load().shineon_nchw_to_planes(_p(x0), C0, _p(x1), C1, _p(out.hi), _p(out.lo), N, H, W, out.cpad,
-                                             ACT[act], float(act_param), _stream()), "shineon_nchw_to_planes")
+                                             ACT[act], float(act_param), out.fmt, _stream()), "shineon_nchw_to_planes")
     return out
 
 
 def instnorm_act(x, *, do_norm=True, act=None, act_param=0.0, eps=1e-5, want_f32=False, want_planes=True,
-                 split=True, out_f32=None, out_planes=None, ws=None):
+                 prec=None, out_f32=None, out_planes=None, ws=None):
     """x: f32 NHWC [N,H,W,C]."""
     x = _req(x, name="x")
     N, H, W, Cc = x.shape
     if want_f32 and out_f32 is None:
         out_f32 = torch.empty_like(x)
     if want_planes and out_planes is None:
-        out_planes = Planes(N, H, W, Cc, split=split, device=x.device)
+        out_planes = Planes(N, H, W, Cc, prec=prec, device=x.device)
     if ws is None and do_norm:
         ws = torch.empty(N * Cc * 2, dtype=torch.float64, device=x.device)
     check(_lib.load().shineon_instnorm_act(_p(x), _p(out_f32), _p(out_planes.hi if out_planes else None),
                                            _p(out_planes.lo if out_planes else None), _p(ws), N, H, W, Cc,
                                            out_planes.cpad if out_planes else Cc, float(eps), int(bool(do_norm)),
-                                           ACT[act], float(act_param), _stream()), "shineon_instnorm_act")
+                                           ACT[act], float(act_param), out_planes.fmt if out_planes else 0,
+                                           _stream()), "shineon_instnorm_act")
     return out_f32, out_planes
 
 
@@ -284,15 +339,14 @@ def upsample2x_cat(s0, s1=None, act=None, act_param=0.0, out=None):
     N, H, W = s0.N, s0.H, s0.W
     c1pad = s1.cpad if s1 is not None else 0
     if out is None:
-        out = Planes(N, 2 * H, 2 * W, s0.cpad + c1pad, split=s0.lo is not None, device=s0.hi.device,
-                     cpad=s0.cpad + c1pad)
+        out = Planes(N, 2 * H, 2 * W, s0.cpad + c1pad, prec=s0.prec, device=s0.hi.device, cpad=s0.cpad + c1pad)
     check(_lib.load().shineon_upsample2x_cat(_p(s0.hi), _p(s0.lo), s0.cpad, _p(s1.hi if s1 else None),
                                              _p(s1.lo if s1 else None), c1pad, _p(out.hi), _p(out.lo), N, H, W,
-                                             ACT[act], float(act_param), _stream()), "shineon_upsample2x_cat")
+                                             ACT[act], float(act_param), s0.fmt, _stream()), "shineon_upsample2x_cat")
     return out
 
 
-def sagan_attention(qkv, x, gamma, Cq, *, act=None, act_param=0.0, want_f32=False, want_planes=True, split=True,
+def sagan_attention(qkv, x, gamma, Cq, *, act=None, act_param=0.0, want_f32=False, want_planes=True, prec=None,
                     out_f32=None, out_planes=None):
     """qkv: f32 NHWC [N,H,W,2*Cq+C]; x: f32 NHWC [N,H,W,C]."""
     qkv, x, gamma = _req(qkv), _req(x), _req(gamma)
@@ -301,24 +355,24 @@ def sagan_attention(qkv, x, gamma, Cq, *, act=None, act_param=0.0, want_f32=Fals
     if want_f32 and out_f32 is None:
         out_f32 = torch.empty_like(x)
     if want_planes and out_planes is None:
-        out_planes = Planes(N, H, W, Cc, split=split, device=x.device)
+        out_planes = Planes(N, H, W, Cc, prec=prec, device=x.device)
     check(_lib.load().shineon_sagan_attention(_p(qkv), _p(x), _p(gamma), _p(out_f32),
                                               _p(out_planes.hi if out_planes else None),
                                               _p(out_planes.lo if out_planes else None), N, H * W, Cc, Cq,
                                               out_planes.cpad if out_planes else Cc, ACT[act], float(act_param),
-                                              _stream()), "shineon_sagan_attention")
+                                              out_planes.fmt if out_planes else 0, _stream()), "shineon_sagan_attention")
     return out_f32, out_planes
 
 
-def l2norm_correlation(featA, featB, *, want_f32=False, want_planes=True, split=True):
+def l2norm_correlation(featA, featB, *, want_f32=False, want_planes=True, prec=None):
     """featA/B: f32 NHWC [B,h,w,C] -> correlation [B,h,w,h*w] (channel = wA*h+hA)."""
     featA, featB = _req(featA), _req(featB)
     B, h, w, Cc = featA.shape
     corr = torch.empty(B, h, w, h * w, dtype=torch.float32, device=featA.device) if want_f32 else None
-    planes = Planes(B, h, w, h * w, split=split, device=featA.device) if want_planes else None
+    planes = Planes(B, h, w, h * w, prec=prec, device=featA.device) if want_planes else None
     check(_lib.load().shineon_l2norm_correlation(_p(featA), _p(featB), _p(corr), _p(planes.hi if planes else None),
                                                  _p(planes.lo if planes else None), B, h, w, Cc,
-                                                 planes.cpad if planes else h * w, _stream()),
+                                                 planes.cpad if planes else h * w, planes.fmt if planes else 0, _stream()),
           "shineon_l2norm_correlation")
     return corr, planes
 

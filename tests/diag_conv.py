@@ -20,8 +20,9 @@ def run(name, N, H, W, Cin, Cout, k, s, p, split, tile_n=0, stages=0, check_cpu=
     x = torch.randn(N, Cin, H, W, generator=g)
     w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
     b = torch.randn(Cout, generator=g) * 0.1
-    xp = ops.nchw_to_planes(x.cuda(), split=split)
-    pc = ops.PackedConv(w.cuda(), b.cuda(), stride=s, pad=p, split=split)
+    prec = 'fp16x3' if split else 'bf16'
+    xp = ops.nchw_to_planes(x.cuda(), prec=prec)
+    pc = ops.PackedConv(w.cuda(), b.cuda(), stride=s, pad=p, prec=prec)
     try:
         yd, _ = ops.conv2d(xp, pc, want_f32=True, direct=True)
         torch.cuda.synchronize()

@@ -15,8 +15,18 @@ def ops(cuda):
     return _ops
 
 
-def _planes_from(ops, x_nchw, split=True):
-    return ops.nchw_to_planes(x_nchw.cuda().contiguous(), split=split)
+def _planes_from(ops, x_nchw, prec="fp16x3"):
+    return ops.nchw_to_planes(x_nchw.cuda().contiguous(), prec=prec)
+
+
+def _rounded(t, prec):
+    """The operand rounding a single-product (non-split) mode applies."""
+    return {"bf16": t.bfloat16().float(), "fp16": t.half().float()}.get(prec, t)
+
+
+# per-mode bound of one conv layer against the fp32 oracle on O(1) data (DESIGN.md §4)
+CONV_TOL = {"fp16x3": dict(atol=5e-6, rtol=1e-5), "bf16x3": dict(atol=1e-4, rtol=1e-4),
+            "fp16": dict(atol=5e-5, rtol=1e-4), "bf16": dict(atol=5e-5, rtol=1e-4)}
 
 
 # ------------------------------------------------------------------------------------------ conv
@@ -36,27 +46,26 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("split", [True, False])
-def test_conv2d_igemm(ops, case, split):
+@pytest.mark.parametrize("prec", ["fp16x3", "bf16x3", "fp16", "bf16"])
+def test_conv2d_igemm(ops, case, prec):
     N, H, W, Cin, Cout, k, s, p = case
     g = torch.Generator().manual_seed(1234 + Cin + Cout + k)
     x = torch.randn(N, Cin, H, W, generator=g)
     w = torch.randn(Cout, Cin, k, k, generator=g) * (1.0 / (Cin * k * k) ** 0.5)
     b = torch.randn(Cout, generator=g) * 0.1
-    xp = _planes_from(ops, x, split)
-    pc = ops.PackedConv(w.cuda(), b.cuda(), stride=s, pad=p, split=split)
-    y, yp = ops.conv2d(xp, pc, want_f32=True, want_planes=True)
+    xp = _planes_from(ops, x, prec)
+    pc = ops.PackedConv(w.cuda(), b.cuda(), stride=s, pad=p, prec=prec)
+    y, _ = ops.conv2d(xp, pc, want_f32=True)
+    _, yp = ops.conv2d(xp, pc, want_planes=True)
     yd, _ = ops.conv2d(xp, pc, want_f32=True, direct=True)
     torch.cuda.synchronize()
-    if split:
-        want = F.conv2d(x, w, b, stride=s, padding=p)
-        tol = dict(atol=2e-5, rtol=1e-4)
-    else:  # single-bf16 products: compare against the same rounding of the operands
-        want = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, stride=s, padding=p)
-        tol = dict(atol=2e-4, rtol=1e-3)
-    assert_close(nchw(yd), want, what="direct vs oracle", **tol)
-    assert_close(nchw(y), want, what="igemm vs oracle", **tol)
-    assert_close(yp.float(), want, what="igemm planes vs oracle", atol=max(tol["atol"], 1e-2 if not split else 0), rtol=1e-2 if not split else tol["rtol"])
+    # split modes are compared with the exact fp32 conv; single-product modes with the conv of the rounded operands
+    want = F.conv2d(_rounded(x, prec), _rounded(w, prec), b, stride=s, padding=p)
+    tol = CONV_TOL[prec]
+    assert_close(nchw(yd), want, what="direct (CUDA-core) vs oracle", **tol)
+    assert_close(nchw(y), want, what="igemm (tcgen05) vs oracle", **tol)
+    ptol = tol if prec.endswith("x3") else dict(atol=2e-2, rtol=1e-2)  # single 16-bit output plane
+    assert_close(yp.float(), want, what="igemm planes vs oracle", **ptol)
 
 
 def test_conv2d_epilogue_and_window(ops):
@@ -71,11 +80,12 @@ def test_conv2d_epilogue_and_window(ops):
     xp = _planes_from(ops, x)
     pc = ops.PackedConv(w.cuda(), b.cuda(), stride=1, pad=1)
     out = ops.Planes(N, H, W, 192, device="cuda")
+    out.hi.zero_(); out.lo.zero_()
     ops.conv2d(xp, pc, scale=sc.cuda(), shift=sh.cuda(), pre_act="relu", out_planes=out, out_coffset=64)
     torch.cuda.synchronize()
     want = F.relu(F.conv2d(x, w, b, padding=1)) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
     got = out.float()
-    assert_close(got[:, 64:128], want, atol=2e-5, rtol=1e-4, what="window")
+    assert_close(got[:, 64:128], want, atol=5e-6, rtol=1e-5, what="window")
     assert got[:, :64].abs().max().item() == 0 and got[:, 128:].abs().max().item() == 0
 
 
@@ -93,7 +103,7 @@ def test_deconv_as_phase_convs(ops):
     dc = PackedDeconv4x4s2(w.cuda(), b.cuda())
     y = dc(xp, want_f32=True)[0]
     torch.cuda.synchronize()
-    assert_close(nchw(y), want, atol=2e-5, rtol=1e-4, what="deconv")
+    assert_close(nchw(y), want, atol=5e-6, rtol=1e-5, what="deconv")
 
 
 # ------------------------------------------------------------------------------------------ gather ops
@@ -126,8 +136,9 @@ def test_tps_grid_and_sample(ops, gs, scale):
     # fused path
     outs, grid2 = ops.tps_grid_sample(theta.cuda(), dev, H, W, [(cloth.cuda(), "border"), (mask.cuda(), "zeros")], want_grid=True)
     assert_close(grid2, want_grid, atol=2e-5, rtol=1e-5, what="fused grid")
-    assert_close(outs[0], gmm.grid_sample(cloth, want_grid, "border"), atol=2e-4, rtol=1e-3, what="fused cloth")
-    assert_close(outs[1], gmm.grid_sample(mask, want_grid, "zeros"), atol=2e-4, rtol=1e-3, what="fused mask")
+    # fused = sampling at OUR grid: per-pixel-noise images amplify the ~1e-6 grid difference by (W/2 * |gradient|)
+    assert_close(outs[0], gmm.grid_sample(cloth, want_grid, "border"), atol=1e-3, rtol=1e-2, what="fused cloth")
+    assert_close(outs[1], gmm.grid_sample(mask, want_grid, "zeros"), atol=1e-3, rtol=1e-2, what="fused mask")
 
 
 @pytest.mark.parametrize("bilinear", [True, False])
