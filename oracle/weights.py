@@ -31,13 +31,9 @@ def synth_tensor(seed, key, shape, conv_std=None):
     if leaf == "bias":
         return torch.randn(shape, generator=g) * 0.05
     if leaf == "weight" and len(shape) >= 2:
-        if conv_std is None:
-            fan_in = 1
-            for s in shape[1:]:
-                fan_in *= s
-            std = (1.0 / fan_in) ** 0.5  # keeps activations O(1) through the stack
-        else:
-            std = conv_std
+        # the reference's own initialiser scale: init.normal_(w, 0.0, 0.02) for Conv / Linear
+        # (models/networks/__init__.py:49-55)
+        std = 0.02 if conv_std is None else conv_std
         return torch.randn(shape, generator=g) * std
     return torch.randn(shape, generator=g) * 0.1
 

@@ -90,7 +90,10 @@ def test_tryon_pipeline_5_frame_clip(cuda):
     B = 5
     person_gmm = torch.randn(B, 22, 256, 192, generator=g)
     person_tom = torch.randn(B, 7, 256, 192, generator=g)
-    cloth = torch.rand(B, 3, 256, 192, generator=g) * 2 - 1
+    # a smooth "garment" image: per-pixel noise would multiply the ~1e-5 TPS-coordinate difference by its unit-scale
+    # gradient (x W/2 pixels) — that conditioning case is covered by the gmm_stress golden with its own bound
+    cloth = torch.nn.functional.interpolate(torch.rand(B, 3, 16, 12, generator=g) * 2 - 1, size=(256, 192),
+                                            mode="bilinear", align_corners=False)
     with torch.no_grad():
         wc, _, _, _ = warp.warp(person_gmm.cuda(), cloth.cuda(), cloth.cuda())
         got = tom(person_tom.cuda(), wc)
@@ -99,9 +102,9 @@ def test_tryon_pipeline_5_frame_clip(cuda):
         owc = gmm.grid_sample(cloth, grid, "border")
         want = unet.tom_forward(sdt, person_tom, owc, **_tom_kwargs({}))
     torch.cuda.synchronize()
-    assert_close(wc, owc, atol=2e-3, rtol=1e-2, what="warped cloth")
+    assert_close(wc, owc, what="warped cloth")
     for gt, w, n in zip(got[:3], want[:3], ["p_rendereds", "tryon_masks", "p_tryons"]):
-        assert_close(gt, w, atol=2e-3, rtol=1e-2, what=f"pipeline {n}")
+        assert_close(gt, w, what=f"pipeline {n}")
 
 
 @pytest.mark.parametrize("prec,max_tol,mean_tol", [("bf16x3", 2e-2, 1e-3), ("fp16", 0.3, 1e-2), ("bf16", 1.0, 5e-2)])
