@@ -195,6 +195,17 @@ int shineon_nchw_to_planes(const float* x0, int C0, const float* x1, int C1, voi
                            int H, int W, int cpad, int act, float act_param, int plane_fmt,
                            shineon_stream_t stream);
 
+/* Same, but written as the im2col matrix of a (kh x kw, stride, pad) convolution: y planes [N,Ho,Wo,kpad] with
+ * k = (fy*kw+fx)*C + c.  Turns a small-Cin first layer (Cin 3/10/22) into a dense 1x1 GEMM. */
+int shineon_nchw_im2col_planes(const float* x0, int C0, const float* x1, int C1, void* y_hi, void* y_lo, int N,
+                               int H, int W, int kh, int kw, int stride, int pad, int Ho, int Wo, int kpad, int act,
+                               float act_param, int plane_fmt, shineon_stream_t stream);
+
+/* col2im of a tap-stacked 3x3 convolution with few output channels: t f32 NHWC [N,H,W,tstride] holds the
+ * 9*Cout per-input-pixel partial products (channel (fy*3+fx)*Cout+co); y f32 NHWC [N,H,W,Cout] = bias + shifted sum. */
+int shineon_col2im3x3(const float* t, const float* bias, float* y, int N, int H, int W, int Cout, int tstride,
+                      shineon_stream_t stream);
+
 /* nn.InstanceNorm2d(affine=False, eps) over f32 NHWC x [N,H,W,C] (unet.py:133,135) followed by
  * activation; writes any subset of: f32 NHWC y_f32 (may alias x), planes y_hi/y_lo [N,H,W,cpad].
  * do_norm=0 skips the normalisation (innermost down block, unet.py:166-175).

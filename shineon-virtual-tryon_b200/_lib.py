@@ -56,6 +56,9 @@ SIGNATURES = {
     "shineon_conv2d_igemm_fwd": [C.POINTER(Conv2dParams), c_p],
     "shineon_conv2d_direct_fwd": [C.POINTER(Conv2dParams), c_p],
     "shineon_nchw_to_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
+    "shineon_nchw_im2col_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
+                                   c_f, c_i, c_p],
+    "shineon_col2im3x3": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_instnorm_act": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_f, c_i, c_p],
     "shineon_upsample2x_cat": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     "shineon_sagan_attention": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],

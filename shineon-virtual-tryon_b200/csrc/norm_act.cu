@@ -37,6 +37,81 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------ nchw -> im2col planes
+// First layers have tiny Cin (3 / 10 / 22): one K-block per filter tap would waste >= 2/3 of every TMA box and
+// MMA on zero padding.  Instead the layout conversion writes, per OUTPUT pixel, the K-vector
+//   k = (fy*kw + fx)*C + c   (tap-major, channel-minor; zero for out-of-image taps and k >= kh*kw*C)
+// so the convolution becomes a 1x1 GEMM with K = pad64(kh*kw*C).
+__global__ void __launch_bounds__(256)
+    nchw_im2col_planes_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+                              plane_t* __restrict__ yh, plane_t* __restrict__ yl, int H, int W, int kh, int kw,
+                              int stride, int pad, int Ho, int Wo, int kpad, int act, float act_param, int fmt) {
+  const int n = blockIdx.y;
+  const int C = C0 + C1;
+  const int K = kh * kw * C;
+  const int groups = kpad / 8;
+  const int HWo = Ho * Wo;
+  const long HW = (long)H * W;
+  const long total = (long)HWo * groups;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int p = (int)(e % HWo);  // pixel fastest: neighbouring threads read neighbouring input columns
+    const int g = (int)(e / HWo);
+    const int oh = p / Wo, ow = p - oh * Wo;
+    __align__(16) plane_t hi[8];
+    __align__(16) plane_t lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float v = 0.f;
+      if (k < K) {
+        const int tap = k / C, c = k - tap * C;
+        const int fy = tap / kw, fx = tap - fy * kw;
+        const int iy = oh * stride + fy - pad, ix = ow * stride + fx - pad;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          v = c < C0 ? __ldg(x0 + ((long)n * C0 + c) * HW + (long)iy * W + ix)
+                     : __ldg(x1 + ((long)n * C1 + (c - C0)) * HW + (long)iy * W + ix);
+          v = apply_act(v, act, act_param);
+        }
+      }
+      split16(v, fmt, hi[j], lo[j]);
+    }
+    const long o = ((long)n * HWo + p) * kpad + g * 8;
+    *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
+    if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+// ------------------------------------------------------------------------------ tap-stacked 3x3 conv: col2im
+// For a 3x3 conv with very few output channels (the U-Net's final 128 -> 4 layer) the implicit GEMM is run
+// "transposed": one 1x1 GEMM produces, for every INPUT pixel q, the 9*Cout partial products
+//   t[q, (fy*3+fx)*Cout + co] = <x[q,:], w[co,:,fy,fx]>
+// (the activation is read once instead of once per tap) and this kernel sums the shifted partials:
+//   out[n,oh,ow,co] = bias[co] + sum_{fy,fx} t[n, oh+fy-1, ow+fx-1, (fy*3+fx)*Cout + co]   (zero outside the image)
+__global__ void __launch_bounds__(256)
+    col2im3x3_kernel(const float* __restrict__ t, const float* __restrict__ bias, float* __restrict__ y, int H, int W,
+                     int Cout, int tstride) {
+  const int n = blockIdx.y;
+  const long total = (long)H * W * Cout;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(e % Cout);
+    const long p = e / Cout;
+    const int ow = (int)(p % W), oh = (int)(p / W);
+    float acc = bias ? __ldg(bias + co) : 0.f;
+#pragma unroll
+    for (int fy = 0; fy < 3; ++fy) {
+      const int iy = oh + fy - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int fx = 0; fx < 3; ++fx) {
+        const int ix = ow + fx - 1;
+        if (ix < 0 || ix >= W) continue;
+        acc += __ldg(t + (((long)n * H + iy) * W + ix) * tstride + (fy * 3 + fx) * Cout + co);
+      }
+    }
+    y[((long)n * H * W + p) * Cout + co] = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------ instance norm
 // Pass 1: per-(n,c) sum and sum of squares.  fp32 partials per CTA, fp64 atomics across CTAs
 // (E[x^2]-E[x]^2 is then evaluated in fp64, so cancellation is not an issue).
@@ -256,6 +331,30 @@ extern "C" int shineon_nchw_to_planes(const float* x0, int C0, const float* x1, 
   nchw_to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo,
                                                                HW, cpad, act, act_param, plane_fmt);
   return after_launch("nchw_to_planes_kernel");
+}
+
+extern "C" int shineon_nchw_im2col_planes(const float* x0, int C0, const float* x1, int C1, void* y_hi, void* y_lo,
+                                         int N, int H, int W, int kh, int kw, int stride, int pad, int Ho, int Wo,
+                                         int kpad, int act, float act_param, int plane_fmt, shineon_stream_t stream) {
+  SHINEON_REQUIRE_FMT(plane_fmt, "nchw_im2col_planes");
+  SHINEON_REQUIRE(x0 && y_hi && C0 > 0, "nchw_im2col_planes: null pointer");
+  SHINEON_REQUIRE((x1 == nullptr) == (C1 == 0), "nchw_im2col_planes: x1/C1 mismatch");
+  SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, "nchw_im2col_planes: bad shape");
+  SHINEON_REQUIRE(Ho == (H + 2 * pad - kh) / stride + 1 && Wo == (W + 2 * pad - kw) / stride + 1, "nchw_im2col_planes: Ho/Wo");
+  SHINEON_REQUIRE(kpad % 8 == 0 && kpad >= kh * kw * (C0 + C1), "nchw_im2col_planes: kpad %d too small / not a multiple of 8", kpad);
+  dim3 grid(grid_x((long)Ho * Wo * (kpad / 8), 256), N);
+  nchw_im2col_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, kh,
+                                                                   kw, stride, pad, Ho, Wo, kpad, act, act_param, plane_fmt);
+  return after_launch("nchw_im2col_planes_kernel");
+}
+
+extern "C" int shineon_col2im3x3(const float* t, const float* bias, float* y, int N, int H, int W, int Cout, int tstride,
+                                 shineon_stream_t stream) {
+  SHINEON_REQUIRE(t && y, "col2im3x3: null pointer");
+  SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && Cout > 0 && tstride >= 9 * Cout, "col2im3x3: bad shape");
+  dim3 grid(grid_x((long)H * W * Cout, 256), N);
+  col2im3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, bias, y, H, W, Cout, tstride);
+  return after_launch("col2im3x3_kernel");
 }
 
 extern "C" int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, void* y_lo, double* stats_ws, int N,

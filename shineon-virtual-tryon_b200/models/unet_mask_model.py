@@ -54,9 +54,8 @@ class UnetMaskModel(BaseModel):
         prec = ops.resolve_precision(self.unet.precision)
         person_representation = person_representation.contiguous()
         warped_cloths = warped_cloths.contiguous()
-        # torch.cat([person, cloth], 1) is fused into the NCHW -> NHWC-planes conversion
-        x = ops.nchw_to_planes(person_representation, warped_cloths, prec=prec)
-        out = self.unet.model.run(x, prec)  # f32 NHWC [B,H,W,(4|5)n]
+        # torch.cat([person, cloth], 1) is fused into the NCHW -> NHWC-planes (im2col) conversion
+        out = self.unet.model.run((person_representation, warped_cloths), prec)  # f32 NHWC [B,H,W,(4|5)n]
         B, H, W, _ = out.shape
         dev = out.device
         p_rendereds = torch.empty(B, 3 * n, H, W, device=dev)

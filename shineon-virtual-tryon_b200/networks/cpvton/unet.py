@@ -45,8 +45,7 @@ class UnetGenerator(nn.Module):
         """input: f32 NCHW CUDA tensor -> f32 NHWC [N,H,W,output_nc]."""
         require_cuda(self, "UnetGenerator")
         prec = ops.resolve_precision(self.precision)
-        x = ops.nchw_to_planes(input.contiguous(), prec=prec)
-        return self.model.run(x, prec)
+        return self.model.run((input.contiguous(), None), prec)
 
     def forward(self, input):
         return self.forward_nhwc(input).permute(0, 3, 1, 2).contiguous()
@@ -112,7 +111,13 @@ class UnetSkipConnectionBlock(nn.Module):
         dc, uc = pr["downconv"], pr["upconv"]
         sub = pr["sub"]
         d = {}
-        d["down"] = ops.PackedConv(dc.weight, dc.bias, stride=2, pad=1, prec=prec)
+        d["down_i2c"] = None
+        if self.outermost and dc.in_channels <= 32:
+            # tiny Cin: im2col'd input + dense 1x1 GEMM instead of one mostly-zero K-block per tap
+            d["down_i2c"] = ops.Im2colConv(dc.weight, dc.bias, 2, 1, prec=prec)
+            d["down"] = d["down_i2c"].pc
+        else:
+            d["down"] = ops.PackedConv(dc.weight, dc.bias, stride=2, pad=1, prec=prec)
         if sub is not None:
             # up-conv input channels: [skip (sub input, padded to 64) | x' (sub output, padded to 64)]
             c_skip = sub._parts["downconv"].in_channels
@@ -123,9 +128,14 @@ class UnetSkipConnectionBlock(nn.Module):
                 cmap[c] = c
             for c in range(c_xp):
                 cmap[p_skip + c] = c_skip + c
+            d["up_tap"] = None
+            if self.outermost and uc.out_channels <= 8 and isinstance(pr["upnorm"], nn.InstanceNorm2d):
+                # few output channels: tap-stacked 1x1 GEMM + col2im (the activation is read once, not once per tap)
+                d["up_tap"] = ops.TapStackedConv3x3(uc.weight, uc.bias, prec=prec, cin_pad=p_skip + p_xp, chan_map=cmap)
             d["up"] = ops.PackedConv(uc.weight, uc.bias, stride=1, pad=1, prec=prec, cin_pad=p_skip + p_xp,
                                      chan_map=cmap)
         else:
+            d["up_tap"] = None
             d["up"] = ops.PackedConv(uc.weight, uc.bias, stride=1, pad=1, prec=prec)
         for key, norm in (("down_bn", pr["downnorm"]), ("up_bn", pr["upnorm"])):
             d[key] = None
@@ -158,7 +168,8 @@ class UnetSkipConnectionBlock(nn.Module):
         return attn.run(y, p, act=act, act_param=act_param, want_f32=False, want_planes=True)[1]
 
     def run(self, a_in, prec):
-        """a_in: Planes holding this block's (already down-activated) input.
+        """a_in: Planes holding this block's (already down-activated) input; for the outermost block a tuple
+        (x0, x1|None) of f32 NCHW tensors (torch.cat([x0, x1], 1) is fused into the layout conversion).
         Outermost: returns f32 NHWC output.  Otherwise returns Planes of up_act(x') for the parent."""
         pr = self._parts
         if self.training and pr["dropout"]:
@@ -171,6 +182,10 @@ class UnetSkipConnectionBlock(nn.Module):
             next_act, next_par = up_act, up_par
         else:
             next_act, next_par = act_name(sub._parts["down_act"])
+        if isinstance(a_in, tuple):
+            x0, x1 = a_in
+            a_in = (pk["down_i2c"].prepare(x0, x1) if pk["down_i2c"] is not None
+                    else ops.nchw_to_planes(x0, x1, prec=prec))
         bn = pk["down_bn"]
         sc, sh = bn if bn is not None else (None, None)
         f32, _ = ops.conv2d(a_in, pk["down"], scale=sc, shift=sh, want_f32=True)
@@ -186,7 +201,10 @@ class UnetSkipConnectionBlock(nn.Module):
             u = ops.upsample2x_cat(a_mid, xp, act=extra)
         bn = pk["up_bn"]
         sc, sh = bn if bn is not None else (None, None)
-        f32, _ = ops.conv2d(u, pk["up"], scale=sc, shift=sh, want_f32=True)
+        if pk["up_tap"] is not None:
+            f32 = pk["up_tap"](u)
+        else:
+            f32, _ = ops.conv2d(u, pk["up"], scale=sc, shift=sh, want_f32=True)
         if self.outermost:
             return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], None, 0.0, prec, want_final_f32=True)
         return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], up_act, up_par, prec)

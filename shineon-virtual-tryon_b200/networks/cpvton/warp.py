@@ -53,8 +53,13 @@ class FeatureExtraction(nn.Module):
             if bn is not None and not isinstance(bn, nn.BatchNorm2d):
                 raise NotImplementedError(f"FeatureExtraction norm {type(bn).__name__} has no native kernel")
             sc, sh = fold_bn(bn) if bn is not None else (None, None)
-            pc = ops.PackedConv(conv.weight, conv.bias, stride=conv.stride[0], pad=conv.padding[0], prec=prec)
-            layers.append((pc, sc, sh))
+            if i == 0 and conv.in_channels <= 32:
+                # tiny Cin: im2col'd input + dense 1x1 GEMM instead of one mostly-zero K-block per tap
+                i2c = ops.Im2colConv(conv.weight, conv.bias, conv.stride[0], conv.padding[0], prec=prec)
+                layers.append((i2c.pc, sc, sh, i2c))
+            else:
+                pc = ops.PackedConv(conv.weight, conv.bias, stride=conv.stride[0], pad=conv.padding[0], prec=prec)
+                layers.append((pc, sc, sh, None))
             i += 3
         self._packed = (sig, layers)
         return layers
@@ -63,8 +68,9 @@ class FeatureExtraction(nn.Module):
         """x f32 NCHW -> f32 NHWC features (conv -> ReLU -> BN ... conv -> ReLU, warp.py:13-31)."""
         prec = ops.resolve_precision(self.precision)
         layers = self._layers(prec)
-        a = ops.nchw_to_planes(x.contiguous(), prec=prec)
-        for li, (pc, sc, sh) in enumerate(layers):
+        first = layers[0][3]
+        a = first.prepare(x.contiguous()) if first is not None else ops.nchw_to_planes(x.contiguous(), prec=prec)
+        for li, (pc, sc, sh, _) in enumerate(layers):
             last = li == len(layers) - 1
             f32, a = ops.conv2d(a, pc, scale=sc, shift=sh, pre_act="relu", want_f32=last, want_planes=not last)
         return f32

@@ -297,7 +297,8 @@ def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_pa
     check(fn(C.byref(p), _stream()), "shineon_conv2d_direct_fwd" if direct else "shineon_conv2d_igemm_fwd")
     if prof is not None and not direct:
         e1.record()
-        prof.append((2.0 * N * Ho * Wo * pc.Cout * pc.kh * pc.kw * pc.Cin, e0, e1))
+        prof.append((2.0 * N * Ho * Wo * pc.Cout * pc.kh * pc.kw * pc.Cin, e0, e1,
+                     (N, H, W, pc.Cin, x.cpad, pc.Cout, pc.kh, pc.stride)))
     return out_f32, out_planes
 
 
@@ -314,6 +315,55 @@ def nchw_to_planes(x0, x1=None, act=None, act_param=0.0, prec=None, out=None):
     check(_lib.load().shineon_nchw_to_planes(_p(x0), C0, _p(x1), C1, _p(out.hi), _p(out.lo), N, H, W, out.cpad,
                                              ACT[act], float(act_param), out.fmt, _stream()), "shineon_nchw_to_planes")
     return out
+
+
+def nchw_im2col_planes(x0, x1, kh, kw, stride, pad, act=None, act_param=0.0, prec=None):
+    """im2col'd first-layer input: Planes [N,Ho,Wo,pad64(kh*kw*C)] with k = (fy*kw+fx)*C + c."""
+    x0 = _req(x0, name="x0")
+    N, C0, H, W = x0.shape
+    C1 = 0
+    if x1 is not None:
+        x1 = _req(x1, name="x1")
+        C1 = x1.shape[1]
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    out = Planes(N, Ho, Wo, kh * kw * (C0 + C1), prec=prec, device=x0.device)
+    check(_lib.load().shineon_nchw_im2col_planes(_p(x0), C0, _p(x1), C1, _p(out.hi), _p(out.lo), N, H, W, kh, kw, stride,
+                                                 pad, Ho, Wo, out.cpad, ACT[act], float(act_param), out.fmt, _stream()),
+          "shineon_nchw_im2col_planes")
+    return out
+
+
+class Im2colConv:
+    """A Conv2d with tiny Cin as a 1x1 GEMM over nchw_im2col_planes (weights reordered tap-major to match)."""
+
+    def __init__(self, weight, bias, stride, pad, prec=None):
+        Cout, Cin, kh, kw = weight.shape
+        self.kh, self.kw, self.stride, self.pad = kh, kw, stride, pad
+        w2 = weight.detach().float().permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin, 1, 1).contiguous()
+        self.pc = PackedConv(w2, bias, stride=1, pad=0, prec=prec)
+
+    def prepare(self, x0, x1=None, act=None, act_param=0.0):
+        return nchw_im2col_planes(x0, x1, self.kh, self.kw, self.stride, self.pad, act, act_param,
+                                  prec=(self.pc.fmt, self.pc.w_lo is not None))
+
+
+class TapStackedConv3x3:
+    """3x3 / stride 1 / pad 1 conv with few output channels as one 1x1 GEMM with 9*Cout outputs + col2im."""
+
+    def __init__(self, weight, bias, prec=None, cin_pad=None, chan_map=None):
+        Cout, Cin, kh, kw = weight.shape
+        assert kh == 3 and kw == 3
+        self.Cout = Cout
+        w2 = weight.detach().float().permute(2, 3, 0, 1).reshape(9 * Cout, Cin, 1, 1).contiguous()  # (tap, co) major
+        self.pc = PackedConv(w2, None, stride=1, pad=0, prec=prec, cin_pad=cin_pad, chan_map=chan_map)
+        self.bias = None if bias is None else _req(bias.detach().float().contiguous(), name="bias")
+
+    def __call__(self, x):
+        t, _ = conv2d(x, self.pc, want_f32=True)  # [N,H,W,9*Cout]
+        y = torch.empty(x.N, x.H, x.W, self.Cout, dtype=torch.float32, device=t.device)
+        check(_lib.load().shineon_col2im3x3(_p(t), _p(self.bias), _p(y), x.N, x.H, x.W, self.Cout, t.shape[-1], _stream()),
+              "shineon_col2im3x3")
+        return y
 
 
 def instnorm_act(x, *, do_norm=True, act=None, act_param=0.0, eps=1e-5, want_f32=False, want_planes=True,

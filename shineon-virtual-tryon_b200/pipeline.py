@@ -13,8 +13,7 @@ class TryOnPipeline:
     def __init__(self, warp_model, tom_model):
         self.warp_model = warp_model
         self.tom_model = tom_model
-        self._host_out = None
-        self._dev_in = None
+        self._host_state = None
 
     def set_precision(self, precision):
         self.warp_model.set_precision(precision)
@@ -29,20 +28,52 @@ class TryOnPipeline:
         return p_tryons, tryon_masks, warped_cloth
 
     @torch.no_grad()
-    def run_host(self, person_gmm_h, cloth_h, person_tom_h, out_h=None):
-        """Host (pinned) tensors in, host (pinned) p_tryon out; H2D / D2H are part of the call."""
+    def run_host(self, person_gmm_h, cloth_h, person_tom_h):
+        """Host (pinned) tensors in, host (pinned) p_tryon out; the H2D / D2H copies are part of the call.
+
+        Asynchronous and double-buffered: the copies run on two side streams so the next call's H2D overlaps this
+        call's kernels.  Returns (out_host, done_event); `out_host` is valid once `done_event` has completed (or after
+        a device synchronize) and is reused by the call after next.
+        """
         dev = next(self.tom_model.parameters()).device
+        cur = torch.cuda.current_stream(dev)
         shapes = (tuple(person_gmm_h.shape), tuple(cloth_h.shape), tuple(person_tom_h.shape))
-        if self._dev_in is None or self._dev_in[0] != shapes:
-            self._dev_in = (shapes, tuple(torch.empty(s, dtype=torch.float32, device=dev) for s in shapes))
-        a, c, p = self._dev_in[1]
-        a.copy_(person_gmm_h, non_blocking=True)
-        c.copy_(cloth_h, non_blocking=True)
-        p.copy_(person_tom_h, non_blocking=True)
+        st = self._host_state
+        if st is None or st["shapes"] != shapes:
+            st = self._host_state = dict(
+                shapes=shapes, call=0, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev),
+                dev_in=[tuple(torch.empty(s, dtype=torch.float32, device=dev) for s in shapes) for _ in range(2)],
+                in_free=[torch.cuda.Event() for _ in range(2)], in_ready=[torch.cuda.Event() for _ in range(2)],
+                out_done=[torch.cuda.Event() for _ in range(2)],
+                host_out=[torch.empty((shapes[1][0], 3) + shapes[1][2:], dtype=torch.float32).pin_memory() for _ in range(2)])
+            for e in st["in_free"] + st["out_done"]:
+                e.record(cur)
+        slot = st["call"] % 2
+        st["call"] += 1
+        a, c, p = st["dev_in"][slot]
+        with torch.cuda.stream(st["s_in"]):
+            st["s_in"].wait_event(st["in_free"][slot])  # kernels of the call before last have consumed this slot
+            a.copy_(person_gmm_h, non_blocking=True)
+            c.copy_(cloth_h, non_blocking=True)
+            p.copy_(person_tom_h, non_blocking=True)
+            st["in_ready"][slot].record(st["s_in"])
+        cur.wait_event(st["in_ready"][slot])
         p_tryons, _, _ = self(a, c, p)
-        if out_h is None:
-            if self._host_out is None or self._host_out.shape != p_tryons.shape:
-                self._host_out = torch.empty(p_tryons.shape, dtype=torch.float32).pin_memory()
-            out_h = self._host_out
-        out_h.copy_(p_tryons, non_blocking=True)
-        return out_h
+        st["in_free"][slot].record(cur)
+        computed = torch.cuda.Event()
+        computed.record(cur)
+        out_h = st["host_out"][slot]
+        p_tryons.record_stream(st["s_out"])
+        with torch.cuda.stream(st["s_out"]):
+            st["s_out"].wait_event(computed)
+            out_h.copy_(p_tryons, non_blocking=True)
+            st["out_done"][slot].record(st["s_out"])
+        return out_h, st["out_done"][slot]
+
+    def host_sync(self):
+        """Wait for every outstanding run_host call (copies included)."""
+        st = self._host_state
+        if st is not None:
+            st["s_in"].synchronize()
+            st["s_out"].synchronize()
+        torch.cuda.current_stream().synchronize()

@@ -1,0 +1,45 @@
+"""Per-launch timing table of one try-on step (GPU box).  Usage: python tests/profile_layers.py [clips] [precision]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from shineon_virtual_tryon_b200 import ops  # noqa: E402
+from shineon_virtual_tryon_b200.pipeline import TryOnPipeline  # noqa: E402
+
+
+def main():
+    clips = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    prec = sys.argv[2] if len(sys.argv) > 2 else "fp16x3"
+    dev = torch.device("cuda")
+    warp, tom = bench.build_models()
+    pipe = TryOnPipeline(warp.to(dev), tom.to(dev))
+    pipe.set_precision(prec)
+    frames = clips * 5
+    a, c, p = (t.to(dev) for t in bench.synth_inputs(frames, 1))
+    for _ in range(3):
+        pipe(a, c, p)
+    torch.cuda.synchronize()
+    prof = []
+    ops.PROFILE = prof
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pipe(a, c, p)
+    e1.record()
+    ops.PROFILE = None
+    torch.cuda.synchronize()
+    total = e0.elapsed_time(e1)
+    print(f"step {total:.3f} ms for {frames} frames ({frames / total * 1e3:.0f} fps) precision {prec}")
+    tconv = 0.0
+    print(f"{'N':>4} {'HxW':>9} {'Cin':>5} {'Cout':>5} k s | {'ms':>8} {'TF/s':>8} {'GF':>8}")
+    for fl, s, e, (N, H, W, Cin, cpad, Cout, k, st) in prof:
+        ms = s.elapsed_time(e)
+        tconv += ms
+        print(f"{N:4d} {H:4d}x{W:<4d} {Cin:5d} {Cout:5d} {k} {st} | {ms:8.3f} {fl / ms / 1e9:8.1f} {fl / 1e9:8.2f}")
+    print(f"conv total {tconv:.3f} ms = {tconv / total * 100:.1f}% of step; non-conv {total - tconv:.3f} ms")
+
+
+if __name__ == "__main__":
+    main()

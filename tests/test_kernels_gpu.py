@@ -89,6 +89,32 @@ def test_conv2d_epilogue_and_window(ops):
     assert got[:, :64].abs().max().item() == 0 and got[:, 128:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("cfg", [(2, 22, 64, 48, 64, 4, 2, 1), (2, 3, 32, 32, 64, 7, 2, 3), (1, 10, 64, 48, 64, 4, 2, 1)])
+def test_im2col_first_layer(ops, cfg):
+    """Small-Cin conv as im2col'd planes + dense 1x1 GEMM (cat of two NCHW inputs fused)."""
+    N, Cin, H, W, Cout, k, s, p = cfg
+    g = torch.Generator().manual_seed(Cin)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) * 0.05
+    b = torch.randn(Cout, generator=g) * 0.1
+    c0 = Cin - Cin // 3
+    conv = ops.Im2colConv(w.cuda(), b.cuda(), s, p)
+    a = conv.prepare(x[:, :c0].contiguous().cuda(), x[:, c0:].contiguous().cuda() if c0 < Cin else None)
+    y, _ = ops.conv2d(a, conv.pc, want_f32=True)
+    assert_close(nchw(y), F.conv2d(x, w, b, stride=s, padding=p), atol=3e-5, rtol=1e-4, what="im2col conv")
+
+
+def test_tap_stacked_conv3x3(ops):
+    g = torch.Generator().manual_seed(44)
+    N, Cin, H, W, Cout = 2, 128, 32, 24, 4
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * 0.03
+    b = torch.randn(Cout, generator=g) * 0.1
+    conv = ops.TapStackedConv3x3(w.cuda(), b.cuda())
+    y = conv(_planes_from(ops, x))
+    assert_close(nchw(y), F.conv2d(x, w, b, padding=1), atol=3e-5, rtol=1e-4, what="tap-stacked conv")
+
+
 def test_deconv_as_phase_convs(ops):
     """ConvTranspose2d(4,2,1) (submodules.py:34-38) = 4 phase-wise 2x2 convolutions scattered into the output."""
     g = torch.Generator().manual_seed(11)
