@@ -174,6 +174,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------- epilogue
+// Scalar form (CUDA-core cross-check kernel).
 __device__ __forceinline__ float conv_epilogue_value(float acc, int c, const ConvArgs& a) {
   float v = acc * a.acc_scale;
   if (a.bias) v += __ldg(a.bias + c);
@@ -183,8 +184,45 @@ __device__ __forceinline__ float conv_epilogue_value(float acc, int c, const Con
   return v;
 }
 
-// Stores `cnt` (<= 32, multiple of 8 unless at the Cout edge) consecutive channels of one pixel.
-__device__ __forceinline__ void conv_store_row(const float* vals, int c_first, int cnt, long pix, const ConvArgs& a) {
+// Vector form for the tcgen05 epilogue: the activation kind is warp-uniform, so dispatch ONCE per 32-column chunk
+// to a loop specialised on it.  (A per-element `switch` unrolled 32x made the kernel 16k SASS instructions and
+// instruction-fetch bound: stall_no_inst dominated the first ncu capture, profiles/r01_conv_epilogue_icache.md.)
+template <int ACT>
+__device__ __forceinline__ void act_chunk(float (&v)[32], float param) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], ACT, param);
+}
+__device__ __forceinline__ void act_chunk_dispatch(float (&v)[32], int act, float param) {
+  switch (act) {  // warp-uniform
+    case SHINEON_ACT_NONE: break;
+    case SHINEON_ACT_RELU: act_chunk<SHINEON_ACT_RELU>(v, param); break;
+    case SHINEON_ACT_LEAKY: act_chunk<SHINEON_ACT_LEAKY>(v, param); break;
+    case SHINEON_ACT_GELU: act_chunk<SHINEON_ACT_GELU>(v, param); break;
+    case SHINEON_ACT_SWISH: act_chunk<SHINEON_ACT_SWISH>(v, param); break;
+    case SHINEON_ACT_SINE: act_chunk<SHINEON_ACT_SINE>(v, param); break;
+    case SHINEON_ACT_TANH: act_chunk<SHINEON_ACT_TANH>(v, param); break;
+    default: act_chunk<SHINEON_ACT_SIGMOID>(v, param); break;
+  }
+}
+
+// Stores `cnt` (<= 32) consecutive channels of one pixel; the vector path needs cnt == 32 (or a multiple of 8
+// for planes / 4 for f32) and an aligned base, which every 64-padded layer satisfies.
+template <int FMT>
+__device__ __forceinline__ void store_planes_vec(const float (&vals)[32], int cnt, plane_t* yh, plane_t* yl, long base) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    if (i < cnt) {
+      __align__(16) plane_t hi[8];
+      __align__(16) plane_t lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split16(vals[i + j], FMT, hi[j], lo[j]);
+      *reinterpret_cast<uint4*>(yh + base + i) = *reinterpret_cast<const uint4*>(hi);
+      if (yl) *reinterpret_cast<uint4*>(yl + base + i) = *reinterpret_cast<const uint4*>(lo);
+    }
+  }
+}
+
+__device__ __forceinline__ void conv_store_row(const float (&vals)[32], int c_first, int cnt, long pix, const ConvArgs& a) {
   const long base = pix * a.out_cstride + a.out_coffset + c_first;
   if (a.y_f32) {
     float* dst = a.y_f32 + base;
@@ -199,23 +237,20 @@ __device__ __forceinline__ void conv_store_row(const float* vals, int c_first, i
     }
   }
   if (a.y_hi) {
-    const bool vec = (cnt & 7) == 0 && (base & 7) == 0;
+    if ((cnt & 7) == 0 && (base & 7) == 0) {
+      if (a.fmt == SHINEON_FMT_FP16)
+        store_planes_vec<SHINEON_FMT_FP16>(vals, cnt, a.y_hi, a.y_lo, base);
+      else
+        store_planes_vec<SHINEON_FMT_BF16>(vals, cnt, a.y_hi, a.y_lo, base);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      if (i >= cnt) break;
-      __align__(16) plane_t hi[8];
-      __align__(16) plane_t lo[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) split16(i + j < cnt ? vals[i + j] : 0.f, a.fmt, hi[j], lo[j]);
-      if (vec) {
-        *reinterpret_cast<uint4*>(a.y_hi + base + i) = *reinterpret_cast<const uint4*>(hi);
-        if (a.y_lo) *reinterpret_cast<uint4*>(a.y_lo + base + i) = *reinterpret_cast<const uint4*>(lo);
-      } else {
-        for (int j = 0; j < 8 && i + j < cnt; ++j) {
-          a.y_hi[base + i + j] = hi[j];
-          if (a.y_lo) a.y_lo[base + i + j] = lo[j];
+      for (int i = 0; i < 32; ++i)
+        if (i < cnt) {
+          plane_t h, l;
+          split16(vals[i], a.fmt, h, l);
+          a.y_hi[base + i] = h;
+          if (a.y_lo) a.y_lo[base + i] = l;
         }
-      }
     }
   }
 }
@@ -235,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[BN], s_scale[BN], s_shift[BN];  // this CTA's output-channel window
 
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -265,6 +301,15 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(&tmem_slot));
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN; i += kThreads - 64) {
+      const int c = cn0 + i;
+      const bool ok = c < a.Cout;
+      s_bias[i] = (ok && a.bias) ? __ldg(a.bias + c) : 0.f;
+      s_scale[i] = (ok && a.scale) ? __ldg(a.scale + c) : 1.f;
+      s_shift[i] = (ok && a.scale) ? __ldg(a.shift + c) : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -349,14 +394,19 @@ __global__ void __launch_bounds__(kThreads, 1)
       else
         tmem_ld16(taddr, v);
       tmem_ld_wait();
-      if (row_ok) {
-        const int cnt = min(kChunk, a.Cout - (cn0 + c0));
-        float vals[32];
+      const int cnt = min(kChunk, a.Cout - (cn0 + c0));  // warp-uniform
+      float vals[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        vals[i] = (i < kChunk) ? fmaf(__uint_as_float(v[i]), a.acc_scale, s_bias[c0 + (i < kChunk ? i : 0)]) : 0.f;
+      act_chunk_dispatch(vals, a.pre_act, a.act_param);
+      if (a.scale != nullptr) {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          vals[i] = (i < cnt) ? conv_epilogue_value(__uint_as_float(v[i]), cn0 + c0 + i, a) : 0.f;
-        conv_store_row(vals, cn0 + c0, cnt, pix, a);
+          if (i < kChunk) vals[i] = fmaf(vals[i], s_scale[c0 + i], s_shift[c0 + i]);
       }
+      act_chunk_dispatch(vals, a.post_act, a.act_param);
+      if (row_ok) conv_store_row(vals, cn0 + c0, cnt, pix, a);
     }
   }
 
