@@ -42,43 +42,46 @@ __global__ void __launch_bounds__(256)
 // MMA on zero padding.  Instead the layout conversion writes, per OUTPUT pixel, the K-vector
 //   k = (fy*kw + fx)*C + c   (tap-major, channel-minor; zero for out-of-image taps and k >= kh*kw*C)
 // so the convolution becomes a 1x1 GEMM with K = pad64(kh*kw*C).
+template <int FMT>
 __global__ void __launch_bounds__(256)
     nchw_im2col_planes_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                               plane_t* __restrict__ yh, plane_t* __restrict__ yl, int H, int W, int kh, int kw,
-                              int stride, int pad, int Ho, int Wo, int kpad, int act, float act_param, int fmt) {
-  const int n = blockIdx.y;
+                              int stride, int pad, int Ho, int Wo, int kpad, int act, float act_param) {
+  // grid: x = (k-group, output column) tiles, y = output row, z = image; output column fastest so neighbouring
+  // threads read neighbouring input columns of the same NCHW channel plane
+  const int n = blockIdx.z, oh = blockIdx.y;
+  const int groups = kpad >> 3;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= Wo * groups) return;
+  const int g = t / Wo, ow = t - g * Wo;
   const int C = C0 + C1;
   const int K = kh * kw * C;
-  const int groups = kpad / 8;
-  const int HWo = Ho * Wo;
-  const long HW = (long)H * W;
-  const long total = (long)HWo * groups;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const int p = (int)(e % HWo);  // pixel fastest: neighbouring threads read neighbouring input columns
-    const int g = (int)(e / HWo);
-    const int oh = p / Wo, ow = p - oh * Wo;
-    __align__(16) plane_t hi[8];
-    __align__(16) plane_t lo[8];
+  const int HW = H * W;
+  int k = g * 8;
+  int tap = k / C, c = k - tap * C;
+  int fy = tap / kw, fx = tap - fy * kw;
+  __align__(16) plane_t hi[8];
+  __align__(16) plane_t lo[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      float v = 0.f;
-      if (k < K) {
-        const int tap = k / C, c = k - tap * C;
-        const int fy = tap / kw, fx = tap - fy * kw;
-        const int iy = oh * stride + fy - pad, ix = ow * stride + fx - pad;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-          v = c < C0 ? __ldg(x0 + ((long)n * C0 + c) * HW + (long)iy * W + ix)
-                     : __ldg(x1 + ((long)n * C1 + (c - C0)) * HW + (long)iy * W + ix);
-          v = apply_act(v, act, act_param);
-        }
+  for (int j = 0; j < 8; ++j, ++k) {
+    float v = 0.f;
+    if (k < K) {
+      const int iy = oh * stride + fy - pad, ix = ow * stride + fx - pad;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        v = c < C0 ? __ldg(x0 + ((long)n * C0 + c) * HW + iy * W + ix)
+                   : __ldg(x1 + ((long)n * C1 + (c - C0)) * HW + iy * W + ix);
+        v = apply_act(v, act, act_param);
       }
-      split16(v, fmt, hi[j], lo[j]);
     }
-    const long o = ((long)n * HWo + p) * kpad + g * 8;
-    *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
-    if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
+    split16(v, FMT, hi[j], lo[j]);
+    if (++c == C) {  // next tap
+      c = 0;
+      if (++fx == kw) { fx = 0; ++fy; }
+    }
   }
+  const long o = (((long)n * Ho + oh) * Wo + ow) * kpad + g * 8;
+  *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
+  if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // ------------------------------------------------------------------------------ tap-stacked 3x3 conv: col2im
@@ -149,11 +152,12 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Pass 2: y = act((x - mean) * rsqrt(var + eps)); 4 channels per thread when C % 4 == 0.
+// Pass 2: y = act((x - mean) * rsqrt(var + eps)); 4 channels per thread (C % 4 == 0) or 1.
+template <int FMT, int ACT, int VEC>  // ACT < 0: runtime activation id
 __global__ void __launch_bounds__(256)
     instnorm_apply_kernel(const float* __restrict__ x, const double* __restrict__ ws, float* __restrict__ yf,
                           plane_t* __restrict__ yh, plane_t* __restrict__ yl, int HW, int C, int cpad,
-                          float eps, int do_norm, int act, float act_param, int fmt) {
+                          float eps, int do_norm, int act_rt, float act_param) {
   extern __shared__ float s_tab[];  // mean[C], rstd[C]
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -170,42 +174,43 @@ __global__ void __launch_bounds__(256)
     s_tab[C + c] = rstd;
   }
   __syncthreads();
-  const int vecC = (C % 4 == 0) ? 4 : 1;
-  const int cg = C / vecC;
-  const long total = (long)HW * cg;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const int g = (int)(e % cg);
-    const long p = e / cg;
-    const long xi = ((long)n * HW + p) * C + g * vecC;
-    float v[4];
-    if (vecC == 4) {
+  const int cg = C / VEC;
+  const unsigned total = (unsigned)HW * (unsigned)cg;
+  const int act = ACT < 0 ? act_rt : ACT;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const unsigned p = e / (unsigned)cg;
+    const int g = (int)(e - p * (unsigned)cg);
+    const long xi = ((long)n * HW + p) * C + g * VEC;
+    float v[VEC];
+    if (VEC == 4) {
       float4 t = *reinterpret_cast<const float4*>(x + xi);
       v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else {
       v[0] = x[xi];
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j < vecC) {
-        const int c = g * vecC + j;
-        v[j] = apply_act((v[j] - s_tab[c]) * s_tab[C + c], act, act_param);
-      }
+    for (int j = 0; j < VEC; ++j) {
+      const int c = g * VEC + j;
+      v[j] = apply_act((v[j] - s_tab[c]) * s_tab[C + c], act, act_param);
+    }
     if (yf) {
-      if (vecC == 4)
+      if (VEC == 4)
         *reinterpret_cast<float4*>(yf + xi) = make_float4(v[0], v[1], v[2], v[3]);
       else
         yf[xi] = v[0];
     }
     if (yh) {
-      const long po = ((long)n * HW + p) * cpad + g * vecC;
+      const long po = ((long)n * HW + p) * cpad + g * VEC;
+      plane_t h[VEC], l[VEC];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j < vecC) {
-          plane_t h, l;
-          split16(v[j], fmt, h, l);
-          yh[po + j] = h;
-          if (yl) yl[po + j] = l;
-        }
+      for (int j = 0; j < VEC; ++j) split16(v[j], FMT, h[j], l[j]);
+      if (VEC == 4) {
+        *reinterpret_cast<uint2*>(yh + po) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        if (yl) *reinterpret_cast<uint2*>(yl + po) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+      } else {
+        yh[po] = h[0];
+        if (yl) yl[po] = l[0];
+      }
     }
   }
 }
@@ -221,61 +226,62 @@ __device__ __forceinline__ void up2_index(int d, int in_size, int& i0, int& i1, 
   l0 = 1.f - l1;
 }
 
+template <int FMT, int ACT>
 __device__ __forceinline__ void load8(const plane_t* __restrict__ h, const plane_t* __restrict__ l, long off,
-                                      int act, float act_param, int fmt, float (&v)[8]) {
-  uint4 uh = *reinterpret_cast<const uint4*>(h + off);
+                                      int act_rt, float act_param, float (&v)[8]) {
+  const int act = ACT < 0 ? act_rt : ACT;
+  uint4 uh = __ldg(reinterpret_cast<const uint4*>(h + off));
   const plane_t* ph = reinterpret_cast<const plane_t*>(&uh);
   if (l) {
-    uint4 ul = *reinterpret_cast<const uint4*>(l + off);
+    uint4 ul = __ldg(reinterpret_cast<const uint4*>(l + off));
     const plane_t* pl = reinterpret_cast<const plane_t*>(&ul);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(join16(ph[j], pl[j], fmt), act, act_param);
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(join16(ph[j], pl[j], FMT), act, act_param);
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(load16(ph[j], fmt), act, act_param);
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(load16(ph[j], FMT), act, act_param);
   }
 }
 
+// grid: x = (output column, 8-channel group) tiles, y = output row, z = image.  No per-thread 64-bit divisions.
+template <int FMT, int ACT>  // ACT < 0: runtime activation id
 __global__ void __launch_bounds__(256)
     upsample2x_cat_kernel(const plane_t* __restrict__ s0h, const plane_t* __restrict__ s0l, int c0pad,
                           const plane_t* __restrict__ s1h, const plane_t* __restrict__ s1l, int c1pad,
                           plane_t* __restrict__ yh, plane_t* __restrict__ yl, int H, int W, int act,
-                          float act_param, int fmt) {
-  const int n = blockIdx.y;
+                          float act_param) {
+  const int n = blockIdx.z, oy = blockIdx.y;
   const int ctot = c0pad + c1pad;
-  const int groups = ctot / 8;
-  const int Ho = 2 * H, Wo = 2 * W;
-  const long total = (long)Ho * Wo * groups;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const int g = (int)(e % groups);
-    const long p = e / groups;
-    const int ox = (int)(p % Wo), oy = (int)(p / Wo);
-    int y0, y1, x0, x1;
-    float ly0, ly1, lx0, lx1;
-    up2_index(oy, H, y0, y1, ly0, ly1);
-    up2_index(ox, W, x0, x1, lx0, lx1);
-    const int c = g * 8;
-    const plane_t *sh, *sl;
-    int cp, cc;
-    if (c < c0pad) { sh = s0h; sl = s0l; cp = c0pad; cc = c; } else { sh = s1h; sl = s1l; cp = c1pad; cc = c - c0pad; }
-    const long rb = (long)n * H * W;
-    float v00[8], v01[8], v10[8], v11[8];
-    load8(sh, sl, (rb + (long)y0 * W + x0) * cp + cc, act, act_param, fmt, v00);
-    load8(sh, sl, (rb + (long)y0 * W + x1) * cp + cc, act, act_param, fmt, v01);
-    load8(sh, sl, (rb + (long)y1 * W + x0) * cp + cc, act, act_param, fmt, v10);
-    load8(sh, sl, (rb + (long)y1 * W + x1) * cp + cc, act, act_param, fmt, v11);
-    __align__(16) plane_t hi[8];
-    __align__(16) plane_t lo[8];
+  const int groups = ctot >> 3;
+  const int Wo = 2 * W;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= Wo * groups) return;
+  const int ox = t / groups, g = t - ox * groups;
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  up2_index(oy, H, y0, y1, ly0, ly1);
+  up2_index(ox, W, x0, x1, lx0, lx1);
+  const int c = g * 8;
+  const plane_t *sh, *sl;
+  int cp, cc;
+  if (c < c0pad) { sh = s0h; sl = s0l; cp = c0pad; cc = c; } else { sh = s1h; sl = s1l; cp = c1pad; cc = c - c0pad; }
+  const long rb = (long)n * H * W;
+  float v00[8], v01[8], v10[8], v11[8];
+  load8<FMT, ACT>(sh, sl, (rb + y0 * W + x0) * cp + cc, act, act_param, v00);
+  load8<FMT, ACT>(sh, sl, (rb + y0 * W + x1) * cp + cc, act, act_param, v01);
+  load8<FMT, ACT>(sh, sl, (rb + y1 * W + x0) * cp + cc, act, act_param, v10);
+  load8<FMT, ACT>(sh, sl, (rb + y1 * W + x1) * cp + cc, act, act_param, v11);
+  __align__(16) plane_t hi[8];
+  __align__(16) plane_t lo[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // ATen: h0lambda*(w0lambda*p00 + w1lambda*p01) + h1lambda*(w0lambda*p10 + w1lambda*p11)
-      float v = ly0 * (lx0 * v00[j] + lx1 * v01[j]) + ly1 * (lx0 * v10[j] + lx1 * v11[j]);
-      split16(v, fmt, hi[j], lo[j]);
-    }
-    const long o = ((long)n * Ho * Wo + p) * ctot + c;
-    *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
-    if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
+  for (int j = 0; j < 8; ++j) {
+    // ATen: h0lambda*(w0lambda*p00 + w1lambda*p01) + h1lambda*(w0lambda*p10 + w1lambda*p11)
+    float v = ly0 * (lx0 * v00[j] + lx1 * v01[j]) + ly1 * (lx0 * v10[j] + lx1 * v11[j]);
+    split16(v, FMT, hi[j], lo[j]);
   }
+  const long o = (((long)n * 2 * H + oy) * Wo + ox) * ctot + c;
+  *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
+  if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // ------------------------------------------------------------------------------ TOM compose
@@ -342,9 +348,14 @@ extern "C" int shineon_nchw_im2col_planes(const float* x0, int C0, const float* 
   SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, "nchw_im2col_planes: bad shape");
   SHINEON_REQUIRE(Ho == (H + 2 * pad - kh) / stride + 1 && Wo == (W + 2 * pad - kw) / stride + 1, "nchw_im2col_planes: Ho/Wo");
   SHINEON_REQUIRE(kpad % 8 == 0 && kpad >= kh * kw * (C0 + C1), "nchw_im2col_planes: kpad %d too small / not a multiple of 8", kpad);
-  dim3 grid(grid_x((long)Ho * Wo * (kpad / 8), 256), N);
-  nchw_im2col_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, kh,
-                                                                   kw, stride, pad, Ho, Wo, kpad, act, act_param, plane_fmt);
+  SHINEON_REQUIRE(Ho <= 65535, "nchw_im2col_planes: Ho too large");
+  dim3 grid(cdiv(Wo * (kpad / 8), 256), Ho, N);
+  if (plane_fmt == SHINEON_FMT_FP16)
+    nchw_im2col_planes_kernel<SHINEON_FMT_FP16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, kh, kw, stride, pad, Ho, Wo, kpad, act, act_param);
+  else
+    nchw_im2col_planes_kernel<SHINEON_FMT_BF16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, kh, kw, stride, pad, Ho, Wo, kpad, act, act_param);
   return after_launch("nchw_im2col_planes_kernel");
 }
 
@@ -388,10 +399,27 @@ extern "C" int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, vo
     if (rc) return rc;
   }
   const int vecC = (C % 4 == 0) ? 4 : 1;
+  SHINEON_REQUIRE((long)HW * (C / vecC) < (1l << 31), "instnorm_act: image too large");
   dim3 grid(grid_x((long)HW * (C / vecC), 256), N);
-  instnorm_apply_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(x, stats_ws, y_f32, (plane_t*)y_hi,
-                                                                     (plane_t*)y_lo, HW, C, cpad, eps, do_norm,
-                                                                     act, act_param, plane_fmt);
+  const size_t sm = 2 * C * sizeof(float);
+  cudaStream_t st = stream;
+#define SHINEON_IN_APPLY(F, A, V)                                                                                   \
+  instnorm_apply_kernel<F, A, V><<<grid, 256, sm, st>>>(x, stats_ws, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, \
+                                                         cpad, eps, do_norm, act, act_param)
+#define SHINEON_IN_ACT(F, V)                                              \
+  switch (act) {                                                          \
+    case SHINEON_ACT_NONE: SHINEON_IN_APPLY(F, SHINEON_ACT_NONE, V); break; \
+    case SHINEON_ACT_RELU: SHINEON_IN_APPLY(F, SHINEON_ACT_RELU, V); break; \
+    case SHINEON_ACT_GELU: SHINEON_IN_APPLY(F, SHINEON_ACT_GELU, V); break; \
+    default: SHINEON_IN_APPLY(F, -1, V); break;                           \
+  }
+  if (plane_fmt == SHINEON_FMT_FP16) {
+    if (vecC == 4) { SHINEON_IN_ACT(SHINEON_FMT_FP16, 4) } else { SHINEON_IN_ACT(SHINEON_FMT_FP16, 1) }
+  } else {
+    if (vecC == 4) { SHINEON_IN_ACT(SHINEON_FMT_BF16, 4) } else { SHINEON_IN_ACT(SHINEON_FMT_BF16, 1) }
+  }
+#undef SHINEON_IN_ACT
+#undef SHINEON_IN_APPLY
   return after_launch("instnorm_apply_kernel");
 }
 
@@ -405,10 +433,22 @@ extern "C" int shineon_upsample2x_cat(const void* s0_hi, const void* s0_lo, int 
   SHINEON_REQUIRE(s1_hi == nullptr || (s1_lo == nullptr) == (s0_lo == nullptr), "upsample2x_cat: s1 lo mismatch");
   SHINEON_REQUIRE(c0pad > 0 && c0pad % 8 == 0 && c1pad % 8 == 0, "upsample2x_cat: channel pads must be multiples of 8");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "upsample2x_cat: bad shape");
-  dim3 grid(grid_x((long)4 * H * W * ((c0pad + c1pad) / 8), 256), N);
-  upsample2x_cat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const plane_t*)s0_hi, (const plane_t*)s0_lo, c0pad, (const plane_t*)s1_hi,
-      (const plane_t*)s1_lo, c1pad, (plane_t*)y_hi, (plane_t*)y_lo, H, W, act, act_param, plane_fmt);
+  SHINEON_REQUIRE(2 * H <= 65535, "upsample2x_cat: H too large");
+  dim3 grid(cdiv(2 * W * ((c0pad + c1pad) / 8), 256), 2 * H, N);
+#define SHINEON_UP(F, A)                                                                                              \
+  upsample2x_cat_kernel<F, A><<<grid, 256, 0, (cudaStream_t)stream>>>(                                               \
+      (const plane_t*)s0_hi, (const plane_t*)s0_lo, c0pad, (const plane_t*)s1_hi, (const plane_t*)s1_lo, c1pad,      \
+      (plane_t*)y_hi, (plane_t*)y_lo, H, W, act, act_param)
+  if (plane_fmt == SHINEON_FMT_FP16) {
+    if (act == SHINEON_ACT_NONE) SHINEON_UP(SHINEON_FMT_FP16, SHINEON_ACT_NONE);
+    else if (act == SHINEON_ACT_RELU) SHINEON_UP(SHINEON_FMT_FP16, SHINEON_ACT_RELU);
+    else SHINEON_UP(SHINEON_FMT_FP16, -1);
+  } else {
+    if (act == SHINEON_ACT_NONE) SHINEON_UP(SHINEON_FMT_BF16, SHINEON_ACT_NONE);
+    else if (act == SHINEON_ACT_RELU) SHINEON_UP(SHINEON_FMT_BF16, SHINEON_ACT_RELU);
+    else SHINEON_UP(SHINEON_FMT_BF16, -1);
+  }
+#undef SHINEON_UP
   return after_launch("upsample2x_cat_kernel");
 }
 

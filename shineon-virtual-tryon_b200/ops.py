@@ -64,11 +64,13 @@ _DTYPES = {_lib.FMT_BF16: torch.bfloat16, _lib.FMT_FP16: torch.float16}
 class Planes:
     """NHWC activation as 16-bit hi (+ lo) planes [N,H,W,cpad]; x ~= hi + lo."""
 
-    def __init__(self, N, H, W, C, prec=None, device="cuda", cpad=None):
+    def __init__(self, N, H, W, C, prec=None, device="cuda", cpad=None, zero_pad=True):
         self.fmt, split = resolve_precision(prec)
         self.N, self.H, self.W, self.C = N, H, W, C
         self.cpad = cpad64(C) if cpad is None else cpad
-        alloc = torch.empty if self.cpad == C else torch.zeros  # padding channels must stay zero
+        # padding channels must hold zeros (they meet zero weights, but NaN * 0 = NaN); producers that write the
+        # padding themselves pass zero_pad=False
+        alloc = torch.empty if (self.cpad == C or not zero_pad) else torch.zeros
         self.hi = alloc(N, H, W, self.cpad, dtype=_DTYPES[self.fmt], device=device)
         self.lo = alloc(N, H, W, self.cpad, dtype=_DTYPES[self.fmt], device=device) if split else None
 
@@ -326,7 +328,7 @@ def nchw_im2col_planes(x0, x1, kh, kw, stride, pad, act=None, act_param=0.0, pre
         x1 = _req(x1, name="x1")
         C1 = x1.shape[1]
     Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
-    out = Planes(N, Ho, Wo, kh * kw * (C0 + C1), prec=prec, device=x0.device)
+    out = Planes(N, Ho, Wo, kh * kw * (C0 + C1), prec=prec, device=x0.device, zero_pad=False)  # kernel writes all of kpad
     check(_lib.load().shineon_nchw_im2col_planes(_p(x0), C0, _p(x1), C1, _p(out.hi), _p(out.lo), N, H, W, kh, kw, stride,
                                                  pad, Ho, Wo, out.cpad, ACT[act], float(act_param), out.fmt, _stream()),
           "shineon_nchw_im2col_planes")
