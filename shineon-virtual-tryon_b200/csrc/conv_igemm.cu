@@ -41,6 +41,7 @@ struct ConvArgs {
   int kh, kw, stride, pad_h, pad_w;
   int cin_pad, cin_blocks;
   int num_kb, stages;
+  int n_tiles, total_tiles;  // channel tiles per pixel tile, pixel tiles * channel tiles
   // epilogue
   const float* bias;
   const float* scale;
@@ -256,6 +257,14 @@ __device__ __forceinline__ void conv_store_row(const float (&vals)[32], int c_fi
 }
 
 // -------------------------------------------------------------------------------------- kernel
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Persistent: one CTA per SM walks output tiles (tile = blockIdx.x + i*gridDim.x, channel tile fastest so that
+// neighbouring CTAs share the same activation tile in L2).  Two TMEM accumulators: the epilogue of tile i
+// (TMEM -> registers -> global) overlaps the TMA/MMA main loop of tile i+1.
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_igemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
@@ -264,27 +273,20 @@ __global__ void __launch_bounds__(kThreads, 1)
   constexpr int kBBytes = BN * kBlockK * 2;
   constexpr int kPlanes = SPLIT ? 2 : 1;
   constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  constexpr int kAccCols = BN < 32 ? 32 : BN;  // TMEM columns per accumulator
+  constexpr int kTmemCols = 2 * kAccCols;      // double-buffered (<= 512)
   const uint32_t kIdesc = a.idesc;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 1];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_bias[BN], s_scale[BN], s_shift[BN];  // this CTA's output-channel window
+  __shared__ float s_bias[BN], s_scale[BN], s_shift[BN];  // current tile's output-channel window
 
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = a.stages;
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]),
-                 bar_tmem = smem_u32(&bars[2 * kMaxStages]);
-
-  // tile coordinates
-  const int mt = blockIdx.x;
-  const int tw = mt % a.tiles_w;
-  const int th = (mt / a.tiles_w) % a.tiles_h;
-  const int tn = mt / (a.tiles_w * a.tiles_h);
-  const int n0 = tn * a.nb, h0 = th * a.bh, w0 = tw * a.bw;
-  const int cn0 = blockIdx.y * BN;
+                 bar_tfull = smem_u32(&bars[2 * kMaxStages]), bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmAh);
@@ -297,122 +299,153 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_tmem, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);   // one tcgen05.commit
+      mbar_init(bar_tempty + 8 * b, 4);  // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(&tmem_slot));
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += kThreads - 64) {
-      const int c = cn0 + i;
-      const bool ok = c < a.Cout;
-      s_bias[i] = (ok && a.bias) ? __ldg(a.bias + c) : 0.f;
-      s_scale[i] = (ok && a.scale) ? __ldg(a.scale + c) : 1.f;
-      s_shift[i] = (ok && a.scale) ? __ldg(a.shift + c) : 0.f;
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = tmem_slot;
+  const uint32_t tmem_base = tmem_slot;
+  const int tiles_hw = a.tiles_w * a.tiles_h;
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       const uint32_t a_rows = a.nb * a.bh * a.bw;
       const uint32_t tx = kPlanes * (a_rows * (kBlockK * 2) + kBBytes);
-      for (int kb = 0; kb < a.num_kb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const uint32_t full = bar_full + 8 * s;
-        mbar_expect_tx(full, tx);
-        const uint32_t sA = tiles + s * kStageBytes;
-        const uint32_t sB = sA + kPlanes * kABytes;
-        const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks;
-        const int fy = tap / a.kw, fx = tap - fy * a.kw;
-        if (a.stride == 1) {
-          const int cx = w0 + fx - a.pad_w, cy = h0 + fy - a.pad_h;
-          tma_load_4d(sA, &tmAh, full, cb * kBlockK, cx, cy, n0);
-          if (SPLIT) tma_load_4d(sA + kABytes, &tmAl, full, cb * kBlockK, cx, cy, n0);
-        } else {
-          // input row 2*oh + fy - pad = 2*(oh + ay) + py ; same for columns
-          const int ty = fy - a.pad_h, tx_ = fx - a.pad_w;
-          const int py = ty & 1, px = tx_ & 1;
-          const int ay = (ty - py) >> 1, ax = (tx_ - px) >> 1;
-          const int cc = px * a.cin_pad + cb * kBlockK;
-          tma_load_5d(sA, &tmAh, full, cc, w0 + ax, py, h0 + ay, n0);
-          if (SPLIT) tma_load_5d(sA + kABytes, &tmAl, full, cc, w0 + ax, py, h0 + ay, n0);
+      uint32_t g = 0;  // running K-block counter across tiles (ring position)
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+        const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, tn = mt / tiles_hw;
+        const int n0 = tn * a.nb, h0 = th * a.bh, w0 = tw * a.bw, cn0 = nt * BN;
+        for (int kb = 0; kb < a.num_kb; ++kb, ++g) {
+          const int s = g % S;
+          const uint32_t ph = (g / S) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_expect_tx(full, tx);
+          const uint32_t sA = tiles + s * kStageBytes;
+          const uint32_t sB = sA + kPlanes * kABytes;
+          const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks;
+          const int fy = tap / a.kw, fx = tap - fy * a.kw;
+          if (a.stride == 1) {
+            const int cx = w0 + fx - a.pad_w, cy = h0 + fy - a.pad_h;
+            tma_load_4d(sA, &tmAh, full, cb * kBlockK, cx, cy, n0);
+            if (SPLIT) tma_load_4d(sA + kABytes, &tmAl, full, cb * kBlockK, cx, cy, n0);
+          } else {
+            // input row 2*oh + fy - pad = 2*(oh + ay) + py ; same for columns
+            const int ty = fy - a.pad_h, tx_ = fx - a.pad_w;
+            const int py = ty & 1, px = tx_ & 1;
+            const int ay = (ty - py) >> 1, ax = (tx_ - px) >> 1;
+            const int cc = px * a.cin_pad + cb * kBlockK;
+            tma_load_5d(sA, &tmAh, full, cc, w0 + ax, py, h0 + ay, n0);
+            if (SPLIT) tma_load_5d(sA + kABytes, &tmAl, full, cc, w0 + ax, py, h0 + ay, n0);
+          }
+          tma_load_2d(sB, &tmBh, full, kb * kBlockK, cn0);
+          if (SPLIT) tma_load_2d(sB + kBBytes, &tmBl, full, kb * kBlockK, cn0);
         }
-        tma_load_2d(sB, &tmBh, full, kb * kBlockK, cn0);
-        if (SPLIT) tma_load_2d(sB + kBBytes, &tmBl, full, kb * kBlockK, cn0);
       }
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (single thread)
     if (lane == 0) {
-      for (int kb = 0; kb < a.num_kb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(bar_full + 8 * s, ph);
+      uint32_t g = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sA = tiles + s * kStageBytes;
-        const uint32_t sB = sA + kPlanes * kABytes;
+        const uint32_t tmem_acc = tmem_base + buf * kAccCols;
+        for (int kb = 0; kb < a.num_kb; ++kb, ++g) {
+          const int s = g % S;
+          const uint32_t ph = (g / S) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sA = tiles + s * kStageBytes;
+          const uint32_t sB = sA + kPlanes * kABytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t dAh = umma_desc_sw128(sA + k * 32);
-          const uint64_t dBh = umma_desc_sw128(sB + k * 32);
-          umma_f16(tmem_acc, dAh, dBh, kIdesc, (kb | k) != 0);
-          if (SPLIT) {
-            const uint64_t dAl = umma_desc_sw128(sA + kABytes + k * 32);
-            const uint64_t dBl = umma_desc_sw128(sB + kBBytes + k * 32);
-            umma_f16(tmem_acc, dAh, dBl, kIdesc, 1);
-            umma_f16(tmem_acc, dAl, dBh, kIdesc, 1);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t dAh = umma_desc_sw128(sA + k * 32);
+            const uint64_t dBh = umma_desc_sw128(sB + k * 32);
+            umma_f16(tmem_acc, dAh, dBh, kIdesc, (kb | k) != 0);
+            if (SPLIT) {
+              const uint64_t dAl = umma_desc_sw128(sA + kABytes + k * 32);
+              const uint64_t dBl = umma_desc_sw128(sB + kBBytes + k * 32);
+              umma_f16(tmem_acc, dAh, dBl, kIdesc, 1);
+              umma_f16(tmem_acc, dAl, dBh, kIdesc, 1);
+            }
           }
+          umma_commit(bar_empty + 8 * s);  // frees the smem slot once these MMAs retire
         }
-        umma_commit(bar_empty + 8 * s);  // frees the smem slot once these MMAs retire
+        umma_commit(bar_tfull + 8 * buf);  // accumulator complete
       }
-      umma_commit(bar_tmem);  // accumulator complete
     }
   } else {
     // ===================================================== epilogue: TMEM -> registers -> global
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;
     const int wi = r % a.bw, hi_ = (r / a.bw) % a.bh, ni = r / (a.bw * a.bh);
-    const int n = n0 + ni, oh = h0 + hi_, ow = w0 + wi;
-    const bool row_ok = ni < a.nb && n < a.N && oh < a.Ho && ow < a.Wo;
-    const long pix = ((long)n * a.out_H + (oh * a.oh_mul + a.oh_off)) * a.out_W + (ow * a.ow_mul + a.ow_off);
-    mbar_wait(bar_tmem, 0);
-    tc_fence_after();
     constexpr int kChunk = BN < 32 ? BN : 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+      const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, tn = mt / tiles_hw;
+      const int cn0 = nt * BN;
+      const int n = tn * a.nb + ni, oh = th * a.bh + hi_, ow = tw * a.bw + wi;
+      const bool row_ok = ni < a.nb && n < a.N && oh < a.Ho && ow < a.Wo;
+      const long pix = ((long)n * a.out_H + (oh * a.oh_mul + a.oh_off)) * a.out_W + (ow * a.ow_mul + a.ow_off);
+      // stage this tile's bias / folded-BN window (all 4 epilogue warps are past the previous tile's reads)
+      epi_bar_sync();
+      for (int i = threadIdx.x - 64; i < BN; i += 128) {
+        const int c = cn0 + i;
+        const bool ok = c < a.Cout;
+        s_bias[i] = (ok && a.bias) ? __ldg(a.bias + c) : 0.f;
+        s_scale[i] = (ok && a.scale) ? __ldg(a.scale + c) : 1.f;
+        s_shift[i] = (ok && a.scale) ? __ldg(a.shift + c) : 0.f;
+      }
+      epi_bar_sync();
+      const int buf = it & 1;
+      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * kAccCols;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += kChunk) {
-      if (cn0 + c0 >= a.Cout) break;  // warp-uniform
-      uint32_t v[32];
-      const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      if (kChunk == 32)
-        tmem_ld32(taddr, v);
-      else
-        tmem_ld16(taddr, v);
-      tmem_ld_wait();
-      const int cnt = min(kChunk, a.Cout - (cn0 + c0));  // warp-uniform
-      float vals[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        vals[i] = (i < kChunk) ? fmaf(__uint_as_float(v[i]), a.acc_scale, s_bias[c0 + (i < kChunk ? i : 0)]) : 0.f;
-      act_chunk_dispatch(vals, a.pre_act, a.act_param);
-      if (a.scale != nullptr) {
+      for (int c0 = 0; c0 < BN; c0 += kChunk) {
+        if (cn0 + c0 >= a.Cout) break;  // warp-uniform
+        uint32_t v[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        if (kChunk == 32)
+          tmem_ld32(taddr, v);
+        else
+          tmem_ld16(taddr, v);
+        tmem_ld_wait();
+        const int cnt = min(kChunk, a.Cout - (cn0 + c0));  // warp-uniform
+        float vals[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (i < kChunk) vals[i] = fmaf(vals[i], s_scale[c0 + i], s_shift[c0 + i]);
+          vals[i] = (i < kChunk) ? fmaf(__uint_as_float(v[i]), a.acc_scale, s_bias[c0 + (i < kChunk ? i : 0)]) : 0.f;
+        act_chunk_dispatch(vals, a.pre_act, a.act_param);
+        if (a.scale != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < kChunk) vals[i] = fmaf(vals[i], s_scale[c0 + i], s_shift[c0 + i]);
+        }
+        act_chunk_dispatch(vals, a.post_act, a.act_param);
+        if (row_ok) conv_store_row(vals, cn0 + c0, cnt, pix, a);
       }
-      act_chunk_dispatch(vals, a.post_act, a.act_param);
-      if (row_ok) conv_store_row(vals, cn0 + c0, cnt, pix, a);
+      // hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_acc);
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------- CUDA-core cross-check
@@ -545,15 +578,36 @@ static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CU
   if (stages < 1) stages = 1;
   a.stages = stages;
   a.idesc = umma_idesc_f16(kBlockM, BN, a.fmt == SHINEON_FMT_FP16 ? 0 : 1);
-  const int smem = stages * kStageBytes + 1024;
-  static int configured_smem = 0;
-  if (smem > configured_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
-    if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "cudaFuncSetAttribute(conv_igemm): %s", cudaGetErrorString(e));
-    configured_smem = 227 * 1024;
+  static int max_dyn_smem = -1;  // per instantiation: opt-in limit minus this kernel's static shared memory
+  if (max_dyn_smem < 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv_igemm_kernel<BN, SPLIT>);
+    if (e == cudaSuccess) {
+      max_dyn_smem = 227 * 1024 - (int)fa.sharedSizeBytes;
+      e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      max_dyn_smem = -1;
+      return fail(SHINEON_ERR_CUDA, "conv_igemm shared-memory opt-in: %s", cudaGetErrorString(e));
+    }
   }
-  dim3 grid(m_tiles, cdiv(a.Cout, BN));
-  conv_igemm_kernel<BN, SPLIT><<<grid, kThreads, smem, stream>>>(tAh, tAl, tBh, tBl, a);
+  while (stages > 1 && stages * kStageBytes + 1024 > max_dyn_smem) --stages;
+  a.stages = stages;
+  const int smem_bytes = stages * kStageBytes + 1024;
+  if (smem_bytes > max_dyn_smem) return fail(SHINEON_ERR_UNSUPPORTED, "conv_igemm: tile does not fit in shared memory");
+  a.n_tiles = cdiv(a.Cout, BN);
+  const long total = (long)m_tiles * a.n_tiles;
+  if (total >= (1l << 31)) return fail(SHINEON_ERR_ARG, "conv2d: too many tiles");
+  a.total_tiles = (int)total;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
+  conv_igemm_kernel<BN, SPLIT><<<grid, kThreads, smem_bytes, stream>>>(tAh, tAl, tBh, tBl, a);
   return after_launch("conv_igemm_kernel");
 }
 
