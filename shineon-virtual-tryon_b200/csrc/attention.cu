@@ -7,81 +7,117 @@
 
 namespace shineon {
 
+// QT query pixels per CTA: K and V rows are read once per CTA and reused for all QT queries (the first version
+// used one query per CTA and was L2-bandwidth bound re-reading V: 15k CTAs x 440 KB).
+template <int QT>
 __global__ void __launch_bounds__(128)
     sagan_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ x, const float* __restrict__ gamma,
                            float* __restrict__ yf, plane_t* __restrict__ yh, plane_t* __restrict__ yl,
                            int HW, int C, int Cq, int cpad, int act, float act_param, int fmt) {
-  extern __shared__ float sm[];  // q[Cq] | e[HW] | red[32]
+  extern __shared__ float sm[];  // q[QT][Cq] | e[QT][HW] | inv[QT]
   float* sq = sm;
-  float* se = sm + Cq;
-  float* red = se + HW;
-  const int n = blockIdx.y, i = blockIdx.x;
+  float* se = sm + QT * Cq;
+  float* sinv = se + QT * HW;
+  const int n = blockIdx.y, i0 = blockIdx.x * QT;
+  const int nq = min(QT, HW - i0);
   const int ld = 2 * Cq + C;
   const float* base = qkv + (long)n * HW * ld;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int c = tid; c < Cq; c += blockDim.x) sq[c] = base[(long)i * ld + c];
+  for (int e = tid; e < QT * Cq; e += 128) {
+    const int q = e / Cq, c = e - q * Cq;
+    sq[e] = q < nq ? base[(long)(i0 + q) * ld + c] : 0.f;
+  }
   __syncthreads();
 
-  // energies
-  float lmax = -INFINITY;
-  for (int j = tid; j < HW; j += blockDim.x) {
+  // energies e[q][j] = <q_q, k_j>
+  for (int j = tid; j < HW; j += 128) {
     const float* kj = base + (long)j * ld + Cq;
-    float acc = 0.f;
+    float acc[QT];
+#pragma unroll
+    for (int q = 0; q < QT; ++q) acc[q] = 0.f;
     if ((Cq & 3) == 0) {
       for (int c = 0; c < Cq; c += 4) {
-        float4 k4 = *reinterpret_cast<const float4*>(kj + c);
-        acc = fmaf(sq[c], k4.x, acc);
-        acc = fmaf(sq[c + 1], k4.y, acc);
-        acc = fmaf(sq[c + 2], k4.z, acc);
-        acc = fmaf(sq[c + 3], k4.w, acc);
+        const float4 k4 = *reinterpret_cast<const float4*>(kj + c);
+#pragma unroll
+        for (int q = 0; q < QT; ++q) {
+          const float* qq = sq + q * Cq + c;
+          acc[q] = fmaf(qq[0], k4.x, acc[q]);
+          acc[q] = fmaf(qq[1], k4.y, acc[q]);
+          acc[q] = fmaf(qq[2], k4.z, acc[q]);
+          acc[q] = fmaf(qq[3], k4.w, acc[q]);
+        }
       }
     } else {
-      for (int c = 0; c < Cq; ++c) acc = fmaf(sq[c], kj[c], acc);
+      for (int c = 0; c < Cq; ++c) {
+        const float kv = kj[c];
+#pragma unroll
+        for (int q = 0; q < QT; ++q) acc[q] = fmaf(sq[q * Cq + c], kv, acc[q]);
+      }
     }
-    se[j] = acc;
-    lmax = fmaxf(lmax, acc);
+#pragma unroll
+    for (int q = 0; q < QT; ++q) se[q * HW + j] = acc[q];
   }
-  lmax = warp_max(lmax);
-  if (lane == 0) red[warp] = lmax;
   __syncthreads();
-  float gmax = red[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) gmax = fmaxf(gmax, red[w]);
-  __syncthreads();
-  float lsum = 0.f;
-  for (int j = tid; j < HW; j += blockDim.x) {
-    float e = expf(se[j] - gmax);
-    se[j] = e;
-    lsum += e;
-  }
-  lsum = warp_sum(lsum);
-  if (lane == 0) red[warp] = lsum;
-  __syncthreads();
-  float gsum = 0.f;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) gsum += red[w];
-  const float inv = 1.f / gsum;
-  const float g = __ldg(gamma);
 
-  // o[c] = sum_j A[j] * v_j[c]; threads stride channels (coalesced rows of V)
-  const float* vbase = base + 2 * Cq;
-  for (int c = tid; c < C; c += blockDim.x) {
-    float a0 = 0.f, a1 = 0.f;
-    int j = 0;
-    for (; j + 1 < HW; j += 2) {
-      a0 = fmaf(se[j], vbase[(long)j * ld + c], a0);
-      a1 = fmaf(se[j + 1], vbase[(long)(j + 1) * ld + c], a1);
+  // softmax over j, one warp per query
+  for (int q = warp; q < QT; q += 4) {
+    float* e = se + q * HW;
+    float m = -INFINITY;
+    for (int j = lane; j < HW; j += 32) m = fmaxf(m, e[j]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < HW; j += 32) {
+      const float p = expf(e[j] - m);
+      e[j] = p;
+      sum += p;
     }
-    if (j < HW) a0 = fmaf(se[j], vbase[(long)j * ld + c], a0);
-    const float o = (a0 + a1) * inv;
-    const long xi = ((long)n * HW + i) * C + c;
-    const float v = apply_act(g * o + x[xi], act, act_param);  // sagan.py:53
-    if (yf) yf[xi] = v;
-    if (yh) {
-      plane_t h, l;
-      split16(v, fmt, h, l);
-      const long po = ((long)n * HW + i) * cpad + c;
-      yh[po] = h;
-      if (yl) yl[po] = l;
+    sum = warp_sum(sum);
+    if (lane == 0) sinv[q] = 1.f / sum;
+  }
+  __syncthreads();
+
+  // o[q][c] = sum_j A[q][j] v_j[c]; 4 consecutive channels per thread (coalesced float4 rows of V)
+  const float g = __ldg(gamma);
+  const float* vbase = base + 2 * Cq;
+  const bool vec = ((C & 3) == 0) && ((ld & 3) == 0) && (((2 * Cq) & 3) == 0);
+  const int cstep = vec ? 4 : 1;
+  for (int c = tid * cstep; c < C; c += 128 * cstep) {
+    float acc[QT][4];
+#pragma unroll
+    for (int q = 0; q < QT; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
+    for (int j = 0; j < HW; ++j) {
+      float4 v4;
+      if (vec)
+        v4 = *reinterpret_cast<const float4*>(vbase + (long)j * ld + c);
+      else
+        v4 = make_float4(vbase[(long)j * ld + c], 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < QT; ++q) {
+        const float aw = se[q * HW + j];
+        acc[q][0] = fmaf(aw, v4.x, acc[q][0]);
+        acc[q][1] = fmaf(aw, v4.y, acc[q][1]);
+        acc[q][2] = fmaf(aw, v4.z, acc[q][2]);
+        acc[q][3] = fmaf(aw, v4.w, acc[q][3]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < QT; ++q) {
+      if (q >= nq) break;
+      const long pix = (long)n * HW + i0 + q;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k >= cstep) break;
+        const float o = acc[q][k] * sinv[q];
+        const float v = apply_act(g * o + x[pix * C + c + k], act, act_param);  // sagan.py:53
+        if (yf) yf[pix * C + c + k] = v;
+        if (yh) {
+          plane_t h, l;
+          split16(v, fmt, h, l);
+          yh[pix * cpad + c + k] = h;
+          if (yl) yl[pix * cpad + c + k] = l;
+        }
+      }
     }
   }
 }
@@ -97,11 +133,16 @@ extern "C" int shineon_sagan_attention(const float* qkv, const float* x, const f
   SHINEON_REQUIRE(qkv && x && gamma && (y_f32 || y_hi), "sagan_attention: null pointer");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && HW > 0 && C > 0 && Cq > 0, "sagan_attention: bad shape");
   SHINEON_REQUIRE(!y_hi || cpad >= C, "sagan_attention: cpad < C");
-  size_t smem = sizeof(float) * (size_t)(Cq + HW + 32);
-  if (smem > 48 * 1024) return fail(SHINEON_ERR_UNSUPPORTED, "sagan_attention: HW=%d too large for this kernel", HW);
   SHINEON_REQUIRE(((2 * Cq + C) & 3) == 0 || (Cq & 3) != 0, "sagan_attention: row stride must keep float4 alignment");
-  dim3 grid(HW, N);
-  sagan_attention_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(qkv, x, gamma, y_f32, (plane_t*)y_hi,
-                                                                   (plane_t*)y_lo, HW, C, Cq, cpad, act, act_param, plane_fmt);
+  auto smem_for = [&](int qt) { return sizeof(float) * ((size_t)qt * Cq + (size_t)qt * HW + qt); };
+  cudaStream_t st = (cudaStream_t)stream;
+#define SHINEON_ATT(QT_)                                                                                            \
+  sagan_attention_kernel<QT_><<<dim3(cdiv(HW, QT_), N), 128, smem_for(QT_), st>>>(                                   \
+      qkv, x, gamma, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, Cq, cpad, act, act_param, plane_fmt)
+  if (smem_for(16) <= 40 * 1024) SHINEON_ATT(16);
+  else if (smem_for(4) <= 40 * 1024) SHINEON_ATT(4);
+  else if (smem_for(1) <= 48 * 1024) SHINEON_ATT(1);
+  else return fail(SHINEON_ERR_UNSUPPORTED, "sagan_attention: HW=%d too large for this kernel", HW);
+#undef SHINEON_ATT
   return after_launch("sagan_attention_kernel");
 }
