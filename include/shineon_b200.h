@@ -151,8 +151,10 @@ int shineon_pack_conv_weight(const float* w, void* w_hi, void* w_lo, int Cout, i
 typedef struct shineon_conv2d_params {
   /* input activation, NHWC planes [N,H,W,cin_pad] bf16 */
   const void* x_hi;
-  const void* x_lo; /* NULL => single-bf16 products (fast mode) */
+  const void* x_lo; /* NULL => single 16-bit products (fast modes) */
   int N, H, W, cin_pad;
+  int x_cstride; /* channels between consecutive pixels of x (0 = cin_pad); lets a conv read a 64-aligned channel
+                    window of a wider concat buffer (the pointers already point at the window's first channel) */
   /* packed weights [Cout][kh*kw][cin_pad] bf16 */
   const void* w_hi;
   const void* w_lo; /* NULL unless x_lo given */
@@ -194,6 +196,10 @@ int shineon_conv2d_direct_fwd(const shineon_conv2d_params* p, shineon_stream_t s
 int shineon_nchw_to_planes(const float* x0, int C0, const float* x1, int C1, void* y_hi, void* y_lo, int N,
                            int H, int W, int cpad, int act, float act_param, int plane_fmt,
                            shineon_stream_t stream);
+
+/* Inverse: planes [N,H,W,(x_cstride)] (pointers at the first channel of the window) -> f32 NCHW [N,C,H,W]. */
+int shineon_planes_to_nchw(const void* x_hi, const void* x_lo, int x_cstride, float* y, int N, int H, int W, int C,
+                           int plane_fmt, shineon_stream_t stream);
 
 /* Same, but written as the im2col matrix of a (kh x kw, stride, pad) convolution: y planes [N,Ho,Wo,kpad] with
  * k = (fy*kw+fx)*C + c.  Turns a small-Cin first layer (Cin 3/10/22) into a dense 1x1 GEMM. */
@@ -258,6 +264,27 @@ int shineon_linear_tanh(const float* x, const float* weight, const float* bias, 
 int shineon_tom_compose(const float* unet_out, int Cout, const float* cloth, const float* warped_prev,
                         float* p_rendereds, float* tryon_masks, float* p_tryons, float* flow_masks, int B,
                         int H, int W, int n_frames, int frame, int flow_warp, shineon_stream_t stream);
+
+/* ------------------------------------------------------------------ */
+/* F2: FlowNet2 glue (models/flownet2_pytorch/models.py:127-192, models/flownet.py:42-63) */
+/* ------------------------------------------------------------------ */
+/* inputs f32 [B,3,2,H,W] -> x f32 NCHW [B,6,H,W] = cat(frame0, frame1) of (inputs - mean_{f,h,w}) / rgb_max.
+ * ws: 3*B doubles of scratch. */
+int shineon_flownet_normalize(const float* inputs, float* x, double* ws, int B, int H, int W, float rgb_max,
+                              shineon_stream_t stream);
+/* nn.Upsample(scale_factor=4, bilinear|nearest) of the first two channels of src (f32 NHWC [B,h,w,src_cstride]),
+ * times `mul`; dst f32 NCHW [B,2,4h,4w]. */
+int shineon_upsample4x_flow(const float* src, int src_cstride, float* dst, int B, int h, int w, float mul,
+                            int bilinear, shineon_stream_t stream);
+/* FlowNetS input: out [B,12,H,W] = [x | Resample2d(x[:,3:6], flow) | flow/div_flow | ChannelNorm(x[:,:3]-resampled)]. */
+int shineon_flownet_warp_concat(const float* x, const float* flow, float* out, int B, int H, int W, float div_flow,
+                                shineon_stream_t stream);
+/* FlowNetFusion input: out [B,11,H,W] = [x[:,:3] | flow_sd | flow_s2 | |flow_sd| | |flow_s2| | diff_sd | diff_s2]. */
+int shineon_flownet_fusion_concat(const float* x, const float* flow_sd, const float* flow_s2, float* out, int B, int H,
+                                  int W, shineon_stream_t stream);
+/* conf [B,1,H,W] = (sum_c (im1 - Resample2d(im2, flow))^2 < threshold) as 0/1 floats. */
+int shineon_flow_confidence(const float* im1, const float* im2, const float* flow, float* conf, int B, int C, int H,
+                            int W, float threshold, shineon_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -45,3 +45,13 @@ def gmm_inputs(name, H=256, W=192):
 
 def subsample(t, step=4):
     return t[..., ::step, ::step].contiguous()
+
+
+def flownet2_inputs(B=1, H=256, W=192):
+    """Two smooth-ish frames in [0,1] (the second a shifted / perturbed copy of the first) as [B,3,2,H,W]."""
+    g = _g("flownet2")
+    base = torch.nn.functional.interpolate(torch.rand(B, 3, H // 8 + 2, W // 8 + 2, generator=g), size=(H + 16, W + 16),
+                                           mode="bilinear", align_corners=False)
+    im1 = base[:, :, 8:8 + H, 8:8 + W] + 0.05 * torch.rand(B, 3, H, W, generator=g)
+    im2 = base[:, :, 5:5 + H, 10:10 + W] + 0.05 * torch.rand(B, 3, H, W, generator=g)
+    return torch.stack([im1, im2], dim=2).contiguous().clamp(0, 1)

@@ -62,5 +62,22 @@ def main():
                   warped_mask=cases.subsample(wmask))
 
 
+def flownet2_golden():
+    """FlowNet2 (162.5 M parameters) through the reference module graph; its three CUDA-only ops run through
+    oracle/flow_ops.py (which tests/test_ref_ext_gpu.py pins against the reference's own kernels)."""
+    from models.flownet2_pytorch import models as fm
+    from oracle import flownet2 as ofn
+
+    with torch.no_grad():
+        net = fm.FlowNet2().eval()
+        shapes = weights.shapes_of(net)
+        net.load_state_dict(weights.synth_state_dict(shapes, SEED), strict=True)
+        inp = cases.flownet2_inputs()
+        flow = net(inp)
+        conf = ofn.flow_confidence(inp[:, :, 0], inp[:, :, 1], flow)  # FlowNet.compute_flow_and_conf (flownet.py:55)
+        _save("flownet2", shapes, flow=cases.subsample(flow, 2), conf=cases.subsample(conf, 2))
+
+
 if __name__ == "__main__":
     main()
+    flownet2_golden()

@@ -23,7 +23,7 @@ class TpsTables(C.Structure):
 
 class Conv2dParams(C.Structure):
     _fields_ = [
-        ("x_hi", c_p), ("x_lo", c_p), ("N", c_i), ("H", c_i), ("W", c_i), ("cin_pad", c_i),
+        ("x_hi", c_p), ("x_lo", c_p), ("N", c_i), ("H", c_i), ("W", c_i), ("cin_pad", c_i), ("x_cstride", c_i),
         ("w_hi", c_p), ("w_lo", c_p), ("Cout", c_i), ("kh", c_i), ("kw", c_i), ("stride", c_i), ("pad_h", c_i), ("pad_w", c_i),
         ("Ho", c_i), ("Wo", c_i),
         ("bias", c_p), ("scale", c_p), ("shift", c_p), ("pre_act", c_i), ("post_act", c_i), ("act_param", c_f),
@@ -56,6 +56,7 @@ SIGNATURES = {
     "shineon_conv2d_igemm_fwd": [C.POINTER(Conv2dParams), c_p],
     "shineon_conv2d_direct_fwd": [C.POINTER(Conv2dParams), c_p],
     "shineon_nchw_to_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
+    "shineon_planes_to_nchw": [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_nchw_im2col_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
                                    c_f, c_i, c_p],
     "shineon_col2im3x3": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
@@ -64,6 +65,11 @@ SIGNATURES = {
     "shineon_sagan_attention": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     "shineon_l2norm_correlation": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_linear_tanh": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_flownet_normalize": [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p],
+    "shineon_upsample4x_flow": [c_p, c_i, c_p, c_i, c_i, c_i, c_f, c_i, c_p],
+    "shineon_flownet_warp_concat": [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p],
+    "shineon_flownet_fusion_concat": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
+    "shineon_flow_confidence": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
     "shineon_tom_compose": [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
 }
 _RESTYPES = {"shineon_last_error": C.c_char_p, "shineon_launch_count": C.c_uint64}

@@ -39,7 +39,7 @@ struct ConvArgs {
   int tiles_w, tiles_h;
   int N, Ho, Wo, Cout;
   int kh, kw, stride, pad_h, pad_w;
-  int cin_pad, cin_blocks;
+  int cin_pad, cin_blocks, x_cstride;
   int num_kb, stages;
   int n_tiles, total_tiles;  // channel tiles per pixel tile, pixel tiles * channel tiles
   // epilogue
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             const int ty = fy - a.pad_h, tx_ = fx - a.pad_w;
             const int py = ty & 1, px = tx_ & 1;
             const int ay = (ty - py) >> 1, ax = (tx_ - px) >> 1;
-            const int cc = px * a.cin_pad + cb * kBlockK;
+            const int cc = px * a.x_cstride + cb * kBlockK;
             tma_load_5d(sA, &tmAh, full, cc, w0 + ax, py, h0 + ay, n0);
             if (SPLIT) tma_load_5d(sA + kABytes, &tmAl, full, cc, w0 + ax, py, h0 + ay, n0);
           }
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(128)
       for (int fx = 0; fx < a.kw; ++fx) {
         const int ix = ow * a.stride + fx - a.pad_w;
         if (ix < 0 || ix >= W) continue;
-        const long xo = (((long)n * H + iy) * W + ix) * a.cin_pad;
+        const long xo = (((long)n * H + iy) * W + ix) * a.x_cstride;
         const long wo = ((long)c * a.kh * a.kw + fy * a.kw + fx) * a.cin_pad;
         for (int ci = 0; ci < a.cin_pad; ++ci) {
           const float xhv = load16(xh[xo + ci], a.fmt), whv = load16(wh[wo + ci], a.fmt);
@@ -629,6 +629,8 @@ static int fill_args(const shineon_conv2d_params* p, ConvArgs& a) {
   a.N = p->N; a.Ho = p->Ho; a.Wo = p->Wo; a.Cout = p->Cout;
   a.kh = p->kh; a.kw = p->kw; a.stride = p->stride; a.pad_h = p->pad_h; a.pad_w = p->pad_w;
   a.cin_pad = p->cin_pad; a.cin_blocks = p->cin_pad / kBlockK;
+  a.x_cstride = p->x_cstride ? p->x_cstride : p->cin_pad;
+  SHINEON_REQUIRE(a.x_cstride >= a.cin_pad && a.x_cstride % 8 == 0, "conv2d: x_cstride %d", a.x_cstride);
   a.num_kb = p->kh * p->kw * a.cin_blocks;
   a.stages = 1;
   a.bias = p->bias; a.scale = p->scale; a.shift = p->shift;
@@ -670,22 +672,23 @@ extern "C" int shineon_conv2d_igemm_fwd(const shineon_conv2d_params* p, shineon_
 
   // ---- tensor maps
   CUtensorMap tAh, tAl, tBh, tBl;
-  const cuuint64_t C = (cuuint64_t)p->cin_pad, H = (cuuint64_t)p->H, W = (cuuint64_t)p->W, N = (cuuint64_t)p->N;
+  // C = channel extent the boxes may touch, Cs = pixel pitch (both in elements)
+  const cuuint64_t Cw = (cuuint64_t)p->cin_pad, C = (cuuint64_t)a.x_cstride, H = (cuuint64_t)p->H, W = (cuuint64_t)p->W, N = (cuuint64_t)p->N;
   if (p->stride == 1) {
-    cuuint64_t dims[4] = {C, W, H, N};
+    cuuint64_t dims[4] = {Cw, W, H, N};
     cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.nb};
     if ((rc = encode_map(&tAh, p->x_hi, 4, dims, strides, box, "A hi", p->plane_fmt))) return rc;
     if (split && (rc = encode_map(&tAl, p->x_lo, 4, dims, strides, box, "A lo", p->plane_fmt))) return rc;
   } else {
-    cuuint64_t dims[5] = {2 * C, W / 2, 2, H / 2, N};
+    cuuint64_t dims[5] = {C + Cw, W / 2, 2, H / 2, N};  // column pair: [q*Cs + c], c < cin_pad
     cuuint64_t strides[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
     cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)a.bw, 1, (cuuint32_t)a.bh, (cuuint32_t)a.nb};
     if ((rc = encode_map(&tAh, p->x_hi, 5, dims, strides, box, "A hi s2", p->plane_fmt))) return rc;
     if (split && (rc = encode_map(&tAl, p->x_lo, 5, dims, strides, box, "A lo s2", p->plane_fmt))) return rc;
   }
   {
-    const cuuint64_t K = (cuuint64_t)p->kh * p->kw * C;
+    const cuuint64_t K = (cuuint64_t)p->kh * p->kw * Cw;
     cuuint64_t dims[2] = {K, (cuuint64_t)p->Cout};
     cuuint64_t strides[1] = {K * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)bn};

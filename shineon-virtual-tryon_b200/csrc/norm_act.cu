@@ -37,6 +37,30 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------ planes -> nchw f32
+// (feeds ops with the reference's NCHW interface, e.g. the FlowNetC correlation, from a tensor-core layer output)
+__global__ void __launch_bounds__(256)
+    planes_to_nchw_kernel(const plane_t* __restrict__ xh, const plane_t* __restrict__ xl, int cstride,
+                          float* __restrict__ y, int HW, int C, int fmt) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {  // read: channel fastest
+    const int p = p0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (p < HW && c < C) {
+      const long o = ((long)n * HW + p) * cstride + c;
+      v = xl ? join16(xh[o], xl[o], fmt) : load16(xh[o], fmt);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {  // write: pixel fastest
+    const int c = c0 + i, p = p0 + tx;
+    if (p < HW && c < C) y[((long)n * C + c) * HW + p] = tile[tx][i];
+  }
+}
+
 // ------------------------------------------------------------------------------ nchw -> im2col planes
 // First layers have tiny Cin (3 / 10 / 22): one K-block per filter tap would waste >= 2/3 of every TMA box and
 // MMA on zero padding.  Instead the layout conversion writes, per OUTPUT pixel, the K-vector
@@ -337,6 +361,16 @@ extern "C" int shineon_nchw_to_planes(const float* x0, int C0, const float* x1, 
   nchw_to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo,
                                                                HW, cpad, act, act_param, plane_fmt);
   return after_launch("nchw_to_planes_kernel");
+}
+
+extern "C" int shineon_planes_to_nchw(const void* x_hi, const void* x_lo, int x_cstride, float* y, int N, int H, int W,
+                                      int C, int plane_fmt, shineon_stream_t stream) {
+  SHINEON_REQUIRE_FMT(plane_fmt, "planes_to_nchw");
+  SHINEON_REQUIRE(x_hi && y && N > 0 && N <= 65535 && H > 0 && W > 0 && C > 0 && x_cstride >= C, "planes_to_nchw: bad argument");
+  dim3 grid(cdiv(H * W, 32), cdiv(C, 32), N);
+  planes_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const plane_t*)x_hi, (const plane_t*)x_lo, x_cstride, y,
+                                                               H * W, C, plane_fmt);
+  return after_launch("planes_to_nchw_kernel");
 }
 
 extern "C" int shineon_nchw_im2col_planes(const float* x0, int C0, const float* x1, int C1, void* y_hi, void* y_lo,

@@ -1,0 +1,47 @@
+"""FlowNet — FlowNet2 wrapper producing flow + confidence (reference: models/flownet.py:11-63).
+
+The reference constructor loads `models/flownet2_pytorch/FlowNet2_checkpoint.pth.tar` and calls `.cuda()`; no
+checkpoint is available offline, so `checkpoint=None` builds the same module tree with its default initialisation
+(load one with `load_state_dict` — the keys are the reference's)."""
+import torch
+from torch import nn
+
+from .. import ops
+from ..networks.flownet2.native_ops import Resample2d
+from ..networks.flownet2.nets import FlowNet2
+
+
+class FlowNet(nn.Module):
+    def __init__(self, checkpoint=None):
+        super().__init__()
+        self.flowNet = FlowNet2()
+        if checkpoint is not None:
+            state = torch.load(checkpoint, map_location="cpu")
+            self.flowNet.load_state_dict(state["state_dict"] if "state_dict" in state else state)
+        self.flowNet.eval()
+        self.resample = Resample2d()
+        self.downsample = torch.nn.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False)
+
+    def forward(self, input_A, input_B):
+        with torch.no_grad():
+            size = input_A.size()
+            assert len(size) == 4 or len(size) == 5
+            if len(size) == 5:
+                b, n, c, h, w = size
+                flow, conf = self.compute_flow_and_conf(input_A.reshape(-1, c, h, w), input_B.reshape(-1, c, h, w))
+                return flow.view(b, n, 2, h, w), conf.view(b, n, 1, h, w)
+            return self.compute_flow_and_conf(input_A, input_B)
+
+    def compute_flow_and_conf(self, im1, im2):
+        assert im1.size()[1] == 3
+        assert im1.size() == im2.size()
+        old_h, old_w = im1.size()[2], im1.size()[3]
+        new_h, new_w = old_h // 64 * 64, old_w // 64 * 64
+        if old_h != new_h or old_w != new_w:
+            raise NotImplementedError(
+                "inputs whose sides are not multiples of 64 need the reference's bilinear pre/post resize "
+                "(flownet.py:46-51,56-58); the 256x192 try-on path never takes that branch")
+        data1 = torch.stack([im1, im2], dim=2).contiguous()  # [B,3,2,H,W]
+        flow1 = self.flowNet(data1)
+        conf = ops.flow_confidence(im1.contiguous(), im2.contiguous(), flow1, 0.02)
+        return flow1.detach(), conf.detach()

@@ -1,0 +1,390 @@
+"""FlowNet2 and its sub-networks (reference: models/flownet2_pytorch/models.py:32-192,
+networks/FlowNetC.py, FlowNetS.py, FlowNetSD.py, FlowNetFusion.py, submodules.py) — same attribute names and
+state_dict keys (`flownetc.conv1.0.weight`, `flownets_1.deconv5.0.weight`, `flownetfusion.predict_flow0.bias` ...).
+
+Engine (eval mode, batchNorm=False as FlowNet2 is built by the reference, models.py:34): every Conv2d /
+ConvTranspose2d runs on the tcgen05 implicit-GEMM kernel with the LeakyReLU(0.1) in its epilogue; `torch.cat`s
+never happen — producers write straight into 64-aligned channel windows of one concat buffer and the consumer's
+packed weights follow that layout; the small-Cin stems (3/6/11/12 channels, up to 7x7) use the im2col'd 1x1 GEMM;
+the warps / norms / concats between sub-networks are the fused kernels of csrc/flownet_glue.cu.
+"""
+import torch
+import torch.nn as nn
+
+from ... import ops
+from .._engine_util import params_signature, require_cuda
+from ..deconv import PackedDeconv4x4s2
+from .native_ops import ChannelNorm, Correlation, Resample2d
+
+LEAK = 0.1
+
+
+# ------------------------------------------------------------------ module constructors (submodules.py:7-38)
+def conv(batchNorm, in_planes, out_planes, kernel_size=3, stride=1):
+    if batchNorm:
+        raise NotImplementedError("FlowNet2 is built with batchNorm=False by the reference (models.py:34)")
+    return nn.Sequential(
+        nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, padding=(kernel_size - 1) // 2, bias=True),
+        nn.LeakyReLU(0.1, inplace=True))
+
+
+def i_conv(batchNorm, in_planes, out_planes, kernel_size=3, stride=1, bias=True):
+    if batchNorm:
+        raise NotImplementedError("batchNorm=True")
+    return nn.Sequential(nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride,
+                                   padding=(kernel_size - 1) // 2, bias=bias))
+
+
+def predict_flow(in_planes):
+    return nn.Conv2d(in_planes, 2, kernel_size=3, stride=1, padding=1, bias=True)
+
+
+def deconv(in_planes, out_planes):
+    return nn.Sequential(nn.ConvTranspose2d(in_planes, out_planes, kernel_size=4, stride=2, padding=1, bias=True),
+                         nn.LeakyReLU(0.1, inplace=True))
+
+
+def _init(net):
+    for m in net.modules():
+        if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+            if m.bias is not None:
+                nn.init.uniform_(m.bias)
+            nn.init.xavier_uniform_(m.weight)
+
+
+# ------------------------------------------------------------------ engine helpers
+class _Concat:
+    """A concat buffer: segments at 64-aligned channel offsets of one Planes; `chan_map` for the consumers."""
+
+    def __init__(self, N, H, W, seg_channels, prec, device):
+        self.offsets, off = [], 0
+        for c in seg_channels:
+            self.offsets.append(off)
+            off += ops.cpad64(c)
+        self.seg = list(seg_channels)
+        self.buf = ops.Planes(N, H, W, off, prec=prec, device=device, cpad=off)
+        self.buf.hi.zero_()
+        if self.buf.lo is not None:
+            self.buf.lo.zero_()
+
+    def window(self, i):
+        return self.buf.window(self.offsets[i], self.seg[i])
+
+    @staticmethod
+    def chan_map(seg_channels):
+        cmap, base = [], 0
+        for c in seg_channels:
+            cmap += list(range(base, base + c)) + [-1] * (ops.cpad64(c) - c)
+            base += c
+        return cmap
+
+
+class _Net(nn.Module):
+    """Packed-weight cache shared by the four sub-networks."""
+
+    def _packs(self, prec):
+        sig = (params_signature(self), prec)
+        if getattr(self, "_pk", None) is None or self._pk[0] != sig:
+            require_cuda(self, type(self).__name__)
+            self._pk = (sig, {})
+        return self._pk[1]
+
+    def _pc(self, prec, name, segs=None, stem=False):
+        """PackedConv / Im2colConv / PackedDeconv4x4s2 for the attribute `name`."""
+        pk = self._packs(prec)
+        if name not in pk:
+            m = getattr(self, name)
+            m = m[0] if isinstance(m, nn.Sequential) else m
+            cmap = _Concat.chan_map(segs) if segs is not None else None
+            cin_pad = len(cmap) if cmap is not None else None
+            if isinstance(m, nn.ConvTranspose2d):
+                pk[name] = PackedDeconv4x4s2(m.weight, m.bias, cin_pad=cin_pad, prec=prec, chan_map=cmap)
+            elif stem:
+                pk[name] = ops.Im2colConv(m.weight, m.bias, m.stride[0], m.padding[0], prec=prec)
+            else:
+                pk[name] = ops.PackedConv(m.weight, m.bias, stride=m.stride[0], pad=m.padding[0], cin_pad=cin_pad,
+                                          prec=prec, chan_map=cmap)
+        return pk[name]
+
+    # conv + LeakyReLU(0.1) -> planes (optionally into a concat window)
+    def _c(self, prec, name, x, out=None, segs=None, act=True):
+        pc = self._pc(prec, name, segs)
+        _, y = ops.conv2d(x, pc, post_act="leaky" if act else None, act_param=LEAK, want_planes=out is None,
+                          out_planes=out)
+        return y
+
+    def _stem(self, prec, name, x_nchw, out=None):
+        i2c = self._pc(prec, name, stem=True)
+        a = i2c.prepare(x_nchw)
+        _, y = ops.conv2d(a, i2c.pc, post_act="leaky", act_param=LEAK, want_planes=out is None, out_planes=out)
+        return y
+
+    def _flow(self, prec, name, x, segs=None, want_f32=False, want_planes=True):
+        """predict_flow: 3x3 conv -> 2 channels, no activation; returns (f32 NHWC [B,h,w,2] | None, planes | None)."""
+        pc = self._pc(prec, name, segs)
+        f32 = ops.conv2d(x, pc, want_f32=True)[0] if want_f32 else None
+        pl = ops.conv2d(x, pc, want_planes=True)[1] if want_planes else None
+        return f32, pl
+
+    def _refine(self, prec, c6, cats, names):
+        """Decoder shared by FlowNetC / FlowNetS (FlowNetC.py:100-123): cats = [concat5, concat4, concat3, concat2]."""
+        src, segs = c6, None
+        flow = None
+        for lvl, cat in zip((5, 4, 3, 2), cats):
+            flow, flow_pl = self._flow(prec, f"predict_flow{lvl + 1}", src, segs)
+            self._pc(prec, f"upsampled_flow{lvl + 1}_to_{lvl}")(flow_pl, out_planes=cat.window(2))
+            self._pc(prec, f"deconv{lvl}", segs)(src, post_act="leaky", act_param=LEAK, out_planes=cat.window(1))
+            src, segs = cat.buf, cat.seg
+        flow2, _ = self._flow(prec, "predict_flow2", src, segs, want_f32=True, want_planes=False)
+        return flow2
+
+
+def _dims(x_or_hw, k):
+    return x_or_hw // k
+
+
+class FlowNetC(_Net):
+    def __init__(self, args=None, batchNorm=True, div_flow=20):
+        super().__init__()
+        self.batchNorm, self.div_flow = batchNorm, div_flow
+        self.conv1 = conv(batchNorm, 3, 64, kernel_size=7, stride=2)
+        self.conv2 = conv(batchNorm, 64, 128, kernel_size=5, stride=2)
+        self.conv3 = conv(batchNorm, 128, 256, kernel_size=5, stride=2)
+        self.conv_redir = conv(batchNorm, 256, 32, kernel_size=1, stride=1)
+        self.corr = Correlation(pad_size=20, kernel_size=1, max_displacement=20, stride1=1, stride2=2, corr_multiply=1)
+        self.corr_activation = nn.LeakyReLU(0.1, inplace=True)
+        self.conv3_1 = conv(batchNorm, 473, 256)
+        self.conv4 = conv(batchNorm, 256, 512, stride=2)
+        self.conv4_1 = conv(batchNorm, 512, 512)
+        self.conv5 = conv(batchNorm, 512, 512, stride=2)
+        self.conv5_1 = conv(batchNorm, 512, 512)
+        self.conv6 = conv(batchNorm, 512, 1024, stride=2)
+        self.conv6_1 = conv(batchNorm, 1024, 1024)
+        self.deconv5 = deconv(1024, 512)
+        self.deconv4 = deconv(1026, 256)
+        self.deconv3 = deconv(770, 128)
+        self.deconv2 = deconv(386, 64)
+        self.predict_flow6 = predict_flow(1024)
+        self.predict_flow5 = predict_flow(1026)
+        self.predict_flow4 = predict_flow(770)
+        self.predict_flow3 = predict_flow(386)
+        self.predict_flow2 = predict_flow(194)
+        self.upsampled_flow6_to_5 = nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=True)
+        self.upsampled_flow5_to_4 = nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=True)
+        self.upsampled_flow4_to_3 = nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=True)
+        self.upsampled_flow3_to_2 = nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=True)
+        _init(self)
+        self.upsample1 = nn.Upsample(scale_factor=4, mode="bilinear")
+
+    def run(self, x, prec):
+        """x: f32 NCHW [B,6,H,W] -> flow2 f32 NHWC [B,H/4,W/4,2] (FlowNetC.py:71-128, eval)."""
+        B, _, H, W = x.shape
+        dev = x.device
+        mk = lambda k, segs: _Concat(B, H // k, W // k, segs, prec, dev)
+        cat5, cat4, cat3, cat2 = mk(32, (512, 512, 2)), mk(16, (512, 256, 2)), mk(8, (256, 128, 2)), mk(4, (128, 64, 2))
+        x1, x2 = x[:, 0:3].contiguous(), x[:, 3:].contiguous()
+        c2a = self._c(prec, "conv2", self._stem(prec, "conv1", x1), out=cat2.window(0))
+        c3a = self._c(prec, "conv3", c2a)
+        c3b = self._c(prec, "conv3", self._c(prec, "conv2", self._stem(prec, "conv1", x2)))
+        # cost volume on the NCHW f32 features (the Correlation op's interface, correlation.py:47-58)
+        in31 = _Concat(B, H // 8, W // 8, (32, 441), prec, dev)
+        corr = ops.correlation_fwd(ops.planes_to_nchw(c3a), ops.planes_to_nchw(c3b), 20, 1, 20, 1, 2)
+        ops.nchw_to_planes(corr, act="leaky", act_param=LEAK, out=in31.window(1))  # corr_activation
+        self._c(prec, "conv_redir", c3a, out=in31.window(0))
+        c31 = self._c(prec, "conv3_1", in31.buf, out=cat3.window(0), segs=in31.seg)
+        c4 = self._c(prec, "conv4_1", self._c(prec, "conv4", c31), out=cat4.window(0))
+        c5 = self._c(prec, "conv5_1", self._c(prec, "conv5", c4), out=cat5.window(0))
+        c6 = self._c(prec, "conv6_1", self._c(prec, "conv6", c5))
+        return self._refine(prec, c6, (cat5, cat4, cat3, cat2), None)
+
+
+class FlowNetS(_Net):
+    def __init__(self, args=None, input_channels=12, batchNorm=True):
+        super().__init__()
+        self.batchNorm = batchNorm
+        self.conv1 = conv(batchNorm, input_channels, 64, kernel_size=7, stride=2)
+        self.conv2 = conv(batchNorm, 64, 128, kernel_size=5, stride=2)
+        self.conv3 = conv(batchNorm, 128, 256, kernel_size=5, stride=2)
+        self.conv3_1 = conv(batchNorm, 256, 256)
+        self.conv4 = conv(batchNorm, 256, 512, stride=2)
+        self.conv4_1 = conv(batchNorm, 512, 512)
+        self.conv5 = conv(batchNorm, 512, 512, stride=2)
+        self.conv5_1 = conv(batchNorm, 512, 512)
+        self.conv6 = conv(batchNorm, 512, 1024, stride=2)
+        self.conv6_1 = conv(batchNorm, 1024, 1024)
+        self.deconv5 = deconv(1024, 512)
+        self.deconv4 = deconv(1026, 256)
+        self.deconv3 = deconv(770, 128)
+        self.deconv2 = deconv(386, 64)
+        self.predict_flow6 = predict_flow(1024)
+        self.predict_flow5 = predict_flow(1026)
+        self.predict_flow4 = predict_flow(770)
+        self.predict_flow3 = predict_flow(386)
+        self.predict_flow2 = predict_flow(194)
+        self.upsampled_flow6_to_5 = nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=False)
+        self.upsampled_flow5_to_4 = nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=False)
+        self.upsampled_flow4_to_3 = nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=False)
+        self.upsampled_flow3_to_2 = nn.ConvTranspose2d(2, 2, 4, 2, 1, bias=False)
+        _init(self)
+        self.upsample1 = nn.Upsample(scale_factor=4, mode="bilinear")
+
+    def run(self, x, prec):
+        """x: f32 NCHW [B,12,H,W] -> flow2 f32 NHWC [B,H/4,W/4,2] (FlowNetS.py:60-94, eval)."""
+        B, _, H, W = x.shape
+        dev = x.device
+        mk = lambda k, segs: _Concat(B, H // k, W // k, segs, prec, dev)
+        cat5, cat4, cat3, cat2 = mk(32, (512, 512, 2)), mk(16, (512, 256, 2)), mk(8, (256, 128, 2)), mk(4, (128, 64, 2))
+        c2 = self._c(prec, "conv2", self._stem(prec, "conv1", x), out=cat2.window(0))
+        c3 = self._c(prec, "conv3_1", self._c(prec, "conv3", c2), out=cat3.window(0))
+        c4 = self._c(prec, "conv4_1", self._c(prec, "conv4", c3), out=cat4.window(0))
+        c5 = self._c(prec, "conv5_1", self._c(prec, "conv5", c4), out=cat5.window(0))
+        c6 = self._c(prec, "conv6_1", self._c(prec, "conv6", c5))
+        return self._refine(prec, c6, (cat5, cat4, cat3, cat2), None)
+
+
+class FlowNetSD(_Net):
+    def __init__(self, args=None, batchNorm=True):
+        super().__init__()
+        self.batchNorm = batchNorm
+        self.conv0 = conv(batchNorm, 6, 64)
+        self.conv1 = conv(batchNorm, 64, 64, stride=2)
+        self.conv1_1 = conv(batchNorm, 64, 128)
+        self.conv2 = conv(batchNorm, 128, 128, stride=2)
+        self.conv2_1 = conv(batchNorm, 128, 128)
+        self.conv3 = conv(batchNorm, 128, 256, stride=2)
+        self.conv3_1 = conv(batchNorm, 256, 256)
+        self.conv4 = conv(batchNorm, 256, 512, stride=2)
+        self.conv4_1 = conv(batchNorm, 512, 512)
+        self.conv5 = conv(batchNorm, 512, 512, stride=2)
+        self.conv5_1 = conv(batchNorm, 512, 512)
+        self.conv6 = conv(batchNorm, 512, 1024, stride=2)
+        self.conv6_1 = conv(batchNorm, 1024, 1024)
+        self.deconv5 = deconv(1024, 512)
+        self.deconv4 = deconv(1026, 256)
+        self.deconv3 = deconv(770, 128)
+        self.deconv2 = deconv(386, 64)
+        self.inter_conv5 = i_conv(batchNorm, 1026, 512)
+        self.inter_conv4 = i_conv(batchNorm, 770, 256)
+        self.inter_conv3 = i_conv(batchNorm, 386, 128)
+        self.inter_conv2 = i_conv(batchNorm, 194, 64)
+        self.predict_flow6 = predict_flow(1024)
+        self.predict_flow5 = predict_flow(512)
+        self.predict_flow4 = predict_flow(256)
+        self.predict_flow3 = predict_flow(128)
+        self.predict_flow2 = predict_flow(64)
+        self.upsampled_flow6_to_5 = nn.ConvTranspose2d(2, 2, 4, 2, 1)
+        self.upsampled_flow5_to_4 = nn.ConvTranspose2d(2, 2, 4, 2, 1)
+        self.upsampled_flow4_to_3 = nn.ConvTranspose2d(2, 2, 4, 2, 1)
+        self.upsampled_flow3_to_2 = nn.ConvTranspose2d(2, 2, 4, 2, 1)
+        _init(self)
+        self.upsample1 = nn.Upsample(scale_factor=4, mode="bilinear")
+
+    def run(self, x, prec):
+        """x: f32 NCHW [B,6,H,W] -> flow2 f32 NHWC [B,H/4,W/4,2] (FlowNetSD.py:66-106, eval)."""
+        B, _, H, W = x.shape
+        dev = x.device
+        mk = lambda k, segs: _Concat(B, H // k, W // k, segs, prec, dev)
+        cat5, cat4, cat3, cat2 = mk(32, (512, 512, 2)), mk(16, (512, 256, 2)), mk(8, (256, 128, 2)), mk(4, (128, 64, 2))
+        c0 = self._stem(prec, "conv0", x)
+        c1 = self._c(prec, "conv1_1", self._c(prec, "conv1", c0))
+        c2 = self._c(prec, "conv2_1", self._c(prec, "conv2", c1), out=cat2.window(0))
+        c3 = self._c(prec, "conv3_1", self._c(prec, "conv3", c2), out=cat3.window(0))
+        c4 = self._c(prec, "conv4_1", self._c(prec, "conv4", c3), out=cat4.window(0))
+        c5 = self._c(prec, "conv5_1", self._c(prec, "conv5", c4), out=cat5.window(0))
+        c6 = self._c(prec, "conv6_1", self._c(prec, "conv6", c5))
+        flow, flow_pl = self._flow(prec, "predict_flow6", c6)
+        src, segs = c6, None
+        for lvl, cat in zip((5, 4, 3, 2), (cat5, cat4, cat3, cat2)):
+            self._pc(prec, f"upsampled_flow{lvl + 1}_to_{lvl}")(flow_pl, out_planes=cat.window(2))
+            self._pc(prec, f"deconv{lvl}", segs)(src, post_act="leaky", act_param=LEAK, out_planes=cat.window(1))
+            inter = self._c(prec, f"inter_conv{lvl}", cat.buf, segs=cat.seg, act=False)
+            flow, flow_pl = self._flow(prec, f"predict_flow{lvl}", inter, want_f32=lvl == 2, want_planes=lvl != 2)
+            src, segs = cat.buf, cat.seg
+        return flow
+
+
+class FlowNetFusion(_Net):
+    def __init__(self, args=None, batchNorm=True):
+        super().__init__()
+        self.batchNorm = batchNorm
+        self.conv0 = conv(batchNorm, 11, 64)
+        self.conv1 = conv(batchNorm, 64, 64, stride=2)
+        self.conv1_1 = conv(batchNorm, 64, 128)
+        self.conv2 = conv(batchNorm, 128, 128, stride=2)
+        self.conv2_1 = conv(batchNorm, 128, 128)
+        self.deconv1 = deconv(128, 32)
+        self.deconv0 = deconv(162, 16)
+        self.inter_conv1 = i_conv(batchNorm, 162, 32)
+        self.inter_conv0 = i_conv(batchNorm, 82, 16)
+        self.predict_flow2 = predict_flow(128)
+        self.predict_flow1 = predict_flow(32)
+        self.predict_flow0 = predict_flow(16)
+        self.upsampled_flow2_to_1 = nn.ConvTranspose2d(2, 2, 4, 2, 1)
+        self.upsampled_flow1_to_0 = nn.ConvTranspose2d(2, 2, 4, 2, 1)
+        _init(self)
+
+    def run(self, x, prec):
+        """x: f32 NCHW [B,11,H,W] -> flow0 f32 NHWC [B,H,W,2] (FlowNetFusion.py:47-67)."""
+        B, _, H, W = x.shape
+        dev = x.device
+        cat1 = _Concat(B, H // 2, W // 2, (128, 32, 2), prec, dev)
+        cat0 = _Concat(B, H, W, (64, 16, 2), prec, dev)
+        c0 = self._stem(prec, "conv0", x, out=cat0.window(0))
+        c1 = self._c(prec, "conv1_1", self._c(prec, "conv1", c0), out=cat1.window(0))
+        c2 = self._c(prec, "conv2_1", self._c(prec, "conv2", c1))
+        _, flow2_pl = self._flow(prec, "predict_flow2", c2)
+        self._pc(prec, "upsampled_flow2_to_1")(flow2_pl, out_planes=cat1.window(2))
+        self._pc(prec, "deconv1")(c2, post_act="leaky", act_param=LEAK, out_planes=cat1.window(1))
+        i1 = self._c(prec, "inter_conv1", cat1.buf, segs=cat1.seg, act=False)
+        _, flow1_pl = self._flow(prec, "predict_flow1", i1)
+        self._pc(prec, "upsampled_flow1_to_0")(flow1_pl, out_planes=cat0.window(2))
+        self._pc(prec, "deconv0", cat1.seg)(cat1.buf, post_act="leaky", act_param=LEAK, out_planes=cat0.window(1))
+        i0 = self._c(prec, "inter_conv0", cat0.buf, segs=cat0.seg, act=False)
+        flow0, _ = self._flow(prec, "predict_flow0", i0, want_f32=True, want_planes=False)
+        return flow0
+
+
+class MyDict(dict):
+    pass
+
+
+class FlowNet2(nn.Module):
+    def __init__(self, args=None, batchNorm=False, div_flow=20.0):
+        super().__init__()
+        if args is None:
+            args = MyDict()
+            args.rgb_max = 1
+            args.fp16 = False
+            args.grads = {}
+        self.batchNorm, self.div_flow, self.rgb_max, self.args = batchNorm, div_flow, args.rgb_max, args
+        self.channelnorm = ChannelNorm()
+        self.flownetc = FlowNetC(args, batchNorm=batchNorm)
+        self.upsample1 = nn.Upsample(scale_factor=4, mode="bilinear")
+        self.resample1 = Resample2d()
+        self.flownets_1 = FlowNetS(args, batchNorm=batchNorm)
+        self.upsample2 = nn.Upsample(scale_factor=4, mode="bilinear")
+        self.resample2 = Resample2d()
+        self.flownets_2 = FlowNetS(args, batchNorm=batchNorm)
+        self.flownets_d = FlowNetSD(args, batchNorm=batchNorm)
+        self.upsample3 = nn.Upsample(scale_factor=4, mode="nearest")
+        self.upsample4 = nn.Upsample(scale_factor=4, mode="nearest")
+        self.resample3 = Resample2d()
+        self.resample4 = Resample2d()
+        self.flownetfusion = FlowNetFusion(args, batchNorm=batchNorm)
+        _init(self)
+        self.precision = None
+
+    def forward(self, inputs):
+        """inputs f32 [B,3,2,H,W] (H, W multiples of 64) -> flow f32 NCHW [B,2,H,W] (models.py:127-192)."""
+        require_cuda(self, "FlowNet2")
+        if self.training:
+            raise NotImplementedError("FlowNet2 training is not part of this build (the reference never trains it either)")
+        prec = ops.resolve_precision(self.precision)
+        df = self.div_flow
+        x = ops.flownet_normalize(inputs.contiguous(), self.rgb_max)
+        c_flow = ops.upsample4x_flow(self.flownetc.run(x, prec), df, bilinear=True)
+        s1_flow = ops.upsample4x_flow(self.flownets_1.run(ops.flownet_warp_concat(x, c_flow, df), prec), df, bilinear=True)
+        s2_flow = ops.upsample4x_flow(self.flownets_2.run(ops.flownet_warp_concat(x, s1_flow, df), prec), df, bilinear=False)
+        sd_flow = ops.upsample4x_flow(self.flownets_d.run(x, prec), 1.0 / df, bilinear=False)
+        flow0 = self.flownetfusion.run(ops.flownet_fusion_concat(x, sd_flow, s2_flow), prec)
+        return flow0.permute(0, 3, 1, 2).contiguous()

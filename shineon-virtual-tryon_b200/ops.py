@@ -15,6 +15,10 @@ from ._lib import ACT, PAD, Conv2dParams, TpsTables, check
 PROFILE = None
 
 
+def C_void(v):
+    return C.c_void_p(v)
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -78,12 +82,30 @@ class Planes:
     def prec(self):
         return (self.fmt, self.lo is not None)
 
+    # a Planes may be a 64-aligned channel window of a wider (concat) buffer
+    coffset = 0
+
+    @property
+    def cstride(self):
+        return self.hi.shape[-1]
+
+    def window(self, c0, C):
+        """View of channels [c0, c0+C) (c0 % 64 == 0) sharing this buffer's storage."""
+        assert c0 % 64 == 0 and c0 + cpad64(C) <= self.hi.shape[-1]
+        v = Planes.__new__(Planes)
+        v.fmt, v.N, v.H, v.W, v.C, v.cpad = self.fmt, self.N, self.H, self.W, C, cpad64(C)
+        v.hi, v.lo, v.coffset = self.hi, self.lo, self.coffset + c0
+        return v
+
+    def _ptr(self, t):
+        return C_void(0 if t is None else t.data_ptr() + 2 * self.coffset)
+
     def float(self):
         """Reconstructed f32 NCHW tensor (debug / tests)."""
         v = self.hi.float()
         if self.lo is not None:
             v = v + self.lo.float()
-        return v[..., : self.C].permute(0, 3, 1, 2).contiguous()
+        return v[..., self.coffset: self.coffset + self.C].permute(0, 3, 1, 2).contiguous()
 
 
 # ----------------------------------------------------------------------------- TPS / grid sample
@@ -271,8 +293,8 @@ def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_pa
     if want_planes and out_planes is None:
         out_planes = Planes(N, oH, oW, pc.Cout, prec=x.prec, device=dev)
     p = Conv2dParams()
-    p.x_hi, p.x_lo = _p(x.hi), _p(x.lo)
-    p.N, p.H, p.W, p.cin_pad = N, H, W, x.cpad
+    p.x_hi, p.x_lo = x._ptr(x.hi), x._ptr(x.lo)
+    p.N, p.H, p.W, p.cin_pad, p.x_cstride = N, H, W, x.cpad, x.cstride
     p.w_hi, p.w_lo = _p(pc.w_hi), _p(pc.w_lo)
     p.Cout, p.kh, p.kw, p.stride, p.pad_h, p.pad_w = pc.Cout, pc.kh, pc.kw, pc.stride, pc.pad_h, pc.pad_w
     p.Ho, p.Wo = Ho, Wo
@@ -284,9 +306,9 @@ def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_pa
     p.y_lo = _p(out_planes.lo if out_planes is not None else None)
     p.out_H, p.out_W = oH, oW
     if out_planes is not None:
-        p.out_cstride, p.out_coffset = out_planes.cpad, out_coffset
+        p.out_cstride, p.out_coffset = out_planes.cstride, out_planes.coffset + out_coffset
         if out_f32 is not None:
-            assert out_f32.shape[-1] == out_planes.cpad, "f32 and planes outputs must share the channel stride"
+            assert out_f32.shape[-1] == out_planes.cstride, "f32 and planes outputs must share the channel stride"
     else:
         p.out_cstride, p.out_coffset = out_f32.shape[-1], out_coffset
     p.oh_mul, p.oh_off, p.ow_mul, p.ow_off = ohm, oho, owm, owo
@@ -314,9 +336,18 @@ def nchw_to_planes(x0, x1=None, act=None, act_param=0.0, prec=None, out=None):
         C1 = x1.shape[1]
     if out is None:
         out = Planes(N, H, W, C0 + C1, prec=prec, device=x0.device)
-    check(_lib.load().shineon_nchw_to_planes(_p(x0), C0, _p(x1), C1, _p(out.hi), _p(out.lo), N, H, W, out.cpad,
-                                             ACT[act], float(act_param), out.fmt, _stream()), "shineon_nchw_to_planes")
+    check(_lib.load().shineon_nchw_to_planes(_p(x0), C0, _p(x1), C1, out._ptr(out.hi), out._ptr(out.lo), N, H, W,
+                                             out.cstride, ACT[act], float(act_param), out.fmt, _stream()),
+          "shineon_nchw_to_planes")
     return out
+
+
+def planes_to_nchw(x):
+    """Planes (or a channel window) -> f32 NCHW [N,C,H,W]."""
+    y = torch.empty(x.N, x.C, x.H, x.W, dtype=torch.float32, device=x.hi.device)
+    check(_lib.load().shineon_planes_to_nchw(x._ptr(x.hi), x._ptr(x.lo), x.cstride, _p(y), x.N, x.H, x.W, x.C, x.fmt,
+                                             _stream()), "shineon_planes_to_nchw")
+    return y
 
 
 def nchw_im2col_planes(x0, x1, kh, kw, stride, pad, act=None, act_param=0.0, prec=None):
@@ -449,3 +480,51 @@ def tom_compose(unet_out, cloth, n_frames, flow_warp, outs, frame=0, warped_prev
     check(_lib.load().shineon_tom_compose(_p(unet_out), Cout, _p(cloth), _p(warped_prev), _p(pr), _p(tm), _p(pt),
                                           _p(fm), B, H, W, n_frames, frame, int(bool(flow_warp)), _stream()),
           "shineon_tom_compose")
+
+
+# ----------------------------------------------------------------------------- FlowNet2 glue
+def flownet_normalize(inputs, rgb_max=1.0):
+    inputs = _req(inputs, name="inputs")
+    B, C3, F2, H, W = inputs.shape
+    assert C3 == 3 and F2 == 2
+    x = torch.empty(B, 6, H, W, dtype=torch.float32, device=inputs.device)
+    ws = torch.empty(3 * B, dtype=torch.float64, device=inputs.device)
+    check(_lib.load().shineon_flownet_normalize(_p(inputs), _p(x), _p(ws), B, H, W, float(rgb_max), _stream()),
+          "shineon_flownet_normalize")
+    return x
+
+
+def upsample4x_flow(src_nhwc, mul, bilinear):
+    src_nhwc = _req(src_nhwc, name="flow")
+    B, h, w, cs = src_nhwc.shape
+    dst = torch.empty(B, 2, 4 * h, 4 * w, dtype=torch.float32, device=src_nhwc.device)
+    check(_lib.load().shineon_upsample4x_flow(_p(src_nhwc), cs, _p(dst), B, h, w, float(mul), int(bool(bilinear)),
+                                              _stream()), "shineon_upsample4x_flow")
+    return dst
+
+
+def flownet_warp_concat(x, flow, div_flow):
+    x, flow = _req(x), _req(flow)
+    B, _, H, W = x.shape
+    out = torch.empty(B, 12, H, W, dtype=torch.float32, device=x.device)
+    check(_lib.load().shineon_flownet_warp_concat(_p(x), _p(flow), _p(out), B, H, W, float(div_flow), _stream()),
+          "shineon_flownet_warp_concat")
+    return out
+
+
+def flownet_fusion_concat(x, flow_sd, flow_s2):
+    x, flow_sd, flow_s2 = _req(x), _req(flow_sd), _req(flow_s2)
+    B, _, H, W = x.shape
+    out = torch.empty(B, 11, H, W, dtype=torch.float32, device=x.device)
+    check(_lib.load().shineon_flownet_fusion_concat(_p(x), _p(flow_sd), _p(flow_s2), _p(out), B, H, W, _stream()),
+          "shineon_flownet_fusion_concat")
+    return out
+
+
+def flow_confidence(im1, im2, flow, threshold=0.02):
+    im1, im2, flow = _req(im1), _req(im2), _req(flow)
+    B, Cc, H, W = im1.shape
+    conf = torch.empty(B, 1, H, W, dtype=torch.float32, device=im1.device)
+    check(_lib.load().shineon_flow_confidence(_p(im1), _p(im2), _p(flow), _p(conf), B, Cc, H, W, float(threshold),
+                                              _stream()), "shineon_flow_confidence")
+    return conf

@@ -129,3 +129,31 @@ def test_no_cpu_fallback(cuda):
 
     with pytest.raises(_lib.ShineonError):
         ops.channelnorm_fwd(torch.randn(1, 3, 4, 4))
+
+
+def test_flownet2_matches_oracle_and_golden(cuda):
+    """FlowNet2 (rows F1/F2): conv/deconv stacks on the tcgen05 kernel + correlation / warp / norm glue."""
+    from oracle import flownet2 as ofn, weights
+    from shineon_virtual_tryon_b200.models.flownet import FlowNet
+
+    seed, shapes, gold = load_golden("flownet2")
+    sd = weights.synth_state_dict(shapes, seed)
+    net = FlowNet()
+    net.flowNet.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    inp = cases.flownet2_inputs()
+    with torch.no_grad():
+        flow, conf = net(inp[:, :, 0].cuda(), inp[:, :, 1].cuda())
+        stages = {}
+        want = ofn.flownet2(sd, inp, stages=stages)
+        want_conf = ofn.flow_confidence(inp[:, :, 0], inp[:, :, 1], want)
+    torch.cuda.synchronize()
+    err = assert_close(flow, want, what="flownet2 flow vs oracle")
+    assert_close(cases.subsample(flow.cpu(), 2), gold["flow"], what="flownet2 flow vs reference golden")
+    print(f"flownet2 flow max abs err {err:.2e} (|flow| max {want.abs().max().item():.2f})")
+    # confidence mask: bit-exact wherever the oracle's residual is not within 1e-4 of the 0.02 threshold
+    from oracle import flow_ops as fo
+
+    d = inp[:, :, 0] - fo.resample2d_fwd(inp[:, :, 1].contiguous(), want)
+    safe = ((d * d).sum(1, keepdim=True) - 0.02).abs() > 1e-4
+    assert torch.equal(conf.cpu()[safe], want_conf[safe])

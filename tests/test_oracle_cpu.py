@@ -102,3 +102,16 @@ def test_channelnorm_backward_is_gradient():
     go = torch.randn_like(o)
     o.backward(go)
     assert_close(fo.channelnorm_bwd(x.detach(), o.detach(), go), x.grad, atol=1e-6, rtol=1e-5, what="d_in")
+
+
+def test_flownet2_oracle_matches_reference_golden():
+    from oracle import flownet2 as ofn
+
+    seed, shapes, gold = load_golden("flownet2")
+    sd = weights.synth_state_dict(shapes, seed)
+    inp = cases.flownet2_inputs()
+    with torch.no_grad():
+        flow = ofn.flownet2(sd, inp)
+        conf = ofn.flow_confidence(inp[:, :, 0], inp[:, :, 1], flow)
+    assert_close(cases.subsample(flow, 2), gold["flow"], atol=1e-5, rtol=1e-5, what="flownet2 flow")
+    assert torch.equal(cases.subsample(conf, 2), gold["conf"])
