@@ -226,19 +226,14 @@ def run_b200(args, rank, world):
     import torch
     import torch.distributed as dist
 
-    from shineon_virtual_tryon_b200 import _lib, ops
+    from shineon_virtual_tryon_b200 import _lib, distributed, ops
     from shineon_virtual_tryon_b200.pipeline import TryOnPipeline
 
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    distributed.init_process_group("nccl", device=dev)
+    barrier = distributed.barrier
 
     warp, tom = build_models()
     pipe = TryOnPipeline(warp.to(dev), tom.to(dev))
@@ -262,10 +257,7 @@ def run_b200(args, rank, world):
         e1.record()
         barrier()
         clocks = sampler.stop() if sampler else None
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item(), clocks
+        return distributed.max_over_ranks(e0.elapsed_time(e1), dev), clocks
 
     def run_mode(precision):
         pipe.set_precision(precision)

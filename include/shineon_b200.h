@@ -132,6 +132,11 @@ int shineon_correlation_out_shape(int C, int H, int W, int pad_size, int kernel_
 int shineon_correlation_fwd(const float* in1, const float* in2, float* out, int B, int C, int H, int W,
                             int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
                             shineon_stream_t stream);
+/* Tensor-core path of the same op for kernel_size == 1, stride1 == 1: `full` f32 [B, H*W, H*W] holds the all-pairs
+ * products <in1[p1,:], in2[p2,:]> (one tcgen05 GEMM per image, shineon_conv2d_igemm_fwd with w_per_image); this
+ * kernel gathers the (2*(maxd/s2)+1)^2 displacements, scales by 1/C and zero-fills out-of-image taps. */
+int shineon_correlation_gather(const float* full, float* out, int B, int C, int H, int W, int pad_size,
+                               int max_displacement, int stride2, shineon_stream_t stream);
 int shineon_correlation_bwd(const float* in1, const float* in2, const float* grad_out, float* grad_in1,
                             float* grad_in2, int B, int C, int H, int W, int pad_size, int kernel_size,
                             int max_displacement, int stride1, int stride2, shineon_stream_t stream);
@@ -158,6 +163,8 @@ typedef struct shineon_conv2d_params {
   /* packed weights [Cout][kh*kw][cin_pad] bf16 */
   const void* w_hi;
   const void* w_lo; /* NULL unless x_lo given */
+  int w_per_image;               /* != 0: weights are a batch [N][Cout][kh*kw][cin_pad], image n of x meets weight set n
+                                    (per-image GEMMs, e.g. the FlowNetC cost volume: "weights" = the other feature map) */
   int Cout, kh, kw, stride;      /* stride 1 or 2 (stride 2 needs even H, W) */
   int pad_h, pad_w;              /* zero padding before the first row / column */
   int Ho, Wo;                    /* output size; rows/cols past the input read zeros, so any

@@ -24,7 +24,7 @@ class TpsTables(C.Structure):
 class Conv2dParams(C.Structure):
     _fields_ = [
         ("x_hi", c_p), ("x_lo", c_p), ("N", c_i), ("H", c_i), ("W", c_i), ("cin_pad", c_i), ("x_cstride", c_i),
-        ("w_hi", c_p), ("w_lo", c_p), ("Cout", c_i), ("kh", c_i), ("kw", c_i), ("stride", c_i), ("pad_h", c_i), ("pad_w", c_i),
+        ("w_hi", c_p), ("w_lo", c_p), ("w_per_image", c_i), ("Cout", c_i), ("kh", c_i), ("kw", c_i), ("stride", c_i), ("pad_h", c_i), ("pad_w", c_i),
         ("Ho", c_i), ("Wo", c_i),
         ("bias", c_p), ("scale", c_p), ("shift", c_p), ("pre_act", c_i), ("post_act", c_i), ("act_param", c_f),
         ("acc_scale", c_f), ("plane_fmt", c_i),
@@ -51,6 +51,7 @@ SIGNATURES = {
     "shineon_correlation_out_shape": [c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
                                       C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i)],
     "shineon_correlation_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_correlation_gather": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_correlation_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_pack_conv_weight": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_f, c_p],
     "shineon_conv2d_igemm_fwd": [C.POINTER(Conv2dParams), c_p],

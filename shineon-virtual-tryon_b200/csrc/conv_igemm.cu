@@ -42,6 +42,7 @@ struct ConvArgs {
   int cin_pad, cin_blocks, x_cstride;
   int num_kb, stages;
   int n_tiles, total_tiles;  // channel tiles per pixel tile, pixel tiles * channel tiles
+  int w_per_image;           // 1: the B operand is a [N][Cout][K] batch indexed by the tile's image (needs nb == 1)
   // epilogue
   const float* bias;
   const float* scale;
@@ -90,6 +91,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
@@ -345,8 +352,13 @@ __global__ void __launch_bounds__(kThreads, 1)
             tma_load_5d(sA, &tmAh, full, cc, w0 + ax, py, h0 + ay, n0);
             if (SPLIT) tma_load_5d(sA + kABytes, &tmAl, full, cc, w0 + ax, py, h0 + ay, n0);
           }
-          tma_load_2d(sB, &tmBh, full, kb * kBlockK, cn0);
-          if (SPLIT) tma_load_2d(sB + kBBytes, &tmBl, full, kb * kBlockK, cn0);
+          if (a.w_per_image) {
+            tma_load_3d(sB, &tmBh, full, kb * kBlockK, cn0, n0);
+            if (SPLIT) tma_load_3d(sB + kBBytes, &tmBl, full, kb * kBlockK, cn0, n0);
+          } else {
+            tma_load_2d(sB, &tmBh, full, kb * kBlockK, cn0);
+            if (SPLIT) tma_load_2d(sB + kBBytes, &tmBl, full, kb * kBlockK, cn0);
+          }
         }
       }
     }
@@ -468,7 +480,7 @@ __global__ void __launch_bounds__(128)
         const int ix = ow * a.stride + fx - a.pad_w;
         if (ix < 0 || ix >= W) continue;
         const long xo = (((long)n * H + iy) * W + ix) * a.x_cstride;
-        const long wo = ((long)c * a.kh * a.kw + fy * a.kw + fx) * a.cin_pad;
+        const long wo = (((long)(a.w_per_image ? n : 0) * a.Cout + c) * a.kh * a.kw + fy * a.kw + fx) * a.cin_pad;
         for (int ci = 0; ci < a.cin_pad; ++ci) {
           const float xhv = load16(xh[xo + ci], a.fmt), whv = load16(wh[wo + ci], a.fmt);
           acc = fmaf(xhv, whv, acc);
@@ -647,7 +659,8 @@ static int fill_args(const shineon_conv2d_params* p, ConvArgs& a) {
   a.out_coffset = p->out_coffset;
   SHINEON_REQUIRE(a.out_coffset >= 0 && a.out_coffset + a.Cout <= a.out_cstride, "conv2d: output channel window out of range");
   SHINEON_REQUIRE((a.Ho - 1) * a.oh_mul + a.oh_off < a.out_H && (a.Wo - 1) * a.ow_mul + a.ow_off < a.out_W, "conv2d: output pixel window out of range");
-  pick_tile(a.N, a.Ho, a.Wo, a.nb, a.bh, a.bw);
+  a.w_per_image = p->w_per_image ? 1 : 0;
+  pick_tile(a.w_per_image ? 1 : a.N, a.Ho, a.Wo, a.nb, a.bh, a.bw);
   a.tiles_w = cdiv(a.Wo, a.bw);
   a.tiles_h = cdiv(a.Ho, a.bh);
   return SHINEON_OK;
@@ -689,11 +702,12 @@ extern "C" int shineon_conv2d_igemm_fwd(const shineon_conv2d_params* p, shineon_
   }
   {
     const cuuint64_t K = (cuuint64_t)p->kh * p->kw * Cw;
-    cuuint64_t dims[2] = {K, (cuuint64_t)p->Cout};
-    cuuint64_t strides[1] = {K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)bn};
-    if ((rc = encode_map(&tBh, p->w_hi, 2, dims, strides, box, "B hi", p->plane_fmt))) return rc;
-    if (split && (rc = encode_map(&tBl, p->w_lo, 2, dims, strides, box, "B lo", p->plane_fmt))) return rc;
+    const int brank = a.w_per_image ? 3 : 2;
+    cuuint64_t dims[3] = {K, (cuuint64_t)p->Cout, N};
+    cuuint64_t strides[2] = {K * 2, K * 2 * (cuuint64_t)p->Cout};
+    cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)bn, 1};
+    if ((rc = encode_map(&tBh, p->w_hi, brank, dims, strides, box, "B hi", p->plane_fmt))) return rc;
+    if (split && (rc = encode_map(&tBl, p->w_lo, brank, dims, strides, box, "B lo", p->plane_fmt))) return rc;
   }
   if (!split) { tAl = tAh; tBl = tBh; }
 

@@ -74,6 +74,26 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Gather of the tensor-core path: full[b, p1, p2] = <in1[p1,:], in2[p2,:]> (all pairs, one GEMM per image) ->
+// out[b, tj*D+ti, y, x] = full[b, (y,x), (y + (tj-r)*s2, x + (ti-r)*s2)] / C, zero outside the image.
+__global__ void __launch_bounds__(256)
+    correlation_gather_kernel(const float* __restrict__ full, float* __restrict__ out, int C, int H, int W, int shift,
+                              int drad, int s2, long total) {
+  const int D = 2 * drad + 1, P = H * W;
+  const float inv = 1.f / (float)C;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(e % W), y = (int)((e / W) % H);
+    const int tc = (int)((e / P) % (D * D)), b = (int)(e / ((long)P * D * D));
+    const int tj = tc / D, ti = tc - tj * D;
+    const int y1 = y + shift, x1 = x + shift;  // window centre in image coordinates (shift = maxd - pad)
+    const int y2 = y1 + (tj - drad) * s2, x2 = x1 + (ti - drad) * s2;
+    float v = 0.f;
+    if (y1 >= 0 && y1 < H && x1 >= 0 && x1 < W && y2 >= 0 && y2 < H && x2 >= 0 && x2 < W)
+      v = __ldg(full + ((long)b * P + (y1 * W + x1)) * P + (y2 * W + x2)) * inv;
+    out[e] = v;
+  }
+}
+
 // Backward, one thread per input element, loops follow correlation_cuda_kernel.cu:151-241 / :244-334
 // (integer divisions truncate toward zero exactly like the reference).
 __global__ void __launch_bounds__(256)
@@ -156,6 +176,22 @@ extern "C" int shineon_correlation_fwd(const float* in1, const float* in2, float
   dim3 grid(g.D, g.outH, B);
   correlation_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in1, in2, out, g);
   return after_launch("correlation_fwd_kernel");
+}
+
+extern "C" int shineon_correlation_gather(const float* full, float* out, int B, int C, int H, int W, int pad_size,
+                                          int max_displacement, int stride2, shineon_stream_t stream) {
+  SHINEON_REQUIRE(full && out, "correlation_gather: null pointer");
+  CorrGeom g;
+  if (!corr_geom(C, H, W, pad_size, 1, max_displacement, 1, stride2, g))
+    return fail(SHINEON_ERR_ARG, "correlation_gather: bad geometry");
+  SHINEON_REQUIRE(g.outH == H && g.outW == W, "correlation_gather: needs pad_size == max_displacement (output size == input size)");
+  const long total = (long)B * g.outC * H * W;
+  if (total == 0) return SHINEON_OK;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  correlation_gather_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(full, out, C, H, W, max_displacement - pad_size,
+                                                                          g.drad, stride2, total);
+  return after_launch("correlation_gather_kernel");
 }
 
 extern "C" int shineon_correlation_bwd(const float* in1, const float* in2, const float* grad_out, float* grad_in1,

@@ -177,6 +177,82 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Batched fused TPS + grid_sample.  U_n(x,y) = d^2 log d^2 depends only on the pixel and the control point, not on
+// the image: each thread computes its pixel's N basis values once (N logf) and reuses them for every image of the
+// batch chunk, leaving ~2N FMAs + the bilinear gathers per (pixel, image) -> memory-bound instead of logf-bound.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTpsChunk = 16;  // images per CTA
+
+template <int N>
+__global__ void __launch_bounds__(256)
+    tps_grid_sample_batched_kernel(const float* __restrict__ theta, TpsTablesDev t, FusedSampleArgs a,
+                                   float* __restrict__ grid_out, int B, int H, int W) {
+  __shared__ float sQ[kTpsChunk][2 * N];
+  __shared__ float2 sWxy[kTpsChunk][N];  // (W_X[n], W_Y[n])
+  __shared__ float sA[kTpsChunk][6];
+  __shared__ float sP[2 * N];
+  const int b0 = blockIdx.y * kTpsChunk;
+  const int nb = min(kTpsChunk, B - b0);
+  constexpr int L = N + 3;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    sP[i] = t.P_X[i];
+    sP[N + i] = t.P_Y[i];
+  }
+  for (int e = threadIdx.x; e < nb * 2 * N; e += blockDim.x) {
+    const int bi = e / (2 * N), k = e - bi * 2 * N;
+    sQ[bi][k] = theta[(long)(b0 + bi) * 2 * N + k] + (k < N ? t.P_X[k] : t.P_Y[k - N]);  // warp.py:207-210
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nb * 2 * L; e += blockDim.x) {
+    const int bi = e / (2 * L), r = e - bi * 2 * L;
+    const int xy = r / L, row = r - xy * L;
+    const float* q = sQ[bi] + xy * N;
+    const float* li = t.Li + row * L;
+    float acc = 0.f;
+    for (int k = 0; k < N; ++k) acc = fmaf(li[k], q[k], acc);
+    if (row < N) {
+      if (xy == 0) sWxy[bi][row].x = acc; else sWxy[bi][row].y = acc;
+    } else {
+      sA[bi][xy * 3 + (row - N)] = acc;
+    }
+  }
+  __syncthreads();
+  const int HW = H * W;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const int y = p / W, x = p - y * W;
+  const float px = t.grid_X[x], py = t.grid_Y[y];
+  float U[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const float dx = px - sP[n], dy = py - sP[N + n];
+    float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (d2 == 0.f) d2 = 1.f;  // warp.py:290
+    U[n] = d2 * logf(d2);
+  }
+  for (int bi = 0; bi < nb; ++bi) {
+    float sx = 0.f, sy = 0.f;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const float2 w = sWxy[bi][n];
+      sx = fmaf(w.x, U[n], sx);
+      sy = fmaf(w.y, U[n], sy);
+    }
+    const float gx = sA[bi][0] + sA[bi][1] * px + sA[bi][2] * py + sx;  // warp.py:303-316
+    const float gy = sA[bi][3] + sA[bi][4] * px + sA[bi][5] * py + sy;
+    const int b = b0 + bi;
+    if (grid_out) reinterpret_cast<float2*>(grid_out)[(long)b * HW + p] = make_float2(gx, gy);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (a.in[i] == nullptr) continue;
+      const BilinearTap tap = make_tap(gx, gy, H, W, a.pad[i]);
+      for (int c = 0; c < a.C[i]; ++c)
+        a.out[i][((long)b * a.C[i] + c) * HW + p] = sample_plane(a.in[i] + ((long)b * a.C[i] + c) * HW, W, tap);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Resample2d  (resample2d_kernel.cu).  kernel_size == 1 (the only value the reference uses).
 // One thread per output pixel; the flow is read once and reused for every channel.
 // ---------------------------------------------------------------------------------------------
@@ -333,6 +409,17 @@ extern "C" int shineon_tps_grid_fwd(const float* theta, const shineon_tps_tables
   SHINEON_REQUIRE(tps->grid_size >= 2 && tps->grid_size * tps->grid_size <= kMaxTpsN, "tps_grid: grid_size %d unsupported", tps->grid_size);
   SHINEON_REQUIRE(B >= 0 && H > 0 && W > 0 && B <= 65535, "tps_grid: bad shape");
   if (B == 0) return SHINEON_OK;
+  const int N = tps->grid_size * tps->grid_size;
+  if (N == 25 || N == 9) {
+    FusedSampleArgs a;
+    for (int i = 0; i < 3; ++i) { a.in[i] = nullptr; a.out[i] = nullptr; a.C[i] = 0; a.pad[i] = 0; }
+    dim3 g(cdiv(H * W, 256), cdiv(B, kTpsChunk));
+    if (N == 25)
+      tps_grid_sample_batched_kernel<25><<<g, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid, B, H, W);
+    else
+      tps_grid_sample_batched_kernel<9><<<g, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid, B, H, W);
+    return after_launch("tps_grid_sample_batched_kernel");
+  }
   tps_grid_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), grid, H, W);
   return after_launch("tps_grid_kernel");
 }
@@ -362,6 +449,15 @@ extern "C" int shineon_tps_grid_sample_fwd(const float* theta, const shineon_tps
   a.in[0] = in0; a.out[0] = out0; a.C[0] = C0; a.pad[0] = pad0;
   a.in[1] = in1; a.out[1] = out1; a.C[1] = C1; a.pad[1] = pad1;
   a.in[2] = in2; a.out[2] = out2; a.C[2] = C2; a.pad[2] = pad2;
+  const int N = tps->grid_size * tps->grid_size;
+  if (N == 25 || N == 9) {
+    dim3 grid(cdiv(H * W, 256), cdiv(B, kTpsChunk));
+    if (N == 25)
+      tps_grid_sample_batched_kernel<25><<<grid, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid_out, B, H, W);
+    else
+      tps_grid_sample_batched_kernel<9><<<grid, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid_out, B, H, W);
+    return after_launch("tps_grid_sample_batched_kernel");
+  }
   tps_grid_sample_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid_out, H, W);
   return after_launch("tps_grid_sample_kernel");
 }

@@ -186,9 +186,8 @@ class FlowNetC(_Net):
         c2a = self._c(prec, "conv2", self._stem(prec, "conv1", x1), out=cat2.window(0))
         c3a = self._c(prec, "conv3", c2a)
         c3b = self._c(prec, "conv3", self._c(prec, "conv2", self._stem(prec, "conv1", x2)))
-        # cost volume on the NCHW f32 features (the Correlation op's interface, correlation.py:47-58)
         in31 = _Concat(B, H // 8, W // 8, (32, 441), prec, dev)
-        corr = ops.correlation_fwd(ops.planes_to_nchw(c3a), ops.planes_to_nchw(c3b), 20, 1, 20, 1, 2)
+        corr = ops.correlation_planes(c3a, c3b, 256, 20, 20, 2)  # tensor-core cost volume straight from the planes
         ops.nchw_to_planes(corr, act="leaky", act_param=LEAK, out=in31.window(1))  # corr_activation
         self._c(prec, "conv_redir", c3a, out=in31.window(0))
         c31 = self._c(prec, "conv3_1", in31.buf, out=cat3.window(0), segs=in31.seg)

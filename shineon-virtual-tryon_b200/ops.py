@@ -208,14 +208,35 @@ def correlation_out_shape(Cc, H, W, pad_size, kernel_size, max_displacement, str
     return oc.value, oh.value, ow.value
 
 
-def correlation_fwd(in1, in2, pad_size, kernel_size, max_displacement, stride1, stride2):
+def correlation_fwd(in1, in2, pad_size, kernel_size, max_displacement, stride1, stride2, tensor_cores=True):
     in1, in2 = _req(in1), _req(in2)
     b, c, h, w = in1.shape
+    if kernel_size == 1 and stride1 == 1 and pad_size == max_displacement and tensor_cores:
+        return correlation_planes(nchw_to_planes(in1), nchw_to_planes(in2), c, pad_size, max_displacement, stride2)
     oc, oh, ow = correlation_out_shape(c, h, w, pad_size, kernel_size, max_displacement, stride1, stride2)
     out = torch.empty(b, oc, oh, ow, dtype=torch.float32, device=in1.device)
     check(_lib.load().shineon_correlation_fwd(_p(in1), _p(in2), _p(out), b, c, h, w, pad_size, kernel_size,
                                               max_displacement, stride1, stride2, _stream()),
           "shineon_correlation_fwd")
+    return out
+
+
+def correlation_planes(f1, f2, C, pad_size, max_displacement, stride2):
+    """Tensor-core cost volume (kernel_size 1, stride1 1, pad == max_displacement): f1, f2 are Planes [B,H,W,C]
+    (e.g. straight out of the conv3 layers).  One per-image tcgen05 GEMM (f2 plays the weights) + a gather.
+    Returns f32 NCHW [B, D*D, H, W]."""
+    assert f1.prec == f2.prec and f1.cpad == f2.cpad and f1.cstride == f1.cpad and f2.cstride == f2.cpad
+    B, H, W = f1.N, f1.H, f1.W
+    P = H * W
+    pc = PackedConv.__new__(PackedConv)
+    pc.fmt = f2.fmt
+    pc.Cout, pc.Cin, pc.kh, pc.kw, pc.stride, pc.pad_h, pc.pad_w = P, C, 1, 1, 1, 0, 0
+    pc.cin_pad, pc.w_hi, pc.w_lo, pc.bias, pc.acc_scale, pc.transposed, pc.per_image = f2.cpad, f2.hi, f2.lo, None, 1.0, False, True
+    full, _ = conv2d(f1, pc, want_f32=True)  # [B,H,W,P]
+    D = 2 * (max_displacement // stride2) + 1
+    out = torch.empty(B, D * D, H, W, dtype=torch.float32, device=full.device)
+    check(_lib.load().shineon_correlation_gather(_p(full), _p(out), B, C, H, W, pad_size, max_displacement, stride2,
+                                                 _stream()), "shineon_correlation_gather")
     return out
 
 
@@ -296,6 +317,7 @@ def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_pa
     p.x_hi, p.x_lo = x._ptr(x.hi), x._ptr(x.lo)
     p.N, p.H, p.W, p.cin_pad, p.x_cstride = N, H, W, x.cpad, x.cstride
     p.w_hi, p.w_lo = _p(pc.w_hi), _p(pc.w_lo)
+    p.w_per_image = int(getattr(pc, "per_image", False))
     p.Cout, p.kh, p.kw, p.stride, p.pad_h, p.pad_w = pc.Cout, pc.kh, pc.kw, pc.stride, pc.pad_h, pc.pad_w
     p.Ho, p.Wo = Ho, Wo
     p.bias, p.scale, p.shift = _p(pc.bias), _p(scale), _p(shift)

@@ -141,7 +141,7 @@ def _tps(ops, gs, H, W):
     return t, dev
 
 
-@pytest.mark.parametrize("gs,scale", [(5, 0.1), (3, 0.3), (5, 0.6)])
+@pytest.mark.parametrize("gs,scale", [(5, 0.1), (3, 0.3), (5, 0.6), (4, 0.2)])
 def test_tps_grid_and_sample(ops, gs, scale):
     from oracle import gmm
 
@@ -208,8 +208,11 @@ def test_correlation(ops, cfg):
     a = torch.randn(2, C, H, W, generator=g)
     b = torch.randn(2, C, H, W, generator=g)
     want = fo.correlation_fwd(a, b, pad, k, maxd, s1, s2)
-    got = ops.correlation_fwd(a.cuda(), b.cuda(), pad, k, maxd, s1, s2)
-    assert_close(got, want, atol=1e-5, rtol=1e-4, what="correlation fwd")
+    got = ops.correlation_fwd(a.cuda(), b.cuda(), pad, k, maxd, s1, s2, tensor_cores=False)
+    assert_close(got, want, atol=1e-5, rtol=1e-4, what="correlation fwd (CUDA-core kernel)")
+    if k == 1 and s1 == 1 and pad == maxd:
+        got_tc = ops.correlation_fwd(a.cuda(), b.cuda(), pad, k, maxd, s1, s2, tensor_cores=True)
+        assert_close(got_tc, want, atol=1e-5, rtol=1e-4, what="correlation fwd (tcgen05 GEMM + gather)")
     if H * W <= 120:
         go = torch.randn(want.shape, generator=g)
         w1, w2 = fo.correlation_bwd(a, b, go, pad, k, maxd, s1, s2)
