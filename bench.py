@@ -229,6 +229,7 @@ def run_b200(args, rank, world):
     from shineon_virtual_tryon_b200 import _lib, distributed, ops
     from shineon_virtual_tryon_b200.pipeline import TryOnPipeline
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("SHINEON_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -303,9 +304,10 @@ def run_b200(args, rank, world):
             "parallelism": f"dp{world} (clips sharded, no collective)", "weights": "seeded random (no checkpoints offline)",
             "l2": f"inputs per step {frames * 32 * H * W * 4 / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
         },
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frames * 32 * H * W * 4,
-                "d2h_bytes_per_step": frames * 3 * H * W * 4, "ms_per_step": main["ms_e2e"] / args.steps},
-        "gpu_launches": main["launches"],
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frames * world * 32 * H * W * 4,
+                "d2h_bytes_per_step": frames * world * 3 * H * W * 4, "ms_per_step": main["ms_e2e"] / args.steps,
+                "api": "TryOnPipeline.run_host: pinned host tensors -> H2D -> kernels -> D2H (double-buffered streams)"},
+        "gpu_launches": main["launches"] * world,
         "clocks": main["clocks"],
         "roofline": {
             "kernel": "conv_igemm_kernel (tcgen05 implicit-GEMM conv, all conv launches of the step)",
