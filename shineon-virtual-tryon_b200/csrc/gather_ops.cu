@@ -117,6 +117,60 @@ __device__ __forceinline__ float sample_plane(const float* __restrict__ plane, i
   return acc;
 }
 
+// Compact tap: 4 clamped offsets + 4 weights, out-of-range taps get weight 0 (x*0 adds exactly 0), so the four
+// loads are unconditional for both padding modes and a pixel costs 8 registers.
+struct Tap4 {
+  int o00, o01, o10, o11;
+  float w00, w01, w10, w11;
+};
+__device__ __forceinline__ Tap4 make_tap4(float gx, float gy, int Hin, int Win, int padding_mode) {
+  float ix = ((gx + 1.f) * Win - 1.f) * 0.5f;
+  float iy = ((gy + 1.f) * Hin - 1.f) * 0.5f;
+  if (padding_mode == SHINEON_PAD_BORDER) {
+    ix = fminf(fmaxf(ix, 0.f), (float)(Win - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(Hin - 1));
+  }
+  const float fx = floorf(ix), fy = floorf(iy);
+  const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;  // ATen: (ix_se - ix), (ix - ix_nw) ...
+  const float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+  const int x0 = (int)fminf(fmaxf(fx, -2.f), (float)Win + 1.f), y0 = (int)fminf(fmaxf(fy, -2.f), (float)Hin + 1.f);
+  const bool vx0 = x0 >= 0 && x0 < Win, vx1 = x0 + 1 >= 0 && x0 + 1 < Win;
+  const bool vy0 = y0 >= 0 && y0 < Hin, vy1 = y0 + 1 >= 0 && y0 + 1 < Hin;
+  const int cx0 = min(max(x0, 0), Win - 1), cx1 = min(max(x0 + 1, 0), Win - 1);
+  const int cy0 = min(max(y0, 0), Hin - 1), cy1 = min(max(y0 + 1, 0), Hin - 1);
+  Tap4 t;
+  t.o00 = cy0 * Win + cx0; t.o01 = cy0 * Win + cx1; t.o10 = cy1 * Win + cx0; t.o11 = cy1 * Win + cx1;
+  t.w00 = (vy0 && vx0) ? wx0 * wy0 : 0.f;
+  t.w01 = (vy0 && vx1) ? wx1 * wy0 : 0.f;
+  t.w10 = (vy1 && vx0) ? wx0 * wy1 : 0.f;
+  t.w11 = (vy1 && vx1) ? wx1 * wy1 : 0.f;
+  return t;
+}
+__device__ __forceinline__ float sample_tap4(const float* __restrict__ plane, const Tap4& t) {
+  float acc = __ldg(plane + t.o00) * t.w00;  // nw, ne, sw, se: ATen's accumulation order
+  acc += __ldg(plane + t.o01) * t.w01;
+  acc += __ldg(plane + t.o10) * t.w10;
+  acc += __ldg(plane + t.o11) * t.w11;
+  return acc;
+}
+
+// Border padding: after clamping the source coordinate every tap index can be clamped too (the weight of an
+// out-of-range neighbour is exactly 0), so the four loads are unconditional.
+__device__ __forceinline__ float sample_plane_clamped(const float* __restrict__ plane, int Hin, int Win, const BilinearTap& t) {
+  const int x0 = min(max(t.x0, 0), Win - 1), x1 = min(max(t.x0 + 1, 0), Win - 1);
+  const int y0 = min(max(t.y0, 0), Hin - 1), y1 = min(max(t.y0 + 1, 0), Hin - 1);
+  const float* r0 = plane + (long)y0 * Win;
+  const float* r1 = plane + (long)y1 * Win;
+  float acc = __ldg(r0 + x0) * t.wnw;
+  acc += __ldg(r0 + x1) * t.wne;
+  acc += __ldg(r1 + x0) * t.wsw;
+  acc += __ldg(r1 + x1) * t.wse;
+  return acc;
+}
+__device__ __forceinline__ float sample_any(const float* __restrict__ plane, int Hin, int Win, const BilinearTap& t, int padding_mode) {
+  return padding_mode == SHINEON_PAD_BORDER ? sample_plane_clamped(plane, Hin, Win, t) : sample_plane(plane, Win, t);
+}
+
 __global__ void __launch_bounds__(256) tps_grid_kernel(const float* __restrict__ theta, TpsTablesDev t,
                                                        float* __restrict__ grid, int H, int W) {
   __shared__ float sQ[2 * kMaxTpsN], sW[2 * kMaxTpsN], sP[2 * kMaxTpsN], sA[6];
@@ -132,17 +186,35 @@ __global__ void __launch_bounds__(256) tps_grid_kernel(const float* __restrict__
   }
 }
 
+constexpr int kPPT = 4;  // pixels per thread: independent load chains in flight (Little's law, not ALU, bounds these)
+
 __global__ void __launch_bounds__(256)
     grid_sample_kernel(const float* __restrict__ in, const float* __restrict__ grid, float* __restrict__ out,
                        int C, int Hin, int Win, int Hout, int Wout, int padding_mode) {
   const int b = blockIdx.y;
   const int HWo = Hout * Wout;
-  const long HWi = (long)Hin * Win;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HWo; p += gridDim.x * blockDim.x) {
-    float2 g = reinterpret_cast<const float2*>(grid)[(long)b * HWo + p];
-    BilinearTap t = make_tap(g.x, g.y, Hin, Win, padding_mode);
-    for (int c = 0; c < C; ++c)
-      out[((long)b * C + c) * HWo + p] = sample_plane(in + ((long)b * C + c) * HWi, Win, t);
+  const int HWi = Hin * Win;
+  const int p0 = blockIdx.x * (256 * kPPT) + threadIdx.x;
+  const float2* gb = reinterpret_cast<const float2*>(grid) + (long)b * HWo;
+  float2 g[kPPT];
+#pragma unroll
+  for (int k = 0; k < kPPT; ++k) {
+    const int p = p0 + k * 256;
+    g[k] = p < HWo ? __ldg(gb + p) : make_float2(0.f, 0.f);
+  }
+  Tap4 t[kPPT];
+#pragma unroll
+  for (int k = 0; k < kPPT; ++k) t[k] = make_tap4(g[k].x, g[k].y, Hin, Win, padding_mode);
+  for (int c = 0; c < C; ++c) {
+    const float* plane = in + ((long)b * C + c) * HWi;
+    float v[kPPT];
+#pragma unroll
+    for (int k = 0; k < kPPT; ++k) v[k] = sample_tap4(plane, t[k]);
+#pragma unroll
+    for (int k = 0; k < kPPT; ++k) {
+      const int p = p0 + k * 256;
+      if (p < HWo) out[((long)b * C + c) * HWo + p] = v[k];
+    }
   }
 }
 
@@ -181,18 +253,18 @@ __global__ void __launch_bounds__(256)
 // the image: each thread computes its pixel's N basis values once (N logf) and reuses them for every image of the
 // batch chunk, leaving ~2N FMAs + the bilinear gathers per (pixel, image) -> memory-bound instead of logf-bound.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTpsChunk = 16;  // images per CTA
+constexpr int kTpsChunk = 16;  // max images per CTA (fewer for small batches so the grid still fills the GPU)
 
 template <int N>
 __global__ void __launch_bounds__(256)
     tps_grid_sample_batched_kernel(const float* __restrict__ theta, TpsTablesDev t, FusedSampleArgs a,
-                                   float* __restrict__ grid_out, int B, int H, int W) {
+                                   float* __restrict__ grid_out, int B, int H, int W, int chunk) {
   __shared__ float sQ[kTpsChunk][2 * N];
   __shared__ float2 sWxy[kTpsChunk][N];  // (W_X[n], W_Y[n])
   __shared__ float sA[kTpsChunk][6];
   __shared__ float sP[2 * N];
-  const int b0 = blockIdx.y * kTpsChunk;
-  const int nb = min(kTpsChunk, B - b0);
+  const int b0 = blockIdx.y * chunk;
+  const int nb = min(chunk, B - b0);
   constexpr int L = N + 3;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     sP[i] = t.P_X[i];
@@ -245,9 +317,9 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       if (a.in[i] == nullptr) continue;
-      const BilinearTap tap = make_tap(gx, gy, H, W, a.pad[i]);
+      const Tap4 tap = make_tap4(gx, gy, H, W, a.pad[i]);
       for (int c = 0; c < a.C[i]; ++c)
-        a.out[i][((long)b * a.C[i] + c) * HW + p] = sample_plane(a.in[i] + ((long)b * a.C[i] + c) * HW, W, tap);
+        a.out[i][((long)b * a.C[i] + c) * HW + p] = sample_tap4(a.in[i] + ((long)b * a.C[i] + c) * HW, tap);
     }
   }
 }
@@ -261,35 +333,59 @@ __global__ void __launch_bounds__(256)
                           float* __restrict__ out, int C, int H, int W, int bilinear) {
   const int b = blockIdx.y;
   const int HW = H * W;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
-    int y = p / W, x = p - y * W;
-    float dx = flow[((long)b * 2 + 0) * HW + p];
-    float dy = flow[((long)b * 2 + 1) * HW + p];
-    float xf = (float)x + dx, yf = (float)y + dy;
+  const int p0 = blockIdx.x * (256 * kPPT) + threadIdx.x;
+  float dx[kPPT], dy[kPPT];
+#pragma unroll
+  for (int k = 0; k < kPPT; ++k) {
+    const int p = min(p0 + k * 256, HW - 1);
+    dx[k] = __ldg(flow + ((long)b * 2 + 0) * HW + p);
+    dy[k] = __ldg(flow + ((long)b * 2 + 1) * HW + p);
+  }
+  int o00[kPPT], o01[kPPT], o10[kPPT], o11[kPPT];
+  float w00[kPPT], w01[kPPT], w10[kPPT], w11[kPPT];
+#pragma unroll
+  for (int k = 0; k < kPPT; ++k) {
+    const int p = min(p0 + k * 256, HW - 1);
+    const int y = p / W, x = p - y * W;
+    const float xf = (float)x + dx[k], yf = (float)y + dy[k];
     if (bilinear) {
-      float fx = floorf(xf), fy = floorf(yf);
-      float alpha = xf - fx, beta = yf - fy;  // resample2d_kernel.cu:42-43
+      const float fx = floorf(xf), fy = floorf(yf);
+      const float alpha = xf - fx, beta = yf - fy;  // resample2d_kernel.cu:42-43
       // int(floor(xf)) with a defined result for huge flows
-      float cfx = fminf(fmaxf(fx, -4.f), (float)W + 4.f), cfy = fminf(fmaxf(fy, -4.f), (float)H + 4.f);
-      int xL = max(min((int)cfx, W - 1), 0), xR = max(min((int)cfx + 1, W - 1), 0);
-      int yT = max(min((int)cfy, H - 1), 0), yB = max(min((int)cfy + 1, H - 1), 0);
-      float w00 = (1.f - alpha) * (1.f - beta), w01 = alpha * (1.f - beta);
-      float w10 = (1.f - alpha) * beta, w11 = alpha * beta;
-      for (int c = 0; c < C; ++c) {
-        const float* pl = in1 + ((long)b * C + c) * HW;
-        float v = 0.f;  // same accumulation order as resample2d_kernel.cu:56-59
-        v += w00 * __ldg(pl + yT * W + xL);
-        v += w01 * __ldg(pl + yT * W + xR);
-        v += w10 * __ldg(pl + yB * W + xL);
-        v += w11 * __ldg(pl + yB * W + xR);
-        out[((long)b * C + c) * HW + p] = v;
-      }
+      const float cfx = fminf(fmaxf(fx, -4.f), (float)W + 4.f), cfy = fminf(fmaxf(fy, -4.f), (float)H + 4.f);
+      const int xL = max(min((int)cfx, W - 1), 0), xR = max(min((int)cfx + 1, W - 1), 0);
+      const int yT = max(min((int)cfy, H - 1), 0), yB = max(min((int)cfy + 1, H - 1), 0);
+      o00[k] = yT * W + xL; o01[k] = yT * W + xR; o10[k] = yB * W + xL; o11[k] = yB * W + xR;
+      w00[k] = (1.f - alpha) * (1.f - beta); w01[k] = alpha * (1.f - beta);
+      w10[k] = (1.f - alpha) * beta; w11[k] = alpha * beta;
     } else {
-      float nx = fminf(fmaxf(floorf(xf + 0.5f), -4.f), (float)W + 4.f);
-      float ny = fminf(fmaxf(floorf(yf + 0.5f), -4.f), (float)H + 4.f);
-      int xN = max(min((int)nx, W - 1), 0), yN = max(min((int)ny, H - 1), 0);
-      for (int c = 0; c < C; ++c)
-        out[((long)b * C + c) * HW + p] = __ldg(in1 + ((long)b * C + c) * HW + yN * W + xN);
+      const float nx = fminf(fmaxf(floorf(xf + 0.5f), -4.f), (float)W + 4.f);
+      const float ny = fminf(fmaxf(floorf(yf + 0.5f), -4.f), (float)H + 4.f);
+      o00[k] = max(min((int)ny, H - 1), 0) * W + max(min((int)nx, W - 1), 0);
+      o01[k] = o10[k] = o11[k] = o00[k];
+      w00[k] = 1.f; w01[k] = w10[k] = w11[k] = 0.f;
+    }
+  }
+  for (int c = 0; c < C; ++c) {
+    const float* pl = in1 + ((long)b * C + c) * HW;
+    float v[kPPT];
+#pragma unroll
+    for (int k = 0; k < kPPT; ++k) {
+      if (bilinear) {  // same accumulation order as resample2d_kernel.cu:56-59
+        float a = 0.f;
+        a += w00[k] * __ldg(pl + o00[k]);
+        a += w01[k] * __ldg(pl + o01[k]);
+        a += w10[k] * __ldg(pl + o10[k]);
+        a += w11[k] * __ldg(pl + o11[k]);
+        v[k] = a;
+      } else {
+        v[k] = __ldg(pl + o00[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kPPT; ++k) {
+      const int p = p0 + k * 256;
+      if (p < HW) out[((long)b * C + c) * HW + p] = v[k];
     }
   }
 }
@@ -363,15 +459,30 @@ __global__ void __launch_bounds__(256)
 // ChannelNorm (channelnorm_kernel.cu): out = sqrt(sum_c x^2); norm_deg is ignored by the reference.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-    channelnorm_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int C, long HW, long total) {
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long b = i / HW, p = i - b * HW;
-    float acc = 0.f;
+    channelnorm_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW) {
+  // grid.y = image; each thread owns 4 consecutive pixels (float4 per channel plane) when HW % 4 == 0
+  const int b = blockIdx.y;
+  const float* ib = in + (long)b * C * HW;
+  float* ob = out + (long)b * HW;
+  if ((HW & 3) == 0) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q * 4 >= HW) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = 0; c < C; ++c) {
-      float v = in[(b * C + c) * HW + p];
-      acc += v * v;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ib + (long)c * HW) + q);
+      acc.x = fmaf(v.x, v.x, acc.x); acc.y = fmaf(v.y, v.y, acc.y);
+      acc.z = fmaf(v.z, v.z, acc.z); acc.w = fmaf(v.w, v.w, acc.w);
     }
-    out[i] = sqrtf(acc);
+    reinterpret_cast<float4*>(ob)[q] = make_float4(sqrtf(acc.x), sqrtf(acc.y), sqrtf(acc.z), sqrtf(acc.w));
+  } else {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
+      float acc = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float v = ib[(long)c * HW + p];
+        acc = fmaf(v, v, acc);
+      }
+      ob[p] = sqrtf(acc);
+    }
   }
 }
 
@@ -413,11 +524,12 @@ extern "C" int shineon_tps_grid_fwd(const float* theta, const shineon_tps_tables
   if (N == 25 || N == 9) {
     FusedSampleArgs a;
     for (int i = 0; i < 3; ++i) { a.in[i] = nullptr; a.out[i] = nullptr; a.C[i] = 0; a.pad[i] = 0; }
-    dim3 g(cdiv(H * W, 256), cdiv(B, kTpsChunk));
+    const int chunk = B >= 128 ? kTpsChunk : (B >= 32 ? 8 : 2);
+    dim3 g(cdiv(H * W, 256), cdiv(B, chunk));
     if (N == 25)
-      tps_grid_sample_batched_kernel<25><<<g, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid, B, H, W);
+      tps_grid_sample_batched_kernel<25><<<g, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid, B, H, W, chunk);
     else
-      tps_grid_sample_batched_kernel<9><<<g, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid, B, H, W);
+      tps_grid_sample_batched_kernel<9><<<g, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid, B, H, W, chunk);
     return after_launch("tps_grid_sample_batched_kernel");
   }
   tps_grid_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), grid, H, W);
@@ -430,8 +542,8 @@ extern "C" int shineon_grid_sample_fwd(const float* input, const float* grid, fl
   SHINEON_REQUIRE(padding_mode == SHINEON_PAD_ZEROS || padding_mode == SHINEON_PAD_BORDER, "grid_sample: padding_mode %d", padding_mode);
   SHINEON_REQUIRE(B >= 0 && C > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && B <= 65535, "grid_sample: bad shape");
   if (B == 0) return SHINEON_OK;
-  grid_sample_kernel<<<pixel_grid(Hout * Wout, B), 256, 0, (cudaStream_t)stream>>>(input, grid, out, C, Hin, Win,
-                                                                                  Hout, Wout, padding_mode);
+  grid_sample_kernel<<<dim3(cdiv(Hout * Wout, 256 * kPPT), B), 256, 0, (cudaStream_t)stream>>>(input, grid, out, C, Hin, Win,
+                                                                                              Hout, Wout, padding_mode);
   return after_launch("grid_sample_kernel");
 }
 
@@ -451,11 +563,12 @@ extern "C" int shineon_tps_grid_sample_fwd(const float* theta, const shineon_tps
   a.in[2] = in2; a.out[2] = out2; a.C[2] = C2; a.pad[2] = pad2;
   const int N = tps->grid_size * tps->grid_size;
   if (N == 25 || N == 9) {
-    dim3 grid(cdiv(H * W, 256), cdiv(B, kTpsChunk));
+    const int chunk = B >= 128 ? kTpsChunk : (B >= 32 ? 8 : 2);
+    dim3 grid(cdiv(H * W, 256), cdiv(B, chunk));
     if (N == 25)
-      tps_grid_sample_batched_kernel<25><<<grid, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid_out, B, H, W);
+      tps_grid_sample_batched_kernel<25><<<grid, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid_out, B, H, W, chunk);
     else
-      tps_grid_sample_batched_kernel<9><<<grid, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid_out, B, H, W);
+      tps_grid_sample_batched_kernel<9><<<grid, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid_out, B, H, W, chunk);
     return after_launch("tps_grid_sample_batched_kernel");
   }
   tps_grid_sample_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid_out, H, W);
@@ -469,7 +582,7 @@ extern "C" int shineon_resample2d_fwd(const float* in1, const float* flow, float
   if (kernel_size != 1) return fail(SHINEON_ERR_UNSUPPORTED, "resample2d: kernel_size %d (only 1, as the reference uses)", kernel_size);
   if (Hi != H || Wi != W) return fail(SHINEON_ERR_UNSUPPORTED, "resample2d: input %dx%d != flow %dx%d", Hi, Wi, H, W);
   if (B == 0) return SHINEON_OK;
-  resample2d_fwd_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(in1, flow, out, C, H, W, bilinear);
+  resample2d_fwd_kernel<<<dim3(cdiv(H * W, 256 * kPPT), B), 256, 0, (cudaStream_t)stream>>>(in1, flow, out, C, H, W, bilinear);
   return after_launch("resample2d_fwd_kernel");
 }
 
@@ -494,10 +607,11 @@ extern "C" int shineon_channelnorm_fwd(const float* in, float* out, int B, int C
   SHINEON_REQUIRE(in && out, "channelnorm_fwd: null pointer");
   SHINEON_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0, "channelnorm_fwd: bad shape");
   (void)norm_deg;
-  long total = (long)B * H * W;
-  if (total == 0) return SHINEON_OK;
-  int blocks = (int)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256);
-  channelnorm_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, C, (long)H * W, total);
+  if (B == 0) return SHINEON_OK;
+  SHINEON_REQUIRE(B <= 65535, "channelnorm_fwd: batch too large");
+  const int HW = H * W;
+  dim3 grid((HW & 3) == 0 ? cdiv(HW / 4, 256) : min(cdiv(HW, 256), 4096), B);
+  channelnorm_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, HW);
   return after_launch("channelnorm_fwd_kernel");
 }
 
