@@ -293,6 +293,13 @@ int shineon_flownet_fusion_concat(const float* x, const float* flow_sd, const fl
 int shineon_flow_confidence(const float* im1, const float* im2, const float* flow, float* conf, int B, int C, int H,
                             int W, float threshold, shineon_stream_t stream);
 
+/* ------------------------------------------------------------------ */
+/* U6/U7 building block: fused Adam over flat f32 buffers (torch.optim.Adam semantics, base_model.py:165-168) */
+/* ------------------------------------------------------------------ */
+/* param -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps), with g = grad*grad_scale (+ weight_decay*param). */
+int shineon_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int step, float grad_scale, shineon_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

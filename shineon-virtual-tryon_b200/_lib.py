@@ -71,6 +71,7 @@ SIGNATURES = {
     "shineon_flownet_warp_concat": [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p],
     "shineon_flownet_fusion_concat": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "shineon_flow_confidence": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
+    "shineon_adam_step": [c_p, c_p, c_p, c_p, C.c_long, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_p],
     "shineon_tom_compose": [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
 }
 _RESTYPES = {"shineon_last_error": C.c_char_p, "shineon_launch_count": C.c_uint64}

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libshineon_b200.so")
-SOURCES = ["capi.cu", "gather_ops.cu", "correlation.cu", "conv_igemm.cu", "norm_act.cu", "attention.cu", "gmm_ops.cu", "flownet_glue.cu"]
+SOURCES = ["capi.cu", "gather_ops.cu", "correlation.cu", "conv_igemm.cu", "norm_act.cu", "attention.cu", "gmm_ops.cu", "flownet_glue.cu", "optim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

@@ -51,3 +51,41 @@ def sum_over_ranks(value, device="cpu"):
     if dist.is_initialized():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+class FlatGradAllReducer:
+    """Data-parallel gradient exchange of the training path: ONE flat f32 gradient buffer,
+    summed over ranks with bucketed asynchronous all-reduces (NCCL over NVLink/NVSwitch on GPUs; gloo in the CPU
+    tests).  The 1/world_size of the mean is folded into the optimiser's `grad_scale` (ops.adam_step), so the
+    collective moves raw sums.  Buckets are issued last-layer-first so the exchange of the layers whose gradients
+    are ready first overlaps the rest of the backward pass."""
+
+    def __init__(self, params, bucket_bytes=32 << 20):
+        self.params = [p for p in params]
+        self.numel = sum(p.numel() for p in self.params)
+        first = self.params[0]
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=first.device)
+        self.views, off = [], 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        per = max(1, bucket_bytes // 4)
+        self.buckets = [(s, min(s + per, self.numel)) for s in range(0, self.numel, per)]
+        self._work = []
+
+    def grad_view(self, i):
+        """Where the backward pass writes the gradient of parameter i (no per-parameter .grad tensors to pack)."""
+        return self.views[i]
+
+    def start(self):
+        """Launch the bucketed sums (async), last bucket first."""
+        self._work = []
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            for s, e in reversed(self.buckets):
+                self._work.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, async_op=True))
+
+    def finish(self):
+        for w in self._work:
+            w.wait()
+        self._work = []
+        return 1.0 / (dist.get_world_size() if dist.is_initialized() else 1)  # grad_scale for the optimiser

@@ -550,3 +550,15 @@ def flow_confidence(im1, im2, flow, threshold=0.02):
     check(_lib.load().shineon_flow_confidence(_p(im1), _p(im2), _p(flow), _p(conf), B, Cc, H, W, float(threshold),
                                               _stream()), "shineon_flow_confidence")
     return conf
+
+
+# ----------------------------------------------------------------------------- optimiser building block (rows U6/U7)
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+              grad_scale=1.0):
+    """In-place fused Adam on flat f32 CUDA buffers (torch.optim.Adam semantics)."""
+    param, grad, exp_avg, exp_avg_sq = _req(param), _req(grad), _req(exp_avg), _req(exp_avg_sq)
+    n = param.numel()
+    assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
+    check(_lib.load().shineon_adam_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), n, float(lr), float(betas[0]),
+                                        float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale),
+                                        _stream()), "shineon_adam_step")

@@ -326,3 +326,19 @@ def test_tom_compose(ops, nf, flow):
             r = (1 - wf) * prev + wf * r
         want = (1 - w_tm[:, f:f + 1]) * r + w_tm[:, f:f + 1] * cloth[:, 3 * f:3 * f + 3]
         assert_close(pt[:, 3 * f:3 * f + 3], want, atol=2e-6, rtol=1e-5, what=f"p_tryon[{f}]")
+
+
+def test_fused_adam_matches_torch_optim(ops):
+    """shineon_adam_step vs torch.optim.Adam (CPU, fp32) over several steps, incl. the folded 1/world grad scale."""
+    g = torch.Generator().manual_seed(77)
+    n, world = 10007, 4
+    p_ref = torch.nn.Parameter(torch.randn(n, generator=g))
+    opt = torch.optim.Adam([p_ref], lr=1e-4)
+    p = p_ref.detach().clone().cuda()
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 6):
+        grad_sum = torch.randn(n, generator=g) * world  # what the all-reduce (SUM) delivers
+        p_ref.grad = grad_sum / world
+        opt.step()
+        ops.adam_step(p, grad_sum.cuda(), m, v, step, lr=1e-4, grad_scale=1.0 / world)
+    assert_close(p, p_ref.detach(), atol=1e-6, rtol=1e-5, what="adam parameters after 5 steps")
