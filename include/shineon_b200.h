@@ -190,6 +190,13 @@ typedef struct shineon_conv2d_params {
 } shineon_conv2d_params;
 
 int shineon_conv2d_igemm_fwd(const shineon_conv2d_params* p, shineon_stream_t stream);
+/* Small-Cin first layers: the same GEMM with the im2col matrix produced INSIDE the kernel (producer warps gather the
+ * NCHW f32 input(s) x0 [N,C0,H,W] (+ x1 [N,C1,H,W], concatenated on C), split to 16-bit planes and write the swizzled
+ * shared-memory tile; nothing is materialised in HBM).  `p` describes the real convolution (N,H,W = input size,
+ * kh,kw,stride,pad_*, Ho,Wo); w_hi/w_lo are packed tap-major: [Cout][1][cin_pad] with k = (fy*kw+fx)*C + c and
+ * cin_pad = pad64(kh*kw*C); x_hi/x_lo are ignored. */
+int shineon_conv2d_im2col_fwd(const shineon_conv2d_params* p, const float* x0, int C0, const float* x1, int C1,
+                              shineon_stream_t stream);
 /* CUDA-core fp32 direct convolution over the same operands: the on-GPU cross-check of the tcgen05
  * kernel used by tests (not on the product path). */
 int shineon_conv2d_direct_fwd(const shineon_conv2d_params* p, shineon_stream_t stream);

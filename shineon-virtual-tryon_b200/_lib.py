@@ -55,6 +55,7 @@ SIGNATURES = {
     "shineon_correlation_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_pack_conv_weight": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_f, c_p],
     "shineon_conv2d_igemm_fwd": [C.POINTER(Conv2dParams), c_p],
+    "shineon_conv2d_im2col_fwd": [C.POINTER(Conv2dParams), c_p, c_i, c_p, c_i, c_p],
     "shineon_conv2d_direct_fwd": [C.POINTER(Conv2dParams), c_p],
     "shineon_nchw_to_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     "shineon_planes_to_nchw": [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p],

@@ -460,6 +460,237 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// First-layer variant: the A operand is produced IN the kernel.  Small-Cin layers (3/10/22 input channels, FlowNet
+// stems) are a dense GEMM over K = kh*kw*Cin; instead of materialising the im2col matrix in HBM (1.5 GB for the
+// GMM's 22-channel input at 80 frames) four producer warps gather the NCHW f32 input, split it to 16-bit hi/lo
+// and write the 128x64 K-major tile straight into shared memory in the SWIZZLE_128B pattern tcgen05.mma expects
+// (16-byte chunk j of row r lives at chunk j ^ (r & 7)); B still arrives by TMA.
+// Warp roles: 0-3 A producers (thread r owns tile row r), 4 = B TMA + TMEM alloc, 5 = MMA issuer, 6-9 = epilogue.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kI2cThreads = 320;
+
+struct Im2colSrc {
+  const float* x0;
+  const float* x1;
+  int C0, C1, H, W;  // input NCHW geometry (two tensors concatenated on C)
+};
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(kI2cThreads, 1)
+    conv_im2col_igemm_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                             const ConvArgs a, const Im2colSrc src) {
+  constexpr int kBBytes = BN * kBlockK * 2;
+  constexpr int kPlanes = SPLIT ? 2 : 1;
+  constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  constexpr int kAccCols = BN < 32 ? 32 : BN;
+  constexpr int kTmemCols = 2 * kAccCols;
+  const uint32_t kIdesc = a.idesc;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[BN], s_scale[BN], s_shift[BN];
+
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* tiles_ptr = smem_raw + (tiles - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = a.stages;
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]),
+                 bar_tfull = smem_u32(&bars[2 * kMaxStages]), bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
+
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&tmBh);
+    if (SPLIT) prefetch_tmap(&tmBl);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, 5);  // 4 producer warps + the TMA thread's arrive.expect_tx
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc<kTmemCols>(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int tiles_hw = a.tiles_w * a.tiles_h;
+  const int C = src.C0 + src.C1;
+  const int K = a.kh * a.kw * C;
+  const int HW = src.H * src.W;
+
+  if (warp < 4) {
+    // ===================================================== A producers: gather + split + swizzled store
+    const int r = threadIdx.x;  // tile row 0..127
+    const int wi = r % a.bw, hi_ = (r / a.bw) % a.bh, ni = r / (a.bw * a.bh);
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const int mt = tile / a.n_tiles;
+      const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, tn = mt / tiles_hw;
+      const int n = tn * a.nb + ni, oh = th * a.bh + hi_, ow = tw * a.bw + wi;
+      const bool row_ok = ni < a.nb && n < a.N && oh < a.Ho && ow < a.Wo;
+      const int iy0 = oh * a.stride - a.pad_h, ix0 = ow * a.stride - a.pad_w;
+      const float* p0 = src.x0 + (long)n * src.C0 * HW;
+      const float* p1 = src.x1 ? src.x1 + (long)n * src.C1 * HW : nullptr;
+      for (int kb = 0; kb < a.num_kb; ++kb, ++g) {
+        const int s = g % S;
+        const uint32_t ph = (g / S) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        uint8_t* rowh = tiles_ptr + s * kStageBytes + r * 128;
+        uint8_t* rowl = rowh + kABytes;
+        int k = kb * kBlockK;
+        int tap = k / C, c = k - tap * C;
+        int fy = tap / a.kw, fx = tap - fy * a.kw;
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {  // 8 chunks of 8 consecutive k
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float val = 0.f;
+            if (row_ok && k + e < K) {
+              const int iy = iy0 + fy, ix = ix0 + fx;
+              if (iy >= 0 && iy < src.H && ix >= 0 && ix < src.W)
+                val = c < src.C0 ? __ldg(p0 + (long)c * HW + iy * src.W + ix)
+                                 : __ldg(p1 + (long)(c - src.C0) * HW + iy * src.W + ix);
+            }
+            v[e] = val;
+            if (++c == C) {
+              c = 0;
+              if (++fx == a.kw) { fx = 0; ++fy; }
+            }
+          }
+          k += 8;
+          __align__(16) plane_t hi[8];
+          __align__(16) plane_t lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split16(v[e], a.fmt, hi[e], lo[e]);
+          const int chunk = (j ^ (r & 7)) * 16;
+          *reinterpret_cast<uint4*>(rowh + chunk) = *reinterpret_cast<const uint4*>(hi);
+          if (SPLIT) *reinterpret_cast<uint4*>(rowl + chunk) = *reinterpret_cast<const uint4*>(lo);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * s);
+      }
+    }
+  } else if (warp == 4) {
+    // ===================================================== B operand by TMA
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int cn0 = (tile % a.n_tiles) * BN;
+        for (int kb = 0; kb < a.num_kb; ++kb, ++g) {
+          const int s = g % S;
+          const uint32_t ph = (g / S) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_expect_tx(full, kPlanes * kBBytes);
+          const uint32_t sB = tiles + s * kStageBytes + kPlanes * kABytes;
+          tma_load_2d(sB, &tmBh, full, kb * kBlockK, cn0);
+          if (SPLIT) tma_load_2d(sB + kBBytes, &tmBl, full, kb * kBlockK, cn0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t g = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + buf * kAccCols;
+        for (int kb = 0; kb < a.num_kb; ++kb, ++g) {
+          const int s = g % S;
+          const uint32_t ph = (g / S) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sA = tiles + s * kStageBytes;
+          const uint32_t sB = sA + kPlanes * kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t dAh = umma_desc_sw128(sA + k * 32);
+            const uint64_t dBh = umma_desc_sw128(sB + k * 32);
+            umma_f16(tmem_acc, dAh, dBh, kIdesc, (kb | k) != 0);
+            if (SPLIT) {
+              const uint64_t dAl = umma_desc_sw128(sA + kABytes + k * 32);
+              const uint64_t dBl = umma_desc_sw128(sB + kBBytes + k * 32);
+              umma_f16(tmem_acc, dAh, dBl, kIdesc, 1);
+              umma_f16(tmem_acc, dAl, dBh, kIdesc, 1);
+            }
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else {
+    // ===================================================== epilogue (same as conv_igemm_kernel)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int wi = r % a.bw, hi_ = (r / a.bw) % a.bh, ni = r / (a.bw * a.bh);
+    constexpr int kChunk = BN < 32 ? BN : 32;
+    const int et = threadIdx.x - 192;  // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+      const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, tn = mt / tiles_hw;
+      const int cn0 = nt * BN;
+      const int n = tn * a.nb + ni, oh = th * a.bh + hi_, ow = tw * a.bw + wi;
+      const bool row_ok = ni < a.nb && n < a.N && oh < a.Ho && ow < a.Wo;
+      const long pix = ((long)n * a.out_H + (oh * a.oh_mul + a.oh_off)) * a.out_W + (ow * a.ow_mul + a.ow_off);
+      epi_bar_sync();
+      for (int i = et; i < BN; i += 128) {
+        const int c = cn0 + i;
+        const bool ok = c < a.Cout;
+        s_bias[i] = (ok && a.bias) ? __ldg(a.bias + c) : 0.f;
+        s_scale[i] = (ok && a.scale) ? __ldg(a.scale + c) : 1.f;
+        s_shift[i] = (ok && a.scale) ? __ldg(a.shift + c) : 0.f;
+      }
+      epi_bar_sync();
+      const int buf = it & 1;
+      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * kAccCols;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += kChunk) {
+        if (cn0 + c0 >= a.Cout) break;
+        uint32_t v[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        if (kChunk == 32)
+          tmem_ld32(taddr, v);
+        else
+          tmem_ld16(taddr, v);
+        tmem_ld_wait();
+        const int cnt = min(kChunk, a.Cout - (cn0 + c0));
+        float vals[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          vals[i] = (i < kChunk) ? fmaf(__uint_as_float(v[i]), a.acc_scale, s_bias[c0 + (i < kChunk ? i : 0)]) : 0.f;
+        act_chunk_dispatch(vals, a.pre_act, a.act_param);
+        if (a.scale != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < kChunk) vals[i] = fmaf(vals[i], s_scale[c0 + i], s_shift[c0 + i]);
+        }
+        act_chunk_dispatch(vals, a.post_act, a.act_param);
+        if (row_ok) conv_store_row(vals, cn0 + c0, cnt, pix, a);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
 // ---------------------------------------------------------------------------- CUDA-core cross-check
 // Same operands, same epilogue, plain fp32 FMAs.  Tests compare the tcgen05 kernel against this on
 // the GPU at sizes where the CPU oracle would take minutes.  Not on the product path.
@@ -722,6 +953,97 @@ extern "C" int shineon_conv2d_igemm_fwd(const shineon_conv2d_params* p, shineon_
     default: return SHINEON_LAUNCH(256);
   }
 #undef SHINEON_LAUNCH
+}
+
+template <int BN, bool SPLIT>
+static int launch_im2col(const CUtensorMap& tBh, const CUtensorMap& tBl, ConvArgs& a, const Im2colSrc& src, int m_tiles,
+                         cudaStream_t stream) {
+  constexpr int kBBytes = BN * kBlockK * 2;
+  constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
+  int stages = a.num_kb < 4 ? a.num_kb : 4;
+  a.idesc = umma_idesc_f16(kBlockM, BN, a.fmt == SHINEON_FMT_FP16 ? 0 : 1);
+  static int max_dyn_smem = -1;
+  if (max_dyn_smem < 0) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv_im2col_igemm_kernel<BN, SPLIT>);
+    if (e == cudaSuccess) {
+      max_dyn_smem = 227 * 1024 - (int)fa.sharedSizeBytes;
+      e = cudaFuncSetAttribute(conv_im2col_igemm_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem);
+    }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      max_dyn_smem = -1;
+      return fail(SHINEON_ERR_CUDA, "conv_im2col shared-memory opt-in: %s", cudaGetErrorString(e));
+    }
+  }
+  while (stages > 1 && stages * kStageBytes + 1024 > max_dyn_smem) --stages;
+  a.stages = stages;
+  a.n_tiles = cdiv(a.Cout, BN);
+  a.total_tiles = m_tiles * a.n_tiles;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
+  conv_im2col_igemm_kernel<BN, SPLIT><<<grid, kI2cThreads, stages * kStageBytes + 1024, stream>>>(tBh, tBl, a, src);
+  return after_launch("conv_im2col_igemm_kernel");
+}
+
+extern "C" int shineon_conv2d_im2col_fwd(const shineon_conv2d_params* p, const float* x0, int C0, const float* x1, int C1,
+                                         shineon_stream_t stream_) {
+  SHINEON_REQUIRE(p && x0 && C0 > 0 && (x1 == nullptr) == (C1 == 0), "conv2d_im2col: bad input tensors");
+  SHINEON_REQUIRE(p->w_hi && p->N > 0 && p->H > 0 && p->W > 0 && p->Cout > 0, "conv2d_im2col: bad shape");
+  SHINEON_REQUIRE(p->cin_pad % kBlockK == 0 && p->cin_pad >= p->kh * p->kw * (C0 + C1), "conv2d_im2col: cin_pad (= padded K) %d", p->cin_pad);
+  SHINEON_REQUIRE(p->Ho == (p->H + 2 * p->pad_h - p->kh) / p->stride + 1 && p->Wo == (p->W + 2 * p->pad_w - p->kw) / p->stride + 1, "conv2d_im2col: Ho/Wo");
+  SHINEON_REQUIRE(p->y_f32 || p->y_hi, "conv2d_im2col: no output");
+  SHINEON_REQUIRE((p->scale == nullptr) == (p->shift == nullptr), "conv2d_im2col: scale/shift");
+  SHINEON_REQUIRE(p->plane_fmt == SHINEON_FMT_BF16 || p->plane_fmt == SHINEON_FMT_FP16, "conv2d_im2col: plane_fmt");
+  ConvArgs a;
+  a.N = p->N; a.Ho = p->Ho; a.Wo = p->Wo; a.Cout = p->Cout;
+  a.kh = p->kh; a.kw = p->kw; a.stride = p->stride; a.pad_h = p->pad_h; a.pad_w = p->pad_w;
+  a.cin_pad = p->cin_pad; a.cin_blocks = p->cin_pad / kBlockK; a.x_cstride = p->cin_pad;
+  a.num_kb = a.cin_blocks;  // the GEMM is 1x1 over the padded K
+  a.stages = 1; a.w_per_image = 0;
+  a.bias = p->bias; a.scale = p->scale; a.shift = p->shift;
+  a.pre_act = p->pre_act; a.post_act = p->post_act; a.act_param = p->act_param;
+  a.fmt = p->plane_fmt; a.acc_scale = p->acc_scale == 0.f ? 1.f : p->acc_scale; a.idesc = 0;
+  a.y_f32 = p->y_f32; a.y_hi = (plane_t*)p->y_hi; a.y_lo = (plane_t*)p->y_lo;
+  a.oh_mul = 1; a.ow_mul = 1; a.oh_off = 0; a.ow_off = 0;
+  a.out_H = p->Ho; a.out_W = p->Wo;
+  a.out_cstride = p->out_cstride ? p->out_cstride : p->Cout;
+  a.out_coffset = p->out_coffset;
+  SHINEON_REQUIRE(a.out_coffset >= 0 && a.out_coffset + a.Cout <= a.out_cstride, "conv2d_im2col: output channel window out of range");
+  pick_tile(a.N, a.Ho, a.Wo, a.nb, a.bh, a.bw);
+  a.tiles_w = cdiv(a.Wo, a.bw);
+  a.tiles_h = cdiv(a.Ho, a.bh);
+  const int m_tiles = a.tiles_w * a.tiles_h * cdiv(a.N, a.nb);
+  const bool split = p->w_lo != nullptr;
+  int bn = p->tile_n;
+  if (bn == 0) bn = a.Cout <= 16 ? 16 : a.Cout <= 32 ? 32 : a.Cout <= 64 ? 64 : 128;
+  SHINEON_REQUIRE(bn == 16 || bn == 32 || bn == 64 || bn == 128, "conv2d_im2col: tile_n %d", bn);
+  CUtensorMap tBh, tBl;
+  int rc;
+  {
+    const cuuint64_t K = (cuuint64_t)p->cin_pad;
+    cuuint64_t dims[2] = {K, (cuuint64_t)p->Cout};
+    cuuint64_t strides[1] = {K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)bn};
+    if ((rc = encode_map(&tBh, p->w_hi, 2, dims, strides, box, "B hi", p->plane_fmt))) return rc;
+    if (split && (rc = encode_map(&tBl, p->w_lo, 2, dims, strides, box, "B lo", p->plane_fmt))) return rc;
+    if (!split) tBl = tBh;
+  }
+  Im2colSrc src{x0, x1, C0, C1, p->H, p->W};
+  cudaStream_t stream = (cudaStream_t)stream_;
+#define SHINEON_LAUNCH_I2C(BN_) (split ? launch_im2col<BN_, true>(tBh, tBl, a, src, m_tiles, stream) : launch_im2col<BN_, false>(tBh, tBl, a, src, m_tiles, stream))
+  switch (bn) {
+    case 16: return SHINEON_LAUNCH_I2C(16);
+    case 32: return SHINEON_LAUNCH_I2C(32);
+    case 64: return SHINEON_LAUNCH_I2C(64);
+    default: return SHINEON_LAUNCH_I2C(128);
+  }
+#undef SHINEON_LAUNCH_I2C
 }
 
 extern "C" int shineon_conv2d_direct_fwd(const shineon_conv2d_params* p, shineon_stream_t stream) {

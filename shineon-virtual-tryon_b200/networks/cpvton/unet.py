@@ -182,13 +182,14 @@ class UnetSkipConnectionBlock(nn.Module):
             next_act, next_par = up_act, up_par
         else:
             next_act, next_par = act_name(sub._parts["down_act"])
-        if isinstance(a_in, tuple):
-            x0, x1 = a_in
-            a_in = (pk["down_i2c"].prepare(x0, x1) if pk["down_i2c"] is not None
-                    else ops.nchw_to_planes(x0, x1, prec=prec))
         bn = pk["down_bn"]
         sc, sh = bn if bn is not None else (None, None)
-        f32, _ = ops.conv2d(a_in, pk["down"], scale=sc, shift=sh, want_f32=True)
+        if isinstance(a_in, tuple) and pk["down_i2c"] is not None:
+            f32, _ = pk["down_i2c"].conv(a_in[0], a_in[1], scale=sc, shift=sh, want_f32=True)
+        else:
+            if isinstance(a_in, tuple):
+                a_in = ops.nchw_to_planes(a_in[0], a_in[1], prec=prec)
+            f32, _ = ops.conv2d(a_in, pk["down"], scale=sc, shift=sh, want_f32=True)
         a_mid = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, prec)
         # ---- child + up-path input
         if self.innermost:

@@ -69,10 +69,13 @@ class FeatureExtraction(nn.Module):
         prec = ops.resolve_precision(self.precision)
         layers = self._layers(prec)
         first = layers[0][3]
-        a = first.prepare(x.contiguous()) if first is not None else ops.nchw_to_planes(x.contiguous(), prec=prec)
-        for li, (pc, sc, sh, _) in enumerate(layers):
+        a = None if first is not None else ops.nchw_to_planes(x.contiguous(), prec=prec)
+        for li, (pc, sc, sh, i2c) in enumerate(layers):
             last = li == len(layers) - 1
-            f32, a = ops.conv2d(a, pc, scale=sc, shift=sh, pre_act="relu", want_f32=last, want_planes=not last)
+            if i2c is not None:  # tiny-Cin stem: im2col tile built in shared memory by the kernel's producer warps
+                f32, a = i2c.conv(x.contiguous(), scale=sc, shift=sh, pre_act="relu", want_f32=last, want_planes=not last)
+            else:
+                f32, a = ops.conv2d(a, pc, scale=sc, shift=sh, pre_act="relu", want_f32=last, want_planes=not last)
         return f32
 
     def forward(self, x):

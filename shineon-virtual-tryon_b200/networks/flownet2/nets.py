@@ -115,8 +115,7 @@ class _Net(nn.Module):
 
     def _stem(self, prec, name, x_nchw, out=None):
         i2c = self._pc(prec, name, stem=True)
-        a = i2c.prepare(x_nchw)
-        _, y = ops.conv2d(a, i2c.pc, post_act="leaky", act_param=LEAK, want_planes=out is None, out_planes=out)
+        _, y = i2c.conv(x_nchw, post_act="leaky", act_param=LEAK, want_planes=out is None, out_planes=out)
         return y
 
     def _flow(self, prec, name, x, segs=None, want_f32=False, want_planes=True):

@@ -398,8 +398,54 @@ class Im2colConv:
         self.pc = PackedConv(w2, bias, stride=1, pad=0, prec=prec)
 
     def prepare(self, x0, x1=None, act=None, act_param=0.0):
+        """Materialised im2col planes (reference / fallback path; `conv` below never writes them to HBM)."""
         return nchw_im2col_planes(x0, x1, self.kh, self.kw, self.stride, self.pad, act, act_param,
                                   prec=(self.pc.fmt, self.pc.w_lo is not None))
+
+    def conv(self, x0, x1=None, *, scale=None, shift=None, pre_act=None, post_act=None, act_param=0.0, want_f32=False,
+             want_planes=False, out_f32=None, out_planes=None):
+        """The whole layer in one kernel: producer warps build the im2col tile in shared memory from the NCHW input."""
+        x0 = _req(x0, name="x0")
+        N, C0, H, W = x0.shape
+        C1 = 0
+        if x1 is not None:
+            x1 = _req(x1, name="x1")
+            C1 = x1.shape[1]
+        pc = self.pc
+        Ho, Wo = (H + 2 * self.pad - self.kh) // self.stride + 1, (W + 2 * self.pad - self.kw) // self.stride + 1
+        dev = x0.device
+        prec = (pc.fmt, pc.w_lo is not None)
+        if want_f32 and out_f32 is None:
+            out_f32 = torch.empty(N, Ho, Wo, pc.Cout, dtype=torch.float32, device=dev)
+        if want_planes and out_planes is None:
+            out_planes = Planes(N, Ho, Wo, pc.Cout, prec=prec, device=dev)
+        p = Conv2dParams()
+        p.N, p.H, p.W, p.cin_pad = N, H, W, pc.cin_pad
+        p.w_hi, p.w_lo = _p(pc.w_hi), _p(pc.w_lo)
+        p.Cout, p.kh, p.kw, p.stride, p.pad_h, p.pad_w = pc.Cout, self.kh, self.kw, self.stride, self.pad, self.pad
+        p.Ho, p.Wo = Ho, Wo
+        p.bias, p.scale, p.shift = _p(pc.bias), _p(scale), _p(shift)
+        p.pre_act, p.post_act, p.act_param = ACT[pre_act], ACT[post_act], float(act_param)
+        p.acc_scale, p.plane_fmt = pc.acc_scale, pc.fmt
+        p.y_f32 = _p(out_f32)
+        p.y_hi = _p(out_planes.hi if out_planes is not None else None)
+        p.y_lo = _p(out_planes.lo if out_planes is not None else None)
+        if out_planes is not None:
+            p.out_cstride, p.out_coffset = out_planes.cstride, out_planes.coffset
+            assert out_f32 is None or out_f32.shape[-1] == out_planes.cstride
+        else:
+            p.out_cstride, p.out_coffset = out_f32.shape[-1], 0
+        prof = PROFILE
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        check(_lib.load().shineon_conv2d_im2col_fwd(C.byref(p), _p(x0), C0, _p(x1), C1, _stream()),
+              "shineon_conv2d_im2col_fwd")
+        if prof is not None:
+            e1.record()
+            prof.append((2.0 * N * Ho * Wo * pc.Cout * self.kh * self.kw * (C0 + C1), e0, e1,
+                         (N, H, W, C0 + C1, pc.cin_pad, pc.Cout, self.kh, self.stride)))
+        return out_f32, out_planes
 
 
 class TapStackedConv3x3:

@@ -101,7 +101,15 @@ def test_im2col_first_layer(ops, cfg):
     conv = ops.Im2colConv(w.cuda(), b.cuda(), s, p)
     a = conv.prepare(x[:, :c0].contiguous().cuda(), x[:, c0:].contiguous().cuda() if c0 < Cin else None)
     y, _ = ops.conv2d(a, conv.pc, want_f32=True)
-    assert_close(nchw(y), F.conv2d(x, w, b, stride=s, padding=p), atol=3e-5, rtol=1e-4, what="im2col conv")
+    want = F.conv2d(x, w, b, stride=s, padding=p)
+    assert_close(nchw(y), want, atol=3e-5, rtol=1e-4, what="im2col conv (materialised planes)")
+    # fused: im2col tile produced inside the kernel
+    x0 = x[:, :c0].contiguous().cuda()
+    x1 = x[:, c0:].contiguous().cuda() if c0 < Cin else None
+    y2, p2 = conv.conv(x0, x1, want_f32=True)
+    assert_close(nchw(y2), want, atol=3e-5, rtol=1e-4, what="im2col conv (in-kernel producer)")
+    _, p3 = conv.conv(x0, x1, post_act="leaky", act_param=0.1, want_planes=True)
+    assert_close(p3.float(), F.leaky_relu(want, 0.1), atol=3e-5, rtol=1e-4, what="im2col conv planes + leaky")
 
 
 def test_tap_stacked_conv3x3(ops):
