@@ -466,9 +466,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 // GMM's 22-channel input at 80 frames) four producer warps gather the NCHW f32 input, split it to 16-bit hi/lo
 // and write the 128x64 K-major tile straight into shared memory in the SWIZZLE_128B pattern tcgen05.mma expects
 // (16-byte chunk j of row r lives at chunk j ^ (r & 7)); B still arrives by TMA.
-// Warp roles: 0-3 A producers (thread r owns tile row r), 4 = B TMA + TMEM alloc, 5 = MMA issuer, 6-9 = epilogue.
+// Warp roles: 0-7 A producers (two threads per tile row, 32 k each), 8 = B TMA, 9 = TMEM alloc + MMA issuer,
+// 10-13 = epilogue.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kI2cThreads = 320;
+constexpr int kI2cProdWarps = 8;  // 2 threads per tile row: enough loads in flight to cover the L2/HBM latency
+constexpr int kI2cThreads = (kI2cProdWarps + 6) * 32;
 
 struct Im2colSrc {
   const float* x0;
@@ -499,11 +501,11 @@ __global__ void __launch_bounds__(kI2cThreads, 1)
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]),
                  bar_tfull = smem_u32(&bars[2 * kMaxStages]), bar_tempty = smem_u32(&bars[2 * kMaxStages + 2]);
 
-  if (warp == 4 && lane == 0) {
+  if (warp == kI2cProdWarps && lane == 0) {
     prefetch_tmap(&tmBh);
     if (SPLIT) prefetch_tmap(&tmBl);
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full + 8 * s, 5);  // 4 producer warps + the TMA thread's arrive.expect_tx
+      mbar_init(bar_full + 8 * s, kI2cProdWarps + 1);  // producer warps + the TMA thread's arrive.expect_tx
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(kI2cThreads, 1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) tmem_alloc<kTmemCols>(smem_u32(&tmem_slot));
+  if (warp == kI2cProdWarps + 1) tmem_alloc<kTmemCols>(smem_u32(&tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -522,9 +524,10 @@ __global__ void __launch_bounds__(kI2cThreads, 1)
   const int K = a.kh * a.kw * C;
   const int HW = src.H * src.W;
 
-  if (warp < 4) {
+  if (warp < kI2cProdWarps) {
     // ===================================================== A producers: gather + split + swizzled store
-    const int r = threadIdx.x;  // tile row 0..127
+    const int r = threadIdx.x & 127;    // tile row
+    const int half = threadIdx.x >> 7;  // which 32-wide half of the 64-wide K block this thread fills
     const int wi = r % a.bw, hi_ = (r / a.bw) % a.bh, ni = r / (a.bw * a.bh);
     uint32_t g = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
@@ -534,40 +537,37 @@ __global__ void __launch_bounds__(kI2cThreads, 1)
       const bool row_ok = ni < a.nb && n < a.N && oh < a.Ho && ow < a.Wo;
       const int iy0 = oh * a.stride - a.pad_h, ix0 = ow * a.stride - a.pad_w;
       const float* p0 = src.x0 + (long)n * src.C0 * HW;
-      const float* p1 = src.x1 ? src.x1 + (long)n * src.C1 * HW : nullptr;
+      const float* p1 = src.x1 ? src.x1 + (long)n * src.C1 * HW : src.x0;
       for (int kb = 0; kb < a.num_kb; ++kb, ++g) {
         const int s = g % S;
         const uint32_t ph = (g / S) & 1;
+        int k = kb * kBlockK + half * 32;
+        int tap = k / C, c = k - tap * C;
+        int fy = tap / a.kw, fx = tap - fy * a.kw;
+        // issue all 32 gathers of this thread before anything consumes them
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float val = 0.f;
+          const int iy = iy0 + fy, ix = ix0 + fx;
+          if (row_ok && k + e < K && iy >= 0 && iy < src.H && ix >= 0 && ix < src.W)
+            val = c < src.C0 ? __ldg(p0 + (long)c * HW + iy * src.W + ix) : __ldg(p1 + (long)(c - src.C0) * HW + iy * src.W + ix);
+          v[e] = val;
+          if (++c == C) {
+            c = 0;
+            if (++fx == a.kw) { fx = 0; ++fy; }
+          }
+        }
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         uint8_t* rowh = tiles_ptr + s * kStageBytes + r * 128;
         uint8_t* rowl = rowh + kABytes;
-        int k = kb * kBlockK;
-        int tap = k / C, c = k - tap * C;
-        int fy = tap / a.kw, fx = tap - fy * a.kw;
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j) {  // 8 chunks of 8 consecutive k
-          float v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float val = 0.f;
-            if (row_ok && k + e < K) {
-              const int iy = iy0 + fy, ix = ix0 + fx;
-              if (iy >= 0 && iy < src.H && ix >= 0 && ix < src.W)
-                val = c < src.C0 ? __ldg(p0 + (long)c * HW + iy * src.W + ix)
-                                 : __ldg(p1 + (long)(c - src.C0) * HW + iy * src.W + ix);
-            }
-            v[e] = val;
-            if (++c == C) {
-              c = 0;
-              if (++fx == a.kw) { fx = 0; ++fy; }
-            }
-          }
-          k += 8;
+        for (int jj = 0; jj < 4; ++jj) {
           __align__(16) plane_t hi[8];
           __align__(16) plane_t lo[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) split16(v[e], a.fmt, hi[e], lo[e]);
-          const int chunk = (j ^ (r & 7)) * 16;
+          for (int e = 0; e < 8; ++e) split16(v[jj * 8 + e], a.fmt, hi[e], lo[e]);
+          const int chunk = ((half * 4 + jj) ^ (r & 7)) * 16;
           *reinterpret_cast<uint4*>(rowh + chunk) = *reinterpret_cast<const uint4*>(hi);
           if (SPLIT) *reinterpret_cast<uint4*>(rowl + chunk) = *reinterpret_cast<const uint4*>(lo);
         }
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(kI2cThreads, 1)
         if (lane == 0) mbar_arrive(bar_full + 8 * s);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kI2cProdWarps) {
     // ===================================================== B operand by TMA
     if (lane == 0) {
       uint32_t g = 0;
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(kI2cThreads, 1)
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kI2cProdWarps + 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
       uint32_t g = 0;
@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(kI2cThreads, 1)
     const int r = q * 32 + lane;
     const int wi = r % a.bw, hi_ = (r / a.bw) % a.bh, ni = r / (a.bw * a.bh);
     constexpr int kChunk = BN < 32 ? BN : 32;
-    const int et = threadIdx.x - 192;  // 0..127
+    const int et = threadIdx.x - (kI2cProdWarps + 2) * 32;  // 0..127
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(kI2cThreads, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == kI2cProdWarps + 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------- CUDA-core cross-check

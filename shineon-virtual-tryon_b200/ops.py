@@ -391,6 +391,11 @@ def nchw_im2col_planes(x0, x1, kh, kw, stride, pad, act=None, act_param=0.0, pre
 class Im2colConv:
     """A Conv2d with tiny Cin as a 1x1 GEMM over nchw_im2col_planes (weights reordered tap-major to match)."""
 
+    # True: the kernel's producer warps build the im2col tile in shared memory (nothing materialised in HBM).
+    # Measured on B200 (profiles/r01_first_layers.md) the gather is latency-bound with only 8 producer warps per SM
+    # and loses to the standalone full-occupancy im2col pass + TMA GEMM, so the materialised path stays the default.
+    FUSED = False
+
     def __init__(self, weight, bias, stride, pad, prec=None):
         Cout, Cin, kh, kw = weight.shape
         self.kh, self.kw, self.stride, self.pad = kh, kw, stride, pad
@@ -403,8 +408,12 @@ class Im2colConv:
                                   prec=(self.pc.fmt, self.pc.w_lo is not None))
 
     def conv(self, x0, x1=None, *, scale=None, shift=None, pre_act=None, post_act=None, act_param=0.0, want_f32=False,
-             want_planes=False, out_f32=None, out_planes=None):
-        """The whole layer in one kernel: producer warps build the im2col tile in shared memory from the NCHW input."""
+             want_planes=False, out_f32=None, out_planes=None, fused=None):
+        """The whole layer: im2col + GEMM.  fused=None -> Im2colConv.FUSED."""
+        if not (self.FUSED if fused is None else fused):
+            a = self.prepare(x0, x1)
+            return conv2d(a, self.pc, scale=scale, shift=shift, pre_act=pre_act, post_act=post_act, act_param=act_param,
+                          want_f32=want_f32, want_planes=want_planes, out_f32=out_f32, out_planes=out_planes)
         x0 = _req(x0, name="x0")
         N, C0, H, W = x0.shape
         C1 = 0

@@ -106,9 +106,9 @@ def test_im2col_first_layer(ops, cfg):
     # fused: im2col tile produced inside the kernel
     x0 = x[:, :c0].contiguous().cuda()
     x1 = x[:, c0:].contiguous().cuda() if c0 < Cin else None
-    y2, p2 = conv.conv(x0, x1, want_f32=True)
+    y2, p2 = conv.conv(x0, x1, want_f32=True, fused=True)
     assert_close(nchw(y2), want, atol=3e-5, rtol=1e-4, what="im2col conv (in-kernel producer)")
-    _, p3 = conv.conv(x0, x1, post_act="leaky", act_param=0.1, want_planes=True)
+    _, p3 = conv.conv(x0, x1, post_act="leaky", act_param=0.1, want_planes=True, fused=True)
     assert_close(p3.float(), F.leaky_relu(want, 0.1), atol=3e-5, rtol=1e-4, what="im2col conv planes + leaky")
 
 
