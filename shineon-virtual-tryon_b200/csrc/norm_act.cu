@@ -276,36 +276,48 @@ __global__ void __launch_bounds__(256)
                           float act_param) {
   const int n = blockIdx.z, oy = blockIdx.y;
   const int ctot = c0pad + c1pad;
-  const int groups = ctot >> 3;
+  const int pairs = ctot >> 4;  // each thread produces two adjacent 8-channel groups (16 loads in flight)
   const int Wo = 2 * W;
   const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= Wo * groups) return;
-  const int ox = t / groups, g = t - ox * groups;
+  if (t >= Wo * pairs) return;
+  const int ox = t / pairs, gp = t - ox * pairs;
   int y0, y1, x0, x1;
   float ly0, ly1, lx0, lx1;
   up2_index(oy, H, y0, y1, ly0, ly1);
   up2_index(ox, W, x0, x1, lx0, lx1);
-  const int c = g * 8;
+  const int c = gp * 16;
   const plane_t *sh, *sl;
   int cp, cc;
   if (c < c0pad) { sh = s0h; sl = s0l; cp = c0pad; cc = c; } else { sh = s1h; sl = s1l; cp = c1pad; cc = c - c0pad; }
   const long rb = (long)n * H * W;
-  float v00[8], v01[8], v10[8], v11[8];
-  load8<FMT, ACT>(sh, sl, (rb + y0 * W + x0) * cp + cc, act, act_param, v00);
-  load8<FMT, ACT>(sh, sl, (rb + y0 * W + x1) * cp + cc, act, act_param, v01);
-  load8<FMT, ACT>(sh, sl, (rb + y1 * W + x0) * cp + cc, act, act_param, v10);
-  load8<FMT, ACT>(sh, sl, (rb + y1 * W + x1) * cp + cc, act, act_param, v11);
-  __align__(16) plane_t hi[8];
-  __align__(16) plane_t lo[8];
+  const long o00 = (rb + y0 * W + x0) * cp + cc, o01 = (rb + y0 * W + x1) * cp + cc;
+  const long o10 = (rb + y1 * W + x0) * cp + cc, o11 = (rb + y1 * W + x1) * cp + cc;
+  float a00[8], a01[8], a10[8], a11[8], b00[8], b01[8], b10[8], b11[8];
+  load8<FMT, ACT>(sh, sl, o00, act, act_param, a00);
+  load8<FMT, ACT>(sh, sl, o01, act, act_param, a01);
+  load8<FMT, ACT>(sh, sl, o10, act, act_param, a10);
+  load8<FMT, ACT>(sh, sl, o11, act, act_param, a11);
+  load8<FMT, ACT>(sh, sl, o00 + 8, act, act_param, b00);
+  load8<FMT, ACT>(sh, sl, o01 + 8, act, act_param, b01);
+  load8<FMT, ACT>(sh, sl, o10 + 8, act, act_param, b10);
+  load8<FMT, ACT>(sh, sl, o11 + 8, act, act_param, b11);
+  __align__(16) plane_t hi[16];
+  __align__(16) plane_t lo[16];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     // ATen: h0lambda*(w0lambda*p00 + w1lambda*p01) + h1lambda*(w0lambda*p10 + w1lambda*p11)
-    float v = ly0 * (lx0 * v00[j] + lx1 * v01[j]) + ly1 * (lx0 * v10[j] + lx1 * v11[j]);
-    split16(v, FMT, hi[j], lo[j]);
+    const float va = ly0 * (lx0 * a00[j] + lx1 * a01[j]) + ly1 * (lx0 * a10[j] + lx1 * a11[j]);
+    const float vb = ly0 * (lx0 * b00[j] + lx1 * b01[j]) + ly1 * (lx0 * b10[j] + lx1 * b11[j]);
+    split16(va, FMT, hi[j], lo[j]);
+    split16(vb, FMT, hi[8 + j], lo[8 + j]);
   }
   const long o = (((long)n * 2 * H + oy) * Wo + ox) * ctot + c;
-  *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
-  if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
+  reinterpret_cast<uint4*>(yh + o)[0] = reinterpret_cast<const uint4*>(hi)[0];
+  reinterpret_cast<uint4*>(yh + o)[1] = reinterpret_cast<const uint4*>(hi)[1];
+  if (yl) {
+    reinterpret_cast<uint4*>(yl + o)[0] = reinterpret_cast<const uint4*>(lo)[0];
+    reinterpret_cast<uint4*>(yl + o)[1] = reinterpret_cast<const uint4*>(lo)[1];
+  }
 }
 
 // ------------------------------------------------------------------------------ TOM compose
@@ -465,10 +477,10 @@ extern "C" int shineon_upsample2x_cat(const void* s0_hi, const void* s0_lo, int 
   SHINEON_REQUIRE((s1_hi == nullptr) == (c1pad == 0), "upsample2x_cat: s1/c1pad mismatch");
   SHINEON_REQUIRE((s0_lo == nullptr) == (y_lo == nullptr), "upsample2x_cat: lo planes must be all present or all absent");
   SHINEON_REQUIRE(s1_hi == nullptr || (s1_lo == nullptr) == (s0_lo == nullptr), "upsample2x_cat: s1 lo mismatch");
-  SHINEON_REQUIRE(c0pad > 0 && c0pad % 8 == 0 && c1pad % 8 == 0, "upsample2x_cat: channel pads must be multiples of 8");
+  SHINEON_REQUIRE(c0pad > 0 && c0pad % 16 == 0 && c1pad % 16 == 0, "upsample2x_cat: channel pads must be multiples of 16");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "upsample2x_cat: bad shape");
   SHINEON_REQUIRE(2 * H <= 65535, "upsample2x_cat: H too large");
-  dim3 grid(cdiv(2 * W * ((c0pad + c1pad) / 8), 256), 2 * H, N);
+  dim3 grid(cdiv(2 * W * ((c0pad + c1pad) / 16), 256), 2 * H, N);
 #define SHINEON_UP(F, A)                                                                                              \
   upsample2x_cat_kernel<F, A><<<grid, 256, 0, (cudaStream_t)stream>>>(                                               \
       (const plane_t*)s0_hi, (const plane_t*)s0_lo, c0pad, (const plane_t*)s1_hi, (const plane_t*)s1_lo, c1pad,      \
