@@ -71,41 +71,47 @@ __global__ void __launch_bounds__(256)
     nchw_im2col_planes_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                               plane_t* __restrict__ yh, plane_t* __restrict__ yl, int H, int W, int kh, int kw,
                               int stride, int pad, int Ho, int Wo, int kpad, int act, float act_param) {
-  // grid: x = (k-group, output column) tiles, y = output row, z = image; output column fastest so neighbouring
-  // threads read neighbouring input columns of the same NCHW channel plane
+  // grid: x = (pair of k-groups, output column) tiles, y = output row, z = image; output column fastest so
+  // neighbouring threads read neighbouring input columns of the same NCHW channel plane.  Each thread produces 16
+  // consecutive k (two 16-byte chunks per plane): 16 independent gathers in flight.
   const int n = blockIdx.z, oh = blockIdx.y;
-  const int groups = kpad >> 3;
+  const int pairs = kpad >> 4;
   const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= Wo * groups) return;
-  const int g = t / Wo, ow = t - g * Wo;
+  if (t >= Wo * pairs) return;
+  const int gp = t / Wo, ow = t - gp * Wo;
   const int C = C0 + C1;
   const int K = kh * kw * C;
   const int HW = H * W;
-  int k = g * 8;
+  int k = gp * 16;
   int tap = k / C, c = k - tap * C;
   int fy = tap / kw, fx = tap - fy * kw;
-  __align__(16) plane_t hi[8];
-  __align__(16) plane_t lo[8];
+  float v[16];
 #pragma unroll
-  for (int j = 0; j < 8; ++j, ++k) {
-    float v = 0.f;
+  for (int j = 0; j < 16; ++j, ++k) {
+    float val = 0.f;
     if (k < K) {
       const int iy = oh * stride + fy - pad, ix = ow * stride + fx - pad;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-        v = c < C0 ? __ldg(x0 + ((long)n * C0 + c) * HW + iy * W + ix)
-                   : __ldg(x1 + ((long)n * C1 + (c - C0)) * HW + iy * W + ix);
-        v = apply_act(v, act, act_param);
-      }
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+        val = c < C0 ? __ldg(x0 + ((long)n * C0 + c) * HW + iy * W + ix)
+                     : __ldg(x1 + ((long)n * C1 + (c - C0)) * HW + iy * W + ix);
     }
-    split16(v, FMT, hi[j], lo[j]);
+    v[j] = val;
     if (++c == C) {  // next tap
       c = 0;
       if (++fx == kw) { fx = 0; ++fy; }
     }
   }
-  const long o = (((long)n * Ho + oh) * Wo + ow) * kpad + g * 8;
-  *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
-  if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
+  __align__(16) plane_t hi[16];
+  __align__(16) plane_t lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) split16(apply_act(v[j], act, act_param), FMT, hi[j], lo[j]);
+  const long o = (((long)n * Ho + oh) * Wo + ow) * kpad + gp * 16;
+  reinterpret_cast<uint4*>(yh + o)[0] = reinterpret_cast<const uint4*>(hi)[0];
+  reinterpret_cast<uint4*>(yh + o)[1] = reinterpret_cast<const uint4*>(hi)[1];
+  if (yl) {
+    reinterpret_cast<uint4*>(yl + o)[0] = reinterpret_cast<const uint4*>(lo)[0];
+    reinterpret_cast<uint4*>(yl + o)[1] = reinterpret_cast<const uint4*>(lo)[1];
+  }
 }
 
 // ------------------------------------------------------------------------------ tap-stacked 3x3 conv: col2im
@@ -393,9 +399,9 @@ extern "C" int shineon_nchw_im2col_planes(const float* x0, int C0, const float* 
   SHINEON_REQUIRE((x1 == nullptr) == (C1 == 0), "nchw_im2col_planes: x1/C1 mismatch");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, "nchw_im2col_planes: bad shape");
   SHINEON_REQUIRE(Ho == (H + 2 * pad - kh) / stride + 1 && Wo == (W + 2 * pad - kw) / stride + 1, "nchw_im2col_planes: Ho/Wo");
-  SHINEON_REQUIRE(kpad % 8 == 0 && kpad >= kh * kw * (C0 + C1), "nchw_im2col_planes: kpad %d too small / not a multiple of 8", kpad);
+  SHINEON_REQUIRE(kpad % 16 == 0 && kpad >= kh * kw * (C0 + C1), "nchw_im2col_planes: kpad %d too small / not a multiple of 16", kpad);
   SHINEON_REQUIRE(Ho <= 65535, "nchw_im2col_planes: Ho too large");
-  dim3 grid(cdiv(Wo * (kpad / 8), 256), Ho, N);
+  dim3 grid(cdiv(Wo * (kpad / 16), 256), Ho, N);
   if (plane_fmt == SHINEON_FMT_FP16)
     nchw_im2col_planes_kernel<SHINEON_FMT_FP16><<<grid, 256, 0, (cudaStream_t)stream>>>(
         x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, kh, kw, stride, pad, Ho, Wo, kpad, act, act_param);
