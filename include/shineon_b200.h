@@ -307,6 +307,44 @@ int shineon_flow_confidence(const float* im1, const float* im2, const float* flo
 int shineon_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long n, float lr, float beta1,
                       float beta2, float eps, float weight_decay, int step, float grad_scale, shineon_stream_t stream);
 
+/* ------------------------------------------------------------------ */
+/* U6: backward of the conv layers (the reference gets these from cuDNN through autograd:               */
+/*     models/unet_mask_model.py:137-217 training_step -> loss.backward() in the Lightning loop)         */
+/* ------------------------------------------------------------------ */
+/* Data gradients reuse shineon_conv2d_igemm_fwd on re-packed weights (shineon_pack_conv_weight with     */
+/* transpose_io = 1: a stride-1 conv's dgrad is the flipped-tap conv with Cin/Cout swapped; a 4x4 s2 conv's */
+/* dgrad is the four-phase 2x2 transposed conv).  Weight gradient:                                        */
+/*   dW[co,(fy,fx),ci] = sum_{n,oh,ow} G[n,oh,ow,co] * X[n, oh*s+fy-p, ow*s+fx-p, ci]                      */
+/* G, X are NHWC 16-bit planes (hi [+ lo]); tcgen05 with MN-major operands straight from the NHWC tiles. */
+typedef struct shineon_conv2d_wgrad_params {
+  const void* g_hi; /* grad of the conv output, planes [N,Ho,Wo,g_cstride], channels >= Cout zero */
+  const void* g_lo; /* NULL in single-plane mode */
+  int g_cpad;       /* channels the G boxes may touch (multiple of 64, >= Cout) */
+  int g_cstride;    /* pixel pitch of G in elements (0 = g_cpad) */
+  const void* x_hi; /* the conv's input planes [N,H,W,x_cstride] */
+  const void* x_lo;
+  int N, H, W, cin_pad, x_cstride; /* x_cstride 0 = cin_pad */
+  int Cout, Cin;                   /* true channel counts of the parameter */
+  int kh, kw, stride, pad_h, pad_w;
+  int Ho, Wo;
+  int plane_fmt;            /* shineon_plane_fmt of G and X */
+  const int32_t* chan_map;  /* [cin_pad] packed channel -> weight input channel (-1 = padding), NULL = identity */
+  int mode;                 /* 0: grad_w is OIHW; 1: im2col'd first layer (kh*kw taps folded into cin_pad, pass the
+                               layer's true kh,kw,Cin and run with a 1x1 geometry); 2: ConvTranspose2d IOHW, flipped taps */
+  float* grad_w;            /* the parameter's gradient (f32, the parameter's own layout) */
+  float alpha, beta;        /* grad_w = beta*grad_w + alpha*dW  (alpha 0 = 1) */
+  void* workspace;          /* >= shineon_conv2d_wgrad_workspace_bytes() */
+  size_t workspace_bytes;
+  int splits;               /* K-split override, 0 = auto (fills ~2 waves of 148 SMs) */
+  int desc_variant;         /* 0 = default UMMA descriptor strides; 1 = swapped LBO/SBO (bring-up diagnostics) */
+} shineon_conv2d_wgrad_params;
+size_t shineon_conv2d_wgrad_workspace_bytes(const shineon_conv2d_wgrad_params* p);
+int shineon_conv2d_wgrad(const shineon_conv2d_wgrad_params* p, shineon_stream_t stream);
+/* grad[c] = beta*grad[c] + alpha * sum over `pixels` rows of x[pixel*cstride + c]  (bias gradients; f64 accumulation).
+ * workspace: C doubles. */
+int shineon_channel_sum(const float* x, float* grad, void* workspace, long pixels, int C, int cstride, float alpha,
+                        float beta, shineon_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

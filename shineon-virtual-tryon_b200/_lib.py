@@ -35,6 +35,17 @@ class Conv2dParams(C.Structure):
     ]
 
 
+class Conv2dWgradParams(C.Structure):
+    _fields_ = [
+        ("g_hi", c_p), ("g_lo", c_p), ("g_cpad", c_i), ("g_cstride", c_i),
+        ("x_hi", c_p), ("x_lo", c_p), ("N", c_i), ("H", c_i), ("W", c_i), ("cin_pad", c_i), ("x_cstride", c_i),
+        ("Cout", c_i), ("Cin", c_i), ("kh", c_i), ("kw", c_i), ("stride", c_i), ("pad_h", c_i), ("pad_w", c_i),
+        ("Ho", c_i), ("Wo", c_i), ("plane_fmt", c_i), ("chan_map", c_p), ("mode", c_i), ("grad_w", c_p),
+        ("alpha", c_f), ("beta", c_f), ("workspace", c_p), ("workspace_bytes", C.c_size_t), ("splits", c_i),
+        ("desc_variant", c_i),
+    ]
+
+
 # name -> argtypes (every function returns int status unless listed in _RESTYPES)
 SIGNATURES = {
     "shineon_version": [],
@@ -73,9 +84,13 @@ SIGNATURES = {
     "shineon_flownet_fusion_concat": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "shineon_flow_confidence": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
     "shineon_adam_step": [c_p, c_p, c_p, c_p, C.c_long, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_p],
+    "shineon_conv2d_wgrad_workspace_bytes": [C.POINTER(Conv2dWgradParams)],
+    "shineon_conv2d_wgrad": [C.POINTER(Conv2dWgradParams), c_p],
+    "shineon_channel_sum": [c_p, c_p, c_p, C.c_long, c_i, c_i, c_f, c_f, c_p],
     "shineon_tom_compose": [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
 }
-_RESTYPES = {"shineon_last_error": C.c_char_p, "shineon_launch_count": C.c_uint64}
+_RESTYPES = {"shineon_last_error": C.c_char_p, "shineon_launch_count": C.c_uint64,
+             "shineon_conv2d_wgrad_workspace_bytes": C.c_size_t}
 
 _lib = None
 

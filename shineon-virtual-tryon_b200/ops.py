@@ -617,3 +617,61 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999
     check(_lib.load().shineon_adam_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), n, float(lr), float(betas[0]),
                                         float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale),
                                         _stream()), "shineon_adam_step")
+
+
+# ----------------------------------------------------------------------------- conv backward (row U6)
+_WGRAD_WS = {}
+
+
+def _workspace(nbytes, device, key="ws"):
+    """Grow-only scratch buffer per (device, key): the C ABI never allocates, the caller owns the workspace."""
+    k = (str(device), key)
+    buf = _WGRAD_WS.get(k)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _WGRAD_WS[k] = buf
+    return buf
+
+
+def conv2d_wgrad(g, x, grad_w, *, Cout, Cin, kh, kw, stride, pad, mode=0, chan_map=None, alpha=1.0, beta=0.0,
+                 out_hw=None, splits=0, desc_variant=0):
+    """Weight gradient of a conv layer: g = Planes of dL/d(conv output) [N,Ho,Wo,>=Cout], x = the conv's input Planes.
+    Writes beta*grad_w + alpha*dW into grad_w (f32, the parameter's own layout: OIHW for mode 0/1, IOHW for mode 2)."""
+    from ._lib import Conv2dWgradParams
+
+    assert g.fmt == x.fmt and (g.lo is None) == (x.lo is None), "precision of gradient and activation planes must agree"
+    grad_w = _req(grad_w, name="grad_w")
+    pad_h, pad_w = pad if isinstance(pad, tuple) else (pad, pad)
+    p = Conv2dWgradParams()
+    p.g_hi, p.g_lo, p.g_cpad, p.g_cstride = g._ptr(g.hi), g._ptr(g.lo), g.cpad, g.cstride
+    p.x_hi, p.x_lo = x._ptr(x.hi), x._ptr(x.lo)
+    p.N, p.H, p.W, p.cin_pad, p.x_cstride = x.N, x.H, x.W, x.cpad, x.cstride
+    p.Cout, p.Cin, p.kh, p.kw, p.stride, p.pad_h, p.pad_w = Cout, Cin, kh, kw, stride, pad_h, pad_w
+    p.Ho, p.Wo = out_hw if out_hw is not None else (g.H, g.W)
+    assert g.N == x.N and (g.H, g.W) == (p.Ho, p.Wo)
+    p.plane_fmt = g.fmt
+    cm = None
+    if chan_map is not None:
+        cm = chan_map if isinstance(chan_map, torch.Tensor) else torch.as_tensor(chan_map, dtype=torch.int32, device=grad_w.device)
+        assert cm.numel() == x.cpad and cm.dtype == torch.int32
+    p.chan_map = _p(cm)
+    p.mode, p.grad_w, p.alpha, p.beta = mode, _p(grad_w), float(alpha), float(beta)
+    p.splits, p.desc_variant = splits, desc_variant
+    lib = _lib.load()
+    need = lib.shineon_conv2d_wgrad_workspace_bytes(C.byref(p))
+    ws = _workspace(need, grad_w.device)
+    p.workspace, p.workspace_bytes = _p(ws), ws.numel()
+    check(lib.shineon_conv2d_wgrad(C.byref(p), _stream()), "shineon_conv2d_wgrad")
+    return grad_w
+
+
+def channel_sum(x, grad, alpha=1.0, beta=0.0):
+    """grad[c] = beta*grad[c] + alpha * sum over all pixels of the NHWC f32 tensor x[..., c]  (bias gradient)."""
+    x, grad = _req(x, name="x"), _req(grad, name="grad")
+    Cc = grad.numel()
+    cs = x.shape[-1]
+    assert cs >= Cc
+    ws = _workspace(8 * Cc, x.device, key="chsum")
+    check(_lib.load().shineon_channel_sum(_p(x), _p(grad), _p(ws), x.numel() // cs, Cc, cs, float(alpha), float(beta),
+                                          _stream()), "shineon_channel_sum")
+    return grad
