@@ -345,6 +345,44 @@ int shineon_conv2d_wgrad(const shineon_conv2d_wgrad_params* p, shineon_stream_t 
 int shineon_channel_sum(const float* x, float* grad, void* workspace, long pixels, int C, int cstride, float alpha,
                         float beta, shineon_stream_t stream);
 
+/* d(act o InstanceNorm2d): x = the conv output the forward normalised (f32 NHWC [N,H,W,C]), stats_fwd = the
+ * forward's statistics workspace (shineon_instnorm_act), g1 (+ optional g2, summed) = dL/d(activated output).
+ * Writes dL/dx as f32 NHWC and/or 16-bit planes [N,H,W,cpad].  do_norm = 0: plain g * act'(x).
+ * stats_ws: 2*N*C doubles. */
+int shineon_instnorm_act_bwd(const float* x, const double* stats_fwd, const float* g1, const float* g2, float* gx_f32,
+                             void* gx_hi, void* gx_lo, double* stats_ws, int N, int H, int W, int C, int cpad, float eps,
+                             int do_norm, int act, float act_param, int plane_fmt, shineon_stream_t stream);
+/* gz[i] = (g1[i] + g2[i]) * act'(z[i])   (g2 may be NULL) */
+int shineon_act_bwd(const float* z, const float* g1, const float* g2, float* gz, long n, int act, float act_param,
+                    shineon_stream_t stream);
+/* Adjoint of shineon_upsample2x_cat: g_up f32 NHWC [N,2H,2W,g_cstride] (channels [0,C0) = first source, [C0,C0+C1) =
+ * second) -> g0 [N,H,W,C0], g1 [N,H,W,C1] (NULL when C1 == 0). */
+int shineon_upsample2x_cat_bwd(const float* g_up, int g_cstride, float* g0, int C0, float* g1, int C1, int N, int H, int W,
+                               shineon_stream_t stream);
+/* SAGAN attention backward (attention/sagan.py:29-53): qkv f32 [N,HW,2Cq+C] (the forward's projections), g_out =
+ * dL/d(gamma*o + x) f32 [N,HW,C] -> g_qkv f32 [N,HW,2Cq+C], g_gamma[0] = beta_gamma*g_gamma[0] + dL/dgamma.
+ * The residual branch (dL/dx += g_out) and the 1x1 projections' dgrad/wgrad are the caller's. */
+size_t shineon_sagan_attention_bwd_workspace_bytes(int N, int HW);
+int shineon_sagan_attention_bwd(const float* qkv, const float* gamma, const float* g_out, float* g_qkv, float* g_gamma,
+                                void* workspace, size_t workspace_bytes, int N, int HW, int C, int Cq, float beta_gamma,
+                                shineon_stream_t stream);
+/* Backward of shineon_tom_compose for one frame: gradients wrt the NCHW outputs (any may be NULL = zero) ->
+ * g_unet_out f32 NHWC (only this frame's channels are written) and, with flow-warp, g_warped_prev [B,3,H,W]. */
+int shineon_tom_compose_bwd(const float* unet_out, int Cout, const float* cloth, const float* warped_prev,
+                            const float* g_rendereds, const float* g_masks, const float* g_tryons,
+                            const float* g_flow_masks, float* g_unet_out, float* g_warped_prev, int B, int H, int W,
+                            int n_frames, int frame, int flow_warp, shineon_stream_t stream);
+/* loss[0] = beta_loss*loss[0] + loss_weight*mean|a-b|; grad_a (may be NULL) (+)= loss_weight*sign(a-b)/n
+ * (F.l1_loss, unet_mask_model.py:174-188; loss.py:106-122).  workspace: one double. */
+int shineon_l1_loss(const float* a, const float* b, float* grad_a, float* loss, void* workspace, long n, float loss_weight,
+                    float beta_loss, int accumulate_grad, shineon_stream_t stream);
+/* VGG19 glue (models/networks/vgg.py:6-38): 2x2/2 max-pool on f32 NHWC -> f32 and/or planes; backward routes to the
+ * first maximum of the window in scan order (ATen). */
+int shineon_maxpool2x2_fwd(const float* x, float* y_f32, void* y_hi, void* y_lo, int N, int H, int W, int C, int cpad,
+                           int plane_fmt, shineon_stream_t stream);
+int shineon_maxpool2x2_bwd(const float* x, const float* g_y, int g_cstride, float* g_x, int N, int H, int W, int C,
+                           shineon_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,10 +87,20 @@ SIGNATURES = {
     "shineon_conv2d_wgrad_workspace_bytes": [C.POINTER(Conv2dWgradParams)],
     "shineon_conv2d_wgrad": [C.POINTER(Conv2dWgradParams), c_p],
     "shineon_channel_sum": [c_p, c_p, c_p, C.c_long, c_i, c_i, c_f, c_f, c_p],
+    "shineon_instnorm_act_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_f, c_i, c_p],
+    "shineon_act_bwd": [c_p, c_p, c_p, c_p, C.c_long, c_i, c_f, c_p],
+    "shineon_upsample2x_cat_bwd": [c_p, c_i, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_p],
+    "shineon_sagan_attention_bwd_workspace_bytes": [c_i, c_i],
+    "shineon_sagan_attention_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, C.c_size_t, c_i, c_i, c_i, c_i, c_f, c_p],
+    "shineon_tom_compose_bwd": [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_l1_loss": [c_p, c_p, c_p, c_p, c_p, C.c_long, c_f, c_f, c_i, c_p],
+    "shineon_maxpool2x2_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_maxpool2x2_bwd": [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_p],
     "shineon_tom_compose": [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
 }
 _RESTYPES = {"shineon_last_error": C.c_char_p, "shineon_launch_count": C.c_uint64,
-             "shineon_conv2d_wgrad_workspace_bytes": C.c_size_t}
+             "shineon_conv2d_wgrad_workspace_bytes": C.c_size_t,
+             "shineon_sagan_attention_bwd_workspace_bytes": C.c_size_t}
 
 _lib = None
 

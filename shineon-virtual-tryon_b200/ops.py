@@ -675,3 +675,106 @@ def channel_sum(x, grad, alpha=1.0, beta=0.0):
     check(_lib.load().shineon_channel_sum(_p(x), _p(grad), _p(ws), x.numel() // cs, Cc, cs, float(alpha), float(beta),
                                           _stream()), "shineon_channel_sum")
     return grad
+
+
+def instnorm_stats_ws(x):
+    """Statistics workspace of instnorm_act for an NHWC tensor (kept by the training path for the backward)."""
+    N, _, _, Cc = x.shape
+    return torch.empty(N * Cc * 2, dtype=torch.float64, device=x.device)
+
+
+def instnorm_act_bwd(x, stats_fwd, g1, g2=None, *, do_norm=True, act=None, act_param=0.0, eps=1e-5, want_f32=False,
+                     want_planes=True, prec=None):
+    """Backward of instnorm_act.  x: the f32 NHWC conv output the forward normalised; g1 (+g2): dL/d(activated output).
+    Returns (gx_f32|None, gx Planes|None)."""
+    x, g1 = _req(x, name="x"), _req(g1, name="g1")
+    if g2 is not None:
+        g2 = _req(g2, name="g2")
+        assert g2.shape == x.shape
+    assert g1.shape == x.shape
+    N, H, W, Cc = x.shape
+    gx = torch.empty_like(x) if want_f32 else None
+    gp = Planes(N, H, W, Cc, prec=prec, device=x.device) if want_planes else None
+    ws = torch.empty(N * Cc * 2, dtype=torch.float64, device=x.device) if do_norm else None
+    check(_lib.load().shineon_instnorm_act_bwd(_p(x), _p(stats_fwd), _p(g1), _p(g2), _p(gx), _p(gp.hi if gp else None),
+                                               _p(gp.lo if gp else None), _p(ws), N, H, W, Cc, gp.cpad if gp else Cc,
+                                               float(eps), int(bool(do_norm)), ACT[act], float(act_param),
+                                               gp.fmt if gp else 0, _stream()), "shineon_instnorm_act_bwd")
+    return gx, gp
+
+
+def act_bwd(z, g1, g2=None, act=None, act_param=0.0):
+    z, g1 = _req(z, name="z"), _req(g1, name="g1")
+    if g2 is not None:
+        g2 = _req(g2, name="g2")
+    gz = torch.empty_like(z)
+    check(_lib.load().shineon_act_bwd(_p(z), _p(g1), _p(g2), _p(gz), z.numel(), ACT[act], float(act_param), _stream()),
+          "shineon_act_bwd")
+    return gz
+
+
+def upsample2x_cat_bwd(g_up, C0, C1=0):
+    """g_up: f32 NHWC [N,2H,2W,>=C0+C1] -> (g0 [N,H,W,C0], g1 [N,H,W,C1] | None)."""
+    g_up = _req(g_up, name="g_up")
+    N, H2, W2, cs = g_up.shape
+    H, W = H2 // 2, W2 // 2
+    g0 = torch.empty(N, H, W, C0, dtype=torch.float32, device=g_up.device)
+    g1 = torch.empty(N, H, W, C1, dtype=torch.float32, device=g_up.device) if C1 else None
+    check(_lib.load().shineon_upsample2x_cat_bwd(_p(g_up), cs, _p(g0), C0, _p(g1), C1, N, H, W, _stream()),
+          "shineon_upsample2x_cat_bwd")
+    return g0, g1
+
+
+def sagan_attention_bwd(qkv, gamma, g_out, Cq, g_gamma, beta_gamma=1.0):
+    """-> g_qkv f32 [N,H,W,2Cq+C]; accumulates dL/dgamma into g_gamma (f32 [1])."""
+    qkv, gamma, g_out, g_gamma = _req(qkv), _req(gamma), _req(g_out), _req(g_gamma)
+    N, H, W, Cc = g_out.shape
+    assert qkv.shape[-1] == 2 * Cq + Cc
+    g_qkv = torch.empty_like(qkv)
+    lib = _lib.load()
+    need = lib.shineon_sagan_attention_bwd_workspace_bytes(N, H * W)
+    ws = _workspace(need, qkv.device, key="attn_bwd")
+    check(lib.shineon_sagan_attention_bwd(_p(qkv), _p(gamma), _p(g_out), _p(g_qkv), _p(g_gamma), _p(ws), ws.numel(), N,
+                                          H * W, Cc, Cq, float(beta_gamma), _stream()), "shineon_sagan_attention_bwd")
+    return g_qkv
+
+
+def tom_compose_bwd(unet_out, cloth, n_frames, flow_warp, g_unet_out, frame=0, warped_prev=None, g_rendereds=None,
+                    g_masks=None, g_tryons=None, g_flow_masks=None, want_g_warped=False):
+    unet_out, cloth, g_unet_out = _req(unet_out), _req(cloth), _req(g_unet_out)
+    B, H, W, Cout = unet_out.shape
+    g_warped = torch.empty(B, 3, H, W, dtype=torch.float32, device=unet_out.device) if want_g_warped else None
+    check(_lib.load().shineon_tom_compose_bwd(_p(unet_out), Cout, _p(cloth), _p(warped_prev), _p(g_rendereds), _p(g_masks),
+                                              _p(g_tryons), _p(g_flow_masks), _p(g_unet_out), _p(g_warped), B, H, W,
+                                              n_frames, frame, int(bool(flow_warp)), _stream()), "shineon_tom_compose_bwd")
+    return g_warped
+
+
+def l1_loss(a, b, loss, grad_a=None, weight=1.0, beta_loss=1.0, accumulate_grad=False):
+    """loss[0] = beta_loss*loss[0] + weight*mean|a-b|; grad_a (+)= weight*sign(a-b)/numel."""
+    a, b, loss = _req(a, name="a"), _req(b, name="b"), _req(loss, name="loss")
+    assert a.shape == b.shape
+    ws = _workspace(8, a.device, key="l1")
+    check(_lib.load().shineon_l1_loss(_p(a), _p(b), _p(grad_a), _p(loss), _p(ws), a.numel(), float(weight),
+                                      float(beta_loss), int(bool(accumulate_grad)), _stream()), "shineon_l1_loss")
+    return loss
+
+
+def maxpool2x2(x, want_f32=True, want_planes=True, prec=None):
+    x = _req(x, name="x")
+    N, H, W, Cc = x.shape
+    y = torch.empty(N, H // 2, W // 2, Cc, dtype=torch.float32, device=x.device) if want_f32 else None
+    yp = Planes(N, H // 2, W // 2, Cc, prec=prec, device=x.device) if want_planes else None
+    check(_lib.load().shineon_maxpool2x2_fwd(_p(x), _p(y), _p(yp.hi if yp else None), _p(yp.lo if yp else None), N, H, W,
+                                             Cc, yp.cpad if yp else Cc, yp.fmt if yp else 0, _stream()),
+          "shineon_maxpool2x2_fwd")
+    return y, yp
+
+
+def maxpool2x2_bwd(x, g_y):
+    x, g_y = _req(x, name="x"), _req(g_y, name="g_y")
+    N, H, W, Cc = x.shape
+    g_x = torch.empty_like(x)
+    check(_lib.load().shineon_maxpool2x2_bwd(_p(x), _p(g_y), g_y.shape[-1], _p(g_x), N, H, W, Cc, _stream()),
+          "shineon_maxpool2x2_bwd")
+    return g_x

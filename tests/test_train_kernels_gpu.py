@@ -102,3 +102,129 @@ def test_conv2d_wgrad_im2col_first_layer(ops):
     gw = torch.zeros(Cout, Cin, 4, 4, device="cuda")
     ops.conv2d_wgrad(gp, a, gw, Cout=Cout, Cin=Cin, kh=4, kw=4, stride=2, pad=1, mode=1)
     assert rel_err(gw, want) < GRAD_TOL["bf16x3"]
+
+
+# ------------------------------------------------------------------------------------------ pointwise backward
+def _act_ref(name):
+    return {None: lambda t: t, "relu": F.relu, "gelu": F.gelu, "swish": lambda t: t * torch.sigmoid(t),
+            "sine": lambda t: torch.sin(30 * t), "leaky": lambda t: F.leaky_relu(t, 0.2)}[name]
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 8, 64), (3, 4, 3, 512), (1, 32, 24, 4), (2, 7, 5, 3)])
+@pytest.mark.parametrize("act", [None, "gelu", "relu", "swish", "leaky"])
+@pytest.mark.parametrize("do_norm", [True, False])
+def test_instnorm_act_bwd(ops, shape, act, do_norm):
+    N, H, W, C = shape
+    gen = torch.Generator().manual_seed(C + H)
+    x = (torch.randn(N, H, W, C, generator=gen) * 1.5 + 0.3).requires_grad_(True)
+    g1 = torch.randn(N, H, W, C, generator=gen)
+    g2 = torch.randn(N, H, W, C, generator=gen)
+    xn = nchw(x)
+    y = _act_ref(act)(F.instance_norm(xn, eps=1e-5) if do_norm else xn)
+    # NB the upstream gradient is made contiguous in NCHW: torch's CPU instance_norm backward mishandles a
+    # permuted (channels-last strided) grad_output when N == 1 (seen with torch 2.11)
+    (y * nchw(g1 + g2)).sum().backward()
+    xc = x.detach().cuda()
+    ws = ops.instnorm_stats_ws(xc)
+    ops.instnorm_act(xc, do_norm=do_norm, act=act, act_param=0.2, want_f32=True, want_planes=False, ws=ws)
+    gx, gp = ops.instnorm_act_bwd(xc, ws if do_norm else None, g1.cuda(), g2.cuda(), do_norm=do_norm, act=act, act_param=0.2,
+                                  want_f32=True, want_planes=True, prec="bf16x3")
+    assert rel_err(gx, x.grad) < 2e-4
+    assert rel_err(nhwc(gp.float()), x.grad) < 3e-4
+
+
+def test_act_bwd(ops):
+    gen = torch.Generator().manual_seed(3)
+    z = torch.randn(3, 5, 7, 11, generator=gen).requires_grad_(True)
+    g = torch.randn(3, 5, 7, 11, generator=gen)
+    (F.gelu(z) * g).sum().backward()
+    assert rel_err(ops.act_bwd(z.detach().cuda(), g.cuda(), None, act="gelu"), z.grad) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 3, 64, 64), (1, 16, 12, 10, 0), (2, 1, 1, 8, 3), (1, 2, 5, 7, 5)])
+def test_upsample2x_cat_bwd(ops, shape):
+    N, H, W, C0, C1 = shape
+    gen = torch.Generator().manual_seed(H * W)
+    s = torch.randn(N, C0 + C1, H, W, generator=gen).requires_grad_(True)
+    g = torch.randn(N, 2 * H, 2 * W, C0 + C1, generator=gen)
+    (F.interpolate(s, scale_factor=2, mode="bilinear", align_corners=False) * nchw(g)).sum().backward()
+    g0, g1 = ops.upsample2x_cat_bwd(g.cuda(), C0, C1)
+    want = nhwc(s.grad)
+    assert rel_err(g0, want[..., :C0]) < 1e-5
+    if C1:
+        assert rel_err(g1, want[..., C0:]) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 3, 64), (1, 16, 12, 512), (3, 8, 6, 128)])
+def test_sagan_attention_bwd(ops, shape):
+    N, H, W, C = shape
+    Cq, HW = C // 8, H * W
+    gen = torch.Generator().manual_seed(C)
+    qkv = (torch.randn(N, H, W, 2 * Cq + C, generator=gen) * 0.5).requires_grad_(True)
+    x = torch.randn(N, H, W, C, generator=gen)
+    gamma = torch.tensor([0.8], requires_grad=True)
+    g = torch.randn(N, H, W, C, generator=gen)
+    t = qkv.view(N, HW, -1)
+    q, k, v = t[..., :Cq], t[..., Cq:2 * Cq], t[..., 2 * Cq:]
+    A = torch.softmax(q @ k.transpose(1, 2), -1)          # [N, i, j]
+    out = gamma * (A @ v) + x.view(N, HW, C)
+    (out * g.view(N, HW, C)).sum().backward()
+    gg = torch.zeros(1, device="cuda")
+    gq = ops.sagan_attention_bwd(qkv.detach().cuda(), gamma.detach().cuda(), g.cuda(), Cq, gg, beta_gamma=0.0)
+    assert rel_err(gq, qkv.grad) < 1e-4
+    assert rel_err(gg, gamma.grad) < 1e-4
+
+
+@pytest.mark.parametrize("nf,flow_warp", [(1, False), (2, False), (2, True)])
+def test_tom_compose_bwd(ops, nf, flow_warp):
+    B, H, W = 2, 8, 6
+    Cout = (5 if flow_warp else 4) * nf
+    gen = torch.Generator().manual_seed(nf)
+    u = torch.randn(B, H, W, Cout, generator=gen).requires_grad_(True)
+    cloth = torch.rand(B, 3 * nf, H, W, generator=gen) * 2 - 1
+    f = nf - 1
+    wp = (torch.rand(B, 3, H, W, generator=gen) * 2 - 1).requires_grad_(True) if (flow_warp and f > 0) else None
+    g_t = torch.randn(B, 3 * nf, H, W, generator=gen)
+    g_m = torch.randn(B, nf, H, W, generator=gen)
+    g_r = torch.randn(B, 3 * nf, H, W, generator=gen)
+    g_f = torch.randn(B, nf, H, W, generator=gen) if flow_warp else None
+    un = nchw(u)
+    r = torch.tanh(un[:, 3 * f:3 * f + 3])
+    m = torch.sigmoid(un[:, 3 * nf + f:3 * nf + f + 1])
+    loss = (r * g_r[:, 3 * f:3 * f + 3]).sum() + (m * g_m[:, f:f + 1]).sum()
+    rr = r
+    if flow_warp:
+        fm = torch.sigmoid(un[:, 4 * nf + f:4 * nf + f + 1])
+        loss = loss + (fm * g_f[:, f:f + 1]).sum()
+        if wp is not None:
+            rr = (1 - fm) * wp + fm * r
+    t = (1 - m) * rr + m * cloth[:, 3 * f:3 * f + 3]
+    loss = loss + (t * g_t[:, 3 * f:3 * f + 3]).sum()
+    loss.backward()
+    gu = torch.zeros(B, H, W, Cout, device="cuda")
+    gw = ops.tom_compose_bwd(u.detach().cuda(), cloth.cuda(), nf, flow_warp, gu, frame=f,
+                             warped_prev=wp.detach().cuda() if wp is not None else None, g_rendereds=g_r.cuda(),
+                             g_masks=g_m.cuda(), g_tryons=g_t.cuda(), g_flow_masks=g_f.cuda() if flow_warp else None,
+                             want_g_warped=wp is not None)
+    assert rel_err(gu, u.grad) < 1e-5
+    if wp is not None:
+        assert rel_err(gw, wp.grad) < 1e-5
+
+
+def test_l1_loss_and_maxpool(ops):
+    gen = torch.Generator().manual_seed(8)
+    a = torch.randn(2, 3, 16, 12, generator=gen).requires_grad_(True)
+    b = torch.randn(2, 3, 16, 12, generator=gen)
+    (0.25 * F.l1_loss(a, b)).backward()
+    loss = torch.full((1,), 2.0, device="cuda")
+    ga = torch.zeros_like(a, device="cuda")
+    ops.l1_loss(a.detach().cuda(), b.cuda(), loss, ga, weight=0.25, beta_loss=1.0)
+    assert abs(loss.item() - 2.0 - 0.25 * F.l1_loss(a, b).item()) < 1e-5
+    assert rel_err(ga, a.grad) < 1e-6
+    x = torch.randn(2, 8, 6, 70, generator=gen).relu().requires_grad_(True)  # ties at zero, like post-ReLU VGG maps
+    g = torch.randn(2, 4, 3, 70, generator=gen)
+    y = F.max_pool2d(nchw(x), 2, 2)
+    (y * nchw(g)).sum().backward()
+    yf, yp = ops.maxpool2x2(x.detach().cuda(), prec="bf16x3")
+    assert rel_err(yf, nhwc(y)) < 1e-6 and rel_err(nhwc(yp.float()), nhwc(y)) < 1e-4
+    assert rel_err(ops.maxpool2x2_bwd(x.detach().cuda(), g.cuda()), x.grad) < 1e-6
