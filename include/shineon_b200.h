@@ -337,13 +337,15 @@ typedef struct shineon_conv2d_wgrad_params {
   size_t workspace_bytes;
   int splits;               /* K-split override, 0 = auto (fills ~2 waves of 148 SMs) */
   int desc_variant;         /* 0 = default UMMA descriptor strides; 1 = swapped LBO/SBO (bring-up diagnostics) */
+  int g_coffset;            /* first channel of G this parameter's outputs occupy (fused q|k|v projections); any value,
+                               g_cpad then counts channels from g_coffset (rounded up to 64) */
 } shineon_conv2d_wgrad_params;
 size_t shineon_conv2d_wgrad_workspace_bytes(const shineon_conv2d_wgrad_params* p);
 int shineon_conv2d_wgrad(const shineon_conv2d_wgrad_params* p, shineon_stream_t stream);
 /* grad[c] = beta*grad[c] + alpha * sum over `pixels` rows of x[pixel*cstride + c]  (bias gradients; f64 accumulation).
  * workspace: C doubles. */
 int shineon_channel_sum(const float* x, float* grad, void* workspace, long pixels, int C, int cstride, float alpha,
-                        float beta, shineon_stream_t stream);
+                        float beta, shineon_stream_t stream); /* x may point at a channel offset inside the row */
 
 /* d(act o InstanceNorm2d): x = the conv output the forward normalised (f32 NHWC [N,H,W,C]), stats_fwd = the
  * forward's statistics workspace (shineon_instnorm_act), g1 (+ optional g2, summed) = dL/d(activated output).
@@ -366,7 +368,8 @@ size_t shineon_sagan_attention_bwd_workspace_bytes(int N, int HW);
 int shineon_sagan_attention_bwd(const float* qkv, const float* gamma, const float* g_out, float* g_qkv, float* g_gamma,
                                 void* workspace, size_t workspace_bytes, int N, int HW, int C, int Cq, float beta_gamma,
                                 shineon_stream_t stream);
-/* Backward of shineon_tom_compose for one frame: gradients wrt the NCHW outputs (any may be NULL = zero) ->
+/* Backward of shineon_tom_compose for one frame: gradients wrt THIS frame's outputs as per-frame NCHW tensors
+ * (g_rendereds / g_tryons [B,3,H,W], g_masks / g_flow_masks [B,1,H,W]; any may be NULL = zero) ->
  * g_unet_out f32 NHWC (only this frame's channels are written) and, with flow-warp, g_warped_prev [B,3,H,W]. */
 int shineon_tom_compose_bwd(const float* unet_out, int Cout, const float* cloth, const float* warped_prev,
                             const float* g_rendereds, const float* g_masks, const float* g_tryons,
@@ -380,6 +383,9 @@ int shineon_l1_loss(const float* a, const float* b, float* grad_a, float* loss, 
  * first maximum of the window in scan order (ATen). */
 int shineon_maxpool2x2_fwd(const float* x, float* y_f32, void* y_hi, void* y_lo, int N, int H, int W, int C, int cpad,
                            int plane_fmt, shineon_stream_t stream);
+/* y [N,C,H,W] (+)= x [N,H,W,x_cstride][..., :C]  (image gradients produced by NHWC kernels back to the reference layout) */
+int shineon_nhwc_to_nchw_add(const float* x, int x_cstride, float* y, int N, int H, int W, int C, int accumulate,
+                             shineon_stream_t stream);
 int shineon_maxpool2x2_bwd(const float* x, const float* g_y, int g_cstride, float* g_x, int N, int H, int W, int C,
                            shineon_stream_t stream);
 

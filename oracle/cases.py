@@ -55,3 +55,40 @@ def flownet2_inputs(B=1, H=256, W=192):
     im1 = base[:, :, 8:8 + H, 8:8 + W] + 0.05 * torch.rand(B, 3, H, W, generator=g)
     im2 = base[:, :, 5:5 + H, 10:10 + W] + 0.05 * torch.rand(B, 3, H, W, generator=g)
     return torch.stack([im1, im2], dim=2).contiguous().clamp(0, 1)
+
+
+# training cases: name -> (hparams overrides, batch size)
+TRAIN_CASES = {
+    "train_gelu_attn": (dict(self_attn=True, num_attn=2, activation="gelu", ngf=64, is_train=True), 2),
+}
+
+
+def train_batch(name, H=256, W=192):
+    """The batch dict UnetMaskModel.training_step reads (unet_mask_model.py:137-146), [B, n, C, H, W] like the
+    reference's collated dataset output; smooth-ish images so the L1 / perceptual terms are not pure noise."""
+    over, B = TRAIN_CASES[name]
+    n = over.get("n_frames_total", 1)
+    g = _g(name)
+
+    def smooth(c):
+        low = torch.rand(B * n, c, H // 8, W // 8, generator=g) * 2 - 1
+        t = torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear", align_corners=False)
+        return (t + 0.1 * torch.randn(B * n, c, H, W, generator=g)).clamp(-1, 1).view(B, n, c, H, W)
+
+    batch = dict(image=smooth(3), prev_image=smooth(3), cloth=smooth(3), agnostic=smooth(4), densepose=smooth(3),
+                 cloth_mask=(smooth(1) > 0).float())
+    if over.get("flow_warp"):
+        batch["flow"] = torch.randn(B, n, 2, H, W, generator=g) * 3
+    return batch
+
+
+def fold_frames(batch):
+    """[B, n, C, H, W] -> [B, n*C, H, W] (datasets/n_frames_interface.py:105-138)."""
+    return {k: (v.reshape(v.shape[0], v.shape[1] * v.shape[2], *v.shape[3:]) if v.dim() == 5 else v) for k, v in batch.items()}
+
+
+def grad_sample(t, n=256):
+    """Fixed strided sample of a gradient tensor kept in the golden files."""
+    f = t.reshape(-1)
+    step = max(1, f.numel() // n)
+    return f[::step][:n].contiguous()

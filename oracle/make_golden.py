@@ -78,6 +78,34 @@ def flownet2_golden():
         _save("flownet2", shapes, flow=cases.subsample(flow, 2), conf=cases.subsample(conf, 2))
 
 
+def train_golden():
+    """Loss terms and parameter gradients of the reference's own UnetMaskModel.training_step + loss.backward()
+    (unet_mask_model.py:137-217) with its real VGGLoss / Vgg19 classes (random weights instead of the ImageNet download)."""
+    ref_shim.install()
+    for name, (over, _) in cases.TRAIN_CASES.items():
+        m = ref_shim.build_unet_mask_model(**over)
+        m.train()
+        shapes = weights.shapes_of(m)
+        m.load_state_dict(weights.synth_state_dict(shapes, SEED), strict=True)
+        m.visualize = lambda *a, **k: None
+        res = m.training_step(cases.train_batch(name), 0)
+        loss = res.minimize
+        loss.backward()
+        arrs = {"loss": loss.detach().reshape(1)}
+        for k, v in res.items():
+            arrs["log:" + k] = torch.as_tensor(v).detach().reshape(1)
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                arrs["gnorm:" + k] = p.grad.norm().reshape(1)
+                arrs["gsamp:" + k] = cases.grad_sample(p.grad)
+        _save(name, shapes, **arrs)
+
+
 if __name__ == "__main__":
-    main()
-    flownet2_golden()
+    which = sys.argv[1:] or ["main", "flownet2", "train"]
+    if "main" in which:
+        main()
+    if "flownet2" in which:
+        flownet2_golden()
+    if "train" in which:
+        train_golden()

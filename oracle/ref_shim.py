@@ -114,9 +114,21 @@ def build_unet_mask_model(**over):
     from torch import nn
     import models.unet_mask_model as umm
 
-    class _NoVGG(nn.Module):  # VGGLoss() downloads torchvision weights and calls .cuda() (loss.py:106-110)
-        def forward(self, a, b):
-            return (a - b).abs().mean() * 0
+    # VGGLoss() downloads torchvision's ImageNet weights and calls .cuda() (loss.py:106-110, vgg.py:9): build the same
+    # torchvision architecture without the download and keep it on the CPU — the reference classes stay untouched
+    import torchvision.models as tvm
+    import models.networks.vgg as ref_vgg
 
-    umm.VGGLoss = _NoVGG
-    return umm.UnetMaskModel(hparams(**over)).eval()
+    class _TV:
+        @staticmethod
+        def vgg19(pretrained=False, **kw):
+            return tvm.vgg19(weights=None)
+
+    ref_vgg.models = _TV
+    orig_cuda = nn.Module.cuda
+    nn.Module.cuda = lambda self, *a, **k: self
+    try:
+        m = umm.UnetMaskModel(hparams(**over))
+    finally:
+        nn.Module.cuda = orig_cuda
+    return m.eval()

@@ -30,6 +30,11 @@ def synth_tensor(seed, key, shape, conv_std=None):
         return torch.rand(shape, generator=g) + 0.5
     if leaf == "bias":
         return torch.randn(shape, generator=g) * 0.05
+    if leaf == "weight" and len(shape) == 4 and "criterionVGG" in key:
+        # stands in for the ImageNet weights the reference downloads (vgg.py:9): fan-in scaled so the 13-layer ReLU
+        # stack keeps O(1) activations and the perceptual term carries signal
+        fan_in = shape[1] * shape[2] * shape[3]
+        return torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
     if leaf == "weight" and len(shape) >= 2:
         # the reference's own initialiser scale: init.normal_(w, 0.0, 0.02) for Conv / Linear
         # (models/networks/__init__.py:49-55)

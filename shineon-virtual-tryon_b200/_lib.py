@@ -42,7 +42,7 @@ class Conv2dWgradParams(C.Structure):
         ("Cout", c_i), ("Cin", c_i), ("kh", c_i), ("kw", c_i), ("stride", c_i), ("pad_h", c_i), ("pad_w", c_i),
         ("Ho", c_i), ("Wo", c_i), ("plane_fmt", c_i), ("chan_map", c_p), ("mode", c_i), ("grad_w", c_p),
         ("alpha", c_f), ("beta", c_f), ("workspace", c_p), ("workspace_bytes", C.c_size_t), ("splits", c_i),
-        ("desc_variant", c_i),
+        ("desc_variant", c_i), ("g_coffset", c_i),
     ]
 
 
@@ -95,6 +95,7 @@ SIGNATURES = {
     "shineon_tom_compose_bwd": [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_l1_loss": [c_p, c_p, c_p, c_p, c_p, C.c_long, c_f, c_f, c_i, c_p],
     "shineon_maxpool2x2_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_nhwc_to_nchw_add": [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_maxpool2x2_bwd": [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_p],
     "shineon_tom_compose": [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
 }

@@ -399,13 +399,15 @@ __global__ void __launch_bounds__(256)
     const float m = 1.f / (1.f + expf(-up[3 * nf + f]));
     float fm = 0.f;
     if (flow_warp) fm = 1.f / (1.f + expf(-up[4 * nf + f]));
-    float gm = g_mask ? g_mask[((long)b * nf + f) * HW + p] : 0.f;
-    float gfm = (flow_warp && g_fmask) ? g_fmask[((long)b * nf + f) * HW + p] : 0.f;
+    // the gradients are per-frame tensors: g_rend / g_tryon [B,3,H,W], g_mask / g_fmask [B,1,H,W]
+    float gm = g_mask ? g_mask[(long)b * HW + p] : 0.f;
+    float gfm = (flow_warp && g_fmask) ? g_fmask[(long)b * HW + p] : 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const long o = ((long)b * 3 * nf + 3 * f + k) * HW + p;
       const float r = tanhf(up[3 * f + k]);
-      const float gt = g_tryon ? g_tryon[o] : 0.f;
+      const long og = ((long)b * 3 + k) * HW + p;
+      const float gt = g_tryon ? g_tryon[og] : 0.f;
       const float grr = gt * (1.f - m);
       float rr = r, gr = grr;
       if (warped_prev) {
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(256)
         gfm = fmaf(grr, r - w, gfm);
         if (g_warped) g_warped[((long)b * 3 + k) * HW + p] = grr * (1.f - fm);
       }
-      if (g_rend) gr += g_rend[o];
+      if (g_rend) gr += g_rend[og];
       gm = fmaf(gt, cloth[o] - rr, gm);
       gp[3 * f + k] = gr * (1.f - r * r);
     }
@@ -504,9 +506,31 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// y[n,c,h,w] (+)= x[n,h,w,c] for a small channel count (gradient of an NCHW image produced by an NHWC kernel)
+__global__ void __launch_bounds__(256)
+    nhwc_to_nchw_add_kernel(const float* __restrict__ x, int cstride, float* __restrict__ y, int HW, int C, long total,
+                            int accumulate) {
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int p = (int)(e % HW);
+    const long r = e / HW;
+    const int c = (int)(r % C);
+    const long n = r / C;
+    const float v = __ldg(x + (n * HW + p) * cstride + c);
+    y[e] = accumulate ? y[e] + v : v;
+  }
+}
+
 }  // namespace shineon
 
 using namespace shineon;
+
+extern "C" int shineon_nhwc_to_nchw_add(const float* x, int x_cstride, float* y, int N, int H, int W, int C, int accumulate,
+                                        shineon_stream_t stream) {
+  SHINEON_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && x_cstride >= C, "nhwc_to_nchw_add: bad arguments");
+  const long total = (long)N * C * H * W;
+  nhwc_to_nchw_add_kernel<<<grid_x(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_cstride, y, H * W, C, total, accumulate);
+  return after_launch("nhwc_to_nchw_add_kernel");
+}
 
 extern "C" int shineon_instnorm_act_bwd(const float* x, const double* stats_fwd, const float* g1, const float* g2,
                                         float* gx_f32, void* gx_hi, void* gx_lo, double* stats_ws, int N, int H, int W,

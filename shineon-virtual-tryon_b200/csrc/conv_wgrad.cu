@@ -30,7 +30,7 @@ struct WgradArgs {
   int nb, bh, bw, tiles_w, tiles_h;
   int stride, pad_h, pad_w, kw;
   int x_cstride;
-  int Cout, g_cpad, cin_pad;
+  int Cout, g_cpad, g_coffset, cin_pad;
   int co_tiles, ci_tiles, taps, splits, kt_per_split, k_tiles;
   int total_items, stages;
   uint32_t idesc, lbo, sbo;
@@ -136,8 +136,8 @@ __global__ void __launch_bounds__(kWgThreads, 1)
           const uint32_t sA = tiles + s * kStageBytes;
           const uint32_t sB = sA + kPlanes * kWgABytes;
           for (int b = 0; b < a_boxes; ++b) {
-            tma_load_4d(sA + b * kWgBoxBytes, &tmGh, full, co0 + b * 64, w0, h0, n0);
-            if (SPLIT) tma_load_4d(sA + kWgABytes + b * kWgBoxBytes, &tmGl, full, co0 + b * 64, w0, h0, n0);
+            tma_load_4d(sA + b * kWgBoxBytes, &tmGh, full, a.g_coffset + co0 + b * 64, w0, h0, n0);
+            if (SPLIT) tma_load_4d(sA + kWgABytes + b * kWgBoxBytes, &tmGl, full, a.g_coffset + co0 + b * 64, w0, h0, n0);
           }
           if (a.stride == 1) {
             const int cx = w0 + fx - a.pad_w, cy = h0 + fy - a.pad_h;
@@ -379,6 +379,7 @@ extern "C" int shineon_conv2d_wgrad(const shineon_conv2d_wgrad_params* p, shineo
   SHINEON_REQUIRE(p->mode >= 0 && p->mode <= 2, "conv2d_wgrad: mode %d", p->mode);
   const int x_cstride = p->x_cstride ? p->x_cstride : p->cin_pad;
   const int g_cstride = p->g_cstride ? p->g_cstride : p->g_cpad;
+  SHINEON_REQUIRE(p->g_coffset >= 0 && p->g_coffset + p->Cout <= g_cstride, "conv2d_wgrad: G channel window out of range");
   SHINEON_REQUIRE(x_cstride >= p->cin_pad && x_cstride % 8 == 0 && g_cstride >= p->g_cpad && g_cstride % 8 == 0, "conv2d_wgrad: channel strides");
   cudaStream_t stream = (cudaStream_t)stream_;
   const bool split = p->g_lo != nullptr;
@@ -392,7 +393,7 @@ extern "C" int shineon_conv2d_wgrad(const shineon_conv2d_wgrad_params* p, shineo
   const bool i2c = p->mode == 1;
   a.stride = i2c ? 1 : p->stride; a.pad_h = i2c ? 0 : p->pad_h; a.pad_w = i2c ? 0 : p->pad_w; a.kw = i2c ? 1 : p->kw;
   a.x_cstride = x_cstride;
-  a.Cout = p->Cout; a.g_cpad = p->g_cpad; a.cin_pad = p->cin_pad;
+  a.Cout = p->Cout; a.g_cpad = p->g_cpad; a.g_coffset = p->g_coffset; a.cin_pad = p->cin_pad;
   const int bn = p->cin_pad >= 128 ? 128 : 64;
   a.co_tiles = cdiv(p->Cout, 128);
   a.ci_tiles = cdiv(p->cin_pad, bn);
@@ -419,7 +420,8 @@ extern "C" int shineon_conv2d_wgrad(const shineon_conv2d_wgrad_params* p, shineo
   CUtensorMap tGh, tGl, tXh, tXl;
   {
     const cuuint64_t C = (cuuint64_t)g_cstride;
-    cuuint64_t dims[4] = {(cuuint64_t)p->g_cpad, (cuuint64_t)p->Wo, (cuuint64_t)p->Ho, (cuuint64_t)p->N};
+    // the channel extent covers the whole pixel row: a window (g_coffset) may start anywhere inside it
+    cuuint64_t dims[4] = {C, (cuuint64_t)p->Wo, (cuuint64_t)p->Ho, (cuuint64_t)p->N};
     cuuint64_t strides[3] = {C * 2, (cuuint64_t)p->Wo * C * 2, (cuuint64_t)p->Ho * p->Wo * C * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.nb};
     if ((rc = encode_map(&tGh, p->g_hi, 4, dims, strides, box, "G hi", p->plane_fmt))) return rc;

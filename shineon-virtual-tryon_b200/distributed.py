@@ -61,6 +61,8 @@ class FlatGradAllReducer:
     are ready first overlaps the rest of the backward pass."""
 
     def __init__(self, params, bucket_bytes=32 << 20):
+        """`params` in the order their gradients become final during the backward pass (see
+        training.backward_order): bucket k can then be launched as soon as the last of its parameters is done."""
         self.params = [p for p in params]
         self.numel = sum(p.numel() for p in self.params)
         first = self.params[0]
@@ -72,6 +74,55 @@ class FlatGradAllReducer:
         per = max(1, bucket_bytes // 4)
         self.buckets = [(s, min(s + per, self.numel)) for s in range(0, self.numel, per)]
         self._work = []
+        # overlap bookkeeping: parameter i ends at offset ends[i]; a bucket is complete once every parameter that
+        # overlaps it has been reported by mark_ready (parameters are reported in buffer order)
+        self._ends, off = [], 0
+        for p in self.params:
+            off += p.numel()
+            self._ends.append(off)
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._ready_upto = 0   # elements [0, _ready_upto) hold final gradients
+        self._next_bucket = 0
+        self._overlap = False
+
+    # ---- overlapped mode: all-reduce of bucket k starts while the backward pass is still producing later buckets
+    def begin_overlap(self):
+        self._work, self._ready_upto, self._next_bucket, self._overlap = [], 0, 0, True
+        self._done = [False] * len(self.params)
+
+    def mark_ready(self, params):
+        """Called by the backward pass when the gradients of `params` are final."""
+        if not self._overlap:
+            return
+        for p in params:
+            i = self._index.get(id(p))
+            if i is not None:
+                self._done[i] = True
+        i = 0
+        while self._ready_upto < self.numel:
+            # advance over the prefix of finished parameters
+            while i < len(self.params) and self._ends[i] <= self._ready_upto:
+                i += 1
+            if i >= len(self.params) or not self._done[i]:
+                break
+            self._ready_upto = self._ends[i]
+        active = dist.is_initialized() and dist.get_world_size() > 1
+        while self._next_bucket < len(self.buckets) and self.buckets[self._next_bucket][1] <= self._ready_upto:
+            s, e = self.buckets[self._next_bucket]
+            if active:
+                self._work.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, async_op=True))
+            self._next_bucket += 1
+
+    def end_overlap(self):
+        """Launches whatever mark_ready has not covered (e.g. frozen parameters at the tail) and waits."""
+        active = dist.is_initialized() and dist.get_world_size() > 1
+        while self._next_bucket < len(self.buckets):
+            s, e = self.buckets[self._next_bucket]
+            if active:
+                self._work.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, async_op=True))
+            self._next_bucket += 1
+        self._overlap = False
+        return self.finish()
 
     def grad_view(self, i):
         """Where the backward pass writes the gradient of parameter i (no per-parameter .grad tensors to pack)."""

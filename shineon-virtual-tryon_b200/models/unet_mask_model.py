@@ -9,6 +9,7 @@ from .. import ops
 from ..networks import init_weights
 from ..networks.cpvton.unet import UnetGenerator
 from ..networks.flownet2.native_ops import Resample2d
+from ..networks.loss import VGGLoss
 from .base_model import BaseModel, get_and_cat_inputs, maybe_combine_frames_and_channels
 
 
@@ -40,7 +41,7 @@ class UnetMaskModel(BaseModel):
             activation=hparams.activation,
         )
         self.resample = Resample2d()
-        # VGGLoss (criterionVGG, unet_mask_model.py:61) is training-only and out of this build's scope
+        self.criterionVGG = VGGLoss()  # frozen VGG19 slices (unet_mask_model.py:61); random until a checkpoint is loaded
         init_weights(self.unet, init_type="normal")
 
     def set_precision(self, precision):
@@ -72,9 +73,88 @@ class UnetMaskModel(BaseModel):
             ops.tom_compose(out, warped_cloths, n, flow_warp, outs, frame=f, warped_prev=warped_prev)
         return p_rendereds, tryon_masks, p_tryons, flow_masks
 
+    def set_train_precision(self, precision):
+        """Numeric mode of the training step: "bf16x3" (default; fp32-grade products, parity-tested) or "bf16" (the
+        BASELINE config-5 speed mode: single bf16 tensor-core products, fp32 accumulation / statistics / master weights)."""
+        self.unet.precision = precision
+        self.criterionVGG.precision = precision
+
     def training_step(self, batch, batch_idx, val=False):
-        raise NotImplementedError("U-Net training (backward kernels, VGG loss) is not part of this build yet "
-                                  "(DESIGN.md §9)")
+        """unet_mask_model.py:137-217 without Lightning: forward, the four loss terms and — unless `val` — the whole
+        backward pass, all on the hand-written kernels.  Parameter gradients are ACCUMULATED into `.grad` (zero them per
+        optimiser step; `accumulated_batches` micro-batches simply call this repeatedly).  Returns
+        {"loss": 0-dim tensor, "log": {name: tensor}} with the reference's log names."""
+        hp = self.hparams
+        batch = maybe_combine_frames_and_channels(hp, batch)
+        n = hp.n_frames_total
+        flow_warp = bool(hp.flow_warp)
+        im, cm = batch["image"].contiguous(), batch["cloth_mask"].contiguous()
+        flows = batch["flow"].contiguous() if flow_warp else None
+        person = get_and_cat_inputs(batch, hp.person_inputs).contiguous()
+        cloths = get_and_cat_inputs(batch, hp.cloth_inputs).contiguous()
+        dev = person.device
+        saved_prec = self.unet.precision
+        if self.unet.precision is None:
+            self.unet.precision = "bf16x3"
+        try:
+            out = self.unet.forward_train(person, cloths) if not val else self.unet.model.run(
+                (person, cloths), ops.resolve_precision(self.unet.precision))
+        finally:
+            self.unet.precision = saved_prec
+        B, H, W, Cout = out.shape
+        p_rendereds = torch.empty(B, 3 * n, H, W, device=dev)
+        tryon_masks = torch.empty(B, n, H, W, device=dev)
+        p_tryons = torch.empty(B, 3 * n, H, W, device=dev)
+        flow_masks = torch.empty(B, n, H, W, device=dev) if flow_warp else None
+        outs = (p_rendereds, tryon_masks, p_tryons, flow_masks)
+        flows_c = [c.contiguous() for c in torch.chunk(flows, n, dim=1)] if flows is not None else None
+        prev_gen, warped = [None] * n, [None] * n
+        for f in range(n):
+            if flows_c is not None and f > 0:
+                prev_gen[f] = p_tryons[:, 3 * (f - 1):3 * f].contiguous()
+                warped[f] = self.resample(prev_gen[f], flows_c[f])
+            ops.tom_compose(out, cloths, n, flow_warp, outs, frame=f, warped_prev=warped[f])
+        self.p_rendereds, self.tryon_masks, self.p_tryons, self.flow_masks = outs
+
+        # ---- losses (unet_mask_model.py:173-191): last frame (and the one before it, each weighted 0.5, when n > 1)
+        acc = torch.zeros(8, device=dev)  # l1, vgg, mask_l1, flow_mask, then per-frame curr/prev copies for the log
+        used = [(n - 1, 0.5 if n > 1 else 1.0)] + ([(n - 2, 0.5)] if n > 1 else [])
+        grad = not val
+        g_tryon = [torch.zeros(B, 3, H, W, device=dev) for _ in range(n)] if grad else [None] * n
+        g_mask = [None] * n
+        for f, w in used:
+            pt = p_tryons[:, 3 * f:3 * f + 3].contiguous()
+            tgt = im[:, 3 * f:3 * f + 3].contiguous()
+            ops.l1_loss(pt, tgt, acc[0:1], g_tryon[f], weight=w, accumulate_grad=True)
+            self.criterionVGG.loss_and_grad(pt, tgt, acc[1:2], g_tryon[f], scale=w)
+            tm = tryon_masks[:, f:f + 1].contiguous()
+            if grad:
+                g_mask[f] = torch.empty(B, 1, H, W, device=dev)
+            ops.l1_loss(tm, cm[:, f:f + 1].contiguous(), acc[2:3], g_mask[f], weight=w)
+        g_fm = None
+        if flow_warp:
+            last_fm = flow_masks[:, n - 1:n].contiguous()
+            ops.channel_sum(last_fm.view(-1, 1), acc[3:4], alpha=float(hp.pen_flow_mask), beta=1.0)
+            if grad:
+                g_fm = torch.full((B, 1, H, W), float(hp.pen_flow_mask), device=dev)
+        loss = acc[0:4].sum()
+
+        # ---- backward: compose (+ flow-warp chain over frames, last to first) -> U-Net
+        if grad:
+            g_out = torch.zeros(B, H, W, Cout, device=dev)
+            for f in reversed(range(n)):
+                gw = ops.tom_compose_bwd(out, cloths, n, flow_warp, g_out, frame=f, warped_prev=warped[f],
+                                         g_tryons=g_tryon[f], g_masks=g_mask[f],
+                                         g_flow_masks=g_fm if f == n - 1 else None, want_g_warped=warped[f] is not None)
+                if warped[f] is not None:  # p_tryon of frame f-1 also feeds frame f through Resample2d
+                    ops.resample2d_bwd(prev_gen[f], flows_c[f], gw, grad_in1=g_tryon[f - 1])
+            self.unet.backward(g_out)
+        if not val:
+            self.global_step += 1
+        v = "val_" if val else ""
+        log = {f"{v}loss/G": loss, f"{v}loss/G/l1": acc[0], f"{v}loss/G/vgg": acc[1], f"{v}loss/G/tryon_mask_l1": acc[2],
+               f"{v}loss/G/flow_mask_l1": acc[3]}
+        return {"loss": loss, "log": log}
 
     def test_step(self, batch, batch_idx):
         """Inference step (unet_mask_model.py:250-281) without the PNG writing."""

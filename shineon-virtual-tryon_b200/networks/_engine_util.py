@@ -3,9 +3,18 @@ import torch
 from torch import nn
 
 
+# Bumped by optimisers that update parameters through raw pointers (the fused Adam over the flat parameter
+# buffer does not touch the tensors' autograd version counters): every packed-weight cache is keyed on it.
+WEIGHTS_EPOCH = [0]
+
+
+def bump_weights_epoch():
+    WEIGHTS_EPOCH[0] += 1
+
+
 def params_signature(module):
     """Cheap change detector for a module's parameters/buffers: (data_ptr, _version) of every tensor."""
-    sig = []
+    sig = [WEIGHTS_EPOCH[0]]
     for t in list(module.parameters()) + list(module.buffers()):
         sig.append((t.data_ptr(), t._version, t.device.index))
     return tuple(sig)

@@ -41,6 +41,32 @@ class SelfAttention(nn.Module):
         return ops.sagan_attention(qkv, x_f32, self.gamma.detach(), self.chanel_in // 8, act=act, act_param=act_param,
                                    want_f32=want_f32, want_planes=want_planes, prec=prec)
 
+    # ---- training (row U6)
+    def run_train(self, x_f32, x_planes):
+        """-> (z = gamma*attention(x) + x as f32 NHWC, qkv projections f32 NHWC) for the backward."""
+        qkv, _ = ops.conv2d(x_planes, self.packed(x_planes.prec), want_f32=True)
+        z, _ = ops.sagan_attention(qkv, x_f32, self.gamma.detach(), self.chanel_in // 8, want_f32=True, want_planes=False)
+        return z, qkv
+
+    def backward(self, x_planes, qkv, g_out, prec):
+        """g_out = dL/dz (f32 NHWC).  Accumulates gamma / q,k,v weight and bias gradients; returns the part of dL/dx that
+        flows through the projections (the residual branch contributes g_out itself, added by the caller)."""
+        from ..cpvton.unet import _grad_of
+
+        C, Cq = self.chanel_in, self.chanel_in // 8
+        g_qkv = ops.sagan_attention_bwd(qkv, self.gamma.detach(), g_out, Cq, _grad_of(self.gamma), beta_gamma=1.0)
+        _, G = ops.instnorm_act(g_qkv, do_norm=False, want_f32=False, want_planes=True, prec=prec)  # f32 -> planes
+        for conv, c0, cn in ((self.query_conv, 0, Cq), (self.key_conv, Cq, Cq), (self.value_conv, 2 * Cq, C)):
+            ops.channel_sum(g_qkv, _grad_of(conv.bias), beta=1.0, coffset=c0)
+            ops.conv2d_wgrad(G, x_planes, _grad_of(conv.weight), Cout=cn, Cin=C, kh=1, kw=1, stride=1, pad=0, beta=1.0,
+                             g_coffset=c0)
+        sig = (params_signature(self), prec, "dgrad")
+        if getattr(self, "_packed_dgrad", None) is None or self._packed_dgrad[0] != sig:
+            w = torch.cat([self.query_conv.weight, self.key_conv.weight, self.value_conv.weight], 0)
+            self._packed_dgrad = (sig, ops.PackedConv(w, None, stride=1, pad=0, prec=prec, transposed=True))
+        g_x, _ = ops.conv2d(G, self._packed_dgrad[1], want_f32=True)
+        return g_x
+
     def forward(self, x):
         """x: [B, C, W, H] f32 CUDA tensor -> gamma * attention(x) + x (sagan.py:29-53)."""
         xp = ops.nchw_to_planes(x.contiguous(), prec=ops.resolve_precision(self.precision))

@@ -50,6 +50,39 @@ class UnetGenerator(nn.Module):
     def forward(self, input):
         return self.forward_nhwc(input).permute(0, 3, 1, 2).contiguous()
 
+    # ------------------------------------------------------------------ training
+    def forward_train(self, x0, x1=None):
+        """Forward that keeps what the hand-written backward needs (conv inputs as planes, pre-norm conv outputs,
+        InstanceNorm statistics, attention projections).  (x0, x1): f32 NCHW inputs, concatenated on channels.
+        Returns the f32 NHWC output; call `backward(grad_nhwc)` next."""
+        require_cuda(self, "UnetGenerator")
+        prec = ops.resolve_precision(self.precision if self.precision is not None else "bf16x3")
+        self._train_prec = prec
+        return self.model.run((x0.contiguous(), None if x1 is None else x1.contiguous()), prec, train=True)
+
+    def backward(self, grad_out_nhwc):
+        """Accumulates dL/dparam into every parameter's .grad (allocated on first use) given dL/d(output) as f32 NHWC
+        [N,H,W,output_nc].  The input gradient is not produced (the U-Net's inputs are data)."""
+        self.model.backward(grad_out_nhwc.contiguous(), None, self._train_prec)
+
+
+# Set by training.Trainer for the micro-batch whose gradients get exchanged: called with the parameters whose
+# gradients just became final, so the data-parallel all-reduce of a full bucket overlaps the rest of the backward.
+GRAD_READY_HOOK = None
+
+
+def _ready(params):
+    if GRAD_READY_HOOK is not None:
+        GRAD_READY_HOOK([p for p in params if p is not None])
+
+
+def _grad_of(p):
+    """The parameter's gradient accumulator (zero-initialised on first use; a view of the flat data-parallel
+    gradient buffer when ops-level training helpers installed one)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
 
 class UnetSkipConnectionBlock(nn.Module):
     def __init__(self, outer_nc, inner_nc, input_nc=None, submodule=None, outermost=False, innermost=False,
@@ -137,6 +170,10 @@ class UnetSkipConnectionBlock(nn.Module):
         else:
             d["up_tap"] = None
             d["up"] = ops.PackedConv(uc.weight, uc.bias, stride=1, pad=1, prec=prec)
+        d["cmap_up"] = None
+        if sub is not None:
+            d["cmap_up"] = torch.as_tensor(cmap, dtype=torch.int32, device=uc.weight.device)
+        d["up_dgrad"] = d["down_dgrad"] = None  # packed lazily by _pack_bwd (training only)
         for key, norm in (("down_bn", pr["downnorm"]), ("up_bn", pr["upnorm"])):
             d[key] = None
             if isinstance(norm, nn.BatchNorm2d):
@@ -147,6 +184,54 @@ class UnetSkipConnectionBlock(nn.Module):
                 raise NotImplementedError("InstanceNorm2d with affine/running stats is not used by the reference")
         self._packed = (sig, d)
         return d
+
+    def _pack_bwd(self, prec):
+        """Data-gradient operands: a stride-1 conv's dgrad is the flipped-tap conv with Cin/Cout swapped, the 4x4 s2
+        down-conv's dgrad is the four-phase transposed conv (both on the same tcgen05 kernel as the forward)."""
+        from ..deconv import PackedDeconv4x4s2
+
+        pk = self._pack(prec)
+        if pk["up_dgrad"] is None:
+            pr = self._parts
+            pk["up_dgrad"] = ops.PackedConv(pr["upconv"].weight, None, stride=1, pad=1, prec=prec, transposed=True)
+            if not self.outermost:
+                pk["down_dgrad"] = PackedDeconv4x4s2(pr["downconv"].weight, None, prec=prec)
+        return pk
+
+    def _finish_train(self, conv_f32, norm, attn, act, act_param, prec, want_final_f32=False):
+        """Training form of _finish: nothing is overwritten in place and the backward's inputs are returned."""
+        inorm = isinstance(norm, nn.InstanceNorm2d)
+        eps = norm.eps if inorm else 1e-5
+        ws = ops.instnorm_stats_ws(conv_f32) if inorm else None
+        sv = dict(c=conv_f32, ws=ws, inorm=inorm, eps=eps, act=act, act_param=act_param, attn=attn)
+        if attn is None:
+            if want_final_f32:
+                y, _ = ops.instnorm_act(conv_f32, do_norm=inorm, eps=eps, act=None, want_f32=True, want_planes=False, ws=ws)
+                sv["act"] = None
+                return y, sv
+            _, p = ops.instnorm_act(conv_f32, do_norm=inorm, eps=eps, act=act, act_param=act_param, want_f32=False,
+                                    want_planes=True, prec=prec, ws=ws)
+            return p, sv
+        y, p = ops.instnorm_act(conv_f32, do_norm=inorm, eps=eps, act=None, want_f32=True, want_planes=True, prec=prec, ws=ws)
+        z, qkv = attn.run_train(y, p)
+        sv.update(p=p, qkv=qkv, z=z)
+        if want_final_f32:
+            sv["act"] = None
+            return z, sv
+        _, out = ops.instnorm_act(z, do_norm=False, act=act, act_param=act_param, want_f32=False, want_planes=True, prec=prec)
+        return out, sv
+
+    @staticmethod
+    def _finish_bwd(sv, g1, g2, prec):
+        """-> (f32 NHWC, Planes) of dL/d(conv output) given dL/d(activated output) = g1 (+ g2)."""
+        attn = sv["attn"]
+        if attn is None:
+            return ops.instnorm_act_bwd(sv["c"], sv["ws"], g1, g2, do_norm=sv["inorm"], act=sv["act"],
+                                        act_param=sv["act_param"], eps=sv["eps"], want_f32=True, want_planes=True, prec=prec)
+        gz = g1 if (sv["act"] is None and g2 is None) else ops.act_bwd(sv["z"], g1, g2, act=sv["act"], act_param=sv["act_param"])
+        g_y = attn.backward(sv["p"], sv["qkv"], gz, prec)  # through the q|k|v projections; the residual is gz itself
+        return ops.instnorm_act_bwd(sv["c"], sv["ws"], gz, g_y, do_norm=sv["inorm"], act=None, eps=sv["eps"],
+                                    want_f32=True, want_planes=True, prec=prec)
 
     def _finish(self, conv_f32, norm, bn, attn, act, act_param, prec, want_final_f32=False):
         """conv output (f32 NHWC, bias [and folded BN] applied) -> [InstanceNorm] -> [SelfAttention] -> act.
@@ -167,7 +252,7 @@ class UnetSkipConnectionBlock(nn.Module):
             return attn.run(y, p, want_f32=True, want_planes=False)[0]
         return attn.run(y, p, act=act, act_param=act_param, want_f32=False, want_planes=True)[1]
 
-    def run(self, a_in, prec):
+    def run(self, a_in, prec, train=False):
         """a_in: Planes holding this block's (already down-activated) input; for the outermost block a tuple
         (x0, x1|None) of f32 NCHW tensors (torch.cat([x0, x1], 1) is fused into the layout conversion).
         Outermost: returns f32 NHWC output.  Otherwise returns Planes of up_act(x') for the parent."""
@@ -176,6 +261,8 @@ class UnetSkipConnectionBlock(nn.Module):
             raise NotImplementedError("Dropout in training mode is not implemented in the native U-Net engine")
         pk = self._pack(prec)
         sub = pr["sub"]
+        if train:
+            return self._run_train(a_in, prec, pk)
         up_act, up_par = act_name(pr["up_act"])
         # ---- down path: conv -> [norm] -> [attn] -> activation consumed next
         if self.innermost:
@@ -209,6 +296,83 @@ class UnetSkipConnectionBlock(nn.Module):
         if self.outermost:
             return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], None, 0.0, prec, want_final_f32=True)
         return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], up_act, up_par, prec)
+
+    # ------------------------------------------------------------------ training engine (row U6)
+    def _run_train(self, a_in, prec, pk):
+        pr = self._parts
+        sub = pr["sub"]
+        if pr["default_act"]:
+            raise NotImplementedError("training the default-activation U-Net (in-place LeakyReLU skip quirk, unet.py:132) "
+                                      "has no native backward; the ShineOn recipe trains with --activation gelu")
+        if pk["down_bn"] is not None or pk["up_bn"] is not None:
+            raise NotImplementedError("BatchNorm2d U-Net training (batch statistics) has no native kernel; the reference's "
+                                      "UnetMaskModel uses InstanceNorm2d (unet_mask_model.py:56)")
+        up_act, up_par = act_name(pr["up_act"])
+        next_act, next_par = (up_act, up_par) if self.innermost else act_name(sub._parts["down_act"])
+        if isinstance(a_in, tuple):
+            if pk["down_i2c"] is not None:
+                a_in = pk["down_i2c"].prepare(a_in[0], a_in[1])  # im2col'd planes: the GEMM operand, kept for wgrad
+            else:
+                a_in = ops.nchw_to_planes(a_in[0], a_in[1], prec=prec)
+        f32, _ = ops.conv2d(a_in, pk["down"], want_f32=True)
+        a_mid, sv_down = self._finish_train(f32, pr["downnorm"], pr["attn_down"], next_act, next_par, prec)
+        xp = None if self.innermost else sub.run(a_mid, prec, train=True)
+        u = ops.upsample2x_cat(a_mid, xp)
+        f32, _ = ops.conv2d(u, pk["up"], want_f32=True)
+        out, sv_up = self._finish_train(f32, pr["upnorm"], pr["attn_up"], up_act, up_par, prec,
+                                        want_final_f32=self.outermost)
+        self._tape = dict(a_in=a_in, down=sv_down, u=u, up=sv_up)
+        return out
+
+    def up_params(self):
+        pr = self._parts
+        ps = [pr["upconv"].weight, pr["upconv"].bias]
+        if pr["attn_up"] is not None:
+            ps += list(pr["attn_up"].parameters())
+        return [p for p in ps if p is not None]
+
+    def down_params(self):
+        pr = self._parts
+        ps = [pr["downconv"].weight, pr["downconv"].bias]
+        if pr["attn_down"] is not None:
+            ps += list(pr["attn_down"].parameters())
+        return [p for p in ps if p is not None]
+
+    def backward(self, g1, g2, prec):
+        """g1 (+ g2): dL/d(this block's returned value), f32 NHWC.  Accumulates parameter gradients; returns
+        dL/d(block input planes) as f32 NHWC (None for the outermost block)."""
+        pr, tp = self._parts, self._tape
+        self._tape = None
+        pk = self._pack_bwd(prec)
+        sub = pr["sub"]
+        dc, uc = pr["downconv"], pr["upconv"]
+        # ---- up path: norm/attn/act -> conv3x3
+        gc, G = self._finish_bwd(tp["up"], g1, g2, prec)
+        if uc.bias is not None:
+            ops.channel_sum(gc, _grad_of(uc.bias), beta=1.0)
+        ops.conv2d_wgrad(G, tp["u"], _grad_of(uc.weight), Cout=uc.out_channels, Cin=uc.in_channels, kh=3, kw=3, stride=1,
+                         pad=1, chan_map=pk["cmap_up"], beta=1.0)
+        _ready(self.up_params())
+        g_u, _ = ops.conv2d(G, pk["up_dgrad"], want_f32=True)  # [N,2H,2W,Cin_up]
+        # ---- bilinear x2 + concat
+        if sub is None:
+            g_skip, _ = ops.upsample2x_cat_bwd(g_u, uc.in_channels, 0)
+            g_child = None
+        else:
+            c_skip = sub._parts["downconv"].in_channels
+            g_skip, g_xp = ops.upsample2x_cat_bwd(g_u, c_skip, uc.in_channels - c_skip)
+            g_child = sub.backward(g_xp, None, prec)
+        # ---- down path: norm/attn/act -> conv4x4 s2
+        gc, G = self._finish_bwd(tp["down"], g_skip, g_child, prec)
+        if dc.bias is not None:
+            ops.channel_sum(gc, _grad_of(dc.bias), beta=1.0)
+        ops.conv2d_wgrad(G, tp["a_in"], _grad_of(dc.weight), Cout=dc.out_channels, Cin=dc.in_channels, kh=4, kw=4, stride=2,
+                         pad=1, mode=1 if pk["down_i2c"] is not None else 0, beta=1.0)
+        _ready(self.down_params())
+        if self.outermost:
+            return None
+        g_in, _ = pk["down_dgrad"](G, want_f32=True)
+        return g_in
 
     def forward(self, x):
         raise NotImplementedError(

@@ -171,11 +171,12 @@ def resample2d_fwd(in1, flow, kernel_size=1, bilinear=True):
     return out
 
 
-def resample2d_bwd(in1, flow, grad_out, kernel_size=1, bilinear=True):
+def resample2d_bwd(in1, flow, grad_out, kernel_size=1, bilinear=True, grad_in1=None):
+    """grad_in1: optional existing accumulator (the kernel scatters with atomicAdd, so it adds onto its content)."""
     in1, flow, grad_out = _req(in1), _req(flow), _req(grad_out.contiguous())
     _, d, Hi, Wi = in1.shape
     b, _, h, w = flow.shape
-    g1 = torch.zeros_like(in1)
+    g1 = torch.zeros_like(in1) if grad_in1 is None else _req(grad_in1, name="grad_in1")
     g2 = torch.empty_like(flow)
     check(_lib.load().shineon_resample2d_bwd(_p(in1), _p(flow), _p(grad_out), _p(g1), _p(g2), b, d, Hi, Wi, h, w,
                                              kernel_size, int(bool(bilinear)), _stream()), "shineon_resample2d_bwd")
@@ -634,7 +635,7 @@ def _workspace(nbytes, device, key="ws"):
 
 
 def conv2d_wgrad(g, x, grad_w, *, Cout, Cin, kh, kw, stride, pad, mode=0, chan_map=None, alpha=1.0, beta=0.0,
-                 out_hw=None, splits=0, desc_variant=0):
+                 out_hw=None, splits=0, desc_variant=0, g_coffset=0):
     """Weight gradient of a conv layer: g = Planes of dL/d(conv output) [N,Ho,Wo,>=Cout], x = the conv's input Planes.
     Writes beta*grad_w + alpha*dW into grad_w (f32, the parameter's own layout: OIHW for mode 0/1, IOHW for mode 2)."""
     from ._lib import Conv2dWgradParams
@@ -643,7 +644,10 @@ def conv2d_wgrad(g, x, grad_w, *, Cout, Cin, kh, kw, stride, pad, mode=0, chan_m
     grad_w = _req(grad_w, name="grad_w")
     pad_h, pad_w = pad if isinstance(pad, tuple) else (pad, pad)
     p = Conv2dWgradParams()
-    p.g_hi, p.g_lo, p.g_cpad, p.g_cstride = g._ptr(g.hi), g._ptr(g.lo), g.cpad, g.cstride
+    p.g_hi, p.g_lo, p.g_cstride = g._ptr(g.hi), g._ptr(g.lo), g.cstride
+    p.g_coffset = g_coffset
+    p.g_cpad = g.cpad if g_coffset == 0 else min(cpad64(Cout), (g.cstride - g_coffset) // 64 * 64)
+    assert p.g_cpad >= 64, "G channel window too close to the end of the pixel row"
     p.x_hi, p.x_lo = x._ptr(x.hi), x._ptr(x.lo)
     p.N, p.H, p.W, p.cin_pad, p.x_cstride = x.N, x.H, x.W, x.cpad, x.cstride
     p.Cout, p.Cin, p.kh, p.kw, p.stride, p.pad_h, p.pad_w = Cout, Cin, kh, kw, stride, pad_h, pad_w
@@ -665,14 +669,14 @@ def conv2d_wgrad(g, x, grad_w, *, Cout, Cin, kh, kw, stride, pad, mode=0, chan_m
     return grad_w
 
 
-def channel_sum(x, grad, alpha=1.0, beta=0.0):
-    """grad[c] = beta*grad[c] + alpha * sum over all pixels of the NHWC f32 tensor x[..., c]  (bias gradient)."""
+def channel_sum(x, grad, alpha=1.0, beta=0.0, coffset=0):
+    """grad[c] = beta*grad[c] + alpha * sum over all pixels of the NHWC f32 tensor x[..., coffset + c]  (bias gradient)."""
     x, grad = _req(x, name="x"), _req(grad, name="grad")
     Cc = grad.numel()
     cs = x.shape[-1]
-    assert cs >= Cc
+    assert cs >= coffset + Cc
     ws = _workspace(8 * Cc, x.device, key="chsum")
-    check(_lib.load().shineon_channel_sum(_p(x), _p(grad), _p(ws), x.numel() // cs, Cc, cs, float(alpha), float(beta),
+    check(_lib.load().shineon_channel_sum(C_void(x.data_ptr() + 4 * coffset), _p(grad), _p(ws), x.numel() // cs, Cc, cs, float(alpha), float(beta),
                                           _stream()), "shineon_channel_sum")
     return grad
 
@@ -778,3 +782,13 @@ def maxpool2x2_bwd(x, g_y):
     check(_lib.load().shineon_maxpool2x2_bwd(_p(x), _p(g_y), g_y.shape[-1], _p(g_x), N, H, W, Cc, _stream()),
           "shineon_maxpool2x2_bwd")
     return g_x
+
+
+def nhwc_to_nchw_add(x, y, accumulate=True):
+    """y [N,C,H,W] (+)= x [N,H,W,>=C]."""
+    x, y = _req(x, name="x"), _req(y, name="y")
+    N, Cc, H, W = y.shape
+    assert x.shape[:3] == (N, H, W) and x.shape[3] >= Cc
+    check(_lib.load().shineon_nhwc_to_nchw_add(_p(x), x.shape[3], _p(y), N, H, W, Cc, int(bool(accumulate)), _stream()),
+          "shineon_nhwc_to_nchw_add")
+    return y

@@ -1,0 +1,87 @@
+"""Data-parallel training driver of the U-Net stage (reference: Lightning's DDP loop around
+UnetMaskModel.training_step + Adam, train.py:52-62, models/base_model.py:165-184).
+
+One process per GPU.  Parameters live in ONE flat f32 buffer and their gradients in another (every `.grad` is a view),
+so the gradient exchange is a handful of bucketed NCCL all-reduces over NVLink/NVSwitch — launched from inside the
+backward pass as soon as a bucket's last gradient is final, i.e. overlapped with the remaining backward kernels — and
+the optimiser is one fused Adam launch over the whole model.  `accumulated_batches` micro-batches accumulate into the
+same gradient buffer; the exchange happens on the last one only.
+"""
+import torch
+
+from . import ops
+from .distributed import FlatGradAllReducer
+from .networks import _engine_util
+from .networks.cpvton import unet as unet_mod
+
+
+def backward_order(unet_generator):
+    """Parameters of a UnetGenerator in the order the hand-written backward finalises their gradients:
+    up-path of the outermost block first, then inwards; the down-paths on the way back out."""
+    blocks, b = [], unet_generator.model
+    while b is not None:
+        blocks.append(b)
+        b = b._parts["sub"]
+    order = []
+    for b in blocks:
+        order += b.up_params()
+    for b in reversed(blocks):
+        order += b.down_params()
+    return order
+
+
+class Trainer:
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, accumulated_batches=1, bucket_bytes=32 << 20,
+                 lr_lambda=None):
+        self.model = model
+        ordered = [p for p in backward_order(model.unet) if p.requires_grad]
+        seen = {id(p) for p in ordered}
+        rest = [p for p in model.parameters() if p.requires_grad and id(p) not in seen]
+        self.params = ordered + rest
+        self.reducer = FlatGradAllReducer(self.params, bucket_bytes=bucket_bytes)
+        dev = self.params[0].device
+        self.flat_param = torch.empty(self.reducer.numel, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for i, p in enumerate(self.params):
+                n = p.numel()
+                view = self.flat_param[off:off + n].view_as(p)
+                view.copy_(p.data)
+                p.data = view              # the parameter now aliases the flat buffer
+                p.grad = self.reducer.grad_view(i)
+                off += n
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.accumulated_batches = max(1, int(accumulated_batches))
+        self.lr_lambda = lr_lambda
+        self.micro, self.steps, self.epoch = 0, 0, 0
+        _engine_util.bump_weights_epoch()
+
+    def zero_grad(self):
+        self.reducer.flat.zero_()
+
+    def train_batch(self, batch, batch_idx=0):
+        """One micro-batch: forward + losses + backward (gradients accumulate); on every `accumulated_batches`-th call
+        the gradient all-reduce (overlapped with that backward) and the fused Adam step.  Returns the step's result."""
+        last = (self.micro + 1) % self.accumulated_batches == 0
+        if last:
+            self.reducer.begin_overlap()
+            unet_mod.GRAD_READY_HOOK = self.reducer.mark_ready
+        try:
+            res = self.model.training_step(batch, batch_idx)
+        finally:
+            unet_mod.GRAD_READY_HOOK = None
+        self.micro += 1
+        if last:
+            inv_world = self.reducer.end_overlap()
+            self.optimizer_step(inv_world / self.accumulated_batches)
+            self.zero_grad()
+        return res
+
+    def optimizer_step(self, grad_scale=1.0):
+        self.steps += 1
+        lr = self.lr * (self.lr_lambda(self.epoch) if self.lr_lambda else 1.0)
+        ops.adam_step(self.flat_param, self.reducer.flat, self.exp_avg, self.exp_avg_sq, self.steps, lr=lr, betas=self.betas,
+                      eps=self.eps, grad_scale=grad_scale)
+        _engine_util.bump_weights_epoch()   # packed 16-bit weight copies are stale now

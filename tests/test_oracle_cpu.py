@@ -115,3 +115,39 @@ def test_flownet2_oracle_matches_reference_golden():
         conf = ofn.flow_confidence(inp[:, :, 0], inp[:, :, 1], flow)
     assert_close(cases.subsample(flow, 2), gold["flow"], atol=1e-5, rtol=1e-5, what="flownet2 flow")
     assert torch.equal(cases.subsample(conf, 2), gold["conf"])
+
+
+# ---- training step (row U6): the oracle's restatement of UnetMaskModel.training_step + autograd against the loss terms
+# and parameter gradients the reference itself produced (oracle/make_golden.py train_golden)
+def _train_kwargs(over):
+    return dict(person_inputs=["agnostic", "densepose"], cloth_inputs=["cloth"], n_frames=over.get("n_frames_total", 1),
+                flow_warp=over.get("flow_warp", False), num_downs=6, num_attention=over.get("num_attn", 2),
+                use_self_attn=over.get("self_attn", True), act=over.get("activation", "gelu"))
+
+
+@pytest.mark.parametrize("name", list(cases.TRAIN_CASES))
+def test_training_oracle_matches_reference_golden(name):
+    from oracle import train as otrain
+
+    seed, shapes, gold = load_golden(name)
+    sd = weights.synth_state_dict(shapes, seed)
+    batch = cases.fold_frames(cases.train_batch(name))
+    loss, comps, grads = otrain.tom_training_grads(sd, batch, **_train_kwargs(cases.TRAIN_CASES[name][0]))
+    assert_close(loss.reshape(1), gold["loss"], atol=1e-5, rtol=1e-5, what="loss")
+    for k in ("l1", "vgg", "tryon_mask_l1", "flow_mask_l1"):
+        assert_close(comps[k].reshape(1), gold["log:loss/G/" + k], atol=1e-5, rtol=1e-5, what=k)
+    keys = [k[6:] for k in gold if k.startswith("gnorm:")]
+    assert sorted(keys) == sorted(grads), "the oracle must produce a gradient for exactly the parameters the reference trains"
+    for k in keys:
+        scale = gold["gnorm:" + k].item() / max(1.0, grads[k].numel() ** 0.5)  # rms of the reference gradient
+        assert_close(cases.grad_sample(grads[k]), gold["gsamp:" + k], atol=1e-3 * scale + 1e-9, rtol=1e-3, what="grad " + k)
+
+
+def test_model_state_dict_matches_reference_key_for_key():
+    """Our UnetMaskModel mirrors the reference's module tree including the frozen VGG19 slices of criterionVGG."""
+    from shineon_virtual_tryon_b200.models.unet_mask_model import UnetMaskModel
+    from tests.util import make_hparams
+
+    _, shapes, _ = load_golden("train_gelu_attn")
+    mine = {k: tuple(v.shape) for k, v in UnetMaskModel(make_hparams(is_train=True)).state_dict().items()}
+    assert mine == shapes

@@ -203,10 +203,12 @@ def test_tom_compose_bwd(ops, nf, flow_warp):
     loss.backward()
     gu = torch.zeros(B, H, W, Cout, device="cuda")
     gw = ops.tom_compose_bwd(u.detach().cuda(), cloth.cuda(), nf, flow_warp, gu, frame=f,
-                             warped_prev=wp.detach().cuda() if wp is not None else None, g_rendereds=g_r.cuda(),
-                             g_masks=g_m.cuda(), g_tryons=g_t.cuda(), g_flow_masks=g_f.cuda() if flow_warp else None,
+                             warped_prev=wp.detach().cuda() if wp is not None else None,
+                             g_rendereds=g_r[:, 3 * f:3 * f + 3].contiguous().cuda(), g_masks=g_m[:, f:f + 1].contiguous().cuda(),
+                             g_tryons=g_t[:, 3 * f:3 * f + 3].contiguous().cuda(),
+                             g_flow_masks=g_f[:, f:f + 1].contiguous().cuda() if flow_warp else None,
                              want_g_warped=wp is not None)
-    assert rel_err(gu, u.grad) < 1e-5
+    assert rel_err(gu, u.grad) < 1e-5  # channels of other frames stay zero in both
     if wp is not None:
         assert rel_err(gw, wp.grad) < 1e-5
 
