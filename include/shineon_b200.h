@@ -152,6 +152,11 @@ int shineon_pack_conv_weight(const float* w, void* w_hi, void* w_lo, int Cout, i
                              int cin_pad, const int32_t* chan_map, int transpose_io, int plane_fmt,
                              float w_scale /* packed = w * w_scale; pass 1/w_scale as acc_scale */,
                              shineon_stream_t stream);
+/* ConvTranspose2d(kernel 4, stride 2, padding 1) weight [Cin][Cout][4][4] (also: the data-gradient operand of a 4x4 s2
+ * Conv2d, whose OIHW weight has exactly that layout with Cin := its Cout) -> the four phase-wise 2x2 stride-1 convs:
+ * w_hi/w_lo [4 phases (py*2+px)][Cout][2*2][cin_pad].  submodules.py:34-38. */
+int shineon_pack_deconv4x4s2_weight(const float* w, void* w_hi, void* w_lo, int Cin, int Cout, int cin_pad,
+                                    const int32_t* chan_map, int plane_fmt, float w_scale, shineon_stream_t stream);
 
 typedef struct shineon_conv2d_params {
   /* input activation, NHWC planes [N,H,W,cin_pad] bf16 */

@@ -65,6 +65,7 @@ SIGNATURES = {
     "shineon_correlation_gather": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_correlation_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_pack_conv_weight": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_f, c_p],
+    "shineon_pack_deconv4x4s2_weight": [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_f, c_p],
     "shineon_conv2d_igemm_fwd": [C.POINTER(Conv2dParams), c_p],
     "shineon_conv2d_im2col_fwd": [C.POINTER(Conv2dParams), c_p, c_i, c_p, c_i, c_p],
     "shineon_conv2d_direct_fwd": [C.POINTER(Conv2dParams), c_p],

@@ -637,6 +637,32 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ConvTranspose2d(4, 2, 1) weight [Cin][Cout][4][4] -> the four phase-wise 2x2 stride-1 convs it decomposes into
+// (networks/deconv.py): out[phase = py*2+px][co][(fy,fx)][ci_pad] = w[ci][co][T[py][fy]][T[px][fx]], T = {0:{3,1}, 1:{2,0}}.
+__global__ void __launch_bounds__(256)
+    pack_deconv4x4s2_weight_kernel(const float* __restrict__ w, plane_t* __restrict__ whi, plane_t* __restrict__ wlo,
+                                   int Cout, int Cin, int cin_pad, const int32_t* __restrict__ chan_map, int fmt,
+                                   float w_scale) {
+  const long per_phase = (long)Cout * 4 * cin_pad;
+  const long total = 4 * per_phase;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int cp = (int)(e % cin_pad);
+    const int tap = (int)((e / cin_pad) & 3);
+    const int co = (int)((e / ((long)cin_pad * 4)) % Cout);
+    const int phase = (int)(e / per_phase);
+    const int py = phase >> 1, px = phase & 1, fy = tap >> 1, fx = tap & 1;
+    const int ty = py ? (fy ? 0 : 2) : (fy ? 1 : 3);
+    const int tx = px ? (fx ? 0 : 2) : (fx ? 1 : 3);
+    const int ci = chan_map ? chan_map[cp] : (cp < Cin ? cp : -1);
+    float v = 0.f;
+    if (ci >= 0 && ci < Cin) v = w[(((long)ci * Cout + co) * 4 + ty) * 4 + tx];
+    plane_t h, l;
+    split16(v * w_scale, fmt, h, l);
+    whi[e] = h;
+    if (wlo) wlo[e] = l;
+  }
+}
+
 // Picks the (nb, bh, bw) pixel tile with the fewest wasted accumulator rows.
 static void pick_tile(int N, int Ho, int Wo, int& nb, int& bh, int& bw) {
   double best = -1.0;
@@ -919,4 +945,18 @@ extern "C" int shineon_pack_conv_weight(const float* w, void* w_hi, void* w_lo, 
   pack_conv_weight_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, (plane_t*)w_hi, (plane_t*)w_lo,
                                                                        Cout, Cin, kh, kw, cin_pad, chan_map, transpose_io, plane_fmt, w_scale);
   return after_launch("pack_conv_weight_kernel");
+}
+
+extern "C" int shineon_pack_deconv4x4s2_weight(const float* w, void* w_hi, void* w_lo, int Cin, int Cout, int cin_pad,
+                                               const int32_t* chan_map, int plane_fmt, float w_scale, shineon_stream_t stream) {
+  SHINEON_REQUIRE(plane_fmt == SHINEON_FMT_BF16 || plane_fmt == SHINEON_FMT_FP16, "pack_deconv4x4s2_weight: plane_fmt %d", plane_fmt);
+  SHINEON_REQUIRE(w && w_hi && Cin > 0 && Cout > 0 && cin_pad >= 1, "pack_deconv4x4s2_weight: bad arguments");
+  SHINEON_REQUIRE(chan_map != nullptr || cin_pad >= Cin, "pack_deconv4x4s2_weight: cin_pad < Cin");
+  if (w_scale == 0.f) w_scale = 1.f;
+  long total = 16l * Cout * cin_pad;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_deconv4x4s2_weight_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, (plane_t*)w_hi, (plane_t*)w_lo, Cout, Cin,
+                                                                              cin_pad, chan_map, plane_fmt, w_scale);
+  return after_launch("pack_deconv4x4s2_weight_kernel");
 }

@@ -241,30 +241,42 @@ __global__ void __launch_bounds__(256)
     wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad, const int32_t* __restrict__ chan_map,
                         int splits, int Cout, int taps, int cin_pad, int Cin, int kh, int kw, int mode, float alpha,
                         float beta) {
-  const long total = (long)Cout * taps * cin_pad;
-  const long split_stride = total;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const int cp = (int)(e % cin_pad);
-    const int tap = (int)((e / cin_pad) % taps);
-    const int co = (int)(e / ((long)cin_pad * taps));
-    long o;
-    if (mode == 1) {
+  const long split_stride = (long)Cout * taps * cin_pad;
+  if (mode == 1) {  // im2col'd first layer: small, one element per thread
+    const long total = (long)Cout * cin_pad;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+      const int cp = (int)(e % cin_pad);
+      const int co = (int)(e / cin_pad);
       if (cp >= kh * kw * Cin) continue;
       const int t = cp / Cin, ci = cp - t * Cin;
-      o = ((long)co * Cin + ci) * kh * kw + t;
-    } else {
-      const int ci = chan_map ? chan_map[cp] : (cp < Cin ? cp : -1);
-      if (ci < 0 || ci >= Cin) continue;
+      const long o = ((long)co * Cin + ci) * kh * kw + t;
+      float s = 0.f;
+      for (int k = 0; k < splits; ++k) s += ws[k * split_stride + e];
+      grad[o] = beta == 0.f ? alpha * s : fmaf(beta, grad[o], alpha * s);
+    }
+    return;
+  }
+  // one thread per (co, packed channel): reads are coalesced over the channel for every tap, the taps of one
+  // (co, ci) are contiguous in the OIHW gradient
+  const long total = (long)Cout * cin_pad;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int cp = (int)(e % cin_pad);
+    const int co = (int)(e / cin_pad);
+    const int ci = chan_map ? chan_map[cp] : (cp < Cin ? cp : -1);
+    if (ci < 0 || ci >= Cin) continue;
+    const float* src = ws + ((long)co * taps) * cin_pad + cp;
+    for (int tap = 0; tap < taps; ++tap) {
+      float s = 0.f;
+      for (int k = 0; k < splits; ++k) s += src[k * split_stride + (long)tap * cin_pad];
+      long o;
       if (mode == 0) {
         o = ((long)co * Cin + ci) * taps + tap;
       } else {
         const int fy = tap / kw, fx = tap - fy * kw;
         o = (((long)ci * Cout + co) * kh + (kh - 1 - fy)) * kw + (kw - 1 - fx);
       }
+      grad[o] = beta == 0.f ? alpha * s : fmaf(beta, grad[o], alpha * s);
     }
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += ws[k * split_stride + e];
-    grad[o] = beta == 0.f ? alpha * s : fmaf(beta, grad[o], alpha * s);
   }
 }
 
@@ -452,7 +464,7 @@ extern "C" int shineon_conv2d_wgrad(const shineon_conv2d_wgrad_params* p, shineo
                : launch_wgrad<64, false>(tGh, tGl, tXh, tXl, a, p->plane_fmt, stream);
   if (rc) return rc;
   {
-    const long total_e = (long)p->Cout * a.taps * p->cin_pad;
+    const long total_e = (long)p->Cout * p->cin_pad;
     long blocks = (total_e + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(a.ws, p->grad_w, p->chan_map, a.splits, p->Cout, a.taps, p->cin_pad,

@@ -14,7 +14,8 @@ def bump_weights_epoch():
 
 def params_signature(module):
     """Cheap change detector for a module's parameters/buffers: (data_ptr, _version) of every tensor."""
-    sig = [WEIGHTS_EPOCH[0]]
+    # frozen modules (the VGG19 slices of the perceptual loss) are never touched by the optimiser
+    sig = [WEIGHTS_EPOCH[0] if any(p.requires_grad for p in module.parameters()) else -1]
     for t in list(module.parameters()) + list(module.buffers()):
         sig.append((t.data_ptr(), t._version, t.device.index))
     return tuple(sig)

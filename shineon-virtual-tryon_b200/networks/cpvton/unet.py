@@ -156,11 +156,17 @@ class UnetSkipConnectionBlock(nn.Module):
             c_skip = sub._parts["downconv"].in_channels
             c_xp = sub._parts["upconv"].out_channels
             p_skip, p_xp = ops.cpad64(c_skip), ops.cpad64(c_xp)
-            cmap = [-1] * (p_skip + p_xp)
-            for c in range(c_skip):
-                cmap[c] = c
-            for c in range(c_xp):
-                cmap[p_skip + c] = c_skip + c
+            # device-resident once per block: re-packing after every optimiser step must not copy from the host
+            # (the training step is CUDA-graph captured)
+            dev = uc.weight.device
+            if getattr(self, "_cmap_dev", None) is None or self._cmap_dev.device != dev:
+                cm = [-1] * (p_skip + p_xp)
+                for c in range(c_skip):
+                    cm[c] = c
+                for c in range(c_xp):
+                    cm[p_skip + c] = c_skip + c
+                self._cmap_dev = torch.as_tensor(cm, dtype=torch.int32, device=dev)
+            cmap = self._cmap_dev
             d["up_tap"] = None
             if self.outermost and uc.out_channels <= 8 and isinstance(pr["upnorm"], nn.InstanceNorm2d):
                 # few output channels: tap-stacked 1x1 GEMM + col2im (the activation is read once, not once per tap)
@@ -172,7 +178,7 @@ class UnetSkipConnectionBlock(nn.Module):
             d["up"] = ops.PackedConv(uc.weight, uc.bias, stride=1, pad=1, prec=prec)
         d["cmap_up"] = None
         if sub is not None:
-            d["cmap_up"] = torch.as_tensor(cmap, dtype=torch.int32, device=uc.weight.device)
+            d["cmap_up"] = cmap
         d["up_dgrad"] = d["down_dgrad"] = None  # packed lazily by _pack_bwd (training only)
         for key, norm in (("down_bn", pr["downnorm"]), ("up_bn", pr["upnorm"])):
             d[key] = None

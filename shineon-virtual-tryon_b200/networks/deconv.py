@@ -16,14 +16,37 @@ class PackedDeconv4x4s2:
     def __init__(self, weight, bias=None, cin_pad=None, prec=None, chan_map=None):
         # weight: [Cin, Cout, 4, 4] (nn.ConvTranspose2d layout)
         assert weight.shape[2] == 4 and weight.shape[3] == 4
-        self.Cout = weight.shape[1]
-        w = weight.detach().float().permute(1, 0, 2, 3)  # -> [Cout, Cin, 4, 4]
+        Cin, Cout = weight.shape[0], weight.shape[1]
+        self.Cout = Cout
+        fmt, split = ops.resolve_precision(prec)
+        weight = ops._req(weight.detach().float().contiguous(), name="weight")
+        cin_pad = ops.cpad64(Cin) if cin_pad is None else cin_pad
+        dev = weight.device
+        w_hi = torch.empty(4, Cout, 4, cin_pad, dtype=ops._DTYPES[fmt], device=dev)
+        w_lo = torch.empty_like(w_hi) if split else None
+        w_scale = 1.0
+        if fmt == ops._lib.FMT_FP16:  # keep hi/lo out of the fp16 subnormals (see ops.PackedConv)
+            amax = float(weight.abs().max())
+            if amax > 0:
+                import math
+
+                w_scale = 2.0 ** math.floor(math.log2(16384.0 / amax))
+        cm = None
+        if chan_map is not None:
+            cm = torch.as_tensor(chan_map, dtype=torch.int32, device=dev).contiguous()
+            assert cm.numel() == cin_pad
+        ops.check(ops._lib.load().shineon_pack_deconv4x4s2_weight(ops._p(weight), ops._p(w_hi), ops._p(w_lo), Cin, Cout,
+                                                                  cin_pad, ops._p(cm), fmt, w_scale, ops._stream()),
+                  "shineon_pack_deconv4x4s2_weight")
+        b = None if bias is None else ops._req(bias.detach().float().contiguous(), name="bias")
         self.phases = []
         for py in (0, 1):
             for px in (0, 1):
-                wk = w[:, :, _TAPS[py]][:, :, :, _TAPS[px]].contiguous()
-                pc = ops.PackedConv(wk, bias, stride=1, pad_hw=(1 - py, 1 - px), cin_pad=cin_pad, prec=prec,
-                                    chan_map=chan_map)
+                pc = ops.PackedConv.__new__(ops.PackedConv)
+                pc.fmt, pc.Cout, pc.Cin, pc.kh, pc.kw, pc.stride = fmt, Cout, Cin, 2, 2, 1
+                pc.pad_h, pc.pad_w, pc.cin_pad = 1 - py, 1 - px, cin_pad
+                pc.w_hi, pc.w_lo = w_hi[py * 2 + px], (w_lo[py * 2 + px] if split else None)
+                pc.acc_scale, pc.bias, pc.transposed = 1.0 / w_scale, b, False
                 self.phases.append((py, px, pc))
 
     def __call__(self, x, *, post_act=None, act_param=0.0, want_f32=False, want_planes=False, out_f32=None,

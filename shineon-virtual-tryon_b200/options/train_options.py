@@ -13,5 +13,10 @@ class TrainOptions(BaseOptions):
         parser.add_argument("--decay_epochs", type=int, default=5, help="number of epochs to linearly decay the learning rate")
         parser.add_argument("--accumulated_batches", type=int, default=1,
                             help="number of batch gradients to accumulate before calling optimizer.step()")
+        parser.add_argument("--b200_train_precision", choices=("bf16x3", "bf16"), default="bf16",
+                            help="numeric mode of the native training step: bf16 = single bf16 tensor-core products with "
+                                 "fp32 accumulation / statistics / master weights (the reference's default is AMP fp16); "
+                                 "bf16x3 = fp32-grade split products (the parity-tested mode)")
+        parser.add_argument("--max_steps", type=int, default=None, help="stop after this many optimiser steps")
         self.is_train = True
         return parser

@@ -32,7 +32,13 @@ def backward_order(unet_generator):
 
 class Trainer:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, accumulated_batches=1, bucket_bytes=32 << 20,
-                 lr_lambda=None):
+                 lr_lambda=None, cuda_graph=False, graph_warmup=2):
+        """cuda_graph=True: after `graph_warmup` eager micro-batches the whole training step (forward, losses, backward:
+        ~450 launches, launch-bound at the recipe's batch 4) is captured once into a CUDA graph and replayed; the batch
+        is copied into static buffers.  The gradient all-reduce then runs after the replay instead of inside the
+        backward (bucketed, asynchronous, but not overlapped)."""
+        self.cuda_graph, self.graph_warmup = bool(cuda_graph), int(graph_warmup)
+        self._graph, self._static_batch, self._static_res = None, None, None
         self.model = model
         ordered = [p for p in backward_order(model.unet) if p.requires_grad]
         seen = {id(p) for p in ordered}
@@ -65,6 +71,15 @@ class Trainer:
         """One micro-batch: forward + losses + backward (gradients accumulate); on every `accumulated_batches`-th call
         the gradient all-reduce (overlapped with that backward) and the fused Adam step.  Returns the step's result."""
         last = (self.micro + 1) % self.accumulated_batches == 0
+        if self.cuda_graph and self.micro >= self.graph_warmup:
+            res = self._replay(batch, batch_idx)
+            self.micro += 1
+            if last:
+                self.reducer.start()
+                inv_world = self.reducer.finish()
+                self.optimizer_step(inv_world / self.accumulated_batches)
+                self.zero_grad()
+            return res
         if last:
             self.reducer.begin_overlap()
             unet_mod.GRAD_READY_HOOK = self.reducer.mark_ready
@@ -78,6 +93,20 @@ class Trainer:
             self.optimizer_step(inv_world / self.accumulated_batches)
             self.zero_grad()
         return res
+
+    def _replay(self, batch, batch_idx):
+        tensors = {k: v for k, v in batch.items() if isinstance(v, torch.Tensor)}
+        if self._graph is None:
+            self._static_batch = {k: v.clone() for k, v in tensors.items()}
+            self._graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(self._graph):
+                self._static_res = self.model.training_step(self._static_batch, batch_idx)
+            # the capture only recorded the work: replay below runs it for this batch
+        for k, v in tensors.items():
+            self._static_batch[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        return self._static_res
 
     def optimizer_step(self, grad_scale=1.0):
         self.steps += 1

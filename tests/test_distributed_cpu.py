@@ -99,3 +99,62 @@ def test_flat_grad_allreduce_is_mean_over_ranks():
     for _, means, nb in res:
         assert nb > 1
         assert means == [1.5 * (i + 1) for i in range(3)]  # mean of (rank+1)*(i+1) over ranks {0,1}
+
+
+def _overlap_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from shineon_virtual_tryon_b200 import distributed as d
+
+    d.init_process_group("gloo")
+    params = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 11, 3, 8, 6)]
+    red = d.FlatGradAllReducer(params, bucket_bytes=4 * 8)  # 8-element buckets: 33 elements -> 5 buckets
+    red.begin_overlap()
+    launched = []
+    # the backward pass reports parameters in buffer order (training.backward_order); buckets go out as they fill
+    for i, p in enumerate(params):
+        red.grad_view(i).fill_(float((rank + 1) * (i + 1)))
+        red.mark_ready([p])
+        launched.append(red._next_bucket)
+    scale = red.end_overlap()
+    vals = [(red.grad_view(i) * scale).unique().tolist() for i in range(len(params))]
+    out.put((rank, launched, vals, len(red.buckets)))
+    torch.distributed.destroy_process_group()
+
+
+def test_overlapped_bucket_launch_order_and_result():
+    """Row U7: buckets are all-reduced as soon as the last gradient they contain is final, and the result is the mean."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, launched, vals, nb in res:
+        assert nb == 5
+        # parameter ends at 5, 16, 19, 27, 33 -> complete buckets after each: 0, 2, 2, 3, 5
+        assert launched == [0, 2, 2, 3, 5]
+        assert vals == [[1.5 * (i + 1)] for i in range(5)]
+
+
+def test_backward_order_covers_every_unet_parameter_once():
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from shineon_virtual_tryon_b200.models.unet_mask_model import UnetMaskModel
+    from shineon_virtual_tryon_b200.training import backward_order
+    from tests.util import make_hparams
+
+    m = UnetMaskModel(make_hparams(is_train=True))
+    order = backward_order(m.unet)
+    assert len({id(p) for p in order}) == len(order) == len(list(m.unet.parameters()))
+    # first finalised: the outermost up-conv (the last layer of the forward); last: the outermost down-conv
+    assert order[0] is m.unet.model._parts["upconv"].weight and order[-2] is m.unet.model._parts["downconv"].weight

@@ -22,13 +22,25 @@ def test_options_defaults_and_synonyms():
     assert (o.self_attn, o.activation, o.flow_warp, o.n_frames_total, o.n_frames_now, o.pen_flow_mask) == (True, "gelu", True, 5, 5, 1.0)
 
 
-def test_train_entry_point_builds_model_and_stops_loudly():
+def test_train_entry_point_rejects_models_without_native_training():
     sys.path.insert(0, ROOT)
     import train
 
     with pytest.raises(SystemExit) as e:
-        train.main(["--model", "unet", "--name", "x", "--self_attn", "--activation", "gelu"])
-    assert "not implemented" in str(e.value)
+        train.main(["--model", "gmm", "--name", "x"])
+    assert "U-Net try-on stage" in str(e.value)
+
+
+@pytest.mark.gpu
+def test_train_entry_point_runs_on_synthetic_data(cuda, tmp_path):
+    sys.path.insert(0, ROOT)
+    import train
+
+    rc = train.main(["--model", "unet", "--name", "smoke", "--self_attn", "--activation", "gelu", "-b", "2",
+                     "--synthetic_samples", "4", "--accumulated_batches", "2", "--max_steps", "2",
+                     "--experiments_dir", str(tmp_path)])
+    assert rc == 0
+    assert os.path.exists(os.path.join(str(tmp_path), "smoke", "final.ckpt"))
 
 
 @pytest.mark.gpu

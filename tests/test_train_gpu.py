@@ -72,3 +72,20 @@ def test_training_reduces_the_loss(cuda):
     assert losses[-1] < losses[0], losses
     # gradient accumulation: two half-weighted micro-batches == one step on the same data
     assert tr.steps == 6
+
+
+def test_cuda_graph_training_matches_eager(cuda):
+    """The captured training step replays to the same losses as the eager one (same kernels, same order)."""
+    from shineon_virtual_tryon_b200.training import Trainer
+
+    name = "train_gelu_attn"
+    batch = _to_cuda(cases.train_batch(name))
+    runs = []
+    for graph in (False, True):
+        model, _ = build_model("unet_mask", **cases.TRAIN_CASES[name][0])
+        model.train()
+        tr = Trainer(model, lr=2e-4, cuda_graph=graph, graph_warmup=1)
+        runs.append([tr.train_batch(batch, i)["loss"].item() for i in range(5)])
+    for a, b in zip(*runs):
+        assert abs(a - b) <= 1e-4 * abs(a) + 1e-5, runs
+    assert runs[1][-1] < runs[1][0]
