@@ -40,6 +40,12 @@ def parse():
     ap.add_argument("--clips", type=int, default=16, help="5-frame clips per step per GPU")
     ap.add_argument("--fast", action="store_true", help="also report the bf16x3 / fp16 / bf16 modes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="tryon", choices=["tryon", "train"],
+                    help="tryon = BASELINE configs[2] (the headline; default); train = configs[4]: U-Net stage training step, "
+                         "data-parallel over the GPUs with the NCCL gradient all-reduce")
+    ap.add_argument("--train-batch", type=int, default=4, help="samples per GPU per optimiser step (recipe: 4)")
+    ap.add_argument("--train-precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--train-eager", action="store_true", help="no CUDA graph: all-reduce overlapped inside the backward")
     ap.add_argument("--cpu-clips", type=int, default=1, help="clips per CPU-baseline step (bounded sample)")
     return ap.parse_args()
 
@@ -202,9 +208,184 @@ def cpu_tryon_fps(clips, min_seconds=10.0, max_iters=20, warmup=1, exact_steps=N
             f"{cores} of {ncpu} host threads (fastest of a sweep)", med)
 
 
+# ------------------------------------------------------------------------------------------- training workload
+TRAIN_METRIC = "train samples/sec @256x192 (U-Net stage: forward + L1/VGG/mask losses + backward + Adam)"
+
+
+def train_models():
+    import argparse
+
+    import torch
+
+    from shineon_virtual_tryon_b200.models.unet_mask_model import UnetMaskModel
+    from shineon_virtual_tryon_b200.networks.attention.sagan import SelfAttention
+
+    torch.manual_seed(420)
+    hp = argparse.Namespace(n_frames_total=1, n_frames_now=1, person_inputs=["agnostic", "densepose"], cloth_inputs=["cloth"],
+                            ngf=64, self_attn=True, num_attn=2, flow_warp=False, activation="gelu", is_train=True,
+                            pen_flow_mask=1.0, display_count=10 ** 9, lr=1e-4, fine_height=H, fine_width=W)
+    m = UnetMaskModel(hp).train()
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, SelfAttention):
+                mod.gamma.uniform_(0.5, 1.5)
+        for name, p in m.criterionVGG.named_parameters():  # stands in for the ImageNet weights (no network): He init
+            if p.dim() == 4:
+                torch.nn.init.kaiming_normal_(p, nonlinearity="relu")
+    return m, hp
+
+
+def train_batch(B, seed, pinned=False):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    b = dict(image=torch.rand(B, 1, 3, H, W, generator=g) * 2 - 1, prev_image=torch.rand(B, 1, 3, H, W, generator=g) * 2 - 1,
+             cloth=torch.rand(B, 1, 3, H, W, generator=g) * 2 - 1, agnostic=torch.randn(B, 1, 4, H, W, generator=g),
+             densepose=torch.randn(B, 1, 3, H, W, generator=g),
+             cloth_mask=(torch.rand(B, 1, 1, H, W, generator=g) > 0.5).float())
+    return {k: v.pin_memory() for k, v in b.items()} if pinned else b
+
+
+def cpu_train_sps(B, iters=2, warmup=1):
+    """Oracle port of the reference training step (oracle/train.py == UnetMaskModel.training_step + loss.backward(),
+    pinned against the reference by tests/golden/train_*.npz) on the host cores."""
+    import torch
+
+    from oracle import train as otrain
+
+    m, hp = train_models()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    batch = {k: v.reshape(v.shape[0], -1, H, W) for k, v in train_batch(B, 7).items()}
+    kw = dict(person_inputs=hp.person_inputs, cloth_inputs=hp.cloth_inputs, n_frames=1, flow_warp=False, num_downs=6,
+              num_attention=2, use_self_attn=True, act="gelu")
+    ncpu = os.cpu_count() or 1
+    cores = min(ncpu, 32)
+    torch.set_num_threads(cores)
+    times = []
+    for i in range(warmup + iters):
+        t0 = time.perf_counter()
+        otrain.tom_training_grads(sd, batch, **kw)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return B / med, cores, f"{B} samples/step, {len(times)} timed iterations, median; {cores} of {ncpu} host threads", med
+
+
+def run_train(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from shineon_virtual_tryon_b200 import _lib, distributed, ops
+    from shineon_virtual_tryon_b200.training import Trainer
+
+    os.environ["NCCL_DEBUG"] = os.environ.get("SHINEON_NCCL_DEBUG", "WARN")
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed.init_process_group("nccl", device=dev)
+    model, hp = train_models()
+    model = model.to(dev)
+    model.set_train_precision(args.train_precision)
+    B = args.train_batch
+    tr = Trainer(model, lr=1e-4, cuda_graph=not args.train_eager)
+    host = train_batch(B, 100 + rank, pinned=True)
+    devb = {k: v.to(dev) for k, v in host.items()}
+    for i in range(max(args.warmup, 3)):
+        tr.train_batch(devb, i)
+
+    def timed(fn, steps, sampler=None):
+        distributed.barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        distributed.barrier()
+        clocks = sampler.stop() if sampler else None
+        return distributed.max_over_ranks(e0.elapsed_time(e1), dev), clocks
+
+    l0 = _lib.launch_count()
+    ms, clocks = timed(lambda i: tr.train_batch(devb, i), args.steps, ClockSampler(local) if rank == 0 else None)
+    replayed = not args.train_eager
+    launches = _lib.launch_count() - l0
+
+    def e2e_step(i):
+        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        res = tr.train_batch(b, i)
+        return float(res["loss"].item())  # device -> host read of the step's result
+
+    e2e_step(0)
+    ms_e2e, _ = timed(e2e_step, args.steps)
+    # roofline of the tensor-core kernels (forward / dgrad conv_igemm + conv_wgrad) on eager steps after the timed region
+    eager = Trainer.__new__(Trainer)
+    eager.__dict__.update(tr.__dict__)
+    eager.cuda_graph = False
+    eager.train_batch(devb, 0)  # first eager step after replays re-packs / re-allocates: not the one measured
+    prof = []
+    l1 = _lib.launch_count()
+    ops.PROFILE = prof
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eager.train_batch(devb, 0)
+    e1.record()
+    ops.PROFILE = None
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - l1
+    tc_ms = sum(r[1].elapsed_time(r[2]) for r in prof)
+    tc_flops = sum(r[0] for r in prof)
+    peaks, peak_src = read_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    ach = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    total = B * world * args.steps
+    line = {
+        "metric": TRAIN_METRIC, "value": total / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 tensor-core products, fp32 accumulation / statistics / master weights / Adam" if args.train_precision == "bf16"
+                 else "bf16x3 (split bf16 operands, fp32-grade)",
+        "data": "synthetic",
+        "config": {"workload": "configs[4]: train.py U-Net stage (UnetMaskModel, self-attn, GELU, InstanceNorm; VGG19 perceptual loss "
+                               "with random VGG weights), synthetic VVT batch 256x192, data-parallel, NCCL gradient all-reduce",
+                   "batch_per_gpu": B, "global_batch": B * world, "accumulated_batches": 1,
+                   "parallelism": f"dp{world} (one flat 90.6 MB f32 gradient buffer, bucketed NCCL all-reduce"
+                                  + (", overlapped with the backward)" if args.train_eager else ", after the CUDA-graph replay)"),
+                   "cuda_graph": replayed,
+                   "l2": "activations + weights + gradients per step exceed the 126 MB L2 (no flush needed)"},
+        "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in host.values())) * world, "d2h_bytes_per_step": 4 * world,
+                "ms_per_step": ms_e2e / args.steps, "api": "training.Trainer.train_batch: pinned host batch -> H2D -> step -> loss.item()"},
+        "gpu_launches": (launches if not replayed else launches_per_step * args.steps) * world,
+        "clocks": clocks,
+        "roofline": {"kernel": "conv_igemm_kernel (forward + data-gradient) and conv_wgrad_kernel (tcgen05), all launches of one step",
+                     "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                     "peak_source": f"{peak_src} bf16_tflops_sustained", "tensor_core_launches_per_step": len(prof),
+                     "algorithmic_gflop_per_sample": tc_flops / B / 1e9, "tensor_core_share_of_eager_step": tc_ms / e0.elapsed_time(e1),
+                     "measured_on": "one eager step after the timed region (CUDA events around every tensor-core launch)",
+                     "traffic": None},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            sps, cores, sample, _ = cpu_train_sps(2)
+            line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank):
     if rank != 0:
+        return
+    if args.workload == "train":
+        sps, cores, sample, med = cpu_train_sps(2, iters=max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
+        print(json.dumps({
+            "impl": "reference", "metric": TRAIN_METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[4]: U-Net stage training step, CPU oracle port (autograd)", "batch": 2},
+            "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return
     fps, cores, sample, med = cpu_tryon_fps(args.cpu_clips, warmup=args.warmup, exact_steps=args.steps)
     line = {
@@ -342,6 +523,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         run_reference(args, rank)
+    elif args.workload == "train":
+        run_train(args, rank, world)
     else:
         run_b200(args, rank, world)
 

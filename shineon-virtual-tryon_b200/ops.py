@@ -665,7 +665,14 @@ def conv2d_wgrad(g, x, grad_w, *, Cout, Cin, kh, kw, stride, pad, mode=0, chan_m
     need = lib.shineon_conv2d_wgrad_workspace_bytes(C.byref(p))
     ws = _workspace(need, grad_w.device)
     p.workspace, p.workspace_bytes = _p(ws), ws.numel()
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib.shineon_conv2d_wgrad(C.byref(p), _stream()), "shineon_conv2d_wgrad")
+    if prof is not None:
+        e1.record()
+        prof.append((2.0 * x.N * p.Ho * p.Wo * Cout * kh * kw * Cin, e0, e1, ("wgrad", x.N, x.H, x.W, Cin, x.cpad, Cout, kh, stride)))
     return grad_w
 
 
