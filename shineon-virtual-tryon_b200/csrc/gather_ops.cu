@@ -324,6 +324,284 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast paths (compile-time channel counts / padding modes).  The generic kernels above are latency- and
+// issue-bound (ncu, profiles/r01_memory_ops.md): per-channel loops expose only 16 loads per thread and the runtime
+// (C, pad) bookkeeping costs more instructions than the sampling itself.  Here every load of a thread's pixels
+// (PPT pixels x C channels x 4 taps) is issued before the first use, offsets are 32-bit, and for border padding
+// the neighbour logic collapses to two clamps (the weight of a clamped neighbour is exactly 0).
+// ---------------------------------------------------------------------------------------------
+struct TapFast {
+  // BYTE offsets of the four taps inside one channel plane, unsigned 32-bit: together with a block-uniform 64-bit
+  // plane base the loads compile to LDG [R.U32 + UR.64] — no per-tap 64-bit address arithmetic
+  unsigned o00, o01, o10, o11;
+  float w00, w01, w10, w11;
+};
+__device__ __forceinline__ void set_offsets(TapFast& t, int o00, int dx, int dy) {
+  t.o00 = (unsigned)o00 * 4u;
+  t.o01 = t.o00 + (unsigned)dx * 4u;
+  t.o10 = t.o00 + (unsigned)dy * 4u;
+  t.o11 = t.o10 + (unsigned)dx * 4u;
+}
+__device__ __forceinline__ float ldg_b(const char* __restrict__ base, unsigned byte_off) {
+  return __ldg(reinterpret_cast<const float*>(base + byte_off));
+}
+
+template <int PAD>
+__device__ __forceinline__ TapFast make_tap_fast(float gx, float gy, int Hin, int Win) {
+  float ix = ((gx + 1.f) * Win - 1.f) * 0.5f;
+  float iy = ((gy + 1.f) * Hin - 1.f) * 0.5f;
+  TapFast t;
+  if (PAD == SHINEON_PAD_BORDER) {
+    ix = fminf(fmaxf(ix, 0.f), (float)(Win - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(Hin - 1));
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+    const float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+    const int x0 = (int)fx, y0 = (int)fy;  // in [0, W-1] x [0, H-1]
+    // at the border wx1 == 0 exactly: any finite neighbour value contributes 0
+    set_offsets(t, y0 * Win + x0, x0 + 1 < Win ? 1 : 0, y0 + 1 < Hin ? Win : 0);
+    t.w00 = wx0 * wy0; t.w01 = wx1 * wy0; t.w10 = wx0 * wy1; t.w11 = wx1 * wy1;
+  } else {
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix;
+    const float wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+    const int x0 = (int)fminf(fmaxf(fx, -2.f), (float)Win + 1.f), y0 = (int)fminf(fmaxf(fy, -2.f), (float)Hin + 1.f);
+    const bool vx0 = (unsigned)x0 < (unsigned)Win, vx1 = (unsigned)(x0 + 1) < (unsigned)Win;
+    const bool vy0 = (unsigned)y0 < (unsigned)Hin, vy1 = (unsigned)(y0 + 1) < (unsigned)Hin;
+    const int cx0 = min(max(x0, 0), Win - 1), cy0 = min(max(y0, 0), Hin - 1);
+    set_offsets(t, cy0 * Win + cx0, (vx0 && vx1) ? 1 : 0, (vy0 && vy1) ? Win : 0);
+    // a tap that is out of range gets weight 0; its (clamped) address still points inside the plane
+    t.w00 = (vy0 && vx0) ? wx0 * wy0 : 0.f;
+    t.w01 = (vy0 && vx1) ? wx1 * wy0 : 0.f;
+    t.w10 = (vy1 && vx0) ? wx0 * wy1 : 0.f;
+    t.w11 = (vy1 && vx1) ? wx1 * wy1 : 0.f;
+    // when exactly one of a neighbour pair is valid the valid one must sit at the clamped address: x0 == -1 -> cx0 = 0
+    // is the "x1" tap (weight w01) and dx = 0 makes both loads hit it; same for y0 == -1
+  }
+  return t;
+}
+
+// Loads the 4 taps of C channel planes (stride `plane_stride` elements) for one pixel.
+template <int C>
+__device__ __forceinline__ void load_taps(const float* __restrict__ base, long plane_stride, const TapFast& t, float (&v)[C][4]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const char* pl = reinterpret_cast<const char*>(base + c * plane_stride);  // block-uniform
+    v[c][0] = ldg_b(pl, t.o00);
+    v[c][1] = ldg_b(pl, t.o01);
+    v[c][2] = ldg_b(pl, t.o10);
+    v[c][3] = ldg_b(pl, t.o11);
+  }
+}
+__device__ __forceinline__ void st_b(float* __restrict__ base, unsigned byte_off, float v) {
+  *reinterpret_cast<float*>(reinterpret_cast<char*>(base) + byte_off) = v;
+}
+__device__ __forceinline__ float blend_taps(const float (&v)[4], const TapFast& t) {
+  float acc = v[0] * t.w00;  // nw, ne, sw, se: ATen's accumulation order
+  acc += v[1] * t.w01;
+  acc += v[2] * t.w10;
+  acc += v[3] * t.w11;
+  return acc;
+}
+
+template <int C, int PAD, int PPT>
+__global__ void __launch_bounds__(256)
+    grid_sample_fast_kernel(const float* __restrict__ in, const float* __restrict__ grid, float* __restrict__ out,
+                            int Hin, int Win, int HWo) {
+  const int b = blockIdx.y;
+  const int HWi = Hin * Win;
+  const int p0 = blockIdx.x * (256 * PPT) + threadIdx.x;
+  const float2* gb = reinterpret_cast<const float2*>(grid) + (long)b * HWo;
+  const float* ib = in + (long)b * C * HWi;
+  float* ob = out + (long)b * C * HWo;
+  float2 g[PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) g[k] = __ldg(gb + min(p0 + k * 256, HWo - 1));
+  TapFast t[PPT];
+  float v[PPT][C][4];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    t[k] = make_tap_fast<PAD>(g[k].x, g[k].y, Hin, Win);
+    load_taps<C>(ib, HWi, t[k], v[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int p = p0 + k * 256;
+    if (p < HWo) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) st_b(ob + (long)c * HWo, (unsigned)p * 4u, blend_taps(v[k][c], t[k]));
+    }
+  }
+}
+
+template <int C, int PPT>
+__global__ void __launch_bounds__(256)
+    resample2d_fast_kernel(const float* __restrict__ in1, const float* __restrict__ flow, float* __restrict__ out,
+                           int H, int W) {
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  const int p0 = blockIdx.x * (256 * PPT) + threadIdx.x;
+  const float* fb = flow + (long)b * 2 * HW;
+  const float* ib = in1 + (long)b * C * HW;
+  float* ob = out + (long)b * C * HW;
+  float dx[PPT], dy[PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int p = min(p0 + k * 256, HW - 1);
+    dx[k] = __ldg(fb + p);
+    dy[k] = __ldg(fb + HW + p);
+  }
+  TapFast t[PPT];
+  float v[PPT][C][4];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int p = min(p0 + k * 256, HW - 1);
+    const int y = p / W, x = p - y * W;
+    const float xf = (float)x + dx[k], yf = (float)y + dy[k];
+    const float fx = floorf(xf), fy = floorf(yf);
+    const float alpha = xf - fx, beta = yf - fy;  // resample2d_kernel.cu:42-43
+    const float cfx = fminf(fmaxf(fx, -4.f), (float)W + 4.f), cfy = fminf(fmaxf(fy, -4.f), (float)H + 4.f);
+    const int xL = max(min((int)cfx, W - 1), 0), xR = max(min((int)cfx + 1, W - 1), 0);
+    const int yT = max(min((int)cfy, H - 1), 0), yB = max(min((int)cfy + 1, H - 1), 0);
+    set_offsets(t[k], yT * W + xL, xR - xL, (yB - yT) * W);
+    t[k].w00 = (1.f - alpha) * (1.f - beta); t[k].w01 = alpha * (1.f - beta);
+    t[k].w10 = (1.f - alpha) * beta; t[k].w11 = alpha * beta;
+    load_taps<C>(ib, HW, t[k], v[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int p = p0 + k * 256;
+    if (p < HW) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {  // same accumulation order as resample2d_kernel.cu:56-59 (0 + w*v ...)
+        float a = 0.f;
+        a += t[k].w00 * v[k][c][0];
+        a += t[k].w01 * v[k][c][1];
+        a += t[k].w10 * v[k][c][2];
+        a += t[k].w11 * v[k][c][3];
+        st_b(ob + (long)c * HW, (unsigned)p * 4u, a);
+      }
+    }
+  }
+}
+
+// Batched fused TPS + grid_sample, specialised: N control points, up to three inputs with compile-time channel
+// counts / padding (C == 0: absent).  Two pixels per thread share every (W_X, W_Y) shared-memory read; the two
+// coordinate sums advance with one packed FFMA2 per control point.
+template <int N, int C0, int P0, int C1, int P1, int C2, int P2>
+__global__ void __launch_bounds__(128)
+    tps_grid_sample_fast_kernel(const float* __restrict__ theta, TpsTablesDev t, FusedSampleArgs a,
+                                float* __restrict__ grid_out, int B, int H, int W, int chunk) {
+  __shared__ float sQ[kTpsChunk][2 * N];
+  __shared__ float2 sWxy[kTpsChunk][N];
+  __shared__ float sA[kTpsChunk][6];
+  __shared__ float sP[2 * N];
+  const int b0 = blockIdx.y * chunk;
+  const int nb = min(chunk, B - b0);
+  constexpr int L = N + 3;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    sP[i] = t.P_X[i];
+    sP[N + i] = t.P_Y[i];
+  }
+  for (int e = threadIdx.x; e < nb * 2 * N; e += blockDim.x) {
+    const int bi = e / (2 * N), k = e - bi * 2 * N;
+    sQ[bi][k] = theta[(long)(b0 + bi) * 2 * N + k] + (k < N ? t.P_X[k] : t.P_Y[k - N]);  // warp.py:207-210
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nb * 2 * L; e += blockDim.x) {
+    const int bi = e / (2 * L), r = e - bi * 2 * L;
+    const int xy = r / L, row = r - xy * L;
+    const float* q = sQ[bi] + xy * N;
+    const float* li = t.Li + row * L;
+    float acc = 0.f;
+    for (int k = 0; k < N; ++k) acc = fmaf(li[k], q[k], acc);
+    if (row < N) {
+      if (xy == 0) sWxy[bi][row].x = acc; else sWxy[bi][row].y = acc;
+    } else {
+      sA[bi][xy * 3 + (row - N)] = acc;
+    }
+  }
+  __syncthreads();
+  const int HW = H * W;
+  // two pixels per thread, 128 apart (coalesced per warp)
+  const int pA = blockIdx.x * 256 + threadIdx.x, pB = pA + 128;
+  if (pA >= HW) return;
+  const bool hasB = pB < HW;
+  const int pBc = hasB ? pB : pA;
+  const int yA = pA / W, xA = pA - yA * W, yB = pBc / W, xB = pBc - yB * W;
+  const float pxA = t.grid_X[xA], pyA = t.grid_Y[yA], pxB = t.grid_X[xB], pyB = t.grid_Y[yB];
+  float UA[N], UB[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const float cx = sP[n], cy = sP[N + n];
+    float dx = pxA - cx, dy = pyA - cy;
+    float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (d2 == 0.f) d2 = 1.f;  // warp.py:290
+    UA[n] = d2 * logf(d2);
+    dx = pxB - cx; dy = pyB - cy;
+    d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (d2 == 0.f) d2 = 1.f;
+    UB[n] = d2 * logf(d2);
+  }
+  for (int bi = 0; bi < nb; ++bi) {
+    float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const float2 w = sWxy[bi][n];
+      sa = __ffma2_rn(w, make_float2(UA[n], UA[n]), sa);  // (sx, sy) += (W_X[n], W_Y[n]) * U_n: same fp32 FMAs, one issue
+      sb = __ffma2_rn(w, make_float2(UB[n], UB[n]), sb);
+    }
+    const float a0 = sA[bi][0], a1 = sA[bi][1], a2 = sA[bi][2], a3 = sA[bi][3], a4 = sA[bi][4], a5 = sA[bi][5];
+    const float gxA = a0 + a1 * pxA + a2 * pyA + sa.x, gyA = a3 + a4 * pxA + a5 * pyA + sa.y;  // warp.py:303-316
+    const float gxB = a0 + a1 * pxB + a2 * pyB + sb.x, gyB = a3 + a4 * pxB + a5 * pyB + sb.y;
+    const int b = b0 + bi;
+    if (grid_out) {
+      reinterpret_cast<float2*>(grid_out)[(long)b * HW + pA] = make_float2(gxA, gyA);
+      if (hasB) reinterpret_cast<float2*>(grid_out)[(long)b * HW + pB] = make_float2(gxB, gyB);
+    }
+    // all loads of both pixels first, then blends + stores
+    float v0[2][C0 > 0 ? C0 : 1][4], v1[2][C1 > 0 ? C1 : 1][4], v2[2][C2 > 0 ? C2 : 1][4];
+    TapFast t0[2], t1[2], t2[2];
+    if (C0 > 0) {
+      t0[0] = make_tap_fast<P0>(gxA, gyA, H, W); t0[1] = make_tap_fast<P0>(gxB, gyB, H, W);
+      load_taps<(C0 > 0 ? C0 : 1)>(a.in[0] + (long)b * C0 * HW, HW, t0[0], v0[0]);
+      load_taps<(C0 > 0 ? C0 : 1)>(a.in[0] + (long)b * C0 * HW, HW, t0[1], v0[1]);
+    }
+    if (C1 > 0) {
+      if (P1 == P0 && C0 > 0) { t1[0] = t0[0]; t1[1] = t0[1]; }
+      else { t1[0] = make_tap_fast<P1>(gxA, gyA, H, W); t1[1] = make_tap_fast<P1>(gxB, gyB, H, W); }
+      load_taps<(C1 > 0 ? C1 : 1)>(a.in[1] + (long)b * C1 * HW, HW, t1[0], v1[0]);
+      load_taps<(C1 > 0 ? C1 : 1)>(a.in[1] + (long)b * C1 * HW, HW, t1[1], v1[1]);
+    }
+    if (C2 > 0) {
+      if (P2 == P1 && C1 > 0) { t2[0] = t1[0]; t2[1] = t1[1]; }
+      else if (P2 == P0 && C0 > 0) { t2[0] = t0[0]; t2[1] = t0[1]; }
+      else { t2[0] = make_tap_fast<P2>(gxA, gyA, H, W); t2[1] = make_tap_fast<P2>(gxB, gyB, H, W); }
+      load_taps<(C2 > 0 ? C2 : 1)>(a.in[2] + (long)b * C2 * HW, HW, t2[0], v2[0]);
+      load_taps<(C2 > 0 ? C2 : 1)>(a.in[2] + (long)b * C2 * HW, HW, t2[1], v2[1]);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k == 1 && !hasB) break;
+      const unsigned pb = (unsigned)(k == 0 ? pA : pB) * 4u;
+      if (C0 > 0) {
+#pragma unroll
+        for (int c = 0; c < C0; ++c) st_b(a.out[0] + ((long)b * C0 + c) * HW, pb, blend_taps(v0[k][c], t0[k]));
+      }
+      if (C1 > 0) {
+#pragma unroll
+        for (int c = 0; c < C1; ++c) st_b(a.out[1] + ((long)b * C1 + c) * HW, pb, blend_taps(v1[k][c], t1[k]));
+      }
+      if (C2 > 0) {
+#pragma unroll
+        for (int c = 0; c < C2; ++c) st_b(a.out[2] + ((long)b * C2 + c) * HW, pb, blend_taps(v2[k][c], t2[k]));
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Resample2d  (resample2d_kernel.cu).  kernel_size == 1 (the only value the reference uses).
 // One thread per output pixel; the flow is read once and reused for every channel.
@@ -542,6 +820,24 @@ extern "C" int shineon_grid_sample_fwd(const float* input, const float* grid, fl
   SHINEON_REQUIRE(padding_mode == SHINEON_PAD_ZEROS || padding_mode == SHINEON_PAD_BORDER, "grid_sample: padding_mode %d", padding_mode);
   SHINEON_REQUIRE(B >= 0 && C > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && B <= 65535, "grid_sample: bad shape");
   if (B == 0) return SHINEON_OK;
+  if (C <= 4 && (long)C * Hin * Win < (1l << 31)) {
+    constexpr int PPT = 2;  // measured on B200 (B=512): PPT 1 / 2 / 4 -> 0.64 / 0.68 / 0.53 of HBM peak
+    const dim3 g(cdiv(Hout * Wout, 256 * PPT), B);
+    cudaStream_t st = (cudaStream_t)stream;
+#define SHINEON_GS(C_)                                                                                                       \
+  if (padding_mode == SHINEON_PAD_BORDER)                                                                                   \
+    grid_sample_fast_kernel<C_, SHINEON_PAD_BORDER, PPT><<<g, 256, 0, st>>>(input, grid, out, Hin, Win, Hout * Wout);       \
+  else                                                                                                                      \
+    grid_sample_fast_kernel<C_, SHINEON_PAD_ZEROS, PPT><<<g, 256, 0, st>>>(input, grid, out, Hin, Win, Hout * Wout)
+    switch (C) {
+      case 1: SHINEON_GS(1); break;
+      case 2: SHINEON_GS(2); break;
+      case 3: SHINEON_GS(3); break;
+      default: SHINEON_GS(4); break;
+    }
+#undef SHINEON_GS
+    return after_launch("grid_sample_fast_kernel");
+  }
   grid_sample_kernel<<<dim3(cdiv(Hout * Wout, 256 * kPPT), B), 256, 0, (cudaStream_t)stream>>>(input, grid, out, C, Hin, Win,
                                                                                               Hout, Wout, padding_mode);
   return after_launch("grid_sample_kernel");
@@ -562,6 +858,29 @@ extern "C" int shineon_tps_grid_sample_fwd(const float* theta, const shineon_tps
   a.in[1] = in1; a.out[1] = out1; a.C[1] = C1; a.pad[1] = pad1;
   a.in[2] = in2; a.out[2] = out2; a.C[2] = C2; a.pad[2] = pad2;
   const int N = tps->grid_size * tps->grid_size;
+  if (N == 25) {  // the ShineOn configuration (grid_size 5) with the two input signatures WarpModel uses
+    const int chunk = B >= 128 ? kTpsChunk : (B >= 32 ? 8 : 2);
+    dim3 grid(cdiv(H * W, 256), cdiv(B, chunk));
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int BD = SHINEON_PAD_BORDER, ZR = SHINEON_PAD_ZEROS;
+    const bool i0 = in0 && C0 == 3 && pad0 == BD;
+    if (i0 && !in1 && !in2) {
+      tps_grid_sample_fast_kernel<25, 3, BD, 0, 0, 0, 0><<<grid, 128, 0, st>>>(theta, to_dev(tps), a, grid_out, B, H, W, chunk);
+      return after_launch("tps_grid_sample_fast_kernel");
+    }
+    if (i0 && in1 && C1 == 3 && pad1 == ZR && !in2) {  // cloth + an RGB "mask" / grid image
+      tps_grid_sample_fast_kernel<25, 3, BD, 3, ZR, 0, 0><<<grid, 128, 0, st>>>(theta, to_dev(tps), a, grid_out, B, H, W, chunk);
+      return after_launch("tps_grid_sample_fast_kernel");
+    }
+    if (i0 && in1 && C1 == 1 && pad1 == ZR && !in2) {
+      tps_grid_sample_fast_kernel<25, 3, BD, 1, ZR, 0, 0><<<grid, 128, 0, st>>>(theta, to_dev(tps), a, grid_out, B, H, W, chunk);
+      return after_launch("tps_grid_sample_fast_kernel");
+    }
+    if (i0 && in1 && C1 == 1 && pad1 == ZR && in2 && C2 == 3 && pad2 == ZR) {
+      tps_grid_sample_fast_kernel<25, 3, BD, 1, ZR, 3, ZR><<<grid, 128, 0, st>>>(theta, to_dev(tps), a, grid_out, B, H, W, chunk);
+      return after_launch("tps_grid_sample_fast_kernel");
+    }
+  }
   if (N == 25 || N == 9) {
     const int chunk = B >= 128 ? kTpsChunk : (B >= 32 ? 8 : 2);
     dim3 grid(cdiv(H * W, 256), cdiv(B, chunk));
@@ -582,6 +901,18 @@ extern "C" int shineon_resample2d_fwd(const float* in1, const float* flow, float
   if (kernel_size != 1) return fail(SHINEON_ERR_UNSUPPORTED, "resample2d: kernel_size %d (only 1, as the reference uses)", kernel_size);
   if (Hi != H || Wi != W) return fail(SHINEON_ERR_UNSUPPORTED, "resample2d: input %dx%d != flow %dx%d", Hi, Wi, H, W);
   if (B == 0) return SHINEON_OK;
+  if (bilinear && C <= 4) {
+    constexpr int PPT = 2;
+    const dim3 g(cdiv(H * W, 256 * PPT), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (C) {
+      case 1: resample2d_fast_kernel<1, PPT><<<g, 256, 0, st>>>(in1, flow, out, H, W); break;
+      case 2: resample2d_fast_kernel<2, PPT><<<g, 256, 0, st>>>(in1, flow, out, H, W); break;
+      case 3: resample2d_fast_kernel<3, PPT><<<g, 256, 0, st>>>(in1, flow, out, H, W); break;
+      default: resample2d_fast_kernel<4, PPT><<<g, 256, 0, st>>>(in1, flow, out, H, W); break;
+    }
+    return after_launch("resample2d_fast_kernel");
+  }
   resample2d_fwd_kernel<<<dim3(cdiv(H * W, 256 * kPPT), B), 256, 0, (cudaStream_t)stream>>>(in1, flow, out, C, H, W, bilinear);
   return after_launch("resample2d_fwd_kernel");
 }

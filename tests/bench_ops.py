@@ -17,7 +17,11 @@ except Exception:  # noqa: BLE001
     pass
 
 
-def timeit(fn, iters=20, flush=None):
+def timeit(fn, iters=20, flush=None, reps=10):
+    """Median CUDA-event time of one launch.  Small configs (flush given): the 126 MB L2 is evicted before every
+    launch, one launch per event pair (launch latency included: these sizes are latency-bound anyway).  Large configs
+    (data > L2): `reps` back-to-back launches per event pair, so the ~5-10 us launch gap of a lone 50 us kernel does not
+    pollute a bandwidth figure; every launch still streams from HBM."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -25,12 +29,14 @@ def timeit(fn, iters=20, flush=None):
     for _ in range(iters):
         if flush is not None:
             flush.zero_()  # 512 MB write: evicts the 126 MB L2
+        n = 1 if flush is not None else reps
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(n):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / n)
     ts.sort()
     return ts[len(ts) // 2]
 
@@ -63,7 +69,12 @@ def main():
         flow = torch.randn(B, 2, H, W, device="cuda") * 4
         fl = flush if B == 16 else None
         ms = timeit(lambda: ops.resample2d_fwd(img, flow), flush=fl)
-        report(f"resample2d B={B}", B * 8 * H * W * 4, ms)
+        report(f"resample2d B={B} (i.i.d. N(0,4px) flow, SURVEY config 4)", B * 8 * H * W * 4, ms)
+        if B == 256:  # a smooth flow field (what FlowNet2 produces): neighbouring pixels sample neighbouring texels
+            sm = torch.nn.functional.interpolate(torch.randn(B, 2, H // 16, W // 16, device="cuda") * 4, size=(H, W),
+                                                 mode="bilinear", align_corners=False).contiguous()
+            ms = timeit(lambda: ops.resample2d_fwd(img, sm))
+            report(f"resample2d B={B} (smooth flow)", B * 8 * H * W * 4, ms)
         ms = timeit(lambda: ops.channelnorm_fwd(img), flush=fl)
         report(f"channelnorm C=3 B={B}", B * 4 * H * W * 4, ms)
     for B in (16, 64):

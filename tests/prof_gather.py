@@ -21,3 +21,8 @@ for _ in range(2):
     ops.resample2d_fwd(cloth, flow)
     ops.channelnorm_fwd(cloth)
 torch.cuda.synchronize()
+f1 = torch.randn(64, 256, 32, 24, device="cuda")
+f2 = torch.randn(64, 256, 32, 24, device="cuda")
+for _ in range(2):
+    ops.correlation_fwd(f1, f2, 20, 1, 20, 1, 2)
+torch.cuda.synchronize()
