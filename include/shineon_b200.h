@@ -226,6 +226,12 @@ int shineon_nchw_im2col_planes(const float* x0, int C0, const float* x1, int C1,
                                int H, int W, int kh, int kw, int stride, int pad, int Ho, int Wo, int kpad, int act,
                                float act_param, int plane_fmt, shineon_stream_t stream);
 
+/* First layers with 4x4 / stride 2 / pad 1 filters and few input channels (GMM 22 ch warp.py:14, U-Net 10 ch
+ * unet.py:129): shifted space-to-depth planes z [N, H/2+1, W/2+1, cpad] with z[Y][X][(py*2+px)*C + c] =
+ * x[c][2Y-1+py][2X-1+px] (zero outside); the conv then is a 2x2 / stride 1 / pad 0 conv over z with the weight
+ * re-indexed fy = 2*ay + py.  torch.cat([x0, x1], 1) is fused (x1 may be NULL). */
+int shineon_nchw_s2d_planes(const float* x0, int C0, const float* x1, int C1, void* y_hi, void* y_lo, int N, int H, int W,
+                            int cpad, int plane_fmt, shineon_stream_t stream);
 /* col2im of a tap-stacked 3x3 convolution with few output channels: t f32 NHWC [N,H,W,tstride] holds the
  * 9*Cout per-input-pixel partial products (channel (fy*3+fx)*Cout+co); y f32 NHWC [N,H,W,Cout] = bias + shifted sum. */
 int shineon_col2im3x3(const float* t, const float* bias, float* y, int N, int H, int W, int Cout, int tstride,

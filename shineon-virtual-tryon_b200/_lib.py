@@ -73,6 +73,7 @@ SIGNATURES = {
     "shineon_planes_to_nchw": [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_nchw_im2col_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
                                    c_f, c_i, c_p],
+    "shineon_nchw_s2d_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_col2im3x3": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_instnorm_act": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_f, c_i, c_p],
     "shineon_upsample2x_cat": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p],

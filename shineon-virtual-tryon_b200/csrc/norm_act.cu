@@ -114,6 +114,44 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------ nchw -> shifted space-to-depth planes
+// A 4x4 / stride 2 / pad 1 conv over x equals a 2x2 / stride 1 / pad 0 conv over
+//   z[Y][X][(py*2+px)*C + c] = x[c][2Y-1+py][2X-1+px]   (zero outside the image),   Y in [0, H/2], X in [0, W/2]
+// (filter row fy = 2*ay + py).  Unlike the im2col form (16 taps per output pixel = 4x the input) z holds every input
+// element exactly once: the layout conversion writes 4x fewer bytes and converts each element to 16-bit once.
+template <int FMT>
+__global__ void __launch_bounds__(256)
+    nchw_s2d_planes_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+                           plane_t* __restrict__ yh, plane_t* __restrict__ yl, int H, int W, int cpad) {
+  const int n = blockIdx.z, Y = blockIdx.y;
+  const int Wz = W / 2 + 1;
+  const int groups = cpad >> 3;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= Wz * groups) return;
+  const int g = t / Wz, X = t - g * Wz;  // X fastest: neighbouring threads read neighbouring columns of one channel plane
+  const int C = C0 + C1;
+  const int HW = H * W;
+  __align__(16) plane_t hi[8];
+  __align__(16) plane_t lo[8];
+  int k = g * 8;
+  int q = k / C, c = k - q * C;  // q = py*2+px
+#pragma unroll
+  for (int j = 0; j < 8; ++j, ++k) {
+    float v = 0.f;
+    if (q < 4) {
+      const int iy = 2 * Y - 1 + (q >> 1), ix = 2 * X - 1 + (q & 1);
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v = c < C0 ? __ldg(x0 + ((long)n * C0 + c) * HW + iy * W + ix)
+                   : __ldg(x1 + ((long)n * C1 + (c - C0)) * HW + iy * W + ix);
+    }
+    split16(v, FMT, hi[j], lo[j]);
+    if (++c == C) { c = 0; ++q; }
+  }
+  const long o = (((long)n * (H / 2 + 1) + Y) * Wz + X) * cpad + g * 8;
+  *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
+  if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
 // ------------------------------------------------------------------------------ tap-stacked 3x3 conv: col2im
 // For a 3x3 conv with very few output channels (the U-Net's final 128 -> 4 layer) the implicit GEMM is run
 // "transposed": one 1x1 GEMM produces, for every INPUT pixel q, the 9*Cout partial products
@@ -273,56 +311,61 @@ __device__ __forceinline__ void load8(const plane_t* __restrict__ h, const plane
   }
 }
 
-// grid: x = (output column, 8-channel group) tiles, y = output row, z = image.  No per-thread 64-bit divisions.
+// One thread = one 2x2 OUTPUT block x 8 channels.  For scale 2 / align_corners=False the outputs (2i+1, 2i+2) x
+// (2j+1, 2j+2) read exactly the source pixels (i, i+1) x (j, j+1): four source loads (hi+lo joined once) feed four
+// outputs, instead of four loads per output.  Blocks i = -1 and i = H-1 are the clamped borders (one valid output
+// row).  grid: x = (block column, 8-channel group) tiles, y = block row (H+1), z = image.
 template <int FMT, int ACT>  // ACT < 0: runtime activation id
 __global__ void __launch_bounds__(256)
     upsample2x_cat_kernel(const plane_t* __restrict__ s0h, const plane_t* __restrict__ s0l, int c0pad,
                           const plane_t* __restrict__ s1h, const plane_t* __restrict__ s1l, int c1pad,
                           plane_t* __restrict__ yh, plane_t* __restrict__ yl, int H, int W, int act,
                           float act_param) {
-  const int n = blockIdx.z, oy = blockIdx.y;
+  const int n = blockIdx.z, bi = (int)blockIdx.y - 1;
   const int ctot = c0pad + c1pad;
-  const int pairs = ctot >> 4;  // each thread produces two adjacent 8-channel groups (16 loads in flight)
-  const int Wo = 2 * W;
+  const int groups = ctot >> 3;
   const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= Wo * pairs) return;
-  const int ox = t / pairs, gp = t - ox * pairs;
-  int y0, y1, x0, x1;
-  float ly0, ly1, lx0, lx1;
-  up2_index(oy, H, y0, y1, ly0, ly1);
-  up2_index(ox, W, x0, x1, lx0, lx1);
-  const int c = gp * 16;
+  if (t >= (W + 1) * groups) return;
+  const int bjp = t / groups, g = t - bjp * groups;
+  const int bj = bjp - 1;
+  const int c = g * 8;
   const plane_t *sh, *sl;
   int cp, cc;
   if (c < c0pad) { sh = s0h; sl = s0l; cp = c0pad; cc = c; } else { sh = s1h; sl = s1l; cp = c1pad; cc = c - c0pad; }
+  const int r0 = max(bi, 0), r1 = min(bi + 1, H - 1), q0 = max(bj, 0), q1 = min(bj + 1, W - 1);
   const long rb = (long)n * H * W;
-  const long o00 = (rb + y0 * W + x0) * cp + cc, o01 = (rb + y0 * W + x1) * cp + cc;
-  const long o10 = (rb + y1 * W + x0) * cp + cc, o11 = (rb + y1 * W + x1) * cp + cc;
-  float a00[8], a01[8], a10[8], a11[8], b00[8], b01[8], b10[8], b11[8];
-  load8<FMT, ACT>(sh, sl, o00, act, act_param, a00);
-  load8<FMT, ACT>(sh, sl, o01, act, act_param, a01);
-  load8<FMT, ACT>(sh, sl, o10, act, act_param, a10);
-  load8<FMT, ACT>(sh, sl, o11, act, act_param, a11);
-  load8<FMT, ACT>(sh, sl, o00 + 8, act, act_param, b00);
-  load8<FMT, ACT>(sh, sl, o01 + 8, act, act_param, b01);
-  load8<FMT, ACT>(sh, sl, o10 + 8, act, act_param, b10);
-  load8<FMT, ACT>(sh, sl, o11 + 8, act, act_param, b11);
-  __align__(16) plane_t hi[16];
-  __align__(16) plane_t lo[16];
+  float a00[8], a01[8], a10[8], a11[8];
+  load8<FMT, ACT>(sh, sl, (rb + r0 * W + q0) * cp + cc, act, act_param, a00);
+  load8<FMT, ACT>(sh, sl, (rb + r0 * W + q1) * cp + cc, act, act_param, a01);
+  load8<FMT, ACT>(sh, sl, (rb + r1 * W + q0) * cp + cc, act, act_param, a10);
+  load8<FMT, ACT>(sh, sl, (rb + r1 * W + q1) * cp + cc, act, act_param, a11);
+  const int Wo = 2 * W, Ho = 2 * H;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    // ATen: h0lambda*(w0lambda*p00 + w1lambda*p01) + h1lambda*(w0lambda*p10 + w1lambda*p11)
-    const float va = ly0 * (lx0 * a00[j] + lx1 * a01[j]) + ly1 * (lx0 * a10[j] + lx1 * a11[j]);
-    const float vb = ly0 * (lx0 * b00[j] + lx1 * b01[j]) + ly1 * (lx0 * b10[j] + lx1 * b11[j]);
-    split16(va, FMT, hi[j], lo[j]);
-    split16(vb, FMT, hi[8 + j], lo[8 + j]);
-  }
-  const long o = (((long)n * 2 * H + oy) * Wo + ox) * ctot + c;
-  reinterpret_cast<uint4*>(yh + o)[0] = reinterpret_cast<const uint4*>(hi)[0];
-  reinterpret_cast<uint4*>(yh + o)[1] = reinterpret_cast<const uint4*>(hi)[1];
-  if (yl) {
-    reinterpret_cast<uint4*>(yl + o)[0] = reinterpret_cast<const uint4*>(lo)[0];
-    reinterpret_cast<uint4*>(yl + o)[1] = reinterpret_cast<const uint4*>(lo)[1];
+  for (int dy = 0; dy < 2; ++dy) {
+    const int oy = 2 * bi + 1 + dy;
+    if (oy < 0 || oy >= Ho) continue;
+    int i0, i1;
+    float ly0, ly1;
+    up2_index(oy, H, i0, i1, ly0, ly1);  // (i0, i1) == (r0, r1) up to the clamped borders, where the weight of the other row is 0
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int ox = 2 * bj + 1 + dx;
+      if (ox < 0 || ox >= Wo) continue;
+      int j0, j1;
+      float lx0, lx1;
+      up2_index(ox, W, j0, j1, lx0, lx1);
+      __align__(16) plane_t hi[8];
+      __align__(16) plane_t lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        // ATen: h0lambda*(w0lambda*p00 + w1lambda*p01) + h1lambda*(w0lambda*p10 + w1lambda*p11)
+        const float v = ly0 * (lx0 * a00[j] + lx1 * a01[j]) + ly1 * (lx0 * a10[j] + lx1 * a11[j]);
+        split16(v, FMT, hi[j], lo[j]);
+      }
+      const long o = (((long)n * Ho + oy) * Wo + ox) * ctot + c;
+      *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
+      if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
+    }
   }
 }
 
@@ -411,6 +454,20 @@ extern "C" int shineon_nchw_im2col_planes(const float* x0, int C0, const float* 
   return after_launch("nchw_im2col_planes_kernel");
 }
 
+extern "C" int shineon_nchw_s2d_planes(const float* x0, int C0, const float* x1, int C1, void* y_hi, void* y_lo, int N, int H,
+                                       int W, int cpad, int plane_fmt, shineon_stream_t stream) {
+  SHINEON_REQUIRE_FMT(plane_fmt, "nchw_s2d_planes");
+  SHINEON_REQUIRE(x0 && y_hi && C0 > 0 && (x1 == nullptr) == (C1 == 0), "nchw_s2d_planes: bad input tensors");
+  SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && H / 2 + 1 <= 65535, "nchw_s2d_planes: bad shape (H, W must be even)");
+  SHINEON_REQUIRE(cpad % 8 == 0 && cpad >= 4 * (C0 + C1), "nchw_s2d_planes: cpad %d too small / not a multiple of 8", cpad);
+  dim3 grid(cdiv((W / 2 + 1) * (cpad / 8), 256), H / 2 + 1, N);
+  if (plane_fmt == SHINEON_FMT_FP16)
+    nchw_s2d_planes_kernel<SHINEON_FMT_FP16><<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad);
+  else
+    nchw_s2d_planes_kernel<SHINEON_FMT_BF16><<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad);
+  return after_launch("nchw_s2d_planes_kernel");
+}
+
 extern "C" int shineon_col2im3x3(const float* t, const float* bias, float* y, int N, int H, int W, int Cout, int tstride,
                                  shineon_stream_t stream) {
   SHINEON_REQUIRE(t && y, "col2im3x3: null pointer");
@@ -485,8 +542,8 @@ extern "C" int shineon_upsample2x_cat(const void* s0_hi, const void* s0_lo, int 
   SHINEON_REQUIRE(s1_hi == nullptr || (s1_lo == nullptr) == (s0_lo == nullptr), "upsample2x_cat: s1 lo mismatch");
   SHINEON_REQUIRE(c0pad > 0 && c0pad % 16 == 0 && c1pad % 16 == 0, "upsample2x_cat: channel pads must be multiples of 16");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0, "upsample2x_cat: bad shape");
-  SHINEON_REQUIRE(2 * H <= 65535, "upsample2x_cat: H too large");
-  dim3 grid(cdiv(2 * W * ((c0pad + c1pad) / 16), 256), 2 * H, N);
+  SHINEON_REQUIRE(H + 1 <= 65535, "upsample2x_cat: H too large");
+  dim3 grid(cdiv((W + 1) * ((c0pad + c1pad) / 8), 256), H + 1, N);
 #define SHINEON_UP(F, A)                                                                                              \
   upsample2x_cat_kernel<F, A><<<grid, 256, 0, (cudaStream_t)stream>>>(                                               \
       (const plane_t*)s0_hi, (const plane_t*)s0_lo, c0pad, (const plane_t*)s1_hi, (const plane_t*)s1_lo, c1pad,      \

@@ -147,8 +147,9 @@ class UnetSkipConnectionBlock(nn.Module):
         d["down_i2c"] = None
         if self.outermost and dc.in_channels <= 32:
             # tiny Cin: im2col'd input + dense 1x1 GEMM instead of one mostly-zero K-block per tap
-            d["down_i2c"] = ops.Im2colConv(dc.weight, dc.bias, 2, 1, prec=prec)
+            d["down_i2c"] = ops.Im2colConv(dc.weight, dc.bias, 2, 1, prec=prec)  # training keeps the im2col operand
             d["down"] = d["down_i2c"].pc
+            d["down_first"] = ops.first_layer_conv(dc.weight, dc.bias, 2, 1, prec=prec)
         else:
             d["down"] = ops.PackedConv(dc.weight, dc.bias, stride=2, pad=1, prec=prec)
         if sub is not None:
@@ -278,7 +279,7 @@ class UnetSkipConnectionBlock(nn.Module):
         bn = pk["down_bn"]
         sc, sh = bn if bn is not None else (None, None)
         if isinstance(a_in, tuple) and pk["down_i2c"] is not None:
-            f32, _ = pk["down_i2c"].conv(a_in[0], a_in[1], scale=sc, shift=sh, want_f32=True)
+            f32, _ = pk["down_first"].conv(a_in[0], a_in[1], scale=sc, shift=sh, want_f32=True)
         else:
             if isinstance(a_in, tuple):
                 a_in = ops.nchw_to_planes(a_in[0], a_in[1], prec=prec)

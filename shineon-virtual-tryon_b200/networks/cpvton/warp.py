@@ -55,7 +55,7 @@ class FeatureExtraction(nn.Module):
             sc, sh = fold_bn(bn) if bn is not None else (None, None)
             if i == 0 and conv.in_channels <= 32:
                 # tiny Cin: im2col'd input + dense 1x1 GEMM instead of one mostly-zero K-block per tap
-                i2c = ops.Im2colConv(conv.weight, conv.bias, conv.stride[0], conv.padding[0], prec=prec)
+                i2c = ops.first_layer_conv(conv.weight, conv.bias, conv.stride[0], conv.padding[0], prec=prec)
                 layers.append((i2c.pc, sc, sh, i2c))
             else:
                 pc = ops.PackedConv(conv.weight, conv.bias, stride=conv.stride[0], pad=conv.padding[0], prec=prec)

@@ -458,6 +458,52 @@ class Im2colConv:
         return out_f32, out_planes
 
 
+class S2dConv:
+    """A 4x4 / stride 2 / pad 1 Conv2d with few input channels as a 2x2 / stride 1 conv over shifted space-to-depth planes
+    (shineon_nchw_s2d_planes): every input element is written once (im2col writes it four times).  Same interface as
+    Im2colConv."""
+
+    def __init__(self, weight, bias, prec=None):
+        Cout, Cin, kh, kw = weight.shape
+        assert (kh, kw) == (4, 4)
+        self.Cin = Cin
+        # fy = 2*ay + py, fx = 2*ax + px  ->  [Cout, (py, px, c), ay, ax]
+        w2 = weight.detach().float().reshape(Cout, Cin, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Cout, 4 * Cin, 2, 2)
+        self.pc = PackedConv(w2.contiguous(), bias, stride=1, pad=0, prec=prec)
+
+    @staticmethod
+    def applicable(weight, stride, pad):
+        Cout, Cin, kh, kw = weight.shape
+        return (kh, kw, stride, pad) == (4, 4, 2, 1) and 8 <= Cin <= 32
+
+    def prepare(self, x0, x1=None):
+        x0 = _req(x0, name="x0")
+        N, C0, H, W = x0.shape
+        C1 = 0
+        if x1 is not None:
+            x1 = _req(x1, name="x1")
+            C1 = x1.shape[1]
+        assert C0 + C1 == self.Cin and H % 2 == 0 and W % 2 == 0
+        out = Planes(N, H // 2 + 1, W // 2 + 1, 4 * self.Cin, prec=(self.pc.fmt, self.pc.w_lo is not None), device=x0.device,
+                     zero_pad=False)  # the kernel writes the padding channels too
+        check(_lib.load().shineon_nchw_s2d_planes(_p(x0), C0, _p(x1), C1, _p(out.hi), _p(out.lo), N, H, W, out.cpad, out.fmt,
+                                                  _stream()), "shineon_nchw_s2d_planes")
+        return out
+
+    def conv(self, x0, x1=None, *, scale=None, shift=None, pre_act=None, post_act=None, act_param=0.0, want_f32=False,
+             want_planes=False, out_f32=None, out_planes=None, fused=None):
+        a = self.prepare(x0, x1)
+        return conv2d(a, self.pc, scale=scale, shift=shift, pre_act=pre_act, post_act=post_act, act_param=act_param,
+                      want_f32=want_f32, want_planes=want_planes, out_f32=out_f32, out_planes=out_planes)
+
+
+def first_layer_conv(weight, bias, stride, pad, prec=None):
+    """Small-Cin stem: space-to-depth form where it applies (4x4 s2 p1, 8 <= Cin <= 32), else im2col."""
+    if S2dConv.applicable(weight, stride, pad):
+        return S2dConv(weight, bias, prec=prec)
+    return Im2colConv(weight, bias, stride, pad, prec=prec)
+
+
 class TapStackedConv3x3:
     """3x3 / stride 1 / pad 1 conv with few output channels as one 1x1 GEMM with 9*Cout outputs + col2im."""
 

@@ -112,6 +112,27 @@ def test_im2col_first_layer(ops, cfg):
     assert_close(p3.float(), F.leaky_relu(want, 0.1), atol=3e-5, rtol=1e-4, what="im2col conv planes + leaky")
 
 
+@pytest.mark.parametrize("cfg", [(2, 22, 64, 48, 64), (1, 10, 32, 24, 64), (3, 8, 8, 12, 96)])
+@pytest.mark.parametrize("prec", ["fp16x3", "bf16"])
+def test_s2d_first_layer(ops, cfg, prec):
+    """4x4 s2 p1 small-Cin conv as a 2x2 s1 conv over shifted space-to-depth planes (cat of two NCHW inputs fused)."""
+    N, Cin, H, W, Cout = cfg
+    g = torch.Generator().manual_seed(Cin + H)
+    x = _rounded(torch.randn(N, Cin, H, W, generator=g), prec)
+    w = _rounded(torch.randn(Cout, Cin, 4, 4, generator=g) * 0.05, prec)
+    b = torch.randn(Cout, generator=g) * 0.1
+    c0 = Cin - Cin // 3
+    conv = ops.first_layer_conv(w.cuda(), b.cuda(), 2, 1, prec=prec)
+    assert isinstance(conv, ops.S2dConv)
+    y, _ = conv.conv(x[:, :c0].contiguous().cuda(), x[:, c0:].contiguous().cuda(), pre_act="relu", want_f32=True)
+    want = F.relu(F.conv2d(x, w, b, stride=2, padding=1))
+    assert_close(nchw(y), want, what="s2d first-layer conv", **CONV_TOL[prec])
+    # single input tensor, planes output
+    _, yp = conv.conv(x.contiguous().cuda(), None, want_planes=True)
+    assert_close(yp.float(), F.conv2d(x, w, b, stride=2, padding=1), atol=2e-2 if prec == "bf16" else 3e-5, rtol=1e-2 if prec == "bf16" else 1e-4,
+                 what="s2d first-layer conv planes")
+
+
 def test_tap_stacked_conv3x3(ops):
     g = torch.Generator().manual_seed(44)
     N, Cin, H, W, Cout = 2, 128, 32, 24, 4
