@@ -53,6 +53,7 @@ struct ConvArgs {
   float acc_scale;   // multiplies the accumulator first (undoes the power-of-two weight scaling of fp16 planes)
   int fmt;           // plane encoding (SHINEON_FMT_*)
   uint32_t idesc;    // tcgen05 instruction descriptor for (fmt, BN)
+  uint32_t idesc_cat;  // same with N = 2*BN (split mode: [B_hi | B_lo] in one MMA)
   float* y_f32;
   plane_t* y_hi;
   plane_t* y_lo;
@@ -156,9 +157,16 @@ __global__ void __launch_bounds__(kThreads, 1)
   constexpr int kBBytes = BN * kBlockK * 2;
   constexpr int kPlanes = SPLIT ? 2 : 1;
   constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  constexpr int kAccCols = BN < 32 ? 32 : BN;  // TMEM columns per accumulator
+  // Split (hi/lo) mode issues hi*hi + hi*lo + lo*hi.  The B_hi and B_lo tiles sit back to back in shared memory, so
+  // A_hi * [B_hi | B_lo] is ONE MMA with N = 2*BN into columns [0, 2*BN) (left half hi*hi, right half hi*lo) and
+  // A_lo * B_hi a second one into the left half; the epilogue adds the halves.  Two MMAs instead of three and A_hi is
+  // read from shared memory once instead of twice: the narrow-N (Cout <= 64) layers are bound by exactly that
+  // operand traffic (128 B/clk/SM), profiles/r01_conv_igemm.md.  Needs 4*BN TMEM columns, i.e. BN <= 128.
+  constexpr bool kCat = SPLIT && BN <= 128;
+  constexpr int kAccCols = (kCat ? 2 : 1) * BN < 32 ? 32 : (kCat ? 2 : 1) * BN;  // TMEM columns per accumulator
   constexpr int kTmemCols = 2 * kAccCols;      // double-buffered (<= 512)
   const uint32_t kIdesc = a.idesc;
+  const uint32_t kIdescCat = a.idesc_cat;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
@@ -259,12 +267,18 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int k = 0; k < kBlockK / 16; ++k) {
             const uint64_t dAh = umma_desc_sw128(sA + k * 32);
             const uint64_t dBh = umma_desc_sw128(sB + k * 32);
-            umma_f16(tmem_acc, dAh, dBh, kIdesc, (kb | k) != 0);
-            if (SPLIT) {
+            if (kCat) {
               const uint64_t dAl = umma_desc_sw128(sA + kABytes + k * 32);
-              const uint64_t dBl = umma_desc_sw128(sB + kBBytes + k * 32);
-              umma_f16(tmem_acc, dAh, dBl, kIdesc, 1);
+              umma_f16(tmem_acc, dAh, dBh, kIdescCat, (kb | k) != 0);  // N = 2*BN: rows of B_hi then B_lo
               umma_f16(tmem_acc, dAl, dBh, kIdesc, 1);
+            } else {
+              umma_f16(tmem_acc, dAh, dBh, kIdesc, (kb | k) != 0);
+              if (SPLIT) {
+                const uint64_t dAl = umma_desc_sw128(sA + kABytes + k * 32);
+                const uint64_t dBl = umma_desc_sw128(sB + kBBytes + k * 32);
+                umma_f16(tmem_acc, dAh, dBl, kIdesc, 1);
+                umma_f16(tmem_acc, dAl, dBh, kIdesc, 1);
+              }
             }
           }
           umma_commit(bar_empty + 8 * s);  // frees the smem slot once these MMAs retire
@@ -305,16 +319,23 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (cn0 + c0 >= a.Cout) break;  // warp-uniform
         uint32_t v[32];
         const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        if (kChunk == 32)
+        uint32_t v2[32];
+        if (kChunk == 32) {
           tmem_ld32(taddr, v);
-        else
+          if (kCat) tmem_ld32(taddr + BN, v2);
+        } else {
           tmem_ld16(taddr, v);
+          if (kCat) tmem_ld16(taddr + BN, v2);
+        }
         tmem_ld_wait();
         const int cnt = min(kChunk, a.Cout - (cn0 + c0));  // warp-uniform
         float vals[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          vals[i] = (i < kChunk) ? fmaf(__uint_as_float(v[i]), a.acc_scale, s_bias[c0 + (i < kChunk ? i : 0)]) : 0.f;
+        for (int i = 0; i < 32; ++i) {
+          float acc = (i < kChunk) ? __uint_as_float(v[i]) : 0.f;
+          if (kCat && i < kChunk) acc += __uint_as_float(v2[i]);  // hi*hi + lo*hi  +  hi*lo
+          vals[i] = (i < kChunk) ? fmaf(acc, a.acc_scale, s_bias[c0 + (i < kChunk ? i : 0)]) : 0.f;
+        }
         act_chunk_dispatch(vals, a.pre_act, a.act_param);
         if (a.scale != nullptr) {
 #pragma unroll
@@ -693,6 +714,7 @@ static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CU
   if (stages < 1) stages = 1;
   a.stages = stages;
   a.idesc = umma_idesc_f16(kBlockM, BN, a.fmt == SHINEON_FMT_FP16 ? 0 : 1);
+  a.idesc_cat = umma_idesc_f16(kBlockM, 2 * BN <= 256 ? 2 * BN : BN, a.fmt == SHINEON_FMT_FP16 ? 0 : 1);
   static int max_dyn_smem = -1;  // per instantiation: opt-in limit minus this kernel's static shared memory
   if (max_dyn_smem < 0) {
     cudaFuncAttributes fa;
@@ -754,6 +776,7 @@ static int fill_args(const shineon_conv2d_params* p, ConvArgs& a) {
   a.fmt = p->plane_fmt;
   a.acc_scale = p->acc_scale == 0.f ? 1.f : p->acc_scale;
   a.idesc = 0;
+  a.idesc_cat = 0;
   a.y_f32 = p->y_f32; a.y_hi = (plane_t*)p->y_hi; a.y_lo = (plane_t*)p->y_lo;
   a.oh_mul = p->oh_mul ? p->oh_mul : 1; a.ow_mul = p->ow_mul ? p->ow_mul : 1;
   a.oh_off = p->oh_off; a.ow_off = p->ow_off;
