@@ -237,6 +237,14 @@ int shineon_nchw_s2d_planes(const float* x0, int C0, const float* x1, int C1, vo
 int shineon_col2im3x3(const float* t, const float* bias, float* y, int N, int H, int W, int Cout, int tstride,
                       shineon_stream_t stream);
 
+/* nn.Upsample(x2, bilinear, align_corners=False) -> Conv2d(3x3, pad 1) (unet.py:138-146,155,166) evaluated from
+ * the tap-stacked products of the LOW-resolution tensor (the contraction over channels commutes with the
+ * interpolation): t f32 NHWC [N,h,w,tstride], t[..., (fy*3+fx)*Cout + co] = <x[n,i,j,:], w[co,:,fy,fx]>
+ * -> y f32 NHWC [N,2h,2w,Cout] = bias + sum over taps of the bilinearly upsampled t_tap, shifted by the tap,
+ * zero where the tap leaves the 2h x 2w image (the conv's zero padding). */
+int shineon_upconv3x3_gather(const float* t, const float* bias, float* y, int N, int h, int w, int Cout,
+                             int tstride, shineon_stream_t stream);
+
 /* nn.InstanceNorm2d(affine=False, eps) over f32 NHWC x [N,H,W,C] (unet.py:133,135) followed by
  * activation; writes any subset of: f32 NHWC y_f32 (may alias x), planes y_hi/y_lo [N,H,W,cpad].
  * do_norm=0 skips the normalisation (innermost down block, unet.py:166-175).

@@ -122,6 +122,146 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// Register-tiled version (the default when the row strides keep 16-byte alignment): 256 threads, QB queries per CTA.
+//   energies  : one (key j, 8-query group) item per thread, q rows broadcast from shared memory;
+//   softmax   : thread = (query, 1/8 of the keys), partial max / sum combined through shared memory; probabilities are
+//               kept TRANSPOSED [HW][QB] so the next phase reads 8 queries with two 128-bit broadcast loads;
+//   P.V       : each thread owns 8 queries x 8 channels (64 accumulators): per key 2 LDG.128 of V (coalesced 2 KB rows,
+//               shared by the CTA's query groups through L1) + 2 LDS.128 of P feed 64 FMAs.
+// The first kernel below (16 queries x 4 channels per thread, 128 threads) spent 16 scalar LDS per 64 FMAs and ran
+// latency-bound at ~15 % of the fp32 FMA rate (profiles/r01_launches_summary.md: 0.30 ms for N = 192, C = 512, 80 images).
+template <int QB>
+__global__ void __launch_bounds__(256)
+    sagan_attention_tiled_kernel(const float* __restrict__ qkv, const float* __restrict__ x, const float* __restrict__ gamma,
+                                 float* __restrict__ yf, plane_t* __restrict__ yh, plane_t* __restrict__ yl,
+                                 int HW, int C, int Cq, int cpad, int act, float act_param, int fmt) {
+  constexpr int QG = QB / 8;       // 8-query groups
+  constexpr int PARTS = 256 / QB;  // key partitions of the softmax phase
+  extern __shared__ __align__(16) float sm[];
+  float* sq = sm;                    // [QB][Cq]
+  float* sp = sm + QB * Cq;          // [HW][QB] energies -> un-normalised probabilities
+  float* sred = sp + (size_t)HW * QB;  // [PARTS][QB] partial max / sum
+  float* sinv = sred + PARTS * QB;   // [QB]
+  const int n = blockIdx.y, i0 = blockIdx.x * QB;
+  const int nq = min(QB, HW - i0);
+  const int ld = 2 * Cq + C;
+  const float* base = qkv + (long)n * HW * ld;
+  const int tid = threadIdx.x;
+
+  for (int e = tid; e < QB * Cq; e += 256) {
+    const int q = e / Cq, c = e - q * Cq;
+    sq[e] = q < nq ? __ldg(base + (long)(i0 + q) * ld + c) : 0.f;
+  }
+  __syncthreads();
+
+  for (int item = tid; item < HW * QG; item += 256) {
+    const int qg = item / HW, j = item - qg * HW;
+    const float* kj = base + (long)j * ld + Cq;
+    const float* q0 = sq + qg * 8 * Cq;
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int c = 0; c < Cq; c += 4) {
+      const float4 k4 = __ldg(reinterpret_cast<const float4*>(kj + c));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 q4 = *reinterpret_cast<const float4*>(q0 + q * Cq + c);
+        acc[q] = fmaf(q4.x, k4.x, acc[q]);
+        acc[q] = fmaf(q4.y, k4.y, acc[q]);
+        acc[q] = fmaf(q4.z, k4.z, acc[q]);
+        acc[q] = fmaf(q4.w, k4.w, acc[q]);
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(sp + (size_t)j * QB + qg * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  __syncthreads();
+
+  {  // softmax over keys; thread = (query q, key partition part)
+    const int q = tid % QB, part = tid / QB;
+    float m = -INFINITY;
+    for (int j = part; j < HW; j += PARTS) m = fmaxf(m, sp[(size_t)j * QB + q]);
+    sred[part * QB + q] = m;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PARTS; ++k) m = fmaxf(m, sred[k * QB + q]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = part; j < HW; j += PARTS) {
+      const float pr = expf(sp[(size_t)j * QB + q] - m);
+      sp[(size_t)j * QB + q] = pr;
+      sum += pr;
+    }
+    sred[part * QB + q] = sum;
+    __syncthreads();
+    if (part == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < PARTS; ++k) tot += sred[k * QB + q];
+      sinv[q] = 1.f / tot;
+    }
+    __syncthreads();
+  }
+
+  const float g = __ldg(gamma);
+  const float* vbase = base + 2 * Cq;
+  constexpr int CGP = 256 / QG;  // channel groups (of 8) per pass
+  const int qg = tid / CGP;
+  const int q_lo = qg * 8;
+  for (int c0 = (tid % CGP) * 8; c0 < C; c0 += CGP * 8) {
+    float acc[8][8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
+    const float* vp = vbase + c0;
+    const float* pp = sp + q_lo;
+#pragma unroll 2
+    for (int j = 0; j < HW; ++j) {
+      const float4 va = __ldg(reinterpret_cast<const float4*>(vp + (long)j * ld));
+      const float4 vb = __ldg(reinterpret_cast<const float4*>(vp + (long)j * ld + 4));
+      const float4 pa = *reinterpret_cast<const float4*>(pp + (size_t)j * QB);
+      const float4 pb = *reinterpret_cast<const float4*>(pp + (size_t)j * QB + 4);
+      const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+      const float pq[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[q][k] = fmaf(pq[q], v[k], acc[q][k]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q_lo + q >= nq) break;
+      const long pix = (long)n * HW + i0 + q_lo + q;
+      const float inv = sinv[q_lo + q];
+      const float4 xa = __ldg(reinterpret_cast<const float4*>(x + pix * C + c0));
+      const float4 xb = __ldg(reinterpret_cast<const float4*>(x + pix * C + c0 + 4));
+      const float xr[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = apply_act(g * (acc[q][k] * inv) + xr[k], act, act_param);  // sagan.py:53
+      if (yf) {
+        float4* d = reinterpret_cast<float4*>(yf + pix * C + c0);
+        d[0] = make_float4(v[0], v[1], v[2], v[3]);
+        d[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      if (yh) {
+        plane_t h[8], l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) split16(v[k], fmt, h[k], l[k]);
+        *reinterpret_cast<uint4*>(yh + pix * cpad + c0) =
+            make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                       (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
+        if (yl)
+          *reinterpret_cast<uint4*>(yl + pix * cpad + c0) =
+              make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
+                         (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
+      }
+    }
+  }
+}
+
 }  // namespace shineon
 
 using namespace shineon;
@@ -136,6 +276,25 @@ extern "C" int shineon_sagan_attention(const float* qkv, const float* x, const f
   SHINEON_REQUIRE(((2 * Cq + C) & 3) == 0 || (Cq & 3) != 0, "sagan_attention: row stride must keep float4 alignment");
   auto smem_for = [&](int qt) { return sizeof(float) * ((size_t)qt * Cq + (size_t)qt * HW + qt); };
   cudaStream_t st = (cudaStream_t)stream;
+  // register-tiled kernel: needs 16-byte aligned q/k/v/x rows and plane rows (8 channels = one 128-bit store)
+  const bool aligned = (C % 8 == 0) && (Cq % 4 == 0) && (!y_hi || cpad % 8 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y_f32) |
+                         reinterpret_cast<uintptr_t>(y_hi) | reinterpret_cast<uintptr_t>(y_lo)) % 16 == 0);
+  if (aligned) {
+    constexpr int QB = 32;
+    const size_t smem = sizeof(float) * ((size_t)QB * Cq + (size_t)HW * QB + (256 / QB) * QB + QB);
+    static size_t opted = 48 * 1024;  // dynamic shared memory this kernel has been opted into
+    if (smem <= 200 * 1024) {
+      if (smem > opted) {
+        cudaError_t e = cudaFuncSetAttribute(sagan_attention_tiled_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "sagan_attention: shared memory opt-in: %s", cudaGetErrorString(e));
+        opted = smem;
+      }
+      sagan_attention_tiled_kernel<QB><<<dim3(cdiv(HW, QB), N), 256, smem, st>>>(
+          qkv, x, gamma, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, Cq, cpad, act, act_param, plane_fmt);
+      return after_launch("sagan_attention_tiled_kernel");
+    }
+  }
 #define SHINEON_ATT(QT_)                                                                                            \
   sagan_attention_kernel<QT_><<<dim3(cdiv(HW, QT_), N), 128, smem_for(QT_), st>>>(                                   \
       qkv, x, gamma, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, Cq, cpad, act, act_param, plane_fmt)

@@ -183,6 +183,114 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------ bilinear x2 -> 3x3 conv, at low resolution
+// nn.Upsample(x2, bilinear, align_corners=False) followed by Conv2d(3x3, pad 1) (unet.py:138-146,155,166) is linear in
+// the low-resolution tensor, and the channel contraction commutes with the spatial interpolation:
+//   conv(up(x))[n,r,s,co] = bias[co] + sum_{fy,fx} [0 <= r+fy-1 < 2h, 0 <= s+fx-1 < 2w] * up(t_{fy,fx,co})[n, r+fy-1, s+fx-1]
+// with t_{fy,fx,co}[n,i,j] = <x[n,i,j,:], w[co,:,fy,fx]> -- the tap-stacked 1x1 GEMM of the LOW-resolution tensor
+// (4x fewer pixels => 4x fewer tensor-core FLOPs, and the upsampled activation is never written or read).
+// This kernel evaluates the right-hand side: one thread owns low-res pixel (i,j) x VEC channels and produces its 2x2
+// output pixels.  Row r = 2i+py+fy-1 of up(.) interpolates low-res rows {i-1,i,i+1} with one of four coefficient
+// triples (clamped at the border like PyTorch's upsample, zero where the conv's zero padding applies):
+//   A: r = 2i-1  (0.75, 0.25, 0)  [zero when i == 0]        B: r = 2i    (0.25, 0.75, 0)  [(0,1,0) when i == 0]
+//   C: r = 2i+1  (0, 0.75, 0.25)  [(0,1,0) when i == h-1]   D: r = 2i+2  (0, 0.25, 0.75)  [zero when i == h-1]
+// (fy,py) -> triple: (0,0) A, (0,1) B, (1,0) B, (1,1) C, (2,0) C, (2,1) D; same for columns.
+struct Up3 { float c[4][3]; };  // A, B, C, D
+__device__ __forceinline__ Up3 up3_coeffs(int i, int n) {
+  Up3 u;
+  const bool first = i == 0, last = i == n - 1;
+  u.c[0][0] = first ? 0.f : 0.75f; u.c[0][1] = first ? 0.f : 0.25f; u.c[0][2] = 0.f;
+  u.c[1][0] = first ? 0.f : 0.25f; u.c[1][1] = first ? 1.f : 0.75f; u.c[1][2] = 0.f;
+  u.c[2][0] = 0.f; u.c[2][1] = last ? 1.f : 0.75f; u.c[2][2] = last ? 0.f : 0.25f;
+  u.c[3][0] = 0.f; u.c[3][1] = last ? 0.f : 0.25f; u.c[3][2] = last ? 0.f : 0.75f;
+  return u;
+}
+// structural support of triple (f + p) in {A,B,C,D}: A,B touch rows {0,1}; C,D rows {1,2}
+__host__ __device__ constexpr bool up3_has(int f, int p, int a) { return (f + p) < 2 ? a < 2 : a > 0; }
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+    upconv3x3_gather_kernel(const float* __restrict__ t, const float* __restrict__ bias, float* __restrict__ y, int h,
+                            int w, int Cout, int tstride, int gpb, int tile_w, int tiles_x) {
+  const int n = blockIdx.z;
+  const int g = blockIdx.y * gpb + (int)threadIdx.x % gpb;
+  const int pix = (int)threadIdx.x / gpb;
+  const int tile_h = (256 / gpb) / tile_w;
+  const int i = ((int)blockIdx.x / tiles_x) * tile_h + pix / tile_w;
+  const int j = ((int)blockIdx.x % tiles_x) * tile_w + pix % tile_w;
+  const int co = g * VEC;
+  if (i >= h || j >= w || co >= Cout) return;
+  const Up3 cy = up3_coeffs(i, h), cx = up3_coeffs(j, w);
+  const int rows[3] = {max(i - 1, 0), i, min(i + 1, h - 1)};
+  const int cols[3] = {max(j - 1, 0), j, min(j + 1, w - 1)};
+  float out[2][2][VEC];
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) out[p][q][k] = bias ? __ldg(bias + co + k) : 0.f;
+  const float* tn = t + (long)n * h * w * tstride + co;
+#pragma unroll
+  for (int fy = 0; fy < 3; ++fy) {
+#pragma unroll
+    for (int fx = 0; fx < 3; ++fx) {
+      const float* tt = tn + (fy * 3 + fx) * Cout;
+      // rows needed by this tap: fy=0 {0,1}, fy=1 {0,1,2}, fy=2 {1,2}; same for columns
+      float v[3][3][VEC];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (!(up3_has(fy, 0, a) || up3_has(fy, 1, a))) continue;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          if (!(up3_has(fx, 0, b) || up3_has(fx, 1, b))) continue;
+          const float* src = tt + ((long)rows[a] * w + cols[b]) * tstride;
+          if constexpr (VEC == 4) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(src));
+            v[a][b][0] = f.x; v[a][b][1] = f.y; v[a][b][2] = f.z; v[a][b][3] = f.w;
+          } else {
+            v[a][b][0] = __ldg(src);
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (!(up3_has(fy, 0, a) || up3_has(fy, 1, a))) continue;
+        float tmp[2][VEC];  // column-interpolated row a, for the two output columns
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            float s = 0.f;
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+              if (up3_has(fx, q, b)) s = fmaf(cx.c[fx + q][b], v[a][b][k], s);
+            tmp[q][k] = s;
+          }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          if (!up3_has(fy, p, a)) continue;
+          const float wy = cy.c[fy + p][a];
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) out[p][q][k] = fmaf(wy, tmp[q][k], out[p][q][k]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float* dst = y + (((long)n * 2 * h + 2 * i + p) * (2 * w) + 2 * j + q) * Cout + co;
+      if constexpr (VEC == 4)
+        *reinterpret_cast<float4*>(dst) = make_float4(out[p][q][0], out[p][q][1], out[p][q][2], out[p][q][3]);
+      else
+        dst[0] = out[p][q][0];
+    }
+}
+
 // ------------------------------------------------------------------------------ instance norm
 // Pass 1: per-(n,c) sum and sum of squares.  fp32 partials per CTA, fp64 atomics across CTAs
 // (E[x^2]-E[x]^2 is then evaluated in fp64, so cancellation is not an issue).
@@ -475,6 +583,27 @@ extern "C" int shineon_col2im3x3(const float* t, const float* bias, float* y, in
   dim3 grid(grid_x((long)H * W * Cout, 256), N);
   col2im3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, bias, y, H, W, Cout, tstride);
   return after_launch("col2im3x3_kernel");
+}
+
+extern "C" int shineon_upconv3x3_gather(const float* t, const float* bias, float* y, int N, int h, int w, int Cout,
+                                        int tstride, shineon_stream_t stream) {
+  SHINEON_REQUIRE(t && y, "upconv3x3_gather: null pointer");
+  SHINEON_REQUIRE(N > 0 && N <= 65535 && h > 0 && w > 0 && Cout > 0 && tstride >= 9 * Cout, "upconv3x3_gather: bad shape");
+  const int vec = (Cout % 4 == 0 && tstride % 4 == 0) ? 4 : 1;
+  const int groups = Cout / vec;
+  int gpb = 1;  // channel groups per CTA (power of two <= 8); the other 256/gpb threads tile low-res pixels
+  while (gpb < 8 && gpb < groups) gpb *= 2;
+  const int pixels = 256 / gpb;
+  const int tile_w = pixels >= 256 ? 32 : (pixels >= 128 ? 16 : 8);
+  const int tile_h = pixels / tile_w;
+  const int tiles_x = cdiv(w, tile_w), tiles_y = cdiv(h, tile_h);
+  SHINEON_REQUIRE(cdiv(groups, gpb) <= 65535, "upconv3x3_gather: too many channels");
+  dim3 grid(tiles_x * tiles_y, cdiv(groups, gpb), N);
+  if (vec == 4)
+    upconv3x3_gather_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(t, bias, y, h, w, Cout, tstride, gpb, tile_w, tiles_x);
+  else
+    upconv3x3_gather_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(t, bias, y, h, w, Cout, tstride, gpb, tile_w, tiles_x);
+  return after_launch("upconv3x3_gather_kernel");
 }
 
 extern "C" int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, void* y_lo, double* stats_ws, int N,

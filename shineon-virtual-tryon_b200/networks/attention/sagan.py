@@ -33,13 +33,13 @@ class SelfAttention(nn.Module):
             self._packed = (sig, ops.PackedConv(w, b, stride=1, pad=0, prec=prec))
         return self._packed[1]
 
-    def run(self, x_f32, x_planes, *, act=None, act_param=0.0, want_f32=False, want_planes=True):
+    def run(self, x_f32, x_planes, *, act=None, act_param=0.0, want_f32=False, want_planes=True, out_planes=None):
         """x_f32: f32 NHWC [N,H,W,C]; x_planes: the same values as planes.  Returns (f32|None, Planes|None) of
         act(gamma * attention(x) + x)."""
         prec = x_planes.prec
         qkv, _ = ops.conv2d(x_planes, self.packed(prec), want_f32=True)
         return ops.sagan_attention(qkv, x_f32, self.gamma.detach(), self.chanel_in // 8, act=act, act_param=act_param,
-                                   want_f32=want_f32, want_planes=want_planes, prec=prec)
+                                   want_f32=want_f32, want_planes=want_planes, prec=prec, out_planes=out_planes)
 
     # ---- training (row U6)
     def run_train(self, x_f32, x_planes):

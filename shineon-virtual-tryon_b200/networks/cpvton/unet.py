@@ -174,9 +174,14 @@ class UnetSkipConnectionBlock(nn.Module):
                 d["up_tap"] = ops.TapStackedConv3x3(uc.weight, uc.bias, prec=prec, cin_pad=p_skip + p_xp, chan_map=cmap)
             d["up"] = ops.PackedConv(uc.weight, uc.bias, stride=1, pad=1, prec=prec, cin_pad=p_skip + p_xp,
                                      chan_map=cmap)
+            d["cat_geom"] = (c_skip, p_skip, c_xp, p_xp)
         else:
             d["up_tap"] = None
             d["up"] = ops.PackedConv(uc.weight, uc.bias, stride=1, pad=1, prec=prec)
+        # inference: upsample -> 3x3 conv evaluated at the low resolution (ops.UpsampledConv3x3).  Not for the
+        # default-activation quirk (skip and child input differ by a ReLU there) nor folded BatchNorm epilogues.
+        d["up_lowres"] = None  # packed on first inference use (_lowres); the training tape never needs it
+        d["lowres_ok"] = not pr["default_act"] and isinstance(pr["upnorm"], nn.InstanceNorm2d)
         d["cmap_up"] = None
         if sub is not None:
             d["cmap_up"] = cmap
@@ -191,6 +196,19 @@ class UnetSkipConnectionBlock(nn.Module):
                 raise NotImplementedError("InstanceNorm2d with affine/running stats is not used by the reference")
         self._packed = (sig, d)
         return d
+
+    def _lowres(self, pk, prec):
+        if not (ops.UPCONV_LOWRES and pk["lowres_ok"]):
+            return None
+        if pk["up_lowres"] is None:
+            uc = self._parts["upconv"]
+            if self._parts["sub"] is not None:
+                _, p_skip, _, p_xp = pk["cat_geom"]
+                pk["up_lowres"] = ops.UpsampledConv3x3(uc.weight, uc.bias, prec=prec, cin_pad=p_skip + p_xp,
+                                                       chan_map=pk["cmap_up"])
+            else:
+                pk["up_lowres"] = ops.UpsampledConv3x3(uc.weight, uc.bias, prec=prec)
+        return pk["up_lowres"]
 
     def _pack_bwd(self, prec):
         """Data-gradient operands: a stride-1 conv's dgrad is the flipped-tap conv with Cin/Cout swapped, the 4x4 s2
@@ -240,7 +258,7 @@ class UnetSkipConnectionBlock(nn.Module):
         return ops.instnorm_act_bwd(sv["c"], sv["ws"], gz, g_y, do_norm=sv["inorm"], act=None, eps=sv["eps"],
                                     want_f32=True, want_planes=True, prec=prec)
 
-    def _finish(self, conv_f32, norm, bn, attn, act, act_param, prec, want_final_f32=False):
+    def _finish(self, conv_f32, norm, bn, attn, act, act_param, prec, want_final_f32=False, out_planes=None):
         """conv output (f32 NHWC, bias [and folded BN] applied) -> [InstanceNorm] -> [SelfAttention] -> act.
         Returns Planes of the activated value, or the final f32 tensor when want_final_f32."""
         inorm = isinstance(norm, nn.InstanceNorm2d)
@@ -250,16 +268,17 @@ class UnetSkipConnectionBlock(nn.Module):
                                         want_f32=True, want_planes=False, out_f32=conv_f32)
                 return y
             _, p = ops.instnorm_act(conv_f32, do_norm=inorm, eps=norm.eps if inorm else 1e-5, act=act,
-                                    act_param=act_param, want_f32=False, want_planes=True, prec=prec)
+                                    act_param=act_param, want_f32=False, want_planes=True, prec=prec,
+                                    out_planes=out_planes)
             return p
         # attention works on the normalised, un-activated tensor: needs it as f32 (residual) and planes (qkv conv)
         y, p = ops.instnorm_act(conv_f32, do_norm=inorm, eps=norm.eps if inorm else 1e-5, act=None, want_f32=True,
                                 want_planes=True, prec=prec, out_f32=conv_f32)
         if want_final_f32:
             return attn.run(y, p, want_f32=True, want_planes=False)[0]
-        return attn.run(y, p, act=act, act_param=act_param, want_f32=False, want_planes=True)[1]
+        return attn.run(y, p, act=act, act_param=act_param, want_f32=False, want_planes=True, out_planes=out_planes)[1]
 
-    def run(self, a_in, prec, train=False):
+    def run(self, a_in, prec, train=False, out=None):
         """a_in: Planes holding this block's (already down-activated) input; for the outermost block a tuple
         (x0, x1|None) of f32 NCHW tensors (torch.cat([x0, x1], 1) is fused into the layout conversion).
         Outermost: returns f32 NHWC output.  Otherwise returns Planes of up_act(x') for the parent."""
@@ -284,6 +303,22 @@ class UnetSkipConnectionBlock(nn.Module):
             if isinstance(a_in, tuple):
                 a_in = ops.nchw_to_planes(a_in[0], a_in[1], prec=prec)
             f32, _ = ops.conv2d(a_in, pk["down"], scale=sc, shift=sh, want_f32=True)
+        low = self._lowres(pk, prec)
+        if low is not None:
+            # up-path operand at the LOW resolution: [skip | x'] written straight into one concat buffer by their producers
+            if self.innermost:
+                cat = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, prec)
+            else:
+                c_skip, p_skip, c_xp, p_xp = pk["cat_geom"]
+                n_, h_, w_ = f32.shape[:3]
+                cat = ops.Planes(n_, h_, w_, c_skip + c_xp, prec=prec, device=f32.device, cpad=p_skip + p_xp)
+                a_mid = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, prec,
+                                     out_planes=cat.window(0, c_skip))
+                sub.run(a_mid, prec, out=cat.window(p_skip, c_xp))
+            f32 = low(cat)
+            if self.outermost:
+                return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], None, 0.0, prec, want_final_f32=True)
+            return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], up_act, up_par, prec, out_planes=out)
         a_mid = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, prec)
         # ---- child + up-path input
         if self.innermost:
@@ -302,7 +337,7 @@ class UnetSkipConnectionBlock(nn.Module):
             f32, _ = ops.conv2d(u, pk["up"], scale=sc, shift=sh, want_f32=True)
         if self.outermost:
             return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], None, 0.0, prec, want_final_f32=True)
-        return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], up_act, up_par, prec)
+        return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], up_act, up_par, prec, out_planes=out)
 
     # ------------------------------------------------------------------ training engine (row U6)
     def _run_train(self, a_in, prec, pk):

@@ -49,6 +49,9 @@ PRECISIONS = {
     "bf16": (_lib.FMT_BF16, False),
 }
 DEFAULT_PRECISION = "fp16x3"
+# Inference U-Net decoders evaluate upsample -> conv3x3 at the low resolution (UpsampledConv3x3); False = materialise
+# the upsampled concat (upsample2x_cat) and convolve at the high resolution, as the training tape does.
+UPCONV_LOWRES = True
 
 
 def resolve_precision(p):
@@ -523,6 +526,42 @@ class TapStackedConv3x3:
         return y
 
 
+class UpsampledConv3x3:
+    """nn.Upsample(x2, bilinear) -> Conv2d(3x3, pad 1) (unet.py:138-146) evaluated at the LOW resolution: the channel
+    contraction commutes with the interpolation, so one tap-stacked 1x1 GEMM over the low-res planes (9*Cout outputs per
+    pixel, a quarter of the FLOPs of the conv over the upsampled tensor, which is never materialised) is followed by
+    `upconv3x3_gather`, which interpolates and sums the nine shifted partials with the exact border rules."""
+
+    def __init__(self, weight, bias, prec=None, cin_pad=None, chan_map=None):
+        Cout, Cin, kh, kw = weight.shape
+        assert kh == 3 and kw == 3
+        self.Cout, self.Cin = Cout, Cin
+        w2 = weight.detach().float().permute(2, 3, 0, 1).reshape(9 * Cout, Cin, 1, 1).contiguous()  # (tap, co) major
+        self.pc = PackedConv(w2, None, stride=1, pad=0, prec=prec, cin_pad=cin_pad, chan_map=chan_map)
+        self.bias = None if bias is None else _req(bias.detach().float().contiguous(), name="bias")
+
+    def __call__(self, x):
+        """x: low-res Planes [N,h,w,cin_pad] -> f32 NHWC [N,2h,2w,Cout]."""
+        global PROFILE
+        prof, PROFILE = PROFILE, None  # one profile record for GEMM + gather, with the reference formulation's FLOPs
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        try:
+            t, _ = conv2d(x, self.pc, want_f32=True)  # [N,h,w,9*Cout]
+        finally:
+            PROFILE = prof
+        y = torch.empty(x.N, 2 * x.H, 2 * x.W, self.Cout, dtype=torch.float32, device=t.device)
+        check(_lib.load().shineon_upconv3x3_gather(_p(t), _p(self.bias), _p(y), x.N, x.H, x.W, self.Cout, t.shape[-1],
+                                                   _stream()), "shineon_upconv3x3_gather")
+        if prof is not None:
+            e1.record()
+            prof.append((2.0 * x.N * 4 * x.H * x.W * self.Cout * 9 * self.Cin, e0, e1,
+                         (x.N, 2 * x.H, 2 * x.W, self.Cin, x.cpad, self.Cout, 3, 1),
+                         2.0 * x.N * x.H * x.W * self.Cout * 9 * self.Cin))  # [4] = FLOPs actually issued
+        return y
+
+
 def instnorm_act(x, *, do_norm=True, act=None, act_param=0.0, eps=1e-5, want_f32=False, want_planes=True,
                  prec=None, out_f32=None, out_planes=None, ws=None):
     """x: f32 NHWC [N,H,W,C]."""
@@ -534,9 +573,10 @@ def instnorm_act(x, *, do_norm=True, act=None, act_param=0.0, eps=1e-5, want_f32
         out_planes = Planes(N, H, W, Cc, prec=prec, device=x.device)
     if ws is None and do_norm:
         ws = torch.empty(N * Cc * 2, dtype=torch.float64, device=x.device)
-    check(_lib.load().shineon_instnorm_act(_p(x), _p(out_f32), _p(out_planes.hi if out_planes else None),
-                                           _p(out_planes.lo if out_planes else None), _p(ws), N, H, W, Cc,
-                                           out_planes.cpad if out_planes else Cc, float(eps), int(bool(do_norm)),
+    # out_planes may be a channel window of a wider (concat) buffer: pointer offset + the buffer's channel stride
+    check(_lib.load().shineon_instnorm_act(_p(x), _p(out_f32), out_planes._ptr(out_planes.hi) if out_planes else _p(None),
+                                           out_planes._ptr(out_planes.lo) if out_planes else _p(None), _p(ws), N, H, W, Cc,
+                                           out_planes.cstride if out_planes else Cc, float(eps), int(bool(do_norm)),
                                            ACT[act], float(act_param), out_planes.fmt if out_planes else 0,
                                            _stream()), "shineon_instnorm_act")
     return out_f32, out_planes
@@ -564,9 +604,9 @@ def sagan_attention(qkv, x, gamma, Cq, *, act=None, act_param=0.0, want_f32=Fals
     if want_planes and out_planes is None:
         out_planes = Planes(N, H, W, Cc, prec=prec, device=x.device)
     check(_lib.load().shineon_sagan_attention(_p(qkv), _p(x), _p(gamma), _p(out_f32),
-                                              _p(out_planes.hi if out_planes else None),
-                                              _p(out_planes.lo if out_planes else None), N, H * W, Cc, Cq,
-                                              out_planes.cpad if out_planes else Cc, ACT[act], float(act_param),
+                                              out_planes._ptr(out_planes.hi) if out_planes else _p(None),
+                                              out_planes._ptr(out_planes.lo) if out_planes else _p(None), N, H * W, Cc, Cq,
+                                              out_planes.cstride if out_planes else Cc, ACT[act], float(act_param),
                                               out_planes.fmt if out_planes else 0, _stream()), "shineon_sagan_attention")
     return out_f32, out_planes
 

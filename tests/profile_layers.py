@@ -34,10 +34,12 @@ def main():
     print(f"step {total:.3f} ms for {frames} frames ({frames / total * 1e3:.0f} fps) precision {prec}")
     tconv = 0.0
     print(f"{'N':>4} {'HxW':>9} {'Cin':>5} {'Cout':>5} k s | {'ms':>8} {'TF/s':>8} {'GF':>8}")
-    for fl, s, e, (N, H, W, Cin, cpad, Cout, k, st) in prof:
+    for rec in prof:  # (algorithmic FLOPs, start, end, shape[, issued FLOPs]): rows with a 5th field = low-res GEMM + gather
+        fl, s, e, (N, H, W, Cin, cpad, Cout, k, st) = rec[:4]
         ms = s.elapsed_time(e)
         tconv += ms
-        print(f"{N:4d} {H:4d}x{W:<4d} {Cin:5d} {Cout:5d} {k} {st} | {ms:8.3f} {fl / ms / 1e9:8.1f} {fl / 1e9:8.2f}")
+        print(f"{N:4d} {H:4d}x{W:<4d} {Cin:5d} {Cout:5d} {k} {st} | {ms:8.3f} {fl / ms / 1e9:8.1f} {fl / 1e9:8.2f}"
+              + (f"  (issued {rec[4] / 1e9:.2f} GF: low-res GEMM + gather)" if len(rec) > 4 else ""))
     print(f"conv total {tconv:.3f} ms = {tconv / total * 100:.1f}% of step; non-conv {total - tconv:.3f} ms")
 
 

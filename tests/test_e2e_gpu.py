@@ -52,6 +52,28 @@ def test_tom_matches_oracle_and_golden(cuda, name):
     assert (q(got[2].cpu()) - q(want[2])).abs().max().item() <= 1
 
 
+def test_tom_materialised_upsample_path_agrees(cuda):
+    """ops.UPCONV_LOWRES=False keeps the decoder on upsample2x_cat + conv3x3 at the high resolution (the form the
+    training tape uses); both formulations must agree with the oracle and with each other far inside the tolerance."""
+    from shineon_virtual_tryon_b200 import ops
+
+    name = next(iter(cases.TOM_CASES))
+    over = cases.TOM_CASES[name][0]
+    model, sd = build_model("unet_mask", **over)
+    person, cloth, flows = cases.tom_inputs(name)
+    with torch.no_grad():
+        low = model(_cuda(person), _cuda(cloth), _cuda(flows))
+        ops.UPCONV_LOWRES = False
+        try:
+            full = model(_cuda(person), _cuda(cloth), _cuda(flows))
+        finally:
+            ops.UPCONV_LOWRES = True
+        want = unet.tom_forward(sd, person, cloth, flows=flows, resample=fo.resample2d_fwd, **_tom_kwargs(over))
+    for a, b, w in zip(low[:3], full[:3], want[:3]):
+        assert_close(b, w, what=f"{name}: materialised-upsample path vs oracle")
+        assert (a - b).abs().max().item() < 2e-4
+
+
 @pytest.mark.parametrize("name", list(cases.GMM_CASES))
 def test_gmm_matches_oracle_and_golden(cuda, name):
     model, sd = build_model("warp")

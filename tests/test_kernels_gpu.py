@@ -144,6 +144,22 @@ def test_tap_stacked_conv3x3(ops):
     assert_close(nchw(y), F.conv2d(x, w, b, padding=1), atol=3e-5, rtol=1e-4, what="tap-stacked conv")
 
 
+@pytest.mark.parametrize("shape", [(2, 128, 12, 9, 4), (1, 64, 1, 3, 5), (2, 192, 8, 6, 64), (1, 64, 5, 1, 36)])
+def test_upsampled_conv3x3_at_low_resolution(ops, shape):
+    """nn.Upsample(x2, bilinear) -> Conv2d(3x3, pad 1) (unet.py:138-146) from the tap-stacked low-res GEMM +
+    upconv3x3_gather: must equal the conv over the materialised upsample, borders included (1-pixel-wide inputs too)."""
+    g = torch.Generator().manual_seed(45)
+    N, Cin, h, w, Cout = shape
+    x = torch.randn(N, Cin, h, w, generator=g)
+    wt = torch.randn(Cout, Cin, 3, 3, generator=g) * 0.03
+    b = torch.randn(Cout, generator=g) * 0.1
+    want = F.conv2d(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), wt, b, padding=1)
+    conv = ops.UpsampledConv3x3(wt.cuda(), b.cuda())
+    y = conv(_planes_from(ops, x))
+    assert tuple(y.shape) == (N, 2 * h, 2 * w, Cout)
+    assert_close(nchw(y), want, atol=3e-5, rtol=1e-4, what="upsample->conv3x3 at low resolution")
+
+
 def test_deconv_as_phase_convs(ops):
     """ConvTranspose2d(4,2,1) (submodules.py:34-38) = 4 phase-wise 2x2 convolutions scattered into the output."""
     g = torch.Generator().manual_seed(11)
