@@ -585,10 +585,17 @@ extern "C" int shineon_col2im3x3(const float* t, const float* bias, float* y, in
   return after_launch("col2im3x3_kernel");
 }
 
+int shineon_upconv3x3_gather_tma(const float* t, const float* bias, float* y, int N, int h, int w, int Cout, int tstride,
+                                 cudaStream_t stream);  // upconv_gather.cu
+
 extern "C" int shineon_upconv3x3_gather(const float* t, const float* bias, float* y, int N, int h, int w, int Cout,
                                         int tstride, shineon_stream_t stream) {
   SHINEON_REQUIRE(t && y, "upconv3x3_gather: null pointer");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && h > 0 && w > 0 && Cout > 0 && tstride >= 9 * Cout, "upconv3x3_gather: bad shape");
+  {  // TMA-staged variant (upconv_gather.cu) where the channel count allows 32-channel boxes
+    const int rc = shineon_upconv3x3_gather_tma(t, bias, y, N, h, w, Cout, tstride, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
   const int vec = (Cout % 4 == 0 && tstride % 4 == 0) ? 4 : 1;
   const int groups = Cout / vec;
   int gpb = 1;  // channel groups per CTA (power of two <= 8); the other 256/gpb threads tile low-res pixels

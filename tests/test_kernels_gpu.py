@@ -144,7 +144,8 @@ def test_tap_stacked_conv3x3(ops):
     assert_close(nchw(y), F.conv2d(x, w, b, padding=1), atol=3e-5, rtol=1e-4, what="tap-stacked conv")
 
 
-@pytest.mark.parametrize("shape", [(2, 128, 12, 9, 4), (1, 64, 1, 3, 5), (2, 192, 8, 6, 64), (1, 64, 5, 1, 36)])
+@pytest.mark.parametrize("shape", [(2, 128, 12, 9, 4), (1, 64, 1, 3, 5), (2, 192, 8, 6, 64), (1, 64, 5, 1, 36), (3, 64, 7, 11, 32),
+                                   (1, 128, 1, 1, 96)])
 def test_upsampled_conv3x3_at_low_resolution(ops, shape):
     """nn.Upsample(x2, bilinear) -> Conv2d(3x3, pad 1) (unet.py:138-146) from the tap-stacked low-res GEMM +
     upconv3x3_gather: must equal the conv over the materialised upsample, borders included (1-pixel-wide inputs too)."""
