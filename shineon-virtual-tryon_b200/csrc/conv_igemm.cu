@@ -32,7 +32,9 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;  // two per TMEM lane quarter (alternating 32-column chunks): one warp per scheduler was
+                              // latency-bound on small-K layers (tcgen05.ld -> math -> store chain fully exposed)
+constexpr int kThreads = (2 + kEpiWarps) * 32;
 
 struct ConvArgs {
   // tile geometry
@@ -42,6 +44,7 @@ struct ConvArgs {
   int kh, kw, stride, pad_h, pad_w;
   int cin_pad, cin_blocks, x_cstride;
   int num_kb, stages;
+  int stage_off;     // byte offset (from the 1024-aligned tile base) of the epilogue transpose buffers, < 0 = direct stores
   int n_tiles, total_tiles;  // channel tiles per pixel tile, pixel tiles * channel tiles
   int w_per_image;           // 1: the B operand is a [N][Cout][K] batch indexed by the tile's image (needs nb == 1)
   // epilogue
@@ -143,8 +146,46 @@ __device__ __forceinline__ void conv_store_row(const float (&vals)[32], int c_fi
   }
 }
 
+// Coalesced form of conv_store_row for a full-warp 32-row x 32-channel chunk.  tcgen05.ld leaves each lane with ONE
+// pixel row (32 consecutive channels = 128 B), so a direct 16-byte store instruction touches 32 different cache lines:
+// the epilogue warps then sit on the store queue (ncu: half of all stall samples were the WAR wait on the address
+// registers of in-flight stores, profiles/r01_conv_epilogue_store.md) and small-K layers are epilogue-bound.  The chunk
+// is transposed through a 4 KB per-warp staging buffer (16-byte unit j of row r at j ^ (r & 7): conflict-free both
+// ways) so that eight lanes write one pixel's 128 contiguous bytes and a store instruction covers 4 full lines.
+// rowbase[it] = element offset (pix * out_cstride + out_coffset) of row it*4 + lane/8; okmask bit r = row r is stored.
+__device__ __forceinline__ void conv_store_chunk_coalesced(const float (&vals)[32], float4* stage, int lane,
+                                                           const long (&rowbase)[8], uint32_t okmask, int c_first, int cnt,
+                                                           const ConvArgs& a) {
+  __syncwarp();  // the previous chunk's reads of the staging buffer are done
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    stage[lane * 8 + (j ^ (lane & 7))] = make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
+  __syncwarp();
+  const int u = lane & 7;
+  if (4 * u >= cnt) return;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + (lane >> 3);
+    if (!((okmask >> row) & 1u)) continue;
+    const float4 v = stage[row * 8 + (u ^ (row & 7))];
+    const long base = rowbase[it] + c_first + 4 * u;
+    if (a.y_f32) *reinterpret_cast<float4*>(a.y_f32 + base) = v;
+    if (a.y_hi) {
+      plane_t h0, h1, h2, h3, l0, l1, l2, l3;
+      split16(v.x, a.fmt, h0, l0);
+      split16(v.y, a.fmt, h1, l1);
+      split16(v.z, a.fmt, h2, l2);
+      split16(v.w, a.fmt, h3, l3);
+      *reinterpret_cast<uint2*>(a.y_hi + base) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+      if (a.y_lo)
+        *reinterpret_cast<uint2*>(a.y_lo + base) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------- kernel
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int NTHREADS>  // named barrier 1 over the kernel's epilogue warps only
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
 // Persistent: one CTA per SM walks output tiles (tile = blockIdx.x + i*gridDim.x, channel tile fastest so that
 // neighbouring CTAs share the same activation tile in L2).  Two TMEM accumulators: the epilogue of tile i
@@ -192,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);   // one tcgen05.commit
-      mbar_init(bar_tempty + 8 * b, 4);  // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8 * b, kEpiWarps);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -289,9 +330,13 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else {
     // ===================================================== epilogue: TMEM -> registers -> global
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int ew = warp - 2;  // epilogue warp index; warps ew and ew + 4 share a lane quarter
+    const int half = ew >> 2;
     const int r = q * 32 + lane;
     const int wi = r % a.bw, hi_ = (r / a.bw) % a.bh, ni = r / (a.bw * a.bh);
     constexpr int kChunk = BN < 32 ? BN : 32;
+    float4* const stage = a.stage_off < 0 ? nullptr
+        : reinterpret_cast<float4*>(smem_raw + (tiles - smem_u32(smem_raw)) + a.stage_off) + ew * 256;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
@@ -300,22 +345,32 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int n = tn * a.nb + ni, oh = th * a.bh + hi_, ow = tw * a.bw + wi;
       const bool row_ok = ni < a.nb && n < a.N && oh < a.Ho && ow < a.Wo;
       const long pix = ((long)n * a.out_H + (oh * a.oh_mul + a.oh_off)) * a.out_W + (ow * a.ow_mul + a.ow_off);
+      // coalesced stores: every lane needs the output offsets of the 8 rows it will write (row = it*4 + lane/8)
+      const bool co_ok = kChunk == 32 && stage != nullptr && (a.out_cstride & 3) == 0 &&
+                         ((a.out_coffset + cn0) & 3) == 0;  // warp-uniform
+      const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+      long rowbase[8];
+      if (co_ok) {
+        const long mybase = pix * a.out_cstride + a.out_coffset;
+#pragma unroll
+        for (int it2 = 0; it2 < 8; ++it2) rowbase[it2] = __shfl_sync(0xffffffffu, mybase, it2 * 4 + (lane >> 3));
+      }
       // stage this tile's bias / folded-BN window (all 4 epilogue warps are past the previous tile's reads)
-      epi_bar_sync();
-      for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      epi_bar_sync<kEpiWarps * 32>();
+      for (int i = threadIdx.x - 64; i < BN; i += kEpiWarps * 32) {
         const int c = cn0 + i;
         const bool ok = c < a.Cout;
         s_bias[i] = (ok && a.bias) ? __ldg(a.bias + c) : 0.f;
         s_scale[i] = (ok && a.scale) ? __ldg(a.scale + c) : 1.f;
         s_shift[i] = (ok && a.scale) ? __ldg(a.shift + c) : 0.f;
       }
-      epi_bar_sync();
+      epi_bar_sync<kEpiWarps * 32>();
       const int buf = it & 1;
       mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + buf * kAccCols;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += kChunk) {
+      for (int c0 = half * kChunk; c0 < BN; c0 += 2 * kChunk) {
         if (cn0 + c0 >= a.Cout) break;  // warp-uniform
         uint32_t v[32];
         const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -343,7 +398,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (i < kChunk) vals[i] = fmaf(vals[i], s_scale[c0 + i], s_shift[c0 + i]);
         }
         act_chunk_dispatch(vals, a.post_act, a.act_param);
-        if (row_ok) conv_store_row(vals, cn0 + c0, cnt, pix, a);
+        if (co_ok && (cnt & 3) == 0)
+          conv_store_chunk_coalesced(vals, stage, lane, rowbase, okmask, cn0 + c0, cnt, a);
+        else if (row_ok)
+          conv_store_row(vals, cn0 + c0, cnt, pix, a);
       }
       // hand the accumulator back to the MMA warp
       tc_fence_before();
@@ -540,7 +598,7 @@ __global__ void __launch_bounds__(kI2cThreads, 1)
       const int n = tn * a.nb + ni, oh = th * a.bh + hi_, ow = tw * a.bw + wi;
       const bool row_ok = ni < a.nb && n < a.N && oh < a.Ho && ow < a.Wo;
       const long pix = ((long)n * a.out_H + (oh * a.oh_mul + a.oh_off)) * a.out_W + (ow * a.ow_mul + a.ow_off);
-      epi_bar_sync();
+      epi_bar_sync<128>();
       for (int i = et; i < BN; i += 128) {
         const int c = cn0 + i;
         const bool ok = c < a.Cout;
@@ -548,7 +606,7 @@ __global__ void __launch_bounds__(kI2cThreads, 1)
         s_scale[i] = (ok && a.scale) ? __ldg(a.scale + c) : 1.f;
         s_shift[i] = (ok && a.scale) ? __ldg(a.shift + c) : 0.f;
       }
-      epi_bar_sync();
+      epi_bar_sync<128>();
       const int buf = it & 1;
       mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
@@ -730,8 +788,20 @@ static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CU
     }
   }
   while (stages > 1 && stages * kStageBytes + 1024 > max_dyn_smem) --stages;
+  // f32-only outputs of short-mainloop layers are epilogue-bound: give them the transpose buffers for coalesced
+  // stores (4 KB per epilogue warp) when that leaves at least min(num_kb, 2) pipeline stages
+  constexpr int kStagingBytes = kEpiWarps * 4096;
+  a.stage_off = -1;
+  if (a.y_hi == nullptr && a.y_f32 != nullptr && BN >= 32 && a.num_kb <= 16) {
+    int st2 = stages;
+    while (st2 > 1 && st2 * kStageBytes + 1024 + kStagingBytes > max_dyn_smem) --st2;
+    if (st2 * kStageBytes + 1024 + kStagingBytes <= max_dyn_smem && st2 >= (a.num_kb < 2 ? a.num_kb : 2)) {
+      stages = st2;
+      a.stage_off = stages * kStageBytes;
+    }
+  }
   a.stages = stages;
-  const int smem_bytes = stages * kStageBytes + 1024;
+  const int smem_bytes = stages * kStageBytes + 1024 + (a.stage_off >= 0 ? kStagingBytes : 0);
   if (smem_bytes > max_dyn_smem) return fail(SHINEON_ERR_UNSUPPORTED, "conv_igemm: tile does not fit in shared memory");
   a.n_tiles = cdiv(a.Cout, BN);
   const long total = (long)m_tiles * a.n_tiles;
@@ -777,6 +847,7 @@ static int fill_args(const shineon_conv2d_params* p, ConvArgs& a) {
   a.acc_scale = p->acc_scale == 0.f ? 1.f : p->acc_scale;
   a.idesc = 0;
   a.idesc_cat = 0;
+  a.stage_off = -1;
   a.y_f32 = p->y_f32; a.y_hi = (plane_t*)p->y_hi; a.y_lo = (plane_t*)p->y_lo;
   a.oh_mul = p->oh_mul ? p->oh_mul : 1; a.ow_mul = p->ow_mul ? p->ow_mul : 1;
   a.oh_off = p->oh_off; a.ow_off = p->ow_off;
