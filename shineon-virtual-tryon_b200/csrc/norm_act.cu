@@ -152,6 +152,54 @@ __global__ void __launch_bounds__(256)
   if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
+// Tiled form (C0 + C1 <= 32): the kernel above reads NCHW rows with neighbouring threads two columns apart and writes
+// one 16-byte fragment per 2*cpad-byte pixel row (uncoalesced both ways: 2.6 TB/s, profiles/r01_launches_summary.md).
+// Here a CTA stages the two input rows of one output row Y for 32 output columns (64 input columns x C channels,
+// 256-byte coalesced reads per channel row) in shared memory and then writes whole pixels: consecutive threads own
+// consecutive 8-channel groups, i.e. 2*cpad contiguous bytes per pixel and plane.
+constexpr int kS2dTX = 32;
+template <int FMT>
+__global__ void __launch_bounds__(256)
+    nchw_s2d_planes_tiled_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
+                                 plane_t* __restrict__ yh, plane_t* __restrict__ yl, int H, int W, int cpad) {
+  __shared__ float s[2][32][2 * kS2dTX + 1];
+  const int n = blockIdx.z, Y = blockIdx.y, X0 = blockIdx.x * kS2dTX;
+  const int Wz = W / 2 + 1;
+  const int C = C0 + C1;
+  const int HW = H * W;
+  const int ixb = 2 * X0 - 1;  // input column of local column 0
+  for (int e = threadIdx.x; e < 2 * C * 2 * kS2dTX; e += 256) {
+    const int lc = e % (2 * kS2dTX);
+    const int rc = e / (2 * kS2dTX);
+    const int c = rc % C, r = rc / C;
+    const int iy = 2 * Y - 1 + r, ix = ixb + lc;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v = c < C0 ? __ldg(x0 + ((long)n * C0 + c) * HW + iy * W + ix) : __ldg(x1 + ((long)n * C1 + (c - C0)) * HW + iy * W + ix);
+    s[r][c][lc] = v;
+  }
+  __syncthreads();
+  const int groups = cpad >> 3;
+  for (int item = threadIdx.x; item < kS2dTX * groups; item += 256) {
+    const int g = item % groups, xl = item / groups;
+    const int X = X0 + xl;
+    if (X >= Wz) break;
+    __align__(16) plane_t hi[8];
+    __align__(16) plane_t lo[8];
+    int k = g * 8;
+    int q = k / C, c = k - q * C;  // q = py*2+px
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = q < 4 ? s[q >> 1][c][2 * xl + (q & 1)] : 0.f;
+      split16(v, FMT, hi[j], lo[j]);
+      if (++c == C) { c = 0; ++q; }
+    }
+    const long o = (((long)n * (H / 2 + 1) + Y) * Wz + X) * cpad + g * 8;
+    *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
+    if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 // ------------------------------------------------------------------------------ tap-stacked 3x3 conv: col2im
 // For a 3x3 conv with very few output channels (the U-Net's final 128 -> 4 layer) the implicit GEMM is run
 // "transposed": one 1x1 GEMM produces, for every INPUT pixel q, the 9*Cout partial products
@@ -328,7 +376,8 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Pass 2: y = act((x - mean) * rsqrt(var + eps)); 4 channels per thread (C % 4 == 0) or 1.
+// Pass 2: y = act((x - mean) * rsqrt(var + eps)); VEC = 8 / 4 / 1 consecutive channels per thread (largest that divides
+// C): 8 channels = two 128-bit loads in flight per thread and one 128-bit store per plane.
 template <int FMT, int ACT, int VEC>  // ACT < 0: runtime activation id
 __global__ void __launch_bounds__(256)
     instnorm_apply_kernel(const float* __restrict__ x, const double* __restrict__ ws, float* __restrict__ yf,
@@ -358,9 +407,12 @@ __global__ void __launch_bounds__(256)
     const int g = (int)(e - p * (unsigned)cg);
     const long xi = ((long)n * HW + p) * C + g * VEC;
     float v[VEC];
-    if (VEC == 4) {
-      float4 t = *reinterpret_cast<const float4*>(x + xi);
-      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    if constexpr (VEC >= 4) {
+#pragma unroll
+      for (int j = 0; j < VEC; j += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(x + xi + j));
+        v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+      }
     } else {
       v[0] = x[xi];
     }
@@ -370,17 +422,28 @@ __global__ void __launch_bounds__(256)
       v[j] = apply_act((v[j] - s_tab[c]) * s_tab[C + c], act, act_param);
     }
     if (yf) {
-      if (VEC == 4)
-        *reinterpret_cast<float4*>(yf + xi) = make_float4(v[0], v[1], v[2], v[3]);
-      else
+      if constexpr (VEC >= 4) {
+#pragma unroll
+        for (int j = 0; j < VEC; j += 4)
+          *reinterpret_cast<float4*>(yf + xi + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
         yf[xi] = v[0];
+      }
     }
     if (yh) {
       const long po = ((long)n * HW + p) * cpad + g * VEC;
       plane_t h[VEC], l[VEC];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) split16(v[j], FMT, h[j], l[j]);
-      if (VEC == 4) {
+      if constexpr (VEC == 8) {
+        *reinterpret_cast<uint4*>(yh + po) =
+            make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                       (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
+        if (yl)
+          *reinterpret_cast<uint4*>(yl + po) =
+              make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
+                         (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
+      } else if constexpr (VEC == 4) {
         *reinterpret_cast<uint2*>(yh + po) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
         if (yl) *reinterpret_cast<uint2*>(yl + po) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
       } else {
@@ -568,6 +631,14 @@ extern "C" int shineon_nchw_s2d_planes(const float* x0, int C0, const float* x1,
   SHINEON_REQUIRE(x0 && y_hi && C0 > 0 && (x1 == nullptr) == (C1 == 0), "nchw_s2d_planes: bad input tensors");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && H / 2 + 1 <= 65535, "nchw_s2d_planes: bad shape (H, W must be even)");
   SHINEON_REQUIRE(cpad % 8 == 0 && cpad >= 4 * (C0 + C1), "nchw_s2d_planes: cpad %d too small / not a multiple of 8", cpad);
+  if (C0 + C1 <= 32) {
+    dim3 tgrid(cdiv(W / 2 + 1, kS2dTX), H / 2 + 1, N);
+    if (plane_fmt == SHINEON_FMT_FP16)
+      nchw_s2d_planes_tiled_kernel<SHINEON_FMT_FP16><<<tgrid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad);
+    else
+      nchw_s2d_planes_tiled_kernel<SHINEON_FMT_BF16><<<tgrid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad);
+    return after_launch("nchw_s2d_planes_tiled_kernel");
+  }
   dim3 grid(cdiv((W / 2 + 1) * (cpad / 8), 256), H / 2 + 1, N);
   if (plane_fmt == SHINEON_FMT_FP16)
     nchw_s2d_planes_kernel<SHINEON_FMT_FP16><<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad);
@@ -643,7 +714,9 @@ extern "C" int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, vo
     int rc = after_launch("instnorm_stats_kernel");
     if (rc) return rc;
   }
-  const int vecC = (C % 4 == 0) ? 4 : 1;
+  // 128-bit plane stores need 16-byte aligned rows: cpad % 8 and 16-byte aligned plane pointers (channel windows are)
+  const bool al8 = (C % 8 == 0) && (!y_hi || (cpad % 8 == 0 && ((reinterpret_cast<uintptr_t>(y_hi) | reinterpret_cast<uintptr_t>(y_lo)) & 15) == 0));
+  const int vecC = al8 ? 8 : ((C % 4 == 0) ? 4 : 1);
   SHINEON_REQUIRE((long)HW * (C / vecC) < (1l << 31), "instnorm_act: image too large");
   dim3 grid(grid_x((long)HW * (C / vecC), 256), N);
   const size_t sm = 2 * C * sizeof(float);
@@ -659,9 +732,9 @@ extern "C" int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, vo
     default: SHINEON_IN_APPLY(F, -1, V); break;                           \
   }
   if (plane_fmt == SHINEON_FMT_FP16) {
-    if (vecC == 4) { SHINEON_IN_ACT(SHINEON_FMT_FP16, 4) } else { SHINEON_IN_ACT(SHINEON_FMT_FP16, 1) }
+    if (vecC == 8) { SHINEON_IN_ACT(SHINEON_FMT_FP16, 8) } else if (vecC == 4) { SHINEON_IN_ACT(SHINEON_FMT_FP16, 4) } else { SHINEON_IN_ACT(SHINEON_FMT_FP16, 1) }
   } else {
-    if (vecC == 4) { SHINEON_IN_ACT(SHINEON_FMT_BF16, 4) } else { SHINEON_IN_ACT(SHINEON_FMT_BF16, 1) }
+    if (vecC == 8) { SHINEON_IN_ACT(SHINEON_FMT_BF16, 8) } else if (vecC == 4) { SHINEON_IN_ACT(SHINEON_FMT_BF16, 4) } else { SHINEON_IN_ACT(SHINEON_FMT_BF16, 1) }
   }
 #undef SHINEON_IN_ACT
 #undef SHINEON_IN_APPLY

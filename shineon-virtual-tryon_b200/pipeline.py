@@ -35,30 +35,48 @@ class TryOnPipeline:
         call's kernels.  Returns (out_host, done_event); `out_host` is valid once `done_event` has completed (or after
         a device synchronize) and is reused by the call after next.
         """
+        return self._run_staged((person_gmm_h, cloth_h, person_tom_h), lambda a, c, p: self(a, c, p))
+
+    # keys of the reference's dataset batch the two stages read (datasets/tryon_dataset.py:47-61; WarpModel person
+    # inputs agnostic+cocopose, UnetMaskModel person inputs agnostic+densepose, cloth for both)
+    BATCH_KEYS = ("agnostic", "cocopose", "densepose", "cloth")
+
+    @torch.no_grad()
+    def run_host_batch(self, batch_h):
+        """The same call on a host batch dict keyed like the reference's dataset samples (`agnostic` [F,4,H,W],
+        `cocopose` [F,18,H,W], `densepose` [F,3,H,W], `cloth` [F,3,H,W], pinned f32).  Every key crosses PCIe once
+        (agnostic feeds both stages: 28 channels per frame instead of 22 + 3 + 7); the per-stage channel concatenation
+        is done on the device like base_model.get_and_cat_inputs (util/__init__.py:64-66)."""
+        def stages(agnostic, cocopose, densepose, cloth):
+            return self(torch.cat([agnostic, cocopose], 1), cloth, torch.cat([agnostic, densepose], 1))
+
+        return self._run_staged(tuple(batch_h[k] for k in self.BATCH_KEYS), stages)
+
+    def _run_staged(self, host_tensors, fn):
         dev = next(self.tom_model.parameters()).device
         cur = torch.cuda.current_stream(dev)
-        shapes = (tuple(person_gmm_h.shape), tuple(cloth_h.shape), tuple(person_tom_h.shape))
+        shapes = tuple(tuple(t.shape) for t in host_tensors)
         st = self._host_state
         if st is None or st["shapes"] != shapes:
+            frames, hw = shapes[0][0], shapes[0][2:]
             st = self._host_state = dict(
                 shapes=shapes, call=0, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev),
                 dev_in=[tuple(torch.empty(s, dtype=torch.float32, device=dev) for s in shapes) for _ in range(2)],
                 in_free=[torch.cuda.Event() for _ in range(2)], in_ready=[torch.cuda.Event() for _ in range(2)],
                 out_done=[torch.cuda.Event() for _ in range(2)],
-                host_out=[torch.empty((shapes[1][0], 3) + shapes[1][2:], dtype=torch.float32).pin_memory() for _ in range(2)])
+                host_out=[torch.empty((frames, 3) + hw, dtype=torch.float32).pin_memory() for _ in range(2)])
             for e in st["in_free"] + st["out_done"]:
                 e.record(cur)
         slot = st["call"] % 2
         st["call"] += 1
-        a, c, p = st["dev_in"][slot]
+        dev_in = st["dev_in"][slot]
         with torch.cuda.stream(st["s_in"]):
             st["s_in"].wait_event(st["in_free"][slot])  # kernels of the call before last have consumed this slot
-            a.copy_(person_gmm_h, non_blocking=True)
-            c.copy_(cloth_h, non_blocking=True)
-            p.copy_(person_tom_h, non_blocking=True)
+            for d, h in zip(dev_in, host_tensors):
+                d.copy_(h, non_blocking=True)
             st["in_ready"][slot].record(st["s_in"])
         cur.wait_event(st["in_ready"][slot])
-        p_tryons, _, _ = self(a, c, p)
+        p_tryons, _, _ = fn(*dev_in)
         st["in_free"][slot].record(cur)
         computed = torch.cuda.Event()
         computed.record(cur)

@@ -129,6 +129,31 @@ def test_tryon_pipeline_5_frame_clip(cuda):
         assert_close(gt, w, what=f"pipeline {n}")
 
 
+def test_host_buffer_entry_points_match_device_call(cuda):
+    """TryOnPipeline.run_host / run_host_batch (pinned host tensors in, pinned host image out, double-buffered
+    copies) return exactly what the device-resident call computes, call after call (slot reuse)."""
+    from shineon_virtual_tryon_b200.pipeline import TryOnPipeline
+
+    warp, _ = build_model("warp")
+    tom, _ = build_model("unet_mask")
+    pipe = TryOnPipeline(warp, tom)
+    g = torch.Generator().manual_seed(6)
+    for rep in range(3):
+        batch = {"agnostic": torch.randn(2, 4, 256, 192, generator=g), "cocopose": torch.randn(2, 18, 256, 192, generator=g),
+                 "densepose": torch.randn(2, 3, 256, 192, generator=g), "cloth": torch.rand(2, 3, 256, 192, generator=g) * 2 - 1}
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+        a = torch.cat([batch["agnostic"], batch["cocopose"]], 1)
+        p = torch.cat([batch["agnostic"], batch["densepose"]], 1)
+        want = pipe(a.cuda(), batch["cloth"].cuda(), p.cuda())[0].cpu()
+        out, done = pipe.run_host_batch(batch)
+        done.synchronize()
+        assert torch.equal(out, want)
+        out2, done2 = pipe.run_host(a.pin_memory(), batch["cloth"], p.pin_memory())
+        done2.synchronize()
+        assert torch.equal(out2, want)
+    pipe.host_sync()
+
+
 @pytest.mark.parametrize("prec,max_tol,mean_tol", [("bf16x3", 2e-2, 1e-3), ("fp16", 0.3, 1e-2), ("bf16", 1.0, 5e-2)])
 def test_other_precision_modes(cuda, prec, max_tol, mean_tol):
     """Non-default numeric modes: measured error against the fp32 oracle, loose documented bounds."""
