@@ -513,6 +513,14 @@ def run_b200(args, rank, world):
             "traffic": None,
         },
     }
+    # measured DRAM bytes of the same launches from the committed ncu --set full capture (profiles/r01_conv_step_full.md)
+    try:
+        cap = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_step_full.json")))
+        line["roofline"]["traffic"] = cap["conv_dram_bytes_per_launch"]
+        line["roofline"]["traffic_note"] = (f"dram__bytes_read+write per conv_igemm launch, mean over {cap['conv_launches_captured']} of "
+                                            f"{cap['conv_launches_per_step']} launches of one step (ncu --set full, profiles/r01_conv_step_full.md)")
+    except Exception:  # noqa: BLE001  (no capture committed: traffic stays null)
+        pass
     if fast is not None:
         line["other_precisions"] = {
             m: {"value": total_frames / (r["ms"] * 1e-3), "unit": "frames/s", "e2e": total_frames / (r["ms_e2e"] * 1e-3),

@@ -168,15 +168,26 @@ __global__ void __launch_bounds__(256)
   const int C = C0 + C1;
   const int HW = H * W;
   const int ixb = 2 * X0 - 1;  // input column of local column 0
-  for (int e = threadIdx.x; e < 2 * C * 2 * kS2dTX; e += 256) {
+  // all of a thread's loads are issued before the first shared-memory store (up to 16 in flight per thread: with one
+  // 4-byte load at a time the first version of this kernel was latency-bound at 1.9 TB/s)
+  const int total = 2 * C * 2 * kS2dTX;  // <= 4096
+  float v[16];
+#pragma unroll
+  for (int it = 0; it < 16; ++it) {
+    const int e = threadIdx.x + it * 256;
     const int lc = e % (2 * kS2dTX);
     const int rc = e / (2 * kS2dTX);
     const int c = rc % C, r = rc / C;
     const int iy = 2 * Y - 1 + r, ix = ixb + lc;
-    float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-      v = c < C0 ? __ldg(x0 + ((long)n * C0 + c) * HW + iy * W + ix) : __ldg(x1 + ((long)n * C1 + (c - C0)) * HW + iy * W + ix);
-    s[r][c][lc] = v;
+    v[it] = 0.f;
+    if (e < total && iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v[it] = c < C0 ? __ldg(x0 + ((long)n * C0 + c) * HW + iy * W + ix) : __ldg(x1 + ((long)n * C1 + (c - C0)) * HW + iy * W + ix);
+  }
+#pragma unroll
+  for (int it = 0; it < 16; ++it) {
+    const int e = threadIdx.x + it * 256;
+    const int rc = e / (2 * kS2dTX);
+    if (e < total) s[rc / C][rc % C][e % (2 * kS2dTX)] = v[it];
   }
   __syncthreads();
   const int groups = cpad >> 3;
