@@ -408,6 +408,44 @@ int shineon_nhwc_to_nchw_add(const float* x, int x_cstride, float* y, int N, int
 int shineon_maxpool2x2_bwd(const float* x, const float* g_y, int g_cstride, float* g_x, int N, int H, int W, int C,
                            shineon_stream_t stream);
 
+/* ------------------------------------------------------------------ */
+/* Dataset-side per-frame tensor prep                    */
+/* ------------------------------------------------------------------ */
+
+/* Pillow's 8-bit BILINEAR resampling coefficients (Resample.c precompute_coeffs + normalize_coeffs_8bpc) for one axis,
+ * computed on the HOST: bounds[2*out] = (first input index, tap count), kk[out*ksize] = 22-bit fixed-point weights.
+ * Returns ksize (call with kk = NULL to query it) or a negative status.  Replaces the two
+ * Image.resize(..., Image.BILINEAR) calls of get_person_body_silhouette (datasets/tryon_dataset.py:352-358). */
+int shineon_pil_bilinear_coeffs(int in_size, int out_size, int* bounds, int* kk);
+
+/* One call = TryonDataset.get_person_representation + get_cloth_representation (datasets/tryon_dataset.py:156-175,
+ * 203-251, 323-447) for F frames from decoded 8-bit images (channel-last, as np.array(PIL.Image) gives them).
+ * Any input / output pair may be NULL.  Outputs are f32 NCHW device tensors, bit-identical to the reference's. */
+typedef struct {
+  const unsigned char* image;     /* [F,H,W,3] person frame                                  */
+  const unsigned char* parse;     /* [F,H,W]   LIP label map                                 */
+  const unsigned char* cloth;     /* [F,H,W,3]                                               */
+  const unsigned char* densepose; /* [F,H,W,3]                                               */
+  const double* pose;             /* [F,n_joints,3] (x, y, confidence); only for im_cocopose */
+  float* image_out;               /* [F,3,H,W]  ToTensor + Normalize(0.5, 0.5)               */
+  float* cloth_out;               /* [F,3,H,W]                                               */
+  float* cloth_mask_out;          /* [F,1,H,W]  where(cloth >= threshold, 0, 1)[0]           */
+  float* densepose_out;           /* [F,3,H,W]                                               */
+  float* agnostic_out;            /* [F,4,H,W]  silhouette | head                            */
+  float* cocopose_out;            /* [F,n_joints,H,W] constant -1 (tryon_dataset.py:415-423) */
+  float* im_cocopose_out;         /* [F,1,H,W]  joint squares, -1 / 1                        */
+  const int* tab_bounds[4];       /* device copies of shineon_pil_bilinear_coeffs tables for */
+  const int* tab_kk[4];           /*   W -> W/16, H -> H/16, W/16 -> W, H/16 -> H            */
+  int tab_ksize[4];
+  int F, H, W, n_joints, radius;
+  float cloth_mask_threshold;
+} shineon_frame_prep_params;
+int shineon_frame_prep(const shineon_frame_prep_params* p, shineon_stream_t stream);
+
+/* Middlebury .flo payload (the interleaved f32 u,v after the 12-byte header) -> f32 [2,H,W] = (x - 0.5) / 0.5
+ * (flownet2_pytorch/utils/flow_utils.py:7-26 + flow_norm, datasets/tryon_dataset.py:121,288-289). */
+int shineon_flo_decode(const void* flo_payload, float* out, int H, int W, shineon_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,16 @@ class Conv2dWgradParams(C.Structure):
     ]
 
 
+class FramePrepParams(C.Structure):
+    _fields_ = [
+        ("image", c_p), ("parse", c_p), ("cloth", c_p), ("densepose", c_p), ("pose", c_p),
+        ("image_out", c_p), ("cloth_out", c_p), ("cloth_mask_out", c_p), ("densepose_out", c_p), ("agnostic_out", c_p),
+        ("cocopose_out", c_p), ("im_cocopose_out", c_p),
+        ("tab_bounds", c_p * 4), ("tab_kk", c_p * 4), ("tab_ksize", c_i * 4),
+        ("F", c_i), ("H", c_i), ("W", c_i), ("n_joints", c_i), ("radius", c_i), ("cloth_mask_threshold", c_f),
+    ]
+
+
 # name -> argtypes (every function returns int status unless listed in _RESTYPES)
 SIGNATURES = {
     "shineon_version": [],
@@ -76,6 +86,9 @@ SIGNATURES = {
     "shineon_nchw_s2d_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_col2im3x3": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_upconv3x3_gather": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_pil_bilinear_coeffs": [c_i, c_i, c_p, c_p],
+    "shineon_frame_prep": [C.POINTER(FramePrepParams), c_p],
+    "shineon_flo_decode": [c_p, c_p, c_i, c_i, c_p],
     "shineon_instnorm_act": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_f, c_i, c_p],
     "shineon_upsample2x_cat": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     "shineon_sagan_attention": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],

@@ -1,0 +1,287 @@
+// Dataset-side per-frame tensor prep on the GPU (reference: datasets/tryon_dataset.py).
+// The reference builds every network input on the CPU inside Dataset.__getitem__ from decoded 8-bit images:
+//   ToTensor + Normalize(0.5, 0.5)                       tryon_dataset.py:109-119,149-152
+//   cloth mask   where(cloth >= thr, 0, 1)[0]            :168-175   (compares the NORMALISED cloth, as written)
+//   head         im * phead - (1 - phead)                :323-344   (phead = LIP label in a fixed set)
+//   silhouette   (parse > 0) * 255 -> PIL BILINEAR /16 -> PIL BILINEAR x16 -> normalise          :346-367
+//   cocopose     18 channels, constant -1 as written (:415-423) + the square visualisation        :389-447
+//   .flo         Middlebury flow bytes -> (x - 0.5) / 0.5                    flow_utils.py:7-26, tryon_dataset.py:288-289
+// Moving this to the device lets a frame cross PCIe as 10 bytes/pixel of uint8 instead of 112 bytes/pixel of f32.
+// Byte / integer work, bit-exact against the reference: the PIL resize is done with Pillow's own fixed-point scheme
+// (Resample.c: 22-bit coefficients, rounding to uint8 after each pass), coefficients from shineon_pil_bilinear_coeffs.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace shineon {
+
+__device__ __forceinline__ float norm_u8(uint8_t u) {
+  // ToTensor: float(u) / 255 (IEEE division), Normalize: (t - 0.5) / 0.5
+  return __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.f), 0.5f), 0.5f);
+}
+
+// LIP labels kept by get_person_head: HAT 1, HAIR 2, SUNGLASSES 4, SOCKS 8, PANTS 9, SCARF 11, SKIRT 12, FACE 13,
+// LEFT_LEG 16, RIGHT_LEG 17, LEFT_SHOE 18, RIGHT_SHOE 19
+constexpr uint32_t kHeadMask = (1u << 1) | (1u << 2) | (1u << 4) | (1u << 8) | (1u << 9) | (1u << 11) | (1u << 12) |
+                               (1u << 13) | (1u << 16) | (1u << 17) | (1u << 18) | (1u << 19);
+
+struct PrepArgs {
+  const uint8_t* image;      // [F,H,W,3] or null
+  const uint8_t* parse;      // [F,H,W] or null (needed for head)
+  const uint8_t* cloth;      // [F,H,W,3] or null
+  const uint8_t* densepose;  // [F,H,W,3] or null
+  float* image_out;          // [F,3,H,W] or null
+  float* cloth_out;          // [F,3,H,W]
+  float* cloth_mask_out;     // [F,1,H,W]
+  float* densepose_out;      // [F,3,H,W]
+  float* agnostic_out;       // [F,4,H,W]: channel 0 = silhouette (other kernel), 1..3 = head
+  float* cocopose_out;       // [F,J,H,W] constant -1
+  int HW, J;
+  float cloth_thr;
+};
+
+// 4 consecutive pixels per thread: 12-byte (3 x uchar4) reads of the interleaved images, float4 stores per channel plane
+__global__ void __launch_bounds__(256) frame_prep_pointwise_kernel(const PrepArgs a) {
+  const int f = blockIdx.y;
+  const int p0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (p0 >= a.HW) return;
+  const long fo = (long)f * a.HW;
+  auto load12 = [&](const uint8_t* base, uint8_t (&v)[12]) {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(base + (fo + p0) * 3);  // (fo + p0) * 3 is a multiple of 4
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint32_t w = __ldg(s + i);
+      v[4 * i] = w & 0xff; v[4 * i + 1] = (w >> 8) & 0xff; v[4 * i + 2] = (w >> 16) & 0xff; v[4 * i + 3] = w >> 24;
+    }
+  };
+  auto store_rgb = [&](float* out, const float (&v)[12]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      *reinterpret_cast<float4*>(out + ((long)f * 3 + c) * a.HW + p0) = make_float4(v[c], v[3 + c], v[6 + c], v[9 + c]);
+  };
+  uint8_t u[12];
+  float v[12];
+  if (a.cloth) {
+    load12(a.cloth, u);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[i] = norm_u8(u[i]);
+    store_rgb(a.cloth_out, v);
+    if (a.cloth_mask_out)  // channel 0 only (tryon_dataset.py:174)
+      *reinterpret_cast<float4*>(a.cloth_mask_out + fo + p0) =
+          make_float4(v[0] >= a.cloth_thr ? 0.f : 1.f, v[3] >= a.cloth_thr ? 0.f : 1.f, v[6] >= a.cloth_thr ? 0.f : 1.f,
+                      v[9] >= a.cloth_thr ? 0.f : 1.f);
+  }
+  if (a.densepose) {
+    load12(a.densepose, u);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[i] = norm_u8(u[i]);
+    store_rgb(a.densepose_out, v);
+  }
+  if (a.image) {
+    load12(a.image, u);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[i] = norm_u8(u[i]);
+    if (a.image_out) store_rgb(a.image_out, v);
+    if (a.agnostic_out) {
+      const uint32_t pw = __ldg(reinterpret_cast<const uint32_t*>(a.parse + fo + p0));
+      float ph[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t lab = (pw >> (8 * i)) & 0xff;
+        ph[i] = (lab < 32 && ((kHeadMask >> lab) & 1u)) ? 1.f : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = __fsub_rn(__fmul_rn(v[3 * i + c], ph[i]), __fsub_rn(1.f, ph[i]));  // im*phead - (1-phead)
+        *reinterpret_cast<float4*>(a.agnostic_out + ((long)f * 4 + 1 + c) * a.HW + p0) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  if (a.cocopose_out) {
+    const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
+    for (int j = 0; j < a.J; ++j) *reinterpret_cast<float4*>(a.cocopose_out + ((long)f * a.J + j) * a.HW + p0) = m1;
+  }
+}
+
+// Pillow's 8-bit resampling pass: out = clip8(((1 << 21) + sum px * k) >> 22)
+__device__ __forceinline__ uint8_t pil_clip8(int ss) {
+  ss >>= 22;
+  return (uint8_t)(ss < 0 ? 0 : (ss > 255 ? 255 : ss));
+}
+
+struct ResizeTab {
+  const int* bounds;  // [out][2] = (first input index, tap count)
+  const int* kk;      // [out][ksize]
+  int ksize;
+};
+
+// One CTA per frame; the three intermediate images live in shared memory (H*w16 + h16*w16 + h16*W bytes).
+__global__ void __launch_bounds__(256)
+    body_silhouette_kernel(const uint8_t* __restrict__ parse, float* __restrict__ out, long out_frame_stride, int H, int W,
+                           ResizeTab dw, ResizeTab dh, ResizeTab uw, ResizeTab uh) {
+  extern __shared__ uint8_t sm[];
+  const int w16 = W / 16, h16 = H / 16;
+  uint8_t* tA = sm;                 // [H][w16]   after the horizontal down pass
+  uint8_t* tS = tA + H * w16;       // [h16][w16] after the vertical down pass
+  uint8_t* tB = tS + h16 * w16;     // [h16][W]   after the horizontal up pass
+  const uint8_t* src = parse + (long)blockIdx.x * H * W;
+  for (int e = threadIdx.x; e < H * w16; e += 256) {
+    const int y = e / w16, xx = e - y * w16;
+    const int x0 = dw.bounds[2 * xx], cnt = dw.bounds[2 * xx + 1];
+    int ss = 1 << 21;
+    for (int t = 0; t < cnt; ++t) ss += (src[y * W + x0 + t] > 0 ? 255 : 0) * dw.kk[xx * dw.ksize + t];
+    tA[e] = pil_clip8(ss);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < h16 * w16; e += 256) {
+    const int yy = e / w16, xx = e - yy * w16;
+    const int y0 = dh.bounds[2 * yy], cnt = dh.bounds[2 * yy + 1];
+    int ss = 1 << 21;
+    for (int t = 0; t < cnt; ++t) ss += tA[(y0 + t) * w16 + xx] * dh.kk[yy * dh.ksize + t];
+    tS[e] = pil_clip8(ss);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < h16 * W; e += 256) {
+    const int yy = e / W, x = e - yy * W;
+    const int x0 = uw.bounds[2 * x], cnt = uw.bounds[2 * x + 1];
+    int ss = 1 << 21;
+    for (int t = 0; t < cnt; ++t) ss += tS[yy * w16 + x0 + t] * uw.kk[x * uw.ksize + t];
+    tB[e] = pil_clip8(ss);
+  }
+  __syncthreads();
+  float* dst = out + (long)blockIdx.x * out_frame_stride;
+  for (int e = threadIdx.x; e < H * W; e += 256) {
+    const int y = e / W, x = e - y * W;
+    const int y0 = uh.bounds[2 * y], cnt = uh.bounds[2 * y + 1];
+    int ss = 1 << 21;
+    for (int t = 0; t < cnt; ++t) ss += tB[(y0 + t) * W + x] * uh.kk[y * uh.ksize + t];
+    dst[e] = norm_u8(pil_clip8(ss));
+  }
+}
+
+// im_cocopose: union of the filled squares ImageDraw.rectangle((x-r, y-r, x+r, y+r)) draws for joints with x > 1, y > 1
+__global__ void __launch_bounds__(256)
+    cocopose_vis_kernel(const double* __restrict__ pose, float* __restrict__ out, int H, int W, int J, int radius) {
+  __shared__ int box[64][4];
+  const int f = blockIdx.y;
+  for (int j = threadIdx.x; j < J; j += 256) {
+    const double x = pose[((long)f * J + j) * 3], y = pose[((long)f * J + j) * 3 + 1];
+    const bool on = x > 1.0 && y > 1.0;
+    box[j][0] = on ? (int)(x - radius) : 1;  // C truncation of the double, like the drawing code
+    box[j][1] = on ? (int)(y - radius) : 1;
+    box[j][2] = on ? (int)(x + radius) : 0;  // empty box when the joint is absent
+    box[j][3] = on ? (int)(y + radius) : 0;
+  }
+  __syncthreads();
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= H * W) return;
+  const int y = p / W, x = p - y * W;
+  bool hit = false;
+  for (int j = 0; j < J; ++j) hit |= (x >= box[j][0] && x <= box[j][2] && y >= box[j][1] && y <= box[j][3]);
+  out[(long)f * H * W + p] = hit ? 1.f : -1.f;  // norm_u8(255) = 1, norm_u8(0) = -1
+}
+
+__global__ void __launch_bounds__(256)
+    flo_decode_kernel(const float* __restrict__ uv, float* __restrict__ out, long hw) {
+  const long p = (long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= hw) return;
+  const float u = __ldg(uv + 2 * p), v = __ldg(uv + 2 * p + 1);  // the payload starts 12 bytes into the file: 4-byte aligned only
+  out[p] = __fdiv_rn(__fsub_rn(u, 0.5f), 0.5f);
+  out[hw + p] = __fdiv_rn(__fsub_rn(v, 0.5f), 0.5f);
+}
+
+}  // namespace shineon
+
+using namespace shineon;
+
+// Host-side: Pillow Resample.c precompute_coeffs + normalize_coeffs_8bpc for the BILINEAR filter (support 1.0).
+// bounds: 2*out_size ints; kk: out_size*ksize ints with ksize = the return value; pass kk = NULL to query ksize.
+extern "C" int shineon_pil_bilinear_coeffs(int in_size, int out_size, int* bounds, int* kk) {
+  if (in_size <= 0 || out_size <= 0) return fail(SHINEON_ERR_ARG, "pil_bilinear_coeffs: bad sizes %d -> %d", in_size, out_size);
+  double scale = (double)((float)in_size - 0.0f) / out_size;
+  double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 1.0 * filterscale;
+  const int ksize = (int)ceil(support) * 2 + 1;
+  if (!kk || !bounds) return ksize;
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = 0.0 + (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double w[1024];
+    if (xmax > 1024) return fail(SHINEON_ERR_UNSUPPORTED, "pil_bilinear_coeffs: filter too wide");
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      double t = (x + xmin - center + 0.5) * ss;
+      if (t < 0.0) t = -t;
+      w[x] = t < 1.0 ? 1.0 - t : 0.0;
+      ww += w[x];
+    }
+    for (int x = 0; x < ksize; ++x) {
+      int q = 0;
+      if (x < xmax) {
+        double v = w[x];
+        if (ww != 0.0) v /= ww;
+        q = v < 0 ? (int)(-0.5 + v * (1 << 22)) : (int)(0.5 + v * (1 << 22));
+      }
+      kk[xx * ksize + x] = q;
+    }
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+  return ksize;
+}
+
+extern "C" int shineon_frame_prep(const shineon_frame_prep_params* p, shineon_stream_t stream) {
+  SHINEON_REQUIRE(p != nullptr, "frame_prep: null params");
+  SHINEON_REQUIRE(p->F > 0 && p->F <= 65535 && p->H > 0 && p->W > 0, "frame_prep: bad shape");
+  SHINEON_REQUIRE((p->H * p->W) % 4 == 0, "frame_prep: H*W must be a multiple of 4");
+  SHINEON_REQUIRE(!p->cloth || p->cloth_out, "frame_prep: cloth given without cloth_out");
+  SHINEON_REQUIRE(!p->densepose || p->densepose_out, "frame_prep: densepose given without densepose_out");
+  SHINEON_REQUIRE(!p->agnostic_out || (p->image && p->parse), "frame_prep: agnostic needs image and parse");
+  SHINEON_REQUIRE(!p->cocopose_out || (p->n_joints > 0 && p->n_joints <= 64), "frame_prep: n_joints must be in 1..64");
+  SHINEON_REQUIRE(!p->im_cocopose_out || (p->pose && p->n_joints > 0 && p->n_joints <= 64), "frame_prep: im_cocopose needs pose");
+  SHINEON_REQUIRE(((reinterpret_cast<uintptr_t>(p->image) | reinterpret_cast<uintptr_t>(p->parse) | reinterpret_cast<uintptr_t>(p->cloth) |
+                    reinterpret_cast<uintptr_t>(p->densepose)) & 3) == 0, "frame_prep: uint8 inputs must be 4-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = p->H * p->W;
+  PrepArgs a;
+  a.image = p->image; a.parse = p->parse; a.cloth = p->cloth; a.densepose = p->densepose;
+  a.image_out = p->image_out; a.cloth_out = p->cloth_out; a.cloth_mask_out = p->cloth_mask_out;
+  a.densepose_out = p->densepose_out; a.agnostic_out = p->agnostic_out; a.cocopose_out = p->cocopose_out;
+  a.HW = HW; a.J = p->n_joints; a.cloth_thr = p->cloth_mask_threshold;
+  frame_prep_pointwise_kernel<<<dim3(cdiv(HW / 4, 256), p->F), 256, 0, st>>>(a);
+  int rc = after_launch("frame_prep_pointwise_kernel");
+  if (rc) return rc;
+  if (p->agnostic_out) {
+    SHINEON_REQUIRE(p->H % 16 == 0 && p->W % 16 == 0, "frame_prep: silhouette needs H, W multiples of 16");
+    SHINEON_REQUIRE(p->tab_bounds[0] && p->tab_kk[0] && p->tab_bounds[1] && p->tab_kk[1] && p->tab_bounds[2] && p->tab_kk[2] &&
+                        p->tab_bounds[3] && p->tab_kk[3], "frame_prep: resize tables missing (shineon_pil_bilinear_coeffs)");
+    ResizeTab t[4];
+    for (int i = 0; i < 4; ++i) t[i] = ResizeTab{p->tab_bounds[i], p->tab_kk[i], p->tab_ksize[i]};
+    const size_t smem = (size_t)p->H * (p->W / 16) + (size_t)(p->H / 16) * (p->W / 16) + (size_t)(p->H / 16) * p->W;
+    SHINEON_REQUIRE(smem <= 48 * 1024, "frame_prep: frame too large for the silhouette kernel");
+    body_silhouette_kernel<<<p->F, 256, smem, st>>>(p->parse, p->agnostic_out, (long)4 * HW, p->H, p->W, t[0], t[1], t[2], t[3]);
+    rc = after_launch("body_silhouette_kernel");
+    if (rc) return rc;
+  }
+  if (p->im_cocopose_out) {
+    cocopose_vis_kernel<<<dim3(cdiv(HW, 256), p->F), 256, 0, st>>>(p->pose, p->im_cocopose_out, p->H, p->W, p->n_joints, p->radius);
+    rc = after_launch("cocopose_vis_kernel");
+    if (rc) return rc;
+  }
+  return SHINEON_OK;
+}
+
+extern "C" int shineon_flo_decode(const void* flo_payload, float* out, int H, int W, shineon_stream_t stream) {
+  SHINEON_REQUIRE(flo_payload && out && H > 0 && W > 0, "flo_decode: bad arguments");
+  SHINEON_REQUIRE((reinterpret_cast<uintptr_t>(flo_payload) & 3) == 0, "flo_decode: payload must be 4-byte aligned");
+  const long hw = (long)H * W;
+  flo_decode_kernel<<<(unsigned)((hw + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)flo_payload, out, hw);
+  return after_launch("flo_decode_kernel");
+}

@@ -168,26 +168,34 @@ __global__ void __launch_bounds__(256)
   const int C = C0 + C1;
   const int HW = H * W;
   const int ixb = 2 * X0 - 1;  // input column of local column 0
-  // all of a thread's loads are issued before the first shared-memory store (up to 16 in flight per thread: with one
-  // 4-byte load at a time the first version of this kernel was latency-bound at 1.9 TB/s)
-  const int total = 2 * C * 2 * kS2dTX;  // <= 4096
+  // all of a thread's loads are issued before the first shared-memory store (up to 16 in flight per thread).  Thread t
+  // owns local column t % 64 of (row, channel) pairs t / 64, t / 64 + 4, ...: no per-element integer division (the
+  // first tiled version spent ~1500 instructions per thread on index arithmetic and was slower than the untiled one)
+  const int lc = threadIdx.x & (2 * kS2dTX - 1);
+  const int ix = ixb + lc;
+  const bool col_ok = ix >= 0 && ix < W;
+  const int rc0 = threadIdx.x >> 6;  // 0..3
   float v[16];
+  {
+    int r = rc0 / C, c = rc0 - r * C;
 #pragma unroll
-  for (int it = 0; it < 16; ++it) {
-    const int e = threadIdx.x + it * 256;
-    const int lc = e % (2 * kS2dTX);
-    const int rc = e / (2 * kS2dTX);
-    const int c = rc % C, r = rc / C;
-    const int iy = 2 * Y - 1 + r, ix = ixb + lc;
-    v[it] = 0.f;
-    if (e < total && iy >= 0 && iy < H && ix >= 0 && ix < W)
-      v[it] = c < C0 ? __ldg(x0 + ((long)n * C0 + c) * HW + iy * W + ix) : __ldg(x1 + ((long)n * C1 + (c - C0)) * HW + iy * W + ix);
+    for (int it = 0; it < 16; ++it) {
+      const int iy = 2 * Y - 1 + r;
+      v[it] = 0.f;
+      if (r < 2 && col_ok && iy >= 0 && iy < H)
+        v[it] = c < C0 ? __ldg(x0 + ((long)n * C0 + c) * HW + iy * W + ix) : __ldg(x1 + ((long)n * C1 + (c - C0)) * HW + iy * W + ix);
+      c += 4;
+      if (c >= C) { c -= C; ++r; }
+    }
   }
+  {
+    int r = rc0 / C, c = rc0 - r * C;
 #pragma unroll
-  for (int it = 0; it < 16; ++it) {
-    const int e = threadIdx.x + it * 256;
-    const int rc = e / (2 * kS2dTX);
-    if (e < total) s[rc / C][rc % C][e % (2 * kS2dTX)] = v[it];
+    for (int it = 0; it < 16; ++it) {
+      if (r < 2) s[r][c][lc] = v[it];
+      c += 4;
+      if (c >= C) { c -= C; ++r; }
+    }
   }
   __syncthreads();
   const int groups = cpad >> 3;

@@ -885,3 +885,74 @@ def nhwc_to_nchw_add(x, y, accumulate=True):
     check(_lib.load().shineon_nhwc_to_nchw_add(_p(x), x.shape[3], _p(y), N, H, W, Cc, int(bool(accumulate)), _stream()),
           "shineon_nhwc_to_nchw_add")
     return y
+
+
+# ----------------------------------------------------------------------------- dataset-side frame prep
+class FramePrep:
+    """TryonDataset.get_person_representation + get_cloth_representation (datasets/tryon_dataset.py:156-175,203-251,
+    323-447) on the device, from decoded 8-bit frames (channel-last uint8 CUDA tensors).  Bit-identical to the
+    reference's CPU tensors, including its two quirks: the cloth mask compares the normalised cloth with the 0-255
+    threshold, and the 18 cocopose channels are the constant -1 (the squares only reach `im_cocopose`)."""
+
+    def __init__(self, H=256, W=192, cloth_mask_threshold=240, radius=5, n_joints=18, device="cuda"):
+        self.H, self.W, self.thr, self.radius, self.J = H, W, float(cloth_mask_threshold), int(radius), int(n_joints)
+        lib = _lib.load()
+        self._tabs = []
+        for a, b in ((W, W // 16), (H, H // 16), (W // 16, W), (H // 16, H)):  # the two Image.resize calls, per axis
+            ks = lib.shineon_pil_bilinear_coeffs(a, b, None, None)
+            if ks <= 0:
+                check(ks, "shineon_pil_bilinear_coeffs")
+            bounds = torch.zeros(b, 2, dtype=torch.int32)
+            kk = torch.zeros(b, ks, dtype=torch.int32)
+            rc = lib.shineon_pil_bilinear_coeffs(a, b, C.c_void_p(bounds.data_ptr()), C.c_void_p(kk.data_ptr()))
+            if rc != ks:
+                check(rc if rc < 0 else -1, "shineon_pil_bilinear_coeffs")
+            self._tabs.append((bounds.to(device), kk.to(device), ks))
+
+    def __call__(self, parse, cloth, densepose, image, pose=None, want_image=False):
+        """parse [F,H,W], cloth / densepose / image [F,H,W,3] uint8 CUDA; pose [F,J,3] float64 CUDA or None.
+        Returns a dict with the batch keys the try-on stages read (f32 NCHW)."""
+        for name, t, nd in (("parse", parse, 3), ("cloth", cloth, 4), ("densepose", densepose, 4), ("image", image, 4)):
+            _req(t, torch.uint8, name)
+            assert t.dim() == nd and tuple(t.shape[1:3]) == (self.H, self.W), f"{name}: shape {tuple(t.shape)}"
+        F = parse.shape[0]
+        dev = parse.device
+        f32 = lambda c: torch.empty(F, c, self.H, self.W, dtype=torch.float32, device=dev)
+        out = {"cloth": f32(3), "cloth_mask": f32(1), "densepose": f32(3), "agnostic": f32(4), "cocopose": f32(self.J)}
+        if want_image:
+            out["image"] = f32(3)
+        p = _lib.FramePrepParams()
+        p.image, p.parse, p.cloth, p.densepose = _p(image), _p(parse), _p(cloth), _p(densepose)
+        p.pose = _p(None)
+        if pose is not None:
+            pose = _req(pose, torch.float64, "pose")
+            assert tuple(pose.shape) == (F, self.J, 3)
+            p.pose = _p(pose)
+            out["im_cocopose"] = f32(1)
+        p.image_out = _p(out.get("image"))
+        p.cloth_out, p.cloth_mask_out, p.densepose_out = _p(out["cloth"]), _p(out["cloth_mask"]), _p(out["densepose"])
+        p.agnostic_out, p.cocopose_out, p.im_cocopose_out = _p(out["agnostic"]), _p(out["cocopose"]), _p(out.get("im_cocopose"))
+        for i, (b, k, ks) in enumerate(self._tabs):
+            p.tab_bounds[i], p.tab_kk[i], p.tab_ksize[i] = b.data_ptr(), k.data_ptr(), ks
+        p.F, p.H, p.W, p.n_joints, p.radius, p.cloth_mask_threshold = F, self.H, self.W, self.J, self.radius, self.thr
+        check(_lib.load().shineon_frame_prep(C.byref(p), _stream()), "shineon_frame_prep")
+        return out
+
+
+def flo_decode(flo_bytes, device="cuda"):
+    """Middlebury .flo file content (bytes / uint8 tensor on the host) -> normalised flow f32 [2,H,W] on the device
+    (flow_utils.readFlow + flow_norm, datasets/tryon_dataset.py:121,288-289).  Header errors raise like the reference."""
+    import struct
+
+    buf = torch.frombuffer(bytearray(flo_bytes), dtype=torch.uint8) if not isinstance(flo_bytes, torch.Tensor) else flo_bytes
+    if buf.numel() < 12:
+        raise ValueError("Invalid .flo file: truncated header")
+    magic, w, h = struct.unpack("<fii", bytes(buf[:12].tolist()))
+    if magic != 202021.25:
+        raise ValueError("Magic number incorrect. Invalid .flo file")
+    if buf.numel() < 12 + 8 * w * h:
+        raise ValueError("Invalid .flo file: truncated payload")
+    d = buf.to(device)
+    out = torch.empty(2, h, w, dtype=torch.float32, device=device)
+    check(_lib.load().shineon_flo_decode(C.c_void_p(d.data_ptr() + 12), _p(out), h, w, _stream()), "shineon_flo_decode")
+    return out

@@ -52,16 +52,34 @@ class TryOnPipeline:
 
         return self._run_staged(tuple(batch_h[k] for k in self.BATCH_KEYS), stages)
 
+    RAW_KEYS = ("parse", "cloth", "densepose", "image")
+
+    @torch.no_grad()
+    def run_host_raw(self, raw_h, prep):
+        """Decoded 8-bit frames in (pinned uint8 host tensors, channel-last: `image`, `cloth`, `densepose` [F,H,W,3],
+        `parse` [F,H,W]), host p_tryon out.  The reference's Dataset.__getitem__ tensor prep (ops.FramePrep, bit-exact)
+        runs on the device, so a frame crosses PCIe as 10 bytes/pixel instead of 112."""
+        def stages(parse, cloth, densepose, image):
+            b = prep(parse, cloth, densepose, image)
+            return self(torch.cat([b["agnostic"], b["cocopose"]], 1), b["cloth"], torch.cat([b["agnostic"], b["densepose"]], 1))
+
+        self._out_hw = raw_h["parse"].shape[1:3]
+        try:
+            return self._run_staged(tuple(raw_h[k] for k in self.RAW_KEYS), stages)
+        finally:
+            self._out_hw = None
+
     def _run_staged(self, host_tensors, fn):
         dev = next(self.tom_model.parameters()).device
         cur = torch.cuda.current_stream(dev)
-        shapes = tuple(tuple(t.shape) for t in host_tensors)
+        shapes = tuple((tuple(t.shape), t.dtype) for t in host_tensors)
         st = self._host_state
         if st is None or st["shapes"] != shapes:
-            frames, hw = shapes[0][0], shapes[0][2:]
+            frames = host_tensors[0].shape[0]
+            hw = tuple(self._out_hw) if getattr(self, "_out_hw", None) else tuple(host_tensors[0].shape[2:])
             st = self._host_state = dict(
                 shapes=shapes, call=0, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev),
-                dev_in=[tuple(torch.empty(s, dtype=torch.float32, device=dev) for s in shapes) for _ in range(2)],
+                dev_in=[tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in host_tensors) for _ in range(2)],
                 in_free=[torch.cuda.Event() for _ in range(2)], in_ready=[torch.cuda.Event() for _ in range(2)],
                 out_done=[torch.cuda.Event() for _ in range(2)],
                 host_out=[torch.empty((frames, 3) + hw, dtype=torch.float32).pin_memory() for _ in range(2)])

@@ -65,3 +65,11 @@ for hw in ((16, 12), (8, 6), (4, 3)):
 c = torch.randn(N, 128, 96, 64, device="cuda", generator=g)
 timed("instnorm_act [N,128,96,64] -> planes", lambda: ops.instnorm_act(c, act="gelu", want_planes=True),
       nbytes=c.numel() * 12)
+# first-layer layout conversions (NCHW f32 -> space-to-depth planes): GMM person 22 ch, U-Net person+cloth 7+3 ch
+for c0, c1 in ((22, 0), (7, 3)):
+    x0 = torch.randn(N, c0, 256, 192, device="cuda", generator=g)
+    x1 = torch.randn(N, c1, 256, 192, device="cuda", generator=g) if c1 else None
+    wt = torch.randn(64, c0 + c1, 4, 4, device="cuda", generator=g) * 0.02
+    s2d = ops.S2dConv(wt, None)
+    nb = N * (c0 + c1) * 256 * 192 * 4 + N * 129 * 97 * ops.cpad64(4 * (c0 + c1)) * 4
+    timed(f"nchw_s2d_planes C={c0 + c1}", lambda: s2d.prepare(x0, x1), nbytes=nb)

@@ -69,3 +69,21 @@ def test_cocopose_squares_match_pil_draw():
             if x > 1 and y > 1:
                 d.rectangle((x - 5, y - 5, x + 5, y + 5), "white", "white")
         assert np.array_equal(fp.cocopose_vis_u8(pose, H, W, 5), np.array(im))
+
+
+def test_library_host_coefficients_match_oracle():
+    """shineon_pil_bilinear_coeffs is a pure host function of the C ABI (no GPU involved)."""
+    import ctypes as C
+
+    import torch
+
+    from shineon_virtual_tryon_b200 import _lib
+
+    lib = _lib.load()
+    for a, b in ((192, 12), (256, 16), (12, 192), (16, 256), (33, 64), (17, 5), (7, 7)):
+        ks = lib.shineon_pil_bilinear_coeffs(a, b, None, None)
+        bo, kk = torch.zeros(b, 2, dtype=torch.int32), torch.zeros(b, ks, dtype=torch.int32)
+        assert lib.shineon_pil_bilinear_coeffs(a, b, C.c_void_p(bo.data_ptr()), C.c_void_p(kk.data_ptr())) == ks
+        ob, ok = fp.pil_resize_coeffs(a, b)
+        assert np.array_equal(bo.numpy(), ob) and np.array_equal(kk.numpy(), ok)
+    assert lib.shineon_pil_bilinear_coeffs(0, 4, None, None) < 0
