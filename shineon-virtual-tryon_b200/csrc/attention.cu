@@ -3,7 +3,7 @@
 //   energy[i,j] = <q_i, k_j>;  A = softmax_j(energy);  o_i[c] = sum_j A[i,j] v_j[c];  y = act(gamma*o + x)
 // for one query pixel i per CTA.  N = H*W <= 192 on the ShineOn U-Net (bottom two levels), so the whole
 // key/value set of an image stays L1/L2 resident; fp32 throughout.
-#include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace shineon {
 
@@ -134,7 +134,7 @@ template <int QB>
 __global__ void __launch_bounds__(256)
     sagan_attention_tiled_kernel(const float* __restrict__ qkv, const float* __restrict__ x, const float* __restrict__ gamma,
                                  float* __restrict__ yf, plane_t* __restrict__ yh, plane_t* __restrict__ yl,
-                                 int HW, int C, int Cq, int cpad, int act, float act_param, int fmt) {
+                                 int HW, int C, int Cq, int cpad, int act, float act_param, int fmt, int kc) {
   constexpr int QG = QB / 8;       // 8-query groups
   constexpr int PARTS = 256 / QB;  // key partitions of the softmax phase
   extern __shared__ __align__(16) float sm[];
@@ -209,6 +209,98 @@ __global__ void __launch_bounds__(256)
   constexpr int CGP = 256 / QG;  // channel groups (of 8) per pass
   const int qg = tid / CGP;
   const int q_lo = qg * 8;
+  if (kc > 0) {
+    // ---- P.V with the value rows staged through shared memory: thread 0 streams chunks of kc keys (each row one
+    // cp.async.bulk of C floats, two chunks in flight) while all threads accumulate from the other buffer.  Reading V
+    // straight from global (the loop below) left only ~4 loads in flight per thread: latency-bound at 20 % of the FMA rate.
+    float* sv = sinv + QB;  // [2][kc][C]; 16-byte aligned (every section above is a multiple of 4 floats)
+    __shared__ __align__(8) uint64_t vbar[2];
+    const uint32_t bar0 = smem_u32(&vbar[0]);
+    if (tid == 0) {
+      mbar_init(bar0, 1);
+      mbar_init(bar0 + 8, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nchunks = (HW + kc - 1) / kc;
+    auto issue = [&](int ch) {
+      const int buf = ch & 1, j0 = ch * kc;
+      const int nk = min(kc, HW - j0);
+      const uint32_t bar = bar0 + 8 * buf;
+      mbar_expect_tx(bar, (uint32_t)nk * C * 4);
+      for (int t = 0; t < nk; ++t)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sv + ((size_t)buf * kc + t) * C)), "l"(vbase + (long)(j0 + t) * ld), "r"(C * 4), "r"(bar)
+                     : "memory");
+    };
+    if (tid == 0) {
+      issue(0);
+      if (nchunks > 1) issue(1);
+    }
+    const int c0 = (tid % CGP) * 8;
+    const bool active = c0 < C;
+    float acc[8][8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[q][k] = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int buf = ch & 1, j0 = ch * kc;
+      const int nk = min(kc, HW - j0);
+      mbar_wait(bar0 + 8 * buf, (ch >> 1) & 1);
+      if (active) {
+        const float* vp = sv + (size_t)buf * kc * C + c0;
+        const float* pp = sp + (size_t)j0 * QB + q_lo;
+#pragma unroll 4
+        for (int t = 0; t < nk; ++t) {
+          const float4 va = *reinterpret_cast<const float4*>(vp + (size_t)t * C);
+          const float4 vb = *reinterpret_cast<const float4*>(vp + (size_t)t * C + 4);
+          const float4 pa = *reinterpret_cast<const float4*>(pp + (size_t)t * QB);
+          const float4 pb = *reinterpret_cast<const float4*>(pp + (size_t)t * QB + 4);
+          const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+          const float pq[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[q][k] = fmaf(pq[q], v[k], acc[q][k]);
+        }
+      }
+      __syncthreads();  // everyone is done with this buffer
+      if (tid == 0 && ch + 2 < nchunks) issue(ch + 2);
+    }
+    if (active) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q_lo + q >= nq) break;
+        const long pix = (long)n * HW + i0 + q_lo + q;
+        const float inv = sinv[q_lo + q];
+        const float4 xa = __ldg(reinterpret_cast<const float4*>(x + pix * C + c0));
+        const float4 xb = __ldg(reinterpret_cast<const float4*>(x + pix * C + c0 + 4));
+        const float xr[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = apply_act(g * (acc[q][k] * inv) + xr[k], act, act_param);  // sagan.py:53
+        if (yf) {
+          float4* d = reinterpret_cast<float4*>(yf + pix * C + c0);
+          d[0] = make_float4(v[0], v[1], v[2], v[3]);
+          d[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (yh) {
+          plane_t h[8], l[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) split16(v[k], fmt, h[k], l[k]);
+          *reinterpret_cast<uint4*>(yh + pix * cpad + c0) =
+              make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                         (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
+          if (yl)
+            *reinterpret_cast<uint4*>(yl + pix * cpad + c0) =
+                make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
+                           (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
+        }
+      }
+    }
+    return;
+  }
   for (int c0 = (tid % CGP) * 8; c0 < C; c0 += CGP * 8) {
     float acc[8][8];
 #pragma unroll
@@ -266,6 +358,8 @@ __global__ void __launch_bounds__(256)
 
 using namespace shineon;
 
+static inline int ld_floats(int C, int Cq) { return 2 * Cq + C; }
+
 extern "C" int shineon_sagan_attention(const float* qkv, const float* x, const float* gamma, float* y_f32, void* y_hi,
                                        void* y_lo, int N, int HW, int C, int Cq, int cpad, int act, float act_param,
                                        int plane_fmt, shineon_stream_t stream) {
@@ -282,7 +376,16 @@ extern "C" int shineon_sagan_attention(const float* qkv, const float* x, const f
                          reinterpret_cast<uintptr_t>(y_hi) | reinterpret_cast<uintptr_t>(y_lo)) % 16 == 0);
   if (aligned) {
     constexpr int QB = 32;
-    const size_t smem = sizeof(float) * ((size_t)QB * Cq + (size_t)HW * QB + (256 / QB) * QB + QB);
+    size_t smem = sizeof(float) * ((size_t)QB * Cq + (size_t)HW * QB + (256 / QB) * QB + QB);
+    // value rows staged through shared memory (two buffers of kc keys) when one channel pass covers C and it fits
+    int kc = 0;
+    if (C <= (256 / (QB / 8)) * 8 && (ld_floats(C, Cq) % 4) == 0) {
+      kc = 16;
+      while (kc > 2 && smem + 2 * (size_t)kc * C * sizeof(float) > 100 * 1024) kc /= 2;
+      if (smem + 2 * (size_t)kc * C * sizeof(float) > 100 * 1024) kc = 0;
+      if (kc > HW) kc = HW;
+    }
+    smem += 2 * (size_t)kc * C * sizeof(float);
     static size_t opted = 48 * 1024;  // dynamic shared memory this kernel has been opted into
     if (smem <= 200 * 1024) {
       if (smem > opted) {
@@ -291,7 +394,7 @@ extern "C" int shineon_sagan_attention(const float* qkv, const float* x, const f
         opted = smem;
       }
       sagan_attention_tiled_kernel<QB><<<dim3(cdiv(HW, QB), N), 256, smem, st>>>(
-          qkv, x, gamma, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, Cq, cpad, act, act_param, plane_fmt);
+          qkv, x, gamma, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, Cq, cpad, act, act_param, plane_fmt, kc);
       return after_launch("sagan_attention_tiled_kernel");
     }
   }

@@ -152,72 +152,9 @@ __global__ void __launch_bounds__(256)
   if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
-// Tiled form (C0 + C1 <= 32): the kernel above reads NCHW rows with neighbouring threads two columns apart and writes
-// one 16-byte fragment per 2*cpad-byte pixel row (uncoalesced both ways: 2.6 TB/s, profiles/r01_launches_summary.md).
-// Here a CTA stages the two input rows of one output row Y for 32 output columns (64 input columns x C channels,
-// 256-byte coalesced reads per channel row) in shared memory and then writes whole pixels: consecutive threads own
-// consecutive 8-channel groups, i.e. 2*cpad contiguous bytes per pixel and plane.
-constexpr int kS2dTX = 32;
-template <int FMT>
-__global__ void __launch_bounds__(256)
-    nchw_s2d_planes_tiled_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
-                                 plane_t* __restrict__ yh, plane_t* __restrict__ yl, int H, int W, int cpad) {
-  __shared__ float s[2][32][2 * kS2dTX + 1];
-  const int n = blockIdx.z, Y = blockIdx.y, X0 = blockIdx.x * kS2dTX;
-  const int Wz = W / 2 + 1;
-  const int C = C0 + C1;
-  const int HW = H * W;
-  const int ixb = 2 * X0 - 1;  // input column of local column 0
-  // all of a thread's loads are issued before the first shared-memory store (up to 16 in flight per thread).  Thread t
-  // owns local column t % 64 of (row, channel) pairs t / 64, t / 64 + 4, ...: no per-element integer division (the
-  // first tiled version spent ~1500 instructions per thread on index arithmetic and was slower than the untiled one)
-  const int lc = threadIdx.x & (2 * kS2dTX - 1);
-  const int ix = ixb + lc;
-  const bool col_ok = ix >= 0 && ix < W;
-  const int rc0 = threadIdx.x >> 6;  // 0..3
-  float v[16];
-  {
-    int r = rc0 / C, c = rc0 - r * C;
-#pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const int iy = 2 * Y - 1 + r;
-      v[it] = 0.f;
-      if (r < 2 && col_ok && iy >= 0 && iy < H)
-        v[it] = c < C0 ? __ldg(x0 + ((long)n * C0 + c) * HW + iy * W + ix) : __ldg(x1 + ((long)n * C1 + (c - C0)) * HW + iy * W + ix);
-      c += 4;
-      if (c >= C) { c -= C; ++r; }
-    }
-  }
-  {
-    int r = rc0 / C, c = rc0 - r * C;
-#pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      if (r < 2) s[r][c][lc] = v[it];
-      c += 4;
-      if (c >= C) { c -= C; ++r; }
-    }
-  }
-  __syncthreads();
-  const int groups = cpad >> 3;
-  for (int item = threadIdx.x; item < kS2dTX * groups; item += 256) {
-    const int g = item % groups, xl = item / groups;
-    const int X = X0 + xl;
-    if (X >= Wz) break;
-    __align__(16) plane_t hi[8];
-    __align__(16) plane_t lo[8];
-    int k = g * 8;
-    int q = k / C, c = k - q * C;  // q = py*2+px
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float v = q < 4 ? s[q >> 1][c][2 * xl + (q & 1)] : 0.f;
-      split16(v, FMT, hi[j], lo[j]);
-      if (++c == C) { c = 0; ++q; }
-    }
-    const long o = (((long)n * (H / 2 + 1) + Y) * Wz + X) * cpad + g * 8;
-    *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
-    if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
-  }
-}
+// (A shared-memory tiled variant -- coalesced 256-byte channel-row reads, whole-pixel writes -- was measured SLOWER than
+// this direct form on B200: 0.41 vs 0.35 ms for 22 channels, 0.28 vs 0.16 ms for 10 at 80 frames; the direct form's
+// strided accesses are absorbed by L1/L2 and it has no barrier.  profiles/r01_memory_ops.md.)
 
 // ------------------------------------------------------------------------------ tap-stacked 3x3 conv: col2im
 // For a 3x3 conv with very few output channels (the U-Net's final 128 -> 4 layer) the implicit GEMM is run
@@ -650,14 +587,6 @@ extern "C" int shineon_nchw_s2d_planes(const float* x0, int C0, const float* x1,
   SHINEON_REQUIRE(x0 && y_hi && C0 > 0 && (x1 == nullptr) == (C1 == 0), "nchw_s2d_planes: bad input tensors");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && H / 2 + 1 <= 65535, "nchw_s2d_planes: bad shape (H, W must be even)");
   SHINEON_REQUIRE(cpad % 8 == 0 && cpad >= 4 * (C0 + C1), "nchw_s2d_planes: cpad %d too small / not a multiple of 8", cpad);
-  if (C0 + C1 <= 32) {
-    dim3 tgrid(cdiv(W / 2 + 1, kS2dTX), H / 2 + 1, N);
-    if (plane_fmt == SHINEON_FMT_FP16)
-      nchw_s2d_planes_tiled_kernel<SHINEON_FMT_FP16><<<tgrid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad);
-    else
-      nchw_s2d_planes_tiled_kernel<SHINEON_FMT_BF16><<<tgrid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad);
-    return after_launch("nchw_s2d_planes_tiled_kernel");
-  }
   dim3 grid(cdiv((W / 2 + 1) * (cpad / 8), 256), H / 2 + 1, N);
   if (plane_fmt == SHINEON_FMT_FP16)
     nchw_s2d_planes_kernel<SHINEON_FMT_FP16><<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad);

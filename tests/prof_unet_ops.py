@@ -73,3 +73,7 @@ for c0, c1 in ((22, 0), (7, 3)):
     s2d = ops.S2dConv(wt, None)
     nb = N * (c0 + c1) * 256 * 192 * 4 + N * 129 * 97 * ops.cpad64(4 * (c0 + c1)) * 4
     timed(f"nchw_s2d_planes C={c0 + c1}", lambda: s2d.prepare(x0, x1), nbytes=nb)
+# GMM correlation
+fa = torch.randn(N, 16, 12, 512, device="cuda", generator=g)
+fb = torch.randn(N, 16, 12, 512, device="cuda", generator=g)
+timed("l2norm_correlation 16x12x512", lambda: ops.l2norm_correlation(fa, fb, want_f32=False, want_planes=True))
