@@ -10,22 +10,56 @@ import torch
 
 
 class TryOnPipeline:
-    def __init__(self, warp_model, tom_model):
+    def __init__(self, warp_model, tom_model, cuda_graph=False):
+        """cuda_graph=True: the ~180 launches of a step are captured once per distinct set of input buffers and
+        replayed (the small launches at the bottom of the U-Net are otherwise issued slower than the GPU runs them).
+        Replayed calls return the graph's static output tensors: they are overwritten by the next call with the same
+        input buffers."""
         self.warp_model = warp_model
         self.tom_model = tom_model
         self._host_state = None
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
+        self.replayed_launches = 0  # kernel launches executed through graph replays (not seen by shineon_launch_count)
 
     def set_precision(self, precision):
         self.warp_model.set_precision(precision)
         self.tom_model.set_precision(precision)
+        self._graphs.clear()  # captured graphs hold the previous mode's kernels
+
+    def _stages(self, person_gmm, cloth, person_tom):
+        warped_cloth, _, _, _ = self.warp_model.warp(person_gmm, cloth, cloth)
+        _, tryon_masks, p_tryons, _ = self.tom_model(person_tom, warped_cloth)
+        return p_tryons, tryon_masks, warped_cloth
+
+    def _graph_call(self, tag, fn, args):
+        """fn(*args) through a CUDA graph keyed by (tag, argument buffers).  Eager while ops.PROFILE is collecting."""
+        from . import _lib, ops
+
+        if not self.cuda_graph or ops.PROFILE is not None:
+            return fn(*args)
+        key = (tag,) + tuple((a.data_ptr(), tuple(a.shape), a.dtype) for a in args)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            for _ in range(2):  # weight packing, allocator warm-up: nothing of that may happen inside the capture
+                fn(*args)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                out = fn(*args)
+            ent = self._graphs[key] = (graph, out, _lib.launch_count() - n0)
+        ent[0].replay()
+        self.replayed_launches += ent[2]
+        return ent[1]
 
     @torch.no_grad()
     def __call__(self, person_gmm, cloth, person_tom):
         """person_gmm [F,22,H,W] (agnostic+cocopose), cloth [F,3,H,W], person_tom [F,7,H,W] (agnostic+densepose);
         all f32 CUDA.  Returns (p_tryon [F,3,H,W], tryon_mask [F,1,H,W], warped_cloth [F,3,H,W])."""
-        warped_cloth, _, _, _ = self.warp_model.warp(person_gmm, cloth, cloth)
-        _, tryon_masks, p_tryons, _ = self.tom_model(person_tom, warped_cloth)
-        return p_tryons, tryon_masks, warped_cloth
+        return self._graph_call("call", self._stages, (person_gmm, cloth, person_tom))
 
     @torch.no_grad()
     def run_host(self, person_gmm_h, cloth_h, person_tom_h):
@@ -35,7 +69,7 @@ class TryOnPipeline:
         call's kernels.  Returns (out_host, done_event); `out_host` is valid once `done_event` has completed (or after
         a device synchronize) and is reused by the call after next.
         """
-        return self._run_staged((person_gmm_h, cloth_h, person_tom_h), lambda a, c, p: self(a, c, p))
+        return self._run_staged("host", (person_gmm_h, cloth_h, person_tom_h), self._stages)
 
     # keys of the reference's dataset batch the two stages read (datasets/tryon_dataset.py:47-61; WarpModel person
     # inputs agnostic+cocopose, UnetMaskModel person inputs agnostic+densepose, cloth for both)
@@ -47,10 +81,10 @@ class TryOnPipeline:
         `cocopose` [F,18,H,W], `densepose` [F,3,H,W], `cloth` [F,3,H,W], pinned f32).  Every key crosses PCIe once
         (agnostic feeds both stages: 28 channels per frame instead of 22 + 3 + 7); the per-stage channel concatenation
         is done on the device like base_model.get_and_cat_inputs (util/__init__.py:64-66)."""
-        def stages(agnostic, cocopose, densepose, cloth):
-            return self(torch.cat([agnostic, cocopose], 1), cloth, torch.cat([agnostic, densepose], 1))
+        return self._run_staged("batch", tuple(batch_h[k] for k in self.BATCH_KEYS), self._stages_batch)
 
-        return self._run_staged(tuple(batch_h[k] for k in self.BATCH_KEYS), stages)
+    def _stages_batch(self, agnostic, cocopose, densepose, cloth):
+        return self._stages(torch.cat([agnostic, cocopose], 1), cloth, torch.cat([agnostic, densepose], 1))
 
     RAW_KEYS = ("parse", "cloth", "densepose", "image")
 
@@ -59,17 +93,22 @@ class TryOnPipeline:
         """Decoded 8-bit frames in (pinned uint8 host tensors, channel-last: `image`, `cloth`, `densepose` [F,H,W,3],
         `parse` [F,H,W]), host p_tryon out.  The reference's Dataset.__getitem__ tensor prep (ops.FramePrep, bit-exact)
         runs on the device, so a frame crosses PCIe as 10 bytes/pixel instead of 112."""
-        def stages(parse, cloth, densepose, image):
-            b = prep(parse, cloth, densepose, image)
-            return self(torch.cat([b["agnostic"], b["cocopose"]], 1), b["cloth"], torch.cat([b["agnostic"], b["densepose"]], 1))
+        if getattr(self, "_raw_prep", None) is not prep:
+            self._raw_prep = prep
 
+            def stages(parse, cloth, densepose, image):
+                b = prep(parse, cloth, densepose, image)
+                return self._stages(torch.cat([b["agnostic"], b["cocopose"]], 1), b["cloth"],
+                                    torch.cat([b["agnostic"], b["densepose"]], 1))
+
+            self._raw_stages = stages
         self._out_hw = raw_h["parse"].shape[1:3]
         try:
-            return self._run_staged(tuple(raw_h[k] for k in self.RAW_KEYS), stages)
+            return self._run_staged("raw", tuple(raw_h[k] for k in self.RAW_KEYS), self._raw_stages)
         finally:
             self._out_hw = None
 
-    def _run_staged(self, host_tensors, fn):
+    def _run_staged(self, tag, host_tensors, fn):
         dev = next(self.tom_model.parameters()).device
         cur = torch.cuda.current_stream(dev)
         shapes = tuple((tuple(t.shape), t.dtype) for t in host_tensors)
@@ -94,12 +133,15 @@ class TryOnPipeline:
                 d.copy_(h, non_blocking=True)
             st["in_ready"][slot].record(st["s_in"])
         cur.wait_event(st["in_ready"][slot])
-        p_tryons, _, _ = fn(*dev_in)
+        if self.cuda_graph:
+            cur.wait_event(st["out_done"][slot])  # this slot's graph owns its output buffer: the last D2H of it must be done
+        p_tryons, _, _ = self._graph_call(tag, fn, dev_in)
         st["in_free"][slot].record(cur)
         computed = torch.cuda.Event()
         computed.record(cur)
         out_h = st["host_out"][slot]
-        p_tryons.record_stream(st["s_out"])
+        if not self.cuda_graph:
+            p_tryons.record_stream(st["s_out"])
         with torch.cuda.stream(st["s_out"]):
             st["s_out"].wait_event(computed)
             out_h.copy_(p_tryons, non_blocking=True)

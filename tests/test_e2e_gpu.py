@@ -154,6 +154,39 @@ def test_host_buffer_entry_points_match_device_call(cuda):
     pipe.host_sync()
 
 
+def test_cuda_graph_replay_matches_eager(cuda):
+    """TryOnPipeline(cuda_graph=True): captured once per set of input buffers; replays (device call and both host-buffer
+    entry points, both slots) must reproduce the eager results bit for bit, also after the inputs' CONTENT changes."""
+    from shineon_virtual_tryon_b200.pipeline import TryOnPipeline
+
+    warp, _ = build_model("warp")
+    tom, _ = build_model("unet_mask")
+    eager, graphed = TryOnPipeline(warp, tom), TryOnPipeline(warp, tom, cuda_graph=True)
+    g = torch.Generator().manual_seed(8)
+    a, c, p = torch.empty(2, 22, 256, 192).cuda(), torch.empty(2, 3, 256, 192).cuda(), torch.empty(2, 7, 256, 192).cuda()
+    for rep in range(3):
+        a.copy_(torch.randn(2, 22, 256, 192, generator=g))
+        c.copy_(torch.rand(2, 3, 256, 192, generator=g) * 2 - 1)
+        p.copy_(torch.randn(2, 7, 256, 192, generator=g))
+        want = [t.clone() for t in eager(a, c, p)]
+        got = graphed(a, c, p)
+        for w, gt in zip(want, got):
+            assert torch.equal(w, gt)
+    assert graphed.replayed_launches > 0
+    for rep in range(4):
+        batch = {"agnostic": torch.randn(2, 4, 256, 192, generator=g), "cocopose": torch.randn(2, 18, 256, 192, generator=g),
+                 "densepose": torch.randn(2, 3, 256, 192, generator=g), "cloth": torch.rand(2, 3, 256, 192, generator=g) * 2 - 1}
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+        w, d1 = eager.run_host_batch(batch)
+        d1.synchronize()
+        w = w.clone()
+        o, d2 = graphed.run_host_batch(batch)
+        d2.synchronize()
+        assert torch.equal(o, w)
+    eager.host_sync()
+    graphed.host_sync()
+
+
 @pytest.mark.parametrize("prec,max_tol,mean_tol", [("bf16x3", 2e-2, 1e-3), ("fp16", 0.3, 1e-2), ("bf16", 1.0, 5e-2)])
 def test_other_precision_modes(cuda, prec, max_tol, mean_tol):
     """Non-default numeric modes: measured error against the fp32 oracle, loose documented bounds."""
