@@ -122,6 +122,52 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// One query row x 8 channels of the epilogue: y = act(gamma * o / sum + x) -> f32 and / or 16-bit planes.  Deliberately
+// NOT inlined: with the runtime activation switch inlined for all 64 accumulators the tiled kernel was 32k SASS
+// instructions, most of them executed once, and a fifth of its stall samples were instruction-cache misses
+// (stall_no_inst, profiles/r01_attention.md).
+__device__ __noinline__ void attn_store_row8(float4 a0, float4 a1, float inv, float g, const float* __restrict__ xrow,
+                                             float* yf_row, plane_t* yh_row, plane_t* yl_row, int act, float act_param, int fmt) {
+  const float4 xa = __ldg(reinterpret_cast<const float4*>(xrow));
+  const float4 xb = __ldg(reinterpret_cast<const float4*>(xrow + 4));
+  const float o[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const float xr[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = g * (o[k] * inv) + xr[k];  // sagan.py:53
+  switch (act) {  // uniform
+    case SHINEON_ACT_NONE: break;
+    case SHINEON_ACT_GELU:
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = apply_act(v[k], SHINEON_ACT_GELU, act_param);
+      break;
+    case SHINEON_ACT_RELU:
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = apply_act(v[k], SHINEON_ACT_RELU, act_param);
+      break;
+    default:
+#pragma unroll 1
+      for (int k = 0; k < 8; ++k) v[k] = apply_act(v[k], act, act_param);
+      break;
+  }
+  if (yf_row) {
+    reinterpret_cast<float4*>(yf_row)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(yf_row)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (yh_row) {
+    plane_t h[8], l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) split16(v[k], fmt, h[k], l[k]);
+    *reinterpret_cast<uint4*>(yh_row) =
+        make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                   (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
+    if (yl_row)
+      *reinterpret_cast<uint4*>(yl_row) =
+          make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
+                     (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
+  }
+}
+
 // Register-tiled version (the default when the row strides keep 16-byte alignment): 256 threads, QB queries per CTA.
 //   energies  : one (key j, 8-query group) item per thread, q rows broadcast from shared memory;
 //   softmax   : thread = (query, 1/8 of the keys), partial max / sum combined through shared memory; probabilities are
@@ -251,7 +297,7 @@ __global__ void __launch_bounds__(256)
       if (active) {
         const float* vp = sv + (size_t)buf * kc * C + c0;
         const float* pp = sp + (size_t)j0 * QB + q_lo;
-#pragma unroll 4
+#pragma unroll 2
         for (int t = 0; t < nk; ++t) {
           const float4 va = *reinterpret_cast<const float4*>(vp + (size_t)t * C);
           const float4 vb = *reinterpret_cast<const float4*>(vp + (size_t)t * C + 4);
@@ -273,30 +319,9 @@ __global__ void __launch_bounds__(256)
       for (int q = 0; q < 8; ++q) {
         if (q_lo + q >= nq) break;
         const long pix = (long)n * HW + i0 + q_lo + q;
-        const float inv = sinv[q_lo + q];
-        const float4 xa = __ldg(reinterpret_cast<const float4*>(x + pix * C + c0));
-        const float4 xb = __ldg(reinterpret_cast<const float4*>(x + pix * C + c0 + 4));
-        const float xr[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = apply_act(g * (acc[q][k] * inv) + xr[k], act, act_param);  // sagan.py:53
-        if (yf) {
-          float4* d = reinterpret_cast<float4*>(yf + pix * C + c0);
-          d[0] = make_float4(v[0], v[1], v[2], v[3]);
-          d[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        if (yh) {
-          plane_t h[8], l[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) split16(v[k], fmt, h[k], l[k]);
-          *reinterpret_cast<uint4*>(yh + pix * cpad + c0) =
-              make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
-                         (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
-          if (yl)
-            *reinterpret_cast<uint4*>(yl + pix * cpad + c0) =
-                make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
-                           (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
-        }
+        attn_store_row8(make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]), make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]),
+                        sinv[q_lo + q], g, x + pix * C + c0, yf ? yf + pix * C + c0 : nullptr, yh ? yh + pix * cpad + c0 : nullptr,
+                        yl ? yl + pix * cpad + c0 : nullptr, act, act_param, fmt);
       }
     }
     return;
@@ -326,30 +351,9 @@ __global__ void __launch_bounds__(256)
     for (int q = 0; q < 8; ++q) {
       if (q_lo + q >= nq) break;
       const long pix = (long)n * HW + i0 + q_lo + q;
-      const float inv = sinv[q_lo + q];
-      const float4 xa = __ldg(reinterpret_cast<const float4*>(x + pix * C + c0));
-      const float4 xb = __ldg(reinterpret_cast<const float4*>(x + pix * C + c0 + 4));
-      const float xr[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = apply_act(g * (acc[q][k] * inv) + xr[k], act, act_param);  // sagan.py:53
-      if (yf) {
-        float4* d = reinterpret_cast<float4*>(yf + pix * C + c0);
-        d[0] = make_float4(v[0], v[1], v[2], v[3]);
-        d[1] = make_float4(v[4], v[5], v[6], v[7]);
-      }
-      if (yh) {
-        plane_t h[8], l[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) split16(v[k], fmt, h[k], l[k]);
-        *reinterpret_cast<uint4*>(yh + pix * cpad + c0) =
-            make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
-                       (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
-        if (yl)
-          *reinterpret_cast<uint4*>(yl + pix * cpad + c0) =
-              make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
-                         (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
-      }
+      attn_store_row8(make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]), make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]),
+                      sinv[q_lo + q], g, x + pix * C + c0, yf ? yf + pix * C + c0 : nullptr, yh ? yh + pix * cpad + c0 : nullptr,
+                      yl ? yl + pix * cpad + c0 : nullptr, act, act_param, fmt);
     }
   }
 }
