@@ -77,7 +77,7 @@ __device__ __forceinline__ float conv_epilogue_value(float acc, int c, const Con
 
 // Vector form for the tcgen05 epilogue: the activation kind is warp-uniform, so dispatch ONCE per 32-column chunk
 // to a loop specialised on it.  (A per-element `switch` unrolled 32x made the kernel 16k SASS instructions and
-// instruction-fetch bound: stall_no_inst dominated the first ncu capture, profiles/r01_conv_epilogue_icache.md.)
+// instruction-fetch bound: stall_no_inst dominated the first ncu capture, profiles/r01_conv_igemm.md capture A.)
 template <int ACT>
 __device__ __forceinline__ void act_chunk(float (&v)[32], float param) {
 #pragma unroll
