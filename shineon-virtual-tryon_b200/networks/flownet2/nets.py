@@ -106,8 +106,30 @@ class _Net(nn.Module):
                                           prec=prec, chan_map=cmap)
         return pk[name]
 
+    def _tap(self, prec, name, segs=None):
+        """3x3 / stride 1 / pad 1 layers with <= 16 output channels (every predict_flow, FlowNetFusion's inter convs) as a
+        tap-stacked 1x1 GEMM + col2im: the activation is read once instead of once per tap from L2, and the K loop of
+        the small-resolution predict_flow layers (2 CTAs, 144 sequential K-blocks: latency-bound) is 9x shorter."""
+        m = getattr(self, name)
+        m = m[0] if isinstance(m, nn.Sequential) else m
+        if not (isinstance(m, nn.Conv2d) and m.kernel_size == (3, 3) and m.stride == (1, 1) and m.padding == (1, 1)
+                and m.out_channels <= 16):
+            return None
+        pk = self._packs(prec)
+        key = name + "/tap"
+        if key not in pk:
+            cmap = _Concat.chan_map(segs) if segs is not None else None
+            pk[key] = ops.TapStackedConv3x3(m.weight, m.bias, prec=prec, cin_pad=len(cmap) if cmap is not None else None,
+                                            chan_map=cmap)
+        return pk[key]
+
     # conv + LeakyReLU(0.1) -> planes (optionally into a concat window)
     def _c(self, prec, name, x, out=None, segs=None, act=True):
+        tap = self._tap(prec, name, segs)
+        if tap is not None:
+            _, y = ops.instnorm_act(tap(x), do_norm=False, act="leaky" if act else None, act_param=LEAK, want_f32=False,
+                                    want_planes=True, prec=prec, out_planes=out)
+            return y
         pc = self._pc(prec, name, segs)
         _, y = ops.conv2d(x, pc, post_act="leaky" if act else None, act_param=LEAK, want_planes=out is None,
                           out_planes=out)
@@ -120,6 +142,11 @@ class _Net(nn.Module):
 
     def _flow(self, prec, name, x, segs=None, want_f32=False, want_planes=True):
         """predict_flow: 3x3 conv -> 2 channels, no activation; returns (f32 NHWC [B,h,w,2] | None, planes | None)."""
+        tap = self._tap(prec, name, segs)
+        if tap is not None:
+            f32 = tap(x)
+            pl = ops.instnorm_act(f32, do_norm=False, want_f32=False, want_planes=True, prec=prec)[1] if want_planes else None
+            return (f32 if want_f32 else None), pl
         pc = self._pc(prec, name, segs)
         f32 = ops.conv2d(x, pc, want_f32=True)[0] if want_f32 else None
         pl = ops.conv2d(x, pc, want_planes=True)[1] if want_planes else None
