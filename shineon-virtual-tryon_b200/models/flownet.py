@@ -50,7 +50,7 @@ class FlowNet(nn.Module):
                 self._compute_flow_and_conf(im1, im2)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):  # other threads (NCCL watchdog) may poll events
                 out = self._compute_flow_and_conf(im1, im2)
             ent = self._graphs[key] = (graph, out)
         ent[0].replay()

@@ -48,7 +48,7 @@ class TryOnPipeline:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):  # other threads (NCCL watchdog) may poll events
                 out = fn(*args)
             ent = self._graphs[key] = (graph, out, _lib.launch_count() - n0)
         ent[0].replay()
