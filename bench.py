@@ -116,6 +116,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _quiet_nccl():
+    """stdout must carry exactly one JSON line: NCCL prints its version banner there at NCCL_DEBUG >= VERSION/WARN."""
+    if "SHINEON_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["SHINEON_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
+
+
 def build_models():
     """WarpModel + UnetMaskModel mirrors on the CPU with the reference's own initialisation under the reference's
     seed (train.py:29), then non-trivial attention gammas / BatchNorm statistics so no layer is a numerical no-op."""
@@ -279,7 +287,7 @@ def run_train(args, rank, world):
     from shineon_virtual_tryon_b200 import _lib, distributed, ops
     from shineon_virtual_tryon_b200.training import Trainer
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("SHINEON_NCCL_DEBUG", "WARN")
+    _quiet_nccl()
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -411,7 +419,7 @@ def run_b200(args, rank, world):
     from shineon_virtual_tryon_b200 import _lib, distributed, ops
     from shineon_virtual_tryon_b200.pipeline import TryOnPipeline
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("SHINEON_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    _quiet_nccl()
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
