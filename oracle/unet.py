@@ -118,3 +118,46 @@ def tom_forward(sd, person, cloths, n_frames=1, flow_warp=False, flows=None, res
             rend = pr[f]
         frames.append((1 - tm[f]) * rend + tm[f] * cl[f])
     return p_rendereds, tryon_masks, torch.cat(frames, dim=1), flow_masks
+
+
+# ----------------------------------------------------------------------------- low-resolution form of upsample -> conv3x3
+def _up3_coeffs(i, n):
+    """The four coefficient triples over low-res neighbours (i-1, i, i+1) that give upsampled rows 2i-1, 2i, 2i+1, 2i+2
+    (PyTorch bilinear x2, align_corners=False: clamped source index) with the conv's zero padding folded in."""
+    first, last = i == 0, i == n - 1
+    A = (0.0, 0.0, 0.0) if first else (0.75, 0.25, 0.0)
+    B = (0.0, 1.0, 0.0) if first else (0.25, 0.75, 0.0)
+    C = (0.0, 1.0, 0.0) if last else (0.0, 0.75, 0.25)
+    D = (0.0, 0.0, 0.0) if last else (0.0, 0.25, 0.75)
+    return A, B, C, D
+
+
+def upsample_conv3x3_lowres(x, weight, bias=None):
+    """CPU restatement of the product's decoder formulation (ops.UpsampledConv3x3 = tap-stacked 1x1 GEMM on the LOW-res
+    tensor + csrc/upconv_gather.cu), used by tests to pin the algebra against the reference's own op order
+    nn.Upsample(scale_factor=2, mode='bilinear') -> nn.Conv2d(3x3, padding=1) (models/networks/cpvton/unet.py:138-146):
+        t[n, (fy,fx,co), i, j] = <x[n,:,i,j], w[co,:,fy,fx]>
+        y[n, co, 2i+p, 2j+q]   = b[co] + sum_{fy,fx} sum_{a,b} cy[fy+p][a] * cx[fx+q][b] * t[n,(fy,fx,co), i-1+a, j-1+b]
+    x: [N,Cin,h,w] -> [N,Cout,2h,2w]."""
+    N, Cin, h, w = x.shape
+    Cout = weight.shape[0]
+    t = torch.einsum("ncij,ocyx->nyxoij", x.double(), weight.double())  # [N,3,3,Cout,h,w]
+    tp = F.pad(t, (1, 1, 1, 1))  # neighbours outside the image meet zero coefficients
+    y = torch.zeros(N, Cout, 2 * h, 2 * w, dtype=torch.float64)
+    if bias is not None:
+        y += bias.double().view(1, -1, 1, 1)
+    for i in range(h):
+        cy = _up3_coeffs(i, h)
+        for j in range(w):
+            cx = _up3_coeffs(j, w)
+            nb = tp[:, :, :, :, i:i + 3, j:j + 3]  # [N,3,3,Cout,3(a),3(b)]
+            for p in range(2):
+                for q in range(2):
+                    acc = 0
+                    for fy in range(3):
+                        wy = torch.tensor(cy[fy + p], dtype=torch.float64)
+                        for fx in range(3):
+                            wx = torch.tensor(cx[fx + q], dtype=torch.float64)
+                            acc = acc + torch.einsum("noab,a,b->no", nb[:, fy, fx], wy, wx)
+                    y[:, :, 2 * i + p, 2 * j + q] += acc
+    return y.float()

@@ -151,3 +151,19 @@ def test_model_state_dict_matches_reference_key_for_key():
     _, shapes, _ = load_golden("train_gelu_attn")
     mine = {k: tuple(v.shape) for k, v in UnetMaskModel(make_hparams(is_train=True)).state_dict().items()}
     assert mine == shapes
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 4, 3, 3), (1, 3, 1, 1, 2), (1, 4, 1, 5, 2), (1, 2, 6, 1, 3), (1, 3, 2, 2, 1)])
+def test_lowres_decoder_formulation_equals_upsample_then_conv(shape):
+    """The algebra behind ops.UpsampledConv3x3 / upconv3x3_gather: conv3x3(bilinear_up2(x)) from the
+    tap-stacked products of the LOW-res tensor, borders (clamped interpolation, zero-padded conv) included."""
+    import torch.nn.functional as F
+
+    N, Cin, h, w, Cout = shape
+    g = torch.Generator().manual_seed(h * 10 + w)
+    x = torch.randn(N, Cin, h, w, generator=g)
+    wt = torch.randn(Cout, Cin, 3, 3, generator=g)
+    b = torch.randn(Cout, generator=g)
+    want = F.conv2d(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), wt, b, padding=1)
+    got = unet.upsample_conv3x3_lowres(x, wt, b)
+    assert torch.allclose(got, want, atol=2e-5, rtol=1e-5), (got - want).abs().max()
