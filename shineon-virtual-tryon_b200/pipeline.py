@@ -48,8 +48,17 @@ class TryOnPipeline:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(graph, capture_error_mode="thread_local"):  # other threads (NCCL watchdog) may poll events
-                out = fn(*args)
+            try:
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):  # other threads (NCCL watchdog) may poll events
+                    out = fn(*args)
+            except RuntimeError as e:  # a capture the runtime refuses must not take the step down: launch eagerly instead
+                import warnings
+
+                warnings.warn(f"TryOnPipeline: CUDA-graph capture failed ({str(e).splitlines()[0]}); running eagerly")
+                torch.cuda.synchronize()
+                self.cuda_graph = False
+                self._graphs.clear()
+                return fn(*args)
             ent = self._graphs[key] = (graph, out, _lib.launch_count() - n0)
         ent[0].replay()
         self.replayed_launches += ent[2]
