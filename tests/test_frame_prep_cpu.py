@@ -87,3 +87,28 @@ def test_library_host_coefficients_match_oracle():
         ob, ok = fp.pil_resize_coeffs(a, b)
         assert np.array_equal(bo.numpy(), ob) and np.array_equal(kk.numpy(), ok)
     assert lib.shineon_pil_bilinear_coeffs(0, 4, None, None) < 0
+
+
+def test_pil_resize_restatement_random_sizes():
+    """Wider sweep of the Pillow restatement: random in/out sizes on both axes (down, up, identity, extreme ratios)."""
+    from PIL import Image
+
+    r = np.random.RandomState(99)
+    for _ in range(40):
+        h, w = int(r.randint(1, 70)), int(r.randint(1, 70))
+        oh, ow = int(r.randint(1, 90)), int(r.randint(1, 90))
+        img = r.randint(0, 256, (h, w), dtype=np.uint8)
+        want = np.array(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
+        got = fp.pil_resize_bilinear_u8(img, ow, oh)
+        assert np.array_equal(got, want), (h, w, oh, ow)
+
+
+def test_silhouette_is_idempotent_on_uniform_maps_and_bounded():
+    """Size-independent properties: an all-background map gives -1 everywhere, an all-foreground map +1, and the
+    silhouette of any map stays inside [-1, 1]."""
+    for h, w in ((256, 192), (64, 48), (128, 16)):
+        assert np.all(fp.body_silhouette(np.zeros((h, w), np.uint8)) == -1.0)
+        assert np.all(fp.body_silhouette(np.full((h, w), 7, np.uint8)) == 1.0)
+        r = np.random.RandomState(h)
+        s = fp.body_silhouette((r.rand(h, w) > 0.5).astype(np.uint8) * 3)
+        assert s.min() >= -1.0 and s.max() <= 1.0 and s.shape == (1, h, w)
