@@ -116,12 +116,37 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def _quiet_nccl():
-    """stdout must carry exactly one JSON line: NCCL prints its version banner there at NCCL_DEBUG >= VERSION/WARN."""
-    if "SHINEON_NCCL_DEBUG" in os.environ:
-        os.environ["NCCL_DEBUG"] = os.environ["SHINEON_NCCL_DEBUG"]
-    else:
-        os.environ.pop("NCCL_DEBUG", None)
+def _route_nccl_log():
+    """stdout must carry exactly one JSON line, and NCCL prints its banner / INFO lines there: route them to stderr
+    (NCCL_DEBUG itself is left as the caller set it, so the driver can count the ranks in the log)."""
+    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+
+
+def bind_local_numa(local_rank, ranks_on_node):
+    """Pin this rank to CPU cores of the NUMA node its GPU hangs off (its share of them), BEFORE any pinned host buffer
+    is allocated, so first-touch places the staging buffers next to the GPU's PCIe root.  Best effort: returns a note."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id  # torch >= 2.1
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        devn = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devn:02x}.0/local_cpulist"
+        cpus = []
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return "no local cpus allowed"
+        per = max(1, len(allowed) // max(1, ranks_on_node))
+        mine = allowed[local_rank * per:(local_rank + 1) * per] or allowed
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, min(8, len(mine))))
+        return f"{len(mine)} cores of GPU-local NUMA cpulist ({mine[0]}-{mine[-1]})"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__}: {e})"
 
 
 def build_models():
@@ -287,10 +312,11 @@ def run_train(args, rank, world):
     from shineon_virtual_tryon_b200 import _lib, distributed, ops
     from shineon_virtual_tryon_b200.training import Trainer
 
-    _quiet_nccl()
+    _route_nccl_log()
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_local_numa(local, world)
     distributed.init_process_group("nccl", device=dev)
     model, hp = train_models()
     model = model.to(dev)
@@ -359,7 +385,7 @@ def run_train(args, rank, world):
                    "batch_per_gpu": B, "global_batch": B * world, "accumulated_batches": 1,
                    "parallelism": f"dp{world} (one flat 90.6 MB f32 gradient buffer, bucketed NCCL all-reduce"
                                   + (", overlapped with the backward)" if args.train_eager else ", after the CUDA-graph replay)"),
-                   "cuda_graph": replayed,
+                   "cuda_graph": replayed, "cpu_binding": numa,
                    "l2": "activations + weights + gradients per step exceed the 126 MB L2 (no flush needed)"},
         "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in host.values())) * world, "d2h_bytes_per_step": 4 * world,
@@ -398,7 +424,7 @@ def run_reference(args, rank):
         return
     fps, cores, sample, med = cpu_tryon_fps(args.cpu_clips, warmup=args.warmup, exact_steps=args.steps)
     line = {
-        "impl": "reference", "metric": "try-on frames/sec @256x192 (GMM warp + U-Net)", "value": fps,
+        "impl": "reference", "metric": TRYON_METRIC, "value": fps,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
@@ -412,6 +438,22 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------- B200 arm
+TRYON_METRIC = "try-on frames/sec @256x192 (GMM warp + U-Net)"
+N_INPUT_SETS = 4  # distinct device-resident input sets cycled by the timed loop: 4 x 39 MB of frames > the 126 MB L2
+
+
+def synth_raw_frames(frames, seed, pinned=True):
+    """Decoded 8-bit frames as the reference's Dataset.__getitem__ receives them from PIL (channel-last)."""
+    import torch
+
+    gr = torch.Generator().manual_seed(seed)
+    raw = {"image": torch.randint(0, 256, (frames, H, W, 3), dtype=torch.uint8, generator=gr),
+           "cloth": torch.randint(0, 256, (frames, H, W, 3), dtype=torch.uint8, generator=gr),
+           "densepose": torch.randint(0, 256, (frames, H, W, 3), dtype=torch.uint8, generator=gr),
+           "parse": torch.randint(0, 20, (frames, H, W), dtype=torch.uint8, generator=gr)}
+    return {k: v.pin_memory() for k, v in raw.items()} if pinned else raw
+
+
 def run_b200(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -419,111 +461,119 @@ def run_b200(args, rank, world):
     from shineon_virtual_tryon_b200 import _lib, distributed, ops
     from shineon_virtual_tryon_b200.pipeline import TryOnPipeline
 
-    _quiet_nccl()
+    _route_nccl_log()
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_local_numa(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     distributed.init_process_group("nccl", device=dev)
     barrier = distributed.barrier
 
     warp, tom = build_models()
     pipe = TryOnPipeline(warp.to(dev), tom.to(dev), cuda_graph=not args.no_graph)
     frames = args.clips * FRAMES_PER_CLIP
+    prep = ops.FramePrep(H, W, device=dev)
+    # headline input: decoded 8-bit frames (10 B/pixel); N_INPUT_SETS sets resident in HBM, cycled by the timed loop
+    raw_h = synth_raw_frames(frames, 200 + rank)
+    raw_sets = [tuple(synth_raw_frames(frames, 200 + rank + 1000 * i, pinned=False)[k].to(dev) for k in pipe.RAW_KEYS)
+                for i in range(N_INPUT_SETS)]
+    # the same work from the reference's f32 dataset tensors (the nn.Module surface)
     a_h, c_h, p_h = synth_inputs(frames, 100 + rank, pinned=True)
     a, c, p = a_h.to(dev), c_h.to(dev), p_h.to(dev)
-    # the same frames as a host batch keyed like the reference's dataset samples (agnostic is shared by both stages)
     batch_h = {"agnostic": a_h[:, :4].contiguous().pin_memory(), "cocopose": a_h[:, 4:].contiguous().pin_memory(),
                "densepose": p_h[:, 4:].contiguous().pin_memory(), "cloth": c_h}
     E2E_CH = 4 + 18 + 3 + 3
-    gr = torch.Generator().manual_seed(200 + rank)
-    raw_h = {"image": torch.randint(0, 256, (frames, H, W, 3), dtype=torch.uint8, generator=gr).pin_memory(),
-             "cloth": torch.randint(0, 256, (frames, H, W, 3), dtype=torch.uint8, generator=gr).pin_memory(),
-             "densepose": torch.randint(0, 256, (frames, H, W, 3), dtype=torch.uint8, generator=gr).pin_memory(),
-             "parse": torch.randint(0, 20, (frames, H, W), dtype=torch.uint8, generator=gr).pin_memory()}
-    prep = ops.FramePrep(H, W, device=dev)
 
-    def timed(fn, steps, sampler=None, drain=None):
+    def timed(fn, steps, sampler=None, drain=False):
         barrier()
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
-        if drain is not None:  # side-stream copies of the last calls must finish inside the timed region
+        for i in range(steps):
+            fn(i)
+        if drain:  # side-stream copies of the last calls must finish inside the timed region
             cur = torch.cuda.current_stream()
-            st = pipe._host_state
-            cur.wait_stream(st["s_in"])
-            cur.wait_stream(st["s_out"])
+            for st in pipe.host_streams():
+                cur.wait_stream(st)
         e1.record()
         barrier()
         clocks = sampler.stop() if sampler else None
         return distributed.max_over_ranks(e0.elapsed_time(e1), dev), clocks
 
+    def step_raw(i):
+        return pipe.run_raw(*raw_sets[i % N_INPUT_SETS], prep)
+
     def run_mode(precision):
         pipe.set_precision(precision)
-        for _ in range(args.warmup):
-            pipe(a, c, p)
+        for i in range(max(args.warmup, N_INPUT_SETS)):  # every input set's graph captured before the timed region
+            step_raw(i)
         l0 = _lib.launch_count() + pipe.replayed_launches
-        ms, clocks = timed(lambda: pipe(a, c, p), args.steps, ClockSampler(local) if rank == 0 else None)
+        ms, clocks = timed(step_raw, args.steps, ClockSampler(local) if rank == 0 else None)
         launches = _lib.launch_count() + pipe.replayed_launches - l0
         torch.cuda.synchronize()
         # roofline of the dominant kernel: the same steps once more, eagerly, with CUDA events around every tensor-core
         # launch on the launching stream (events cannot be recorded inside the replayed graph of the timed region)
         prof = []
         ops.PROFILE = prof
-        ms_prof, _ = timed(lambda: pipe(a, c, p), args.steps)
+        ms_prof, _ = timed(step_raw, args.steps)
         ops.PROFILE = None
         torch.cuda.synchronize()
         conv_ms = sum(r[1].elapsed_time(r[2]) for r in prof)
         conv_flops = sum(r[0] for r in prof)
         exec_flops = sum(r[4] if len(r) > 4 else r[0] for r in prof)  # decoder convs run at the low resolution
-        # end-to-end through the host-buffer API
+        # end to end through the host-buffer API: uint8 frames up, uint8 try-on frames down
         for _ in range(max(2, args.warmup)):  # both double-buffer slots (each owns a captured graph) must be warm
-            pipe.run_host_batch(batch_h)
-        pipe.host_sync()
-        ms_e2e, _ = timed(lambda: pipe.run_host_batch(batch_h), args.steps, drain=pipe.host_sync)
-        # the same frames/step from decoded 8-bit frames: the reference's Dataset.__getitem__ tensor prep runs on the GPU
-        for _ in range(max(2, args.warmup)):
             pipe.run_host_raw(raw_h, prep)
         pipe.host_sync()
-        ms_raw, _ = timed(lambda: pipe.run_host_raw(raw_h, prep), args.steps, drain=pipe.host_sync)
-        return dict(ms_raw=ms_raw, ms=ms, clocks=clocks, launches=launches, conv_ms=conv_ms, conv_flops=conv_flops,
-                    conv_launches=len(prof), ms_e2e=ms_e2e, exec_flops=exec_flops, ms_prof=ms_prof)
+        ms_e2e, _ = timed(lambda i: pipe.run_host_raw(raw_h, prep), args.steps, drain=True)
+        # the f32 tensor surface, device-resident and through the host
+        for _ in range(args.warmup):
+            pipe(a, c, p)
+        ms_f32, _ = timed(lambda i: pipe(a, c, p), args.steps)
+        for _ in range(max(2, args.warmup)):
+            pipe.run_host_batch(batch_h)
+        pipe.host_sync()
+        ms_f32_e2e, _ = timed(lambda i: pipe.run_host_batch(batch_h), args.steps, drain=True)
+        pipe.host_sync()
+        return dict(ms=ms, clocks=clocks, launches=launches, conv_ms=conv_ms, conv_flops=conv_flops,
+                    conv_launches=len(prof), ms_e2e=ms_e2e, exec_flops=exec_flops, ms_prof=ms_prof, ms_f32=ms_f32,
+                    ms_f32_e2e=ms_f32_e2e)
 
     main = run_mode("fp16x3")
     fast = {m: run_mode(m) for m in ("bf16x3", "fp16", "bf16")} if args.fast else None
 
     total_frames = frames * world * args.steps
-    value = total_frames / (main["ms"] * 1e-3)
-    e2e = total_frames / (main["ms_e2e"] * 1e-3)
+    fps = lambda ms: total_frames / (ms * 1e-3)
     peaks, peak_src = read_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     ach_tf = main["conv_flops"] / (main["conv_ms"] * 1e-3) / 1e12 if main["conv_ms"] > 0 else 0.0
 
     line = {
-        "metric": "try-on frames/sec @256x192 (GMM warp + U-Net)", "value": value, "unit": "frames/s",
+        "metric": TRYON_METRIC, "value": fps(main["ms"]), "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms"] / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp16x3 (hi/lo-split fp16 operands, 3 tcgen05 MMAs per product, fp32 TMEM accumulate; fp32-grade)",
         "data": "synthetic",
         "config": {
-            "workload": "configs[2]: 5-frame clips 256x192, GMM(FeatureExtraction x2, correlation, regression, TPS) -> "
-                        "grid_sample(border) -> U-Net(num_downs 6, self-attn x4, GELU, InstanceNorm) -> tanh/sigmoid compose",
+            "workload": "configs[2]: 5-frame clips 256x192, decoded 8-bit frames -> dataset tensor prep (ops.FramePrep) -> "
+                        "GMM(FeatureExtraction x2, correlation, regression, TPS) -> grid_sample(border) -> "
+                        "U-Net(num_downs 6, self-attn x4, GELU, InstanceNorm) -> tanh/sigmoid compose -> 8-bit try-on frames",
             "clips_per_step_per_gpu": args.clips, "frames_per_clip": FRAMES_PER_CLIP, "frames_per_step": frames * world,
             "parallelism": f"dp{world} (clips sharded, no collective)", "weights": "seeded random (no checkpoints offline)",
-            "cuda_graph": not args.no_graph,
-            "l2": f"inputs per step {frames * 32 * H * W * 4 / 1e6:.0f} MB > 126 MB L2 (no flush needed)",
+            "cuda_graph": not args.no_graph, "cpu_binding": numa,
+            "l2": f"{N_INPUT_SETS} input sets of {frames * 10 * H * W / 1e6:.0f} MB cycled (> 126 MB L2 together); each step also "
+                  "moves > 5 GB of activations through HBM (no flush needed)",
         },
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": frames * world * E2E_CH * H * W * 4,
-                "d2h_bytes_per_step": frames * world * 3 * H * W * 4, "ms_per_step": main["ms_e2e"] / args.steps,
-                "api": "TryOnPipeline.run_host_batch: pinned host batch dict (agnostic, cocopose, densepose, cloth; f32) -> H2D -> "
-                       "kernels -> D2H of p_tryon (double-buffered streams); PCIe-bound"},
-        "e2e_raw_u8": {"value": total_frames / (main["ms_raw"] * 1e-3), "unit": "frames/s",
-                       "h2d_bytes_per_step": frames * world * 10 * H * W, "d2h_bytes_per_step": frames * world * 3 * H * W * 4,
-                       "ms_per_step": main["ms_raw"] / args.steps,
-                       "api": "TryOnPipeline.run_host_raw: pinned uint8 decoded frames (image, parse, cloth, densepose) -> H2D -> "
-                              "ops.FramePrep (the reference Dataset.__getitem__ tensor prep, bit-exact, SURVEY 8f N4) -> kernels -> D2H"},
+        "e2e": {"value": fps(main["ms_e2e"]), "unit": "frames/s", "h2d_bytes_per_step": frames * world * 10 * H * W,
+                "d2h_bytes_per_step": frames * world * 3 * H * W, "ms_per_step": main["ms_e2e"] / args.steps,
+                "api": "TryOnPipeline.run_host_raw: pinned uint8 decoded frames (image, parse, cloth, densepose) -> H2D -> "
+                       "ops.FramePrep (the reference Dataset.__getitem__ tensor prep, bit-exact) -> kernels -> uint8 frames as "
+                       "visualization.save_images encodes them -> D2H (double-buffered copy streams)"},
+        "f32_tensor_api": {"value": fps(main["ms_f32"]), "e2e": fps(main["ms_f32_e2e"]), "unit": "frames/s",
+                           "h2d_bytes_per_step": frames * world * E2E_CH * H * W * 4, "d2h_bytes_per_step": frames * world * 3 * H * W * 4,
+                           "api": "TryOnPipeline.__call__ / run_host_batch on the reference's f32 dataset tensors (112 B/pixel up, 12 down; "
+                                  "round 1's headline)"},
         "gpu_launches": main["launches"] * world,
         "clocks": main["clocks"],
         "roofline": {
@@ -545,25 +595,28 @@ def run_b200(args, rank, world):
             "traffic": None,
         },
     }
-    # measured DRAM bytes of the same launches from the committed ncu --set full capture (profiles/r01_conv_step_full.md)
-    try:
-        cap = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_step_full.json")))
-        line["roofline"]["traffic"] = cap["conv_dram_bytes_per_launch"]
-        line["roofline"]["traffic_note"] = (f"dram__bytes_read+write per conv_igemm launch, mean over {cap['conv_launches_captured']} of "
-                                            f"{cap['conv_launches_per_step']} launches of one step (ncu --set full, profiles/r01_conv_step_full.md)")
-    except Exception:  # noqa: BLE001  (no capture committed: traffic stays null)
-        pass
+    # measured DRAM bytes of the same launches from the newest committed ncu --set full capture of one step
+    for cap_name in ("r02_conv_step_full.json", "r01_conv_step_full.json"):
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", cap_name)))
+            line["roofline"]["traffic"] = cap["conv_dram_bytes_per_launch"]
+            line["roofline"]["traffic_note"] = (f"dram__bytes_read+write per conv_igemm launch, mean over {cap['conv_launches_captured']} of "
+                                                f"{cap['conv_launches_per_step']} launches of one step (ncu --set full capture committed as "
+                                                f"profiles/{cap_name}; not re-measured by this run)")
+            break
+        except Exception:  # noqa: BLE001  (no capture committed: traffic stays null)
+            pass
     if fast is not None:
         line["other_precisions"] = {
-            m: {"value": total_frames / (r["ms"] * 1e-3), "unit": "frames/s", "e2e": total_frames / (r["ms_e2e"] * 1e-3),
+            m: {"value": fps(r["ms"]), "unit": "frames/s", "e2e": fps(r["ms_e2e"]),
                 "conv_tflops": r["conv_flops"] / (r["conv_ms"] * 1e-3) / 1e12}
             for m, r in fast.items()}
         line["other_precisions"]["note"] = ("not parity-green at 1e-3 except bf16x3; measured error bounds in "
                                             "tests/test_e2e_gpu.py::test_other_precision_modes")
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            fps, cores, sample, _ = cpu_tryon_fps(args.cpu_clips)
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+            cfps, cores, sample, _ = cpu_tryon_fps(args.cpu_clips)
+            line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

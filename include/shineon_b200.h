@@ -292,11 +292,18 @@ int shineon_linear_tanh(const float* x, const float* weight, const float* bias, 
  *   if warped_prev != NULL (frame f>0 with flows): rend' = (1-fmask)*warped_prev + fmask*rend
  *   tryon = (1-mask)*rend' + mask*cloth
  * Writes NCHW f32 channel slices of p_rendereds [B,3n,H,W], tryon_masks [B,n,H,W],
- * p_tryons [B,3n,H,W], flow_masks [B,n,H,W] (may be NULL) for frame index f.
+ * p_tryons [B,3n,H,W], flow_masks [B,n,H,W] for frame index f (any of them may be NULL = not wanted), and, when
+ * p_tryons_u8 != NULL, the frame's try-on image as the reference saves it (shineon_image_to_u8) into
+ * uint8 [B,n,H,W,3].  At least one of p_tryons / p_tryons_u8 must be given.
  * cloth is [B,3n,H,W]; warped_prev is [B,3,H,W] or NULL. */
 int shineon_tom_compose(const float* unet_out, int Cout, const float* cloth, const float* warped_prev,
-                        float* p_rendereds, float* tryon_masks, float* p_tryons, float* flow_masks, int B,
-                        int H, int W, int n_frames, int frame, int flow_warp, shineon_stream_t stream);
+                        float* p_rendereds, float* tryon_masks, float* p_tryons, float* flow_masks,
+                        unsigned char* p_tryons_u8, int B, int H, int W, int n_frames, int frame, int flow_warp,
+                        shineon_stream_t stream);
+/* U8 / 8f N2: the reference's image writer (visualization.py:73-76 save_images) without the PNG encoder:
+ *   y = uint8(clamp((x + 1) * 0.5 * 255, 0, 255))  (truncation, like numpy astype), channel-last.
+ * x f32 [B,C,H,W] -> y uint8 [B,H,W,C].  Bit-exact against the reference arithmetic on the same f32 input. */
+int shineon_image_to_u8(const float* x, unsigned char* y, int B, int C, int H, int W, shineon_stream_t stream);
 
 /* ------------------------------------------------------------------ */
 /* F2: FlowNet2 glue (models/flownet2_pytorch/models.py:127-192, models/flownet.py:42-63) */

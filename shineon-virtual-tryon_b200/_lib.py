@@ -113,7 +113,8 @@ SIGNATURES = {
     "shineon_maxpool2x2_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_nhwc_to_nchw_add": [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_maxpool2x2_bwd": [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_p],
-    "shineon_tom_compose": [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_tom_compose": [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_image_to_u8": [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
 }
 _RESTYPES = {"shineon_last_error": C.c_char_p, "shineon_launch_count": C.c_uint64,
              "shineon_conv2d_wgrad_workspace_bytes": C.c_size_t,

@@ -496,31 +496,113 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------ 8-bit image writer
+// visualization.save_images (visualization.py:73-76): tensor = (img + 1) * 0.5 * 255 -> clamp(0, 255) ->
+// numpy astype("uint8") (truncation) -> channel-last.  Separate roundings like the reference's three torch ops (no FMA).
+__device__ __forceinline__ uint8_t image_u8(float x) {
+  float t = __fmul_rn(__fmul_rn(__fadd_rn(x, 1.f), 0.5f), 255.f);
+  t = fminf(fmaxf(t, 0.f), 255.f);
+  return (uint8_t)(int)t;
+}
+
+// x f32 [B,C,H,W] (C = 1 or 3) -> y uint8 [B,H,W,C]; 4 consecutive pixels per thread (float4 loads per channel plane,
+// 32-bit stores of the interleaved bytes).
+template <int C>
+__global__ void __launch_bounds__(256)
+    image_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int HW) {
+  const int b = blockIdx.y;
+  const int p0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (p0 >= HW) return;
+  uint8_t v[4 * C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(x + ((long)b * C + c) * HW + p0));
+    v[c] = image_u8(f.x); v[C + c] = image_u8(f.y); v[2 * C + c] = image_u8(f.z); v[3 * C + c] = image_u8(f.w);
+  }
+  uint32_t* dst = reinterpret_cast<uint32_t*>(y + ((long)b * HW + p0) * C);
+#pragma unroll
+  for (int i = 0; i < C; ++i)
+    dst[i] = (uint32_t)v[4 * i] | ((uint32_t)v[4 * i + 1] << 8) | ((uint32_t)v[4 * i + 2] << 16) | ((uint32_t)v[4 * i + 3] << 24);
+}
+
+__global__ void __launch_bounds__(256)
+    image_to_u8_scalar_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int HW, int C) {
+  const int b = blockIdx.y;
+  for (long e = (long)blockIdx.x * 256 + threadIdx.x; e < (long)HW * C; e += (long)gridDim.x * 256) {
+    const int c = (int)(e % C);
+    const long p = e / C;
+    y[(long)b * HW * C + e] = image_u8(x[((long)b * C + c) * HW + p]);
+  }
+}
+
 // ------------------------------------------------------------------------------ TOM compose
+// One thread = 4 consecutive pixels of one image: the NHWC U-Net output is read as whole pixels, every NCHW plane is
+// written with float4 stores, the optional 8-bit try-on image with three 32-bit stores.
+template <bool VEC4>
 __global__ void __launch_bounds__(256)
     tom_compose_kernel(const float* __restrict__ u, int Cout, const float* __restrict__ cloth,
                        const float* __restrict__ warped_prev, float* __restrict__ p_rend, float* __restrict__ masks,
-                       float* __restrict__ p_tryon, float* __restrict__ fmasks, int HW, int nf, int f, int flow_warp) {
+                       float* __restrict__ p_tryon, float* __restrict__ fmasks, uint8_t* __restrict__ tryon_u8, int HW,
+                       int nf, int f, int flow_warp) {
+  constexpr int PX = VEC4 ? 4 : 1;
   const int b = blockIdx.y;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
-    const float* up = u + ((long)b * HW + p) * Cout;
-    const float m = 1.f / (1.f + expf(-up[3 * nf + f]));  // F.sigmoid (unet_mask_model.py:85)
-    float fm = 0.f;
-    if (flow_warp) fm = 1.f / (1.f + expf(-up[4 * nf + f]));
-    masks[((long)b * nf + f) * HW + p] = m;
-    if (flow_warp && fmasks) fmasks[((long)b * nf + f) * HW + p] = fm;
+  for (int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX; p0 < HW; p0 += gridDim.x * blockDim.x * PX) {
+    float m[PX], fm[PX], r[3][PX];
+#pragma unroll
+    for (int i = 0; i < PX; ++i) {
+      const float* up = u + ((long)b * HW + p0 + i) * Cout;
+      m[i] = 1.f / (1.f + expf(-__ldg(up + 3 * nf + f)));  // F.sigmoid (unet_mask_model.py:85)
+      fm[i] = flow_warp ? 1.f / (1.f + expf(-__ldg(up + 4 * nf + f))) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) r[k][i] = tanhf(__ldg(up + 3 * f + k));  // F.tanh (unet_mask_model.py:84)
+    }
+    auto store = [&](float* base, long o, const float (&v)[PX]) {
+      if (!base) return;
+      if constexpr (VEC4) *reinterpret_cast<float4*>(base + o) = make_float4(v[0], v[1], v[2], v[3]);
+      else base[o] = v[0];
+    };
+    auto load = [&](const float* base, long o, float (&v)[PX]) {
+      if constexpr (VEC4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(base + o));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+        v[0] = __ldg(base + o);
+      }
+    };
+    store(masks, ((long)b * nf + f) * HW + p0, m);
+    if (flow_warp) store(fmasks, ((long)b * nf + f) * HW + p0, fm);
+    uint8_t q[3][PX];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const float r = tanhf(up[3 * f + k]);  // F.tanh (unet_mask_model.py:84)
-      const long o = ((long)b * 3 * nf + 3 * f + k) * HW + p;
-      p_rend[o] = r;
-      float rr = r;
+      const long o = ((long)b * 3 * nf + 3 * f + k) * HW + p0;
+      store(p_rend, o, r[k]);
+      float rr[PX], c[PX], t[PX];
+#pragma unroll
+      for (int i = 0; i < PX; ++i) rr[i] = r[k][i];
       if (warped_prev) {  // unet_mask_model.py:118-121
-        const float w = warped_prev[((long)b * 3 + k) * HW + p];
-        rr = (1.f - fm) * w + fm * r;
+        float w[PX];
+        load(warped_prev, ((long)b * 3 + k) * HW + p0, w);
+#pragma unroll
+        for (int i = 0; i < PX; ++i) rr[i] = (1.f - fm[i]) * w[i] + fm[i] * r[k][i];
       }
-      const float c = cloth[o];
-      p_tryon[o] = (1.f - m) * rr + m * c;  // unet_mask_model.py:126-129
+      load(cloth, o, c);
+#pragma unroll
+      for (int i = 0; i < PX; ++i) {
+        t[i] = (1.f - m[i]) * rr[i] + m[i] * c[i];  // unet_mask_model.py:126-129
+        q[k][i] = image_u8(t[i]);
+      }
+      store(p_tryon, o, t);
+    }
+    if (tryon_u8) {  // [B, nf, H, W, 3]
+      uint8_t* dst = tryon_u8 + (((long)b * nf + f) * HW + p0) * 3;
+      if constexpr (VEC4) {
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+        d32[0] = (uint32_t)q[0][0] | ((uint32_t)q[1][0] << 8) | ((uint32_t)q[2][0] << 16) | ((uint32_t)q[0][1] << 24);
+        d32[1] = (uint32_t)q[1][1] | ((uint32_t)q[2][1] << 8) | ((uint32_t)q[0][2] << 16) | ((uint32_t)q[1][2] << 24);
+        d32[2] = (uint32_t)q[2][2] | ((uint32_t)q[0][3] << 8) | ((uint32_t)q[1][3] << 16) | ((uint32_t)q[2][3] << 24);
+      } else {
+        dst[0] = q[0][0]; dst[1] = q[1][0]; dst[2] = q[2][0];
+      }
     }
   }
 }
@@ -719,15 +801,40 @@ extern "C" int shineon_upsample2x_cat(const void* s0_hi, const void* s0_lo, int 
 }
 
 extern "C" int shineon_tom_compose(const float* unet_out, int Cout, const float* cloth, const float* warped_prev,
-                                   float* p_rendereds, float* tryon_masks, float* p_tryons, float* flow_masks, int B,
-                                   int H, int W, int n_frames, int frame, int flow_warp, shineon_stream_t stream) {
-  SHINEON_REQUIRE(unet_out && cloth && p_rendereds && tryon_masks && p_tryons, "tom_compose: null pointer");
+                                   float* p_rendereds, float* tryon_masks, float* p_tryons, float* flow_masks,
+                                   unsigned char* p_tryons_u8, int B, int H, int W, int n_frames, int frame, int flow_warp,
+                                   shineon_stream_t stream) {
+  SHINEON_REQUIRE(unet_out && cloth && (p_tryons || p_tryons_u8), "tom_compose: null pointer");
   SHINEON_REQUIRE(n_frames >= 1 && frame >= 0 && frame < n_frames, "tom_compose: frame %d of %d", frame, n_frames);
   SHINEON_REQUIRE(Cout == (flow_warp ? 5 : 4) * n_frames, "tom_compose: Cout %d != %d*n_frames", Cout, flow_warp ? 5 : 4);
   SHINEON_REQUIRE(!warped_prev || flow_warp, "tom_compose: warped_prev needs flow_warp");
   SHINEON_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "tom_compose: bad shape");
-  dim3 grid(grid_x((long)H * W, 256), B);
-  tom_compose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(unet_out, Cout, cloth, warped_prev, p_rendereds, tryon_masks,
-                                                            p_tryons, flow_masks, H * W, n_frames, frame, flow_warp);
+  const int HW = H * W;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec4 = HW % 4 == 0 && al16(cloth) && al16(warped_prev) && al16(p_rendereds) && al16(tryon_masks) &&
+                    al16(p_tryons) && al16(flow_masks) && (reinterpret_cast<uintptr_t>(p_tryons_u8) & 3) == 0;
+  if (vec4) {
+    dim3 grid(grid_x((long)HW / 4, 256), B);
+    tom_compose_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(unet_out, Cout, cloth, warped_prev, p_rendereds, tryon_masks,
+                                                                   p_tryons, flow_masks, p_tryons_u8, HW, n_frames, frame, flow_warp);
+  } else {
+    dim3 grid(grid_x((long)HW, 256), B);
+    tom_compose_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(unet_out, Cout, cloth, warped_prev, p_rendereds, tryon_masks,
+                                                                    p_tryons, flow_masks, p_tryons_u8, HW, n_frames, frame, flow_warp);
+  }
   return after_launch("tom_compose_kernel");
+}
+
+extern "C" int shineon_image_to_u8(const float* x, unsigned char* y, int B, int C, int H, int W, shineon_stream_t stream) {
+  SHINEON_REQUIRE(x && y, "image_to_u8: null pointer");
+  SHINEON_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "image_to_u8: bad shape");
+  const int HW = H * W;
+  const bool vec = HW % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 3) == 0;
+  if (vec && C == 3)
+    image_to_u8_kernel<3><<<dim3(cdiv(HW / 4, 256), B), 256, 0, (cudaStream_t)stream>>>(x, y, HW);
+  else if (vec && C == 1)
+    image_to_u8_kernel<1><<<dim3(cdiv(HW / 4, 256), B), 256, 0, (cudaStream_t)stream>>>(x, y, HW);
+  else
+    image_to_u8_scalar_kernel<<<dim3(grid_x((long)HW * C, 256), B), 256, 0, (cudaStream_t)stream>>>(x, y, HW, C);
+  return after_launch("image_to_u8_kernel");
 }

@@ -50,6 +50,16 @@ class UnetMaskModel(BaseModel):
 
     def forward(self, person_representation, warped_cloths, flows=None, prev_im=None):
         """-> (p_rendereds, tryon_masks, p_tryons, flow_masks)  (unet_mask_model.py:64-135)."""
+        return self._forward(person_representation, warped_cloths, flows)[:4]
+
+    def forward_u8(self, person_representation, warped_cloths, flows=None, f32_outputs=False):
+        """The same forward with the try-on frames encoded the way the reference writes them to disk
+        (visualization.py:73-76, fused into the compose kernel): returns uint8 [B,n,H,W,3]; with f32_outputs also the
+        reference's 4-tuple."""
+        res = self._forward(person_representation, warped_cloths, flows, want_u8=True, want_f32=f32_outputs)
+        return (res[4],) + tuple(res[:4]) if f32_outputs else res[4]
+
+    def _forward(self, person_representation, warped_cloths, flows=None, want_u8=False, want_f32=True):
         n = self.hparams.n_frames_total
         flow_warp = bool(self.hparams.flow_warp)
         prec = ops.resolve_precision(self.unet.precision)
@@ -57,12 +67,19 @@ class UnetMaskModel(BaseModel):
         warped_cloths = warped_cloths.contiguous()
         # torch.cat([person, cloth], 1) is fused into the NCHW -> NHWC-planes (im2col) conversion
         out = self.unet.model.run((person_representation, warped_cloths), prec)  # f32 NHWC [B,H,W,(4|5)n]
+        return self._compose(out, warped_cloths, flows, want_u8, want_f32)
+
+    def _compose(self, out, warped_cloths, flows=None, want_u8=False, want_f32=True):
+        n = self.hparams.n_frames_total
+        flow_warp = bool(self.hparams.flow_warp)
         B, H, W, _ = out.shape
         dev = out.device
-        p_rendereds = torch.empty(B, 3 * n, H, W, device=dev)
-        tryon_masks = torch.empty(B, n, H, W, device=dev)
-        p_tryons = torch.empty(B, 3 * n, H, W, device=dev)
-        flow_masks = torch.empty(B, n, H, W, device=dev) if flow_warp else None
+        chain = flows is not None and n > 1  # frame f reads p_tryon of frame f-1 through Resample2d
+        p_rendereds = torch.empty(B, 3 * n, H, W, device=dev) if want_f32 else None
+        tryon_masks = torch.empty(B, n, H, W, device=dev) if want_f32 else None
+        p_tryons = torch.empty(B, 3 * n, H, W, device=dev) if (want_f32 or chain) else None
+        flow_masks = torch.empty(B, n, H, W, device=dev) if (flow_warp and want_f32) else None
+        tryon_u8 = torch.empty(B, n, H, W, 3, dtype=torch.uint8, device=dev) if want_u8 else None
         outs = (p_rendereds, tryon_masks, p_tryons, flow_masks)
         flows_c = list(torch.chunk(flows, n, dim=1)) if flows is not None else None
         for f in range(n):
@@ -70,8 +87,8 @@ class UnetMaskModel(BaseModel):
             if flows_c is not None and f > 0:
                 prev_generated = p_tryons[:, 3 * (f - 1):3 * f].contiguous()
                 warped_prev = self.resample(prev_generated, flows_c[f].contiguous())
-            ops.tom_compose(out, warped_cloths, n, flow_warp, outs, frame=f, warped_prev=warped_prev)
-        return p_rendereds, tryon_masks, p_tryons, flow_masks
+            ops.tom_compose(out, warped_cloths, n, flow_warp, outs, frame=f, warped_prev=warped_prev, tryon_u8=tryon_u8)
+        return p_rendereds, tryon_masks, p_tryons, flow_masks, tryon_u8
 
     def set_train_precision(self, precision):
         """Numeric mode of the training step: "bf16x3" (default; fp32-grade products, parity-tested) or "bf16" (the

@@ -636,14 +636,28 @@ def linear_tanh(x, weight, bias):
     return theta
 
 
-def tom_compose(unet_out, cloth, n_frames, flow_warp, outs, frame=0, warped_prev=None):
-    """unet_out f32 NHWC [B,H,W,Cout]; outs = (p_rendereds, tryon_masks, p_tryons, flow_masks|None) NCHW."""
+def tom_compose(unet_out, cloth, n_frames, flow_warp, outs, frame=0, warped_prev=None, tryon_u8=None):
+    """unet_out f32 NHWC [B,H,W,Cout]; outs = (p_rendereds, tryon_masks, p_tryons, flow_masks|None) NCHW, any may be None;
+    tryon_u8: optional uint8 [B,n,H,W,3] receiving the frame's try-on image as visualization.save_images encodes it."""
     unet_out, cloth = _req(unet_out), _req(cloth)
     B, H, W, Cout = unet_out.shape
     pr, tm, pt, fm = outs
+    if tryon_u8 is not None:
+        _req(tryon_u8, torch.uint8, "tryon_u8")
+        assert tuple(tryon_u8.shape) == (B, n_frames, H, W, 3)
     check(_lib.load().shineon_tom_compose(_p(unet_out), Cout, _p(cloth), _p(warped_prev), _p(pr), _p(tm), _p(pt),
-                                          _p(fm), B, H, W, n_frames, frame, int(bool(flow_warp)), _stream()),
+                                          _p(fm), _p(tryon_u8), B, H, W, n_frames, frame, int(bool(flow_warp)), _stream()),
           "shineon_tom_compose")
+
+
+def image_to_u8(x):
+    """visualization.save_images' encoding (visualization.py:73-76) on the device: f32 [B,C,H,W] in [-1,1] ->
+    uint8 [B,H,W,C] = clamp((x + 1) * 0.5 * 255, 0, 255) truncated.  Bit-exact on the same f32 input."""
+    x = _req(x, name="image")
+    B, Cc, H, W = x.shape
+    y = torch.empty(B, H, W, Cc, dtype=torch.uint8, device=x.device)
+    check(_lib.load().shineon_image_to_u8(_p(x), _p(y), B, Cc, H, W, _stream()), "shineon_image_to_u8")
+    return y
 
 
 # ----------------------------------------------------------------------------- FlowNet2 glue

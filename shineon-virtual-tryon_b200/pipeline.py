@@ -3,23 +3,36 @@
 The reference runs the two stages as separate `test.py` invocations and passes the warped cloth through 8-bit
 PNGs on disk (docs/2_inference.md:13-39, models/warp_model.py:146-148, datasets/vvt_dataset.py:133-150).
 This class chains the same two forwards (WarpModel.forward + grid_sample(border), UnetMaskModel.forward)
-on the device; `run_host` is the host-buffer entry point used for the end-to-end number (pinned host
-tensors in, pinned host tensor out, copies on the caller's stream).
+on the device.  Entry points, from the reference's tensors to its file formats:
+
+  pipe(person_gmm, cloth, person_tom)      f32 device tensors in, f32 device tensors out (the nn.Module surface)
+  pipe.run_raw(parse, cloth, densepose, image, prep)
+                                           decoded 8-bit frames on the device in (what Dataset.__getitem__ starts from),
+                                           8-bit try-on frames out (what visualization.save_images hands to the PNG encoder)
+  pipe.run_host / run_host_batch           pinned f32 host tensors in, pinned f32 host image out
+  pipe.run_host_raw(raw_h, prep)           pinned uint8 host frames in, pinned uint8 host frames out: 10 B/pixel up,
+                                           3 B/pixel down (the f32 forms move 112 and 12)
 """
+from collections import OrderedDict
+
 import torch
 
 
 class TryOnPipeline:
+    MAX_GRAPHS = 8
+
     def __init__(self, warp_model, tom_model, cuda_graph=False):
         """cuda_graph=True: the ~180 launches of a step are captured once per distinct set of input buffers and
         replayed (the small launches at the bottom of the U-Net are otherwise issued slower than the GPU runs them).
         Replayed calls return the graph's static output tensors: they are overwritten by the next call with the same
-        input buffers."""
+        input buffers.  A graph is keyed on its input buffers, the stage function and the models' weights / precision,
+        so loading a checkpoint or changing a parameter re-captures instead of replaying stale packed weights."""
         self.warp_model = warp_model
         self.tom_model = tom_model
-        self._host_state = None
+        self._host_state = {}
         self.cuda_graph = bool(cuda_graph)
-        self._graphs = {}
+        self._graphs = OrderedDict()
+        self._tensors = None
         self.replayed_launches = 0  # kernel launches executed through graph replays (not seen by shineon_launch_count)
 
     def set_precision(self, precision):
@@ -27,22 +40,53 @@ class TryOnPipeline:
         self.tom_model.set_precision(precision)
         self._graphs.clear()  # captured graphs hold the previous mode's kernels
 
+    # ------------------------------------------------------------------ stage functions (device tensors -> device tensors)
     def _stages(self, person_gmm, cloth, person_tom):
         warped_cloth, _, _, _ = self.warp_model.warp(person_gmm, cloth, cloth)
         _, tryon_masks, p_tryons, _ = self.tom_model(person_tom, warped_cloth)
         return p_tryons, tryon_masks, warped_cloth
 
+    def _stages_batch(self, agnostic, cocopose, densepose, cloth):
+        return self._stages(torch.cat([agnostic, cocopose], 1), cloth, torch.cat([agnostic, densepose], 1))
+
+    def _raw_fn(self, prep, u8_out):
+        """Stage function over decoded 8-bit frames for one FramePrep instance (cached: graphs are keyed on it)."""
+        cache = self.__dict__.setdefault("_raw_fns", {})
+        key = (id(prep), bool(u8_out))
+        if key not in cache:
+            def stages(parse, cloth, densepose, image):
+                b = prep(parse, cloth, densepose, image)
+                person_gmm = torch.cat([b["agnostic"], b["cocopose"]], 1)
+                person_tom = torch.cat([b["agnostic"], b["densepose"]], 1)
+                if not u8_out:
+                    return self._stages(person_gmm, b["cloth"], person_tom)
+                warped_cloth, _, _, _ = self.warp_model.warp(person_gmm, b["cloth"], b["cloth"])
+                u8 = self.tom_model.forward_u8(person_tom, warped_cloth)  # [F,1,H,W,3]
+                return (u8.view(u8.shape[0], u8.shape[2], u8.shape[3], 3),)
+
+            cache[key] = (stages, prep)  # keeps `prep` alive so its id stays unique
+        return cache[key][0]
+
+    # ------------------------------------------------------------------ CUDA-graph cache
+    def _weights_signature(self):
+        if self._tensors is None:
+            self._tensors = [t for m in (self.warp_model, self.tom_model) for t in list(m.parameters()) + list(m.buffers())]
+        from .networks._engine_util import WEIGHTS_EPOCH
+
+        return (WEIGHTS_EPOCH[0],) + tuple((t.data_ptr(), t._version) for t in self._tensors)
+
     def _graph_call(self, tag, fn, args):
-        """fn(*args) through a CUDA graph keyed by (tag, argument buffers).  Eager while ops.PROFILE is collecting."""
+        """fn(*args) through a CUDA graph keyed by (tag, fn, argument buffers, weights).  Eager while ops.PROFILE is
+        collecting."""
         from . import _lib, ops
 
         if not self.cuda_graph or ops.PROFILE is not None:
             return fn(*args)
-        key = (tag,) + tuple((a.data_ptr(), tuple(a.shape), a.dtype) for a in args)
+        key = (tag, id(fn), self._weights_signature()) + tuple((a.data_ptr(), tuple(a.shape), a.dtype) for a in args)
         ent = self._graphs.get(key)
         if ent is None:
-            if len(self._graphs) >= 8:
-                self._graphs.clear()
+            while len(self._graphs) >= self.MAX_GRAPHS:
+                self._graphs.popitem(last=False)  # least recently used
             for _ in range(2):  # weight packing, allocator warm-up: nothing of that may happen inside the capture
                 fn(*args)
             torch.cuda.synchronize()
@@ -60,16 +104,30 @@ class TryOnPipeline:
                 self._graphs.clear()
                 return fn(*args)
             ent = self._graphs[key] = (graph, out, _lib.launch_count() - n0)
+        else:
+            self._graphs.move_to_end(key)
         ent[0].replay()
         self.replayed_launches += ent[2]
         return ent[1]
 
+    # ------------------------------------------------------------------ device entry points
     @torch.no_grad()
     def __call__(self, person_gmm, cloth, person_tom):
         """person_gmm [F,22,H,W] (agnostic+cocopose), cloth [F,3,H,W], person_tom [F,7,H,W] (agnostic+densepose);
         all f32 CUDA.  Returns (p_tryon [F,3,H,W], tryon_mask [F,1,H,W], warped_cloth [F,3,H,W])."""
         return self._graph_call("call", self._stages, (person_gmm, cloth, person_tom))
 
+    RAW_KEYS = ("parse", "cloth", "densepose", "image")
+
+    @torch.no_grad()
+    def run_raw(self, parse, cloth, densepose, image, prep, u8_out=True):
+        """Decoded 8-bit frames on the device (`image`, `cloth`, `densepose` [F,H,W,3], `parse` [F,H,W], uint8) ->
+        try-on frames uint8 [F,H,W,3] exactly as visualization.save_images would encode them (u8_out=False: the f32
+        triple of __call__).  The reference's Dataset.__getitem__ tensor prep runs on the device (ops.FramePrep)."""
+        out = self._graph_call("raw", self._raw_fn(prep, u8_out), (parse, cloth, densepose, image))
+        return out[0] if u8_out else out
+
+    # ------------------------------------------------------------------ host entry points
     @torch.no_grad()
     def run_host(self, person_gmm_h, cloth_h, person_tom_h):
         """Host (pinned) tensors in, host (pinned) p_tryon out; the H2D / D2H copies are part of the call.
@@ -92,47 +150,28 @@ class TryOnPipeline:
         is done on the device like base_model.get_and_cat_inputs (util/__init__.py:64-66)."""
         return self._run_staged("batch", tuple(batch_h[k] for k in self.BATCH_KEYS), self._stages_batch)
 
-    def _stages_batch(self, agnostic, cocopose, densepose, cloth):
-        return self._stages(torch.cat([agnostic, cocopose], 1), cloth, torch.cat([agnostic, densepose], 1))
-
-    RAW_KEYS = ("parse", "cloth", "densepose", "image")
-
     @torch.no_grad()
-    def run_host_raw(self, raw_h, prep):
+    def run_host_raw(self, raw_h, prep, u8_out=True):
         """Decoded 8-bit frames in (pinned uint8 host tensors, channel-last: `image`, `cloth`, `densepose` [F,H,W,3],
-        `parse` [F,H,W]), host p_tryon out.  The reference's Dataset.__getitem__ tensor prep (ops.FramePrep, bit-exact)
-        runs on the device, so a frame crosses PCIe as 10 bytes/pixel instead of 112."""
-        if getattr(self, "_raw_prep", None) is not prep:
-            self._raw_prep = prep
-
-            def stages(parse, cloth, densepose, image):
-                b = prep(parse, cloth, densepose, image)
-                return self._stages(torch.cat([b["agnostic"], b["cocopose"]], 1), b["cloth"],
-                                    torch.cat([b["agnostic"], b["densepose"]], 1))
-
-            self._raw_stages = stages
-        self._out_hw = raw_h["parse"].shape[1:3]
-        try:
-            return self._run_staged("raw", tuple(raw_h[k] for k in self.RAW_KEYS), self._raw_stages)
-        finally:
-            self._out_hw = None
+        `parse` [F,H,W]), try-on frames out: pinned uint8 [F,H,W,3] (the bytes the reference's PNG writer receives), or
+        the f32 p_tryon [F,3,H,W] with u8_out=False.  A frame crosses PCIe as 10 bytes/pixel up and 3 down instead of
+        112 and 12."""
+        return self._run_staged("raw_u8" if u8_out else "raw", tuple(raw_h[k] for k in self.RAW_KEYS), self._raw_fn(prep, u8_out))
 
     def _run_staged(self, tag, host_tensors, fn):
         dev = next(self.tom_model.parameters()).device
         cur = torch.cuda.current_stream(dev)
         shapes = tuple((tuple(t.shape), t.dtype) for t in host_tensors)
-        st = self._host_state
+        st = self._host_state.get(tag)
         if st is None or st["shapes"] != shapes:
-            frames = host_tensors[0].shape[0]
-            hw = tuple(self._out_hw) if getattr(self, "_out_hw", None) else tuple(host_tensors[0].shape[2:])
-            st = self._host_state = dict(
+            st = self._host_state[tag] = dict(
                 shapes=shapes, call=0, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev),
                 dev_in=[tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in host_tensors) for _ in range(2)],
                 in_free=[torch.cuda.Event() for _ in range(2)], in_ready=[torch.cuda.Event() for _ in range(2)],
-                out_done=[torch.cuda.Event() for _ in range(2)],
-                host_out=[torch.empty((frames, 3) + hw, dtype=torch.float32).pin_memory() for _ in range(2)])
+                out_done=[torch.cuda.Event() for _ in range(2)], host_out=[None, None])
             for e in st["in_free"] + st["out_done"]:
                 e.record(cur)
+        self._last_state = st
         slot = st["call"] % 2
         st["call"] += 1
         dev_in = st["dev_in"][slot]
@@ -144,23 +183,27 @@ class TryOnPipeline:
         cur.wait_event(st["in_ready"][slot])
         if self.cuda_graph:
             cur.wait_event(st["out_done"][slot])  # this slot's graph owns its output buffer: the last D2H of it must be done
-        p_tryons, _, _ = self._graph_call(tag, fn, dev_in)
+        result = self._graph_call(tag, fn, dev_in)[0]
         st["in_free"][slot].record(cur)
         computed = torch.cuda.Event()
         computed.record(cur)
+        if st["host_out"][slot] is None:
+            st["host_out"][slot] = torch.empty(result.shape, dtype=result.dtype).pin_memory()
         out_h = st["host_out"][slot]
         if not self.cuda_graph:
-            p_tryons.record_stream(st["s_out"])
+            result.record_stream(st["s_out"])
         with torch.cuda.stream(st["s_out"]):
             st["s_out"].wait_event(computed)
-            out_h.copy_(p_tryons, non_blocking=True)
+            out_h.copy_(result, non_blocking=True)
             st["out_done"][slot].record(st["s_out"])
         return out_h, st["out_done"][slot]
 
+    def host_streams(self):
+        """The copy streams of every host entry point used so far (a caller timing on its own stream waits on these)."""
+        return [s for st in self._host_state.values() for s in (st["s_in"], st["s_out"])]
+
     def host_sync(self):
-        """Wait for every outstanding run_host call (copies included)."""
-        st = self._host_state
-        if st is not None:
-            st["s_in"].synchronize()
-            st["s_out"].synchronize()
+        """Wait for every outstanding run_host* call (copies included)."""
+        for s in self.host_streams():
+            s.synchronize()
         torch.cuda.current_stream().synchronize()

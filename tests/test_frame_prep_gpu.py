@@ -86,7 +86,8 @@ def test_raw_frame_entry_point_matches_tensor_entry_point(cuda):
     pipe = TryOnPipeline(warp, tom)
     fr, image, parse, cloth, densepose, pose = _frames([21, 22])
     raw = {"image": image.pin_memory(), "parse": parse.pin_memory(), "cloth": cloth.pin_memory(), "densepose": densepose.pin_memory()}
-    out, done = pipe.run_host_raw(raw, ops.FramePrep(H, W))
+    prep = ops.FramePrep(H, W)
+    out, done = pipe.run_host_raw(raw, prep, u8_out=False)
     done.synchronize()
     got = out.clone()
     want_b = [fp.frame_prep(*f) for f in fr]
@@ -94,4 +95,22 @@ def test_raw_frame_entry_point_matches_tensor_entry_point(cuda):
     out2, done2 = pipe.run_host_batch(batch)
     done2.synchronize()
     assert torch.equal(got, out2)
+    # 8-bit frames out (the default): exactly the reference writer's encoding of that f32 image, from the host entry
+    # point and from the device-resident one, eager and replayed
+    from oracle import image_io
+
+    want_u8 = image_io.image_to_u8(got.numpy())
+    out3, done3 = pipe.run_host_raw(raw, prep)
+    done3.synchronize()
+    assert out3.dtype == torch.uint8 and np.array_equal(out3.numpy(), want_u8)
+    dev_raw = [raw[k].cuda() for k in pipe.RAW_KEYS]
+    assert np.array_equal(pipe.run_raw(*dev_raw, prep).cpu().numpy(), want_u8)
+    graphed = TryOnPipeline(warp, tom, cuda_graph=True)
+    for _ in range(3):
+        assert np.array_equal(graphed.run_raw(*dev_raw, prep).cpu().numpy(), want_u8)
+        o, d = graphed.run_host_raw(raw, prep)
+        d.synchronize()
+        assert np.array_equal(o.numpy(), want_u8)
+    assert graphed.replayed_launches > 0
     pipe.host_sync()
+    graphed.host_sync()
