@@ -274,10 +274,13 @@ int shineon_sagan_attention(const float* qkv, const float* x, const float* gamma
 
 /* FeatureL2Norm x2 + FeatureCorrelation (warp.py:39-67) on f32 NHWC features [B,h*w,C]:
  * out planes [B,h,w,cpad] with channel iA = wA*h + hA (warp.py:60), value = <A/|A|, B/|B|>.
- * corr_f32 (optional) receives the same values as f32 NHWC [B,h,w,h*w]. */
+ * corr_f32 (optional) receives the same values as f32 NHWC [B,h,w,h*w].
+ * normalize = 0: FeatureCorrelation.forward alone (warp.py:53-67) on features the caller normalised already. */
 int shineon_l2norm_correlation(const float* featA, const float* featB, float* corr_f32, void* y_hi,
-                               void* y_lo, int B, int h, int w, int C, int cpad, int plane_fmt,
+                               void* y_lo, int B, int h, int w, int C, int cpad, int plane_fmt, int normalize,
                                shineon_stream_t stream);
+/* FeatureL2Norm.forward (warp.py:43-50) on the reference layout: y = x / sqrt(sum_c x^2 + 1e-6), f32 NCHW [B,C,H,W]. */
+int shineon_feature_l2norm(const float* x, float* y, int B, int C, int H, int W, shineon_stream_t stream);
 
 /* FeatureRegression tail (warp.py:94-99): x f32 NHWC [B,h,w,C] flattened in NCHW order ->
  * Linear(C*h*w -> out_dim) -> tanh.  weight [out_dim, C*h*w], bias [out_dim]; theta [B,out_dim]. */
@@ -322,6 +325,10 @@ int shineon_flownet_warp_concat(const float* x, const float* flow, float* out, i
 /* FlowNetFusion input: out [B,11,H,W] = [x[:,:3] | flow_sd | flow_s2 | |flow_sd| | |flow_s2| | diff_sd | diff_s2]. */
 int shineon_flownet_fusion_concat(const float* x, const float* flow_sd, const float* flow_s2, float* out, int B, int H,
                                   int W, shineon_stream_t stream);
+/* nn.Upsample(size=(Ho,Wo), mode="bilinear") (align_corners=False) times `mul`: FlowNet's pre/post resize for inputs
+ * whose height is not a multiple of 64 (models/flownet.py:46-51,56-58).  x f32 [BC,Hi,Wi] -> y f32 [BC,Ho,Wo]. */
+int shineon_bilinear_resize(const float* x, float* y, int BC, int Hi, int Wi, int Ho, int Wo, float mul,
+                            shineon_stream_t stream);
 /* conf [B,1,H,W] = (sum_c (im1 - Resample2d(im2, flow))^2 < threshold) as 0/1 floats. */
 int shineon_flow_confidence(const float* im1, const float* im2, const float* flow, float* conf, int B, int C, int H,
                             int W, float threshold, shineon_stream_t stream);

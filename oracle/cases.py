@@ -9,8 +9,19 @@ TOM_CASES = {
     "tom_swish_attn3": (dict(self_attn=True, num_attn=3, activation="swish", ngf=64), 1),
     "tom_flow2": (dict(self_attn=True, num_attn=2, activation="gelu", n_frames_total=2, n_frames_now=2,
                        flow_warp=True), 1),                                                  # ngf=int(64*(ln2+1))=108
+    # BASELINE config 3 secondary: channel-stacked 5-frame clip, 4 chained Resample2d blends, odd widths
+    "tom_flow5": (dict(self_attn=True, num_attn=2, activation="gelu", n_frames_total=5, n_frames_now=5,
+                       flow_warp=True), 1),                                                  # ngf=int(64*(ln5+1))=167
 }
-GMM_CASES = {"gmm_b2": dict(batch=2, theta_scale=None), "gmm_stress": dict(batch=2, theta_scale=0.3)}
+GMM_CASES = {"gmm_b2": dict(batch=2, theta_scale=None), "gmm_stress": dict(batch=2, theta_scale=0.3),
+             "gmm_b8": dict(batch=8, theta_scale=None)}                                      # BASELINE configs[1]
+# spatial subsampling step of the stored reference outputs (default 4)
+SUBSAMPLE = {"gmm_b8": 8, "tom_flow5": 4}
+
+# The benchmarked step itself (bench.py: 16 clips x 5 frames through TryOnPipeline): inputs for all 80 frames, reference
+# outputs stored for every PIPELINE_FRAME_STEP-th frame at every PIPELINE_SUB-th pixel.
+PIPELINE_FRAMES, PIPELINE_FRAME_STEP, PIPELINE_SUB = 80, 5, 8
+FLOWNET2_B16 = 16  # BASELINE configs[3] batch
 
 
 def _g(name):
@@ -45,6 +56,23 @@ def gmm_inputs(name, H=256, W=192):
 
 def subsample(t, step=4):
     return t[..., ::step, ::step].contiguous()
+
+
+def sub_step(name):
+    return SUBSAMPLE.get(name, 4)
+
+
+def pipeline_inputs(frames=PIPELINE_FRAMES, H=256, W=192):
+    """(person_gmm [F,22,H,W], cloth [F,3,H,W], person_tom [F,7,H,W]) of the benchmarked step; agnostic (4 channels)
+    is shared by both person tensors like in the reference's batches.  Clothes are smooth images in [-1,1]."""
+    g = _g("pipeline_b80")
+    agnostic = torch.randn(frames, 4, H, W, generator=g)
+    cocopose = torch.randn(frames, 18, H, W, generator=g)
+    densepose = torch.randn(frames, 3, H, W, generator=g)
+    low = torch.rand(frames, 3, H // 8, W // 8, generator=g) * 2 - 1
+    cloth = torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear", align_corners=False)
+    cloth = (cloth + 0.05 * torch.randn(frames, 3, H, W, generator=g)).clamp(-1, 1)
+    return torch.cat([agnostic, cocopose], 1), cloth, torch.cat([agnostic, densepose], 1)
 
 
 def flownet2_inputs(B=1, H=256, W=192):

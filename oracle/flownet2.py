@@ -144,3 +144,19 @@ def flow_confidence(im1, im2, flow):
     """FlowNet.compute_flow_and_conf / norm (models/flownet.py:55,61-62): ||im1 - resample(im2, flow)||^2 < 0.02."""
     d = im1 - fo.resample2d_fwd(im2.contiguous(), flow.contiguous())
     return (torch.sum(d * d, dim=1, keepdim=True) < 0.02).float()
+
+
+def compute_flow_and_conf(sd, im1, im2):
+    """FlowNet.compute_flow_and_conf (models/flownet.py:42-59) including the bilinear pre/post resize taken when the
+    HEIGHT is not a multiple of 64 (`if old_h != new_h`, :47,:56): nn.Upsample(size=..., mode='bilinear')."""
+    old_h, old_w = im1.shape[2], im1.shape[3]
+    new_h, new_w = old_h // 64 * 64, old_w // 64 * 64
+    if old_h != new_h:
+        im1 = F.interpolate(im1, size=(new_h, new_w), mode="bilinear", align_corners=False)
+        im2 = F.interpolate(im2, size=(new_h, new_w), mode="bilinear", align_corners=False)
+    flow = flownet2(sd, torch.cat([im1.unsqueeze(2), im2.unsqueeze(2)], dim=2))
+    conf = flow_confidence(im1, im2, flow)
+    if old_h != new_h:
+        flow = F.interpolate(flow, size=(old_h, old_w), mode="bilinear", align_corners=False) * old_h / new_h
+        conf = F.interpolate(conf, size=(old_h, old_w), mode="bilinear", align_corners=False)
+    return flow, conf

@@ -41,9 +41,10 @@ def main():
             m.load_state_dict(weights.synth_state_dict(shapes, SEED), strict=True)
             person, cloth, flows = cases.tom_inputs(name)
             pr, tm, pt, fm = m.forward(person, cloth, flows)
-            arrs = dict(p_rendereds=cases.subsample(pr), tryon_masks=cases.subsample(tm), p_tryons=cases.subsample(pt))
+            st = cases.sub_step(name)
+            arrs = dict(p_rendereds=cases.subsample(pr, st), tryon_masks=cases.subsample(tm, st), p_tryons=cases.subsample(pt, st))
             if fm is not None:
-                arrs["flow_masks"] = cases.subsample(fm)
+                arrs["flow_masks"] = cases.subsample(fm, st)
             _save(name, shapes, **arrs)
         import torch.nn.functional as F
 
@@ -58,13 +59,43 @@ def main():
                 grid, theta_out = w.gridGen(theta), theta
             warped = F.grid_sample(cloth, grid, padding_mode="border")
             wmask = F.grid_sample(mask, grid, padding_mode="zeros")
-            _save(name, shapes, theta=theta_out, grid=grid[:, ::4, ::4].contiguous(), warped_cloth=cases.subsample(warped),
-                  warped_mask=cases.subsample(wmask))
+            st = cases.sub_step(name)
+            _save(name, shapes, theta=theta_out, grid=grid[:, ::st, ::st].contiguous(), warped_cloth=cases.subsample(warped, st),
+                  warped_mask=cases.subsample(wmask, st))
 
 
-def flownet2_golden():
+def pipeline_golden():
+    """The benchmarked step (bench.py): all 80 frames as ONE batch through the reference's WarpModel.forward ->
+    F.grid_sample(border) -> UnetMaskModel.forward; outputs of every 5th frame at every 8th pixel are stored."""
+    import torch.nn.functional as F
+
+    ref_shim.install()
+    with torch.no_grad():
+        w = ref_shim.build_warp_model()
+        wshapes = weights.shapes_of(w)
+        w.load_state_dict(weights.synth_state_dict(wshapes, SEED), strict=True)
+        m = ref_shim.build_unet_mask_model(**cases.TOM_CASES["tom_gelu_attn"][0])
+        mshapes = weights.shapes_of(m)
+        m.load_state_dict(weights.synth_state_dict(mshapes, SEED), strict=True)
+        pg, cloth, pt = cases.pipeline_inputs()
+        outs = []
+        for s in range(0, pg.shape[0], 16):  # chunks only bound the CPU's memory; every op here is per-sample
+            grid, theta = w.forward(pg[s:s + 16], cloth[s:s + 16])
+            wc = F.grid_sample(cloth[s:s + 16], grid, padding_mode="border")
+            pr, tm, ptry, _ = m.forward(pt[s:s + 16], wc)
+            outs.append((theta, wc, tm, ptry))
+        theta, wc, tm, ptry = (torch.cat(t) for t in zip(*outs))
+        fs, st = cases.PIPELINE_FRAME_STEP, cases.PIPELINE_SUB
+        _save("pipeline_b80", {}, theta=theta, warped_cloth=cases.subsample(wc[::fs], st),
+              tryon_masks=cases.subsample(tm[::fs], st), p_tryons=cases.subsample(ptry[::fs], st))
+
+
+def flownet2_golden(batch=1):
     """FlowNet2 (162.5 M parameters) through the reference module graph; its three CUDA-only ops run through
-    oracle/flow_ops.py (which tests/test_ref_ext_gpu.py pins against the reference's own kernels)."""
+    oracle/flow_ops.py (which tests/test_ref_ext_gpu.py pins against the reference's own kernels).
+    batch=16 is BASELINE configs[3]'s shape (stored at every 4th pixel, without the state_dict shape list)."""
+    ref_shim.install()
+    ref_shim.patch_native_ops_with_oracle()
     from models.flownet2_pytorch import models as fm
     from oracle import flownet2 as ofn
 
@@ -72,10 +103,13 @@ def flownet2_golden():
         net = fm.FlowNet2().eval()
         shapes = weights.shapes_of(net)
         net.load_state_dict(weights.synth_state_dict(shapes, SEED), strict=True)
-        inp = cases.flownet2_inputs()
-        flow = net(inp)
+        inp = cases.flownet2_inputs(batch)
+        flow = torch.cat([net(inp[i:i + 4]) for i in range(0, batch, 4)])  # per-sample network: chunks bound CPU memory
         conf = ofn.flow_confidence(inp[:, :, 0], inp[:, :, 1], flow)  # FlowNet.compute_flow_and_conf (flownet.py:55)
-        _save("flownet2", shapes, flow=cases.subsample(flow, 2), conf=cases.subsample(conf, 2))
+        if batch == 1:
+            _save("flownet2", shapes, flow=cases.subsample(flow, 2), conf=cases.subsample(conf, 2))
+        else:
+            _save(f"flownet2_b{batch}", {}, flow=cases.subsample(flow, 4), conf=cases.subsample(conf, 4))
 
 
 def train_golden():
@@ -102,10 +136,14 @@ def train_golden():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["main", "flownet2", "train"]
+    which = sys.argv[1:] or ["main", "flownet2", "flownet2_b16", "pipeline", "train"]
     if "main" in which:
         main()
     if "flownet2" in which:
         flownet2_golden()
+    if "flownet2_b16" in which:
+        flownet2_golden(cases.FLOWNET2_B16)
+    if "pipeline" in which:
+        pipeline_golden()
     if "train" in which:
         train_golden()

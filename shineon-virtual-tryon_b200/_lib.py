@@ -92,12 +92,14 @@ SIGNATURES = {
     "shineon_instnorm_act": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_f, c_i, c_p],
     "shineon_upsample2x_cat": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     "shineon_sagan_attention": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
-    "shineon_l2norm_correlation": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_l2norm_correlation": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_feature_l2norm": [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "shineon_linear_tanh": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_flownet_normalize": [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p],
     "shineon_upsample4x_flow": [c_p, c_i, c_p, c_i, c_i, c_i, c_f, c_i, c_p],
     "shineon_flownet_warp_concat": [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p],
     "shineon_flownet_fusion_concat": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
+    "shineon_bilinear_resize": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p],
     "shineon_flow_confidence": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_p],
     "shineon_adam_step": [c_p, c_p, c_p, c_p, C.c_long, c_f, c_f, c_f, c_f, c_f, c_i, c_f, c_p],
     "shineon_conv2d_wgrad_workspace_bytes": [C.POINTER(Conv2dWgradParams)],

@@ -168,6 +168,28 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- nn.Upsample(size=(Ho, Wo), mode="bilinear") (align_corners=False), models/flownet.py:47-51,56-58:
+// ATen upsample_bilinear2d: scale = in / out (float), src = max(scale * (dst + 0.5) - 0.5, 0), i1 = i0 + (i0 < in - 1),
+// value = l0y * (l0x * p00 + l1x * p01) + l1y * (l0x * p10 + l1x * p11), times `mul` (the flow rescale old_h / new_h).
+__global__ void __launch_bounds__(256)
+    bilinear_resize_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi, int Wi, int Ho, int Wo, float sy,
+                           float sx, float mul, long total) {
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(e % Wo), oy = (int)((e / Wo) % Ho);
+    const long bc = e / ((long)Wo * Ho);
+    float fy = __fsub_rn(__fmul_rn(sy, (float)oy + 0.5f), 0.5f), fx = __fsub_rn(__fmul_rn(sx, (float)ox + 0.5f), 0.5f);
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < Hi - 1 ? 1 : 0), x1 = x0 + (x0 < Wi - 1 ? 1 : 0);
+    const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float* p = x + bc * Hi * Wi;
+    const float v = ly0 * (lx0 * __ldg(p + (long)y0 * Wi + x0) + lx1 * __ldg(p + (long)y0 * Wi + x1)) +
+                    ly1 * (lx0 * __ldg(p + (long)y1 * Wi + x0) + lx1 * __ldg(p + (long)y1 * Wi + x1));
+    y[e] = v * mul;
+  }
+}
+
 static inline int blocks_for(long total) {
   long b = (total + 255) / 256;
   return (int)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
@@ -224,4 +246,14 @@ extern "C" int shineon_flow_confidence(const float* im1, const float* im2, const
   SHINEON_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "flow_confidence: bad shape");
   flow_confidence_kernel<<<dim3(blocks_for((long)H * W), B), 256, 0, (cudaStream_t)stream>>>(im1, im2, flow, conf, C, H, W, threshold);
   return after_launch("flow_confidence_kernel");
+}
+
+extern "C" int shineon_bilinear_resize(const float* x, float* y, int BC, int Hi, int Wi, int Ho, int Wo, float mul,
+                                       shineon_stream_t stream) {
+  SHINEON_REQUIRE(x && y, "bilinear_resize: null pointer");
+  SHINEON_REQUIRE(BC > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bilinear_resize: bad shape");
+  const long total = (long)BC * Ho * Wo;
+  bilinear_resize_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(x, y, Hi, Wi, Ho, Wo, (float)Hi / (float)Ho,
+                                                                            (float)Wi / (float)Wo, mul, total);
+  return after_launch("bilinear_resize_kernel");
 }

@@ -14,7 +14,8 @@ constexpr int kTK = 32;
 // squared norms).  The first version (4 x 2 per thread, scalar shared loads) ran at 17 TFLOP/s, shared-memory bound.
 __global__ void __launch_bounds__(128)
     l2norm_corr_kernel(const float* __restrict__ fA, const float* __restrict__ fB, float* __restrict__ corr,
-                       plane_t* __restrict__ yh, plane_t* __restrict__ yl, int h, int w, int C, int cpad, int fmt) {
+                       plane_t* __restrict__ yh, plane_t* __restrict__ yl, int h, int w, int C, int cpad, int fmt,
+                       int normalize) {
   __shared__ __align__(16) float sA[kTK][kTA + 4];
   __shared__ __align__(16) float sB[kTK][kTB + 4];
   const int P = h * w;
@@ -62,12 +63,12 @@ __global__ void __launch_bounds__(128)
   for (int j = 0; j < 4; ++j) {
     const int pB = b0 + ty * 4 + j;
     if (pB >= P) continue;
-    const float inb = 1.f / sqrtf(nb[j] + 1e-6f);  // warp.py:44-49
+    const float inb = normalize ? 1.f / sqrtf(nb[j] + 1e-6f) : 1.f;  // warp.py:44-49
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int pA = a0 + (i < 4 ? tx * 4 + i : 32 + tx * 4 + (i - 4));
       if (pA >= P) continue;
-      const float ina = 1.f / sqrtf(na[i] + 1e-6f);
+      const float ina = normalize ? 1.f / sqrtf(na[i] + 1e-6f) : 1.f;
       const float v = acc[j][i] * ina * inb;
       const int hA = pA / w, wA = pA - hA * w;
       const int iA = wA * h + hA;  // feature_A.transpose(2,3) (warp.py:60)
@@ -81,6 +82,24 @@ __global__ void __launch_bounds__(128)
       }
     }
   }
+}
+
+// FeatureL2Norm.forward on the reference layout (warp.py:43-50): y[b,c,p] = x[b,c,p] / sqrt(sum_c x[b,c,p]^2 + 1e-6).
+// One thread per pixel, channel planes read coalesced across the warp.
+__global__ void __launch_bounds__(128)
+    feature_l2norm_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW) {
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  if (p >= HW) return;
+  const float* xb = x + (long)b * C * HW + p;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = __ldg(xb + (long)c * HW);
+    s = fmaf(v, v, s);
+  }
+  const float inv = 1.f / sqrtf(s + 1e-6f);
+  float* yb = y + (long)b * C * HW + p;
+  for (int c = 0; c < C; ++c) yb[(long)c * HW] = __ldg(xb + (long)c * HW) * inv;
 }
 
 // theta[b, o] = tanh(bias[o] + sum_{c,y,x} W[o, c*h*w + y*w + x] * x_nhwc[b, y, x, c]); one warp per output.
@@ -109,7 +128,7 @@ using namespace shineon;
 
 extern "C" int shineon_l2norm_correlation(const float* featA, const float* featB, float* corr_f32, void* y_hi,
                                           void* y_lo, int B, int h, int w, int C, int cpad, int plane_fmt,
-                                          shineon_stream_t stream) {
+                                          int normalize, shineon_stream_t stream) {
   SHINEON_REQUIRE(plane_fmt == SHINEON_FMT_BF16 || plane_fmt == SHINEON_FMT_FP16, "l2norm_correlation: plane_fmt %d", plane_fmt);
   SHINEON_REQUIRE(featA && featB && (corr_f32 || y_hi), "l2norm_correlation: null pointer");
   SHINEON_REQUIRE(B > 0 && B <= 65535 && h > 0 && w > 0 && C > 0 && C % 4 == 0, "l2norm_correlation: bad shape (C %% 4)");
@@ -117,8 +136,15 @@ extern "C" int shineon_l2norm_correlation(const float* featA, const float* featB
   const int P = h * w;
   dim3 grid(cdiv(P, kTA), cdiv(P, kTB), B);
   l2norm_corr_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(featA, featB, corr_f32, (plane_t*)y_hi,
-                                                           (plane_t*)y_lo, h, w, C, cpad, plane_fmt);
+                                                           (plane_t*)y_lo, h, w, C, cpad, plane_fmt, normalize);
   return after_launch("l2norm_corr_kernel");
+}
+
+extern "C" int shineon_feature_l2norm(const float* x, float* y, int B, int C, int H, int W, shineon_stream_t stream) {
+  SHINEON_REQUIRE(x && y, "feature_l2norm: null pointer");
+  SHINEON_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "feature_l2norm: bad shape");
+  feature_l2norm_kernel<<<dim3(cdiv(H * W, 128), B), 128, 0, (cudaStream_t)stream>>>(x, y, C, H * W);
+  return after_launch("feature_l2norm_kernel");
 }
 
 extern "C" int shineon_linear_tanh(const float* x, const float* weight, const float* bias, float* theta, int B, int h,

@@ -61,11 +61,22 @@ class FlowNet(nn.Module):
         assert im1.size() == im2.size()
         old_h, old_w = im1.size()[2], im1.size()[3]
         new_h, new_w = old_h // 64 * 64, old_w // 64 * 64
-        if old_h != new_h or old_w != new_w:
-            raise NotImplementedError(
-                "inputs whose sides are not multiples of 64 need the reference's bilinear pre/post resize "
-                "(flownet.py:46-51,56-58); the 256x192 try-on path never takes that branch")
+        resized = old_h != new_h  # as written in the reference: only the height decides (flownet.py:47)
+        if resized:
+            if new_h == 0 or new_w == 0:
+                raise ValueError(f"FlowNet needs inputs of at least 64x64, got {old_h}x{old_w}")
+            im1 = ops.bilinear_resize(im1.contiguous(), (new_h, new_w))
+            im2 = ops.bilinear_resize(im2.contiguous(), (new_h, new_w))
+        elif old_w != new_w:
+            raise ValueError(
+                f"FlowNet: width {old_w} is not a multiple of 64 while the height is; the reference does not resize in "
+                "that case either (flownet.py:47 tests old_h only) and its FlowNet2 then fails on mismatched pyramid levels")
         data1 = torch.stack([im1, im2], dim=2).contiguous()  # [B,3,2,H,W]
         flow1 = self.flowNet(data1)
         conf = ops.flow_confidence(im1.contiguous(), im2.contiguous(), flow1, 0.02)
+        if resized:
+            # flownet.py:56-58: `upsample(flow1) * old_h / new_h` (both flow components scaled by the height ratio)
+            flow1 = ops.bilinear_resize(flow1.contiguous(), (old_h, old_w), mul=1.0)
+            flow1 = flow1 * old_h / new_h
+            conf = ops.bilinear_resize(conf.contiguous(), (old_h, old_w))
         return flow1.detach(), conf.detach()

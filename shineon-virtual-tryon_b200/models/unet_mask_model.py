@@ -102,6 +102,8 @@ class UnetMaskModel(BaseModel):
         optimiser step; `accumulated_batches` micro-batches simply call this repeatedly).  Returns
         {"loss": 0-dim tensor, "log": {name: tensor}} with the reference's log names."""
         hp = self.hparams
+        if not val:
+            self.criterionVGG.warn_if_random()
         batch = maybe_combine_frames_and_channels(hp, batch)
         n = hp.n_frames_total
         flow_warp = bool(hp.flow_warp)

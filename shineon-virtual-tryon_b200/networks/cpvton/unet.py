@@ -278,10 +278,10 @@ class UnetSkipConnectionBlock(nn.Module):
             return attn.run(y, p, want_f32=True, want_planes=False)[0]
         return attn.run(y, p, act=act, act_param=act_param, want_f32=False, want_planes=True, out_planes=out_planes)[1]
 
-    def run(self, a_in, prec, train=False, out=None):
+    def run(self, a_in, prec, train=False, out=None, raw_out=False):
         """a_in: Planes holding this block's (already down-activated) input; for the outermost block a tuple
         (x0, x1|None) of f32 NCHW tensors (torch.cat([x0, x1], 1) is fused into the layout conversion).
-        Outermost: returns f32 NHWC output.  Otherwise returns Planes of up_act(x') for the parent."""
+        Outermost (or raw_out): returns the f32 NHWC output x'.  Otherwise returns Planes of up_act(x') for the parent."""
         pr = self._parts
         if self.training and pr["dropout"]:
             raise NotImplementedError("Dropout in training mode is not implemented in the native U-Net engine")
@@ -316,7 +316,7 @@ class UnetSkipConnectionBlock(nn.Module):
                                      out_planes=cat.window(0, c_skip))
                 sub.run(a_mid, prec, out=cat.window(p_skip, c_xp))
             f32 = low(cat)
-            if self.outermost:
+            if self.outermost or raw_out:
                 return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], None, 0.0, prec, want_final_f32=True)
             return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], up_act, up_par, prec, out_planes=out)
         a_mid = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, prec)
@@ -335,7 +335,7 @@ class UnetSkipConnectionBlock(nn.Module):
             f32 = pk["up_tap"](u)
         else:
             f32, _ = ops.conv2d(u, pk["up"], scale=sc, shift=sh, want_f32=True)
-        if self.outermost:
+        if self.outermost or raw_out:
             return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], None, 0.0, prec, want_final_f32=True)
         return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], up_act, up_par, prec, out_planes=out)
 
@@ -416,10 +416,27 @@ class UnetSkipConnectionBlock(nn.Module):
         g_in, _ = pk["down_dgrad"](G, want_f32=True)
         return g_in
 
+    precision = None  # ops.PRECISIONS name for a block used on its own (UnetGenerator passes its own)
+
     def forward(self, x):
-        raise NotImplementedError(
-            "UnetSkipConnectionBlock is driven by UnetGenerator.forward in the B200 build (activations stay in "
-            "NHWC planes between blocks); call the generator instead")
+        """unet.py:188-198 for a block used on its own (inference): outermost -> model(x); otherwise
+        torch.cat([x, model(x)], 1).  x: f32 NCHW CUDA.  With the default activation the reference's in-place
+        LeakyReLU(0.2, True) (unet.py:132) also rewrites the caller's x, so the skip half holds leaky(x): reproduced."""
+        require_cuda(self, "UnetSkipConnectionBlock")
+        if self.training and self._parts["dropout"]:
+            raise NotImplementedError("Dropout in training mode is not implemented in the native U-Net engine")
+        prec = ops.resolve_precision(self.precision)
+        x = x.contiguous()
+        if self.outermost:
+            return self.run((x, None), prec).permute(0, 3, 1, 2).contiguous()
+        act, par = act_name(self._parts["down_act"])
+        a_in = ops.nchw_to_planes(x, act=act, act_param=par, prec=prec)
+        xp = self.run(a_in, prec, raw_out=True).permute(0, 3, 1, 2)
+        if self._parts["default_act"]:
+            flat, _ = ops.instnorm_act(x.view(1, 1, -1, 8) if x.numel() % 8 == 0 else x.view(1, 1, -1, 1), do_norm=False,
+                                       act=act, act_param=par, want_f32=True, want_planes=False)
+            x.copy_(flat.view_as(x))  # the in-place side effect on the caller's tensor
+        return torch.cat([x, xp], 1)
 
 
 def _get_activation_fn(activation):

@@ -83,13 +83,11 @@ class FeatureExtraction(nn.Module):
 
 
 class FeatureL2Norm(nn.Module):
-    """x / sqrt(sum_c x^2 + 1e-6) (warp.py:39-50).  In WarpModel it is fused into the correlation kernel;
-    standalone it runs that kernel's normalisation through a 1-pixel correlation-free path."""
+    """x / sqrt(sum_c x^2 + 1e-6) (warp.py:39-50).  WarpModel fuses it into the correlation kernel
+    (FeatureCorrelation.forward_fused); standalone it is one small kernel on the reference layout."""
 
     def forward(self, feature):
-        raise NotImplementedError(
-            "FeatureL2Norm is fused into shineon_l2norm_correlation in the B200 build; use "
-            "FeatureCorrelation.forward_fused(featureA, featureB) on the un-normalised features")
+        return ops.feature_l2norm(feature.contiguous())
 
 
 class FeatureCorrelation(nn.Module):
@@ -98,9 +96,12 @@ class FeatureCorrelation(nn.Module):
         return ops.l2norm_correlation(fa_nhwc, fb_nhwc, want_f32=want_f32, want_planes=True, prec=prec)
 
     def forward(self, feature_A, feature_B):
-        raise NotImplementedError(
-            "FeatureCorrelation on pre-normalised NCHW features is not a separate kernel in the B200 build; "
-            "WarpModel.forward uses forward_fused (L2-norm + correlation in one kernel)")
+        """warp.py:53-67 on (already normalised) NCHW features: [B,C,h,w] x2 -> [B,h*w,h,w],
+        out[b, wA*h + hA, hB, wB] = sum_c A[b,c,hA,wA] * B[b,c,hB,wB]."""
+        fa = feature_A.permute(0, 2, 3, 1).contiguous()
+        fb = feature_B.permute(0, 2, 3, 1).contiguous()
+        corr, _ = ops.l2norm_correlation(fa, fb, want_f32=True, want_planes=False, normalize=False)
+        return corr.permute(0, 3, 1, 2).contiguous()
 
 
 class FeatureRegression(nn.Module):

@@ -116,6 +116,47 @@ class VGGLoss(nn.Module):
         self.weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
         self.layids = layids
         self.precision = None
+        # The reference builds torchvision.models.vgg19(pretrained=True) (vgg.py:9).  There is no network here, so the
+        # slices keep a random initialisation until ImageNet weights arrive through load_pretrained() / a checkpoint
+        # that contains criterionVGG.* keys; training on random features is allowed but never silent.
+        self.pretrained_loaded = False
+        self._warned = False
+        self.register_load_state_dict_post_hook(
+            lambda module, incompatible: setattr(module, "pretrained_loaded",
+                                                 not any("vgg.slice" in k for k in incompatible.missing_keys)))
+
+    def load_pretrained(self, path=None):
+        """ImageNet weights for the five slices: `path` = a torchvision vgg19 state_dict file (`features.N.weight` keys,
+        e.g. vgg19-dcbff6f7.pth); path=None asks torchvision for its cached download.  Returns True when loaded."""
+        if path is None:
+            try:
+                import torchvision
+
+                sd = torchvision.models.vgg19(weights=torchvision.models.VGG19_Weights.IMAGENET1K_V1).state_dict()
+            except Exception:  # noqa: BLE001  (no cache / no network)
+                return False
+        else:
+            sd = torch.load(path, map_location="cpu")
+            sd = sd.get("state_dict", sd)
+        own = self.vgg.state_dict()
+        mapped = {}
+        for k in own:  # "slice3.10.weight" <- "features.10.weight"
+            src = "features." + k.split(".", 1)[1]
+            if src not in sd:
+                raise KeyError(f"{src} missing from the VGG19 weights file")
+            mapped[k] = sd[src]
+        self.vgg.load_state_dict(mapped, strict=True)
+        self.pretrained_loaded = True
+        return True
+
+    def warn_if_random(self):
+        if not self.pretrained_loaded and not self._warned:
+            import warnings
+
+            warnings.warn("VGGLoss: the VGG19 slices hold RANDOM weights (the reference uses torchvision's ImageNet weights, "
+                          "models/networks/vgg.py:9); the perceptual term is then a random-feature loss.  Pass --vgg_weights "
+                          "FILE (torchvision vgg19 state_dict) or load a checkpoint that contains criterionVGG.*", stacklevel=3)
+            self._warned = True
 
     def loss_and_grad(self, x, y, loss, grad_x, scale=1.0):
         """loss[0] += scale * VGGLoss(x, y); grad_x (f32 NCHW [B,3,H,W], None = value only) += scale * dVGGLoss/dx.

@@ -611,7 +611,16 @@ def sagan_attention(qkv, x, gamma, Cq, *, act=None, act_param=0.0, want_f32=Fals
     return out_f32, out_planes
 
 
-def l2norm_correlation(featA, featB, *, want_f32=False, want_planes=True, prec=None):
+def feature_l2norm(x):
+    """FeatureL2Norm.forward (warp.py:43-50): f32 NCHW -> x / sqrt(sum_c x^2 + 1e-6)."""
+    x = _req(x, name="feature")
+    B, Cc, H, W = x.shape
+    y = torch.empty_like(x)
+    check(_lib.load().shineon_feature_l2norm(_p(x), _p(y), B, Cc, H, W, _stream()), "shineon_feature_l2norm")
+    return y
+
+
+def l2norm_correlation(featA, featB, *, want_f32=False, want_planes=True, prec=None, normalize=True):
     """featA/B: f32 NHWC [B,h,w,C] -> correlation [B,h,w,h*w] (channel = wA*h+hA)."""
     featA, featB = _req(featA), _req(featB)
     B, h, w, Cc = featA.shape
@@ -619,7 +628,8 @@ def l2norm_correlation(featA, featB, *, want_f32=False, want_planes=True, prec=N
     planes = Planes(B, h, w, h * w, prec=prec, device=featA.device) if want_planes else None
     check(_lib.load().shineon_l2norm_correlation(_p(featA), _p(featB), _p(corr), _p(planes.hi if planes else None),
                                                  _p(planes.lo if planes else None), B, h, w, Cc,
-                                                 planes.cpad if planes else h * w, planes.fmt if planes else 0, _stream()),
+                                                 planes.cpad if planes else h * w, planes.fmt if planes else 0,
+                                                 int(bool(normalize)), _stream()),
           "shineon_l2norm_correlation")
     return corr, planes
 
@@ -697,6 +707,17 @@ def flownet_fusion_concat(x, flow_sd, flow_s2):
     check(_lib.load().shineon_flownet_fusion_concat(_p(x), _p(flow_sd), _p(flow_s2), _p(out), B, H, W, _stream()),
           "shineon_flownet_fusion_concat")
     return out
+
+
+def bilinear_resize(x, size, mul=1.0):
+    """nn.Upsample(size=size, mode="bilinear") (align_corners=False) of an f32 NCHW tensor, times `mul`."""
+    x = _req(x, name="x")
+    B, Cc, Hi, Wi = x.shape
+    Ho, Wo = size
+    y = torch.empty(B, Cc, Ho, Wo, dtype=torch.float32, device=x.device)
+    check(_lib.load().shineon_bilinear_resize(_p(x), _p(y), B * Cc, Hi, Wi, Ho, Wo, float(mul), _stream()),
+          "shineon_bilinear_resize")
+    return y
 
 
 def flow_confidence(im1, im2, flow, threshold=0.02):

@@ -17,6 +17,10 @@ class TrainOptions(BaseOptions):
                             help="numeric mode of the native training step: bf16 = single bf16 tensor-core products with "
                                  "fp32 accumulation / statistics / master weights (the reference's default is AMP fp16); "
                                  "bf16x3 = fp32-grade split products (the parity-tested mode)")
+        parser.add_argument("--vgg_weights", default=None,
+                            help="torchvision vgg19 state_dict file for the perceptual loss (the reference downloads the "
+                                 "ImageNet weights, models/networks/vgg.py:9; without them the VGG slices are random and "
+                                 "training warns)")
         parser.add_argument("--max_steps", type=int, default=None, help="stop after this many optimiser steps")
         self.is_train = True
         return parser

@@ -82,7 +82,9 @@ class TryOnPipeline:
 
         if not self.cuda_graph or ops.PROFILE is not None:
             return fn(*args)
-        key = (tag, id(fn), self._weights_signature()) + tuple((a.data_ptr(), tuple(a.shape), a.dtype) for a in args)
+        # bound methods are created anew on every attribute access: key them on the underlying function, closures on id
+        fn_id = id(getattr(fn, "__func__", fn))
+        key = (tag, fn_id, self._weights_signature()) + tuple((a.data_ptr(), tuple(a.shape), a.dtype) for a in args)
         ent = self._graphs.get(key)
         if ent is None:
             while len(self._graphs) >= self.MAX_GRAPHS:

@@ -38,8 +38,18 @@ class Trainer:
         is copied into static buffers.  The gradient all-reduce then runs after the replay instead of inside the
         backward (bucketed, asynchronous, but not overlapped)."""
         self.cuda_graph, self.graph_warmup = bool(cuda_graph), int(graph_warmup)
-        self._graph, self._static_batch, self._static_res = None, None, None
+        # two captured variants: [True] the first micro-batch after an optimiser step (the 16-bit weight re-pack is part of
+        # the captured work) and [False] the following micro-batches of an accumulation window (weights unchanged: they
+        # read the buffers the [True] graph re-packs into)
+        self._graphs, self._static_batch = {}, None
         self.model = model
+        if self.cuda_graph:
+            from . import _lib
+
+            fmt, _ = ops.resolve_precision(model.unet.precision if model.unet.precision is not None else "bf16x3")
+            if fmt == _lib.FMT_FP16:
+                raise NotImplementedError("Trainer(cuda_graph=True) needs a bf16 plane format: the fp16 modes derive a "
+                                          "power-of-two weight scale on the host at every re-pack, which a graph would freeze")
         ordered = [p for p in backward_order(model.unet) if p.requires_grad]
         seen = {id(p) for p in ordered}
         rest = [p for p in model.parameters() if p.requires_grad and id(p) not in seen]
@@ -64,6 +74,11 @@ class Trainer:
         self.micro, self.steps, self.epoch = 0, 0, 0
         _engine_util.bump_weights_epoch()
 
+    def named_params(self, model=None):
+        """(name, parameter) in flat-buffer order (checkpoints store the Adam moments in this order)."""
+        names = {id(p): n for n, p in (model or self.model).named_parameters()}
+        return [(names.get(id(p), f"param{i}"), p) for i, p in enumerate(self.params)]
+
     def zero_grad(self):
         self.reducer.flat.zero_()
 
@@ -71,8 +86,11 @@ class Trainer:
         """One micro-batch: forward + losses + backward (gradients accumulate); on every `accumulated_batches`-th call
         the gradient all-reduce (overlapped with that backward) and the fused Adam step.  Returns the step's result."""
         last = (self.micro + 1) % self.accumulated_batches == 0
-        if self.cuda_graph and self.micro >= self.graph_warmup:
-            res = self._replay(batch, batch_idx)
+        first = self.micro % self.accumulated_batches == 0  # weights changed since the previous micro-batch
+        # the first capture must be of a `first` micro-batch, so the packed-weight buffers every later graph reads are
+        # the ones that graph rewrites on each replay
+        if self.cuda_graph and self.micro >= self.graph_warmup and (first or True in self._graphs):
+            res = self._replay(batch, batch_idx, first)
             self.micro += 1
             if last:
                 self.reducer.start()
@@ -94,19 +112,32 @@ class Trainer:
             self.zero_grad()
         return res
 
-    def _replay(self, batch, batch_idx):
+    def _replay(self, batch, batch_idx, first):
         tensors = {k: v for k, v in batch.items() if isinstance(v, torch.Tensor)}
-        if self._graph is None:
+        if self._static_batch is None:
             self._static_batch = {k: v.clone() for k, v in tensors.items()}
-            self._graph = torch.cuda.CUDAGraph()
+        ent = self._graphs.get(first)
+        if ent is None:
+            from . import _lib
+
+            graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            with torch.cuda.graph(self._graph):
-                self._static_res = self.model.training_step(self._static_batch, batch_idx)
-            # the capture only recorded the work: replay below runs it for this batch
+            epoch0 = _engine_util.WEIGHTS_EPOCH[0]
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):  # the NCCL watchdog thread may poll events
+                res = self.model.training_step(self._static_batch, batch_idx)
+            ent = self._graphs[first] = (graph, res, _lib.launch_count() - n0)
+            assert _engine_util.WEIGHTS_EPOCH[0] == epoch0
+            if first:
+                # the re-pack of every trainable layer must have been recorded: compare with the no-repack variant later
+                self.repack_launches = ent[2]
+            elif True in self._graphs:
+                assert ent[2] < self._graphs[True][2], "the weight re-pack was not captured in the post-step graph"
+            # the capture only recorded the work: the replay below runs it for this batch
         for k, v in tensors.items():
             self._static_batch[k].copy_(v, non_blocking=True)
-        self._graph.replay()
-        return self._static_res
+        ent[0].replay()
+        return ent[1]
 
     def optimizer_step(self, grad_scale=1.0):
         self.steps += 1

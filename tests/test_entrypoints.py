@@ -31,16 +31,42 @@ def test_train_entry_point_rejects_models_without_native_training():
     assert "U-Net try-on stage" in str(e.value)
 
 
-@pytest.mark.gpu
-def test_train_entry_point_runs_on_synthetic_data(cuda, tmp_path):
+def test_train_entry_point_refuses_datasets_it_does_not_have():
+    """--dataset vvt must not silently train on synthetic noise."""
     sys.path.insert(0, ROOT)
     import train
 
-    rc = train.main(["--model", "unet", "--name", "smoke", "--self_attn", "--activation", "gelu", "-b", "2",
-                     "--synthetic_samples", "4", "--accumulated_batches", "2", "--max_steps", "2",
-                     "--experiments_dir", str(tmp_path)])
+    with pytest.raises(SystemExit) as e:
+        train.main(["--model", "unet", "--name", "x", "--dataset", "vvt"])
+    assert "--dataset vvt" in str(e.value) and "synthetic" in str(e.value)
+
+
+@pytest.mark.gpu
+def test_train_entry_point_runs_on_synthetic_data(cuda, tmp_path):
+    sys.path.insert(0, ROOT)
+    import warnings
+
+    import torch
+    import train
+
+    args = ["--model", "unet", "--name", "smoke", "--self_attn", "--activation", "gelu", "-b", "2", "--synthetic_samples", "4",
+            "--accumulated_batches", "2", "--experiments_dir", str(tmp_path), "--save_count", "1"]
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        rc = train.main(args + ["--max_steps", "2"])
     assert rc == 0
-    assert os.path.exists(os.path.join(str(tmp_path), "smoke", "final.ckpt"))
+    assert any("RANDOM weights" in str(x.message) for x in w), "training on a random VGG19 must warn"
+    ck = torch.load(os.path.join(str(tmp_path), "smoke", "final.ckpt"), map_location="cpu")
+    # Lightning-readable (state_dict + hyper_parameters + global_step) and resumable (Adam moments, step, epoch)
+    assert {"state_dict", "hyper_parameters", "global_step", "epoch", "b200_optimizer"} <= set(ck)
+    assert ck["global_step"] == 2 and ck["hyper_parameters"]["activation"] == "gelu"
+    assert ck["b200_optimizer"]["exp_avg_sq"].abs().sum() > 0
+    assert os.path.exists(os.path.join(str(tmp_path), "smoke", "step_0000001.ckpt"))  # --save_count
+    # resume: the optimiser continues at step 2 (bias correction / schedule), not from scratch
+    rc = train.main(args + ["--max_steps", "3", "--checkpoint", os.path.join(str(tmp_path), "smoke", "final.ckpt")])
+    assert rc == 0
+    ck2 = torch.load(os.path.join(str(tmp_path), "smoke", "final.ckpt"), map_location="cpu")
+    assert ck2["global_step"] == 3
 
 
 @pytest.mark.gpu

@@ -58,6 +58,45 @@ def test_training_step_matches_oracle_and_golden(cuda, name):
             assert p.grad is None
 
 
+def test_training_step_bf16_mode_is_pinned(cuda):
+    """The numeric mode `bench.py --workload train` runs by default: single bf16 tensor-core products (fp32 accumulation,
+    statistics, master weights) — the B200 counterpart of the reference's AMP recipe (train.py: Trainer(precision=16)).
+    Pinned against the reference-generated golden / fp32 oracle with mixed-precision tolerances written here:
+    loss terms within 2e-2 relative; every parameter gradient's direction (cosine over the stored sample) >= 0.98 and
+    its norm within 10 %; parameters whose true gradient is round-off (|g| < 1e-5 of the model's largest) are skipped."""
+    name = "train_gelu_attn"
+    over = cases.TRAIN_CASES[name][0]
+    model, sd = build_model("unet_mask", **over)
+    model.train()
+    model.set_train_precision("bf16")
+    batch = cases.train_batch(name)
+    res = model.training_step(_to_cuda(batch), 0)
+    torch.cuda.synchronize()
+    seed, shapes, gold = load_golden(name)
+    assert abs(res["loss"].item() - gold["loss"].item()) <= 2e-2 * abs(gold["loss"].item()), (res["loss"].item(), gold["loss"].item())
+    for k in ("l1", "vgg", "tryon_mask_l1"):
+        got, want = res["log"]["loss/G/" + k].item(), gold["log:loss/G/" + k].item() if ("log:loss/G/" + k) in gold else None
+        if want is not None:
+            assert abs(got - want) <= 2e-2 * abs(want) + 1e-4, (k, got, want)
+    named = dict(model.named_parameters())
+    gmax = max(v.abs().max().item() for k, v in gold.items() if k.startswith("gsamp:"))
+    worst_cos, worst_norm = 1.0, 0.0
+    for k, p in named.items():
+        if k.startswith("criterionVGG") or ("gsamp:" + k) not in gold:
+            continue
+        want = gold["gsamp:" + k]
+        if want.abs().max().item() < 1e-5 * gmax:
+            continue
+        got = cases.grad_sample(p.grad.detach().float().cpu())
+        cos = torch.nn.functional.cosine_similarity(got, want, dim=0).item()
+        nrm = abs(p.grad.norm().item() - gold["gnorm:" + k].item()) / gold["gnorm:" + k].item()
+        worst_cos, worst_norm = min(worst_cos, cos), max(worst_norm, nrm)
+        assert cos >= 0.98, f"{k}: gradient direction cos {cos:.4f}"
+        assert nrm <= 0.10, f"{k}: gradient norm off by {nrm:.3f}"
+    print(f"bf16 training mode: loss {res['loss'].item():.5f} vs reference {gold['loss'].item():.5f}; worst gradient cosine "
+          f"{worst_cos:.4f}, worst norm error {worst_norm:.3f}")
+
+
 def test_training_reduces_the_loss(cuda):
     """A few fused-Adam steps through training.Trainer (flat parameter / gradient buffers, weight re-pack per step)."""
     from shineon_virtual_tryon_b200.training import Trainer
@@ -70,8 +109,55 @@ def test_training_reduces_the_loss(cuda):
     losses = [tr.train_batch(batch, i)["loss"].item() for i in range(6)]
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < losses[0], losses
-    # gradient accumulation: two half-weighted micro-batches == one step on the same data
     assert tr.steps == 6
+
+
+def test_gradient_accumulation_equals_the_combined_batch(cuda):
+    """accumulated_batches = 2: the gradients two micro-batches accumulate, scaled by 1/2 (what Trainer hands to Adam),
+    equal the gradients of one step on the two micro-batches concatenated (all losses are batch means, the U-Net's
+    InstanceNorm has no cross-sample statistics)."""
+    name = "train_gelu_attn"
+    over = cases.TRAIN_CASES[name][0]
+    batch = _to_cuda(cases.train_batch(name))  # B = 2
+    halves = [{k: v[i:i + 1].contiguous() for k, v in batch.items()} for i in range(2)]
+    model, _ = build_model("unet_mask", **over)
+    model.train()
+    l_acc = [model.training_step(h, i)["loss"].item() for i, h in enumerate(halves)]
+    g_acc = {k: p.grad.detach().clone() * 0.5 for k, p in model.named_parameters() if p.grad is not None}
+    model2, _ = build_model("unet_mask", **over)
+    model2.train()
+    l_comb = model2.training_step(batch, 0)["loss"].item()
+    assert abs(0.5 * sum(l_acc) - l_comb) <= 1e-4 * abs(l_comb) + 1e-5
+    gmax = max(g.abs().max().item() for g in g_acc.values())
+    for k, p in model2.named_parameters():
+        if p.grad is None:
+            continue
+        err = (p.grad - g_acc[k]).abs().max().item()
+        assert err <= 2e-3 * g_acc[k].abs().max().item() + 1e-5 * gmax, (k, err)
+
+
+def test_cuda_graph_training_with_accumulation_tracks_the_weights(cuda):
+    """Trainer(cuda_graph=True, accumulated_batches=2): the captured graphs must re-pack the 16-bit weight copies after
+    every optimiser step (a capture taken mid-window recorded no re-pack and replayed frozen weights).
+    Graph and eager runs of the same schedule give the same loss curve, and the loss goes down."""
+    from shineon_virtual_tryon_b200.training import Trainer
+
+    name = "train_gelu_attn"
+    batch = _to_cuda(cases.train_batch(name))
+    runs = []
+    for graph in (False, True):
+        model, _ = build_model("unet_mask", **cases.TRAIN_CASES[name][0])
+        model.train()
+        tr = Trainer(model, lr=2e-4, cuda_graph=graph, graph_warmup=1, accumulated_batches=2)
+        runs.append([tr.train_batch(batch, i)["loss"].item() for i in range(10)])
+        assert tr.steps == 5
+        if graph:
+            assert set(tr._graphs) == {True, False} and tr._graphs[True][2] > tr._graphs[False][2]
+    for a, b in zip(*runs):
+        assert abs(a - b) <= 1e-4 * abs(a) + 1e-5, runs
+    assert runs[1][-1] < runs[1][0]
+    # inside a window the two micro-batches see the same weights, across windows they do not
+    assert abs(runs[1][0] - runs[1][1]) <= 1e-6 and abs(runs[1][1] - runs[1][2]) > 1e-6
 
 
 def test_cuda_graph_training_matches_eager(cuda):
