@@ -192,6 +192,14 @@ typedef struct shineon_conv2d_params {
   /* tuning overrides, 0 = auto */
   int tile_n; /* 16,32,64,128,256 */
   int stages;
+  /* optional: InstanceNorm statistics of the f32 output values, ACCUMULATED into [N][Cout][2] doubles (sum, sum of
+   * squares; the caller zeroes them) for shineon_instnorm_act(stats_ready = 1) -- saves that call's statistics pass over
+   * the output.  Needs y_f32 when the kernel's pixel tiles span several images (output smaller than 128 pixels). */
+  double* stats_ws;
+  /* K-blocks (64 input channels of one filter tap each) accumulated in one TMEM chain before the partial sum is taken
+   * over in registers: 0 = default (16, i.e. 1024 K), < 0 = the whole K in one chain (tensor-core accumulation
+   * truncates, so long chains lose accuracy: DESIGN.md section 4) */
+  int acc_chunk_kb;
 } shineon_conv2d_params;
 
 int shineon_conv2d_igemm_fwd(const shineon_conv2d_params* p, shineon_stream_t stream);
@@ -241,16 +249,18 @@ int shineon_col2im3x3(const float* t, const float* bias, float* y, int N, int H,
  * the tap-stacked products of the LOW-resolution tensor (the contraction over channels commutes with the
  * interpolation): t f32 NHWC [N,h,w,tstride], t[..., (fy*3+fx)*Cout + co] = <x[n,i,j,:], w[co,:,fy,fx]>
  * -> y f32 NHWC [N,2h,2w,Cout] = bias + sum over taps of the bilinearly upsampled t_tap, shifted by the tap,
- * zero where the tap leaves the 2h x 2w image (the conv's zero padding). */
-int shineon_upconv3x3_gather(const float* t, const float* bias, float* y, int N, int h, int w, int Cout,
+ * zero where the tap leaves the 2h x 2w image (the conv's zero padding).
+ * stats_ws (optional, like shineon_conv2d_params.stats_ws): [N][Cout][2] doubles accumulating sum / sum of squares of y. */
+int shineon_upconv3x3_gather(const float* t, const float* bias, float* y, double* stats_ws, int N, int h, int w, int Cout,
                              int tstride, shineon_stream_t stream);
 
 /* nn.InstanceNorm2d(affine=False, eps) over f32 NHWC x [N,H,W,C] (unet.py:133,135) followed by
  * activation; writes any subset of: f32 NHWC y_f32 (may alias x), planes y_hi/y_lo [N,H,W,cpad].
  * do_norm=0 skips the normalisation (innermost down block, unet.py:166-175).
- * stats_ws: caller-owned scratch of 2*N*C doubles (sum, sum of squares); zeroed by the call. */
+ * stats_ws: caller-owned scratch of 2*N*C doubles (sum, sum of squares); zeroed and filled by the call, unless
+ * stats_ready != 0: the producer of x accumulated them already (shineon_conv2d_params.stats_ws, shineon_upconv3x3_gather). */
 int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, void* y_lo, double* stats_ws, int N, int H,
-                         int W, int C, int cpad, float eps, int do_norm, int act, float act_param,
+                         int W, int C, int cpad, float eps, int do_norm, int stats_ready, int act, float act_param,
                          int plane_fmt, shineon_stream_t stream);
 
 /* Up-path input of a U-Net block (unet.py:138-146): up_act -> cat([skip, x'],C) -> bilinear x2

@@ -31,7 +31,7 @@ class Conv2dParams(C.Structure):
         ("y_f32", c_p), ("y_hi", c_p), ("y_lo", c_p),
         ("out_H", c_i), ("out_W", c_i), ("out_cstride", c_i), ("out_coffset", c_i),
         ("oh_mul", c_i), ("oh_off", c_i), ("ow_mul", c_i), ("ow_off", c_i),
-        ("tile_n", c_i), ("stages", c_i),
+        ("tile_n", c_i), ("stages", c_i), ("stats_ws", c_p), ("acc_chunk_kb", c_i),
     ]
 
 
@@ -85,11 +85,11 @@ SIGNATURES = {
                                    c_f, c_i, c_p],
     "shineon_nchw_s2d_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_col2im3x3": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
-    "shineon_upconv3x3_gather": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_upconv3x3_gather": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_pil_bilinear_coeffs": [c_i, c_i, c_p, c_p],
     "shineon_frame_prep": [C.POINTER(FramePrepParams), c_p],
     "shineon_flo_decode": [c_p, c_p, c_i, c_i, c_p],
-    "shineon_instnorm_act": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_f, c_i, c_p],
+    "shineon_instnorm_act": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_i, c_f, c_i, c_p],
     "shineon_upsample2x_cat": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     "shineon_sagan_attention": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     "shineon_l2norm_correlation": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],

@@ -44,11 +44,26 @@ inline int after_launch(const char* what) {
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- activations
+// nn.GELU() (exact erf form): 0.5 x (1 + erf(x / sqrt 2)), with erfc from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7):
+//   x >= 0: x - 0.5 x erfc(z),  x < 0: 0.5 x erfc(z),  z = |x| / sqrt 2   (no cancellation in the negative tail).
+// ~14 instructions with two MUFU ops; erff() costs about twice that and made the normalise + activate pass issue-bound
+// (profiles/r01_memory_ops.md).  Absolute error <= 0.5 |x| 1.5e-7, four orders below the parity tolerance.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float half_erfc = 0.5f * p * t * __expf(-z * z);
+  return x >= 0.f ? fmaf(-x, half_erfc, x) : x * half_erfc;
+}
+
 __device__ __forceinline__ float apply_act(float v, int act, float param) {
   switch (act) {
     case SHINEON_ACT_RELU: return fmaxf(v, 0.f);
     case SHINEON_ACT_LEAKY: return v > 0.f ? v : v * param;
-    case SHINEON_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    case SHINEON_ACT_GELU: return gelu_erf(v);
     case SHINEON_ACT_SWISH: return v / (1.f + expf(-v));
     case SHINEON_ACT_SINE: return sinf(30.f * v);
     case SHINEON_ACT_TANH: return tanhf(v);
@@ -86,6 +101,24 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Column sums of a 32 x 32 matrix held one ROW per lane (v[c] = this lane's value for column c): after five
+// recursive-halving exchange steps lane l returns sum over all lanes of v[l] (31 shuffles instead of 32 x 5).
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < off) {
+        const float send = up ? v[i] : v[i + off];
+        const float keep = up ? v[i + off] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return v[0];
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -44,6 +44,7 @@ struct ConvArgs {
   int kh, kw, stride, pad_h, pad_w;
   int cin_pad, cin_blocks, x_cstride;
   int num_kb, stages;
+  int chunk_kb;      // K-blocks accumulated in one TMEM buffer before the epilogue warps take the partial sum over
   int stage_off;     // byte offset (from the 1024-aligned tile base) of the epilogue transpose buffers, < 0 = direct stores
   int n_tiles, total_tiles;  // channel tiles per pixel tile, pixel tiles * channel tiles
   int w_per_image;           // 1: the B operand is a [N][Cout][K] batch indexed by the tile's image (needs nb == 1)
@@ -62,6 +63,7 @@ struct ConvArgs {
   plane_t* y_lo;
   int out_H, out_W, out_cstride, out_coffset;
   int oh_mul, oh_off, ow_mul, ow_off;
+  double* stats;  // [N][Cout][2] per-(image, channel) sum / sum of squares of the f32 output (InstanceNorm), nb == 1 only
 };
 
 // ------------------------------------------------------------------------------------- epilogue
@@ -152,10 +154,15 @@ __device__ __forceinline__ void conv_store_row(const float (&vals)[32], int c_fi
 // registers of in-flight stores, profiles/r01_conv_epilogue_store.md) and small-K layers are epilogue-bound.  The chunk
 // is transposed through a 4 KB per-warp staging buffer (16-byte unit j of row r at j ^ (r & 7): conflict-free both
 // ways) so that eight lanes write one pixel's 128 contiguous bytes and a store instruction covers 4 full lines.
-// rowbase[it] = element offset (pix * out_cstride + out_coffset) of row it*4 + lane/8; okmask bit r = row r is stored.
+// mybase = element offset (pix * out_cstride + out_coffset) of this lane's row; okmask bit r = row r is stored.
 __device__ __forceinline__ void conv_store_chunk_coalesced(const float (&vals)[32], float4* stage, int lane,
-                                                           const long (&rowbase)[8], uint32_t okmask, int c_first, int cnt,
+                                                           long mybase, uint32_t okmask, int c_first, int cnt,
                                                            const ConvArgs& a) {
+  // every lane needs the output offsets of the 8 rows it will write (row = it*4 + lane/8); fetched here, per chunk,
+  // instead of living in 16 registers across the whole tile
+  long rowbase[8];
+#pragma unroll
+  for (int it2 = 0; it2 < 8; ++it2) rowbase[it2] = __shfl_sync(0xffffffffu, mybase, it2 * 4 + (lane >> 3));
   __syncwarp();  // the previous chunk's reads of the staging buffer are done
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -213,6 +220,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_bias[BN], s_scale[BN], s_shift[BN];  // current tile's output-channel window
+  // current tile's per-channel sum / sum of squares (a.stats), one slot per TMEM lane quarter: every slot has exactly one
+  // writer warp and the flush adds the four in a fixed order, so the statistics are reproducible run to run
+  __shared__ float s_stat[4][BN][2];
 
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -289,42 +299,51 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (single thread)
+    // The K loop of a tile is cut into chunks of a.chunk_kb K-blocks; each chunk accumulates into its own TMEM buffer
+    // (the two buffers alternate) and the epilogue warps add the finished chunks in registers.  The tensor core adds into
+    // its fp32 accumulator with truncation, so one long accumulation chain loses ~(MMA count) x 2^-25 relative -- 9e-5 for
+    // the K = 24048 layers of the 5-frame U-Net, 1.7e-5 at K = 9216; chunks of 1024 K keep every
+    // chain at 128-192 MMAs and the cross-chunk sums are round-to-nearest.
     if (lane == 0) {
       uint32_t g = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + buf * kAccCols;
-        for (int kb = 0; kb < a.num_kb; ++kb, ++g) {
-          const int s = g % S;
-          const uint32_t ph = (g / S) & 1;
-          mbar_wait(bar_full + 8 * s, ph);
+      int it = 0;  // running chunk counter (accumulator ring position)
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        for (int kb0 = 0; kb0 < a.num_kb; kb0 += a.chunk_kb, ++it) {
+          const int buf = it & 1;
+          mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
           tc_fence_after();
-          const uint32_t sA = tiles + s * kStageBytes;
-          const uint32_t sB = sA + kPlanes * kABytes;
+          const uint32_t tmem_acc = tmem_base + buf * kAccCols;
+          const int kb1 = min(a.num_kb, kb0 + a.chunk_kb);
+          for (int kb = kb0; kb < kb1; ++kb, ++g) {
+            const int s = g % S;
+            const uint32_t ph = (g / S) & 1;
+            mbar_wait(bar_full + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t sA = tiles + s * kStageBytes;
+            const uint32_t sB = sA + kPlanes * kABytes;
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t dAh = umma_desc_sw128(sA + k * 32);
-            const uint64_t dBh = umma_desc_sw128(sB + k * 32);
-            if (kCat) {
-              const uint64_t dAl = umma_desc_sw128(sA + kABytes + k * 32);
-              umma_f16(tmem_acc, dAh, dBh, kIdescCat, (kb | k) != 0);  // N = 2*BN: rows of B_hi then B_lo
-              umma_f16(tmem_acc, dAl, dBh, kIdesc, 1);
-            } else {
-              umma_f16(tmem_acc, dAh, dBh, kIdesc, (kb | k) != 0);
-              if (SPLIT) {
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t dAh = umma_desc_sw128(sA + k * 32);
+              const uint64_t dBh = umma_desc_sw128(sB + k * 32);
+              const uint32_t accum = (kb != kb0 || k != 0) ? 1u : 0u;
+              if (kCat) {
                 const uint64_t dAl = umma_desc_sw128(sA + kABytes + k * 32);
-                const uint64_t dBl = umma_desc_sw128(sB + kBBytes + k * 32);
-                umma_f16(tmem_acc, dAh, dBl, kIdesc, 1);
+                umma_f16(tmem_acc, dAh, dBh, kIdescCat, accum);  // N = 2*BN: rows of B_hi then B_lo
                 umma_f16(tmem_acc, dAl, dBh, kIdesc, 1);
+              } else {
+                umma_f16(tmem_acc, dAh, dBh, kIdesc, accum);
+                if (SPLIT) {
+                  const uint64_t dAl = umma_desc_sw128(sA + kABytes + k * 32);
+                  const uint64_t dBl = umma_desc_sw128(sB + kBBytes + k * 32);
+                  umma_f16(tmem_acc, dAh, dBl, kIdesc, 1);
+                  umma_f16(tmem_acc, dAl, dBh, kIdesc, 1);
+                }
               }
             }
+            umma_commit(bar_empty + 8 * s);  // frees the smem slot once these MMAs retire
           }
-          umma_commit(bar_empty + 8 * s);  // frees the smem slot once these MMAs retire
+          umma_commit(bar_tfull + 8 * buf);  // chunk accumulator complete
         }
-        umma_commit(bar_tfull + 8 * buf);  // accumulator complete
       }
     }
   } else {
@@ -335,10 +354,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int r = q * 32 + lane;
     const int wi = r % a.bw, hi_ = (r / a.bw) % a.bh, ni = r / (a.bw * a.bh);
     constexpr int kChunk = BN < 32 ? BN : 32;
+    constexpr int kNCH = (BN + 2 * kChunk - 1) / (2 * kChunk);  // 32-column chunks this warp owns: c0 = (2*ci + half) * kChunk
     float4* const stage = a.stage_off < 0 ? nullptr
         : reinterpret_cast<float4*>(smem_raw + (tiles - smem_u32(smem_raw)) + a.stage_off) + ew * 256;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+    int it = 0;  // running chunk counter (accumulator ring position)
+    int ti = 0;  // tiles done by this CTA
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
       const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
       const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, tn = mt / tiles_hw;
       const int cn0 = nt * BN;
@@ -349,13 +370,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       const bool co_ok = kChunk == 32 && stage != nullptr && (a.out_cstride & 3) == 0 &&
                          ((a.out_coffset + cn0) & 3) == 0;  // warp-uniform
       const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
-      long rowbase[8];
-      if (co_ok) {
-        const long mybase = pix * a.out_cstride + a.out_coffset;
-#pragma unroll
-        for (int it2 = 0; it2 < 8; ++it2) rowbase[it2] = __shfl_sync(0xffffffffu, mybase, it2 * 4 + (lane >> 3));
-      }
-      // stage this tile's bias / folded-BN window (all 4 epilogue warps are past the previous tile's reads)
+      const long mybase = pix * a.out_cstride + a.out_coffset;
+      // stage this tile's bias / folded-BN window (all epilogue warps are past the previous tile's reads)
       epi_bar_sync<kEpiWarps * 32>();
       for (int i = threadIdx.x - 64; i < BN; i += kEpiWarps * 32) {
         const int c = cn0 + i;
@@ -363,32 +379,66 @@ __global__ void __launch_bounds__(kThreads, 1)
         s_bias[i] = (ok && a.bias) ? __ldg(a.bias + c) : 0.f;
         s_scale[i] = (ok && a.scale) ? __ldg(a.scale + c) : 1.f;
         s_shift[i] = (ok && a.scale) ? __ldg(a.shift + c) : 0.f;
+        if (a.stats) {  // InstanceNorm statistics: flush the previous tile's partial sums (one image per tile)
+          if (ti > 0) {
+            const int ptile = tile - (int)gridDim.x;
+            const int pc = (ptile % a.n_tiles) * BN + i, pn = (ptile / a.n_tiles) / tiles_hw;
+            if (pc < a.Cout) {
+              atomicAdd(a.stats + ((long)pn * a.Cout + pc) * 2,
+                        (double)s_stat[0][i][0] + (double)s_stat[1][i][0] + (double)s_stat[2][i][0] + (double)s_stat[3][i][0]);
+              atomicAdd(a.stats + ((long)pn * a.Cout + pc) * 2 + 1,
+                        (double)s_stat[0][i][1] + (double)s_stat[1][i][1] + (double)s_stat[2][i][1] + (double)s_stat[3][i][1]);
+            }
+          }
+        }
       }
       epi_bar_sync<kEpiWarps * 32>();
-      const int buf = it & 1;
-      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + buf * kAccCols;
-#pragma unroll 1
-      for (int c0 = half * kChunk; c0 < BN; c0 += 2 * kChunk) {
-        if (cn0 + c0 >= a.Cout) break;  // warp-uniform
-        uint32_t v[32];
-        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        uint32_t v2[32];
-        if (kChunk == 32) {
-          tmem_ld32(taddr, v);
-          if (kCat) tmem_ld32(taddr + BN, v2);
-        } else {
-          tmem_ld16(taddr, v);
-          if (kCat) tmem_ld16(taddr + BN, v2);
+      // ---- gather the tile's accumulator: one TMEM buffer per K chunk, summed here (round-to-nearest)
+      float accr[kNCH][32];
+      for (int kb0 = 0; kb0 < a.num_kb; kb0 += a.chunk_kb, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + buf * kAccCols;
+#pragma unroll
+        for (int ci = 0; ci < kNCH; ++ci) {
+          const int c0 = (2 * ci + half) * kChunk;
+          if (c0 < BN && cn0 + c0 < a.Cout) {  // warp-uniform
+            uint32_t v[32];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            if (kChunk == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float acc = (i < kChunk) ? __uint_as_float(v[i]) : 0.f;
+              accr[ci][i] = kb0 == 0 ? acc : accr[ci][i] + acc;
+            }
+            if (kCat) {  // right half of the accumulator: hi*lo (the left half holds hi*hi + lo*hi)
+              if (kChunk == 32) tmem_ld32(taddr + BN, v); else tmem_ld16(taddr + BN, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < kChunk) accr[ci][i] += __uint_as_float(v[i]);
+            }
+          }
         }
-        tmem_ld_wait();
+        // hand the accumulator back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      }
+      // ---- bias / activation / folded BN / statistics / stores, from registers (the MMA warp is already on the next tile)
+#pragma unroll 1
+      for (int ci = 0; ci < kNCH; ++ci) {
+        const int c0 = (2 * ci + half) * kChunk;
+        if (c0 >= BN || cn0 + c0 >= a.Cout) break;  // warp-uniform
         const int cnt = min(kChunk, a.Cout - (cn0 + c0));  // warp-uniform
         float vals[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float acc = (i < kChunk) ? __uint_as_float(v[i]) : 0.f;
-          if (kCat && i < kChunk) acc += __uint_as_float(v2[i]);  // hi*hi + lo*hi  +  hi*lo
+          float acc = accr[0][i];
+#pragma unroll
+          for (int k = 1; k < kNCH; ++k) acc = ci == k ? accr[k][i] : acc;
           vals[i] = (i < kChunk) ? fmaf(acc, a.acc_scale, s_bias[c0 + (i < kChunk ? i : 0)]) : 0.f;
         }
         act_chunk_dispatch(vals, a.pre_act, a.act_param);
@@ -398,15 +448,33 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (i < kChunk) vals[i] = fmaf(vals[i], s_scale[c0 + i], s_shift[c0 + i]);
         }
         act_chunk_dispatch(vals, a.post_act, a.act_param);
+        if (a.stats != nullptr) {  // warp-uniform: column sums of this 32-row x 32-channel chunk -> shared partials
+          float sv[32];  // one scratch array, used twice (register budget: 168 per thread with 10 warps)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[i] = (row_ok && i < cnt) ? vals[i] : 0.f;
+          s_stat[q][c0 + lane][0] = warp_transpose_sum(sv, lane);  // single writer of (quarter q, chunk c0); lanes >= cnt: 0
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[i] = (row_ok && i < cnt) ? vals[i] * vals[i] : 0.f;
+          s_stat[q][c0 + lane][1] = warp_transpose_sum(sv, lane);
+        }
         if (co_ok && (cnt & 3) == 0)
-          conv_store_chunk_coalesced(vals, stage, lane, rowbase, okmask, cn0 + c0, cnt, a);
+          conv_store_chunk_coalesced(vals, stage, lane, mybase, okmask, cn0 + c0, cnt, a);
         else if (row_ok)
           conv_store_row(vals, cn0 + c0, cnt, pix, a);
       }
-      // hand the accumulator back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+    }
+    if (a.stats != nullptr && ti > 0) {  // the last tile's statistics
+      epi_bar_sync<kEpiWarps * 32>();
+      const int ptile = blockIdx.x + (ti - 1) * (int)gridDim.x;
+      for (int i = threadIdx.x - 64; i < BN; i += kEpiWarps * 32) {
+        const int pc = (ptile % a.n_tiles) * BN + i, pn = (ptile / a.n_tiles) / tiles_hw;
+        if (pc < a.Cout) {
+          atomicAdd(a.stats + ((long)pn * a.Cout + pc) * 2,
+                    (double)s_stat[0][i][0] + (double)s_stat[1][i][0] + (double)s_stat[2][i][0] + (double)s_stat[3][i][0]);
+          atomicAdd(a.stats + ((long)pn * a.Cout + pc) * 2 + 1,
+                    (double)s_stat[0][i][1] + (double)s_stat[1][i][1] + (double)s_stat[2][i][1] + (double)s_stat[3][i][1]);
+        }
+      }
     }
   }
 
@@ -839,6 +907,7 @@ static int fill_args(const shineon_conv2d_params* p, ConvArgs& a) {
   a.x_cstride = p->x_cstride ? p->x_cstride : p->cin_pad;
   SHINEON_REQUIRE(a.x_cstride >= a.cin_pad && a.x_cstride % 8 == 0, "conv2d: x_cstride %d", a.x_cstride);
   a.num_kb = p->kh * p->kw * a.cin_blocks;
+  a.chunk_kb = p->acc_chunk_kb > 0 ? p->acc_chunk_kb : (p->acc_chunk_kb < 0 ? a.num_kb : 16);
   a.stages = 1;
   a.bias = p->bias; a.scale = p->scale; a.shift = p->shift;
   a.pre_act = p->pre_act; a.post_act = p->post_act; a.act_param = p->act_param;
@@ -858,6 +927,7 @@ static int fill_args(const shineon_conv2d_params* p, ConvArgs& a) {
   SHINEON_REQUIRE((a.Ho - 1) * a.oh_mul + a.oh_off < a.out_H && (a.Wo - 1) * a.ow_mul + a.ow_off < a.out_W, "conv2d: output pixel window out of range");
   a.w_per_image = p->w_per_image ? 1 : 0;
   pick_tile(a.w_per_image ? 1 : a.N, a.Ho, a.Wo, a.nb, a.bh, a.bw);
+  a.stats = nullptr;
   a.tiles_w = cdiv(a.Wo, a.bw);
   a.tiles_h = cdiv(a.Ho, a.bh);
   return SHINEON_OK;
@@ -867,11 +937,34 @@ static int fill_args(const shineon_conv2d_params* p, ConvArgs& a) {
 
 using namespace shineon;
 
+int launch_instnorm_stats(const float* x, double* ws, int N, int HW, int C, cudaStream_t stream);  // norm_act.cu
+
+static int conv2d_igemm_launch(const shineon_conv2d_params* p, ConvArgs& a, cudaStream_t stream);
+
 extern "C" int shineon_conv2d_igemm_fwd(const shineon_conv2d_params* p, shineon_stream_t stream_) {
   ConvArgs a;
   int rc = fill_args(p, a);
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
+  // InstanceNorm statistics of the f32 output: in the epilogue when every pixel tile lies inside one image, otherwise
+  // (the 4x3 ... 8x6 levels, a few hundred KB) by the standalone pass right behind the conv
+  bool stats_after = false;
+  if (p->stats_ws != nullptr) {
+    if (a.nb == 1) {
+      a.stats = p->stats_ws;
+    } else {
+      SHINEON_REQUIRE(p->y_f32 && a.out_cstride == a.Cout && a.out_H == a.Ho && a.out_W == a.Wo,
+                      "conv2d: stats_ws on a multi-image tile needs a dense f32 output");
+      stats_after = true;
+    }
+  }
+  rc = conv2d_igemm_launch(p, a, stream);
+  if (rc == SHINEON_OK && stats_after) rc = launch_instnorm_stats(p->y_f32, p->stats_ws, a.N, a.Ho * a.Wo, a.Cout, stream);
+  return rc;
+}
+
+static int conv2d_igemm_launch(const shineon_conv2d_params* p, ConvArgs& a, cudaStream_t stream) {
+  int rc;
   const bool split = p->x_lo != nullptr;
   const int m_tiles = a.tiles_w * a.tiles_h * cdiv(a.N, a.nb);
   SHINEON_REQUIRE((long)m_tiles < (1l << 31), "conv2d: too many tiles");
@@ -971,7 +1064,8 @@ extern "C" int shineon_conv2d_im2col_fwd(const shineon_conv2d_params* p, const f
   a.kh = p->kh; a.kw = p->kw; a.stride = p->stride; a.pad_h = p->pad_h; a.pad_w = p->pad_w;
   a.cin_pad = p->cin_pad; a.cin_blocks = p->cin_pad / kBlockK; a.x_cstride = p->cin_pad;
   a.num_kb = a.cin_blocks;  // the GEMM is 1x1 over the padded K
-  a.stages = 1; a.w_per_image = 0;
+  a.chunk_kb = a.num_kb;
+  a.stages = 1; a.w_per_image = 0; a.stats = nullptr;
   a.bias = p->bias; a.scale = p->scale; a.shift = p->shift;
   a.pre_act = p->pre_act; a.post_act = p->post_act; a.act_param = p->act_param;
   a.fmt = p->plane_fmt; a.acc_scale = p->acc_scale == 0.f ? 1.f : p->acc_scale; a.idesc = 0;

@@ -616,6 +616,8 @@ static inline int grid_x(long total, int threads) {
 
 using namespace shineon;
 
+int launch_instnorm_stats(const float* x, double* ws, int N, int HW, int C, cudaStream_t stream);
+
 #define SHINEON_REQUIRE_FMT(f, who) SHINEON_REQUIRE((f) == SHINEON_FMT_BF16 || (f) == SHINEON_FMT_FP16, who ": plane_fmt %d", (f))
 
 extern "C" int shineon_nchw_to_planes(const float* x0, int C0, const float* x1, int C1, void* y_hi, void* y_lo,
@@ -686,17 +688,27 @@ extern "C" int shineon_col2im3x3(const float* t, const float* bias, float* y, in
   return after_launch("col2im3x3_kernel");
 }
 
-int shineon_upconv3x3_gather_tma(const float* t, const float* bias, float* y, int N, int h, int w, int Cout, int tstride,
-                                 cudaStream_t stream);  // upconv_gather.cu
+int shineon_upconv3x3_gather_tma(const float* t, const float* bias, float* y, double* stats_ws, int N, int h, int w,
+                                 int Cout, int tstride, cudaStream_t stream);  // upconv_gather.cu
 
-extern "C" int shineon_upconv3x3_gather(const float* t, const float* bias, float* y, int N, int h, int w, int Cout,
-                                        int tstride, shineon_stream_t stream) {
+static int upconv3x3_gather_direct(const float* t, const float* bias, float* y, int N, int h, int w, int Cout, int tstride,
+                                   shineon_stream_t stream);
+
+extern "C" int shineon_upconv3x3_gather(const float* t, const float* bias, float* y, double* stats_ws, int N, int h, int w,
+                                        int Cout, int tstride, shineon_stream_t stream) {
   SHINEON_REQUIRE(t && y, "upconv3x3_gather: null pointer");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && h > 0 && w > 0 && Cout > 0 && tstride >= 9 * Cout, "upconv3x3_gather: bad shape");
   {  // TMA-staged variant (upconv_gather.cu) where the channel count allows 32-channel boxes
-    const int rc = shineon_upconv3x3_gather_tma(t, bias, y, N, h, w, Cout, tstride, (cudaStream_t)stream);
+    const int rc = shineon_upconv3x3_gather_tma(t, bias, y, stats_ws, N, h, w, Cout, tstride, (cudaStream_t)stream);
     if (rc <= 0) return rc;
   }
+  int rc = upconv3x3_gather_direct(t, bias, y, N, h, w, Cout, tstride, stream);
+  if (rc == SHINEON_OK && stats_ws) rc = launch_instnorm_stats(y, stats_ws, N, 4 * h * w, Cout, (cudaStream_t)stream);
+  return rc;
+}
+
+static int upconv3x3_gather_direct(const float* t, const float* bias, float* y, int N, int h, int w, int Cout, int tstride,
+                                   shineon_stream_t stream) {
   const int vec = (Cout % 4 == 0 && tstride % 4 == 0) ? 4 : 1;
   const int groups = Cout / vec;
   int gpb = 1;  // channel groups per CTA (power of two <= 8); the other 256/gpb threads tile low-res pixels
@@ -714,9 +726,28 @@ extern "C" int shineon_upconv3x3_gather(const float* t, const float* bias, float
   return after_launch("upconv3x3_gather_kernel");
 }
 
+// Accumulates per-(n, c) sum / sum of squares of x [N,HW,C] into ws (NOT zeroed here).  Also used by the conv kernel's
+// host side for layers whose pixel tiles span several images (conv_igemm.cu).
+int launch_instnorm_stats(const float* x, double* ws, int N, int HW, int C, cudaStream_t stream) {
+  int cb = 32;
+  while (cb > 1 && cb / 2 >= C) cb /= 2;
+  const int pp = 256 / cb;
+  int pix_per_cta = pp * 16;
+  dim3 grid(cdiv(HW, pix_per_cta), cdiv(C, cb), N);
+  switch (cb) {
+    case 32: instnorm_stats_kernel<32><<<grid, 256, 0, stream>>>(x, ws, HW, C, pix_per_cta); break;
+    case 16: instnorm_stats_kernel<16><<<grid, 256, 0, stream>>>(x, ws, HW, C, pix_per_cta); break;
+    case 8: instnorm_stats_kernel<8><<<grid, 256, 0, stream>>>(x, ws, HW, C, pix_per_cta); break;
+    case 4: instnorm_stats_kernel<4><<<grid, 256, 0, stream>>>(x, ws, HW, C, pix_per_cta); break;
+    case 2: instnorm_stats_kernel<2><<<grid, 256, 0, stream>>>(x, ws, HW, C, pix_per_cta); break;
+    default: instnorm_stats_kernel<1><<<grid, 256, 0, stream>>>(x, ws, HW, C, pix_per_cta); break;
+  }
+  return after_launch("instnorm_stats_kernel");
+}
+
 extern "C" int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, void* y_lo, double* stats_ws, int N,
-                                    int H, int W, int C, int cpad, float eps, int do_norm, int act, float act_param,
-                                    int plane_fmt, shineon_stream_t stream_) {
+                                    int H, int W, int C, int cpad, float eps, int do_norm, int stats_ready, int act,
+                                    float act_param, int plane_fmt, shineon_stream_t stream_) {
   SHINEON_REQUIRE_FMT(plane_fmt, "instnorm_act");
   SHINEON_REQUIRE(x && (y_f32 || y_hi), "instnorm_act: null pointer");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && C > 0, "instnorm_act: bad shape");
@@ -725,23 +756,10 @@ extern "C" int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, vo
   SHINEON_REQUIRE(2 * C * sizeof(float) <= 48 * 1024, "instnorm_act: C too large");
   cudaStream_t stream = (cudaStream_t)stream_;
   const int HW = H * W;
-  if (do_norm) {
+  if (do_norm && !stats_ready) {
     cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * (size_t)N * C, stream);
     if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "instnorm_act memset: %s", cudaGetErrorString(e));
-    int cb = 32;
-    while (cb > 1 && cb / 2 >= C) cb /= 2;
-    const int pp = 256 / cb;
-    int pix_per_cta = pp * 16;
-    dim3 grid(cdiv(HW, pix_per_cta), cdiv(C, cb), N);
-    switch (cb) {
-      case 32: instnorm_stats_kernel<32><<<grid, 256, 0, stream>>>(x, stats_ws, HW, C, pix_per_cta); break;
-      case 16: instnorm_stats_kernel<16><<<grid, 256, 0, stream>>>(x, stats_ws, HW, C, pix_per_cta); break;
-      case 8: instnorm_stats_kernel<8><<<grid, 256, 0, stream>>>(x, stats_ws, HW, C, pix_per_cta); break;
-      case 4: instnorm_stats_kernel<4><<<grid, 256, 0, stream>>>(x, stats_ws, HW, C, pix_per_cta); break;
-      case 2: instnorm_stats_kernel<2><<<grid, 256, 0, stream>>>(x, stats_ws, HW, C, pix_per_cta); break;
-      default: instnorm_stats_kernel<1><<<grid, 256, 0, stream>>>(x, stats_ws, HW, C, pix_per_cta); break;
-    }
-    int rc = after_launch("instnorm_stats_kernel");
+    int rc = launch_instnorm_stats(x, stats_ws, N, HW, C, stream);
     if (rc) return rc;
   }
   // 128-bit plane stores need 16-byte aligned rows: cpad % 8 and 16-byte aligned plane pointers (channel windows are)

@@ -31,9 +31,10 @@ __host__ __device__ constexpr bool up3c_has(int f, int p, int a) { return (f + p
 
 __global__ void __launch_bounds__(256, 3)
     upconv3x3_gather_tma_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restrict__ bias,
-                                float* __restrict__ y, int h, int w, int Cout, int tiles_x) {
+                                float* __restrict__ y, double* __restrict__ stats, int h, int w, int Cout, int tiles_x) {
   extern __shared__ __align__(128) float sv[];  // [9 taps][TH+2][TW+2][CB]
   __shared__ __align__(8) uint64_t bar;
+  __shared__ float s_stat[8][kGatherCB][2];  // per warp: single writer per slot, summed in a fixed order (reproducible)
   const int n = blockIdx.z;
   const int co0 = blockIdx.y * kGatherCB;
   const int i0 = ((int)blockIdx.x / tiles_x) * kGatherTH, j0 = ((int)blockIdx.x % tiles_x) * kGatherTW;
@@ -103,7 +104,8 @@ __global__ void __launch_bounds__(256, 3)
       }
     }
   }
-  if (i < h && j < w) {
+  const bool ok = i < h && j < w;
+  if (ok) {
 #pragma unroll
     for (int p = 0; p < 2; ++p)
 #pragma unroll
@@ -112,6 +114,45 @@ __global__ void __launch_bounds__(256, 3)
         *reinterpret_cast<float4*>(dst) = make_float4(out[p][q][0], out[p][q][1], out[p][q][2], out[p][q][3]);
       }
   }
+  if (stats != nullptr) {
+    // InstanceNorm statistics of the f32 output (the whole CTA lies in image n): per-thread sums over its 2x2 pixels,
+    // lanes sharing a channel group (g = lane & 7) combined by shuffles, warps through shared atomics, one pair of
+    // f64 atomics per channel and CTA
+    float s4[4], q4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float sacc = 0.f, qacc = 0.f;
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float x = ok ? out[p][q][k] : 0.f;
+          sacc += x;
+          qacc = fmaf(x, x, qacc);
+        }
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 8);
+      qacc += __shfl_xor_sync(0xffffffffu, qacc, 8);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+      qacc += __shfl_xor_sync(0xffffffffu, qacc, 16);
+      s4[k] = sacc;
+      q4[k] = qacc;
+    }
+    if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s_stat[threadIdx.x >> 5][g * 4 + k][0] = s4[k];
+        s_stat[threadIdx.x >> 5][g * 4 + k][1] = q4[k];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kGatherCB) {
+      const int c = threadIdx.x >> 1, which = threadIdx.x & 1;
+      double tot = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) tot += (double)s_stat[wv][c][which];
+      atomicAdd(stats + ((long)n * Cout + co0 + c) * 2 + which, tot);
+    }
+  }
 }
 
 }  // namespace shineon
@@ -119,8 +160,8 @@ __global__ void __launch_bounds__(256, 3)
 using namespace shineon;
 
 // Returns SHINEON_OK after launching, or a positive value when the shape does not fit this variant (caller falls back).
-int shineon_upconv3x3_gather_tma(const float* t, const float* bias, float* y, int N, int h, int w, int Cout, int tstride,
-                                 cudaStream_t stream) {
+int shineon_upconv3x3_gather_tma(const float* t, const float* bias, float* y, double* stats_ws, int N, int h, int w, int Cout,
+                                 int tstride, cudaStream_t stream) {
   if (Cout % kGatherCB != 0 || tstride % 4 != 0 || (reinterpret_cast<uintptr_t>(t) & 15) != 0 ||
       (reinterpret_cast<uintptr_t>(y) & 15) != 0 || (bias && (reinterpret_cast<uintptr_t>(bias) & 15) != 0))
     return 1;
@@ -143,6 +184,6 @@ int shineon_upconv3x3_gather_tma(const float* t, const float* bias, float* y, in
   }
   const int tiles_x = cdiv(w, kGatherTW), tiles_y = cdiv(h, kGatherTH);
   dim3 grid(tiles_x * tiles_y, Cout / kGatherCB, N);
-  upconv3x3_gather_tma_kernel<<<grid, 256, kGatherSmemBytes, stream>>>(tm, bias, y, h, w, Cout, tiles_x);
+  upconv3x3_gather_tma_kernel<<<grid, 256, kGatherSmemBytes, stream>>>(tm, bias, y, stats_ws, h, w, Cout, tiles_x);
   return after_launch("upconv3x3_gather_tma_kernel");
 }

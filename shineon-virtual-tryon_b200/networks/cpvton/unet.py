@@ -258,25 +258,37 @@ class UnetSkipConnectionBlock(nn.Module):
         return ops.instnorm_act_bwd(sv["c"], sv["ws"], gz, g_y, do_norm=sv["inorm"], act=None, eps=sv["eps"],
                                     want_f32=True, want_planes=True, prec=prec)
 
-    def _finish(self, conv_f32, norm, bn, attn, act, act_param, prec, want_final_f32=False, out_planes=None):
+    def _finish(self, conv_f32, norm, bn, attn, act, act_param, prec, want_final_f32=False, out_planes=None, ws=None):
         """conv output (f32 NHWC, bias [and folded BN] applied) -> [InstanceNorm] -> [SelfAttention] -> act.
-        Returns Planes of the activated value, or the final f32 tensor when want_final_f32."""
+        Returns Planes of the activated value, or the final f32 tensor when want_final_f32.
+        ws: InstanceNorm statistics already accumulated by the kernel that produced conv_f32 (_stats_ws)."""
         inorm = isinstance(norm, nn.InstanceNorm2d)
+        st = dict(ws=ws, stats_ready=True) if (inorm and ws is not None) else {}
         if attn is None:
             if want_final_f32:
                 y, _ = ops.instnorm_act(conv_f32, do_norm=inorm, eps=norm.eps if inorm else 1e-5, act=None,
-                                        want_f32=True, want_planes=False, out_f32=conv_f32)
+                                        want_f32=True, want_planes=False, out_f32=conv_f32, **st)
                 return y
             _, p = ops.instnorm_act(conv_f32, do_norm=inorm, eps=norm.eps if inorm else 1e-5, act=act,
                                     act_param=act_param, want_f32=False, want_planes=True, prec=prec,
-                                    out_planes=out_planes)
+                                    out_planes=out_planes, **st)
             return p
         # attention works on the normalised, un-activated tensor: needs it as f32 (residual) and planes (qkv conv)
         y, p = ops.instnorm_act(conv_f32, do_norm=inorm, eps=norm.eps if inorm else 1e-5, act=None, want_f32=True,
-                                want_planes=True, prec=prec, out_f32=conv_f32)
+                                want_planes=True, prec=prec, out_f32=conv_f32, **st)
         if want_final_f32:
             return attn.run(y, p, want_f32=True, want_planes=False)[0]
         return attn.run(y, p, act=act, act_param=act_param, want_f32=False, want_planes=True, out_planes=out_planes)[1]
+
+    # InstanceNorm statistics are accumulated by the kernel that PRODUCES the tensor (conv epilogue / upconv gather):
+    # False = the separate statistics pass of instnorm_act (kept for A/B measurements and the tests)
+    FUSE_STATS = True
+
+    @classmethod
+    def _stats_ws(cls, norm, N, C, device):
+        if cls.FUSE_STATS and isinstance(norm, nn.InstanceNorm2d):
+            return torch.zeros(2 * N * C, dtype=torch.float64, device=device)
+        return None
 
     def run(self, a_in, prec, train=False, out=None, raw_out=False):
         """a_in: Planes holding this block's (already down-activated) input; for the outermost block a tuple
@@ -297,29 +309,50 @@ class UnetSkipConnectionBlock(nn.Module):
             next_act, next_par = act_name(sub._parts["down_act"])
         bn = pk["down_bn"]
         sc, sh = bn if bn is not None else (None, None)
+        dc, uc = pr["downconv"], pr["upconv"]
+        low = self._lowres(pk, prec)
+        N_ = a_in[0].shape[0] if isinstance(a_in, tuple) else a_in.N
+        dev = a_in[0].device if isinstance(a_in, tuple) else a_in.hi.device
+        if isinstance(a_in, tuple):
+            hin, win = a_in[0].shape[2:]
+        else:
+            hin, win = a_in.H, a_in.W
+        # a down conv with neither norm nor attention behind it (outermost / innermost block): bias + the next layer's
+        # activation in the conv epilogue, planes written straight into the concat buffer -- no f32 round trip
+        direct_planes = (low is not None and pr["downnorm"] is None and pr["attn_down"] is None and bn is None
+                         and (self.outermost or self.innermost))
+        cat = None
+        if low is not None and not self.innermost:
+            c_skip, p_skip, c_xp, p_xp = pk["cat_geom"]
+            cat = ops.Planes(N_, hin // 2, win // 2, c_skip + c_xp, prec=prec, device=dev, cpad=p_skip + p_xp)
+        ws_d = self._stats_ws(pr["downnorm"], N_, dc.out_channels, dev)
+        if direct_planes:
+            okw = dict(post_act=next_act, act_param=next_par,
+                       **(dict(out_planes=cat.window(0, pk["cat_geom"][0])) if cat is not None else dict(want_planes=True)))
+        else:
+            okw = dict(scale=sc, shift=sh, want_f32=True)
         if isinstance(a_in, tuple) and pk["down_i2c"] is not None:
-            f32, _ = pk["down_first"].conv(a_in[0], a_in[1], scale=sc, shift=sh, want_f32=True)
+            f32, a_mid = pk["down_first"].conv(a_in[0], a_in[1], **okw)
         else:
             if isinstance(a_in, tuple):
                 a_in = ops.nchw_to_planes(a_in[0], a_in[1], prec=prec)
-            f32, _ = ops.conv2d(a_in, pk["down"], scale=sc, shift=sh, want_f32=True)
-        low = self._lowres(pk, prec)
+            f32, a_mid = ops.conv2d(a_in, pk["down"], stats_ws=ws_d, **okw)
         if low is not None:
             # up-path operand at the LOW resolution: [skip | x'] written straight into one concat buffer by their producers
             if self.innermost:
-                cat = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, prec)
+                cat = a_mid if direct_planes else self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par,
+                                                               prec, ws=ws_d)
             else:
-                c_skip, p_skip, c_xp, p_xp = pk["cat_geom"]
-                n_, h_, w_ = f32.shape[:3]
-                cat = ops.Planes(n_, h_, w_, c_skip + c_xp, prec=prec, device=f32.device, cpad=p_skip + p_xp)
-                a_mid = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, prec,
-                                     out_planes=cat.window(0, c_skip))
+                if not direct_planes:
+                    a_mid = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, prec,
+                                         out_planes=cat.window(0, c_skip), ws=ws_d)
                 sub.run(a_mid, prec, out=cat.window(p_skip, c_xp))
-            f32 = low(cat)
+            ws_u = self._stats_ws(pr["upnorm"], N_, uc.out_channels, dev)
+            f32 = low(cat, stats_ws=ws_u)
             if self.outermost or raw_out:
-                return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], None, 0.0, prec, want_final_f32=True)
-            return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], up_act, up_par, prec, out_planes=out)
-        a_mid = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, prec)
+                return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], None, 0.0, prec, want_final_f32=True, ws=ws_u)
+            return self._finish(f32, pr["upnorm"], bn, pr["attn_up"], up_act, up_par, prec, out_planes=out, ws=ws_u)
+        a_mid = self._finish(f32, pr["downnorm"], bn, pr["attn_down"], next_act, next_par, prec, ws=ws_d)
         # ---- child + up-path input
         if self.innermost:
             u = ops.upsample2x_cat(a_mid, None)

@@ -13,6 +13,9 @@ from ._lib import ACT, PAD, Conv2dParams, TpsTables, check
 # When set to a list, conv2d() brackets every tensor-core conv launch with CUDA events on the launching stream
 # and appends (algorithmic_flops, start_event, end_event); bench.py uses it for the roofline of the dominant kernel.
 PROFILE = None
+# K-blocks per TMEM accumulation chain of the conv kernel (shineon_conv2d_params.acc_chunk_kb): 0 = kernel default (16),
+# -1 = one chain over the whole K (the round-1 behaviour; kept for the accuracy A/B in tests/diag_accum.py)
+ACC_CHUNK_KB = 0
 
 
 def C_void(v):
@@ -297,11 +300,13 @@ class PackedConv:
 
 def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_param=0.0, out_f32=None,
            out_planes=None, out_coffset=0, want_f32=False, want_planes=False, direct=False, tile_n=0, stages=0,
-           out_geom=None, out_hw=None):
+           out_geom=None, out_hw=None, stats_ws=None):
     """Run one convolution layer on planes `x` with packed weights `pc`.
 
     Outputs: f32 NHWC tensor [N,Ho,Wo,Cout] (want_f32 / out_f32) and/or Planes (want_planes / out_planes).
     out_geom = (out_H, out_W, oh_mul, oh_off, ow_mul, ow_off) scatters into a larger output (deconv phases).
+    stats_ws: zeroed f64 [N*Cout*2] buffer; the kernel adds the per-(image, channel) sum / sum of squares of the f32
+    output values to it (InstanceNorm statistics for instnorm_act(stats_ready=True)).
     """
     N, H, W = x.N, x.H, x.W
     assert x.cpad == pc.cin_pad, f"activation cpad {x.cpad} != packed cin_pad {pc.cin_pad}"
@@ -339,6 +344,9 @@ def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_pa
         p.out_cstride, p.out_coffset = out_f32.shape[-1], out_coffset
     p.oh_mul, p.oh_off, p.ow_mul, p.ow_off = ohm, oho, owm, owo
     p.tile_n, p.stages = tile_n, stages
+    p.stats_ws = _p(stats_ws)
+    p.acc_chunk_kb = ACC_CHUNK_KB
+    assert stats_ws is None or (not direct and stats_ws.dtype == torch.float64 and stats_ws.numel() == 2 * N * pc.Cout)
     fn = _lib.load().shineon_conv2d_direct_fwd if direct else _lib.load().shineon_conv2d_igemm_fwd
     prof = PROFILE
     if prof is not None and not direct:
@@ -496,8 +504,12 @@ class S2dConv:
     def conv(self, x0, x1=None, *, scale=None, shift=None, pre_act=None, post_act=None, act_param=0.0, want_f32=False,
              want_planes=False, out_f32=None, out_planes=None, fused=None):
         a = self.prepare(x0, x1)
-        return conv2d(a, self.pc, scale=scale, shift=shift, pre_act=pre_act, post_act=post_act, act_param=act_param,
-                      want_f32=want_f32, want_planes=want_planes, out_f32=out_f32, out_planes=out_planes)
+        return self.conv_planes(a, scale=scale, shift=shift, pre_act=pre_act, post_act=post_act, act_param=act_param,
+                                want_f32=want_f32, want_planes=want_planes, out_f32=out_f32, out_planes=out_planes)
+
+    def conv_planes(self, a, **kw):
+        """The GEMM on space-to-depth planes that already exist (prepare(), or written directly by the frame prep)."""
+        return conv2d(a, self.pc, **kw)
 
 
 def first_layer_conv(weight, bias, stride, pad, prec=None):
@@ -540,8 +552,8 @@ class UpsampledConv3x3:
         self.pc = PackedConv(w2, None, stride=1, pad=0, prec=prec, cin_pad=cin_pad, chan_map=chan_map)
         self.bias = None if bias is None else _req(bias.detach().float().contiguous(), name="bias")
 
-    def __call__(self, x):
-        """x: low-res Planes [N,h,w,cin_pad] -> f32 NHWC [N,2h,2w,Cout]."""
+    def __call__(self, x, stats_ws=None):
+        """x: low-res Planes [N,h,w,cin_pad] -> f32 NHWC [N,2h,2w,Cout].  stats_ws: see conv2d."""
         global PROFILE
         prof, PROFILE = PROFILE, None  # one profile record for GEMM + gather, with the reference formulation's FLOPs
         if prof is not None:
@@ -552,8 +564,8 @@ class UpsampledConv3x3:
         finally:
             PROFILE = prof
         y = torch.empty(x.N, 2 * x.H, 2 * x.W, self.Cout, dtype=torch.float32, device=t.device)
-        check(_lib.load().shineon_upconv3x3_gather(_p(t), _p(self.bias), _p(y), x.N, x.H, x.W, self.Cout, t.shape[-1],
-                                                   _stream()), "shineon_upconv3x3_gather")
+        check(_lib.load().shineon_upconv3x3_gather(_p(t), _p(self.bias), _p(y), _p(stats_ws), x.N, x.H, x.W, self.Cout,
+                                                   t.shape[-1], _stream()), "shineon_upconv3x3_gather")
         if prof is not None:
             e1.record()
             prof.append((2.0 * x.N * 4 * x.H * x.W * self.Cout * 9 * self.Cin, e0, e1,
@@ -563,8 +575,9 @@ class UpsampledConv3x3:
 
 
 def instnorm_act(x, *, do_norm=True, act=None, act_param=0.0, eps=1e-5, want_f32=False, want_planes=True,
-                 prec=None, out_f32=None, out_planes=None, ws=None):
-    """x: f32 NHWC [N,H,W,C]."""
+                 prec=None, out_f32=None, out_planes=None, ws=None, stats_ready=False):
+    """x: f32 NHWC [N,H,W,C].  stats_ready: `ws` already holds the statistics (accumulated by x's producer)."""
+    assert not stats_ready or ws is not None
     x = _req(x, name="x")
     N, H, W, Cc = x.shape
     if want_f32 and out_f32 is None:
@@ -577,8 +590,8 @@ def instnorm_act(x, *, do_norm=True, act=None, act_param=0.0, eps=1e-5, want_f32
     check(_lib.load().shineon_instnorm_act(_p(x), _p(out_f32), out_planes._ptr(out_planes.hi) if out_planes else _p(None),
                                            out_planes._ptr(out_planes.lo) if out_planes else _p(None), _p(ws), N, H, W, Cc,
                                            out_planes.cstride if out_planes else Cc, float(eps), int(bool(do_norm)),
-                                           ACT[act], float(act_param), out_planes.fmt if out_planes else 0,
-                                           _stream()), "shineon_instnorm_act")
+                                           int(bool(stats_ready)), ACT[act], float(act_param),
+                                           out_planes.fmt if out_planes else 0, _stream()), "shineon_instnorm_act")
     return out_f32, out_planes
 
 
