@@ -297,6 +297,14 @@ int shineon_feature_l2norm(const float* x, float* y, int B, int C, int H, int W,
 int shineon_linear_tanh(const float* x, const float* weight, const float* bias, float* theta, int B, int h,
                         int w, int C, int out_dim, shineon_stream_t stream);
 
+/* TPS warp of the decoded 8-bit cloth [B,H,W,3] (normalised on load like ToTensor + Normalize(0.5, 0.5)): the same
+ * samples as shineon_tps_grid_sample_fwd(cloth f32, border) written (a) as f32 NCHW `warped` [B,3,H,W] and (b) split into
+ * 16-bit hi/lo into the cloth channels of the U-Net stem's space-to-depth planes z [B,H/2+1,W/2+1,z_cstride]:
+ * z[b][Y][X][(py*2+px)*ctot + c_off + c] = warped[b][c][2Y-1+py][2X-1+px]  (ctot channels per position). */
+int shineon_tps_warp_u8_planes(const float* theta, const shineon_tps_tables* tps, const unsigned char* cloth_u8,
+                               float* warped, void* z_hi, void* z_lo, int z_cstride, int ctot, int c_off, int plane_fmt,
+                               int B, int H, int W, shineon_stream_t stream);
+
 /* ------------------------------------------------------------------ */
 /* U5: try-on composition (unet_mask_model.py:74-135)                   */
 /* ------------------------------------------------------------------ */
@@ -465,6 +473,30 @@ typedef struct {
   float cloth_mask_threshold;
 } shineon_frame_prep_params;
 int shineon_frame_prep(const shineon_frame_prep_params* p, shineon_stream_t stream);
+
+/* The same prep written straight into the first layers' operands (TryOnPipeline.run_raw): instead of f32 NCHW tensors
+ * (which torch.cat + shineon_nchw_s2d_planes / shineon_nchw_im2col_planes would re-read and re-write) it emits 16-bit
+ * hi (+ lo) planes, bit-identical to that chain:
+ *   gmm   [F,H/2+1,W/2+1,gmm_cpad]   shifted space-to-depth of cat(agnostic, cocopose)            (WarpModel person input)
+ *   unet  [F,H/2+1,W/2+1,unet_cpad]  the same of cat(agnostic, densepose, cloth'): cloth' (channels 7..9 of each of the
+ *                                    four positions) is left zero for shineon_tps_warp_u8_planes   (U-Net stem input)
+ *   cloth [F,H/2,W/2,cloth_cpad]     im2col (4x4, stride 2, pad 1; k = (fy*4+fx)*3 + c) of the cloth (extractionB stem)
+ * silhouette_scratch: F*H*W bytes (the 8-bit silhouette after Pillow's two resizes). */
+typedef struct {
+  const unsigned char* image;     /* [F,H,W,3] */
+  const unsigned char* parse;     /* [F,H,W]   */
+  const unsigned char* cloth;     /* [F,H,W,3] */
+  const unsigned char* densepose; /* [F,H,W,3] */
+  unsigned char* silhouette_scratch;
+  void *gmm_hi, *gmm_lo, *unet_hi, *unet_lo, *cloth_hi, *cloth_lo; /* lo: all NULL in single-plane modes */
+  int gmm_cpad, unet_cpad, cloth_cpad;
+  int plane_fmt;
+  const int* tab_bounds[4];       /* as in shineon_frame_prep_params */
+  const int* tab_kk[4];
+  int tab_ksize[4];
+  int F, H, W, n_joints;
+} shineon_frame_prep_planes_params;
+int shineon_frame_prep_planes(const shineon_frame_prep_planes_params* p, shineon_stream_t stream);
 
 /* Middlebury .flo payload (the interleaved f32 u,v after the 12-byte header) -> f32 [2,H,W] = (x - 0.5) / 0.5
  * (flownet2_pytorch/utils/flow_utils.py:7-26 + flow_norm, datasets/tryon_dataset.py:121,288-289). */

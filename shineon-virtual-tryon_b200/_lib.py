@@ -56,6 +56,16 @@ class FramePrepParams(C.Structure):
     ]
 
 
+class FramePrepPlanesParams(C.Structure):
+    _fields_ = [
+        ("image", c_p), ("parse", c_p), ("cloth", c_p), ("densepose", c_p), ("silhouette_scratch", c_p),
+        ("gmm_hi", c_p), ("gmm_lo", c_p), ("unet_hi", c_p), ("unet_lo", c_p), ("cloth_hi", c_p), ("cloth_lo", c_p),
+        ("gmm_cpad", c_i), ("unet_cpad", c_i), ("cloth_cpad", c_i), ("plane_fmt", c_i),
+        ("tab_bounds", c_p * 4), ("tab_kk", c_p * 4), ("tab_ksize", c_i * 4),
+        ("F", c_i), ("H", c_i), ("W", c_i), ("n_joints", c_i),
+    ]
+
+
 # name -> argtypes (every function returns int status unless listed in _RESTYPES)
 SIGNATURES = {
     "shineon_version": [],
@@ -88,6 +98,8 @@ SIGNATURES = {
     "shineon_upconv3x3_gather": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_pil_bilinear_coeffs": [c_i, c_i, c_p, c_p],
     "shineon_frame_prep": [C.POINTER(FramePrepParams), c_p],
+    "shineon_frame_prep_planes": [C.POINTER(FramePrepPlanesParams), c_p],
+    "shineon_tps_warp_u8_planes": [c_p, C.POINTER(TpsTables), c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_flo_decode": [c_p, c_p, c_i, c_i, c_p],
     "shineon_instnorm_act": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_i, c_f, c_i, c_p],
     "shineon_upsample2x_cat": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_p],

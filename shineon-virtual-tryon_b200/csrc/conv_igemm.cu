@@ -393,9 +393,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
       epi_bar_sync<kEpiWarps * 32>();
-      // ---- gather the tile's accumulator: one TMEM buffer per K chunk, summed here (round-to-nearest)
+      // ---- all K chunks but the last: partial sums TMEM -> registers (round-to-nearest adds), buffer handed straight back
+      const bool multi = a.num_kb > a.chunk_kb;  // uniform over the launch
       float accr[kNCH][32];
-      for (int kb0 = 0; kb0 < a.num_kb; kb0 += a.chunk_kb, ++it) {
+      for (int kb0 = 0; kb0 + a.chunk_kb < a.num_kb; kb0 += a.chunk_kb, ++it) {
         const int buf = it & 1;
         mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
         tc_fence_after();
@@ -422,23 +423,42 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
         }
-        // hand the accumulator back to the MMA warp
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
       }
-      // ---- bias / activation / folded BN / statistics / stores, from registers (the MMA warp is already on the next tile)
+      // ---- last (or only) chunk: streamed 32 columns at a time straight into bias / activation / folded BN / statistics /
+      // stores (both TMEM loads of a column chunk in flight together: short-mainloop layers are bound by this loop)
+      const int buf = it & 1;
+      mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + buf * kAccCols;
 #pragma unroll 1
       for (int ci = 0; ci < kNCH; ++ci) {
         const int c0 = (2 * ci + half) * kChunk;
         if (c0 >= BN || cn0 + c0 >= a.Cout) break;  // warp-uniform
+        uint32_t v[32], v2[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        if (kChunk == 32) {
+          tmem_ld32(taddr, v);
+          if (kCat) tmem_ld32(taddr + BN, v2);
+        } else {
+          tmem_ld16(taddr, v);
+          if (kCat) tmem_ld16(taddr + BN, v2);
+        }
+        tmem_ld_wait();
         const int cnt = min(kChunk, a.Cout - (cn0 + c0));  // warp-uniform
         float vals[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float acc = accr[0][i];
+          float acc = (i < kChunk) ? __uint_as_float(v[i]) : 0.f;
+          if (kCat && i < kChunk) acc += __uint_as_float(v2[i]);  // hi*hi + lo*hi  +  hi*lo
+          if (multi) {  // earlier chunks' partial sum (register array indexed by the runtime ci through selects)
+            float prev = accr[0][i];
 #pragma unroll
-          for (int k = 1; k < kNCH; ++k) acc = ci == k ? accr[k][i] : acc;
+            for (int k = 1; k < kNCH; ++k) prev = ci == k ? accr[k][i] : prev;
+            acc += prev;
+          }
           vals[i] = (i < kChunk) ? fmaf(acc, a.acc_scale, s_bias[c0 + (i < kChunk ? i : 0)]) : 0.f;
         }
         act_chunk_dispatch(vals, a.pre_act, a.act_param);
@@ -462,6 +482,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         else if (row_ok)
           conv_store_row(vals, cn0 + c0, cnt, pix, a);
       }
+      // hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      ++it;
     }
     if (a.stats != nullptr && ti > 0) {  // the last tile's statistics
       epi_bar_sync<kEpiWarps * 32>();

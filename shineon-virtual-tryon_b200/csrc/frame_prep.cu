@@ -118,16 +118,17 @@ struct ResizeTab {
 };
 
 // One CTA per frame; the three intermediate images live in shared memory (H*w16 + h16*w16 + h16*W bytes).
-__global__ void __launch_bounds__(256)
-    body_silhouette_kernel(const uint8_t* __restrict__ parse, float* __restrict__ out, long out_frame_stride, int H, int W,
-                           ResizeTab dw, ResizeTab dh, ResizeTab uw, ResizeTab uh) {
+__global__ void __launch_bounds__(1024)
+    body_silhouette_kernel(const uint8_t* __restrict__ parse, float* __restrict__ out, long out_frame_stride,
+                           uint8_t* __restrict__ out_u8, int H, int W, ResizeTab dw, ResizeTab dh, ResizeTab uw, ResizeTab uh) {
   extern __shared__ uint8_t sm[];
   const int w16 = W / 16, h16 = H / 16;
   uint8_t* tA = sm;                 // [H][w16]   after the horizontal down pass
   uint8_t* tS = tA + H * w16;       // [h16][w16] after the vertical down pass
   uint8_t* tB = tS + h16 * w16;     // [h16][W]   after the horizontal up pass
   const uint8_t* src = parse + (long)blockIdx.x * H * W;
-  for (int e = threadIdx.x; e < H * w16; e += 256) {
+  const int nt = blockDim.x;  // 1024: one CTA per frame, a single wave -- the kernel's time is one CTA's latency
+  for (int e = threadIdx.x; e < H * w16; e += nt) {
     const int y = e / w16, xx = e - y * w16;
     const int x0 = dw.bounds[2 * xx], cnt = dw.bounds[2 * xx + 1];
     int ss = 1 << 21;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(256)
     tA[e] = pil_clip8(ss);
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < h16 * w16; e += 256) {
+  for (int e = threadIdx.x; e < h16 * w16; e += nt) {
     const int yy = e / w16, xx = e - yy * w16;
     const int y0 = dh.bounds[2 * yy], cnt = dh.bounds[2 * yy + 1];
     int ss = 1 << 21;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(256)
     tS[e] = pil_clip8(ss);
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < h16 * W; e += 256) {
+  for (int e = threadIdx.x; e < h16 * W; e += nt) {
     const int yy = e / W, x = e - yy * W;
     const int x0 = uw.bounds[2 * x], cnt = uw.bounds[2 * x + 1];
     int ss = 1 << 21;
@@ -151,14 +152,111 @@ __global__ void __launch_bounds__(256)
     tB[e] = pil_clip8(ss);
   }
   __syncthreads();
-  float* dst = out + (long)blockIdx.x * out_frame_stride;
-  for (int e = threadIdx.x; e < H * W; e += 256) {
+  float* dst = out ? out + (long)blockIdx.x * out_frame_stride : nullptr;
+  uint8_t* dst8 = out_u8 ? out_u8 + (long)blockIdx.x * H * W : nullptr;
+  for (int e = threadIdx.x; e < H * W; e += nt) {
     const int y = e / W, x = e - y * W;
     const int y0 = uh.bounds[2 * y], cnt = uh.bounds[2 * y + 1];
     int ss = 1 << 21;
     for (int t = 0; t < cnt; ++t) ss += tB[(y0 + t) * W + x] * uh.kk[y * uh.ksize + t];
-    dst[e] = norm_u8(pil_clip8(ss));
+    const uint8_t r = pil_clip8(ss);
+    if (dst) dst[e] = norm_u8(r);
+    if (dst8) dst8[e] = r;
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Frame prep written straight into the first layers' operands (TryOnPipeline.run_raw).  Per frame it produces, from the
+// decoded 8-bit images and the 8-bit silhouette of body_silhouette_kernel,
+//   pg  [F, H/2+1, W/2+1, cg]: shifted space-to-depth planes of cat(agnostic, cocopose)  (WarpModel's person input),
+//   pu  [F, H/2+1, W/2+1, cu]: the same for cat(agnostic, densepose, cloth'): the U-Net stem's input; the three cloth'
+//                              channels are left zero here and filled by tps_warp_u8_planes_kernel,
+//   pc  [F, H/2,   W/2,   cc]: im2col planes (4x4, stride 2, pad 1; k = (fy*4+fx)*3 + c) of the cloth (extractionB's stem),
+// each as 16-bit hi (+ lo) halves -- bit-identical to shineon_frame_prep -> torch.cat -> shineon_nchw_s2d_planes /
+// shineon_nchw_im2col_planes, which this replaces: 1.0 GB written per 80-frame step instead of 2.9 GB moved.
+// One CTA = 32 consecutive X of one (frame, Y): values are assembled as finished plane rows in shared memory, then
+// copied out with fully coalesced 16-byte stores.
+struct PrepPlanesArgs {
+  const uint8_t *image, *parse, *cloth, *densepose, *sil;
+  plane_t *pg_hi, *pg_lo, *pu_hi, *pu_lo, *pc_hi, *pc_lo;
+  int H, W, J, cg, cu, cc, fmt;
+};
+constexpr int kPrepPx = 32;
+
+__global__ void __launch_bounds__(256) frame_prep_planes_kernel(const PrepPlanesArgs a) {
+  extern __shared__ __align__(16) plane_t sm_rows[];
+  const int f = blockIdx.z, Y = blockIdx.y, X0 = blockIdx.x * kPrepPx;
+  const int Hz = a.H / 2 + 1, Wz = a.W / 2 + 1;
+  const int row_hw = a.cg + a.cu + a.cc;         // halfwords per pixel and half (hi or lo)
+  plane_t* s_hi = sm_rows;                        // [kPrepPx][cg | cu | cc]
+  plane_t* s_lo = sm_rows + kPrepPx * row_hw;
+  {  // zero (padding channels, out-of-image taps, the cloth' slots)
+    uint4* z = reinterpret_cast<uint4*>(sm_rows);
+    const int n16 = 2 * kPrepPx * row_hw / 8;
+    for (int i = threadIdx.x; i < n16; i += 256) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  const long fo = (long)f * a.H * a.W;
+  const int cper_g = 4 + a.J, cper_u = 10;
+  auto put = [&](int px, int k, float v) {
+    plane_t h, l;
+    split16(v, a.fmt, h, l);
+    s_hi[px * row_hw + k] = h;
+    s_lo[px * row_hw + k] = l;
+  };
+  if (threadIdx.x < 4 * kPrepPx) {  // (pixel, position q): the person channels of pg and pu
+    const int px = threadIdx.x >> 2, q = threadIdx.x & 3;
+    const int X = X0 + px;
+    const int iy = 2 * Y - 1 + (q >> 1), ix = 2 * X - 1 + (q & 1);
+    if (X < Wz && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
+      const long p = fo + (long)iy * a.W + ix;
+      const uint32_t lab = a.parse[p];
+      const float ph = (lab < 32 && ((kHeadMask >> lab) & 1u)) ? 1.f : 0.f;
+      float agn[4];
+      agn[0] = norm_u8(a.sil[p]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)  // im * phead - (1 - phead)
+        agn[1 + c] = __fsub_rn(__fmul_rn(norm_u8(a.image[p * 3 + c]), ph), __fsub_rn(1.f, ph));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        put(px, q * cper_g + c, agn[c]);
+        put(px, a.cg + q * cper_u + c, agn[c]);
+      }
+      for (int j = 0; j < a.J; ++j) put(px, q * cper_g + 4 + j, -1.f);  // cocopose maps: constant -1 as the reference writes them
+#pragma unroll
+      for (int c = 0; c < 3; ++c) put(px, a.cg + q * cper_u + 4 + c, norm_u8(a.densepose[p * 3 + c]));
+    }
+  }
+  for (int it = threadIdx.x; it < 16 * kPrepPx; it += 256) {  // (pixel, filter tap): the cloth's im2col row
+    const int px = it >> 4, tap = it & 15;
+    const int X = X0 + px;
+    const int iy = 2 * Y - 1 + (tap >> 2), ix = 2 * X - 1 + (tap & 3);
+    if (Y < a.H / 2 && X < a.W / 2 && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
+      const long p = fo + (long)iy * a.W + ix;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) put(px, a.cg + a.cu + tap * 3 + c, norm_u8(a.cloth[p * 3 + c]));
+    }
+  }
+  __syncthreads();
+  // coalesced copy-out: per destination tensor, 16-byte units of the CTA's contiguous row segment
+  const int nz = min(kPrepPx, Wz - X0), nc = (Y < a.H / 2) ? max(0, min(kPrepPx, a.W / 2 - X0)) : 0;
+  auto copy_out = [&](plane_t* dst_hi, plane_t* dst_lo, int cw, int soff, long row0, int npx) {
+    if (!dst_hi || npx <= 0) return;
+    const int u_per_px = cw / 8;
+    for (int i = threadIdx.x; i < npx * u_per_px; i += 256) {
+      const int px = i / u_per_px, u = i - px * u_per_px;
+      const uint4 vh = *reinterpret_cast<const uint4*>(s_hi + px * row_hw + soff + u * 8);
+      *reinterpret_cast<uint4*>(dst_hi + (row0 + px) * cw + u * 8) = vh;
+      if (dst_lo) {
+        const uint4 vl = *reinterpret_cast<const uint4*>(s_lo + px * row_hw + soff + u * 8);
+        *reinterpret_cast<uint4*>(dst_lo + (row0 + px) * cw + u * 8) = vl;
+      }
+    }
+  };
+  const long zrow = ((long)f * Hz + Y) * Wz + X0;
+  copy_out(a.pg_hi, a.pg_lo, a.cg, 0, zrow, nz);
+  copy_out(a.pu_hi, a.pu_lo, a.cu, a.cg, zrow, nz);
+  copy_out(a.pc_hi, a.pc_lo, a.cc, a.cg + a.cu, ((long)f * (a.H / 2) + Y) * (a.W / 2) + X0, nc);
 }
 
 // im_cocopose: union of the filled squares ImageDraw.rectangle((x-r, y-r, x+r, y+r)) draws for joints with x > 1, y > 1
@@ -266,7 +364,7 @@ extern "C" int shineon_frame_prep(const shineon_frame_prep_params* p, shineon_st
     for (int i = 0; i < 4; ++i) t[i] = ResizeTab{p->tab_bounds[i], p->tab_kk[i], p->tab_ksize[i]};
     const size_t smem = (size_t)p->H * (p->W / 16) + (size_t)(p->H / 16) * (p->W / 16) + (size_t)(p->H / 16) * p->W;
     SHINEON_REQUIRE(smem <= 48 * 1024, "frame_prep: frame too large for the silhouette kernel");
-    body_silhouette_kernel<<<p->F, 256, smem, st>>>(p->parse, p->agnostic_out, (long)4 * HW, p->H, p->W, t[0], t[1], t[2], t[3]);
+    body_silhouette_kernel<<<p->F, 1024, smem, st>>>(p->parse, p->agnostic_out, (long)4 * HW, nullptr, p->H, p->W, t[0], t[1], t[2], t[3]);
     rc = after_launch("body_silhouette_kernel");
     if (rc) return rc;
   }
@@ -276,6 +374,46 @@ extern "C" int shineon_frame_prep(const shineon_frame_prep_params* p, shineon_st
     if (rc) return rc;
   }
   return SHINEON_OK;
+}
+
+extern "C" int shineon_frame_prep_planes(const shineon_frame_prep_planes_params* p, shineon_stream_t stream) {
+  SHINEON_REQUIRE(p != nullptr, "frame_prep_planes: null params");
+  SHINEON_REQUIRE(p->F > 0 && p->F <= 65535 && p->H > 0 && p->W > 0 && p->H % 16 == 0 && p->W % 16 == 0,
+                  "frame_prep_planes: bad shape (H, W multiples of 16)");
+  SHINEON_REQUIRE(p->image && p->parse && p->cloth && p->densepose && p->silhouette_scratch, "frame_prep_planes: null input");
+  SHINEON_REQUIRE(p->gmm_hi && p->unet_hi && p->cloth_hi, "frame_prep_planes: null output");
+  SHINEON_REQUIRE((p->gmm_lo == nullptr) == (p->unet_lo == nullptr) && (p->gmm_lo == nullptr) == (p->cloth_lo == nullptr),
+                  "frame_prep_planes: lo planes must be all present or all absent");
+  SHINEON_REQUIRE(p->plane_fmt == SHINEON_FMT_BF16 || p->plane_fmt == SHINEON_FMT_FP16, "frame_prep_planes: plane_fmt %d", p->plane_fmt);
+  SHINEON_REQUIRE(p->n_joints >= 0 && p->n_joints <= 64, "frame_prep_planes: n_joints");
+  SHINEON_REQUIRE(p->gmm_cpad % 8 == 0 && p->gmm_cpad >= 4 * (4 + p->n_joints) && p->unet_cpad % 8 == 0 && p->unet_cpad >= 40 &&
+                      p->cloth_cpad % 8 == 0 && p->cloth_cpad >= 48, "frame_prep_planes: channel pads too small / not multiples of 8");
+  SHINEON_REQUIRE(p->tab_bounds[0] && p->tab_kk[0] && p->tab_bounds[1] && p->tab_kk[1] && p->tab_bounds[2] && p->tab_kk[2] &&
+                      p->tab_bounds[3] && p->tab_kk[3], "frame_prep_planes: resize tables missing (shineon_pil_bilinear_coeffs)");
+  cudaStream_t st = (cudaStream_t)stream;
+  ResizeTab t[4];
+  for (int i = 0; i < 4; ++i) t[i] = ResizeTab{p->tab_bounds[i], p->tab_kk[i], p->tab_ksize[i]};
+  const size_t smem_s = (size_t)p->H * (p->W / 16) + (size_t)(p->H / 16) * (p->W / 16) + (size_t)(p->H / 16) * p->W;
+  SHINEON_REQUIRE(smem_s <= 48 * 1024, "frame_prep_planes: frame too large for the silhouette kernel");
+  body_silhouette_kernel<<<p->F, 1024, smem_s, st>>>(p->parse, nullptr, 0, p->silhouette_scratch, p->H, p->W, t[0], t[1], t[2], t[3]);
+  int rc = after_launch("body_silhouette_kernel");
+  if (rc) return rc;
+  PrepPlanesArgs a;
+  a.image = p->image; a.parse = p->parse; a.cloth = p->cloth; a.densepose = p->densepose; a.sil = p->silhouette_scratch;
+  a.pg_hi = (plane_t*)p->gmm_hi; a.pg_lo = (plane_t*)p->gmm_lo; a.pu_hi = (plane_t*)p->unet_hi; a.pu_lo = (plane_t*)p->unet_lo;
+  a.pc_hi = (plane_t*)p->cloth_hi; a.pc_lo = (plane_t*)p->cloth_lo;
+  a.H = p->H; a.W = p->W; a.J = p->n_joints; a.cg = p->gmm_cpad; a.cu = p->unet_cpad; a.cc = p->cloth_cpad; a.fmt = p->plane_fmt;
+  const size_t smem = (size_t)2 * kPrepPx * (a.cg + a.cu + a.cc) * sizeof(plane_t);
+  static bool opted = false;
+  if (!opted && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(frame_prep_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "frame_prep_planes: shared memory opt-in: %s", cudaGetErrorString(e));
+    opted = true;
+  }
+  SHINEON_REQUIRE(smem <= 96 * 1024, "frame_prep_planes: channel pads too large");
+  dim3 grid(cdiv(p->W / 2 + 1, kPrepPx), p->H / 2 + 1, p->F);
+  frame_prep_planes_kernel<<<grid, 256, smem, st>>>(a);
+  return after_launch("frame_prep_planes_kernel");
 }
 
 extern "C" int shineon_flo_decode(const void* flo_payload, float* out, int H, int W, shineon_stream_t stream) {

@@ -603,6 +603,128 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---------------------------------------------------------------------------------------------
+// TPS warp of the cloth for the uint8 pipeline (TryOnPipeline.run_raw): the same batched TPS + grid_sample(border) as
+// tps_grid_sample_fast_kernel<N, 3, BORDER>, but
+//   * the source is the decoded 8-bit cloth [B,H,W,3] (channel-last), normalised on load exactly like
+//     ToTensor + Normalize(0.5, 0.5) do (frame_prep.cu norm_u8), so the f32 cloth tensor is never materialised;
+//   * besides the f32 NCHW warped cloth (read again by the compose kernel) every sample is also written, split into 16-bit
+//     hi/lo halves, into the cloth channels of the U-Net stem's space-to-depth planes
+//       z[b][Y][X][(py*2+px)*ctot + c_off + c] = x[c][2Y-1+py][2X-1+px]   (norm_act.cu nchw_s2d_planes_kernel)
+//     whose person channels the frame-prep kernel filled: torch.cat + the layout pass disappear from the step.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float norm_u8_tps(uint8_t u) {
+  return __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.f), 0.5f), 0.5f);
+}
+
+template <int N>
+__global__ void __launch_bounds__(128)
+    tps_warp_u8_planes_kernel(const float* __restrict__ theta, TpsTablesDev t, const uint8_t* __restrict__ cloth,
+                              float* __restrict__ out, plane_t* __restrict__ zh, plane_t* __restrict__ zl, int zc, int ctot,
+                              int c_off, int fmt, int B, int H, int W, int chunk) {
+  __shared__ float sQ[kTpsChunk][2 * N];
+  __shared__ float2 sWxy[kTpsChunk][N];
+  __shared__ float sA[kTpsChunk][6];
+  __shared__ float sP[2 * N];
+  const int b0 = blockIdx.y * chunk;
+  const int nb = min(chunk, B - b0);
+  constexpr int L = N + 3;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    sP[i] = t.P_X[i];
+    sP[N + i] = t.P_Y[i];
+  }
+  for (int e = threadIdx.x; e < nb * 2 * N; e += blockDim.x) {
+    const int bi = e / (2 * N), k = e - bi * 2 * N;
+    sQ[bi][k] = theta[(long)(b0 + bi) * 2 * N + k] + (k < N ? t.P_X[k] : t.P_Y[k - N]);  // warp.py:207-210
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nb * 2 * L; e += blockDim.x) {
+    const int bi = e / (2 * L), r = e - bi * 2 * L;
+    const int xy = r / L, row = r - xy * L;
+    const float* q = sQ[bi] + xy * N;
+    const float* li = t.Li + row * L;
+    float acc = 0.f;
+    for (int k = 0; k < N; ++k) acc = fmaf(li[k], q[k], acc);
+    if (row < N) {
+      if (xy == 0) sWxy[bi][row].x = acc; else sWxy[bi][row].y = acc;
+    } else {
+      sA[bi][xy * 3 + (row - N)] = acc;
+    }
+  }
+  __syncthreads();
+  const int HW = H * W;
+  const int pA = blockIdx.x * 256 + threadIdx.x, pB = pA + 128;
+  if (pA >= HW) return;
+  const bool hasB = pB < HW;
+  const int pBc = hasB ? pB : pA;
+  const int yy[2] = {pA / W, pBc / W};
+  const int xx[2] = {pA - yy[0] * W, pBc - yy[1] * W};
+  const float pxA = t.grid_X[xx[0]], pyA = t.grid_Y[yy[0]], pxB = t.grid_X[xx[1]], pyB = t.grid_Y[yy[1]];
+  float UA[N], UB[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    const float cx = sP[n], cy = sP[N + n];
+    float dx = pxA - cx, dy = pyA - cy;
+    float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (d2 == 0.f) d2 = 1.f;  // warp.py:290
+    UA[n] = d2 * logf(d2);
+    dx = pxB - cx; dy = pyB - cy;
+    d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    if (d2 == 0.f) d2 = 1.f;
+    UB[n] = d2 * logf(d2);
+  }
+  // where the two pixels land in the space-to-depth planes (element offsets of channel 0 of the cloth group)
+  const int Wz = W / 2 + 1, Hz = H / 2 + 1;
+  long zoff[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int Y = (yy[k] + 1) >> 1, py = (yy[k] + 1) & 1, X = (xx[k] + 1) >> 1, px = (xx[k] + 1) & 1;
+    zoff[k] = ((long)Y * Wz + X) * zc + (py * 2 + px) * ctot + c_off;
+  }
+  for (int bi = 0; bi < nb; ++bi) {
+    float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const float2 w = sWxy[bi][n];
+      sa = __ffma2_rn(w, make_float2(UA[n], UA[n]), sa);
+      sb = __ffma2_rn(w, make_float2(UB[n], UB[n]), sb);
+    }
+    const float a0 = sA[bi][0], a1 = sA[bi][1], a2 = sA[bi][2], a3 = sA[bi][3], a4 = sA[bi][4], a5 = sA[bi][5];
+    const float gx[2] = {a0 + a1 * pxA + a2 * pyA + sa.x, a0 + a1 * pxB + a2 * pyB + sb.x};  // warp.py:303-316
+    const float gy[2] = {a3 + a4 * pxA + a5 * pyA + sa.y, a3 + a4 * pxB + a5 * pyB + sb.y};
+    const int b = b0 + bi;
+    const uint8_t* src = cloth + (long)b * HW * 3;
+    TapFast tp[2];
+    uint8_t u[2][4][3];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      tp[k] = make_tap_fast<SHINEON_PAD_BORDER>(gx[k], gy[k], H, W);  // byte offsets of f32 planes: /4 = pixel index
+      const unsigned o[4] = {tp[k].o00 >> 2, tp[k].o01 >> 2, tp[k].o10 >> 2, tp[k].o11 >> 2};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) u[k][j][c] = __ldg(src + o[j] * 3u + c);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k == 1 && !hasB) break;
+      const int p = k == 0 ? pA : pB;
+      plane_t* zhb = zh + (long)b * Hz * Wz * zc + zoff[k];
+      plane_t* zlb = zl ? zl + (long)b * Hz * Wz * zc + zoff[k] : nullptr;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v[4] = {norm_u8_tps(u[k][0][c]), norm_u8_tps(u[k][1][c]), norm_u8_tps(u[k][2][c]), norm_u8_tps(u[k][3][c])};
+        const float r = blend_taps(v, tp[k]);
+        out[((long)b * 3 + c) * HW + p] = r;
+        plane_t hh, ll;
+        split16(r, fmt, hh, ll);
+        zhb[c] = hh;
+        if (zlb) zlb[c] = ll;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Resample2d  (resample2d_kernel.cu).  kernel_size == 1 (the only value the reference uses).
 // One thread per output pixel; the flow is read once and reused for every channel.
 // ---------------------------------------------------------------------------------------------
@@ -956,4 +1078,28 @@ extern "C" int shineon_channelnorm_bwd(const float* in, const float* out, const 
   int blocks = (int)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256);
   channelnorm_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, grad_out, grad_in, C, (long)H * W, total);
   return after_launch("channelnorm_bwd_kernel");
+}
+
+extern "C" int shineon_tps_warp_u8_planes(const float* theta, const shineon_tps_tables* tps, const unsigned char* cloth_u8,
+                                          float* warped, void* z_hi, void* z_lo, int z_cstride, int ctot, int c_off,
+                                          int plane_fmt, int B, int H, int W, shineon_stream_t stream) {
+  SHINEON_REQUIRE(theta && tps && cloth_u8 && warped && z_hi, "tps_warp_u8_planes: null pointer");
+  SHINEON_REQUIRE(tps->Li && tps->P_X && tps->P_Y && tps->grid_X && tps->grid_Y, "tps_warp_u8_planes: null table");
+  SHINEON_REQUIRE(plane_fmt == SHINEON_FMT_BF16 || plane_fmt == SHINEON_FMT_FP16, "tps_warp_u8_planes: plane_fmt %d", plane_fmt);
+  SHINEON_REQUIRE(B >= 0 && B <= 65535 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "tps_warp_u8_planes: bad shape (H, W even)");
+  SHINEON_REQUIRE(ctot >= 3 && c_off >= 0 && c_off + 3 <= ctot && 4 * ctot <= z_cstride, "tps_warp_u8_planes: channel window");
+  if (B == 0) return SHINEON_OK;
+  const int N = tps->grid_size * tps->grid_size;
+  const int chunk = B >= 64 ? kTpsChunk : (B >= 16 ? 8 : 2);
+  dim3 grid(cdiv(H * W, 256), cdiv(B, chunk));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N == 25)
+    tps_warp_u8_planes_kernel<25><<<grid, 128, 0, st>>>(theta, to_dev(tps), cloth_u8, warped, (plane_t*)z_hi, (plane_t*)z_lo,
+                                                         z_cstride, ctot, c_off, plane_fmt, B, H, W, chunk);
+  else if (N == 9)
+    tps_warp_u8_planes_kernel<9><<<grid, 128, 0, st>>>(theta, to_dev(tps), cloth_u8, warped, (plane_t*)z_hi, (plane_t*)z_lo,
+                                                        z_cstride, ctot, c_off, plane_fmt, B, H, W, chunk);
+  else
+    return fail(SHINEON_ERR_UNSUPPORTED, "tps_warp_u8_planes: grid_size %d (3 and 5 are compiled)", tps->grid_size);
+  return after_launch("tps_warp_u8_planes_kernel");
 }

@@ -59,6 +59,14 @@ class UnetMaskModel(BaseModel):
         res = self._forward(person_representation, warped_cloths, flows, want_u8=True, want_f32=f32_outputs)
         return (res[4],) + tuple(res[:4]) if f32_outputs else res[4]
 
+    def forward_u8_planes(self, unet_in, warped_cloths):
+        """forward_u8 when the stem's operand already exists as space-to-depth planes (ops.S2dInput written by
+        ops.frame_prep_planes + TpsGridGen.warp_u8): cat([person, warped_cloths], 1) is never materialised."""
+        prec = ops.resolve_precision(self.unet.precision)
+        assert unet_in.planes.prec == prec, "stem operand precision differs from the model's"
+        out = self.unet.model.run(unet_in, prec)
+        return self._compose(out, warped_cloths.contiguous(), None, want_u8=True, want_f32=False)[4]
+
     def _forward(self, person_representation, warped_cloths, flows=None, want_u8=False, want_f32=True):
         n = self.hparams.n_frames_total
         flow_warp = bool(self.hparams.flow_warp)

@@ -43,6 +43,7 @@ class WarpModel(BaseModel):
         self.regression.precision = precision
 
     def regress_theta(self, inputA, inputB):
+        """inputA / inputB: f32 NCHW tensors, or the two stems' operands from ops.frame_prep_planes."""
         featureA = self.extractionA.forward_nhwc(inputA)
         featureB = self.extractionB.forward_nhwc(inputB)
         _, corr = self.correlation.forward_fused(featureA, featureB, prec=ops.resolve_precision(self.precision))

@@ -311,12 +311,16 @@ class UnetSkipConnectionBlock(nn.Module):
         sc, sh = bn if bn is not None else (None, None)
         dc, uc = pr["downconv"], pr["upconv"]
         low = self._lowres(pk, prec)
-        N_ = a_in[0].shape[0] if isinstance(a_in, tuple) else a_in.N
-        dev = a_in[0].device if isinstance(a_in, tuple) else a_in.hi.device
-        if isinstance(a_in, tuple):
+        s2d_in = a_in if isinstance(a_in, ops.S2dInput) else None  # the stem's operand, built by ops.frame_prep_planes
+        if s2d_in is not None:
+            assert self.outermost and isinstance(pk.get("down_first"), ops.S2dConv) and s2d_in.C == pk["down_first"].Cin, \
+                "S2dInput does not match this U-Net's first layer"
+            N_, dev, hin, win = s2d_in.N, s2d_in.planes.hi.device, s2d_in.H, s2d_in.W
+        elif isinstance(a_in, tuple):
+            N_, dev = a_in[0].shape[0], a_in[0].device
             hin, win = a_in[0].shape[2:]
         else:
-            hin, win = a_in.H, a_in.W
+            N_, dev, hin, win = a_in.N, a_in.hi.device, a_in.H, a_in.W
         # a down conv with neither norm nor attention behind it (outermost / innermost block): bias + the next layer's
         # activation in the conv epilogue, planes written straight into the concat buffer -- no f32 round trip
         direct_planes = (low is not None and pr["downnorm"] is None and pr["attn_down"] is None and bn is None
@@ -331,7 +335,9 @@ class UnetSkipConnectionBlock(nn.Module):
                        **(dict(out_planes=cat.window(0, pk["cat_geom"][0])) if cat is not None else dict(want_planes=True)))
         else:
             okw = dict(scale=sc, shift=sh, want_f32=True)
-        if isinstance(a_in, tuple) and pk["down_i2c"] is not None:
+        if s2d_in is not None:
+            f32, a_mid = pk["down_first"].conv_planes(s2d_in.planes, **okw)
+        elif isinstance(a_in, tuple) and pk["down_i2c"] is not None:
             f32, a_mid = pk["down_first"].conv(a_in[0], a_in[1], **okw)
         else:
             if isinstance(a_in, tuple):

@@ -65,15 +65,28 @@ class FeatureExtraction(nn.Module):
         return layers
 
     def forward_nhwc(self, x):
-        """x f32 NCHW -> f32 NHWC features (conv -> ReLU -> BN ... conv -> ReLU, warp.py:13-31)."""
+        """x f32 NCHW -> f32 NHWC features (conv -> ReLU -> BN ... conv -> ReLU, warp.py:13-31).
+        x may also be the stem's operand built elsewhere (ops.frame_prep_planes): an ops.S2dInput for the space-to-depth
+        stem, or the im2col Planes for the 3-channel stem."""
         prec = ops.resolve_precision(self.precision)
         layers = self._layers(prec)
         first = layers[0][3]
-        a = None if first is not None else ops.nchw_to_planes(x.contiguous(), prec=prec)
+        prebuilt = None
+        if isinstance(x, ops.S2dInput):
+            assert isinstance(first, ops.S2dConv) and x.C == first.Cin, "stem operand does not match this network's first layer"
+            prebuilt = x.planes
+        elif isinstance(x, ops.Planes):
+            assert isinstance(first, ops.Im2colConv) and x.cpad == first.pc.cin_pad, "stem operand does not match the first layer"
+            prebuilt = x
+        else:
+            x = x.contiguous()
+        a = None if first is not None else ops.nchw_to_planes(x, prec=prec)
         for li, (pc, sc, sh, i2c) in enumerate(layers):
             last = li == len(layers) - 1
-            if i2c is not None:  # tiny-Cin stem: im2col tile built in shared memory by the kernel's producer warps
-                f32, a = i2c.conv(x.contiguous(), scale=sc, shift=sh, pre_act="relu", want_f32=last, want_planes=not last)
+            if i2c is not None and prebuilt is not None:
+                f32, a = ops.conv2d(prebuilt, i2c.pc, scale=sc, shift=sh, pre_act="relu", want_f32=last, want_planes=not last)
+            elif i2c is not None:  # tiny-Cin stem: layout pass (space-to-depth / im2col planes) + GEMM
+                f32, a = i2c.conv(x, scale=sc, shift=sh, pre_act="relu", want_f32=last, want_planes=not last)
             else:
                 f32, a = ops.conv2d(a, pc, scale=sc, shift=sh, pre_act="relu", want_f32=last, want_planes=not last)
         return f32
@@ -196,6 +209,11 @@ class TpsGridGen(nn.Module):
         if theta.dim() == 4:
             theta = theta.reshape(theta.shape[0], -1)
         return ops.tps_grid(theta.contiguous(), self.tables(theta.device), self.out_h, self.out_w)
+
+    def warp_u8(self, theta, cloth_u8, unet_in):
+        """Fused TPS + grid_sample(border) of the decoded 8-bit cloth [B,H,W,3]: returns the f32 NCHW warped cloth and
+        writes the same samples into the cloth' channels of the U-Net stem operand (ops.tps_warp_u8_planes)."""
+        return ops.tps_warp_u8_planes(theta.contiguous(), self.tables(theta.device), cloth_u8, unet_in)
 
     def warp(self, theta, inputs, want_grid=False):
         """Fused TPS + grid_sample: inputs = [(tensor [B,C,H,W], padding_mode), ...] (<= 3)."""

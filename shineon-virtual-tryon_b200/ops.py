@@ -987,6 +987,57 @@ class FramePrep:
         return out
 
 
+class S2dInput:
+    """Shifted space-to-depth planes of an f32 NCHW tensor [N,C,H,W] that never existed as such (FramePrep.planes +
+    tps_warp_u8_planes write them directly): what S2dConv.prepare would have produced."""
+
+    def __init__(self, planes, C, H, W):
+        self.planes, self.C, self.H, self.W = planes, C, H, W
+        self.N = planes.N
+
+
+def frame_prep_planes(prep, parse, cloth, densepose, image, prec=None):
+    """FramePrep fused with the first layers' layout passes (TryOnPipeline.run_raw): decoded 8-bit frames -> the three
+    stem operands as 16-bit planes, bit-identical to prep(...) -> torch.cat -> S2dConv.prepare / Im2colConv.prepare:
+      gmm_person  S2dInput of cat(agnostic, cocopose)              [F, 4+J, H, W]
+      unet_in     S2dInput of cat(agnostic, densepose, cloth')     [F, 10, H, W]   (cloth' slots zero: tps_warp_u8_planes)
+      cloth_i2c   Planes [F, H/2, W/2, 64]: im2col (4x4 s2 p1) of the cloth."""
+    for name, t, nd in (("parse", parse, 3), ("cloth", cloth, 4), ("densepose", densepose, 4), ("image", image, 4)):
+        _req(t, torch.uint8, name)
+        assert t.dim() == nd and tuple(t.shape[1:3]) == (prep.H, prep.W), f"{name}: shape {tuple(t.shape)}"
+    F, H, W, J = parse.shape[0], prep.H, prep.W, prep.J
+    dev = parse.device
+    fmt, split = resolve_precision(prec)
+    pg = Planes(F, H // 2 + 1, W // 2 + 1, 4 * (4 + J), prec=(fmt, split), device=dev, zero_pad=False)
+    pu = Planes(F, H // 2 + 1, W // 2 + 1, 40, prec=(fmt, split), device=dev, zero_pad=False)
+    pc = Planes(F, H // 2, W // 2, 48, prec=(fmt, split), device=dev, zero_pad=False)
+    sil = torch.empty(F, H, W, dtype=torch.uint8, device=dev)
+    p = _lib.FramePrepPlanesParams()
+    p.image, p.parse, p.cloth, p.densepose, p.silhouette_scratch = _p(image), _p(parse), _p(cloth), _p(densepose), _p(sil)
+    p.gmm_hi, p.gmm_lo, p.unet_hi, p.unet_lo, p.cloth_hi, p.cloth_lo = _p(pg.hi), _p(pg.lo), _p(pu.hi), _p(pu.lo), _p(pc.hi), _p(pc.lo)
+    p.gmm_cpad, p.unet_cpad, p.cloth_cpad, p.plane_fmt = pg.cpad, pu.cpad, pc.cpad, fmt
+    for i, (b, k, ks) in enumerate(prep._tabs):
+        p.tab_bounds[i], p.tab_kk[i], p.tab_ksize[i] = b.data_ptr(), k.data_ptr(), ks
+    p.F, p.H, p.W, p.n_joints = F, H, W, J
+    check(_lib.load().shineon_frame_prep_planes(C.byref(p), _stream()), "shineon_frame_prep_planes")
+    return {"gmm_person": S2dInput(pg, 4 + J, H, W), "unet_in": S2dInput(pu, 10, H, W), "cloth_i2c": pc}
+
+
+def tps_warp_u8_planes(theta, tables, cloth_u8, unet_in, c_off=7):
+    """TPS warp (border padding) of the decoded 8-bit cloth [B,H,W,3]: returns the f32 NCHW warped cloth and fills the cloth'
+    channels [c_off, c_off+3) of the U-Net stem operand `unet_in` (S2dInput)."""
+    theta = _req(theta, name="theta")
+    _req(cloth_u8, torch.uint8, "cloth_u8")
+    B, H, W, _ = cloth_u8.shape
+    z = unet_in.planes
+    assert (unet_in.H, unet_in.W, z.N) == (H, W, B) and z.coffset == 0
+    warped = torch.empty(B, 3, H, W, dtype=torch.float32, device=theta.device)
+    check(_lib.load().shineon_tps_warp_u8_planes(_p(theta), C.byref(tables.struct), _p(cloth_u8), _p(warped), _p(z.hi), _p(z.lo),
+                                                 z.cstride, unet_in.C, c_off, z.fmt, B, H, W, _stream()),
+          "shineon_tps_warp_u8_planes")
+    return warped
+
+
 def flo_decode(flo_bytes, device="cuda"):
     """Middlebury .flo file content (bytes / uint8 tensor on the host) -> normalised flow f32 [2,H,W] on the device
     (flow_utils.readFlow + flow_norm, datasets/tryon_dataset.py:121,288-289).  Header errors raise like the reference."""

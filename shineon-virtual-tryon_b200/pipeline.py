@@ -54,7 +54,20 @@ class TryOnPipeline:
         cache = self.__dict__.setdefault("_raw_fns", {})
         key = (id(prep), bool(u8_out))
         if key not in cache:
+            def stages_fused(parse, cloth, densepose, image):
+                # frame prep writes the three stem operands directly; the sampler reads the 8-bit cloth and fills the
+                # U-Net operand's cloth channels: no f32 dataset tensors, no torch.cat, no layout passes
+                from . import ops
+
+                b = ops.frame_prep_planes(prep, parse, cloth, densepose, image, prec=ops.resolve_precision(self.warp_model.precision))
+                theta = self.warp_model.regress_theta(b["gmm_person"], b["cloth_i2c"])
+                warped = self.warp_model.gridGen.warp_u8(theta, cloth, b["unet_in"])
+                u8 = self.tom_model.forward_u8_planes(b["unet_in"], warped)
+                return (u8.view(u8.shape[0], u8.shape[2], u8.shape[3], 3),)
+
             def stages(parse, cloth, densepose, image):
+                if u8_out and self.FUSED_PREP and self._fused_prep_ok(prep):
+                    return stages_fused(parse, cloth, densepose, image)
                 b = prep(parse, cloth, densepose, image)
                 person_gmm = torch.cat([b["agnostic"], b["cocopose"]], 1)
                 person_tom = torch.cat([b["agnostic"], b["densepose"]], 1)
@@ -66,6 +79,28 @@ class TryOnPipeline:
 
             cache[key] = (stages, prep)  # keeps `prep` alive so its id stays unique
         return cache[key][0]
+
+    # True: run_raw / run_host_raw(u8_out=True) use the fused frame-prep -> stem-operand path (ops.frame_prep_planes);
+    # False keeps prep -> f32 tensors -> torch.cat -> layout kernels (same results bit for bit; A/B and tests)
+    FUSED_PREP = True
+
+    def _fused_prep_ok(self, prep):
+        """The fused path covers the reference recipe's stems: WarpModel on agnostic+cocopose / 3-channel cloth, U-Net on
+        agnostic+densepose+cloth (10 channels), one frame per sample, same precision in both models."""
+        from . import ops
+        from .networks.cpvton.warp import FeatureExtraction  # noqa: F401
+
+        w, t = self.warp_model, self.tom_model
+        try:
+            ok = (list(w.hparams.person_inputs) == ["agnostic", "cocopose"] and list(t.hparams.person_inputs) == ["agnostic", "densepose"]
+                  and list(w.hparams.cloth_inputs) == ["cloth"] and list(t.hparams.cloth_inputs) == ["cloth"]
+                  and w.extractionA.model[0].in_channels == 4 + prep.J and w.extractionB.model[0].in_channels == 3
+                  and t.unet.model._parts["downconv"].in_channels == 10 and t.hparams.n_frames_total == 1
+                  and ops.resolve_precision(w.precision) == ops.resolve_precision(t.unet.precision)
+                  and w.gridGen.grid_size in (3, 5))
+        except AttributeError:
+            return False
+        return ok
 
     # ------------------------------------------------------------------ CUDA-graph cache
     def _weights_signature(self):

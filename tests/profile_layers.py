@@ -11,6 +11,14 @@ from shineon_virtual_tryon_b200.pipeline import TryOnPipeline  # noqa: E402
 
 
 def main():
+    # A/B switches: SHINEON_ACC_CHUNK (ops.ACC_CHUNK_KB), SHINEON_FUSE_STATS=0 (separate InstanceNorm statistics pass)
+    if "SHINEON_ACC_CHUNK" in os.environ:
+        ops.ACC_CHUNK_KB = int(os.environ["SHINEON_ACC_CHUNK"])
+    if os.environ.get("SHINEON_FUSE_STATS") == "0":
+        from shineon_virtual_tryon_b200.networks.cpvton.unet import UnetSkipConnectionBlock
+
+        UnetSkipConnectionBlock.FUSE_STATS = False
+    print(f"ACC_CHUNK_KB={ops.ACC_CHUNK_KB} FUSE_STATS={os.environ.get('SHINEON_FUSE_STATS', '1')}")
     clips = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     prec = sys.argv[2] if len(sys.argv) > 2 else "fp16x3"
     dev = torch.device("cuda")
@@ -19,14 +27,20 @@ def main():
     pipe.set_precision(prec)
     frames = clips * 5
     a, c, p = (t.to(dev) for t in bench.synth_inputs(frames, 1))
+    if os.environ.get("SHINEON_RAW") == "1":  # the uint8 path bench.py times (frame prep fused into the stems' operands)
+        raw = [bench.synth_raw_frames(frames, 1, pinned=False)[k].to(dev) for k in TryOnPipeline.RAW_KEYS]
+        prep = ops.FramePrep(256, 192, device=dev)
+        call = lambda: pipe.run_raw(*raw, prep)
+    else:
+        call = lambda: pipe(a, c, p)
     for _ in range(3):
-        pipe(a, c, p)
+        call()
     torch.cuda.synchronize()
     prof = []
     ops.PROFILE = prof
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    pipe(a, c, p)
+    call()
     e1.record()
     ops.PROFILE = None
     torch.cuda.synchronize()

@@ -114,3 +114,51 @@ def test_raw_frame_entry_point_matches_tensor_entry_point(cuda):
     assert graphed.replayed_launches > 0
     pipe.host_sync()
     graphed.host_sync()
+
+
+def test_fused_prep_writes_the_stem_operands_bit_exactly(cuda):
+    """ops.frame_prep_planes + ops.tps_warp_u8_planes == FramePrep -> torch.cat -> space-to-depth / im2col layout kernels
+    (+ tps_grid_sample for the cloth), halfword for halfword, in both plane formats; and TryOnPipeline's fused raw path
+    returns the same bytes as the unfused one, eager and replayed."""
+    from shineon_virtual_tryon_b200 import ops
+    from shineon_virtual_tryon_b200.pipeline import TryOnPipeline
+    from tests.util import build_model
+
+    fr, image, parse, cloth, densepose, pose = _frames([31, 32, 33])
+    dev = [t.cuda() for t in (parse, cloth, densepose, image)]
+    prep = ops.FramePrep(H, W)
+    warp, _ = build_model("warp")
+    tom, _ = build_model("unet_mask")
+    for prec in ("fp16x3", "bf16x3", "bf16"):
+        pr = ops.resolve_precision(prec)
+        b = prep(*dev)
+        fused = ops.frame_prep_planes(prep, *dev, prec=pr)
+        # reference operands through the unfused kernels
+        s2d_g = ops.S2dConv(torch.zeros(64, 22, 4, 4).cuda(), None, prec=pr)
+        s2d_u = ops.S2dConv(torch.zeros(64, 10, 4, 4).cuda(), None, prec=pr)
+        i2c = ops.Im2colConv(torch.zeros(64, 3, 4, 4).cuda(), None, 2, 1, prec=pr)
+        want_g = s2d_g.prepare(torch.cat([b["agnostic"], b["cocopose"]], 1))
+        want_c = i2c.prepare(b["cloth"])
+        for got, want, what in ((fused["gmm_person"].planes, want_g, "gmm"), (fused["cloth_i2c"], want_c, "cloth im2col")):
+            assert torch.equal(got.hi, want.hi), f"{prec} {what} hi"
+            assert (got.lo is None and want.lo is None) or torch.equal(got.lo, want.lo), f"{prec} {what} lo"
+        theta = (torch.rand(3, 50, generator=torch.Generator().manual_seed(3)) * 0.4 - 0.2).cuda()
+        tables = warp.gridGen.tables(theta.device)
+        warped = ops.tps_warp_u8_planes(theta, tables, dev[1], fused["unet_in"])
+        (want_w,), _ = ops.tps_grid_sample(theta, tables, H, W, [(b["cloth"], "border")])
+        assert torch.equal(warped, want_w), f"{prec} warped cloth"
+        want_u = s2d_u.prepare(torch.cat([b["agnostic"], b["densepose"], want_w], 1))
+        assert torch.equal(fused["unet_in"].planes.hi, want_u.hi), f"{prec} unet operand hi"
+        assert want_u.lo is None or torch.equal(fused["unet_in"].planes.lo, want_u.lo), f"{prec} unet operand lo"
+    # whole pipeline: fused == unfused
+    pipe = TryOnPipeline(warp, tom)
+    graphed = TryOnPipeline(warp, tom, cuda_graph=True)
+    TryOnPipeline.FUSED_PREP = False
+    try:
+        want = pipe.run_raw(*dev, prep).clone()
+    finally:
+        TryOnPipeline.FUSED_PREP = True
+    pipe2 = TryOnPipeline(warp, tom)
+    assert torch.equal(pipe2.run_raw(*dev, prep), want)
+    for _ in range(3):
+        assert torch.equal(graphed.run_raw(*dev, prep), want)
