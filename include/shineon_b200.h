@@ -289,6 +289,12 @@ int shineon_sagan_attention(const float* qkv, const float* x, const float* gamma
 int shineon_l2norm_correlation(const float* featA, const float* featB, float* corr_f32, void* y_hi,
                                void* y_lo, int B, int h, int w, int C, int cpad, int plane_fmt, int normalize,
                                shineon_stream_t stream);
+/* The same pair of FeatureL2Norms written as the operands of a per-image tensor-core GEMM (shineon_conv2d_igemm_fwd with
+ * w_per_image): b_* [B,h,w,C] = scale * featB / |featB| (activation planes) and a_* [B][h*w][C] = scale * featA / |featA|
+ * with rows in FeatureCorrelation's transposed pixel order iA = wA*h + hA (the per-image weights).  The 1x1 "conv" of b_*
+ * with a_*, acc_scale = 1 / scale^2, then IS FeatureCorrelation's output [B,h,w,h*w].  C % 64 == 0; scale: a power of two. */
+int shineon_l2norm_planes(const float* featA, const float* featB, void* a_hi, void* a_lo, void* b_hi, void* b_lo, int B, int h,
+                          int w, int C, int plane_fmt, float scale, shineon_stream_t stream);
 /* FeatureL2Norm.forward (warp.py:43-50) on the reference layout: y = x / sqrt(sum_c x^2 + 1e-6), f32 NCHW [B,C,H,W]. */
 int shineon_feature_l2norm(const float* x, float* y, int B, int C, int H, int W, shineon_stream_t stream);
 

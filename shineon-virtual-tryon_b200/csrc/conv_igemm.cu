@@ -197,7 +197,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // Persistent: one CTA per SM walks output tiles (tile = blockIdx.x + i*gridDim.x, channel tile fastest so that
 // neighbouring CTAs share the same activation tile in L2).  Two TMEM accumulators: the epilogue of tile i
 // (TMEM -> registers -> global) overlaps the TMA/MMA main loop of tile i+1.
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool MULTI>  // MULTI: the K loop spans several accumulation chunks (num_kb > chunk_kb)
 __global__ void __launch_bounds__(kThreads, 1)
     conv_igemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -394,9 +394,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       epi_bar_sync<kEpiWarps * 32>();
       // ---- all K chunks but the last: partial sums TMEM -> registers (round-to-nearest adds), buffer handed straight back
-      const bool multi = a.num_kb > a.chunk_kb;  // uniform over the launch
-      float accr[kNCH][32];
-      for (int kb0 = 0; kb0 + a.chunk_kb < a.num_kb; kb0 += a.chunk_kb, ++it) {
+      // (compiled only into the MULTI instantiations: the single-chunk ones -- every short-mainloop, epilogue-bound layer --
+      // keep the register footprint of a plain streaming epilogue)
+      float accr[MULTI ? kNCH : 1][32];
+      for (int kb0 = 0; MULTI && kb0 + a.chunk_kb < a.num_kb; kb0 += a.chunk_kb, ++it) {
         const int buf = it & 1;
         mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
         tc_fence_after();
@@ -453,10 +454,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int i = 0; i < 32; ++i) {
           float acc = (i < kChunk) ? __uint_as_float(v[i]) : 0.f;
           if (kCat && i < kChunk) acc += __uint_as_float(v2[i]);  // hi*hi + lo*hi  +  hi*lo
-          if (multi) {  // earlier chunks' partial sum (register array indexed by the runtime ci through selects)
+          if (MULTI) {  // earlier chunks' partial sum (register array indexed by the runtime ci through selects)
             float prev = accr[0][i];
 #pragma unroll
-            for (int k = 1; k < kNCH; ++k) prev = ci == k ? accr[k][i] : prev;
+            for (int k = 1; k < (MULTI ? kNCH : 1); ++k) prev = ci == k ? accr[k][i] : prev;
             acc += prev;
           }
           vals[i] = (i < kChunk) ? fmaf(acc, a.acc_scale, s_bias[c0 + (i < kChunk ? i : 0)]) : 0.f;
@@ -853,7 +854,7 @@ static void pick_tile(int N, int Ho, int Wo, int& nb, int& bh, int& bw) {
   }
 }
 
-template <int BN, bool SPLIT>
+template <int BN, bool SPLIT, bool MULTI>
 static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUtensorMap& tBh, const CUtensorMap& tBl,
                         ConvArgs& a, int m_tiles, int stages_req, cudaStream_t stream) {
   constexpr int kBBytes = BN * kBlockK * 2;
@@ -869,10 +870,10 @@ static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CU
   static int max_dyn_smem = -1;  // per instantiation: opt-in limit minus this kernel's static shared memory
   if (max_dyn_smem < 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, conv_igemm_kernel<BN, SPLIT>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv_igemm_kernel<BN, SPLIT, MULTI>);
     if (e == cudaSuccess) {
       max_dyn_smem = 227 * 1024 - (int)fa.sharedSizeBytes;
-      e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem);
+      e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem);
     }
     if (e != cudaSuccess) {
       cudaGetLastError();
@@ -907,7 +908,7 @@ static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CU
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
   }
   const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
-  conv_igemm_kernel<BN, SPLIT><<<grid, kThreads, smem_bytes, stream>>>(tAh, tAl, tBh, tBl, a);
+  conv_igemm_kernel<BN, SPLIT, MULTI><<<grid, kThreads, smem_bytes, stream>>>(tAh, tAl, tBh, tBl, a);
   return after_launch("conv_igemm_kernel");
 }
 
@@ -1026,9 +1027,12 @@ static int conv2d_igemm_launch(const shineon_conv2d_params* p, ConvArgs& a, cuda
   }
   if (!split) { tAl = tAh; tBl = tBh; }
 
-#define SHINEON_LAUNCH(BN_)                                                                            \
-  (split ? launch_igemm<BN_, true>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream)                  \
-         : launch_igemm<BN_, false>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream))
+  const bool multi = a.num_kb > a.chunk_kb;
+#define SHINEON_LAUNCH(BN_)                                                                                                      \
+  (split ? (multi ? launch_igemm<BN_, true, true>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream)                             \
+                  : launch_igemm<BN_, true, false>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream))                           \
+         : (multi ? launch_igemm<BN_, false, true>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream)                            \
+                  : launch_igemm<BN_, false, false>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream)))
   switch (bn) {
     case 16: return SHINEON_LAUNCH(16);
     case 32: return SHINEON_LAUNCH(32);

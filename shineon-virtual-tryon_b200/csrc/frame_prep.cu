@@ -10,6 +10,7 @@
 // Byte / integer work, bit-exact against the reference: the PIL resize is done with Pillow's own fixed-point scheme
 // (Resample.c: 22-bit coefficients, rounding to uint8 after each pass), coefficients from shineon_pil_bilinear_coeffs.
 #include <cmath>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -179,31 +180,38 @@ __global__ void __launch_bounds__(1024)
 struct PrepPlanesArgs {
   const uint8_t *image, *parse, *cloth, *densepose, *sil;
   plane_t *pg_hi, *pg_lo, *pu_hi, *pu_lo, *pc_hi, *pc_lo;
-  int H, W, J, cg, cu, cc, fmt;
+  int H, W, J, fmt;
 };
 constexpr int kPrepPx = 32;
 
+// CG / CU / CC: channel pads of the three outputs (compile-time: index math without divisions).  ToTensor + Normalize of
+// a byte has 256 possible results: a shared table (hi/lo halves precomputed) replaces two IEEE divisions and a split per use.
+template <int CG, int CU, int CC>
 __global__ void __launch_bounds__(256) frame_prep_planes_kernel(const PrepPlanesArgs a) {
+  constexpr int ROW = CG + CU + CC;  // halfwords per pixel and half (hi or lo)
   extern __shared__ __align__(16) plane_t sm_rows[];
+  __shared__ uint32_t s_lut[256];   // hi | lo << 16 of norm_u8(b)
+  __shared__ float s_lutf[256];
   const int f = blockIdx.z, Y = blockIdx.y, X0 = blockIdx.x * kPrepPx;
   const int Hz = a.H / 2 + 1, Wz = a.W / 2 + 1;
-  const int row_hw = a.cg + a.cu + a.cc;         // halfwords per pixel and half (hi or lo)
-  plane_t* s_hi = sm_rows;                        // [kPrepPx][cg | cu | cc]
-  plane_t* s_lo = sm_rows + kPrepPx * row_hw;
-  {  // zero (padding channels, out-of-image taps, the cloth' slots)
-    uint4* z = reinterpret_cast<uint4*>(sm_rows);
-    const int n16 = 2 * kPrepPx * row_hw / 8;
-    for (int i = threadIdx.x; i < n16; i += 256) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  plane_t* s_hi = sm_rows;                     // [kPrepPx][CG | CU | CC]
+  plane_t* s_lo = sm_rows + kPrepPx * ROW;
+  {
+    const float v = norm_u8((uint8_t)threadIdx.x);
+    plane_t h, l;
+    split16(v, a.fmt, h, l);
+    s_lut[threadIdx.x] = (uint32_t)h | ((uint32_t)l << 16);
+    s_lutf[threadIdx.x] = v;
+    uint4* z = reinterpret_cast<uint4*>(sm_rows);  // zero: padding channels, out-of-image taps, the cloth' slots
+#pragma unroll
+    for (int i = 0; i < 2 * kPrepPx * ROW / 8 / 256; ++i) z[threadIdx.x + i * 256] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
   const long fo = (long)f * a.H * a.W;
-  const int cper_g = 4 + a.J, cper_u = 10;
-  auto put = [&](int px, int k, float v) {
-    plane_t h, l;
-    split16(v, a.fmt, h, l);
-    s_hi[px * row_hw + k] = h;
-    s_lo[px * row_hw + k] = l;
-  };
+  const int cper_g = 4 + a.J;
+  constexpr int cper_u = 10;
+  plane_t neg1_hi, neg1_lo;
+  split16(-1.f, a.fmt, neg1_hi, neg1_lo);  // -1 is exact in both formats: lo == 0
   if (threadIdx.x < 4 * kPrepPx) {  // (pixel, position q): the person channels of pg and pu
     const int px = threadIdx.x >> 2, q = threadIdx.x & 3;
     const int X = X0 + px;
@@ -211,20 +219,24 @@ __global__ void __launch_bounds__(256) frame_prep_planes_kernel(const PrepPlanes
     if (X < Wz && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
       const long p = fo + (long)iy * a.W + ix;
       const uint32_t lab = a.parse[p];
-      const float ph = (lab < 32 && ((kHeadMask >> lab) & 1u)) ? 1.f : 0.f;
-      float agn[4];
-      agn[0] = norm_u8(a.sil[p]);
+      const bool head = lab < 32 && ((kHeadMask >> lab) & 1u);
+      plane_t* gh = s_hi + px * ROW + q * cper_g;
+      plane_t* gl = s_lo + px * ROW + q * cper_g;
+      plane_t* uh = s_hi + px * ROW + CG + q * cper_u;
+      plane_t* ul = s_lo + px * ROW + CG + q * cper_u;
+      const uint32_t sv = s_lut[a.sil[p]];
+      gh[0] = uh[0] = (plane_t)sv;
+      gl[0] = ul[0] = (plane_t)(sv >> 16);
 #pragma unroll
-      for (int c = 0; c < 3; ++c)  // im * phead - (1 - phead)
-        agn[1 + c] = __fsub_rn(__fmul_rn(norm_u8(a.image[p * 3 + c]), ph), __fsub_rn(1.f, ph));
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        put(px, q * cper_g + c, agn[c]);
-        put(px, a.cg + q * cper_u + c, agn[c]);
+      for (int c = 0; c < 3; ++c) {  // im * phead - (1 - phead): the pixel itself inside the head labels, -1 elsewhere
+        const uint32_t hv = head ? s_lut[a.image[p * 3 + c]] : (uint32_t)neg1_hi;
+        gh[1 + c] = uh[1 + c] = (plane_t)hv;
+        gl[1 + c] = ul[1 + c] = (plane_t)(hv >> 16);
+        const uint32_t dv = s_lut[a.densepose[p * 3 + c]];
+        uh[4 + c] = (plane_t)dv;
+        ul[4 + c] = (plane_t)(dv >> 16);
       }
-      for (int j = 0; j < a.J; ++j) put(px, q * cper_g + 4 + j, -1.f);  // cocopose maps: constant -1 as the reference writes them
-#pragma unroll
-      for (int c = 0; c < 3; ++c) put(px, a.cg + q * cper_u + 4 + c, norm_u8(a.densepose[p * 3 + c]));
+      for (int j = 0; j < a.J; ++j) gh[4 + j] = neg1_hi;  // cocopose maps: constant -1 as the reference writes them (lo = 0)
     }
   }
   for (int it = threadIdx.x; it < 16 * kPrepPx; it += 256) {  // (pixel, filter tap): the cloth's im2col row
@@ -234,29 +246,31 @@ __global__ void __launch_bounds__(256) frame_prep_planes_kernel(const PrepPlanes
     if (Y < a.H / 2 && X < a.W / 2 && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
       const long p = fo + (long)iy * a.W + ix;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) put(px, a.cg + a.cu + tap * 3 + c, norm_u8(a.cloth[p * 3 + c]));
+      for (int c = 0; c < 3; ++c) {
+        const uint32_t cv = s_lut[a.cloth[p * 3 + c]];
+        s_hi[px * ROW + CG + CU + tap * 3 + c] = (plane_t)cv;
+        s_lo[px * ROW + CG + CU + tap * 3 + c] = (plane_t)(cv >> 16);
+      }
     }
   }
   __syncthreads();
   // coalesced copy-out: per destination tensor, 16-byte units of the CTA's contiguous row segment
   const int nz = min(kPrepPx, Wz - X0), nc = (Y < a.H / 2) ? max(0, min(kPrepPx, a.W / 2 - X0)) : 0;
-  auto copy_out = [&](plane_t* dst_hi, plane_t* dst_lo, int cw, int soff, long row0, int npx) {
+  auto copy_out = [&](plane_t* dst_hi, plane_t* dst_lo, auto cw_tag, int soff, long row0, int npx) {
+    constexpr int CW = decltype(cw_tag)::value;
+    constexpr int UPP = CW / 8;  // 16-byte units per pixel
     if (!dst_hi || npx <= 0) return;
-    const int u_per_px = cw / 8;
-    for (int i = threadIdx.x; i < npx * u_per_px; i += 256) {
-      const int px = i / u_per_px, u = i - px * u_per_px;
-      const uint4 vh = *reinterpret_cast<const uint4*>(s_hi + px * row_hw + soff + u * 8);
-      *reinterpret_cast<uint4*>(dst_hi + (row0 + px) * cw + u * 8) = vh;
-      if (dst_lo) {
-        const uint4 vl = *reinterpret_cast<const uint4*>(s_lo + px * row_hw + soff + u * 8);
-        *reinterpret_cast<uint4*>(dst_lo + (row0 + px) * cw + u * 8) = vl;
-      }
+    for (int i = threadIdx.x; i < npx * UPP; i += 256) {
+      const int px = i / UPP, u = i % UPP;
+      *reinterpret_cast<uint4*>(dst_hi + (row0 + px) * CW + u * 8) = *reinterpret_cast<const uint4*>(s_hi + px * ROW + soff + u * 8);
+      if (dst_lo)
+        *reinterpret_cast<uint4*>(dst_lo + (row0 + px) * CW + u * 8) = *reinterpret_cast<const uint4*>(s_lo + px * ROW + soff + u * 8);
     }
   };
   const long zrow = ((long)f * Hz + Y) * Wz + X0;
-  copy_out(a.pg_hi, a.pg_lo, a.cg, 0, zrow, nz);
-  copy_out(a.pu_hi, a.pu_lo, a.cu, a.cg, zrow, nz);
-  copy_out(a.pc_hi, a.pc_lo, a.cc, a.cg + a.cu, ((long)f * (a.H / 2) + Y) * (a.W / 2) + X0, nc);
+  copy_out(a.pg_hi, a.pg_lo, std::integral_constant<int, CG>{}, 0, zrow, nz);
+  copy_out(a.pu_hi, a.pu_lo, std::integral_constant<int, CU>{}, CG, zrow, nz);
+  copy_out(a.pc_hi, a.pc_lo, std::integral_constant<int, CC>{}, CG + CU, ((long)f * (a.H / 2) + Y) * (a.W / 2) + X0, nc);
 }
 
 // im_cocopose: union of the filled squares ImageDraw.rectangle((x-r, y-r, x+r, y+r)) draws for joints with x > 1, y > 1
@@ -402,17 +416,19 @@ extern "C" int shineon_frame_prep_planes(const shineon_frame_prep_planes_params*
   a.image = p->image; a.parse = p->parse; a.cloth = p->cloth; a.densepose = p->densepose; a.sil = p->silhouette_scratch;
   a.pg_hi = (plane_t*)p->gmm_hi; a.pg_lo = (plane_t*)p->gmm_lo; a.pu_hi = (plane_t*)p->unet_hi; a.pu_lo = (plane_t*)p->unet_lo;
   a.pc_hi = (plane_t*)p->cloth_hi; a.pc_lo = (plane_t*)p->cloth_lo;
-  a.H = p->H; a.W = p->W; a.J = p->n_joints; a.cg = p->gmm_cpad; a.cu = p->unet_cpad; a.cc = p->cloth_cpad; a.fmt = p->plane_fmt;
-  const size_t smem = (size_t)2 * kPrepPx * (a.cg + a.cu + a.cc) * sizeof(plane_t);
-  static bool opted = false;
-  if (!opted && smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(frame_prep_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "frame_prep_planes: shared memory opt-in: %s", cudaGetErrorString(e));
-    opted = true;
-  }
-  SHINEON_REQUIRE(smem <= 96 * 1024, "frame_prep_planes: channel pads too large");
+  a.H = p->H; a.W = p->W; a.J = p->n_joints; a.fmt = p->plane_fmt;
   dim3 grid(cdiv(p->W / 2 + 1, kPrepPx), p->H / 2 + 1, p->F);
-  frame_prep_planes_kernel<<<grid, 256, smem, st>>>(a);
+  // channel pads are compile-time: the recipe's (18 joints: 88 -> 128, 40 -> 64, 48 -> 64) and the joint-free variant
+  if (p->gmm_cpad == 128 && p->unet_cpad == 64 && p->cloth_cpad == 64) {
+    constexpr size_t smem = (size_t)2 * kPrepPx * (128 + 64 + 64) * sizeof(plane_t);
+    frame_prep_planes_kernel<128, 64, 64><<<grid, 256, smem, st>>>(a);
+  } else if (p->gmm_cpad == 64 && p->unet_cpad == 64 && p->cloth_cpad == 64) {
+    constexpr size_t smem = (size_t)2 * kPrepPx * (64 + 64 + 64) * sizeof(plane_t);
+    frame_prep_planes_kernel<64, 64, 64><<<grid, 256, smem, st>>>(a);
+  } else {
+    return fail(SHINEON_ERR_UNSUPPORTED, "frame_prep_planes: channel pads (%d, %d, %d) not compiled (128/64/64 and 64/64/64 are)",
+                p->gmm_cpad, p->unet_cpad, p->cloth_cpad);
+  }
   return after_launch("frame_prep_planes_kernel");
 }
 

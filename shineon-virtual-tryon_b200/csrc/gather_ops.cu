@@ -625,9 +625,11 @@ __global__ void __launch_bounds__(128)
   __shared__ float2 sWxy[kTpsChunk][N];
   __shared__ float sA[kTpsChunk][6];
   __shared__ float sP[2 * N];
+  __shared__ float s_lut[256];  // ToTensor + Normalize of every byte value (two IEEE divisions each: once per CTA, not per tap)
   const int b0 = blockIdx.y * chunk;
   const int nb = min(chunk, B - b0);
   constexpr int L = N + 3;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = norm_u8_tps((uint8_t)i);
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     sP[i] = t.P_X[i];
     sP[N + i] = t.P_Y[i];
@@ -712,7 +714,7 @@ __global__ void __launch_bounds__(128)
       plane_t* zlb = zl ? zl + (long)b * Hz * Wz * zc + zoff[k] : nullptr;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float v[4] = {norm_u8_tps(u[k][0][c]), norm_u8_tps(u[k][1][c]), norm_u8_tps(u[k][2][c]), norm_u8_tps(u[k][3][c])};
+        const float v[4] = {s_lut[u[k][0][c]], s_lut[u[k][1][c]], s_lut[u[k][2][c]], s_lut[u[k][3][c]]};
         const float r = blend_taps(v, tp[k]);
         out[((long)b * 3 + c) * HW + p] = r;
         plane_t hh, ll;

@@ -84,6 +84,45 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// FeatureL2Norm of both feature maps written as the operands of a per-image tensor-core GEMM (conv_igemm, w_per_image):
+//   B' [b][pB][c]          = scale * fB[b,pB,c] / |fB[b,pB,:]|        the "activation" planes, pixel order hB*w + wB
+//   A' [b][iA = wA*h+hA][c] = scale * fA[b,pA,c] / |fA[b,pA,:]|        the per-image "weights", rows in the transposed
+//                                                                      pixel order of warp.py:60 (feature_A.transpose(2,3))
+// so that out[b,pB,iA] = <B'[pB], A'[iA]> / scale^2 is FeatureCorrelation's output.  scale (a power of two) keeps the lo
+// halves of the ~1/sqrt(C)-sized components out of the fp16 subnormals.  One warp per pixel.
+__global__ void __launch_bounds__(256)
+    l2norm_planes_kernel(const float* __restrict__ fA, const float* __restrict__ fB, plane_t* __restrict__ ah,
+                         plane_t* __restrict__ al, plane_t* __restrict__ bh, plane_t* __restrict__ bl, int h, int w, int C,
+                         int fmt, float scale) {
+  const int P = h * w;
+  const int b = blockIdx.z, isA = blockIdx.y;
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (p >= P) return;
+  const float* src = (isA ? fA : fB) + ((long)b * P + p) * C;
+  float ss = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+    ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = scale / sqrtf(ss + 1e-6f);  // warp.py:44-49
+  const int hp = p / w, wp = p - hp * w;
+  const long row = (long)b * P + (isA ? wp * h + hp : p);
+  plane_t* dh = (isA ? ah : bh) + row * C;
+  plane_t* dl = (isA ? al : bl);
+  if (dl) dl += row * C;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+    plane_t hh[4], ll[4];
+    split16(v.x * inv, fmt, hh[0], ll[0]);
+    split16(v.y * inv, fmt, hh[1], ll[1]);
+    split16(v.z * inv, fmt, hh[2], ll[2]);
+    split16(v.w * inv, fmt, hh[3], ll[3]);
+    *reinterpret_cast<uint2*>(dh + c) = make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16));
+    if (dl) *reinterpret_cast<uint2*>(dl + c) = make_uint2((uint32_t)ll[0] | ((uint32_t)ll[1] << 16), (uint32_t)ll[2] | ((uint32_t)ll[3] << 16));
+  }
+}
+
 // FeatureL2Norm.forward on the reference layout (warp.py:43-50): y[b,c,p] = x[b,c,p] / sqrt(sum_c x[b,c,p]^2 + 1e-6).
 // One thread per pixel, channel planes read coalesced across the warp.
 __global__ void __launch_bounds__(128)
@@ -153,4 +192,16 @@ extern "C" int shineon_linear_tanh(const float* x, const float* weight, const fl
   SHINEON_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && out_dim > 0, "linear_tanh: bad shape");
   linear_tanh_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, weight, bias, theta, h * w, C, out_dim);
   return after_launch("linear_tanh_kernel");
+}
+
+extern "C" int shineon_l2norm_planes(const float* featA, const float* featB, void* a_hi, void* a_lo, void* b_hi, void* b_lo,
+                                     int B, int h, int w, int C, int plane_fmt, float scale, shineon_stream_t stream) {
+  SHINEON_REQUIRE(plane_fmt == SHINEON_FMT_BF16 || plane_fmt == SHINEON_FMT_FP16, "l2norm_planes: plane_fmt %d", plane_fmt);
+  SHINEON_REQUIRE(featA && featB && a_hi && b_hi && (a_lo == nullptr) == (b_lo == nullptr), "l2norm_planes: null pointer");
+  SHINEON_REQUIRE(B > 0 && B <= 65535 && h > 0 && w > 0 && C > 0 && C % 64 == 0, "l2norm_planes: bad shape (C %% 64)");
+  SHINEON_REQUIRE(scale > 0.f, "l2norm_planes: scale");
+  l2norm_planes_kernel<<<dim3(cdiv(h * w, 8), 2, B), 256, 0, (cudaStream_t)stream>>>(featA, featB, (plane_t*)a_hi, (plane_t*)a_lo,
+                                                                                    (plane_t*)b_hi, (plane_t*)b_lo, h, w, C,
+                                                                                    plane_fmt, scale);
+  return after_launch("l2norm_planes_kernel");
 }

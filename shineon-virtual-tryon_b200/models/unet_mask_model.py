@@ -64,7 +64,7 @@ class UnetMaskModel(BaseModel):
         ops.frame_prep_planes + TpsGridGen.warp_u8): cat([person, warped_cloths], 1) is never materialised."""
         prec = ops.resolve_precision(self.unet.precision)
         assert unet_in.planes.prec == prec, "stem operand precision differs from the model's"
-        out = self.unet.model.run(unet_in, prec)
+        out = self.unet.run_operand(unet_in, prec)
         return self._compose(out, warped_cloths.contiguous(), None, want_u8=True, want_f32=False)[4]
 
     def _forward(self, person_representation, warped_cloths, flows=None, want_u8=False, want_f32=True):
@@ -74,7 +74,7 @@ class UnetMaskModel(BaseModel):
         person_representation = person_representation.contiguous()
         warped_cloths = warped_cloths.contiguous()
         # torch.cat([person, cloth], 1) is fused into the NCHW -> NHWC-planes (im2col) conversion
-        out = self.unet.model.run((person_representation, warped_cloths), prec)  # f32 NHWC [B,H,W,(4|5)n]
+        out = self.unet.run_operand((person_representation, warped_cloths), prec)  # f32 NHWC [B,H,W,(4|5)n]
         return self._compose(out, warped_cloths, flows, want_u8, want_f32)
 
     def _compose(self, out, warped_cloths, flows=None, want_u8=False, want_f32=True):

@@ -45,7 +45,18 @@ class UnetGenerator(nn.Module):
         """input: f32 NCHW CUDA tensor -> f32 NHWC [N,H,W,output_nc]."""
         require_cuda(self, "UnetGenerator")
         prec = ops.resolve_precision(self.precision)
-        return self.model.run((input.contiguous(), None), prec)
+        return self.run_operand((input.contiguous(), None), prec)
+
+    def run_operand(self, a_in, prec):
+        """The inference pass on (x0, x1|None) f32 NCHW inputs or a prebuilt stem operand (ops.S2dInput)."""
+        N = a_in.N if isinstance(a_in, ops.S2dInput) else a_in[0].shape[0]
+        dev = a_in.planes.hi.device if isinstance(a_in, ops.S2dInput) else a_in[0].device
+        blk = UnetSkipConnectionBlock
+        blk._ARENA = [torch.zeros(self.model.stats_arena_size(N), dtype=torch.float64, device=dev), 0] if blk.FUSE_STATS else None
+        try:
+            return self.model.run(a_in, prec)
+        finally:
+            blk._ARENA = None
 
     def forward(self, input):
         return self.forward_nhwc(input).permute(0, 3, 1, 2).contiguous()
@@ -284,11 +295,30 @@ class UnetSkipConnectionBlock(nn.Module):
     # False = the separate statistics pass of instnorm_act (kept for A/B measurements and the tests)
     FUSE_STATS = True
 
+    # one zero-filled f64 arena per forward pass (UnetGenerator.forward_nhwc sets it up): the blocks carve their
+    # statistics buffers out of it instead of launching one fill kernel per normalisation
+    _ARENA = None
+
     @classmethod
     def _stats_ws(cls, norm, N, C, device):
-        if cls.FUSE_STATS and isinstance(norm, nn.InstanceNorm2d):
-            return torch.zeros(2 * N * C, dtype=torch.float64, device=device)
-        return None
+        if not (cls.FUSE_STATS and isinstance(norm, nn.InstanceNorm2d)):
+            return None
+        n = 2 * N * C
+        ar = cls._ARENA
+        if ar is not None and ar[0].device == device and ar[1] + n <= ar[0].numel():
+            ws = ar[0][ar[1]:ar[1] + n]
+            ar[1] += n
+            return ws
+        return torch.zeros(n, dtype=torch.float64, device=device)
+
+    def stats_arena_size(self, N):
+        """f64 elements the statistics buffers of one pass through this block (and its children) need for batch N."""
+        pr = self._parts
+        n = 0
+        for norm, conv in ((pr["downnorm"], pr["downconv"]), (pr["upnorm"], pr["upconv"])):
+            if isinstance(norm, nn.InstanceNorm2d):
+                n += 2 * N * conv.out_channels
+        return n + (pr["sub"].stats_arena_size(N) if pr["sub"] is not None else 0)
 
     def run(self, a_in, prec, train=False, out=None, raw_out=False):
         """a_in: Planes holding this block's (already down-activated) input; for the outermost block a tuple

@@ -105,7 +105,10 @@ class FeatureL2Norm(nn.Module):
 
 class FeatureCorrelation(nn.Module):
     def forward_fused(self, fa_nhwc, fb_nhwc, prec=None, want_f32=False):
-        """FeatureL2Norm x2 + FeatureCorrelation (warp.py:39-67) on f32 NHWC features."""
+        """FeatureL2Norm x2 + FeatureCorrelation (warp.py:39-67) on f32 NHWC features: a per-image tensor-core GEMM over
+        the normalised planes where the channel count allows (ops.l2norm_correlation_tc), else the fp32 kernel."""
+        if ops.CORRELATION_TC and fa_nhwc.shape[-1] % 64 == 0:
+            return ops.l2norm_correlation_tc(fa_nhwc, fb_nhwc, prec=prec, want_f32=want_f32)
         return ops.l2norm_correlation(fa_nhwc, fb_nhwc, want_f32=want_f32, want_planes=True, prec=prec)
 
     def forward(self, feature_A, feature_B):

@@ -647,6 +647,32 @@ def l2norm_correlation(featA, featB, *, want_f32=False, want_planes=True, prec=N
     return corr, planes
 
 
+# tensor-core form of l2norm_correlation (per-image tcgen05 GEMM); False = the fp32 CUDA-core kernel
+CORRELATION_TC = True
+
+
+def l2norm_correlation_tc(featA, featB, prec=None, want_f32=False):
+    """FeatureL2Norm x2 + FeatureCorrelation (warp.py:39-67) on the tensor cores: one pass writes both normalised feature
+    maps as 16-bit planes (featA's rows in the transposed pixel order of warp.py:60), then the all-pairs products are ONE
+    per-image implicit GEMM (featA's planes play the weights).  featA/B: f32 NHWC [B,h,w,C], C % 64 == 0.
+    Returns (f32 NHWC [B,h,w,h*w] | None, Planes [B,h,w,h*w])."""
+    featA, featB = _req(featA), _req(featB)
+    B, h, w, Cc = featA.shape
+    P = h * w
+    fmt, split = resolve_precision(prec)
+    dev = featA.device
+    a = Planes(B, 1, P, Cc, prec=(fmt, split), device=dev, zero_pad=False)   # [B][P rows][C]
+    b = Planes(B, h, w, Cc, prec=(fmt, split), device=dev, zero_pad=False)
+    scale = 64.0
+    check(_lib.load().shineon_l2norm_planes(_p(featA), _p(featB), _p(a.hi), _p(a.lo), _p(b.hi), _p(b.lo), B, h, w, Cc, fmt,
+                                            scale, _stream()), "shineon_l2norm_planes")
+    pc = PackedConv.__new__(PackedConv)
+    pc.fmt = fmt
+    pc.Cout, pc.Cin, pc.kh, pc.kw, pc.stride, pc.pad_h, pc.pad_w = P, Cc, 1, 1, 1, 0, 0
+    pc.cin_pad, pc.w_hi, pc.w_lo, pc.bias, pc.acc_scale, pc.transposed, pc.per_image = Cc, a.hi, a.lo, None, 1.0 / (scale * scale), False, True
+    return conv2d(b, pc, want_f32=want_f32, want_planes=True)
+
+
 def linear_tanh(x, weight, bias):
     """x: f32 NHWC [B,h,w,C]; weight [out, C*h*w] over the NCHW-flattened input (warp.py:94-99)."""
     x, weight = _req(x), _req(weight)

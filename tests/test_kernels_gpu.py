@@ -341,6 +341,13 @@ def test_l2norm_correlation_and_linear(ops):
     corr, planes = ops.l2norm_correlation(nhwc(fa).cuda(), nhwc(fb).cuda(), want_f32=True, want_planes=True)
     assert_close(nchw(corr), want, atol=2e-6, rtol=1e-4, what="l2norm+corr f32")
     assert_close(planes.float(), want, atol=1e-5, rtol=1e-4, what="l2norm+corr planes")
+    # tensor-core form (per-image tcgen05 GEMM over the normalised planes), all plane formats; signed features too
+    for fa2, fb2 in ((fa, fb), (torch.randn(B, C, h, w, generator=g), torch.randn(B, C, h, w, generator=g))):
+        want2 = gmm.feature_correlation(gmm.feature_l2norm(fa2), gmm.feature_l2norm(fb2))
+        for prec, tol in (("fp16x3", 2e-6), ("bf16x3", 2e-5), ("bf16", 2e-2)):
+            c2, p2 = ops.l2norm_correlation_tc(nhwc(fa2).cuda(), nhwc(fb2).cuda(), prec=ops.resolve_precision(prec), want_f32=True)
+            assert_close(nchw(c2), want2, atol=tol, rtol=1e-4, what=f"tensor-core l2norm+corr f32 ({prec})")
+            assert_close(p2.float(), want2, atol=max(tol, 1e-5), rtol=1e-4, what=f"tensor-core l2norm+corr planes ({prec})")
     x = torch.randn(B, 64, 4, 3, generator=g)
     wt = torch.randn(50, 768, generator=g) * 0.05
     bs = torch.randn(50, generator=g) * 0.1
