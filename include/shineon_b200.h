@@ -508,6 +508,40 @@ int shineon_frame_prep_planes(const shineon_frame_prep_planes_params* p, shineon
  * (flownet2_pytorch/utils/flow_utils.py:7-26 + flow_norm, datasets/tryon_dataset.py:121,288-289). */
 int shineon_flo_decode(const void* flo_payload, float* out, int H, int W, shineon_stream_t stream);
 
+/* ------------------------------------------------------------------ */
+/* SAMS generator: SPADE modulation and the nearest     */
+/* resizes around the blocks                                           */
+/* ------------------------------------------------------------------ */
+
+/* Per-(image, channel) sum and sum of squares of f32 NHWC x [N,HW,C] into stats_ws (2*N*C doubles, zeroed by the call):
+ * the statistics nn.InstanceNorm2d(affine=False) needs (SPADE's param_free_norm, models/networks/sams/spade.py:55,71). */
+int shineon_chan_stats(const float* x, double* stats_ws, int N, int HW, int C, shineon_stream_t stream);
+
+/* SPADE.forward's modulation (models/networks/sams/spade.py:68-84) on f32 NHWC x [N,H,W,C]:
+ *   y = act( norm(x) * gb[..., c] + gb[..., C + c] )
+ * norm_mode 0: identity; 1: InstanceNorm2d from stats_ws (shineon_chan_stats); 2: eval-mode BatchNorm2d /
+ * SynchronizedBatchNorm2d(affine=False) as per-channel nscale / nshift [C].  gb: f32 NHWC [N,H,W,gb_cstride], the output
+ * of ONE conv holding (1 + gamma) in channels [0,C) and beta in [C,2C) (mlp_gamma / mlp_beta stacked, the "+1" folded into
+ * the bias).  act = the activation AnySpadeResBlock applies next (spade.py:157-158), 0 for norm_s.
+ * Writes any subset of f32 y_f32 (row stride y_cstride; may be a channel window) and planes y_hi / y_lo (stride cpad). */
+int shineon_spade_modulate(const float* x, const double* stats_ws, const float* nscale, const float* nshift,
+                           const float* gb, int gb_cstride, float* y_f32, int y_cstride, void* y_hi, void* y_lo, int N,
+                           int H, int W, int C, int cpad, float eps, int norm_mode, int act, float act_param,
+                           int plane_fmt, shineon_stream_t stream);
+
+/* nn.Upsample(scale_factor=s) (mode nearest; sams_generator.py:295-310) on f32 NHWC: y[n,h,w,:] = x[n, min(floor(h *
+ * scale_h), Hs-1), min(floor(w * scale_w), Ws-1), :] with scale = 1/s (PyTorch's source-index rule). */
+int shineon_nearest_resize_nhwc(const float* x, float* y, int N, int Hs, int Ws, int H, int W, int C, float scale_h,
+                                float scale_w, shineon_stream_t stream);
+
+/* F.interpolate(segmap, size=(H,W), mode="nearest") (spade.py:74) of an f32 NCHW label map [N,C,Hs,Ws], written as the
+ * 16-bit planes [N,H,W,cpad] the mlp_shared conv reads (padding channels zero).  scale = Hs / H, Ws / W. */
+int shineon_nearest_resize_planes(const float* x, int N, int C, int Hs, int Ws, void* y_hi, void* y_lo, int H, int W,
+                                  int cpad, float scale_h, float scale_w, int plane_fmt, shineon_stream_t stream);
+
+/* y = a + b over n f32 elements (the residual x_s + dx of AnySpadeResBlock.forward, spade.py:160); y may alias a or b. */
+int shineon_add_nhwc(const float* a, const float* b, float* y, long n, shineon_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,38 @@ PIPELINE_FRAMES, PIPELINE_FRAME_STEP, PIPELINE_SUB = 80, 5, 8
 FLOWNET2_B16 = 16  # BASELINE configs[3] batch
 
 
+# SAMS generator: name -> (hparams overrides, batch, H, W)
+_SAMS_BASE = dict(norm_G="spectralspadesyncbatch3x3", ngf_base=2, ngf_pow_outer=6, ngf_pow_inner=10, ngf_pow_step=1, num_middle=3,
+                  attention_middle_indices=[], attention_decoder_indices=[], encoder_input="agnostic", n_frames_total=1,
+                  flow_warp=False, activation="gelu", person_inputs=["agnostic", "densepose"], cloth_inputs=["cloth"])
+SAMS_CASES = {
+    # three-level network, 3-frame window (two previous frames feed the encoder), spectral norm + eval-mode batch norm
+    "sams_small": (dict(_SAMS_BASE, ngf_pow_outer=4, ngf_pow_inner=6, num_middle=2, n_frames_total=3, flow_warp=True), 2, 64, 48),
+    # instance norm, no spectral norm, LeakyReLU/ReLU activations, AttentiveMultiSpade in the middle (48 px) and the first
+    # decoder layer (192 px), single-frame (zero previous frame), cocopose as a fourth label map
+    "sams_instance_attn": (dict(_SAMS_BASE, norm_G="spadeinstance3x3", activation="relu", ngf_pow_outer=4, ngf_pow_inner=6,
+                                num_middle=2, attention_middle_indices=["0"], attention_decoder_indices=["0"],
+                                person_inputs=["agnostic", "densepose", "cocopose"], encoder_input="densepose"), 2, 32, 24),
+    # the reference's default architecture (64 .. 1024 features, 3 middle blocks) on one 256x192 frame
+    "sams_default": (dict(_SAMS_BASE), 1, 256, 192),
+}
+
+
+def sams_inputs(name):
+    """(prev_frames [b,n-1,3,h,w] | None, prev_labelmaps [b,n-1,c,h,w] | None, {input name: [b,c,h,w]})."""
+    from oracle.sams import CHANNELS
+
+    over, B, H, W = SAMS_CASES[name]
+    g = _g(name)
+    n = over["n_frames_total"]
+    maps = {k: torch.randn(B, CHANNELS[k.upper()], H, W, generator=g) for k in sorted(over["person_inputs"] + over["cloth_inputs"])}
+    if n == 1:
+        return None, None, maps
+    prev = torch.rand(B, n - 1, 3, H, W, generator=g) * 2 - 1
+    prev_maps = torch.randn(B, n - 1, CHANNELS[over["encoder_input"].upper()], H, W, generator=g)
+    return prev, prev_maps, maps
+
+
 def _g(name):
     import zlib
 

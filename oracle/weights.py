@@ -35,7 +35,7 @@ def synth_tensor(seed, key, shape, conv_std=None):
         # stack keeps O(1) activations and the perceptual term carries signal
         fan_in = shape[1] * shape[2] * shape[3]
         return torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
-    if leaf == "weight" and len(shape) >= 2:
+    if leaf in ("weight", "weight_orig") and len(shape) >= 2:
         # the reference's own initialiser scale: init.normal_(w, 0.0, 0.02) for Conv / Linear
         # (models/networks/__init__.py:49-55)
         std = 0.02 if conv_std is None else conv_std
@@ -46,6 +46,25 @@ def synth_tensor(seed, key, shape, conv_std=None):
 def synth_state_dict(shapes, seed=420, conv_std=None):
     """shapes: {key: shape}.  Returns {key: tensor}."""
     return {k: synth_tensor(seed, k, tuple(s), conv_std) for k, s in shapes.items()}
+
+
+def fix_spectral(sd, iters=5):
+    """Replace every synthesized (weight_u, weight_v) pair of a spectral_norm'd conv by the result of `iters` power
+    iterations on its weight_orig (torch.nn.utils.spectral_norm.compute_weight's update, run on the CPU), so the
+    eval-mode weight W / (u . W v) is a properly normalised one instead of W divided by a random number."""
+    import torch.nn.functional as F
+
+    for k in list(sd):
+        if not k.endswith(".weight_orig"):
+            continue
+        base = k[: -len("weight_orig")]
+        w = sd[k].reshape(sd[k].shape[0], -1).double()
+        u = F.normalize(sd[base + "weight_u"].double().abs() + 0.1, dim=0)
+        for _ in range(iters):
+            v = F.normalize(torch.mv(w.t(), u), dim=0, eps=1e-12)
+            u = F.normalize(torch.mv(w, v), dim=0, eps=1e-12)
+        sd[base + "weight_u"], sd[base + "weight_v"] = u.float(), v.float()
+    return sd
 
 
 def shapes_of(module):

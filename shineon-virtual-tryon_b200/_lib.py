@@ -130,6 +130,12 @@ SIGNATURES = {
     "shineon_maxpool2x2_bwd": [c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_p],
     "shineon_tom_compose": [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_image_to_u8": [c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "shineon_chan_stats": [c_p, c_p, c_i, c_i, c_i, c_p],
+    "shineon_spade_modulate": [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_f,
+                               c_i, c_p],
+    "shineon_nearest_resize_nhwc": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p],
+    "shineon_nearest_resize_planes": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_i, c_p],
+    "shineon_add_nhwc": [c_p, c_p, c_p, C.c_long, c_p],
 }
 _RESTYPES = {"shineon_last_error": C.c_char_p, "shineon_launch_count": C.c_uint64,
              "shineon_conv2d_wgrad_workspace_bytes": C.c_size_t,

@@ -1,0 +1,4 @@
+"""models/networks/attention/__init__.py: the attention layers selectable by name."""
+from . import sagan
+
+ATTENTION_TYPES = {"sagan": sagan.SelfAttention}

@@ -709,6 +709,72 @@ def image_to_u8(x):
     return y
 
 
+# ----------------------------------------------------------------------------- SAMS generator passes
+def chan_stats(x):
+    """x: f32 NHWC [N,H,W,C] -> f64 [N*C*2] per-(image, channel) sum / sum of squares (InstanceNorm statistics)."""
+    x = _req(x, name="x")
+    N, H, W, Cc = x.shape
+    ws = torch.empty(N * Cc * 2, dtype=torch.float64, device=x.device)
+    check(_lib.load().shineon_chan_stats(_p(x), _p(ws), N, H * W, Cc, _stream()), "shineon_chan_stats")
+    return ws
+
+
+def spade_modulate(x, gb, *, stats_ws=None, nscale=None, nshift=None, eps=1e-5, act=None, act_param=0.0, want_f32=False,
+                   want_planes=True, prec=None, out_f32=None, out_f32_coffset=0, out_planes=None):
+    """SPADE.forward's `norm(x) * (1 + gamma) + beta` (+ the activation applied next), spade.py:68-84.
+    x: f32 NHWC [N,H,W,C]; gb: f32 NHWC [N,H,W,>=2C] = (1 + gamma | beta) from one stacked conv.
+    stats_ws -> InstanceNorm2d; nscale/nshift [C] -> eval-mode BatchNorm2d(affine=False); neither -> no normalisation.
+    out_f32 may be a wider NHWC buffer (the stacked tensor of AttentiveMultiSpade): written at channel out_f32_coffset."""
+    x, gb = _req(x, name="x"), _req(gb, name="gamma_beta")
+    N, H, W, Cc = x.shape
+    assert gb.shape[:3] == x.shape[:3] and gb.shape[3] >= 2 * Cc
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty_like(x)
+    if want_planes and out_planes is None:
+        out_planes = Planes(N, H, W, Cc, prec=prec, device=x.device)
+    mode = 1 if stats_ws is not None else (2 if nscale is not None else 0)
+    yf = C_void(0) if out_f32 is None else C_void(_req(out_f32, name="out_f32").data_ptr() + 4 * out_f32_coffset)
+    check(_lib.load().shineon_spade_modulate(_p(x), _p(stats_ws), _p(nscale), _p(nshift), _p(gb), gb.shape[3], yf,
+                                             out_f32.shape[3] if out_f32 is not None else Cc,
+                                             out_planes._ptr(out_planes.hi) if out_planes else _p(None),
+                                             out_planes._ptr(out_planes.lo) if out_planes else _p(None), N, H, W, Cc,
+                                             out_planes.cstride if out_planes else Cc, float(eps), mode, ACT[act],
+                                             float(act_param), out_planes.fmt if out_planes else 0, _stream()),
+          "shineon_spade_modulate")
+    return out_f32, out_planes
+
+
+def nearest_resize_nhwc(x, scale_factor):
+    """nn.Upsample(scale_factor) (nearest) of an f32 NHWC tensor (sams_generator.py:295-310)."""
+    x = _req(x, name="x")
+    N, Hs, Ws, Cc = x.shape
+    H, W = int(Hs * scale_factor), int(Ws * scale_factor)  # floor, like F.interpolate's output size
+    y = torch.empty(N, H, W, Cc, dtype=torch.float32, device=x.device)
+    check(_lib.load().shineon_nearest_resize_nhwc(_p(x), _p(y), N, Hs, Ws, H, W, Cc, 1.0 / scale_factor, 1.0 / scale_factor,
+                                                  _stream()), "shineon_nearest_resize_nhwc")
+    return y
+
+
+def nearest_resize_planes(x, size, prec=None):
+    """F.interpolate(x, size, mode="nearest") of an f32 NCHW tensor, as conv-operand Planes [N,H,W,pad64(C)] (spade.py:74)."""
+    x = _req(x, name="segmap")
+    N, Cc, Hs, Ws = x.shape
+    H, W = size
+    out = Planes(N, H, W, Cc, prec=prec, device=x.device, zero_pad=False)  # the kernel writes the padding channels
+    check(_lib.load().shineon_nearest_resize_planes(_p(x), N, Cc, Hs, Ws, _p(out.hi), _p(out.lo), H, W, out.cpad, Hs / H, Ws / W,
+                                                    out.fmt, _stream()), "shineon_nearest_resize_planes")
+    return out
+
+
+def add_nhwc(a, b, out=None):
+    a, b = _req(a, name="a"), _req(b, name="b")
+    assert a.shape == b.shape
+    if out is None:
+        out = torch.empty_like(a)
+    check(_lib.load().shineon_add_nhwc(_p(a), _p(b), _p(out), a.numel(), _stream()), "shineon_add_nhwc")
+    return out
+
+
 # ----------------------------------------------------------------------------- FlowNet2 glue
 def flownet_normalize(inputs, rgb_max=1.0):
     inputs = _req(inputs, name="inputs")

@@ -39,9 +39,15 @@ def main():
     prof = []
     ops.PROFILE = prof
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cuprof = os.environ.get("SHINEON_CUPROF") == "1"  # ncu --profile-from-start off: capture exactly this step
+    if cuprof:
+        torch.cuda.profiler.start()
     e0.record()
     call()
     e1.record()
+    if cuprof:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     ops.PROFILE = None
     torch.cuda.synchronize()
     total = e0.elapsed_time(e1)
