@@ -542,6 +542,13 @@ int shineon_nearest_resize_planes(const float* x, int N, int C, int Hs, int Ws, 
 /* y = a + b over n f32 elements (the residual x_s + dx of AnySpadeResBlock.forward, spade.py:160); y may alias a or b. */
 int shineon_add_nhwc(const float* a, const float* b, float* y, long n, shineon_stream_t stream);
 
+/* The tail of SamsModel.generate_n_frames (models/sams_model.py:226-236): gen_out f32 NHWC [B,H,W,Cg] = frame (3) [+ blend
+ * weight (1)]; out (one frame slot of the [b,n,3,h,w] buffer, batch stride out_bstride floats, NCHW) =
+ * (1 - w) * warped_prev + w * frame when warped_prev (f32 NCHW [B,3,H,W], the Resample2d of the last frame) is given
+ * (Cg == 4), else the frame (Cg == 3). */
+int shineon_sams_flow_blend(const float* gen_out, int Cg, const float* warped_prev, float* out, long out_bstride, int B,
+                            int H, int W, shineon_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

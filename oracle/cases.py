@@ -26,11 +26,11 @@ FLOWNET2_B16 = 16  # BASELINE configs[3] batch
 
 # SAMS generator: name -> (hparams overrides, batch, H, W)
 _SAMS_BASE = dict(norm_G="spectralspadesyncbatch3x3", ngf_base=2, ngf_pow_outer=6, ngf_pow_inner=10, ngf_pow_step=1, num_middle=3,
-                  attention_middle_indices=[], attention_decoder_indices=[], encoder_input="agnostic", n_frames_total=1,
+                  attention_middle_indices=[], attention_decoder_indices=[], encoder_input="agnostic", n_frames_total=1, n_frames_now=1,
                   flow_warp=False, activation="gelu", person_inputs=["agnostic", "densepose"], cloth_inputs=["cloth"])
 SAMS_CASES = {
     # three-level network, 3-frame window (two previous frames feed the encoder), spectral norm + eval-mode batch norm
-    "sams_small": (dict(_SAMS_BASE, ngf_pow_outer=4, ngf_pow_inner=6, num_middle=2, n_frames_total=3, flow_warp=True), 2, 64, 48),
+    "sams_small": (dict(_SAMS_BASE, ngf_pow_outer=4, ngf_pow_inner=6, num_middle=2, n_frames_total=3, n_frames_now=3, flow_warp=True), 2, 64, 48),
     # instance norm, no spectral norm, LeakyReLU/ReLU activations, AttentiveMultiSpade in the middle (48 px) and the first
     # decoder layer (192 px), single-frame (zero previous frame), cocopose as a fourth label map
     "sams_instance_attn": (dict(_SAMS_BASE, norm_G="spadeinstance3x3", activation="relu", ngf_pow_outer=4, ngf_pow_inner=6,
@@ -54,6 +54,21 @@ def sams_inputs(name):
     prev = torch.rand(B, n - 1, 3, H, W, generator=g) * 2 - 1
     prev_maps = torch.randn(B, n - 1, CHANNELS[over["encoder_input"].upper()], H, W, generator=g)
     return prev, prev_maps, maps
+
+
+def sams_model_batch(name):
+    """The batch dict SamsModel.generate_n_frames reads (models/sams_model.py:204-238): [b, n, c, h, w] per key."""
+    from oracle.sams import CHANNELS
+
+    over, B, H, W = SAMS_CASES[name]
+    g = _g(name + ":model")
+    n = over["n_frames_total"]
+    keys = sorted(set(over["person_inputs"] + over["cloth_inputs"] + [over["encoder_input"]]))
+    batch = {k: torch.randn(B, n, CHANNELS[k.upper()], H, W, generator=g) for k in keys}
+    batch["image"] = torch.rand(B, n, 3, H, W, generator=g) * 2 - 1
+    if over["flow_warp"]:
+        batch["flow"] = torch.randn(B, n, 2, H, W, generator=g) * 2
+    return batch
 
 
 def _g(name):

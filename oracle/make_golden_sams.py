@@ -36,5 +36,22 @@ def main():
             _save(name, shapes, out=cases.subsample(out, 4 if H >= 256 else 1))
 
 
+def model_golden(name="sams_small"):
+    """SamsModel.generate_n_frames of the unmodified reference (Resample2d routed to the pinned CPU oracle, its only
+    implementation being CUDA): the whole frame buffer after n_frames_total generator passes with flow blending."""
+    ref_shim.install()
+    ref_shim.patch_native_ops_with_oracle()
+    from models.sams_model import SamsModel
+
+    over = cases.SAMS_CASES[name][0]
+    with torch.no_grad():
+        m = SamsModel(ref_shim.hparams(**over)).eval()
+        shapes = weights.shapes_of(m)
+        m.load_state_dict(weights.fix_spectral(weights.synth_state_dict(shapes, SEED)), strict=True)
+        last, _, frames = m.generate_n_frames(cases.sams_model_batch(name))
+        _save(name + "_model", shapes, last=last, frames=frames)
+
+
 if __name__ == "__main__":
+    model_golden()
     main()

@@ -139,3 +139,40 @@ def generator_forward(sd, hp, prev_frames, prev_labelmaps, labelmaps):
         else:
             x = F.conv2d(x, sd[f"decode_layers.{i}.weight"], sd[f"decode_layers.{i}.bias"], padding=1)
     return x
+
+
+def prev_frames_and_maps(hp, batch, fIdx, all_G):
+    """SamsModel.get_prev_frames_and_maps (models/sams_model.py:240-271): the window of previously generated frames (a ring
+    over the frame buffer) and the encoder label maps of the frames before fIdx, zero-padded at the front."""
+    enc = batch[hp.encoder_input]
+    n = hp.n_frames_total
+    if n == 1:
+        return torch.zeros_like(all_G), torch.zeros_like(enc)
+    n_prev = n - 1
+    idx = torch.tensor([(i + 1) % n for i in range(fIdx, fIdx + n_prev)])
+    prev = torch.index_select(all_G, 1, idx)
+    b, _, c, h, w = enc.shape
+    start = n_prev - fIdx
+    maps = torch.cat((torch.zeros(b, start, c, h, w), enc[:, start:-1]), dim=1)
+    return prev, maps
+
+
+def generate_n_frames(sd, hp, batch, resample):
+    """SamsModel.generate_n_frames (models/sams_model.py:204-238); frames before n_frames_total - n_frames_now stay zero
+    (the reference's progressive-training window).  sd: generator.* keys
+    stripped.  Returns (last frame, all generated frames [b,n,3,h,w])."""
+    inputs = hp.person_inputs + hp.cloth_inputs
+    all_G = torch.zeros_like(batch["image"])
+    flows = torch.unbind(batch["flow"], dim=1) if hp.flow_warp else None
+    fake = None
+    for f in range(hp.n_frames_total - (getattr(hp, "n_frames_now", None) or hp.n_frames_total), hp.n_frames_total):
+        maps = {k: batch[k][:, f] for k in inputs}
+        prev, prev_maps = prev_frames_and_maps(hp, batch, f, all_G)
+        out = generator_forward(sd, hp, prev, prev_maps, maps)
+        fake, wmask = out[:, :3], out[:, 3:]
+        if hp.flow_warp:
+            last = all_G[:, f - 1].clone() if f > 0 else torch.zeros_like(all_G[:, f])
+            warped = resample(last.contiguous(), flows[f].contiguous())
+            fake = (1 - wmask) * warped + wmask * fake
+        all_G[:, f] = fake
+    return fake, all_G

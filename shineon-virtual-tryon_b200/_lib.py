@@ -136,6 +136,7 @@ SIGNATURES = {
     "shineon_nearest_resize_nhwc": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p],
     "shineon_nearest_resize_planes": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_i, c_p],
     "shineon_add_nhwc": [c_p, c_p, c_p, C.c_long, c_p],
+    "shineon_sams_flow_blend": [c_p, c_i, c_p, c_p, C.c_long, c_i, c_i, c_i, c_p],
 }
 _RESTYPES = {"shineon_last_error": C.c_char_p, "shineon_launch_count": C.c_uint64,
              "shineon_conv2d_wgrad_workspace_bytes": C.c_size_t,

@@ -156,9 +156,38 @@ __global__ void __launch_bounds__(256) add_nhwc_kernel(const float* a, const flo
     for (long e = n4 * 4 + threadIdx.x; e < n; e += blockDim.x) y[e] = a[e] + b[e];
 }
 
+// SamsModel.generate_n_frames' tail (models/sams_model.py:226-236): split the generator output into the frame and the
+// blend weight, fake = (1 - w) * warped_prev + w * frame (flow_warp) or the frame itself; NHWC in, NCHW frame slot out.
+__global__ void __launch_bounds__(256)
+    sams_flow_blend_kernel(const float* __restrict__ g, int Cg, const float* __restrict__ warped, float* __restrict__ out,
+                           long out_bstride, int HW) {
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= HW) return;
+  const float* gp = g + ((long)b * HW + p) * Cg;
+  float r[3] = {gp[0], gp[1], gp[2]};
+  if (warped) {
+    const float w = gp[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) r[c] = (1.f - w) * __ldg(warped + ((long)b * 3 + c) * HW + p) + w * r[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[(long)b * out_bstride + (long)c * HW + p] = r[c];
+}
+
 }  // namespace shineon
 
 using namespace shineon;
+
+extern "C" int shineon_sams_flow_blend(const float* gen_out, int Cg, const float* warped_prev, float* out, long out_bstride,
+                                       int B, int H, int W, shineon_stream_t stream) {
+  SHINEON_REQUIRE(gen_out && out && B > 0 && B <= 65535 && H > 0 && W > 0, "sams_flow_blend: bad argument");
+  SHINEON_REQUIRE(Cg == (warped_prev ? 4 : 3), "sams_flow_blend: generator output has %d channels, expected %d", Cg, warped_prev ? 4 : 3);
+  SHINEON_REQUIRE(out_bstride >= 3l * H * W, "sams_flow_blend: out_bstride");
+  dim3 grid(cdiv(H * W, 256), B);
+  sams_flow_blend_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gen_out, Cg, warped_prev, out, out_bstride, H * W);
+  return after_launch("sams_flow_blend_kernel");
+}
 
 extern "C" int shineon_chan_stats(const float* x, double* stats_ws, int N, int HW, int C, shineon_stream_t stream_) {
   SHINEON_REQUIRE(x && stats_ws && N > 0 && N <= 65535 && HW > 0 && C > 0, "chan_stats: bad argument");

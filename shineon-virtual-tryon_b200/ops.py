@@ -775,6 +775,19 @@ def add_nhwc(a, b, out=None):
     return out
 
 
+def sams_flow_blend(gen_out, out_frame, warped_prev=None):
+    """gen_out: f32 NHWC [B,H,W,3|4]; out_frame: f32 [B,3,H,W] view of one frame slot (batch-strided); see the C ABI."""
+    gen_out = _req(gen_out, name="gen_out")
+    B, H, W, Cg = gen_out.shape
+    assert out_frame.is_cuda and out_frame.dtype == torch.float32 and tuple(out_frame.shape) == (B, 3, H, W)
+    assert out_frame.stride()[1:] == (H * W, W, 1), "frame slot must be dense per image"
+    if warped_prev is not None:
+        warped_prev = _req(warped_prev, name="warped_prev")
+    check(_lib.load().shineon_sams_flow_blend(_p(gen_out), Cg, _p(warped_prev), _p(out_frame), out_frame.stride(0), B, H, W,
+                                              _stream()), "shineon_sams_flow_blend")
+    return out_frame
+
+
 # ----------------------------------------------------------------------------- FlowNet2 glue
 def flownet_normalize(inputs, rgb_max=1.0):
     inputs = _req(inputs, name="inputs")

@@ -101,5 +101,42 @@ def main():
                       "tflops": round(49.56 * B / ms, 2), "frac_of_measured_bf16_peak": round(49.56 * B / ms / PEAK_TF, 4)}), flush=True)
 
 
+def sams():
+    """the reference's default SamsGenerator (64..1024 features, 3 middle blocks, agnostic + densepose + cloth
+    label maps) on 256x192 frames; FLOPs counted from the module tree (2 * MAC of every conv the reference runs)."""
+    import argparse
+
+    from oracle import cases, weights
+    from shineon_virtual_tryon_b200.networks.sams import SamsGenerator
+
+    dev = torch.device("cuda", 0)
+    hp = argparse.Namespace(**cases.SAMS_CASES["sams_default"][0])
+    g = SamsGenerator(hp)
+    shapes = {k: tuple(v.shape) for k, v in g.state_dict().items()}
+    g.load_state_dict(weights.fix_spectral(weights.synth_state_dict(shapes, 420)), strict=True)
+    g = g.to(dev).eval()
+    gen = torch.Generator().manual_seed(1)
+    for B in (1, 8):
+        maps = {k: torch.randn(B, c, 256, 192, generator=gen).to(dev) for k, c in (("agnostic", 4), ("cloth", 3), ("densepose", 3))}
+        from shineon_virtual_tryon_b200 import ops
+
+        prof = []
+        with torch.no_grad():
+            ms = timeit(lambda: g(None, None, maps), iters=5)
+            ops.PROFILE = prof
+            g(None, None, maps)
+            ops.PROFILE = None
+            torch.cuda.synchronize()
+        gf = sum(r[0] for r in prof) / 1e9
+        tconv = sum(r[1].elapsed_time(r[2]) for r in prof)
+        print(json.dumps({"config": f"SURVEY 8f N3: SamsGenerator default architecture, batch {B} x 256x192, fp16x3", "ms": round(ms, 3),
+                          "frames_per_s": round(B * 1e3 / ms, 2), "conv_gflop": round(gf, 1), "conv_launches": len(prof),
+                          "conv_ms_eager": round(tconv, 3), "tflops": round(gf / ms, 1),
+                          "frac_of_measured_bf16_peak": round(gf / ms / PEAK_TF, 4)}), flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "--sams" in sys.argv:
+        sams()
+    else:
+        main()

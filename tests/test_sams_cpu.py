@@ -46,3 +46,26 @@ def test_spectral_eval_weight_is_normalised():
     sigma = torch.dot(sd[k + ".weight_u"], torch.mv(w, sd[k + ".weight_v"]))
     top = torch.linalg.matrix_norm(w, ord=2)
     assert 0.6 < float(sigma / top) <= 1.0 + 1e-5
+
+
+def test_sams_model_oracle_matches_reference_golden():
+    """generate_n_frames restated (oracle/sams.py) against SamsModel.generate_n_frames of the reference."""
+    from oracle import flow_ops as fo
+
+    name = "sams_small"
+    seed, shapes, gold = load_golden(name + "_model")
+    sd = weights.fix_spectral(weights.synth_state_dict(shapes, seed))
+    gsd = {k[len("generator."):]: v for k, v in sd.items() if k.startswith("generator.")}
+    with torch.no_grad():
+        last, frames = sams.generate_n_frames(gsd, _hp(name), cases.sams_model_batch(name), fo.resample2d_fwd)
+    assert_close(frames, gold["frames"], atol=2e-5, rtol=1e-4, what="frames")
+    assert_close(last, gold["last"], atol=2e-5, rtol=1e-4, what="last")
+
+
+def test_sams_model_state_dict_matches_reference():
+    from shineon_virtual_tryon_b200.models import find_model_using_name
+
+    _, shapes, _ = load_golden("sams_small_model")
+    hp = argparse.Namespace(**cases.SAMS_CASES["sams_small"][0], is_train=False)
+    mine = {k: tuple(v.shape) for k, v in find_model_using_name("sams")(hp).state_dict().items()}
+    assert mine == shapes

@@ -97,3 +97,30 @@ def test_nearest_resize_matches_interpolate(cuda, factor):
         p = ops.nearest_resize_planes(seg.cuda(), size)
         want = F.interpolate(seg, size=size, mode="nearest")
         assert_close(p.float(), want, atol=1e-6, rtol=1e-6, what=f"planes {size}")  # hi + lo carries 22 mantissa bits
+
+
+def test_sams_model_generate_n_frames(cuda):
+    """SamsModel.generate_n_frames (3-frame window, flow blend through Resample2d) against the oracle and the golden made by
+    the reference's own SamsModel; the frame buffer feeds back into the encoder, so errors would compound."""
+    from shineon_virtual_tryon_b200.models import find_model_using_name
+    from oracle import flow_ops as fo
+
+    name = "sams_small"
+    seed, shapes, gold = load_golden(name + "_model")
+    sd = weights.fix_spectral(weights.synth_state_dict(shapes, seed))
+    hp = argparse.Namespace(**cases.SAMS_CASES[name][0], is_train=False)
+    m = find_model_using_name("sams")(hp)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    batch = cases.sams_model_batch(name)
+    last, maps, frames = m.generate_n_frames({k: v.cuda() for k, v in batch.items()})
+    torch.cuda.synchronize()
+    gsd = {k[len("generator."):]: v for k, v in sd.items() if k.startswith("generator.")}
+    with torch.no_grad():
+        want_last, want_frames = osams.generate_n_frames(gsd, hp, batch, fo.resample2d_fwd)
+    assert sorted(maps) == sorted(hp.person_inputs + hp.cloth_inputs)
+    err = assert_close(frames, want_frames, what="frames vs oracle")
+    assert_close(last, want_last, what="last frame vs oracle")
+    assert_close(frames.cpu(), gold["frames"], what="frames vs reference golden")
+    assert_close(last.cpu(), gold["last"], what="last frame vs reference golden")
+    print(f"generate_n_frames: max abs err {err:.2e}")
