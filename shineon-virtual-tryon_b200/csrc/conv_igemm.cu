@@ -1003,18 +1003,21 @@ static int conv2d_igemm_launch(const shineon_conv2d_params* p, ConvArgs& a, cuda
   CUtensorMap tAh, tAl, tBh, tBl;
   // C = channel extent the boxes may touch, Cs = pixel pitch (both in elements)
   const cuuint64_t Cw = (cuuint64_t)p->cin_pad, C = (cuuint64_t)a.x_cstride, H = (cuuint64_t)p->H, W = (cuuint64_t)p->W, N = (cuuint64_t)p->N;
+  // a channel window of a wider (concat) buffer: the bytes next to a pixel's window belong to another tensor, so a 256-byte L2
+  // promotion would fetch them for nothing (measured: 2.0x DRAM over-read on the 64-of-128-channel U-Net skip window)
+  const bool promo = a.x_cstride == p->cin_pad;
   if (p->stride == 1) {
     cuuint64_t dims[4] = {Cw, W, H, N};
     cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.nb};
-    if ((rc = encode_map(&tAh, p->x_hi, 4, dims, strides, box, "A hi", p->plane_fmt))) return rc;
-    if (split && (rc = encode_map(&tAl, p->x_lo, 4, dims, strides, box, "A lo", p->plane_fmt))) return rc;
+    if ((rc = encode_map(&tAh, p->x_hi, 4, dims, strides, box, "A hi", p->plane_fmt, promo))) return rc;
+    if (split && (rc = encode_map(&tAl, p->x_lo, 4, dims, strides, box, "A lo", p->plane_fmt, promo))) return rc;
   } else {
     cuuint64_t dims[5] = {C + Cw, W / 2, 2, H / 2, N};  // column pair: [q*Cs + c], c < cin_pad
     cuuint64_t strides[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
     cuuint32_t box[5] = {(cuuint32_t)kBlockK, (cuuint32_t)a.bw, 1, (cuuint32_t)a.bh, (cuuint32_t)a.nb};
-    if ((rc = encode_map(&tAh, p->x_hi, 5, dims, strides, box, "A hi s2", p->plane_fmt))) return rc;
-    if (split && (rc = encode_map(&tAl, p->x_lo, 5, dims, strides, box, "A lo s2", p->plane_fmt))) return rc;
+    if ((rc = encode_map(&tAh, p->x_hi, 5, dims, strides, box, "A hi s2", p->plane_fmt, promo))) return rc;
+    if (split && (rc = encode_map(&tAl, p->x_lo, 5, dims, strides, box, "A lo s2", p->plane_fmt, promo))) return rc;
   }
   {
     const cuuint64_t K = (cuuint64_t)p->kh * p->kw * Cw;

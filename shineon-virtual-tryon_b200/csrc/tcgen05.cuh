@@ -153,13 +153,14 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 inline int encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box, const char* what, int fmt) {
+                      const cuuint32_t* box, const char* what, int fmt, bool promote_256 = true) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(SHINEON_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found (driver too old?)");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(tm, fmt == SHINEON_FMT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  promote_256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SHINEON_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed: CUresult %d", what, (int)r);
   return SHINEON_OK;
 }
