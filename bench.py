@@ -41,9 +41,11 @@ def parse():
     ap.add_argument("--fast", action="store_true", help="also report the bf16x3 / fp16 / bf16 modes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="try-on workload: launch every step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--workload", default="tryon", choices=["tryon", "train"],
+    ap.add_argument("--workload", default="tryon", choices=["tryon", "train", "flow"],
                     help="tryon = BASELINE configs[2] (the headline; default); train = configs[4]: U-Net stage training step, "
-                         "data-parallel over the GPUs with the NCCL gradient all-reduce")
+                         "data-parallel over the GPUs with the NCCL gradient all-reduce; flow = configs[3]: FlowNet2 two-frame "
+                         "forward + confidence at batch 16, with the Correlation / Resample2d HBM rooflines")
+    ap.add_argument("--flow-batch", type=int, default=16, help="frame pairs per GPU per step (configs[3]: 16)")
     ap.add_argument("--train-batch", type=int, default=4, help="samples per GPU per optimiser step (recipe: 4)")
     ap.add_argument("--train-precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--train-eager", action="store_true", help="no CUDA graph: all-reduce overlapped inside the backward")
@@ -408,9 +410,210 @@ def run_train(args, rank, world):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------- flow workload (configs[3])
+FLOW_METRIC = "flow pairs/sec @256x192 (FlowNet2 correlation + conv stack + warp confidence)"
+FLOW_GFLOP_PER_PAIR = 49.56  # conv / deconv FLOPs of FlowNetC + S + S + SD + Fusion per pair
+
+
+def flow_model():
+    import torch
+
+    from shineon_virtual_tryon_b200.models.flownet import FlowNet
+
+    torch.manual_seed(420)
+    net = FlowNet()  # no checkpoint offline: the reference's module tree with seeded xavier weights
+    for m in net.modules():
+        if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)):
+            torch.nn.init.xavier_uniform_(m.weight)
+            if m.bias is not None:
+                torch.nn.init.uniform_(m.bias, -0.1, 0.1)
+    return net.eval()
+
+
+def flow_frames(B, seed, pinned=False):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    base = torch.nn.functional.interpolate(torch.rand(B, 3, H // 8 + 2, W // 8 + 2, generator=g), size=(H + 16, W + 16),
+                                           mode="bilinear", align_corners=False)
+    im1 = (base[:, :, 8:8 + H, 8:8 + W] + 0.05 * torch.rand(B, 3, H, W, generator=g)).clamp(0, 1).contiguous()
+    im2 = (base[:, :, 5:5 + H, 10:10 + W] + 0.05 * torch.rand(B, 3, H, W, generator=g)).clamp(0, 1).contiguous()
+    return (im1.pin_memory(), im2.pin_memory()) if pinned else (im1, im2)
+
+
+def cpu_flow_pps(pairs=1, iters=3, warmup=1):
+    """Oracle port of FlowNet.compute_flow_and_conf (oracle/flownet2.py over oracle/flow_ops.py: the reference's module
+    graph with its three CUDA-only ops restated for the CPU; the reference itself has no CPU path for this model)."""
+    import torch
+
+    from oracle import flownet2 as of2
+
+    sd = {k: v.detach() for k, v in flow_model().flowNet.state_dict().items()}
+    im1, im2 = flow_frames(pairs, 7)
+    ncpu = os.cpu_count() or 1
+    cores = min(ncpu, 32)
+    torch.set_num_threads(cores)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + iters):
+            t0 = time.perf_counter()
+            of2.compute_flow_and_conf(sd, im1, im2)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return pairs / med, cores, f"{pairs} pair(s)/step, {len(times)} timed iterations, median; {cores} of {ncpu} host threads", med
+
+
+def run_flow(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from shineon_virtual_tryon_b200 import _lib, distributed, ops
+
+    _route_nccl_log()
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa = bind_local_numa(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    distributed.init_process_group("nccl", device=dev)
+    net = flow_model().to(dev)
+    net.cuda_graph = True
+    B = args.flow_batch
+    n_sets = 4  # one captured graph per input-buffer pair (FlowNet keeps 4); every step also streams > 2 GB of activations
+    sets = [tuple(t.to(dev) for t in flow_frames(B, 300 + rank + 1000 * i)) for i in range(n_sets)]
+    host = flow_frames(B, 300 + rank, pinned=True)
+    stage = tuple(torch.empty_like(t, device=dev) for t in host)
+    out_h = (torch.empty(B, 2, H, W).pin_memory(), torch.empty(B, 1, H, W).pin_memory())
+
+    def timed(fn, steps, sampler=None):
+        distributed.barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        distributed.barrier()
+        clocks = sampler.stop() if sampler else None
+        return distributed.max_over_ranks(e0.elapsed_time(e1), dev), clocks
+
+    step = lambda i: net(*sets[i % n_sets])
+
+    def e2e_step(i):
+        stage[0].copy_(host[0], non_blocking=True)
+        stage[1].copy_(host[1], non_blocking=True)
+        flow, conf = net(*stage)
+        out_h[0].copy_(flow, non_blocking=True)
+        out_h[1].copy_(conf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the flow before asking for the next pair batch
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, n_sets)):
+            step(i)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        ms, clocks = timed(step, args.steps, ClockSampler(local) if rank == 0 else None)
+        prof = []
+        net.cuda_graph = False
+        l1 = _lib.launch_count()
+        step(0)
+        launches_per_step = _lib.launch_count() - l1
+        ops.PROFILE = prof
+        ms_prof, _ = timed(step, args.steps)
+        ops.PROFILE = None
+        net.cuda_graph = True
+        torch.cuda.synchronize()
+        for i in range(max(2, args.warmup)):
+            e2e_step(i)
+        ms_e2e, _ = timed(e2e_step, args.steps)
+    conv_ms = sum(r[1].elapsed_time(r[2]) for r in prof)
+    conv_flops = sum(r[0] for r in prof)
+    peaks, peak_src = read_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+    ach = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+
+    # HBM rooflines of the two gather ops at the configs[3] shapes (SURVEY 8d algorithmic bytes), L2 flushed per launch
+    def op_time(fn, iters=10):
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    g = torch.Generator().manual_seed(5)
+    f1, f2 = torch.randn(B, 256, 32, 24, generator=g).to(dev), torch.randn(B, 256, 32, 24, generator=g).to(dev)
+    img, flw = torch.rand(B, 3, H, W, generator=g).to(dev), (torch.randn(B, 2, H, W, generator=g) * 4).to(dev)
+    p1, p2 = ops.nchw_to_planes(f1), ops.nchw_to_planes(f2)
+    t_corr = op_time(lambda: ops.correlation_planes(p1, p2, 256, 20, 20, 2))
+    t_res = op_time(lambda: ops.resample2d_fwd(img, flw))
+    corr_bytes = B * (2 * 256 * 2 * 2 + 441 * 4) * 32 * 24  # both feature maps as hi/lo 16-bit planes in, f32 cost volume out
+    res_bytes = B * 8 * H * W * 4
+    gather_ops = {
+        "correlation": {"shape": f"2 x [{B},256,32,24] -> [{B},441,32,24]", "ms": t_corr, "algorithmic_bytes": corr_bytes,
+                        "GB/s": corr_bytes / t_corr / 1e6, "frac_of_hbm_peak": corr_bytes / t_corr / 1e6 / peak_hbm,
+                        "form": "per-image tcgen05 GEMM over the conv3 planes + displacement gather (ops.correlation_planes)"},
+        "resample2d": {"shape": f"[{B},3,256,192] by N(0, 4 px) flow", "ms": t_res, "algorithmic_bytes": res_bytes,
+                       "GB/s": res_bytes / t_res / 1e6, "frac_of_hbm_peak": res_bytes / t_res / 1e6 / peak_hbm},
+        "peak": peak_hbm, "peak_source": f"{peak_src} hbm_gbs", "l2": "flushed before every timed launch"}
+
+    total = B * world * args.steps
+    pps = lambda t: total / (t * 1e-3)
+    line = {
+        "metric": FLOW_METRIC, "value": pps(ms), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16x3 (hi/lo-split fp16 operands, 3 tcgen05 MMAs per product, fp32 TMEM accumulate; fp32-grade)",
+        "data": "synthetic",
+        "config": {"workload": "configs[3]: FlowNet2 (FlowNetC with the 441-displacement Correlation, 2 x FlowNetS, FlowNetSD, "
+                               "FlowNetFusion; Resample2d / ChannelNorm glue) two-frame forward + flow confidence, 256x192",
+                   "pairs_per_step_per_gpu": B, "parallelism": f"dp{world} (pairs sharded, no collective)",
+                   "weights": "seeded xavier (no checkpoint offline)", "cuda_graph": True, "cpu_binding": numa,
+                   "l2": f"{n_sets} input sets cycled; each step streams > 2 GB of activations through HBM (no flush needed)"},
+        "e2e": {"value": pps(ms_e2e), "unit": "pairs/s", "h2d_bytes_per_step": 2 * B * 3 * H * W * 4 * world,
+                "d2h_bytes_per_step": B * 3 * H * W * 4 * world, "ms_per_step": ms_e2e / args.steps,
+                "api": "models.flownet.FlowNet.forward: pinned f32 frame pairs -> H2D -> FlowNet2 + confidence -> flow, conf D2H"},
+        "gpu_launches": launches_per_step * args.steps * world, "clocks": clocks,
+        "roofline": {"kernel": "conv_igemm_kernel (tcgen05 implicit-GEMM conv / deconv, all launches of the step incl. the "
+                               "cost-volume GEMM)", "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": ach / peak_tf, "peak_source": f"{peak_src} bf16_tflops_sustained",
+                     "algorithmic_gflop_per_pair": conv_flops / (B * args.steps) / 1e9, "survey_gflop_per_pair": FLOW_GFLOP_PER_PAIR,
+                     "conv_launches_per_step": len(prof) // args.steps, "conv_share_of_eager_step": conv_ms / ms_prof,
+                     "whole_step_frac_of_tensor_peak": FLOW_GFLOP_PER_PAIR * 1e9 * B * args.steps / (ms * 1e-3) / 1e12 / peak_tf,
+                     "measured_on": f"the same steps launched eagerly after the timed region ({ms_prof / args.steps:.3f} ms/step eager vs "
+                                    f"{ms / args.steps:.3f} replayed)", "traffic": None},
+        "gather_ops": gather_ops,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample, _ = cpu_flow_pps(1, iters=5)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank):
     if rank != 0:
+        return
+    if args.workload == "flow":
+        v, cores, sample, med = cpu_flow_pps(1, iters=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+        print(json.dumps({
+            "impl": "reference", "metric": FLOW_METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[3]: FlowNet2 two-frame forward + confidence, CPU oracle port", "pairs_per_step": 1},
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
         return
     if args.workload == "train":
         sps, cores, sample, med = cpu_train_sps(2, iters=max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
@@ -630,6 +833,8 @@ def main():
         run_reference(args, rank)
     elif args.workload == "train":
         run_train(args, rank, world)
+    elif args.workload == "flow":
+        run_flow(args, rank, world)
     else:
         run_b200(args, rank, world)
 
