@@ -124,6 +124,14 @@ class FlatGradAllReducer:
         self._overlap = False
         return self.finish()
 
+    @staticmethod
+    def active():
+        return dist.is_initialized() and dist.get_world_size() > 1
+
+    @staticmethod
+    def inv_world():
+        return 1.0 / (dist.get_world_size() if dist.is_initialized() else 1)
+
     def grad_view(self, i):
         """Where the backward pass writes the gradient of parameter i (no per-parameter .grad tensors to pack)."""
         return self.views[i]

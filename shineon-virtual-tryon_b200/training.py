@@ -32,12 +32,14 @@ def backward_order(unet_generator):
 
 class Trainer:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, accumulated_batches=1, bucket_bytes=32 << 20,
-                 lr_lambda=None, cuda_graph=False, graph_warmup=2):
+                 lr_lambda=None, cuda_graph=False, graph_warmup=2, graph_allreduce=False):
         """cuda_graph=True: after `graph_warmup` eager micro-batches the whole training step (forward, losses, backward:
         ~450 launches, launch-bound at the recipe's batch 4) is captured once into a CUDA graph and replayed; the batch
-        is copied into static buffers.  The gradient all-reduce then runs after the replay instead of inside the
-        backward (bucketed, asynchronous, but not overlapped)."""
-        self.cuda_graph, self.graph_warmup = bool(cuda_graph), int(graph_warmup)
+        is copied into static buffers and the gradient exchange runs after the replay (bucketed, asynchronous, not overlapped
+        with the backward: 90.6 MB over NVLink is ~0.4 ms of a 6 ms step).  graph_allreduce=True (EXPERIMENTAL, off by default)
+        captures the bucketed NCCL all-reduces issued from inside the backward as side-stream nodes of the same graph; on this
+        image (torch 2.11 / NCCL 2.28.9) the 2-GPU capture dead-locked, so the measured configuration is the default."""
+        self.cuda_graph, self.graph_warmup, self.graph_allreduce = bool(cuda_graph), int(graph_warmup), bool(graph_allreduce)
         # two captured variants: [True] the first micro-batch after an optimiser step (the 16-bit weight re-pack is part of
         # the captured work) and [False] the following micro-batches of an accumulation window (weights unchanged: they
         # read the buffers the [True] graph re-packs into)
@@ -89,12 +91,16 @@ class Trainer:
         first = self.micro % self.accumulated_batches == 0  # weights changed since the previous micro-batch
         # the first capture must be of a `first` micro-batch, so the packed-weight buffers every later graph reads are
         # the ones that graph rewrites on each replay
-        if self.cuda_graph and self.micro >= self.graph_warmup and (first or True in self._graphs):
-            res = self._replay(batch, batch_idx, first)
+        if self.cuda_graph and self.micro >= self.graph_warmup and (first or any(k[0] for k in self._graphs)):
+            in_graph = last and self.graph_allreduce and self.reducer.active()
+            res = self._replay(batch, batch_idx, first, in_graph)
             self.micro += 1
             if last:
-                self.reducer.start()
-                inv_world = self.reducer.finish()
+                if in_graph:
+                    inv_world = self.reducer.inv_world()
+                else:
+                    self.reducer.start()
+                    inv_world = self.reducer.finish()
                 self.optimizer_step(inv_world / self.accumulated_batches)
                 self.zero_grad()
             return res
@@ -112,11 +118,13 @@ class Trainer:
             self.zero_grad()
         return res
 
-    def _replay(self, batch, batch_idx, first):
+    def _replay(self, batch, batch_idx, first, exchange=False):
+        """exchange: this micro-batch ends an accumulation window on a multi-rank job -- its graph also holds the bucketed
+        gradient all-reduces, issued by the backward as the buckets complete."""
         tensors = {k: v for k, v in batch.items() if isinstance(v, torch.Tensor)}
         if self._static_batch is None:
             self._static_batch = {k: v.clone() for k, v in tensors.items()}
-        ent = self._graphs.get(first)
+        ent = self._graphs.get((first, exchange))
         if ent is None:
             from . import _lib
 
@@ -125,14 +133,23 @@ class Trainer:
             epoch0 = _engine_util.WEIGHTS_EPOCH[0]
             n0 = _lib.launch_count()
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):  # the NCCL watchdog thread may poll events
-                res = self.model.training_step(self._static_batch, batch_idx)
-            ent = self._graphs[first] = (graph, res, _lib.launch_count() - n0)
+                if exchange:
+                    self.reducer.begin_overlap()
+                    unet_mod.GRAD_READY_HOOK = self.reducer.mark_ready
+                try:
+                    res = self.model.training_step(self._static_batch, batch_idx)
+                finally:
+                    unet_mod.GRAD_READY_HOOK = None
+                if exchange:
+                    self.reducer.end_overlap()  # the waits join NCCL's stream back into the captured one
+            ent = self._graphs[(first, exchange)] = (graph, res, _lib.launch_count() - n0)
             assert _engine_util.WEIGHTS_EPOCH[0] == epoch0
+            with_repack = [v[2] for k, v in self._graphs.items() if k[0]]
             if first:
                 # the re-pack of every trainable layer must have been recorded: compare with the no-repack variant later
                 self.repack_launches = ent[2]
-            elif True in self._graphs:
-                assert ent[2] < self._graphs[True][2], "the weight re-pack was not captured in the post-step graph"
+            elif with_repack:
+                assert ent[2] < max(with_repack), "the weight re-pack was not captured in the post-step graph"
             # the capture only recorded the work: the replay below runs it for this batch
         for k, v in tensors.items():
             self._static_batch[k].copy_(v, non_blocking=True)

@@ -27,9 +27,15 @@ def main():
         prof = []
         ops.PROFILE = prof
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cuprof = os.environ.get("SHINEON_CUPROF") == "1"  # ncu --profile-from-start off: capture exactly this forward
+        if cuprof:
+            torch.cuda.profiler.start()
         e0.record()
         net(im1, im2)
         e1.record()
+        if cuprof:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         ops.PROFILE = None
         torch.cuda.synchronize()
     total = e0.elapsed_time(e1)

@@ -154,7 +154,7 @@ def test_cuda_graph_training_with_accumulation_tracks_the_weights(cuda):
         runs.append([tr.train_batch(batch, i)["loss"].item() for i in range(10)])
         assert tr.steps == 5
         if graph:
-            assert set(tr._graphs) == {True, False} and tr._graphs[True][2] > tr._graphs[False][2]
+            assert set(tr._graphs) == {(True, False), (False, False)} and tr._graphs[(True, False)][2] > tr._graphs[(False, False)][2]
     for a, b in zip(*runs):
         assert abs(a - b) <= 1e-4 * abs(a) + 1e-5, runs
     assert runs[1][-1] < runs[1][0]
