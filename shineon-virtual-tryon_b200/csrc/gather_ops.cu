@@ -1018,6 +1018,8 @@ extern "C" int shineon_tps_grid_sample_fwd(const float* theta, const shineon_tps
   return after_launch("tps_grid_sample_kernel");
 }
 
+int shineon_resample2d_tile(const float* in1, const float* flow, float* out, int B, int C, int H, int W, cudaStream_t stream);  // resample_tile.cu
+
 extern "C" int shineon_resample2d_fwd(const float* in1, const float* flow, float* out, int B, int C, int Hi, int Wi,
                                       int H, int W, int kernel_size, int bilinear, shineon_stream_t stream) {
   SHINEON_REQUIRE(in1 && flow && out, "resample2d_fwd: null pointer");
@@ -1025,6 +1027,10 @@ extern "C" int shineon_resample2d_fwd(const float* in1, const float* flow, float
   if (kernel_size != 1) return fail(SHINEON_ERR_UNSUPPORTED, "resample2d: kernel_size %d (only 1, as the reference uses)", kernel_size);
   if (Hi != H || Wi != W) return fail(SHINEON_ERR_UNSUPPORTED, "resample2d: input %dx%d != flow %dx%d", Hi, Wi, H, W);
   if (B == 0) return SHINEON_OK;
+  if (bilinear && C <= 4 && H >= 32 && W >= 64) {  // shared-memory halo tiles (resample_tile.cu); > 0 = shape does not fit
+    const int rc = shineon_resample2d_tile(in1, flow, out, B, C, H, W, (cudaStream_t)stream);
+    if (rc <= 0) return rc;
+  }
   if (bilinear && C <= 4) {
     constexpr int PPT = 2;
     const dim3 g(cdiv(H * W, 256 * PPT), B);
