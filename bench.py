@@ -125,6 +125,26 @@ def _route_nccl_log():
         os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 
 
+def init_dist_stdout_clean(dev):
+    """Process-group set-up with file descriptor 1 pointed at stderr: NCCL printf()s its version banner to stdout whenever
+    NCCL_DEBUG >= VERSION (init.cc showVersion), whatever NCCL_DEBUG_FILE says, and stdout must carry exactly one JSON line.
+    NCCL_DEBUG itself stays as the caller set it (the driver counts the ranks in the log); the first collective runs inside
+    the redirected region too, since communicators may initialise lazily."""
+    from shineon_virtual_tryon_b200 import distributed
+
+    _route_nccl_log()
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        distributed.init_process_group("nccl", device=dev)
+        distributed.barrier()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def bind_local_numa(local_rank, ranks_on_node):
     """Pin this rank to CPU cores of the NUMA node its GPU hangs off (its share of them), BEFORE any pinned host buffer
     is allocated, so first-touch places the staging buffers next to the GPU's PCIe root.  Best effort: returns a note."""
@@ -314,12 +334,11 @@ def run_train(args, rank, world):
     from shineon_virtual_tryon_b200 import _lib, distributed, ops
     from shineon_virtual_tryon_b200.training import Trainer
 
-    _route_nccl_log()
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bind_local_numa(local, world)
-    distributed.init_process_group("nccl", device=dev)
+    init_dist_stdout_clean(dev)
     model, hp = train_models()
     model = model.to(dev)
     model.set_train_precision(args.train_precision)
@@ -470,12 +489,11 @@ def run_flow(args, rank, world):
 
     from shineon_virtual_tryon_b200 import _lib, distributed, ops
 
-    _route_nccl_log()
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bind_local_numa(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
-    distributed.init_process_group("nccl", device=dev)
+    init_dist_stdout_clean(dev)
     net = flow_model().to(dev)
     net.cuda_graph = True
     B = args.flow_batch
@@ -664,12 +682,11 @@ def run_b200(args, rank, world):
     from shineon_virtual_tryon_b200 import _lib, distributed, ops
     from shineon_virtual_tryon_b200.pipeline import TryOnPipeline
 
-    _route_nccl_log()
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bind_local_numa(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
-    distributed.init_process_group("nccl", device=dev)
+    init_dist_stdout_clean(dev)
     barrier = distributed.barrier
 
     warp, tom = build_models()

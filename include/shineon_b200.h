@@ -200,7 +200,16 @@ typedef struct shineon_conv2d_params {
    * over in registers: 0 = default (16, i.e. 1024 K), < 0 = the whole K in one chain (tensor-core accumulation
    * truncates, so long chains lose accuracy: DESIGN.md section 4) */
   int acc_chunk_kb;
+  /* optional split-K workspace (shineon_conv2d_igemm_fwd only): layers with fewer output tiles than half the SMs and a deep
+   * K loop are cut along K so that tiles x K-slices cover the chip; every slice parks its partial sums here and the last
+   * one to arrive adds them in slice order (bit-reproducible) and runs the epilogue.  Size from
+   * shineon_conv2d_splitk_workspace_bytes() (0: this shape does not split); the first 256-byte-rounded total_tiles ints are
+   * arrival counters that must be ZERO at the first launch (the kernel leaves them zero).  NULL = never split.  One
+   * workspace per concurrently running launch. */
+  void* splitk_ws;
+  size_t splitk_ws_bytes;
 } shineon_conv2d_params;
+size_t shineon_conv2d_splitk_workspace_bytes(const shineon_conv2d_params* p);
 
 int shineon_conv2d_igemm_fwd(const shineon_conv2d_params* p, shineon_stream_t stream);
 /* Small-Cin first layers: the same GEMM with the im2col matrix produced INSIDE the kernel (producer warps gather the

@@ -32,6 +32,7 @@ class Conv2dParams(C.Structure):
         ("out_H", c_i), ("out_W", c_i), ("out_cstride", c_i), ("out_coffset", c_i),
         ("oh_mul", c_i), ("oh_off", c_i), ("ow_mul", c_i), ("ow_off", c_i),
         ("tile_n", c_i), ("stages", c_i), ("stats_ws", c_p), ("acc_chunk_kb", c_i),
+        ("splitk_ws", c_p), ("splitk_ws_bytes", C.c_size_t),
     ]
 
 
@@ -87,6 +88,7 @@ SIGNATURES = {
     "shineon_pack_conv_weight": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_f, c_p],
     "shineon_pack_deconv4x4s2_weight": [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_f, c_p],
     "shineon_conv2d_igemm_fwd": [C.POINTER(Conv2dParams), c_p],
+    "shineon_conv2d_splitk_workspace_bytes": [C.POINTER(Conv2dParams)],
     "shineon_conv2d_im2col_fwd": [C.POINTER(Conv2dParams), c_p, c_i, c_p, c_i, c_p],
     "shineon_conv2d_direct_fwd": [C.POINTER(Conv2dParams), c_p],
     "shineon_nchw_to_planes": [c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
@@ -139,6 +141,7 @@ SIGNATURES = {
     "shineon_sams_flow_blend": [c_p, c_i, c_p, c_p, C.c_long, c_i, c_i, c_i, c_p],
 }
 _RESTYPES = {"shineon_last_error": C.c_char_p, "shineon_launch_count": C.c_uint64,
+             "shineon_conv2d_splitk_workspace_bytes": C.c_size_t,
              "shineon_conv2d_wgrad_workspace_bytes": C.c_size_t,
              "shineon_sagan_attention_bwd_workspace_bytes": C.c_size_t}
 

@@ -64,6 +64,14 @@ struct ConvArgs {
   int out_H, out_W, out_cstride, out_coffset;
   int oh_mul, oh_off, ow_mul, ow_off;
   double* stats;  // [N][Cout][2] per-(image, channel) sum / sum of squares of the f32 output (InstanceNorm), nb == 1 only
+  // split-K (layers with fewer tiles than SMs and a deep K: the 4x3 ... 8x6 levels): work item = (tile, K slice); every
+  // item writes its raw partial accumulator to its own workspace slice, the LAST item of a tile to arrive (per-tile counter)
+  // sums the slices in slice order -- deterministic -- and runs the normal epilogue
+  int ksplit, kb_per_split;  // ksplit == 1: off
+  float* sk_ws;              // [ksplit][m_tiles * 128][sk_ctot]
+  int* sk_cnt;               // [total_tiles], zero before the launch; the finalising item resets its counter
+  int sk_ctot;               // n_tiles * BN
+  long sk_slice;             // floats per slice
 };
 
 // ------------------------------------------------------------------------------------- epilogue
@@ -223,6 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   // current tile's per-channel sum / sum of squares (a.stats), one slot per TMEM lane quarter: every slot has exactly one
   // writer warp and the flush adds the four in a fixed order, so the statistics are reproducible run to run
   __shared__ float s_stat[4][BN][2];
+  __shared__ int s_flag;  // split-K: arrival order of this item among its tile's K slices
 
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -253,6 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   const int tiles_hw = a.tiles_w * a.tiles_h;
+  const int total_items = a.total_tiles * a.ksplit;  // work items: (tile, K slice), the slices of a tile on neighbouring CTAs
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -260,11 +270,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t a_rows = a.nb * a.bh * a.bw;
       const uint32_t tx = kPlanes * (a_rows * (kBlockK * 2) + kBBytes);
       uint32_t g = 0;  // running K-block counter across tiles (ring position)
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int tile = item / a.ksplit, ks = item - tile * a.ksplit;
+        const int kb_lo = ks * a.kb_per_split, kb_hi = min(a.num_kb, kb_lo + a.kb_per_split);
         const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
         const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, tn = mt / tiles_hw;
         const int n0 = tn * a.nb, h0 = th * a.bh, w0 = tw * a.bw, cn0 = nt * BN;
-        for (int kb = 0; kb < a.num_kb; ++kb, ++g) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++g) {
           const int s = g % S;
           const uint32_t ph = (g / S) & 1;
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -307,13 +319,15 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       uint32_t g = 0;
       int it = 0;  // running chunk counter (accumulator ring position)
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        for (int kb0 = 0; kb0 < a.num_kb; kb0 += a.chunk_kb, ++it) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int ks = item % a.ksplit;
+        const int kb_lo = ks * a.kb_per_split, kb_hi = min(a.num_kb, kb_lo + a.kb_per_split);
+        for (int kb0 = kb_lo; kb0 < kb_hi; kb0 += a.chunk_kb, ++it) {
           const int buf = it & 1;
           mbar_wait(bar_tempty + 8 * buf, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
           tc_fence_after();
           const uint32_t tmem_acc = tmem_base + buf * kAccCols;
-          const int kb1 = min(a.num_kb, kb0 + a.chunk_kb);
+          const int kb1 = min(kb_hi, kb0 + a.chunk_kb);
           for (int kb = kb0; kb < kb1; ++kb, ++g) {
             const int s = g % S;
             const uint32_t ph = (g / S) & 1;
@@ -358,8 +372,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     float4* const stage = a.stage_off < 0 ? nullptr
         : reinterpret_cast<float4*>(smem_raw + (tiles - smem_u32(smem_raw)) + a.stage_off) + ew * 256;
     int it = 0;  // running chunk counter (accumulator ring position)
-    int ti = 0;  // tiles done by this CTA
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
+    int stat_tile = -1;  // tile whose InstanceNorm partial sums sit in s_stat, waiting to be flushed
+    const bool split_k = a.ksplit > 1;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int tile = item / a.ksplit, ks = item - tile * a.ksplit;
+      const int kb_lo = ks * a.kb_per_split, kb_hi = min(a.num_kb, kb_lo + a.kb_per_split);
       const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
       const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, tn = mt / tiles_hw;
       const int cn0 = nt * BN;
@@ -379,9 +396,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         s_bias[i] = (ok && a.bias) ? __ldg(a.bias + c) : 0.f;
         s_scale[i] = (ok && a.scale) ? __ldg(a.scale + c) : 1.f;
         s_shift[i] = (ok && a.scale) ? __ldg(a.shift + c) : 0.f;
-        if (a.stats) {  // InstanceNorm statistics: flush the previous tile's partial sums (one image per tile)
-          if (ti > 0) {
-            const int ptile = tile - (int)gridDim.x;
+        if (a.stats) {  // InstanceNorm statistics: flush the previous finalised tile's partial sums (one image per tile)
+          if (stat_tile >= 0) {
+            const int ptile = stat_tile;
             const int pc = (ptile % a.n_tiles) * BN + i, pn = (ptile / a.n_tiles) / tiles_hw;
             if (pc < a.Cout) {
               atomicAdd(a.stats + ((long)pn * a.Cout + pc) * 2,
@@ -393,11 +410,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
       epi_bar_sync<kEpiWarps * 32>();
+      stat_tile = -1;
       // ---- all K chunks but the last: partial sums TMEM -> registers (round-to-nearest adds), buffer handed straight back
       // (compiled only into the MULTI instantiations: the single-chunk ones -- every short-mainloop, epilogue-bound layer --
       // keep the register footprint of a plain streaming epilogue)
       float accr[MULTI ? kNCH : 1][32];
-      for (int kb0 = 0; MULTI && kb0 + a.chunk_kb < a.num_kb; kb0 += a.chunk_kb, ++it) {
+      for (int kb0 = kb_lo; MULTI && kb0 + a.chunk_kb < kb_hi; kb0 += a.chunk_kb, ++it) {
         const int buf = it & 1;
         mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
         tc_fence_after();
@@ -413,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float acc = (i < kChunk) ? __uint_as_float(v[i]) : 0.f;
-              accr[ci][i] = kb0 == 0 ? acc : accr[ci][i] + acc;
+              accr[ci][i] = kb0 == kb_lo ? acc : accr[ci][i] + acc;
             }
             if (kCat) {  // right half of the accumulator: hi*lo (the left half holds hi*hi + lo*hi)
               if (kChunk == 32) tmem_ld32(taddr + BN, v); else tmem_ld16(taddr + BN, v);
@@ -434,34 +452,75 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_wait(bar_tfull + 8 * buf, (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + buf * kAccCols;
+      // split-K: pass 0 parks this item's raw accumulator in its workspace slice, pass 1 (only in the item that arrives last
+      // for the tile) re-reads all slices in slice order and runs the epilogue proper; otherwise one pass straight from TMEM
+      float* const sk_row = split_k ? a.sk_ws + ((long)mt * kBlockM + r) * a.sk_ctot + cn0 : nullptr;
+      bool finalized = !split_k;
+#pragma unroll 1
+      for (int pass = 0; pass < (split_k ? 2 : 1); ++pass) {
+      if (pass == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);  // accumulator drained: the MMA warp may reuse it
+        __threadfence();                                   // this thread's slice stores are visible device-wide ...
+        epi_bar_sync<kEpiWarps * 32>();
+        if (threadIdx.x == 64) s_flag = atomicAdd(a.sk_cnt + tile, 1);  // ... before the item is counted
+        epi_bar_sync<kEpiWarps * 32>();
+        if (s_flag != a.ksplit - 1) break;  // CTA-uniform: another item will finalise this tile
+        finalized = true;
+        __threadfence();
+        if (threadIdx.x == 64) a.sk_cnt[tile] = 0;  // ready for the next launch on this workspace
+      }
 #pragma unroll 1
       for (int ci = 0; ci < kNCH; ++ci) {
         const int c0 = (2 * ci + half) * kChunk;
         if (c0 >= BN || cn0 + c0 >= a.Cout) break;  // warp-uniform
-        uint32_t v[32], v2[32];
-        const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        if (kChunk == 32) {
-          tmem_ld32(taddr, v);
-          if (kCat) tmem_ld32(taddr + BN, v2);
-        } else {
-          tmem_ld16(taddr, v);
-          if (kCat) tmem_ld16(taddr + BN, v2);
-        }
-        tmem_ld_wait();
         const int cnt = min(kChunk, a.Cout - (cn0 + c0));  // warp-uniform
         float vals[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float acc = (i < kChunk) ? __uint_as_float(v[i]) : 0.f;
-          if (kCat && i < kChunk) acc += __uint_as_float(v2[i]);  // hi*hi + lo*hi  +  hi*lo
-          if (MULTI) {  // earlier chunks' partial sum (register array indexed by the runtime ci through selects)
-            float prev = accr[0][i];
-#pragma unroll
-            for (int k = 1; k < (MULTI ? kNCH : 1); ++k) prev = ci == k ? accr[k][i] : prev;
-            acc += prev;
+        if (pass == 0) {
+          uint32_t v[32], v2[32];
+          const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+          if (kChunk == 32) {
+            tmem_ld32(taddr, v);
+            if (kCat) tmem_ld32(taddr + BN, v2);
+          } else {
+            tmem_ld16(taddr, v);
+            if (kCat) tmem_ld16(taddr + BN, v2);
           }
-          vals[i] = (i < kChunk) ? fmaf(acc, a.acc_scale, s_bias[c0 + (i < kChunk ? i : 0)]) : 0.f;
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float acc = (i < kChunk) ? __uint_as_float(v[i]) : 0.f;
+            if (kCat && i < kChunk) acc += __uint_as_float(v2[i]);  // hi*hi + lo*hi  +  hi*lo
+            if (MULTI) {  // earlier chunks' partial sum (register array indexed by the runtime ci through selects)
+              float prev = accr[0][i];
+#pragma unroll
+              for (int k = 1; k < (MULTI ? kNCH : 1); ++k) prev = ci == k ? accr[k][i] : prev;
+              acc += prev;
+            }
+            vals[i] = acc;
+          }
+          if (split_k) {  // kChunk is a multiple of 16: float4 stores of this lane's row segment
+            float4* dst = reinterpret_cast<float4*>(sk_row + (long)ks * a.sk_slice + c0);
+#pragma unroll
+            for (int i = 0; i < kChunk; i += 4) __stcg(dst + i / 4, make_float4(vals[i], vals[i + 1], vals[i + 2], vals[i + 3]));
+            continue;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) vals[i] = 0.f;
+          for (int k2 = 0; k2 < a.ksplit; ++k2) {
+            const float4* src = reinterpret_cast<const float4*>(sk_row + (long)k2 * a.sk_slice + c0);
+#pragma unroll
+            for (int i = 0; i < kChunk; i += 4) {
+              const float4 t4 = __ldcg(src + i / 4);
+              vals[i] += t4.x; vals[i + 1] += t4.y; vals[i + 2] += t4.z; vals[i + 3] += t4.w;
+            }
+          }
         }
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          vals[i] = (i < kChunk) ? fmaf(vals[i], a.acc_scale, s_bias[c0 + (i < kChunk ? i : 0)]) : 0.f;
         act_chunk_dispatch(vals, a.pre_act, a.act_param);
         if (a.scale != nullptr) {
 #pragma unroll
@@ -483,15 +542,18 @@ __global__ void __launch_bounds__(kThreads, 1)
         else if (row_ok)
           conv_store_row(vals, cn0 + c0, cnt, pix, a);
       }
-      // hand the accumulator back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      }
+      if (a.stats != nullptr && finalized) stat_tile = tile;  // CTA-uniform
+      if (!split_k) {  // hand the accumulator back to the MMA warp (split-K did so before counting the item)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      }
       ++it;
     }
-    if (a.stats != nullptr && ti > 0) {  // the last tile's statistics
-      epi_bar_sync<kEpiWarps * 32>();
-      const int ptile = blockIdx.x + (ti - 1) * (int)gridDim.x;
+    if (a.stats != nullptr) epi_bar_sync<kEpiWarps * 32>();
+    if (a.stats != nullptr && stat_tile >= 0) {  // the last finalised tile's statistics
+      const int ptile = stat_tile;
       for (int i = threadIdx.x - 64; i < BN; i += kEpiWarps * 32) {
         const int pc = (ptile % a.n_tiles) * BN + i, pn = (ptile / a.n_tiles) / tiles_hw;
         if (pc < a.Cout) {
@@ -836,6 +898,35 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+static int sm_count() {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  return num_sms;
+}
+
+// Split-K plan: layers whose tiles fill less than half of the SMs and whose K loop is deep (the 4x3 ... 8x6 levels of the
+// U-Net / GMM regression / FlowNet pyramids: 8-40 tiles, 36-150 K-blocks each) cut K into slices of >= 8 K-blocks so that
+// tiles x slices covers the chip.  Returns the slice count (1 = off) and the K-blocks per slice.
+static int plan_splitk(int total_tiles, int num_kb, int* kb_per_split) {
+  *kb_per_split = num_kb;
+  const int sms = sm_count();
+  if (total_tiles * 2 > sms || num_kb < 16) return 1;
+  int ks = sms / total_tiles;
+  if (ks > num_kb / 8) ks = num_kb / 8;
+  if (ks < 2) return 1;
+  const int per = cdiv(num_kb, ks);
+  *kb_per_split = per;
+  return cdiv(num_kb, per);
+}
+static size_t splitk_bytes(int total_tiles, int m_tiles, int n_tiles, int bn, int ksplit) {
+  const size_t cnt = ((size_t)total_tiles * sizeof(int) + 255) & ~(size_t)255;
+  return cnt + (size_t)ksplit * m_tiles * kBlockM * ((size_t)n_tiles * bn) * sizeof(float);
+}
+
 // Picks the (nb, bh, bw) pixel tile with the fewest wasted accumulator rows.
 static void pick_tile(int N, int Ho, int Wo, int& nb, int& bh, int& bw) {
   double best = -1.0;
@@ -901,13 +992,9 @@ static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CU
   const long total = (long)m_tiles * a.n_tiles;
   if (total >= (1l << 31)) return fail(SHINEON_ERR_ARG, "conv2d: too many tiles");
   a.total_tiles = (int)total;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
-  const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
+  const int num_sms = sm_count();
+  const long items = (long)a.total_tiles * a.ksplit;
+  const int grid = items < num_sms ? (int)items : num_sms;
   conv_igemm_kernel<BN, SPLIT, MULTI><<<grid, kThreads, smem_bytes, stream>>>(tAh, tAl, tBh, tBl, a);
   return after_launch("conv_igemm_kernel");
 }
@@ -989,6 +1076,19 @@ extern "C" int shineon_conv2d_igemm_fwd(const shineon_conv2d_params* p, shineon_
   return rc;
 }
 
+extern "C" size_t shineon_conv2d_splitk_workspace_bytes(const shineon_conv2d_params* p) {
+  ConvArgs a;
+  if (fill_args(p, a) != SHINEON_OK) return 0;
+  int bn = p->tile_n;
+  if (bn == 0) bn = a.Cout <= 16 ? 16 : a.Cout <= 32 ? 32 : a.Cout <= 64 ? 64 : 128;
+  const long m_tiles = (long)a.tiles_w * a.tiles_h * cdiv(a.N, a.nb);
+  const int n_tiles = cdiv(a.Cout, bn);
+  if (m_tiles * n_tiles > 4096) return 0;
+  int per;
+  const int ks = plan_splitk((int)(m_tiles * n_tiles), a.num_kb, &per);
+  return ks > 1 ? splitk_bytes((int)(m_tiles * n_tiles), (int)m_tiles, n_tiles, bn, ks) : 0;
+}
+
 static int conv2d_igemm_launch(const shineon_conv2d_params* p, ConvArgs& a, cudaStream_t stream) {
   int rc;
   const bool split = p->x_lo != nullptr;
@@ -1030,7 +1130,27 @@ static int conv2d_igemm_launch(const shineon_conv2d_params* p, ConvArgs& a, cuda
   }
   if (!split) { tAl = tAh; tBl = tBh; }
 
-  const bool multi = a.num_kb > a.chunk_kb;
+  // split-K (see plan_splitk): only with a caller-provided workspace of the size shineon_conv2d_splitk_workspace_bytes says
+  a.ksplit = 1;
+  a.kb_per_split = a.num_kb;
+  a.sk_ws = nullptr; a.sk_cnt = nullptr; a.sk_ctot = 0; a.sk_slice = 0;
+  if (p->splitk_ws != nullptr) {
+    const int n_tiles = cdiv(a.Cout, bn);
+    int per = a.num_kb;
+    const int ks = plan_splitk(m_tiles * n_tiles, a.num_kb, &per);
+    if (ks > 1) {
+      const size_t need = splitk_bytes(m_tiles * n_tiles, m_tiles, n_tiles, bn, ks);
+      SHINEON_REQUIRE(p->splitk_ws_bytes >= need, "conv2d: split-K workspace of %zu bytes, need %zu", p->splitk_ws_bytes, need);
+      SHINEON_REQUIRE((reinterpret_cast<uintptr_t>(p->splitk_ws) & 15) == 0, "conv2d: split-K workspace must be 16-byte aligned");
+      a.ksplit = ks;
+      a.kb_per_split = per;
+      a.sk_cnt = reinterpret_cast<int*>(p->splitk_ws);
+      a.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(p->splitk_ws) + (((size_t)m_tiles * n_tiles * sizeof(int) + 255) & ~(size_t)255));
+      a.sk_ctot = n_tiles * bn;
+      a.sk_slice = (long)m_tiles * kBlockM * a.sk_ctot;
+    }
+  }
+  const bool multi = a.kb_per_split > a.chunk_kb;
 #define SHINEON_LAUNCH(BN_)                                                                                                      \
   (split ? (multi ? launch_igemm<BN_, true, true>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream)                             \
                   : launch_igemm<BN_, true, false>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream))                           \
@@ -1098,6 +1218,7 @@ extern "C" int shineon_conv2d_im2col_fwd(const shineon_conv2d_params* p, const f
   a.num_kb = a.cin_blocks;  // the GEMM is 1x1 over the padded K
   a.chunk_kb = a.num_kb;
   a.stages = 1; a.w_per_image = 0; a.stats = nullptr;
+  a.ksplit = 1; a.kb_per_split = a.num_kb; a.sk_ws = nullptr; a.sk_cnt = nullptr; a.sk_ctot = 0; a.sk_slice = 0;
   a.bias = p->bias; a.scale = p->scale; a.shift = p->shift;
   a.pre_act = p->pre_act; a.post_act = p->post_act; a.act_param = p->act_param;
   a.fmt = p->plane_fmt; a.acc_scale = p->acc_scale == 0.f ? 1.f : p->acc_scale; a.idesc = 0;

@@ -16,6 +16,9 @@ PROFILE = None
 # K-blocks per TMEM accumulation chain of the conv kernel (shineon_conv2d_params.acc_chunk_kb): 0 = kernel default (16),
 # -1 = one chain over the whole K (the round-1 behaviour; kept for the accuracy A/B in tests/diag_accum.py)
 ACC_CHUNK_KB = 0
+# split-K for layers with fewer output tiles than half the SMs and a deep K loop (shineon_conv2d_params.splitk_ws);
+# False = one CTA per tile walks the whole K (the round-1 behaviour; kept for A/B measurements)
+SPLIT_K = True
 
 
 def C_void(v):
@@ -346,6 +349,17 @@ def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_pa
     p.tile_n, p.stages = tile_n, stages
     p.stats_ws = _p(stats_ws)
     p.acc_chunk_kb = ACC_CHUNK_KB
+    if SPLIT_K and not direct:
+        # split-K workspace (few tiles, deep K): owned by the layer and kept for its lifetime, so captured CUDA graphs keep
+        # pointing at live memory; zero-filled once (the arrival counters), the kernel leaves it reusable
+        need = _lib.load().shineon_conv2d_splitk_workspace_bytes(C.byref(p))
+        if need:
+            cache = pc.__dict__.setdefault("_sk_ws", {})
+            key = (N, H, W, Ho, Wo, x.cpad, tile_n, str(dev))
+            ws = cache.get(key)
+            if ws is None or ws.numel() < need:
+                ws = cache[key] = torch.zeros(need, dtype=torch.uint8, device=dev)
+            p.splitk_ws, p.splitk_ws_bytes = _p(ws), ws.numel()
     assert stats_ws is None or (not direct and stats_ws.dtype == torch.float64 and stats_ws.numel() == 2 * N * pc.Cout)
     fn = _lib.load().shineon_conv2d_direct_fwd if direct else _lib.load().shineon_conv2d_igemm_fwd
     prof = PROFILE
