@@ -205,7 +205,9 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // Persistent: one CTA per SM walks output tiles (tile = blockIdx.x + i*gridDim.x, channel tile fastest so that
 // neighbouring CTAs share the same activation tile in L2).  Two TMEM accumulators: the epilogue of tile i
 // (TMEM -> registers -> global) overlaps the TMA/MMA main loop of tile i+1.
-template <int BN, bool SPLIT, bool MULTI>  // MULTI: the K loop spans several accumulation chunks (num_kb > chunk_kb)
+// MULTI: the K loop spans several accumulation chunks (num_kb > chunk_kb); SPLITK: work items are (tile, K slice) pairs
+// (compiled separately so the common single-pass epilogue keeps its register budget)
+template <int BN, bool SPLIT, bool MULTI, bool SPLITK = false>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_igemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         : reinterpret_cast<float4*>(smem_raw + (tiles - smem_u32(smem_raw)) + a.stage_off) + ew * 256;
     int it = 0;  // running chunk counter (accumulator ring position)
     int stat_tile = -1;  // tile whose InstanceNorm partial sums sit in s_stat, waiting to be flushed
-    const bool split_k = a.ksplit > 1;
+    constexpr bool split_k = SPLITK;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int tile = item / a.ksplit, ks = item - tile * a.ksplit;
       const int kb_lo = ks * a.kb_per_split, kb_hi = min(a.num_kb, kb_lo + a.kb_per_split);
@@ -509,12 +511,24 @@ __global__ void __launch_bounds__(kThreads, 1)
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) vals[i] = 0.f;
-          for (int k2 = 0; k2 < a.ksplit; ++k2) {
+          for (int k2 = 0; k2 < a.ksplit; k2 += 2) {  // two slices' loads in flight, added in slice order
             const float4* src = reinterpret_cast<const float4*>(sk_row + (long)k2 * a.sk_slice + c0);
+            const bool two = k2 + 1 < a.ksplit;
+            const float4* src2 = two ? src + a.sk_slice / 4 : src;
+            float4 ta[kChunk / 4], tb[kChunk / 4];
 #pragma unroll
-            for (int i = 0; i < kChunk; i += 4) {
-              const float4 t4 = __ldcg(src + i / 4);
-              vals[i] += t4.x; vals[i + 1] += t4.y; vals[i + 2] += t4.z; vals[i + 3] += t4.w;
+            for (int i = 0; i < kChunk / 4; ++i) ta[i] = __ldcg(src + i);
+#pragma unroll
+            for (int i = 0; i < kChunk / 4; ++i) tb[i] = __ldcg(src2 + i);
+#pragma unroll
+            for (int i = 0; i < kChunk / 4; ++i) {
+              vals[4 * i] += ta[i].x; vals[4 * i + 1] += ta[i].y; vals[4 * i + 2] += ta[i].z; vals[4 * i + 3] += ta[i].w;
+            }
+            if (two) {
+#pragma unroll
+              for (int i = 0; i < kChunk / 4; ++i) {
+                vals[4 * i] += tb[i].x; vals[4 * i + 1] += tb[i].y; vals[4 * i + 2] += tb[i].z; vals[4 * i + 3] += tb[i].w;
+              }
             }
           }
         }
@@ -898,6 +912,9 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+constexpr int kSplitKMinKb = 32;  // K-blocks below which the K loop is too short to be worth a second pass
+constexpr int kSplitKMax = 16;    // slices per tile (the finalising CTA reads them all)
+
 static int sm_count() {
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -911,14 +928,16 @@ static int sm_count() {
 // Split-K plan: layers whose tiles fill less than half of the SMs and whose K loop is deep (the 4x3 ... 8x6 levels of the
 // U-Net / GMM regression / FlowNet pyramids: 8-40 tiles, 36-150 K-blocks each) cut K into slices of >= 8 K-blocks so that
 // tiles x slices covers the chip.  Returns the slice count (1 = off) and the K-blocks per slice.
-static int plan_splitk(int total_tiles, int num_kb, int* kb_per_split) {
+static int plan_splitk(int total_tiles, int num_kb, int bn, int chunk_kb, int* kb_per_split) {
   *kb_per_split = num_kb;
   const int sms = sm_count();
-  if (total_tiles * 2 > sms || num_kb < 16) return 1;
+  if ((bn != 64 && bn != 128) || total_tiles * 2 > sms || num_kb < kSplitKMinKb) return 1;
   int ks = sms / total_tiles;
   if (ks > num_kb / 8) ks = num_kb / 8;
+  if (ks > kSplitKMax) ks = kSplitKMax;
   if (ks < 2) return 1;
-  const int per = cdiv(num_kb, ks);
+  int per = cdiv(num_kb, ks);
+  if (per > chunk_kb) per = chunk_kb;  // one TMEM accumulation chain per slice (the split-K kernels are not MULTI)
   *kb_per_split = per;
   return cdiv(num_kb, per);
 }
@@ -945,7 +964,7 @@ static void pick_tile(int N, int Ho, int Wo, int& nb, int& bh, int& bw) {
   }
 }
 
-template <int BN, bool SPLIT, bool MULTI>
+template <int BN, bool SPLIT, bool MULTI, bool SPLITK = false>
 static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CUtensorMap& tBh, const CUtensorMap& tBl,
                         ConvArgs& a, int m_tiles, int stages_req, cudaStream_t stream) {
   constexpr int kBBytes = BN * kBlockK * 2;
@@ -961,10 +980,10 @@ static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CU
   static int max_dyn_smem = -1;  // per instantiation: opt-in limit minus this kernel's static shared memory
   if (max_dyn_smem < 0) {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaFuncGetAttributes(&fa, conv_igemm_kernel<BN, SPLIT, MULTI>);
+    cudaError_t e = cudaFuncGetAttributes(&fa, conv_igemm_kernel<BN, SPLIT, MULTI, SPLITK>);
     if (e == cudaSuccess) {
       max_dyn_smem = 227 * 1024 - (int)fa.sharedSizeBytes;
-      e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem);
+      e = cudaFuncSetAttribute(conv_igemm_kernel<BN, SPLIT, MULTI, SPLITK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem);
     }
     if (e != cudaSuccess) {
       cudaGetLastError();
@@ -995,7 +1014,7 @@ static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CU
   const int num_sms = sm_count();
   const long items = (long)a.total_tiles * a.ksplit;
   const int grid = items < num_sms ? (int)items : num_sms;
-  conv_igemm_kernel<BN, SPLIT, MULTI><<<grid, kThreads, smem_bytes, stream>>>(tAh, tAl, tBh, tBl, a);
+  conv_igemm_kernel<BN, SPLIT, MULTI, SPLITK><<<grid, kThreads, smem_bytes, stream>>>(tAh, tAl, tBh, tBl, a);
   return after_launch("conv_igemm_kernel");
 }
 
@@ -1085,7 +1104,7 @@ extern "C" size_t shineon_conv2d_splitk_workspace_bytes(const shineon_conv2d_par
   const int n_tiles = cdiv(a.Cout, bn);
   if (m_tiles * n_tiles > 4096) return 0;
   int per;
-  const int ks = plan_splitk((int)(m_tiles * n_tiles), a.num_kb, &per);
+  const int ks = plan_splitk((int)(m_tiles * n_tiles), a.num_kb, bn, a.chunk_kb, &per);
   return ks > 1 ? splitk_bytes((int)(m_tiles * n_tiles), (int)m_tiles, n_tiles, bn, ks) : 0;
 }
 
@@ -1137,7 +1156,7 @@ static int conv2d_igemm_launch(const shineon_conv2d_params* p, ConvArgs& a, cuda
   if (p->splitk_ws != nullptr) {
     const int n_tiles = cdiv(a.Cout, bn);
     int per = a.num_kb;
-    const int ks = plan_splitk(m_tiles * n_tiles, a.num_kb, &per);
+    const int ks = plan_splitk(m_tiles * n_tiles, a.num_kb, bn, a.chunk_kb, &per);
     if (ks > 1) {
       const size_t need = splitk_bytes(m_tiles * n_tiles, m_tiles, n_tiles, bn, ks);
       SHINEON_REQUIRE(p->splitk_ws_bytes >= need, "conv2d: split-K workspace of %zu bytes, need %zu", p->splitk_ws_bytes, need);
@@ -1151,6 +1170,13 @@ static int conv2d_igemm_launch(const shineon_conv2d_params* p, ConvArgs& a, cuda
     }
   }
   const bool multi = a.kb_per_split > a.chunk_kb;
+  if (a.ksplit > 1) {  // split-K instantiations: slices never exceed one accumulation chunk (plan_splitk), BN 64 / 128 only
+    if (bn == 64)
+      return split ? launch_igemm<64, true, false, true>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream)
+                   : launch_igemm<64, false, false, true>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream);
+    return split ? launch_igemm<128, true, false, true>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream)
+                 : launch_igemm<128, false, false, true>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream);
+  }
 #define SHINEON_LAUNCH(BN_)                                                                                                      \
   (split ? (multi ? launch_igemm<BN_, true, true>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream)                             \
                   : launch_igemm<BN_, true, false>(tAh, tAl, tBh, tBl, a, m_tiles, p->stages, stream))                           \

@@ -16,9 +16,11 @@ PROFILE = None
 # K-blocks per TMEM accumulation chain of the conv kernel (shineon_conv2d_params.acc_chunk_kb): 0 = kernel default (16),
 # -1 = one chain over the whole K (the round-1 behaviour; kept for the accuracy A/B in tests/diag_accum.py)
 ACC_CHUNK_KB = 0
-# split-K for layers with fewer output tiles than half the SMs and a deep K loop (shineon_conv2d_params.splitk_ws);
-# False = one CTA per tile walks the whole K (the round-1 behaviour; kept for A/B measurements)
-SPLIT_K = True
+# split-K for layers with fewer output tiles than half the SMs and a deep K loop (shineon_conv2d_params.splitk_ws).
+# OFF by default: measured on B200 as graph replays (tests/prof_splitk.py, profiles/r02_splitk.md) it wins 10-17 % on the
+# 16-tile layers (8x6 512->256 at 80 frames: 75 -> 67 us; FlowNet 4x3 1024->1024: 82 -> 68 us) and loses up to 2x wherever
+# tiles x slices exceeds the SM count; the whole try-on step got 1.7 % slower, FlowNet2 8 %.  Kept (and tested) as an option.
+SPLIT_K = False
 
 
 def C_void(v):

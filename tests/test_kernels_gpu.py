@@ -68,6 +68,53 @@ def test_conv2d_igemm(ops, case, prec):
     assert_close(yp.float(), want, what="igemm planes vs oracle", **ptol)
 
 
+@pytest.mark.parametrize("case", [
+    # N, H, W, Cin, Cout, k, s, p: few output tiles, deep K (the 4x3 .. 8x6 levels) -> split-K
+    (10, 8, 6, 512, 256, 4, 2, 1), (10, 4, 3, 256, 128, 3, 1, 1), (16, 4, 3, 1024, 1024, 3, 1, 1), (1, 16, 12, 512, 512, 3, 1, 1),
+    (3, 8, 6, 192, 24, 3, 1, 1), (2, 4, 3, 2688, 72, 3, 1, 1)])
+def test_conv2d_split_k(ops, case):
+    """Split-K (K slices in workspace, last arriver finalises) against the single-pass kernel and the fp32 conv: f32 and
+    planes outputs, fused InstanceNorm statistics, activation epilogue; repeated launches reuse the workspace (counters
+    must come back to zero) and are bit-identical (fixed slice order)."""
+    import ctypes as C
+
+    from shineon_virtual_tryon_b200 import _lib
+
+    N, H, W, Cin, Cout, k, s, p = case
+    g = torch.Generator().manual_seed(77 + Cin + Cout)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) * (1.0 / (Cin * k * k) ** 0.5)
+    b = torch.randn(Cout, generator=g) * 0.1
+    xp = _planes_from(ops, x, "fp16x3")
+    pc = ops.PackedConv(w.cuda(), b.cuda(), stride=s, pad=p, prec="fp16x3")
+    want = F.conv2d(x, w, b, stride=s, padding=p)
+    Ho, Wo = want.shape[2:]
+    outs = {}
+    for split in (False, True):
+        ops.SPLIT_K = split
+        try:
+            ws = torch.zeros(2 * N * Cout, dtype=torch.float64, device="cuda")
+            y, _ = ops.conv2d(xp, pc, want_f32=True, stats_ws=ws)
+            _, yp = ops.conv2d(xp, pc, want_planes=True, post_act="gelu")
+            y2, _ = ops.conv2d(xp, pc, want_f32=True)
+        finally:
+            ops.SPLIT_K = False
+        torch.cuda.synchronize()
+        outs[split] = (y, yp.float(), ws.clone(), y2)
+    assert getattr(pc, "_sk_ws", None), "this shape was expected to take the split-K path"
+    for split in (False, True):
+        y, yp, ws, y2 = outs[split]
+        assert_close(nchw(y), want, what=f"split_k={split} f32", **CONV_TOL["fp16x3"])
+        assert_close(yp, F.gelu(want), what=f"split_k={split} planes + gelu", **CONV_TOL["fp16x3"])
+        assert torch.equal(y, y2), "repeated launch on the same workspace differs"
+        st = ws.view(N, Cout, 2).cpu()
+        yc = nchw(y).double().cpu()
+        assert_close(st[..., 0], yc.sum((2, 3)), atol=1e-4, rtol=1e-5, what="fused statistics: sum")
+        assert_close(st[..., 1], (yc * yc).sum((2, 3)), atol=1e-4, rtol=1e-5, what="fused statistics: sum of squares")
+    # slices are added in a fixed order: same accuracy class as the single pass (both within a few f32 ulps of each other)
+    assert (outs[True][0] - outs[False][0]).abs().max().item() <= 2e-5 * want.abs().max().item()
+
+
 def test_conv2d_epilogue_and_window(ops):
     """bias -> ReLU -> per-channel affine (folded BN) and writing into a channel window of a wider buffer."""
     g = torch.Generator().manual_seed(7)
