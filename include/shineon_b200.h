@@ -548,6 +548,12 @@ int shineon_nearest_resize_nhwc(const float* x, float* y, int N, int Hs, int Ws,
 int shineon_nearest_resize_planes(const float* x, int N, int C, int Hs, int Ws, void* y_hi, void* y_lo, int H, int W,
                                   int cpad, float scale_h, float scale_w, int plane_fmt, shineon_stream_t stream);
 
+/* The same resize fused with the im2col of the conv that reads it (mlp_shared: ks x ks, stride 1, pad ks/2, spade.py:60-62):
+ * planes [N,H,W,kpad], k = (fy*ks + fx)*C + c, zero outside the resized map and for k >= ks*ks*C.  The conv is then a dense
+ * 1x1 GEMM over K = kpad with the weight reordered tap-major (label maps have 2-18 channels). */
+int shineon_nearest_im2col_planes(const float* x, int N, int C, int Hs, int Ws, void* y_hi, void* y_lo, int H, int W, int ks,
+                                  int kpad, float scale_h, float scale_w, int plane_fmt, shineon_stream_t stream);
+
 /* y = a + b over n f32 elements (the residual x_s + dx of AnySpadeResBlock.forward, spade.py:160); y may alias a or b. */
 int shineon_add_nhwc(const float* a, const float* b, float* y, long n, shineon_stream_t stream);
 

@@ -137,6 +137,7 @@ SIGNATURES = {
                                c_i, c_p],
     "shineon_nearest_resize_nhwc": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_f, c_p],
     "shineon_nearest_resize_planes": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_f, c_f, c_i, c_p],
+    "shineon_nearest_im2col_planes": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_f, c_i, c_p],
     "shineon_add_nhwc": [c_p, c_p, c_p, C.c_long, c_p],
     "shineon_sams_flow_blend": [c_p, c_i, c_p, c_p, C.c_long, c_i, c_i, c_i, c_p],
 }

@@ -20,6 +20,7 @@
 //     (folded BatchNorm) and store fp32 NHWC and/or bf16 hi/lo planes for the next layer.
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -972,7 +973,7 @@ static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CU
   int stages = (200 * 1024) / kStageBytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages_req > 0 && stages_req < stages) stages = stages_req;
-  if (stages > a.num_kb) stages = a.num_kb;
+  if (stages > a.num_kb) stages = a.num_kb;  // (more stages than K-blocks on short-K layers: measured, no gain, r02)
   if (stages < 1) stages = 1;
   a.stages = stages;
   a.idesc = umma_idesc_f16(kBlockM, BN, a.fmt == SHINEON_FMT_FP16 ? 0 : 1);
@@ -993,7 +994,8 @@ static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CU
   }
   while (stages > 1 && stages * kStageBytes + 1024 > max_dyn_smem) --stages;
   // f32-only outputs of short-mainloop layers are epilogue-bound: give them the transpose buffers for coalesced
-  // stores (4 KB per epilogue warp) when that leaves at least min(num_kb, 2) pipeline stages
+  // stores (4 KB per epilogue warp) when that leaves at least min(num_kb, 2) pipeline stages.  (Plane outputs through the
+  // same buffers -- 8 lanes x 8 bytes per pixel and plane -- were measured in r02: the try-on step got 2 % slower.)
   constexpr int kStagingBytes = kEpiWarps * 4096;
   a.stage_off = -1;
   if (a.y_hi == nullptr && a.y_f32 != nullptr && BN >= 32 && a.num_kb <= 16) {

@@ -146,6 +146,43 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// im2col (ks x ks, stride 1, pad ks/2) of the nearest-resized label map, straight from the source map: the operand of the
+// mlp_shared conv as a dense 1x1 GEMM with K = pad64(ks*ks*C) (label maps have 2-18 channels: one 64-channel K-block per
+// filter tap would be 9x the MMA work).  k = (fy*ks + fx)*C + c like nchw_im2col_planes_kernel.
+__global__ void __launch_bounds__(256)
+    nearest_im2col_planes_kernel(const float* __restrict__ x, int C, int Hs, int Ws, plane_t* __restrict__ yh,
+                                 plane_t* __restrict__ yl, int H, int W, int ks, int kpad, float scale_h, float scale_w, int fmt) {
+  const int n = blockIdx.y;
+  const int groups = kpad >> 3;
+  const int pad = ks / 2, K = ks * ks * C;
+  const long total = (long)H * W * groups;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int p = (int)(e % ((long)H * W));
+    const int g = (int)(e / ((long)H * W));
+    const int h = p / W, w = p - h * W;
+    __align__(16) plane_t hi[8];
+    __align__(16) plane_t lo[8];
+    int k = g * 8;
+    int tap = k / C, c = k - tap * C;
+    int fy = tap / ks, fx = tap - fy * ks;
+#pragma unroll
+    for (int j = 0; j < 8; ++j, ++k) {
+      float v = 0.f;
+      const int hh = h + fy - pad, ww = w + fx - pad;  // position in the RESIZED map (zero padding outside it)
+      if (k < K && hh >= 0 && hh < H && ww >= 0 && ww < W)
+        v = __ldg(x + (((long)n * C + c) * Hs + nearest_src(hh, scale_h, Hs)) * Ws + nearest_src(ww, scale_w, Ws));
+      split16(v, fmt, hi[j], lo[j]);
+      if (++c == C) {
+        c = 0;
+        if (++fx == ks) { fx = 0; ++fy; }
+      }
+    }
+    const long o = ((long)n * H * W + p) * kpad + g * 8;
+    *reinterpret_cast<uint4*>(yh + o) = *reinterpret_cast<const uint4*>(hi);
+    if (yl) *reinterpret_cast<uint4*>(yl + o) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 // y may alias a or b (every element is read and written by the same thread): no __restrict__, no read-only loads
 __global__ void __launch_bounds__(256) add_nhwc_kernel(const float* a, const float* b, float* y, long n4, long n) {
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long)gridDim.x * blockDim.x) {
@@ -256,6 +293,20 @@ extern "C" int shineon_nearest_resize_planes(const float* x, int N, int C, int H
   nearest_resize_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, C, Hs, Ws, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad,
                                                                        scale_h, scale_w, plane_fmt);
   return after_launch("nearest_resize_planes_kernel");
+}
+
+extern "C" int shineon_nearest_im2col_planes(const float* x, int N, int C, int Hs, int Ws, void* y_hi, void* y_lo, int H, int W,
+                                            int ks, int kpad, float scale_h, float scale_w, int plane_fmt,
+                                            shineon_stream_t stream) {
+  SHINEON_REQUIRE(plane_fmt == SHINEON_FMT_BF16 || plane_fmt == SHINEON_FMT_FP16, "nearest_im2col_planes: plane_fmt %d", plane_fmt);
+  SHINEON_REQUIRE(x && y_hi && N > 0 && N <= 65535 && C > 0 && Hs > 0 && Ws > 0 && H > 0 && W > 0, "nearest_im2col_planes: bad argument");
+  SHINEON_REQUIRE(ks >= 1 && ks <= 7 && (ks & 1) == 1, "nearest_im2col_planes: kernel size %d", ks);
+  SHINEON_REQUIRE(kpad % 8 == 0 && kpad >= ks * ks * C, "nearest_im2col_planes: kpad %d too small / not a multiple of 8", kpad);
+  SHINEON_REQUIRE(scale_h > 0.f && scale_w > 0.f, "nearest_im2col_planes: bad scale");
+  dim3 grid(grid_1d((long)H * W * (kpad >> 3), 256), N);
+  nearest_im2col_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, C, Hs, Ws, (plane_t*)y_hi, (plane_t*)y_lo, H, W, ks, kpad,
+                                                                       scale_h, scale_w, plane_fmt);
+  return after_launch("nearest_im2col_planes_kernel");
 }
 
 extern "C" int shineon_add_nhwc(const float* a, const float* b, float* y, long n, shineon_stream_t stream) {

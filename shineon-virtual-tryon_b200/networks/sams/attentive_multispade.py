@@ -28,7 +28,7 @@ class AttentiveMultiSpade(MultiSpade):
             self._packed_final = (sig, ops.PackedConv(c.weight, c.bias, stride=1, pad=c.padding[0], prec=prec))
         return self._packed_final[1]
 
-    def run(self, ctx, x, labelmap_dict, *, act=None, act_param=0.0, want_f32=False, want_planes=True, out_f32=None,
+    def run(self, ctx, x, labelmap_dict, *, act=None, act_param=0.0, shared=None, want_f32=False, want_planes=True, out_f32=None,
             out_planes=None):
         items = self._ordered(labelmap_dict)
         N, H, W, C = x.shape
@@ -37,7 +37,7 @@ class AttentiveMultiSpade(MultiSpade):
         for i, (key, seg) in enumerate(items):  # attentive_multispade.py:37-43: channel order = sorted key order
             win = stack_p.window(0, self.attn_nc)
             win.coffset, win.C = stack_p.coffset + i * C, C  # modulate's stores only need 8-byte alignment
-            self.spade_layers[key].run(ctx, x, seg, out_f32=stack, out_f32_coffset=i * C, out_planes=win)
+            self.spade_layers[key].run(ctx, x, seg, shared=shared, out_f32=stack, out_f32_coffset=i * C, out_planes=win)
         _, attended = self.attention_layer.run(stack, stack_p, want_f32=False, want_planes=True)
         slope = float(self.mlp_final[1].negative_slope)
         if act is None:

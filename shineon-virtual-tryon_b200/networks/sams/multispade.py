@@ -29,11 +29,11 @@ class MultiSpade(SPADE):
         assert len(labelmap_dict) == len(self.spade_layers), f"{len(labelmap_dict)=} != {len(self.spade_layers)=}"
         return list(self.sort_fn(labelmap_dict.items()))
 
-    def run(self, ctx, x, labelmap_dict, *, act=None, act_param=0.0, **out):
+    def run(self, ctx, x, labelmap_dict, *, act=None, act_param=0.0, shared=None, **out):
         """multispade.py:48-65: every layer but the last hands an un-activated f32 tensor to the next one (which
         normalises it again); the last applies the caller's activation and output selection."""
         items = self._ordered(labelmap_dict)
         for key, seg in items[:-1]:
-            x, _ = self.spade_layers[key].run(ctx, x, seg, want_f32=True, want_planes=False)
+            x, _ = self.spade_layers[key].run(ctx, x, seg, shared=shared, want_f32=True, want_planes=False)
         key, seg = items[-1]
-        return self.spade_layers[key].run(ctx, x, seg, act=act, act_param=act_param, **out)
+        return self.spade_layers[key].run(ctx, x, seg, act=act, act_param=act_param, shared=shared, **out)

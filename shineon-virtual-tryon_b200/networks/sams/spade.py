@@ -1,7 +1,9 @@
 """SPADE and AnySpadeResBlock (reference: models/networks/sams/spade.py:17-183).
 
 Engine view of one SPADE layer (spade.py:68-84), x kept as f32 NHWC between passes:
-    seg planes (nearest-resized label map, cached per resolution)  --conv ks x ks + act-->  actv planes (128 ch)
+    label map --nearest resize + im2col (one pass, cached per map and resolution)--> operand planes, K = pad64(ks*ks*label_nc)
+    operand --ONE dense GEMM for the mlp_shared convs of ALL SPADE layers of the block that read this map, + act--> actv planes
+              (128 channels per layer, each layer reads its window)
     actv  --ONE conv ks x ks with mlp_gamma | mlp_beta stacked (bias of gamma + 1)-->  (1+gamma | beta) f32
     spade_modulate: param-free norm of x, * (1+gamma) + beta, the block's activation, hi/lo split  -->  conv operand
 """
@@ -44,6 +46,13 @@ def effective_weight(conv):
     return conv.weight.detach()
 
 
+def shared_gemm_weight(spades):
+    """mlp_shared weights of `spades` (all reading the same label map) as ONE 1x1 GEMM weight [128 * len, ks*ks*label_nc, 1, 1]
+    over the im2col operand (k = (fy*ks + fx)*label_nc + c, ops.nearest_im2col_planes)."""
+    ws = [sp.mlp_shared[0].weight.detach().float() for sp in spades]
+    return torch.cat([w.permute(0, 2, 3, 1).reshape(w.shape[0], -1, 1, 1) for w in ws], 0).contiguous()
+
+
 class EngineContext:
     """State of one generator pass: numeric mode, label-map planes per resolution, InstanceNorm statistics per tensor."""
 
@@ -52,10 +61,11 @@ class EngineContext:
         self._seg = {}
         self._stats = {}
 
-    def seg_planes(self, seg, H, W):
-        key = (seg.data_ptr(), H, W)
+    def seg_operand(self, seg, H, W, ks):
+        """im2col planes (ks x ks, pad ks/2) of the label map nearest-resized to (H, W): the A operand of mlp_shared."""
+        key = (seg.data_ptr(), H, W, ks)
         if key not in self._seg:
-            self._seg[key] = (seg, ops.nearest_resize_planes(seg, (H, W), prec=self.prec))  # keeps `seg` alive: the key is its address
+            self._seg[key] = (seg, ops.nearest_im2col_planes(seg, (H, W), ks, prec=self.prec))  # keeps `seg` alive: the key is its address
         return self._seg[key][1]
 
     def stats(self, x):
@@ -101,7 +111,7 @@ class SPADE(nn.Module):
         require_cuda(self, "SPADE")
         sh = self.mlp_shared[0]
         pw = sh.padding[0]
-        d = dict(shared=ops.PackedConv(sh.weight, sh.bias, stride=1, pad=pw, prec=prec))
+        d = dict(shared=ops.PackedConv(shared_gemm_weight([self]), sh.bias, stride=1, pad=0, prec=prec))
         w = torch.cat([self.mlp_gamma.weight, self.mlp_beta.weight], 0)
         b = torch.cat([self.mlp_gamma.bias + 1.0, self.mlp_beta.bias], 0)  # (1 + gamma) | beta
         d["gb"] = ops.PackedConv(w, b, stride=1, pad=pw, prec=prec)
@@ -115,16 +125,22 @@ class SPADE(nn.Module):
         self._packed = (sig, d)
         return d
 
-    def run(self, ctx, x, seg, *, act=None, act_param=0.0, **out):
-        """x: f32 NHWC [N,H,W,norm_nc]; seg: f32 NCHW label map at any resolution.  `out`: the output selection of
-        ops.spade_modulate (want_f32 / want_planes / out_f32 / out_f32_coffset / out_planes).  Returns (f32|None, Planes|None)."""
+    def run(self, ctx, x, seg, *, act=None, act_param=0.0, actv=None, shared=None, **out):
+        """x: f32 NHWC [N,H,W,norm_nc]; seg: f32 NCHW label map at any resolution.  actv: this layer's mlp_shared output if the
+        caller already has it (AnySpadeResBlock computes the mlp_shared convs of all its layers per label map in one GEMM).
+        `out`: the output selection of ops.spade_modulate (want_f32 / want_planes / out_f32 / out_f32_coffset / out_planes).
+        Returns (f32|None, Planes|None)."""
         norm = self.param_free_norm
         if self.training and isinstance(norm, nn.BatchNorm2d):
             raise NotImplementedError("SPADE with batch statistics (training mode) has no native kernel; call .eval()")
         pk = self._pack(ctx.prec)
         N, H, W, _ = x.shape
-        a, ap = act_name(self.actvn)
-        _, actv = ops.conv2d(ctx.seg_planes(seg, H, W), pk["shared"], post_act=a, act_param=ap, want_planes=True)
+        if actv is None and shared:
+            actv = shared.get(id(self))
+        if actv is None:
+            a, ap = act_name(self.actvn)
+            ks = self.mlp_shared[0].kernel_size[0]
+            _, actv = ops.conv2d(ctx.seg_operand(seg, H, W, ks), pk["shared"], post_act=a, act_param=ap, want_planes=True)
         gb, _ = ops.conv2d(actv, pk["gb"], want_f32=True)
         if pk["bn"] is not None:
             nk = dict(nscale=pk["bn"][0], nshift=pk["bn"][1])
@@ -181,18 +197,56 @@ class AnySpadeResBlock(nn.Module):
         self._packed = (sig, d)
         return d
 
+    def _spade_groups(self):
+        """{label key (None for the encoder's single map): [leaf SPADE layers of this block that read it]}."""
+        groups = {}
+        for mod in [self.spade_0, self.spade_1] + ([self.norm_s] if self.learned_shortcut else []):
+            if hasattr(mod, "spade_layers"):
+                for key, leaf in mod.spade_layers.items():
+                    groups.setdefault(key, []).append(leaf)
+            else:
+                groups.setdefault(None, []).append(mod)
+        return groups
+
+    def _shared_actv(self, ctx, H, W, seg):
+        """The mlp_shared convs (spade.py:60-62) of every SPADE layer of the block, one GEMM per label map: all of them read the
+        same resized map at the same resolution.  Returns {id(leaf SPADE): its 128-channel window of the activated output}."""
+        groups = self._spade_groups()
+        if isinstance(seg, torch.Tensor):
+            if len(groups) != 1:
+                return {}  # MultiSpade.try_fix_labelmap_dict raises the reference's error later
+            seg = {next(iter(groups)): seg}
+        leaves = [l for ls in groups.values() for l in ls]
+        sig = (tuple(params_signature(l.mlp_shared) for l in leaves), ctx.prec)
+        if getattr(self, "_packed_shared", None) is None or self._packed_shared[0] != sig:
+            d = {key: ops.PackedConv(shared_gemm_weight(ls), torch.cat([l.mlp_shared[0].bias for l in ls], 0), stride=1, pad=0,
+                                     prec=ctx.prec) for key, ls in groups.items()}
+            self._packed_shared = (sig, d)
+        out = {}
+        for key, ls in groups.items():
+            if key not in seg:
+                continue
+            a, ap = act_name(ls[0].actvn)
+            ks = ls[0].mlp_shared[0].kernel_size[0]
+            _, actv = ops.conv2d(ctx.seg_operand(seg[key], H, W, ks), self._packed_shared[1][key], post_act=a, act_param=ap,
+                                 want_planes=True)
+            for i, leaf in enumerate(ls):
+                out[id(leaf)] = actv.window(i * leaf.nhidden, leaf.nhidden)
+        return out
+
     def run(self, ctx, x, seg):
         """spade.py:151-171.  x: f32 NHWC; seg: label map tensor (SPADE) or {name: tensor} (MultiSpade family) -> f32 NHWC."""
         pk = self._pack(ctx.prec)
         act, ap = act_name(self.actvn)
+        shared = self._shared_actv(ctx, x.shape[1], x.shape[2], seg)
         if self.learned_shortcut:
-            _, ps = self.norm_s.run(ctx, x, seg, want_f32=False, want_planes=True)
+            _, ps = self.norm_s.run(ctx, x, seg, shared=shared, want_f32=False, want_planes=True)
             x_s, _ = ops.conv2d(ps, pk["conv_s"], want_f32=True)
         else:
             x_s = x
-        _, p0 = self.spade_0.run(ctx, x, seg, act=act, act_param=ap, want_f32=False, want_planes=True)
+        _, p0 = self.spade_0.run(ctx, x, seg, act=act, act_param=ap, shared=shared, want_f32=False, want_planes=True)
         dx, _ = ops.conv2d(p0, pk["conv_0"], want_f32=True)
-        _, p1 = self.spade_1.run(ctx, dx, seg, act=act, act_param=ap, want_f32=False, want_planes=True)
+        _, p1 = self.spade_1.run(ctx, dx, seg, act=act, act_param=ap, shared=shared, want_f32=False, want_planes=True)
         dx, _ = ops.conv2d(p1, pk["conv_1"], want_f32=True)
         return ops.add_nhwc(x_s, dx, out=dx)
 

@@ -782,6 +782,17 @@ def nearest_resize_planes(x, size, prec=None):
     return out
 
 
+def nearest_im2col_planes(x, size, ks, prec=None):
+    """im2col (ks x ks, stride 1, pad ks/2) of F.interpolate(x, size, mode="nearest"): Planes [N,H,W,pad64(ks*ks*C)]."""
+    x = _req(x, name="segmap")
+    N, Cc, Hs, Ws = x.shape
+    H, W = size
+    out = Planes(N, H, W, ks * ks * Cc, prec=prec, device=x.device, zero_pad=False)  # the kernel writes all of kpad
+    check(_lib.load().shineon_nearest_im2col_planes(_p(x), N, Cc, Hs, Ws, _p(out.hi), _p(out.lo), H, W, ks, out.cpad, Hs / H,
+                                                    Ws / W, out.fmt, _stream()), "shineon_nearest_im2col_planes")
+    return out
+
+
 def add_nhwc(a, b, out=None):
     a, b = _req(a, name="a"), _req(b, name="b")
     assert a.shape == b.shape

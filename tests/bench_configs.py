@@ -129,6 +129,13 @@ def sams():
             torch.cuda.synchronize()
         gf = sum(r[0] for r in prof) / 1e9
         tconv = sum(r[1].elapsed_time(r[2]) for r in prof)
+        if "--layers" in sys.argv:
+            agg = {}
+            for r in prof:
+                e = agg.setdefault(r[3], [0, 0.0, 0.0])
+                e[0] += 1; e[1] += r[1].elapsed_time(r[2]); e[2] += r[0]
+            for shp, (n, ms_, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+                print(f"  {n:3d} x (N,H,W,Cin,cpad,Cout,k,s)={shp}: {ms_:7.3f} ms  {fl / ms_ / 1e9:7.1f} TF/s", file=sys.stderr)
         print(json.dumps({"config": f"SURVEY 8f N3: SamsGenerator default architecture, batch {B} x 256x192, fp16x3", "ms": round(ms, 3),
                           "frames_per_s": round(B * 1e3 / ms, 2), "conv_gflop": round(gf, 1), "conv_launches": len(prof),
                           "conv_ms_eager": round(tconv, 3), "tflops": round(gf / ms, 1),
