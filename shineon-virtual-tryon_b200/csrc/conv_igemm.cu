@@ -114,12 +114,11 @@ __device__ __forceinline__ void store_planes_vec(const float (&vals)[32], int cn
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     if (i < cnt) {
-      __align__(16) plane_t hi[8];
-      __align__(16) plane_t lo[8];
+      uint32_t hi[4], lo[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) split16(vals[i + j], FMT, hi[j], lo[j]);
-      *reinterpret_cast<uint4*>(yh + base + i) = *reinterpret_cast<const uint4*>(hi);
-      if (yl) *reinterpret_cast<uint4*>(yl + base + i) = *reinterpret_cast<const uint4*>(lo);
+      for (int j = 0; j < 4; ++j) split16x2(vals[i + 2 * j], vals[i + 2 * j + 1], FMT, hi[j], lo[j]);
+      *reinterpret_cast<uint4*>(yh + base + i) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (yl) *reinterpret_cast<uint4*>(yl + base + i) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
   }
 }
@@ -187,14 +186,11 @@ __device__ __forceinline__ void conv_store_chunk_coalesced(const float (&vals)[3
     const long base = rowbase[it] + c_first + 4 * u;
     if (a.y_f32) *reinterpret_cast<float4*>(a.y_f32 + base) = v;
     if (a.y_hi) {
-      plane_t h0, h1, h2, h3, l0, l1, l2, l3;
-      split16(v.x, a.fmt, h0, l0);
-      split16(v.y, a.fmt, h1, l1);
-      split16(v.z, a.fmt, h2, l2);
-      split16(v.w, a.fmt, h3, l3);
-      *reinterpret_cast<uint2*>(a.y_hi + base) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
-      if (a.y_lo)
-        *reinterpret_cast<uint2*>(a.y_lo + base) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+      uint32_t h01, h23, l01, l23;
+      split16x2(v.x, v.y, a.fmt, h01, l01);
+      split16x2(v.z, v.w, a.fmt, h23, l23);
+      *reinterpret_cast<uint2*>(a.y_hi + base) = make_uint2(h01, h23);
+      if (a.y_lo) *reinterpret_cast<uint2*>(a.y_lo + base) = make_uint2(l01, l23);
     }
   }
 }

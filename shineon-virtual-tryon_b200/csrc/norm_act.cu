@@ -388,23 +388,22 @@ __global__ void __launch_bounds__(256)
     }
     if (yh) {
       const long po = ((long)n * HW + p) * cpad + g * VEC;
-      plane_t h[VEC], l[VEC];
+      if constexpr (VEC >= 4) {
+        uint32_t h[VEC / 2], l[VEC / 2];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) split16(v[j], FMT, h[j], l[j]);
-      if constexpr (VEC == 8) {
-        *reinterpret_cast<uint4*>(yh + po) =
-            make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
-                       (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
-        if (yl)
-          *reinterpret_cast<uint4*>(yl + po) =
-              make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
-                         (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
-      } else if constexpr (VEC == 4) {
-        *reinterpret_cast<uint2*>(yh + po) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
-        if (yl) *reinterpret_cast<uint2*>(yl + po) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+        for (int j = 0; j < VEC / 2; ++j) split16x2(v[2 * j], v[2 * j + 1], FMT, h[j], l[j]);
+        if constexpr (VEC == 8) {
+          *reinterpret_cast<uint4*>(yh + po) = make_uint4(h[0], h[1], h[2], h[3]);
+          if (yl) *reinterpret_cast<uint4*>(yl + po) = make_uint4(l[0], l[1], l[2], l[3]);
+        } else {
+          *reinterpret_cast<uint2*>(yh + po) = make_uint2(h[0], h[1]);
+          if (yl) *reinterpret_cast<uint2*>(yl + po) = make_uint2(l[0], l[1]);
+        }
       } else {
-        yh[po] = h[0];
-        if (yl) yl[po] = l[0];
+        plane_t h, l;
+        split16(v[0], FMT, h, l);
+        yh[po] = h;
+        if (yl) yl[po] = l;
       }
     }
   }

@@ -84,16 +84,18 @@ __global__ void __launch_bounds__(256)
         yf[pix * yf_cstride + c0] = v[0];
     }
     if (yh) {
-      plane_t h[VEC], l[VEC];
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) split16(v[j], FMT, h[j], l[j]);
       const long po = pix * cpad + c0;
       if constexpr (VEC == 4) {
-        *reinterpret_cast<uint2*>(yh + po) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
-        if (yl) *reinterpret_cast<uint2*>(yl + po) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+        uint32_t h01, h23, l01, l23;
+        split16x2(v[0], v[1], FMT, h01, l01);
+        split16x2(v[2], v[3], FMT, h23, l23);
+        *reinterpret_cast<uint2*>(yh + po) = make_uint2(h01, h23);
+        if (yl) *reinterpret_cast<uint2*>(yl + po) = make_uint2(l01, l23);
       } else {
-        yh[po] = h[0];
-        if (yl) yl[po] = l[0];
+        plane_t h, l;
+        split16(v[0], FMT, h, l);
+        yh[po] = h;
+        if (yl) yl[po] = l;
       }
     }
   }
