@@ -3,6 +3,8 @@
 //   energy[i,j] = <q_i, k_j>;  A = softmax_j(energy);  o_i[c] = sum_j A[i,j] v_j[c];  y = act(gamma*o + x)
 // for one query pixel i per CTA.  N = H*W <= 192 on the ShineOn U-Net (bottom two levels), so the whole
 // key/value set of an image stays L1/L2 resident; fp32 throughout.
+#include <stdlib.h>
+
 #include "tcgen05.cuh"
 
 namespace shineon {
@@ -364,6 +366,10 @@ using namespace shineon;
 
 static inline int ld_floats(int C, int Cq) { return 2 * Cq + C; }
 
+int shineon_sagan_attention_tc(const float* qkv, const float* x, const float* gamma, float* y_f32, void* y_hi, void* y_lo,
+                               int N, int HW, int C, int Cq, int cpad, int act, float act_param, int plane_fmt,
+                               cudaStream_t stream);  // attention_tc.cu
+
 extern "C" int shineon_sagan_attention(const float* qkv, const float* x, const float* gamma, float* y_f32, void* y_hi,
                                        void* y_lo, int N, int HW, int C, int Cq, int cpad, int act, float act_param,
                                        int plane_fmt, shineon_stream_t stream) {
@@ -374,6 +380,13 @@ extern "C" int shineon_sagan_attention(const float* qkv, const float* x, const f
   SHINEON_REQUIRE(((2 * Cq + C) & 3) == 0 || (Cq & 3) != 0, "sagan_attention: row stride must keep float4 alignment");
   auto smem_for = [&](int qt) { return sizeof(float) * ((size_t)qt * Cq + (size_t)qt * HW + qt); };
   cudaStream_t st = (cudaStream_t)stream;
+  // tensor-core kernel (attention_tc.cu) for the U-Net's shapes; > 0 = shape does not fit.  SHINEON_ATTENTION_TC=0 keeps the
+  // CUDA-core kernels below (A/B measurements, the fp32 cross-check in the tests)
+  static const bool use_tc = [] { const char* e = getenv("SHINEON_ATTENTION_TC"); return !(e && e[0] == '0'); }();
+  if (use_tc) {
+    const int rc = shineon_sagan_attention_tc(qkv, x, gamma, y_f32, y_hi, y_lo, N, HW, C, Cq, cpad, act, act_param, plane_fmt, st);
+    if (rc <= 0) return rc;
+  }
   // register-tiled kernel: needs 16-byte aligned q/k/v/x rows and plane rows (8 channels = one 128-bit store)
   const bool aligned = (C % 8 == 0) && (Cq % 4 == 0) && (!y_hi || cpad % 8 == 0) &&
                        ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y_f32) |

@@ -396,6 +396,36 @@ def test_sagan_attention(ops, hw):
     assert_close(yp.float(), want, atol=3e-5, rtol=1e-4, what="attention planes")
 
 
+@pytest.mark.parametrize("hw", [(4, 3), (8, 6), (16, 12), (13, 10), (1, 1)])
+@pytest.mark.parametrize("act", [None, "gelu"])
+def test_sagan_attention_tensor_core(ops, hw, act):
+    """The tcgen05 attention kernel (csrc/attention_tc.cu: C = 512, Cq = 64, HW <= 192 -- the U-Net's shapes): one and two
+    query tiles, ragged tiles, key padding, energies with a wide dynamic range, f32 and plane outputs."""
+    from oracle.unet import self_attention
+
+    H, W = hw
+    C, Cq, N = 512, 64, 3
+    g = torch.Generator().manual_seed(H * 31 + W)
+    x = torch.randn(N, C, H, W, generator=g)
+    sd = {"a.query_conv.weight": torch.randn(Cq, C, 1, 1, generator=g) * 0.06, "a.query_conv.bias": torch.randn(Cq, generator=g) * 0.1,
+          "a.key_conv.weight": torch.randn(Cq, C, 1, 1, generator=g) * 0.06, "a.key_conv.bias": torch.randn(Cq, generator=g) * 0.1,
+          "a.value_conv.weight": torch.randn(C, C, 1, 1, generator=g) * 0.05, "a.value_conv.bias": torch.randn(C, generator=g) * 0.1,
+          "a.gamma": torch.tensor([1.3])}
+    want = self_attention(sd, "a.", x)
+    if act == "gelu":
+        want = F.gelu(want)
+    q = F.conv2d(x, sd["a.query_conv.weight"], sd["a.query_conv.bias"])
+    k = F.conv2d(x, sd["a.key_conv.weight"], sd["a.key_conv.bias"])
+    v = F.conv2d(x, sd["a.value_conv.weight"], sd["a.value_conv.bias"])
+    energy_span = torch.bmm(q.flatten(2).transpose(1, 2), k.flatten(2)).abs().max().item()
+    qkv = nhwc(torch.cat([q, k, v], 1)).cuda()
+    yf, yp = ops.sagan_attention(qkv, nhwc(x).cuda(), sd["a.gamma"].cuda(), Cq, act=act, want_f32=True, want_planes=True)
+    torch.cuda.synchronize()
+    err = assert_close(nchw(yf), want, atol=5e-5, rtol=1e-4, what="attention (tcgen05) f32")
+    assert_close(yp.float(), want, atol=6e-5, rtol=1e-4, what="attention (tcgen05) planes")
+    print(f"HW={H * W} act={act}: max abs err {err:.2e} (|energy| up to {energy_span:.1f})")
+
+
 def test_l2norm_correlation_and_linear(ops):
     from oracle import gmm
 
