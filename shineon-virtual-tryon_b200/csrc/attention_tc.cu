@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(256, 1)
   constexpr uint32_t kKBytes = HWP * 128;          // one plane of K
   constexpr uint32_t kVAtom = HWP * 128;           // one 64-channel MN atom of a V chunk, all keys
   constexpr uint32_t kVPlane = 2 * kVAtom;         // 128 channels
-  constexpr uint32_t kRegionA = (2 * kVPlane > 2 * (kQBytes + kKBytes)) ? 2 * kVPlane : 2 * (kQBytes + kKBytes);
+  constexpr int kCPP = HWP == 64 ? 4 : 1;          // 128-channel V chunks staged (and multiplied) per pass: all of C for short key sets
+  constexpr uint32_t kRegionA = (kCPP * 2 * kVPlane > 2 * (kQBytes + kKBytes)) ? kCPP * 2 * kVPlane : 2 * (kQBytes + kKBytes);
   constexpr uint32_t kPTile = kAtM * 128;          // one 64-key k-block of P, one plane
   constexpr uint32_t kPPlane = kKB * kPTile;
   extern __shared__ uint8_t smem_raw[];
@@ -167,44 +168,47 @@ __global__ void __launch_bounds__(256, 1)
     }
     rowsum = sum;
   }
-  // ---- phase 3: o = P V, one 128-channel chunk at a time (V chunk staged as the MN-major B operand)
+  // ---- phase 3: o = P V, kCPP 128-channel chunks per pass (V staged as the MN-major B operand)
   const int n_chunks = C / kAtCN;
-  for (int cc = 0; cc < n_chunks; ++cc) {
-    if (cc > 0) {  // the previous chunk's MMAs have consumed region A
+  for (int c_first = 0; c_first < n_chunks; c_first += kCPP) {
+    if (c_first > 0) {  // the previous pass's MMAs have consumed region A
       mbar_wait(bar_a, phase);
       phase ^= 1;
     }
-    uint8_t* vh = sA;
-    uint8_t* vl = sA + kVPlane;
-    for (int it = tid; it < HWP * 16; it += 256) {
-      const int j = it >> 4, ch = it & 15;  // key, 8-channel chunk of the 128-channel window
+    const int n_pass = min(kCPP, n_chunks - c_first);
+    for (int it = tid; it < HWP * 16 * n_pass; it += 256) {
+      const int j = (it >> 4) % HWP, ch = it & 15, cl = it / (HWP * 16);  // key, 8-channel chunk of the 128-channel window, window
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
       if (j < HW) {
-        const float* src = qkv_n + (long)j * ld + 2 * kAtCq + cc * kAtCN + ch * 8;
+        const float* src = qkv_n + (long)j * ld + 2 * kAtCq + (c_first + cl) * kAtCN + ch * 8;
         a = __ldg(reinterpret_cast<const float4*>(src));
         b = __ldg(reinterpret_cast<const float4*>(src + 4));
       }
+      uint8_t* vh = sA + (uint32_t)cl * 2u * kVPlane;
       const uint32_t off = (uint32_t)(ch >> 3) * kVAtom + (uint32_t)j * 128u + (uint32_t)(((ch & 7) ^ (j & 7)) * 16);
-      at_store8(vh + off, vl + off, a, b, kAtVScale);
+      at_store8(vh + off, vh + kVPlane + off, a, b, kAtVScale);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
-    __syncthreads();  // also orders the softmax warps' P stores (first chunk) before the MMAs
+    __syncthreads();  // also orders the softmax warps' P stores (first pass) before the MMAs
     tc_fence_after();
     if (tid == 0) {
       const uint32_t ph = base_u + kRegionA, pl = ph + kPPlane;
-      const uint32_t vhh = base_u, vll = base_u + kVPlane;
-      const uint32_t tacc = tmem_base + (uint32_t)(cc * kAtCN);
 #pragma unroll 1
-      for (int kb = 0; kb < kKB; ++kb) {
+      for (int cl = 0; cl < n_pass; ++cl) {
+        const uint32_t vhh = base_u + (uint32_t)cl * 2u * kVPlane, vll = vhh + kVPlane;
+        const uint32_t tacc = tmem_base + (uint32_t)((c_first + cl) * kAtCN);
+#pragma unroll 1
+        for (int kb = 0; kb < kKB; ++kb) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t dPh = umma_desc_sw128(ph + kb * kPTile + k * 32), dPl = umma_desc_sw128(pl + kb * kPTile + k * 32);
-          const uint32_t voff = (uint32_t)(kb * 8 + k * 2) * 1024u;  // 16 keys per MMA = two 8-key groups
-          const uint64_t dVh = umma_desc_mn_sw128(vhh + voff, kVAtom, 1024u), dVl = umma_desc_mn_sw128(vll + voff, kVAtom, 1024u);
-          umma_f16(tacc, dPh, dVh, idesc_o, (kb | k) != 0);
-          umma_f16(tacc, dPh, dVl, idesc_o, 1);
-          umma_f16(tacc, dPl, dVh, idesc_o, 1);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t dPh = umma_desc_sw128(ph + kb * kPTile + k * 32), dPl = umma_desc_sw128(pl + kb * kPTile + k * 32);
+            const uint32_t voff = (uint32_t)(kb * 8 + k * 2) * 1024u;  // 16 keys per MMA = two 8-key groups
+            const uint64_t dVh = umma_desc_mn_sw128(vhh + voff, kVAtom, 1024u), dVl = umma_desc_mn_sw128(vll + voff, kVAtom, 1024u);
+            umma_f16(tacc, dPh, dVh, idesc_o, (kb | k) != 0);
+            umma_f16(tacc, dPh, dVl, idesc_o, 1);
+            umma_f16(tacc, dPl, dVh, idesc_o, 1);
+          }
         }
       }
       umma_commit(bar_a);
@@ -225,8 +229,9 @@ __global__ void __launch_bounds__(256, 1)
     const bool ok = pix_i < HW;
     const long pix = (long)n * HW + pix_i;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool quarter_live = i0 + q * 32 < HW;  // warp-uniform: quarters past the last query have nothing to store
 #pragma unroll 1
-    for (int c0 = half * 32; c0 < C; c0 += 64) {
+    for (int c0 = half * 32; quarter_live && c0 < C; c0 += 64) {
       uint32_t v[32];
       tmem_ld32(trow + c0, v);
       tmem_ld_wait();
@@ -293,7 +298,7 @@ int shineon_sagan_attention_tc(const float* qkv, const float* x, const float* ga
     return 1;
   const int hwp = HW <= 64 ? 64 : 192;
   auto smem_of = [](int HWP) {
-    const size_t qk = 2 * ((size_t)kAtM * 128 + (size_t)HWP * 128), v = 2 * (size_t)2 * HWP * 128;
+    const size_t qk = 2 * ((size_t)kAtM * 128 + (size_t)HWP * 128), v = (HWP == 64 ? 4 : 1) * 2 * (size_t)2 * HWP * 128;
     return (qk > v ? qk : v) + 2 * (size_t)(HWP / 64) * kAtM * 128 + 1024;
   };
   const size_t smem = smem_of(hwp);
