@@ -736,7 +736,16 @@ def run_b200(args, rank, world):
         # launch on the launching stream (events cannot be recorded inside the replayed graph of the timed region)
         prof = []
         ops.PROFILE = prof
-        ms_prof, _ = timed(step_raw, args.steps)
+
+        def step_prof(i):
+            # a ~12 ms spin kernel ahead of every eager step lets the host run ahead of the device, so the event pairs around
+            # the tensor-core launches bracket back-to-back GPU execution instead of host launch gaps (eager issue of the ~65
+            # launches takes longer than the kernels themselves); the spin is outside every event pair
+            torch.cuda._sleep(spin_cycles)
+            return step_raw(i)
+
+        spin_cycles = int(12e-3 * 1.9e9)
+        ms_prof, _ = timed(step_prof, args.steps)
         ops.PROFILE = None
         torch.cuda.synchronize()
         conv_ms = sum(r[1].elapsed_time(r[2]) for r in prof)
@@ -808,9 +817,10 @@ def run_b200(args, rank, world):
                            "counts the reference formulation's (algorithmic) FLOPs per SURVEY 8d, x3 MMAs each in fp16x3",
             "issued_tflops": main["exec_flops"] / (main["conv_ms"] * 1e-3) / 1e12 if main["conv_ms"] > 0 else 0.0,
             "conv_launches_per_step": main["conv_launches"] // args.steps,
-            "conv_share_of_step": main["conv_ms"] / main["ms_prof"],
-            "measured_on": "the same steps run eagerly right after the timed region (CUDA events around every tensor-core launch); "
-                           f"eager {main['ms_prof'] / args.steps:.3f} ms/step vs {main['ms'] / args.steps:.3f} ms/step replayed as a CUDA graph",
+            "conv_share_of_step": main["conv_ms"] / main["ms"],
+            "measured_on": "the same steps launched eagerly right after the timed region, CUDA events around every tensor-core launch, "
+                           "a spin kernel ahead of each step so the host runs ahead and the events bracket GPU execution only; "
+                           f"conv launches {main['conv_ms'] / args.steps:.3f} ms of the {main['ms'] / args.steps:.3f} ms replayed step",
             "whole_step_frac_of_tensor_peak": (GFLOP_PER_FRAME * 1e9 * frames * args.steps) / (main["ms"] * 1e-3) / 1e12 / peak_tf,
             "traffic": None,
         },
