@@ -38,6 +38,10 @@ SAMS_CASES = {
                                 person_inputs=["agnostic", "densepose", "cocopose"], encoder_input="densepose"), 2, 32, 24),
     # the reference's default architecture (64 .. 1024 features, 3 middle blocks) on one 256x192 frame
     "sams_default": (dict(_SAMS_BASE), 1, 256, 192),
+    # power step 2 that does not land on the inner / outer widths (the "extra layer" branches, sams_generator.py:158-165,
+    # 197-209), 4 .. 128 features, 5x5 SPADE kernels on plain BatchNorm, Swish, a 2-frame window
+    "sams_odd_widths": (dict(_SAMS_BASE, norm_G="spectralspadebatch5x5", activation="swish", ngf_pow_outer=3, ngf_pow_inner=6,
+                             ngf_pow_step=2, num_middle=1, n_frames_total=2, n_frames_now=2, encoder_input="densepose"), 2, 32, 24),
 }
 
 
