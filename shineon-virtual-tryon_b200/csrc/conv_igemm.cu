@@ -858,28 +858,30 @@ __global__ void __launch_bounds__(128)
 }
 
 // ------------------------------------------------------------------------------- weight packing
-__global__ void __launch_bounds__(256)
+// One thread per (output channel, packed input channel): its kh*kw taps are consecutive floats of the source (a warp reads
+// 32 neighbouring runs: every fetched sector is used across the tap loop) and each tap's store is coalesced over the packed
+// channels.  (The first version walked the destination linearly with three 64-bit divisions per element and a
+// kh*kw-strided gather: 0.43 ms per training step for 45 M elements, profiles/r02_train_launches_summary.md.)
+__global__ void __launch_bounds__(128)
     pack_conv_weight_kernel(const float* __restrict__ w, plane_t* __restrict__ whi,
                             plane_t* __restrict__ wlo, int Cout, int Cin, int kh, int kw, int cin_pad,
                             const int32_t* __restrict__ chan_map, int transpose_io, int fmt, float w_scale) {
-  const long total = (long)Cout * kh * kw * cin_pad;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
-    const int cp = (int)(e % cin_pad);
-    const int tap = (int)((e / cin_pad) % (kh * kw));
-    const int co = (int)(e / ((long)cin_pad * kh * kw));
-    const int ci = chan_map ? chan_map[cp] : (cp < Cin ? cp : -1);
-    float v = 0.f;
-    if (ci >= 0 && ci < Cin) {
-      const int fy = tap / kw, fx = tap - fy * kw;
-      if (!transpose_io)
-        v = w[(((long)co * Cin + ci) * kh + fy) * kw + fx];
-      else  // ConvTranspose2d weight [Cin][Cout][kh][kw], taps flipped
-        v = w[(((long)ci * Cout + co) * kh + (kh - 1 - fy)) * kw + (kw - 1 - fx)];
+  const int taps = kh * kw;
+  for (int co = blockIdx.y; co < Cout; co += gridDim.y) {
+    for (int cp = blockIdx.x * blockDim.x + threadIdx.x; cp < cin_pad; cp += gridDim.x * blockDim.x) {
+      const int ci = chan_map ? chan_map[cp] : (cp < Cin ? cp : -1);
+      const bool ok = ci >= 0 && ci < Cin;
+      // ConvTranspose2d weight [Cin][Cout][kh][kw] is read with its taps flipped
+      const float* src = ok ? (transpose_io ? w + ((long)ci * Cout + co) * taps : w + ((long)co * Cin + ci) * taps) : w;
+      const long dst = (long)co * taps * cin_pad + cp;
+      for (int t = 0; t < taps; ++t) {
+        const float v = ok ? __ldg(src + (transpose_io ? taps - 1 - t : t)) : 0.f;
+        plane_t h, l;
+        split16(v * w_scale, fmt, h, l);
+        whi[dst + (long)t * cin_pad] = h;
+        if (wlo) wlo[dst + (long)t * cin_pad] = l;
+      }
     }
-    plane_t h, l;
-    split16(v * w_scale, fmt, h, l);
-    whi[e] = h;
-    if (wlo) wlo[e] = l;
   }
 }
 
@@ -1304,11 +1306,9 @@ extern "C" int shineon_pack_conv_weight(const float* w, void* w_hi, void* w_lo, 
   SHINEON_REQUIRE(w && w_hi, "pack_conv_weight: null pointer");
   SHINEON_REQUIRE(Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && cin_pad >= 1, "pack_conv_weight: bad shape");
   SHINEON_REQUIRE(chan_map != nullptr || cin_pad >= Cin, "pack_conv_weight: cin_pad < Cin");
-  long total = (long)Cout * kh * kw * cin_pad;
-  long blocks = (total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  pack_conv_weight_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, (plane_t*)w_hi, (plane_t*)w_lo,
-                                                                       Cout, Cin, kh, kw, cin_pad, chan_map, transpose_io, plane_fmt, w_scale);
+  const dim3 grid(cdiv(cin_pad, 128), Cout < 65535 ? Cout : 65535);
+  pack_conv_weight_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(w, (plane_t*)w_hi, (plane_t*)w_lo, Cout, Cin, kh, kw, cin_pad,
+                                                                  chan_map, transpose_io, plane_fmt, w_scale);
   return after_launch("pack_conv_weight_kernel");
 }
 

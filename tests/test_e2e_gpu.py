@@ -148,6 +148,48 @@ def test_benchmarked_step_80_frames(cuda, graph):
         assert torch.equal((tryon_masks.cpu()[::fs] > 0.5)[safe], (wm > 0.5)[safe])
 
 
+def test_benchmarked_step_160_frames(cuda):
+    """bench.py's default step since round 2: 32 clips x 5 frames = 160 frames as one batch.  (a) tensor entry point, replayed
+    as a CUDA graph, on the 80 golden frames twice over (frames are independent in the reference: eval-mode BatchNorm in the
+    GMM, InstanceNorm in the U-Net), both halves against the reference golden; (b) the uint8 entry point bench.py times
+    (TryOnPipeline.run_raw: fused frame prep -> stem operands -> 8-bit writer, CUDA graph) bit-identical to FramePrep -> tensor
+    entry point -> visualization.save_images' encoding on the same 160 synthetic frames."""
+    import bench
+    from shineon_virtual_tryon_b200 import ops
+    from shineon_virtual_tryon_b200.pipeline import TryOnPipeline
+
+    warp, _ = build_model("warp")
+    tom, _ = build_model("unet_mask")
+    pipe = TryOnPipeline(warp, tom, cuda_graph=True)
+    pg, cloth, pt = (torch.cat([t, t], 0).cuda() for t in cases.pipeline_inputs())
+    assert pg.shape[0] == 160
+    _, _, gold = load_golden("pipeline_b80")
+    fs, st = cases.PIPELINE_FRAME_STEP, cases.PIPELINE_SUB
+    with torch.no_grad():
+        for _ in range(3):
+            p_tryons, tryon_masks, warped = pipe(pg, cloth, pt)
+    torch.cuda.synchronize()
+    assert pipe.replayed_launches > 0
+    for half in (0, 1):
+        sl = slice(80 * half, 80 * (half + 1))
+        assert_close(cases.subsample(warped[sl].cpu()[::fs], st), gold["warped_cloth"], what=f"warped cloth, half {half}")
+        assert_close(cases.subsample(tryon_masks[sl].cpu()[::fs], st), gold["tryon_masks"], what=f"tryon_masks, half {half}")
+        assert_close(cases.subsample(p_tryons[sl].cpu()[::fs], st), gold["p_tryons"], what=f"p_tryons, half {half}")
+    # (b) the uint8 step
+    raw = bench.synth_raw_frames(160, 11, pinned=False)
+    dev = [raw[k].cuda() for k in TryOnPipeline.RAW_KEYS]
+    prep = ops.FramePrep(256, 192, device="cuda")
+    with torch.no_grad():
+        for _ in range(3):
+            got = pipe.run_raw(*dev, prep)
+        b = prep(*dev)  # RAW_KEYS order = FramePrep's argument order (parse, cloth, densepose, image)
+        eager = TryOnPipeline(warp, tom)
+        pt2, _, _ = eager(torch.cat([b["agnostic"], b["cocopose"]], 1), b["cloth"], torch.cat([b["agnostic"], b["densepose"]], 1))
+        want = ops.image_to_u8(pt2.contiguous())
+    torch.cuda.synchronize()
+    assert got.dtype == torch.uint8 and torch.equal(got.reshape(want.shape), want)
+
+
 def test_tryon_pipeline_5_frame_clip(cuda):
     """BASELINE config 3 (primary): a 5-frame clip as a batch through GMM -> warp -> TOM."""
     warp, sdw = build_model("warp")
