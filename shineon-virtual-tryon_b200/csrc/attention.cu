@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(128)
     sagan_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ x, const float* __restrict__ gamma,
                            float* __restrict__ yf, plane_t* __restrict__ yh, plane_t* __restrict__ yl,
                            int HW, int C, int Cq, int cpad, int act, float act_param, int fmt) {
+  pdl_grid_sync();
   extern __shared__ float sm[];  // q[QT][Cq] | e[QT][HW] | inv[QT]
   float* sq = sm;
   float* se = sm + QT * Cq;
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(256)
     sagan_attention_tiled_kernel(const float* __restrict__ qkv, const float* __restrict__ x, const float* __restrict__ gamma,
                                  float* __restrict__ yf, plane_t* __restrict__ yh, plane_t* __restrict__ yl,
                                  int HW, int C, int Cq, int cpad, int act, float act_param, int fmt, int kc) {
+  pdl_grid_sync();
   constexpr int QG = QB / 8;       // 8-query groups
   constexpr int PARTS = 256 / QB;  // key partitions of the softmax phase
   extern __shared__ __align__(16) float sm[];
@@ -410,13 +412,13 @@ extern "C" int shineon_sagan_attention(const float* qkv, const float* x, const f
         if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "sagan_attention: shared memory opt-in: %s", cudaGetErrorString(e));
         opted = smem;
       }
-      sagan_attention_tiled_kernel<QB><<<dim3(cdiv(HW, QB), N), 256, smem, st>>>(
+      klaunch(sagan_attention_tiled_kernel<QB>, dim3(cdiv(HW, QB), N), 256, smem, st, 
           qkv, x, gamma, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, Cq, cpad, act, act_param, plane_fmt, kc);
       return after_launch("sagan_attention_tiled_kernel");
     }
   }
 #define SHINEON_ATT(QT_)                                                                                            \
-  sagan_attention_kernel<QT_><<<dim3(cdiv(HW, QT_), N), 128, smem_for(QT_), st>>>(                                   \
+  klaunch(sagan_attention_kernel<QT_>, dim3(cdiv(HW, QT_), N), 128, smem_for(QT_), st,                                    \
       qkv, x, gamma, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, Cq, cpad, act, act_param, plane_fmt)
   if (smem_for(16) <= 40 * 1024) SHINEON_ATT(16);
   else if (smem_for(4) <= 40 * 1024) SHINEON_ATT(4);

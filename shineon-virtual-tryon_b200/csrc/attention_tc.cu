@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(256, 1)
     sagan_attention_tc_kernel(const float* __restrict__ qkv, const float* __restrict__ x, const float* __restrict__ gamma,
                               float* __restrict__ yf, plane_t* __restrict__ yh, plane_t* __restrict__ yl, int HW, int C,
                               int cpad, int act, float act_param, int fmt) {
+  pdl_grid_sync();
   constexpr int kKB = HWP / 64;                    // key k-blocks
   constexpr uint32_t kQBytes = kAtM * 128;         // one plane of Q
   constexpr uint32_t kKBytes = HWP * 128;          // one plane of K
@@ -311,7 +312,7 @@ int shineon_sagan_attention_tc(const float* qkv, const float* x, const float* ga
       opted = e == cudaSuccess;
     }
     if (e == cudaSuccess)
-      sagan_attention_tc_kernel<64><<<grid, 256, smem, stream>>>(qkv, x, gamma, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, cpad,
+      klaunch(sagan_attention_tc_kernel<64>, grid, 256, smem, stream, qkv, x, gamma, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, cpad,
                                                                  act, act_param, plane_fmt);
   } else {
     static bool opted = false;
@@ -320,7 +321,7 @@ int shineon_sagan_attention_tc(const float* qkv, const float* x, const float* ga
       opted = e == cudaSuccess;
     }
     if (e == cudaSuccess)
-      sagan_attention_tc_kernel<192><<<grid, 256, smem, stream>>>(qkv, x, gamma, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, cpad,
+      klaunch(sagan_attention_tc_kernel<192>, grid, 256, smem, stream, qkv, x, gamma, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, cpad,
                                                                   act, act_param, plane_fmt);
   }
   if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "sagan_attention_tc: shared memory opt-in: %s", cudaGetErrorString(e));

@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(256)
     instnorm_bwd_stats_kernel(const float* __restrict__ x, const double* __restrict__ ws_fwd,
                               const float* __restrict__ g1, const float* __restrict__ g2, double* __restrict__ ws_bwd,
                               int HW, int C, int pix_per_cta, float eps, int act, float act_param) {
+  pdl_grid_sync();
   __shared__ float s1[8][33], s2[8][33];
   const int n = blockIdx.z;
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256)
                               const float* __restrict__ g2, float* __restrict__ gxf, plane_t* __restrict__ gxh,
                               plane_t* __restrict__ gxl, int HW, int C, int cpad, float eps, int do_norm, int act,
                               float act_param, int fmt) {
+  pdl_grid_sync();
   extern __shared__ float s_tab[];  // mean[C], rstd[C], m1[C], m2[C]
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     act_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g1, const float* __restrict__ g2,
                    float* __restrict__ gz, long n, int act, float act_param) {
+  pdl_grid_sync();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     float g = g1[i];
     if (g2) g += g2[i];
@@ -186,6 +189,7 @@ __device__ __forceinline__ void up2_adj(int i, int n_in, int (&r)[4], float (&w)
 __global__ void __launch_bounds__(256)
     upsample2x_cat_bwd_kernel(const float* __restrict__ gu, int cs_in, float* __restrict__ g0, int C0,
                               float* __restrict__ g1, int C1, int H, int W) {
+  pdl_grid_sync();
   const int n = blockIdx.z, iy = blockIdx.y;
   const int Ct = C0 + C1;
   const int cg = (Ct + 3) / 4;
@@ -236,6 +240,7 @@ __global__ void __launch_bounds__(128)
     sagan_bwd_a_kernel(const float* __restrict__ qkv, const float* __restrict__ gamma, const float* __restrict__ gout,
                        float* __restrict__ Abuf, float* __restrict__ dEbuf, float* __restrict__ gqkv,
                        double* __restrict__ ggamma, int HW, int C, int Cq) {
+  pdl_grid_sync();
   extern __shared__ float sm[];  // q[QT][Cq] | e[QT][HW] | de[QT][HW] | red[QT][4] | D[QT]
   float* sq = sm;
   float* se = sq + QT * Cq;
@@ -354,6 +359,7 @@ __global__ void __launch_bounds__(128)
     sagan_bwd_b_kernel(const float* __restrict__ qkv, const float* __restrict__ gamma, const float* __restrict__ gout,
                        const float* __restrict__ Abuf, const float* __restrict__ dEbuf, float* __restrict__ gqkv,
                        int HW, int C, int Cq) {
+  pdl_grid_sync();
   // one CTA per key j: dk_j[c'] = sum_i dE[i][j] q_i[c'],  dv_j[c] = gamma * sum_i A[i][j] g_i[c]
   extern __shared__ float sm[];  // a[HW] | de[HW]
   float* sa = sm;
@@ -382,6 +388,7 @@ __global__ void __launch_bounds__(128)
 }
 
 __global__ void scalar_finish_kernel(const double* __restrict__ acc, float* __restrict__ out, float alpha, float beta) {
+  pdl_grid_sync();
   if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = beta == 0.f ? alpha * (float)acc[0] : fmaf(beta, out[0], alpha * (float)acc[0]);
 }
 
@@ -392,6 +399,7 @@ __global__ void __launch_bounds__(256)
                            const float* __restrict__ g_mask, const float* __restrict__ g_tryon,
                            const float* __restrict__ g_fmask, float* __restrict__ gu, float* __restrict__ g_warped,
                            int HW, int nf, int f, int flow_warp) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
     const float* up = u + ((long)b * HW + p) * Cout;
@@ -430,6 +438,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     l1_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ ga, double* __restrict__ acc,
                    long n, float gscale, int accumulate_grad) {
+  pdl_grid_sync();
   float part = 0.f;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float d = a[i] - b[i];
@@ -456,6 +465,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     maxpool2x2_fwd_kernel(const float* __restrict__ x, float* __restrict__ yf, plane_t* __restrict__ yh,
                           plane_t* __restrict__ yl, int H, int W, int C, int cpad, int fmt, long total) {
+  pdl_grid_sync();
   const int Ho = H / 2, Wo = W / 2;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const int c = (int)(e % C);
@@ -483,6 +493,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     maxpool2x2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, int gy_cstride, float* __restrict__ gx,
                           int H, int W, int C, long total) {
+  pdl_grid_sync();
   const int Ho = H / 2, Wo = W / 2;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const int c = (int)(e % C);
@@ -510,6 +521,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     nhwc_to_nchw_add_kernel(const float* __restrict__ x, int cstride, float* __restrict__ y, int HW, int C, long total,
                             int accumulate) {
+  pdl_grid_sync();
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const int p = (int)(e % HW);
     const long r = e / HW;
@@ -528,7 +540,7 @@ extern "C" int shineon_nhwc_to_nchw_add(const float* x, int x_cstride, float* y,
                                         shineon_stream_t stream) {
   SHINEON_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && x_cstride >= C, "nhwc_to_nchw_add: bad arguments");
   const long total = (long)N * C * H * W;
-  nhwc_to_nchw_add_kernel<<<grid_x(total, 256), 256, 0, (cudaStream_t)stream>>>(x, x_cstride, y, H * W, C, total, accumulate);
+  klaunch(nhwc_to_nchw_add_kernel, grid_x(total, 256), 256, 0, (cudaStream_t)stream, x, x_cstride, y, H * W, C, total, accumulate);
   return after_launch("nhwc_to_nchw_add_kernel");
 }
 
@@ -549,7 +561,7 @@ extern "C" int shineon_instnorm_act_bwd(const float* x, const double* stats_fwd,
     if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "instnorm_act_bwd memset: %s", cudaGetErrorString(e));
     const int pix_per_cta = 128;
     dim3 grid(cdiv(HW, pix_per_cta), cdiv(C, 32), N);
-    instnorm_bwd_stats_kernel<<<grid, 256, 0, stream>>>(x, stats_fwd, g1, g2, stats_ws, HW, C, pix_per_cta, eps, act, act_param);
+    klaunch(instnorm_bwd_stats_kernel, grid, 256, 0, stream, x, stats_fwd, g1, g2, stats_ws, HW, C, pix_per_cta, eps, act, act_param);
     int rc = after_launch("instnorm_bwd_stats_kernel");
     if (rc) return rc;
   }
@@ -558,10 +570,10 @@ extern "C" int shineon_instnorm_act_bwd(const float* x, const double* stats_fwd,
   dim3 grid(grid_x((long)HW * (C / vec), 256), N);
   const size_t sm = 4 * C * sizeof(float);
   if (vec == 4)
-    instnorm_bwd_apply_kernel<4><<<grid, 256, sm, stream>>>(x, stats_fwd, stats_ws, g1, g2, gx_f32, (plane_t*)gx_hi, (plane_t*)gx_lo,
+    klaunch(instnorm_bwd_apply_kernel<4>, grid, 256, sm, stream, x, stats_fwd, stats_ws, g1, g2, gx_f32, (plane_t*)gx_hi, (plane_t*)gx_lo,
                                                             HW, C, cpad, eps, do_norm, act, act_param, plane_fmt);
   else
-    instnorm_bwd_apply_kernel<1><<<grid, 256, sm, stream>>>(x, stats_fwd, stats_ws, g1, g2, gx_f32, (plane_t*)gx_hi, (plane_t*)gx_lo,
+    klaunch(instnorm_bwd_apply_kernel<1>, grid, 256, sm, stream, x, stats_fwd, stats_ws, g1, g2, gx_f32, (plane_t*)gx_hi, (plane_t*)gx_lo,
                                                             HW, C, cpad, eps, do_norm, act, act_param, plane_fmt);
   return after_launch("instnorm_bwd_apply_kernel");
 }
@@ -569,7 +581,7 @@ extern "C" int shineon_instnorm_act_bwd(const float* x, const double* stats_fwd,
 extern "C" int shineon_act_bwd(const float* z, const float* g1, const float* g2, float* gz, long n, int act, float act_param,
                                shineon_stream_t stream) {
   SHINEON_REQUIRE(z && g1 && gz && n > 0, "act_bwd: bad arguments");
-  act_bwd_kernel<<<grid_x(n, 256), 256, 0, (cudaStream_t)stream>>>(z, g1, g2, gz, n, act, act_param);
+  klaunch(act_bwd_kernel, grid_x(n, 256), 256, 0, (cudaStream_t)stream, z, g1, g2, gz, n, act, act_param);
   return after_launch("act_bwd_kernel");
 }
 
@@ -578,7 +590,7 @@ extern "C" int shineon_upsample2x_cat_bwd(const float* g_up, int g_cstride, floa
   SHINEON_REQUIRE(g_up && g0 && C0 > 0 && (g1 != nullptr) == (C1 > 0), "upsample2x_cat_bwd: bad arguments");
   SHINEON_REQUIRE(g_cstride >= C0 + C1 && N > 0 && N <= 65535 && H > 0 && H <= 65535 && W > 0, "upsample2x_cat_bwd: bad shape");
   dim3 grid(cdiv(W * ((C0 + C1 + 3) / 4), 256), H, N);
-  upsample2x_cat_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g_up, g_cstride, g0, C0, g1, C1, H, W);
+  klaunch(upsample2x_cat_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, g_up, g_cstride, g0, C0, g1, C1, H, W);
   return after_launch("upsample2x_cat_bwd_kernel");
 }
 
@@ -601,13 +613,13 @@ extern "C" int shineon_sagan_attention_bwd(const float* qkv, const float* gamma,
   constexpr int QT = 8;
   const size_t smA = sizeof(float) * ((size_t)QT * Cq + 2 * (size_t)QT * HW + QT * 4 + QT);
   SHINEON_REQUIRE(smA <= 48 * 1024 && 2 * HW * sizeof(float) <= 48 * 1024, "sagan_attention_bwd: HW=%d too large for this kernel", HW);
-  sagan_bwd_a_kernel<QT><<<dim3(cdiv(HW, QT), N), 128, smA, st>>>(qkv, gamma, g_out, Abuf, dEbuf, g_qkv, acc, HW, C, Cq);
+  klaunch(sagan_bwd_a_kernel<QT>, dim3(cdiv(HW, QT), N), 128, smA, st, qkv, gamma, g_out, Abuf, dEbuf, g_qkv, acc, HW, C, Cq);
   int rc = after_launch("sagan_bwd_a_kernel");
   if (rc) return rc;
-  sagan_bwd_b_kernel<<<dim3(HW, N), 128, 2 * HW * sizeof(float), st>>>(qkv, gamma, g_out, Abuf, dEbuf, g_qkv, HW, C, Cq);
+  klaunch(sagan_bwd_b_kernel, dim3(HW, N), 128, 2 * HW * sizeof(float), st, qkv, gamma, g_out, Abuf, dEbuf, g_qkv, HW, C, Cq);
   rc = after_launch("sagan_bwd_b_kernel");
   if (rc) return rc;
-  scalar_finish_kernel<<<1, 32, 0, st>>>(acc, g_gamma, 1.f, beta_gamma);
+  klaunch(scalar_finish_kernel, 1, 32, 0, st, acc, g_gamma, 1.f, beta_gamma);
   return after_launch("scalar_finish_kernel");
 }
 
@@ -621,7 +633,7 @@ extern "C" int shineon_tom_compose_bwd(const float* unet_out, int Cout, const fl
   SHINEON_REQUIRE(!warped_prev || flow_warp, "tom_compose_bwd: warped_prev needs flow_warp");
   SHINEON_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "tom_compose_bwd: bad shape");
   dim3 grid(grid_x((long)H * W, 256), B);
-  tom_compose_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(unet_out, Cout, cloth, warped_prev, g_rendereds, g_masks,
+  klaunch(tom_compose_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, unet_out, Cout, cloth, warped_prev, g_rendereds, g_masks,
                                                                 g_tryons, g_flow_masks, g_unet_out, g_warped_prev, H * W,
                                                                 n_frames, frame, flow_warp);
   return after_launch("tom_compose_bwd_kernel");
@@ -635,10 +647,10 @@ extern "C" int shineon_l1_loss(const float* a, const float* b, float* grad_a, fl
   if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "l1_loss memset: %s", cudaGetErrorString(e));
   int blocks = grid_x(n, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  l1_loss_kernel<<<blocks, 256, 0, st>>>(a, b, grad_a, (double*)workspace, n, loss_weight / (float)n, accumulate_grad);
+  klaunch(l1_loss_kernel, blocks, 256, 0, st, a, b, grad_a, (double*)workspace, n, loss_weight / (float)n, accumulate_grad);
   int rc = after_launch("l1_loss_kernel");
   if (rc) return rc;
-  scalar_finish_kernel<<<1, 32, 0, st>>>((const double*)workspace, loss, loss_weight / (float)n, beta_loss);
+  klaunch(scalar_finish_kernel, 1, 32, 0, st, (const double*)workspace, loss, loss_weight / (float)n, beta_loss);
   return after_launch("scalar_finish_kernel");
 }
 
@@ -647,7 +659,7 @@ extern "C" int shineon_maxpool2x2_fwd(const float* x, float* y_f32, void* y_hi, 
   SHINEON_REQUIRE(x && (y_f32 || y_hi) && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0, "maxpool2x2_fwd: bad arguments");
   SHINEON_REQUIRE(!y_hi || cpad >= C, "maxpool2x2_fwd: cpad < C");
   const long total = (long)N * (H / 2) * (W / 2) * C;
-  maxpool2x2_fwd_kernel<<<grid_x(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, H, W, C,
+  klaunch(maxpool2x2_fwd_kernel, grid_x(total, 256), 256, 0, (cudaStream_t)stream, x, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, H, W, C,
                                                                              cpad, plane_fmt, total);
   return after_launch("maxpool2x2_fwd_kernel");
 }
@@ -656,6 +668,6 @@ extern "C" int shineon_maxpool2x2_bwd(const float* x, const float* g_y, int g_cs
                                       shineon_stream_t stream) {
   SHINEON_REQUIRE(x && g_y && g_x && N > 0 && H > 0 && W > 0 && C > 0 && H % 2 == 0 && W % 2 == 0 && g_cstride >= C, "maxpool2x2_bwd: bad arguments");
   const long total = (long)N * (H / 2) * (W / 2) * C;
-  maxpool2x2_bwd_kernel<<<grid_x(total, 256), 256, 0, (cudaStream_t)stream>>>(x, g_y, g_cstride, g_x, H, W, C, total);
+  klaunch(maxpool2x2_bwd_kernel, grid_x(total, 256), 256, 0, (cudaStream_t)stream, x, g_y, g_cstride, g_x, H, W, C, total);
   return after_launch("maxpool2x2_bwd_kernel");
 }

@@ -4,6 +4,7 @@
 namespace shineon {
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launch_count{0};
+thread_local cudaError_t g_launch_error = cudaSuccess;
 }  // namespace shineon
 
 extern "C" int shineon_version(void) { return 100; }

@@ -7,8 +7,11 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <string>
+#include <utility>
 
 #include "../../include/shineon_b200.h"
 
@@ -28,10 +31,52 @@ inline int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (optional, off)
+// Every kernel of the library starts with pdl_grid_sync() and is launched through klaunch().  With SHINEON_PDL=1 the
+// launches carry the programmatic stream-serialisation attribute: the next kernel of the stream (or of the captured
+// graph) is scheduled while this one still runs - its CTAs become resident as SMs free up and block in
+// griddepcontrol.wait until this grid has completed and flushed.  Ordering is unchanged: nothing before the wait touches
+// memory, and the trigger comes after the wait, so at most one dependent grid is ever resident ahead of time (a chain
+// A -> B -> C stays transitive: C passes its wait only after B completed, and B only after it passed its own wait on A).
+// Measured on B200 (profiles/r02_pdl.md): parity suite green, but the graph-replayed steps got SLOWER (try-on 11.93 ->
+// 12.44 ms, training 6.10 -> 6.21 ms, FlowNet2 8.50 -> 8.43 ms), so the default is plain stream ordering; without the attribute
+// the two instructions are no-ops.
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SHINEON_PDL");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
+extern thread_local cudaError_t g_launch_error;
+
+template <typename... P, typename... A>
+inline void klaunch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  g_launch_error = cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+
 // Every launch goes through this: counts it and converts a launch error into a status.
 inline int after_launch(const char* what) {
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = g_launch_error;
+  g_launch_error = cudaSuccess;
   if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return SHINEON_OK;
 }

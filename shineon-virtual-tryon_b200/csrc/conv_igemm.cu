@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     conv_igemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                       const ConvArgs a) {
+  pdl_grid_sync();
   constexpr int kBBytes = BN * kBlockK * 2;
   constexpr int kPlanes = SPLIT ? 2 : 1;
   constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
@@ -604,6 +605,7 @@ template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(kI2cThreads, 1)
     conv_im2col_igemm_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                              const ConvArgs a, const Im2colSrc src) {
+  pdl_grid_sync();
   constexpr int kBBytes = BN * kBlockK * 2;
   constexpr int kPlanes = SPLIT ? 2 : 1;
   constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
@@ -820,6 +822,7 @@ __global__ void __launch_bounds__(128)
     conv_direct_kernel(const plane_t* __restrict__ xh, const plane_t* __restrict__ xl,
                        const plane_t* __restrict__ wh, const plane_t* __restrict__ wl, int H, int W,
                        ConvArgs a) {
+  pdl_grid_sync();
   const long total = (long)a.N * a.Ho * a.Wo * a.Cout;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const int c = (int)(e % a.Cout);
@@ -866,6 +869,7 @@ __global__ void __launch_bounds__(128)
     pack_conv_weight_kernel(const float* __restrict__ w, plane_t* __restrict__ whi,
                             plane_t* __restrict__ wlo, int Cout, int Cin, int kh, int kw, int cin_pad,
                             const int32_t* __restrict__ chan_map, int transpose_io, int fmt, float w_scale) {
+  pdl_grid_sync();
   const int taps = kh * kw;
   for (int co = blockIdx.y; co < Cout; co += gridDim.y) {
     for (int cp = blockIdx.x * blockDim.x + threadIdx.x; cp < cin_pad; cp += gridDim.x * blockDim.x) {
@@ -891,6 +895,7 @@ __global__ void __launch_bounds__(256)
     pack_deconv4x4s2_weight_kernel(const float* __restrict__ w, plane_t* __restrict__ whi, plane_t* __restrict__ wlo,
                                    int Cout, int Cin, int cin_pad, const int32_t* __restrict__ chan_map, int fmt,
                                    float w_scale) {
+  pdl_grid_sync();
   const long per_phase = (long)Cout * 4 * cin_pad;
   const long total = 4 * per_phase;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
@@ -1014,7 +1019,7 @@ static int launch_igemm(const CUtensorMap& tAh, const CUtensorMap& tAl, const CU
   const int num_sms = sm_count();
   const long items = (long)a.total_tiles * a.ksplit;
   const int grid = items < num_sms ? (int)items : num_sms;
-  conv_igemm_kernel<BN, SPLIT, MULTI, SPLITK><<<grid, kThreads, smem_bytes, stream>>>(tAh, tAl, tBh, tBl, a);
+  klaunch(conv_igemm_kernel<BN, SPLIT, MULTI, SPLITK>, grid, kThreads, smem_bytes, stream, tAh, tAl, tBh, tBl, a);
   return after_launch("conv_igemm_kernel");
 }
 
@@ -1224,7 +1229,7 @@ static int launch_im2col(const CUtensorMap& tBh, const CUtensorMap& tBl, ConvArg
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
   }
   const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
-  conv_im2col_igemm_kernel<BN, SPLIT><<<grid, kI2cThreads, stages * kStageBytes + 1024, stream>>>(tBh, tBl, a, src);
+  klaunch(conv_im2col_igemm_kernel<BN, SPLIT>, grid, kI2cThreads, stages * kStageBytes + 1024, stream, tBh, tBl, a, src);
   return after_launch("conv_im2col_igemm_kernel");
 }
 
@@ -1292,7 +1297,7 @@ extern "C" int shineon_conv2d_direct_fwd(const shineon_conv2d_params* p, shineon
   long total = (long)a.N * a.Ho * a.Wo * a.Cout;
   long blocks = (total + 127) / 128;
   if (blocks > 148 * 64) blocks = 148 * 64;
-  conv_direct_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(
+  klaunch(conv_direct_kernel, (int)blocks, 128, 0, (cudaStream_t)stream, 
       (const plane_t*)p->x_hi, (const plane_t*)p->x_lo, (const plane_t*)p->w_hi,
       (const plane_t*)p->w_lo, p->H, p->W, a);
   return after_launch("conv_direct_kernel");
@@ -1307,7 +1312,7 @@ extern "C" int shineon_pack_conv_weight(const float* w, void* w_hi, void* w_lo, 
   SHINEON_REQUIRE(Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && cin_pad >= 1, "pack_conv_weight: bad shape");
   SHINEON_REQUIRE(chan_map != nullptr || cin_pad >= Cin, "pack_conv_weight: cin_pad < Cin");
   const dim3 grid(cdiv(cin_pad, 128), Cout < 65535 ? Cout : 65535);
-  pack_conv_weight_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(w, (plane_t*)w_hi, (plane_t*)w_lo, Cout, Cin, kh, kw, cin_pad,
+  klaunch(pack_conv_weight_kernel, grid, 128, 0, (cudaStream_t)stream, w, (plane_t*)w_hi, (plane_t*)w_lo, Cout, Cin, kh, kw, cin_pad,
                                                                   chan_map, transpose_io, plane_fmt, w_scale);
   return after_launch("pack_conv_weight_kernel");
 }
@@ -1321,7 +1326,7 @@ extern "C" int shineon_pack_deconv4x4s2_weight(const float* w, void* w_hi, void*
   long total = 16l * Cout * cin_pad;
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  pack_deconv4x4s2_weight_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, (plane_t*)w_hi, (plane_t*)w_lo, Cout, Cin,
+  klaunch(pack_deconv4x4s2_weight_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, w, (plane_t*)w_hi, (plane_t*)w_lo, Cout, Cin,
                                                                               cin_pad, chan_map, plane_fmt, w_scale);
   return after_launch("pack_deconv4x4s2_weight_kernel");
 }

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
     conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl,
                       const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
                       const WgradArgs a) {
+  pdl_grid_sync();
   constexpr int kBBoxes = BN / 64;
   constexpr int kBBytes = kBBoxes * kWgBoxBytes;
   constexpr int kPlanes = SPLIT ? 2 : 1;
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(256)
     wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad, const int32_t* __restrict__ chan_map,
                         int splits, int Cout, int taps, int cin_pad, int Cin, int kh, int kw, int mode, float alpha,
                         float beta) {
+  pdl_grid_sync();
   const long split_stride = (long)Cout * taps * cin_pad;
   if (mode == 1) {  // im2col'd first layer: small, one element per thread
     const long total = (long)Cout * cin_pad;
@@ -284,6 +286,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     channel_sum_kernel(const float* __restrict__ x, double* __restrict__ acc, long pixels, int C, int cstride,
                        int pix_per_cta) {
+  pdl_grid_sync();
   // block: 32 channels x 8 pixel lanes
   __shared__ float s[8][33];
   const int c = blockIdx.y * 32 + (threadIdx.x & 31);
@@ -303,6 +306,7 @@ __global__ void __launch_bounds__(256)
 }
 __global__ void channel_sum_finish_kernel(const double* __restrict__ acc, float* __restrict__ grad, int C, float alpha,
                                           float beta) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) grad[c] = beta == 0.f ? alpha * (float)acc[c] : fmaf(beta, grad[c], alpha * (float)acc[c]);
 }
@@ -354,7 +358,7 @@ static int launch_wgrad(const CUtensorMap& tGh, const CUtensorMap& tGl, const CU
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
   }
   const int grid = a.total_items < num_sms ? a.total_items : num_sms;
-  conv_wgrad_kernel<BN, SPLIT><<<grid, kWgThreads, stages * kStageBytes + 1024, stream>>>(tGh, tGl, tXh, tXl, a);
+  klaunch(conv_wgrad_kernel<BN, SPLIT>, grid, kWgThreads, stages * kStageBytes + 1024, stream, tGh, tGl, tXh, tXl, a);
   return after_launch("conv_wgrad_kernel");
 }
 
@@ -467,7 +471,7 @@ extern "C" int shineon_conv2d_wgrad(const shineon_conv2d_wgrad_params* p, shineo
     const long total_e = (long)p->Cout * p->cin_pad;
     long blocks = (total_e + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    wgrad_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(a.ws, p->grad_w, p->chan_map, a.splits, p->Cout, a.taps, p->cin_pad,
+    klaunch(wgrad_reduce_kernel, (int)blocks, 256, 0, stream, a.ws, p->grad_w, p->chan_map, a.splits, p->Cout, a.taps, p->cin_pad,
                                                          p->Cin, p->kh, p->kw, p->mode, p->alpha == 0.f ? 1.f : p->alpha, p->beta);
     return after_launch("wgrad_reduce_kernel");
   }
@@ -483,9 +487,9 @@ extern "C" int shineon_channel_sum(const float* x, float* grad, void* workspace,
   if (ctas > 148 * 4) ctas = 148 * 4;
   const int per = (int)((pixels + ctas - 1) / ctas);
   ctas = (int)((pixels + per - 1) / per);
-  channel_sum_kernel<<<dim3(ctas, cdiv(C, 32)), 256, 0, stream>>>(x, (double*)workspace, pixels, C, cstride, per);
+  klaunch(channel_sum_kernel, dim3(ctas, cdiv(C, 32)), 256, 0, stream, x, (double*)workspace, pixels, C, cstride, per);
   int rc = after_launch("channel_sum_kernel");
   if (rc) return rc;
-  channel_sum_finish_kernel<<<cdiv(C, 128), 128, 0, stream>>>((const double*)workspace, grad, C, alpha == 0.f ? 1.f : alpha, beta);
+  klaunch(channel_sum_finish_kernel, cdiv(C, 128), 128, 0, stream, (const double*)workspace, grad, C, alpha == 0.f ? 1.f : alpha, beta);
   return after_launch("channel_sum_finish_kernel");
 }

@@ -35,6 +35,7 @@ static inline bool corr_geom(int C, int H, int W, int pad, int k, int maxd, int 
 __global__ void __launch_bounds__(256)
     correlation_fwd_kernel(const float* __restrict__ in1, const float* __restrict__ in2, float* __restrict__ out,
                            CorrGeom g) {
+  pdl_grid_sync();
   const int n = blockIdx.z, oy = blockIdx.y;
   const long HW = (long)g.H * g.W;
   const float* a = in1 + (long)n * g.C * HW;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     correlation_gather_kernel(const float* __restrict__ full, float* __restrict__ out, int C, int H, int W, int shift,
                               int drad, int s2, long total) {
+  pdl_grid_sync();
   const int D = 2 * drad + 1, P = H * W;
   const float inv = 1.f / (float)C;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(256)
     correlation_bwd_kernel(const float* __restrict__ in1, const float* __restrict__ in2,
                            const float* __restrict__ gout, float* __restrict__ gin1, float* __restrict__ gin2,
                            CorrGeom g, long total) {
+  pdl_grid_sync();
   const long HW = (long)g.H * g.W;
   const float nelems = (float)(g.k * g.k * g.C);
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
@@ -174,7 +177,7 @@ extern "C" int shineon_correlation_fwd(const float* in1, const float* in2, float
   SHINEON_REQUIRE(B >= 0 && B <= 65535 && g.outH <= 65535, "correlation_fwd: bad batch");
   if (B == 0) return SHINEON_OK;
   dim3 grid(g.D, g.outH, B);
-  correlation_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in1, in2, out, g);
+  klaunch(correlation_fwd_kernel, grid, 256, 0, (cudaStream_t)stream, in1, in2, out, g);
   return after_launch("correlation_fwd_kernel");
 }
 
@@ -189,7 +192,7 @@ extern "C" int shineon_correlation_gather(const float* full, float* out, int B, 
   if (total == 0) return SHINEON_OK;
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  correlation_gather_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(full, out, C, H, W, max_displacement - pad_size,
+  klaunch(correlation_gather_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, full, out, C, H, W, max_displacement - pad_size,
                                                                           g.drad, stride2, total);
   return after_launch("correlation_gather_kernel");
 }
@@ -205,6 +208,6 @@ extern "C" int shineon_correlation_bwd(const float* in1, const float* in2, const
   if (total == 0) return SHINEON_OK;
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  correlation_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in1, in2, grad_out, grad_in1, grad_in2, g, total);
+  klaunch(correlation_bwd_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, in1, in2, grad_out, grad_in1, grad_in2, g, total);
   return after_launch("correlation_bwd_kernel");
 }

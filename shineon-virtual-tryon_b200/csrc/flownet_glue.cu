@@ -36,6 +36,7 @@ __device__ __forceinline__ float warp_sample(const float* __restrict__ pl, const
 // ---- rgb mean over (frame, H, W) per (b, c)  (models.py:128)
 __global__ void __launch_bounds__(256)
     flownet_mean_kernel(const float* __restrict__ in, double* __restrict__ ws, long per_bc) {
+  pdl_grid_sync();
   const int bc = blockIdx.y;
   const float* p = in + (long)bc * per_bc;
   float s = 0.f;
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     flownet_normalize_kernel(const float* __restrict__ in, const double* __restrict__ ws, float* __restrict__ x, int HW,
                              float rgb_max, long total) {
+  pdl_grid_sync();
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const int p = (int)(e % HW);
     const int ch = (int)((e / HW) % 6);
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     upsample4x_flow_kernel(const float* __restrict__ src, int cs, float* __restrict__ dst, int h, int w, float mul,
                            int bilinear, long total) {
+  pdl_grid_sync();
   const int H = 4 * h, W = 4 * w;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const int ox = (int)(e % W), oy = (int)((e / W) % H);
@@ -94,6 +97,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     flownet_warp_concat_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out,
                                int H, int W, float div_flow) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int HW = H * W;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     flownet_fusion_concat_kernel(const float* __restrict__ x, const float* __restrict__ fsd, const float* __restrict__ fs2,
                                  float* __restrict__ out, int H, int W) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int HW = H * W;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
@@ -154,6 +159,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     flow_confidence_kernel(const float* __restrict__ im1, const float* __restrict__ im2, const float* __restrict__ flow,
                            float* __restrict__ conf, int C, int H, int W, float thr) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int HW = H * W;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
@@ -174,6 +180,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     bilinear_resize_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi, int Wi, int Ho, int Wo, float sy,
                            float sx, float mul, long total) {
+  pdl_grid_sync();
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const int ox = (int)(e % Wo), oy = (int)((e / Wo) % Ho);
     const long bc = e / ((long)Wo * Ho);
@@ -207,11 +214,11 @@ extern "C" int shineon_flownet_normalize(const float* inputs, float* x, double* 
   cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 3 * (size_t)B, stream);
   if (e != cudaSuccess) return fail(SHINEON_ERR_CUDA, "flownet_normalize memset: %s", cudaGetErrorString(e));
   const long per_bc = 2l * H * W;
-  flownet_mean_kernel<<<dim3(blocks_for(per_bc) > 64 ? 64 : blocks_for(per_bc), B * 3), 256, 0, stream>>>(inputs, ws, per_bc);
+  klaunch(flownet_mean_kernel, dim3(blocks_for(per_bc) > 64 ? 64 : blocks_for(per_bc), B * 3), 256, 0, stream, inputs, ws, per_bc);
   int rc = after_launch("flownet_mean_kernel");
   if (rc) return rc;
   const long total = (long)B * 6 * H * W;
-  flownet_normalize_kernel<<<blocks_for(total), 256, 0, stream>>>(inputs, ws, x, H * W, rgb_max, total);
+  klaunch(flownet_normalize_kernel, blocks_for(total), 256, 0, stream, inputs, ws, x, H * W, rgb_max, total);
   return after_launch("flownet_normalize_kernel");
 }
 
@@ -220,7 +227,7 @@ extern "C" int shineon_upsample4x_flow(const float* src, int src_cstride, float*
   SHINEON_REQUIRE(src && dst && src_cstride >= 2, "upsample4x_flow: bad argument");
   SHINEON_REQUIRE(B > 0 && h > 0 && w > 0, "upsample4x_flow: bad shape");
   const long total = (long)B * 2 * 16 * h * w;
-  upsample4x_flow_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(src, src_cstride, dst, h, w, mul, bilinear, total);
+  klaunch(upsample4x_flow_kernel, blocks_for(total), 256, 0, (cudaStream_t)stream, src, src_cstride, dst, h, w, mul, bilinear, total);
   return after_launch("upsample4x_flow_kernel");
 }
 
@@ -228,7 +235,7 @@ extern "C" int shineon_flownet_warp_concat(const float* x, const float* flow, fl
                                            float div_flow, shineon_stream_t stream) {
   SHINEON_REQUIRE(x && flow && out && div_flow != 0.f, "flownet_warp_concat: bad argument");
   SHINEON_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "flownet_warp_concat: bad shape");
-  flownet_warp_concat_kernel<<<dim3(blocks_for((long)H * W), B), 256, 0, (cudaStream_t)stream>>>(x, flow, out, H, W, div_flow);
+  klaunch(flownet_warp_concat_kernel, dim3(blocks_for((long)H * W), B), 256, 0, (cudaStream_t)stream, x, flow, out, H, W, div_flow);
   return after_launch("flownet_warp_concat_kernel");
 }
 
@@ -236,7 +243,7 @@ extern "C" int shineon_flownet_fusion_concat(const float* x, const float* flow_s
                                              int H, int W, shineon_stream_t stream) {
   SHINEON_REQUIRE(x && flow_sd && flow_s2 && out, "flownet_fusion_concat: null pointer");
   SHINEON_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "flownet_fusion_concat: bad shape");
-  flownet_fusion_concat_kernel<<<dim3(blocks_for((long)H * W), B), 256, 0, (cudaStream_t)stream>>>(x, flow_sd, flow_s2, out, H, W);
+  klaunch(flownet_fusion_concat_kernel, dim3(blocks_for((long)H * W), B), 256, 0, (cudaStream_t)stream, x, flow_sd, flow_s2, out, H, W);
   return after_launch("flownet_fusion_concat_kernel");
 }
 
@@ -244,7 +251,7 @@ extern "C" int shineon_flow_confidence(const float* im1, const float* im2, const
                                        int H, int W, float threshold, shineon_stream_t stream) {
   SHINEON_REQUIRE(im1 && im2 && flow && conf, "flow_confidence: null pointer");
   SHINEON_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "flow_confidence: bad shape");
-  flow_confidence_kernel<<<dim3(blocks_for((long)H * W), B), 256, 0, (cudaStream_t)stream>>>(im1, im2, flow, conf, C, H, W, threshold);
+  klaunch(flow_confidence_kernel, dim3(blocks_for((long)H * W), B), 256, 0, (cudaStream_t)stream, im1, im2, flow, conf, C, H, W, threshold);
   return after_launch("flow_confidence_kernel");
 }
 
@@ -253,7 +260,7 @@ extern "C" int shineon_bilinear_resize(const float* x, float* y, int BC, int Hi,
   SHINEON_REQUIRE(x && y, "bilinear_resize: null pointer");
   SHINEON_REQUIRE(BC > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bilinear_resize: bad shape");
   const long total = (long)BC * Ho * Wo;
-  bilinear_resize_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(x, y, Hi, Wi, Ho, Wo, (float)Hi / (float)Ho,
+  klaunch(bilinear_resize_kernel, blocks_for(total), 256, 0, (cudaStream_t)stream, x, y, Hi, Wi, Ho, Wo, (float)Hi / (float)Ho,
                                                                             (float)Wi / (float)Wo, mul, total);
   return after_launch("bilinear_resize_kernel");
 }

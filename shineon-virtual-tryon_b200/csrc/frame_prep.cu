@@ -43,6 +43,7 @@ struct PrepArgs {
 
 // 4 consecutive pixels per thread: 12-byte (3 x uchar4) reads of the interleaved images, float4 stores per channel plane
 __global__ void __launch_bounds__(256) frame_prep_pointwise_kernel(const PrepArgs a) {
+  pdl_grid_sync();
   const int f = blockIdx.y;
   const int p0 = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (p0 >= a.HW) return;
@@ -122,6 +123,7 @@ struct ResizeTab {
 __global__ void __launch_bounds__(1024)
     body_silhouette_kernel(const uint8_t* __restrict__ parse, float* __restrict__ out, long out_frame_stride,
                            uint8_t* __restrict__ out_u8, int H, int W, ResizeTab dw, ResizeTab dh, ResizeTab uw, ResizeTab uh) {
+  pdl_grid_sync();
   extern __shared__ uint8_t sm[];
   const int w16 = W / 16, h16 = H / 16;
   uint8_t* tA = sm;                 // [H][w16]   after the horizontal down pass
@@ -188,6 +190,7 @@ constexpr int kPrepPx = 32;
 // a byte has 256 possible results: a shared table (hi/lo halves precomputed) replaces two IEEE divisions and a split per use.
 template <int CG, int CU, int CC>
 __global__ void __launch_bounds__(256) frame_prep_planes_kernel(const PrepPlanesArgs a) {
+  pdl_grid_sync();
   constexpr int ROW = CG + CU + CC;  // halfwords per pixel and half (hi or lo)
   extern __shared__ __align__(16) plane_t sm_rows[];
   __shared__ uint32_t s_lut[256];   // hi | lo << 16 of norm_u8(b)
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(256) frame_prep_planes_kernel(const PrepPlanes
 // im_cocopose: union of the filled squares ImageDraw.rectangle((x-r, y-r, x+r, y+r)) draws for joints with x > 1, y > 1
 __global__ void __launch_bounds__(256)
     cocopose_vis_kernel(const double* __restrict__ pose, float* __restrict__ out, int H, int W, int J, int radius) {
+  pdl_grid_sync();
   __shared__ int box[64][4];
   const int f = blockIdx.y;
   for (int j = threadIdx.x; j < J; j += 256) {
@@ -297,6 +301,7 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     flo_decode_kernel(const float* __restrict__ uv, float* __restrict__ out, long hw) {
+  pdl_grid_sync();
   const long p = (long)blockIdx.x * 256 + threadIdx.x;
   if (p >= hw) return;
   const float u = __ldg(uv + 2 * p), v = __ldg(uv + 2 * p + 1);  // the payload starts 12 bytes into the file: 4-byte aligned only
@@ -367,7 +372,7 @@ extern "C" int shineon_frame_prep(const shineon_frame_prep_params* p, shineon_st
   a.image_out = p->image_out; a.cloth_out = p->cloth_out; a.cloth_mask_out = p->cloth_mask_out;
   a.densepose_out = p->densepose_out; a.agnostic_out = p->agnostic_out; a.cocopose_out = p->cocopose_out;
   a.HW = HW; a.J = p->n_joints; a.cloth_thr = p->cloth_mask_threshold;
-  frame_prep_pointwise_kernel<<<dim3(cdiv(HW / 4, 256), p->F), 256, 0, st>>>(a);
+  klaunch(frame_prep_pointwise_kernel, dim3(cdiv(HW / 4, 256), p->F), 256, 0, st, a);
   int rc = after_launch("frame_prep_pointwise_kernel");
   if (rc) return rc;
   if (p->agnostic_out) {
@@ -378,12 +383,12 @@ extern "C" int shineon_frame_prep(const shineon_frame_prep_params* p, shineon_st
     for (int i = 0; i < 4; ++i) t[i] = ResizeTab{p->tab_bounds[i], p->tab_kk[i], p->tab_ksize[i]};
     const size_t smem = (size_t)p->H * (p->W / 16) + (size_t)(p->H / 16) * (p->W / 16) + (size_t)(p->H / 16) * p->W;
     SHINEON_REQUIRE(smem <= 48 * 1024, "frame_prep: frame too large for the silhouette kernel");
-    body_silhouette_kernel<<<p->F, 1024, smem, st>>>(p->parse, p->agnostic_out, (long)4 * HW, nullptr, p->H, p->W, t[0], t[1], t[2], t[3]);
+    klaunch(body_silhouette_kernel, p->F, 1024, smem, st, p->parse, p->agnostic_out, (long)4 * HW, nullptr, p->H, p->W, t[0], t[1], t[2], t[3]);
     rc = after_launch("body_silhouette_kernel");
     if (rc) return rc;
   }
   if (p->im_cocopose_out) {
-    cocopose_vis_kernel<<<dim3(cdiv(HW, 256), p->F), 256, 0, st>>>(p->pose, p->im_cocopose_out, p->H, p->W, p->n_joints, p->radius);
+    klaunch(cocopose_vis_kernel, dim3(cdiv(HW, 256), p->F), 256, 0, st, p->pose, p->im_cocopose_out, p->H, p->W, p->n_joints, p->radius);
     rc = after_launch("cocopose_vis_kernel");
     if (rc) return rc;
   }
@@ -409,7 +414,7 @@ extern "C" int shineon_frame_prep_planes(const shineon_frame_prep_planes_params*
   for (int i = 0; i < 4; ++i) t[i] = ResizeTab{p->tab_bounds[i], p->tab_kk[i], p->tab_ksize[i]};
   const size_t smem_s = (size_t)p->H * (p->W / 16) + (size_t)(p->H / 16) * (p->W / 16) + (size_t)(p->H / 16) * p->W;
   SHINEON_REQUIRE(smem_s <= 48 * 1024, "frame_prep_planes: frame too large for the silhouette kernel");
-  body_silhouette_kernel<<<p->F, 1024, smem_s, st>>>(p->parse, nullptr, 0, p->silhouette_scratch, p->H, p->W, t[0], t[1], t[2], t[3]);
+  klaunch(body_silhouette_kernel, p->F, 1024, smem_s, st, p->parse, nullptr, 0, p->silhouette_scratch, p->H, p->W, t[0], t[1], t[2], t[3]);
   int rc = after_launch("body_silhouette_kernel");
   if (rc) return rc;
   PrepPlanesArgs a;
@@ -421,10 +426,10 @@ extern "C" int shineon_frame_prep_planes(const shineon_frame_prep_planes_params*
   // channel pads are compile-time: the recipe's (18 joints: 88 -> 128, 40 -> 64, 48 -> 64) and the joint-free variant
   if (p->gmm_cpad == 128 && p->unet_cpad == 64 && p->cloth_cpad == 64) {
     constexpr size_t smem = (size_t)2 * kPrepPx * (128 + 64 + 64) * sizeof(plane_t);
-    frame_prep_planes_kernel<128, 64, 64><<<grid, 256, smem, st>>>(a);
+    klaunch(frame_prep_planes_kernel<128, 64, 64>, grid, 256, smem, st, a);
   } else if (p->gmm_cpad == 64 && p->unet_cpad == 64 && p->cloth_cpad == 64) {
     constexpr size_t smem = (size_t)2 * kPrepPx * (64 + 64 + 64) * sizeof(plane_t);
-    frame_prep_planes_kernel<64, 64, 64><<<grid, 256, smem, st>>>(a);
+    klaunch(frame_prep_planes_kernel<64, 64, 64>, grid, 256, smem, st, a);
   } else {
     return fail(SHINEON_ERR_UNSUPPORTED, "frame_prep_planes: channel pads (%d, %d, %d) not compiled (128/64/64 and 64/64/64 are)",
                 p->gmm_cpad, p->unet_cpad, p->cloth_cpad);
@@ -436,6 +441,6 @@ extern "C" int shineon_flo_decode(const void* flo_payload, float* out, int H, in
   SHINEON_REQUIRE(flo_payload && out && H > 0 && W > 0, "flo_decode: bad arguments");
   SHINEON_REQUIRE((reinterpret_cast<uintptr_t>(flo_payload) & 3) == 0, "flo_decode: payload must be 4-byte aligned");
   const long hw = (long)H * W;
-  flo_decode_kernel<<<(unsigned)((hw + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)flo_payload, out, hw);
+  klaunch(flo_decode_kernel, (unsigned)((hw + 255) / 256), 256, 0, (cudaStream_t)stream, (const float*)flo_payload, out, hw);
   return after_launch("flo_decode_kernel");
 }

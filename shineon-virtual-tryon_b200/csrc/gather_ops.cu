@@ -173,6 +173,7 @@ __device__ __forceinline__ float sample_any(const float* __restrict__ plane, int
 
 __global__ void __launch_bounds__(256) tps_grid_kernel(const float* __restrict__ theta, TpsTablesDev t,
                                                        float* __restrict__ grid, int H, int W) {
+  pdl_grid_sync();
   __shared__ float sQ[2 * kMaxTpsN], sW[2 * kMaxTpsN], sP[2 * kMaxTpsN], sA[6];
   const int b = blockIdx.y;
   const int N = t.gs * t.gs;
@@ -191,6 +192,7 @@ constexpr int kPPT = 4;  // pixels per thread: independent load chains in flight
 __global__ void __launch_bounds__(256)
     grid_sample_kernel(const float* __restrict__ in, const float* __restrict__ grid, float* __restrict__ out,
                        int C, int Hin, int Win, int Hout, int Wout, int padding_mode) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int HWo = Hout * Wout;
   const int HWi = Hin * Win;
@@ -228,6 +230,7 @@ struct FusedSampleArgs {
 __global__ void __launch_bounds__(256)
     tps_grid_sample_kernel(const float* __restrict__ theta, TpsTablesDev t, FusedSampleArgs a,
                            float* __restrict__ grid_out, int H, int W) {
+  pdl_grid_sync();
   __shared__ float sQ[2 * kMaxTpsN], sW[2 * kMaxTpsN], sP[2 * kMaxTpsN], sA[6];
   const int b = blockIdx.y;
   const int N = t.gs * t.gs;
@@ -259,6 +262,7 @@ template <int N>
 __global__ void __launch_bounds__(256)
     tps_grid_sample_batched_kernel(const float* __restrict__ theta, TpsTablesDev t, FusedSampleArgs a,
                                    float* __restrict__ grid_out, int B, int H, int W, int chunk) {
+  pdl_grid_sync();
   __shared__ float sQ[kTpsChunk][2 * N];
   __shared__ float2 sWxy[kTpsChunk][N];  // (W_X[n], W_Y[n])
   __shared__ float sA[kTpsChunk][6];
@@ -410,6 +414,7 @@ template <int C, int PAD, int PPT>
 __global__ void __launch_bounds__(256)
     grid_sample_fast_kernel(const float* __restrict__ in, const float* __restrict__ grid, float* __restrict__ out,
                             int Hin, int Win, int HWo) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int HWi = Hin * Win;
   const int p0 = blockIdx.x * (256 * PPT) + threadIdx.x;
@@ -440,6 +445,7 @@ template <int C, int PPT>
 __global__ void __launch_bounds__(256)
     resample2d_fast_kernel(const float* __restrict__ in1, const float* __restrict__ flow, float* __restrict__ out,
                            int H, int W) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int HW = H * W;
   const int p0 = blockIdx.x * (256 * PPT) + threadIdx.x;
@@ -494,6 +500,7 @@ template <int N, int C0, int P0, int C1, int P1, int C2, int P2>
 __global__ void __launch_bounds__(128)
     tps_grid_sample_fast_kernel(const float* __restrict__ theta, TpsTablesDev t, FusedSampleArgs a,
                                 float* __restrict__ grid_out, int B, int H, int W, int chunk) {
+  pdl_grid_sync();
   __shared__ float sQ[kTpsChunk][2 * N];
   __shared__ float2 sWxy[kTpsChunk][N];
   __shared__ float sA[kTpsChunk][6];
@@ -621,6 +628,7 @@ __global__ void __launch_bounds__(128)
     tps_warp_u8_planes_kernel(const float* __restrict__ theta, TpsTablesDev t, const uint8_t* __restrict__ cloth,
                               float* __restrict__ out, plane_t* __restrict__ zh, plane_t* __restrict__ zl, int zc, int ctot,
                               int c_off, int fmt, int B, int H, int W, int chunk) {
+  pdl_grid_sync();
   __shared__ float sQ[kTpsChunk][2 * N];
   __shared__ float2 sWxy[kTpsChunk][N];
   __shared__ float sA[kTpsChunk][6];
@@ -733,6 +741,7 @@ __global__ void __launch_bounds__(128)
 __global__ void __launch_bounds__(256)
     resample2d_fwd_kernel(const float* __restrict__ in1, const float* __restrict__ flow,
                           float* __restrict__ out, int C, int H, int W, int bilinear) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int HW = H * W;
   const int p0 = blockIdx.x * (256 * kPPT) + threadIdx.x;
@@ -797,6 +806,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     resample2d_bwd_in1_kernel(const float* __restrict__ flow, const float* __restrict__ gout,
                               float* __restrict__ gin1, int C, int H, int W) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int HW = H * W;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
@@ -824,6 +834,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     resample2d_bwd_flow_kernel(const float* __restrict__ in1, const float* __restrict__ flow,
                                const float* __restrict__ gout, float* __restrict__ gflow, int C, int H, int W) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int HW = H * W;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
@@ -862,6 +873,7 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     channelnorm_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW) {
+  pdl_grid_sync();
   // grid.y = image; each thread owns 4 consecutive pixels (float4 per channel plane) when HW % 4 == 0
   const int b = blockIdx.y;
   const float* ib = in + (long)b * C * HW;
@@ -891,6 +903,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     channelnorm_bwd_kernel(const float* __restrict__ in, const float* __restrict__ out,
                            const float* __restrict__ gout, float* __restrict__ gin, int C, long HW, long total) {
+  pdl_grid_sync();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long b = i / (C * HW), p = i % HW;
     long o = b * HW + p;
@@ -929,12 +942,12 @@ extern "C" int shineon_tps_grid_fwd(const float* theta, const shineon_tps_tables
     const int chunk = B >= 128 ? kTpsChunk : (B >= 32 ? 8 : 2);
     dim3 g(cdiv(H * W, 256), cdiv(B, chunk));
     if (N == 25)
-      tps_grid_sample_batched_kernel<25><<<g, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid, B, H, W, chunk);
+      klaunch(tps_grid_sample_batched_kernel<25>, g, 256, 0, (cudaStream_t)stream, theta, to_dev(tps), a, grid, B, H, W, chunk);
     else
-      tps_grid_sample_batched_kernel<9><<<g, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid, B, H, W, chunk);
+      klaunch(tps_grid_sample_batched_kernel<9>, g, 256, 0, (cudaStream_t)stream, theta, to_dev(tps), a, grid, B, H, W, chunk);
     return after_launch("tps_grid_sample_batched_kernel");
   }
-  tps_grid_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), grid, H, W);
+  klaunch(tps_grid_kernel, pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream, theta, to_dev(tps), grid, H, W);
   return after_launch("tps_grid_kernel");
 }
 
@@ -950,9 +963,9 @@ extern "C" int shineon_grid_sample_fwd(const float* input, const float* grid, fl
     cudaStream_t st = (cudaStream_t)stream;
 #define SHINEON_GS(C_)                                                                                                       \
   if (padding_mode == SHINEON_PAD_BORDER)                                                                                   \
-    grid_sample_fast_kernel<C_, SHINEON_PAD_BORDER, PPT><<<g, 256, 0, st>>>(input, grid, out, Hin, Win, Hout * Wout);       \
+    klaunch(grid_sample_fast_kernel<C_, SHINEON_PAD_BORDER, PPT>, g, 256, 0, st, input, grid, out, Hin, Win, Hout * Wout);       \
   else                                                                                                                      \
-    grid_sample_fast_kernel<C_, SHINEON_PAD_ZEROS, PPT><<<g, 256, 0, st>>>(input, grid, out, Hin, Win, Hout * Wout)
+    klaunch(grid_sample_fast_kernel<C_, SHINEON_PAD_ZEROS, PPT>, g, 256, 0, st, input, grid, out, Hin, Win, Hout * Wout)
     switch (C) {
       case 1: SHINEON_GS(1); break;
       case 2: SHINEON_GS(2); break;
@@ -962,7 +975,7 @@ extern "C" int shineon_grid_sample_fwd(const float* input, const float* grid, fl
 #undef SHINEON_GS
     return after_launch("grid_sample_fast_kernel");
   }
-  grid_sample_kernel<<<dim3(cdiv(Hout * Wout, 256 * kPPT), B), 256, 0, (cudaStream_t)stream>>>(input, grid, out, C, Hin, Win,
+  klaunch(grid_sample_kernel, dim3(cdiv(Hout * Wout, 256 * kPPT), B), 256, 0, (cudaStream_t)stream, input, grid, out, C, Hin, Win,
                                                                                               Hout, Wout, padding_mode);
   return after_launch("grid_sample_kernel");
 }
@@ -989,19 +1002,19 @@ extern "C" int shineon_tps_grid_sample_fwd(const float* theta, const shineon_tps
     constexpr int BD = SHINEON_PAD_BORDER, ZR = SHINEON_PAD_ZEROS;
     const bool i0 = in0 && C0 == 3 && pad0 == BD;
     if (i0 && !in1 && !in2) {
-      tps_grid_sample_fast_kernel<25, 3, BD, 0, 0, 0, 0><<<grid, 128, 0, st>>>(theta, to_dev(tps), a, grid_out, B, H, W, chunk);
+      klaunch(tps_grid_sample_fast_kernel<25, 3, BD, 0, 0, 0, 0>, grid, 128, 0, st, theta, to_dev(tps), a, grid_out, B, H, W, chunk);
       return after_launch("tps_grid_sample_fast_kernel");
     }
     if (i0 && in1 && C1 == 3 && pad1 == ZR && !in2) {  // cloth + an RGB "mask" / grid image
-      tps_grid_sample_fast_kernel<25, 3, BD, 3, ZR, 0, 0><<<grid, 128, 0, st>>>(theta, to_dev(tps), a, grid_out, B, H, W, chunk);
+      klaunch(tps_grid_sample_fast_kernel<25, 3, BD, 3, ZR, 0, 0>, grid, 128, 0, st, theta, to_dev(tps), a, grid_out, B, H, W, chunk);
       return after_launch("tps_grid_sample_fast_kernel");
     }
     if (i0 && in1 && C1 == 1 && pad1 == ZR && !in2) {
-      tps_grid_sample_fast_kernel<25, 3, BD, 1, ZR, 0, 0><<<grid, 128, 0, st>>>(theta, to_dev(tps), a, grid_out, B, H, W, chunk);
+      klaunch(tps_grid_sample_fast_kernel<25, 3, BD, 1, ZR, 0, 0>, grid, 128, 0, st, theta, to_dev(tps), a, grid_out, B, H, W, chunk);
       return after_launch("tps_grid_sample_fast_kernel");
     }
     if (i0 && in1 && C1 == 1 && pad1 == ZR && in2 && C2 == 3 && pad2 == ZR) {
-      tps_grid_sample_fast_kernel<25, 3, BD, 1, ZR, 3, ZR><<<grid, 128, 0, st>>>(theta, to_dev(tps), a, grid_out, B, H, W, chunk);
+      klaunch(tps_grid_sample_fast_kernel<25, 3, BD, 1, ZR, 3, ZR>, grid, 128, 0, st, theta, to_dev(tps), a, grid_out, B, H, W, chunk);
       return after_launch("tps_grid_sample_fast_kernel");
     }
   }
@@ -1009,12 +1022,12 @@ extern "C" int shineon_tps_grid_sample_fwd(const float* theta, const shineon_tps
     const int chunk = B >= 128 ? kTpsChunk : (B >= 32 ? 8 : 2);
     dim3 grid(cdiv(H * W, 256), cdiv(B, chunk));
     if (N == 25)
-      tps_grid_sample_batched_kernel<25><<<grid, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid_out, B, H, W, chunk);
+      klaunch(tps_grid_sample_batched_kernel<25>, grid, 256, 0, (cudaStream_t)stream, theta, to_dev(tps), a, grid_out, B, H, W, chunk);
     else
-      tps_grid_sample_batched_kernel<9><<<grid, 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid_out, B, H, W, chunk);
+      klaunch(tps_grid_sample_batched_kernel<9>, grid, 256, 0, (cudaStream_t)stream, theta, to_dev(tps), a, grid_out, B, H, W, chunk);
     return after_launch("tps_grid_sample_batched_kernel");
   }
-  tps_grid_sample_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(theta, to_dev(tps), a, grid_out, H, W);
+  klaunch(tps_grid_sample_kernel, pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream, theta, to_dev(tps), a, grid_out, H, W);
   return after_launch("tps_grid_sample_kernel");
 }
 
@@ -1036,14 +1049,14 @@ extern "C" int shineon_resample2d_fwd(const float* in1, const float* flow, float
     const dim3 g(cdiv(H * W, 256 * PPT), B);
     cudaStream_t st = (cudaStream_t)stream;
     switch (C) {
-      case 1: resample2d_fast_kernel<1, PPT><<<g, 256, 0, st>>>(in1, flow, out, H, W); break;
-      case 2: resample2d_fast_kernel<2, PPT><<<g, 256, 0, st>>>(in1, flow, out, H, W); break;
-      case 3: resample2d_fast_kernel<3, PPT><<<g, 256, 0, st>>>(in1, flow, out, H, W); break;
-      default: resample2d_fast_kernel<4, PPT><<<g, 256, 0, st>>>(in1, flow, out, H, W); break;
+      case 1: klaunch(resample2d_fast_kernel<1, PPT>, g, 256, 0, st, in1, flow, out, H, W); break;
+      case 2: klaunch(resample2d_fast_kernel<2, PPT>, g, 256, 0, st, in1, flow, out, H, W); break;
+      case 3: klaunch(resample2d_fast_kernel<3, PPT>, g, 256, 0, st, in1, flow, out, H, W); break;
+      default: klaunch(resample2d_fast_kernel<4, PPT>, g, 256, 0, st, in1, flow, out, H, W); break;
     }
     return after_launch("resample2d_fast_kernel");
   }
-  resample2d_fwd_kernel<<<dim3(cdiv(H * W, 256 * kPPT), B), 256, 0, (cudaStream_t)stream>>>(in1, flow, out, C, H, W, bilinear);
+  klaunch(resample2d_fwd_kernel, dim3(cdiv(H * W, 256 * kPPT), B), 256, 0, (cudaStream_t)stream, in1, flow, out, C, H, W, bilinear);
   return after_launch("resample2d_fwd_kernel");
 }
 
@@ -1056,10 +1069,10 @@ extern "C" int shineon_resample2d_bwd(const float* in1, const float* flow, const
   if (Hi != H || Wi != W) return fail(SHINEON_ERR_UNSUPPORTED, "resample2d: input %dx%d != flow %dx%d", Hi, Wi, H, W);
   (void)bilinear;  // the reference's backward ignores the flag too (resample2d_kernel.cu:76-198)
   if (B == 0) return SHINEON_OK;
-  resample2d_bwd_in1_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(flow, grad_out, grad_in1, C, H, W);
+  klaunch(resample2d_bwd_in1_kernel, pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream, flow, grad_out, grad_in1, C, H, W);
   int rc = after_launch("resample2d_bwd_in1_kernel");
   if (rc) return rc;
-  resample2d_bwd_flow_kernel<<<pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream>>>(in1, flow, grad_out, grad_flow, C, H, W);
+  klaunch(resample2d_bwd_flow_kernel, pixel_grid(H * W, B), 256, 0, (cudaStream_t)stream, in1, flow, grad_out, grad_flow, C, H, W);
   return after_launch("resample2d_bwd_flow_kernel");
 }
 
@@ -1072,7 +1085,7 @@ extern "C" int shineon_channelnorm_fwd(const float* in, float* out, int B, int C
   SHINEON_REQUIRE(B <= 65535, "channelnorm_fwd: batch too large");
   const int HW = H * W;
   dim3 grid((HW & 3) == 0 ? cdiv(HW / 4, 256) : min(cdiv(HW, 256), 4096), B);
-  channelnorm_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, HW);
+  klaunch(channelnorm_fwd_kernel, grid, 256, 0, (cudaStream_t)stream, in, out, C, HW);
   return after_launch("channelnorm_fwd_kernel");
 }
 
@@ -1084,7 +1097,7 @@ extern "C" int shineon_channelnorm_bwd(const float* in, const float* out, const 
   long total = (long)B * C * H * W;
   if (total == 0) return SHINEON_OK;
   int blocks = (int)((total + 255) / 256 > 65535 ? 65535 : (total + 255) / 256);
-  channelnorm_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, grad_out, grad_in, C, (long)H * W, total);
+  klaunch(channelnorm_bwd_kernel, blocks, 256, 0, (cudaStream_t)stream, in, out, grad_out, grad_in, C, (long)H * W, total);
   return after_launch("channelnorm_bwd_kernel");
 }
 
@@ -1102,10 +1115,10 @@ extern "C" int shineon_tps_warp_u8_planes(const float* theta, const shineon_tps_
   dim3 grid(cdiv(H * W, 256), cdiv(B, chunk));
   cudaStream_t st = (cudaStream_t)stream;
   if (N == 25)
-    tps_warp_u8_planes_kernel<25><<<grid, 128, 0, st>>>(theta, to_dev(tps), cloth_u8, warped, (plane_t*)z_hi, (plane_t*)z_lo,
+    klaunch(tps_warp_u8_planes_kernel<25>, grid, 128, 0, st, theta, to_dev(tps), cloth_u8, warped, (plane_t*)z_hi, (plane_t*)z_lo,
                                                          z_cstride, ctot, c_off, plane_fmt, B, H, W, chunk);
   else if (N == 9)
-    tps_warp_u8_planes_kernel<9><<<grid, 128, 0, st>>>(theta, to_dev(tps), cloth_u8, warped, (plane_t*)z_hi, (plane_t*)z_lo,
+    klaunch(tps_warp_u8_planes_kernel<9>, grid, 128, 0, st, theta, to_dev(tps), cloth_u8, warped, (plane_t*)z_hi, (plane_t*)z_lo,
                                                         z_cstride, ctot, c_off, plane_fmt, B, H, W, chunk);
   else
     return fail(SHINEON_ERR_UNSUPPORTED, "tps_warp_u8_planes: grid_size %d (3 and 5 are compiled)", tps->grid_size);

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(128)
     l2norm_corr_kernel(const float* __restrict__ fA, const float* __restrict__ fB, float* __restrict__ corr,
                        plane_t* __restrict__ yh, plane_t* __restrict__ yl, int h, int w, int C, int cpad, int fmt,
                        int normalize) {
+  pdl_grid_sync();
   __shared__ __align__(16) float sA[kTK][kTA + 4];
   __shared__ __align__(16) float sB[kTK][kTB + 4];
   const int P = h * w;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(256)
     l2norm_planes_kernel(const float* __restrict__ fA, const float* __restrict__ fB, plane_t* __restrict__ ah,
                          plane_t* __restrict__ al, plane_t* __restrict__ bh, plane_t* __restrict__ bl, int h, int w, int C,
                          int fmt, float scale) {
+  pdl_grid_sync();
   const int P = h * w;
   const int b = blockIdx.z, isA = blockIdx.y;
   const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -127,6 +129,7 @@ __global__ void __launch_bounds__(256)
 // One thread per pixel, channel planes read coalesced across the warp.
 __global__ void __launch_bounds__(128)
     feature_l2norm_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int p = blockIdx.x * 128 + threadIdx.x;
   if (p >= HW) return;
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(128)
 __global__ void __launch_bounds__(256)
     linear_tanh_kernel(const float* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
                        float* __restrict__ theta, int hw, int C, int out_dim) {
+  pdl_grid_sync();
   const int b = blockIdx.x;
   const int K = hw * C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -174,7 +178,7 @@ extern "C" int shineon_l2norm_correlation(const float* featA, const float* featB
   SHINEON_REQUIRE(!y_hi || cpad >= h * w, "l2norm_correlation: cpad < h*w");
   const int P = h * w;
   dim3 grid(cdiv(P, kTA), cdiv(P, kTB), B);
-  l2norm_corr_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(featA, featB, corr_f32, (plane_t*)y_hi,
+  klaunch(l2norm_corr_kernel, grid, 128, 0, (cudaStream_t)stream, featA, featB, corr_f32, (plane_t*)y_hi,
                                                            (plane_t*)y_lo, h, w, C, cpad, plane_fmt, normalize);
   return after_launch("l2norm_corr_kernel");
 }
@@ -182,7 +186,7 @@ extern "C" int shineon_l2norm_correlation(const float* featA, const float* featB
 extern "C" int shineon_feature_l2norm(const float* x, float* y, int B, int C, int H, int W, shineon_stream_t stream) {
   SHINEON_REQUIRE(x && y, "feature_l2norm: null pointer");
   SHINEON_REQUIRE(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "feature_l2norm: bad shape");
-  feature_l2norm_kernel<<<dim3(cdiv(H * W, 128), B), 128, 0, (cudaStream_t)stream>>>(x, y, C, H * W);
+  klaunch(feature_l2norm_kernel, dim3(cdiv(H * W, 128), B), 128, 0, (cudaStream_t)stream, x, y, C, H * W);
   return after_launch("feature_l2norm_kernel");
 }
 
@@ -190,7 +194,7 @@ extern "C" int shineon_linear_tanh(const float* x, const float* weight, const fl
                                    int w, int C, int out_dim, shineon_stream_t stream) {
   SHINEON_REQUIRE(x && weight && theta, "linear_tanh: null pointer");
   SHINEON_REQUIRE(B > 0 && h > 0 && w > 0 && C > 0 && out_dim > 0, "linear_tanh: bad shape");
-  linear_tanh_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, weight, bias, theta, h * w, C, out_dim);
+  klaunch(linear_tanh_kernel, B, 256, 0, (cudaStream_t)stream, x, weight, bias, theta, h * w, C, out_dim);
   return after_launch("linear_tanh_kernel");
 }
 
@@ -200,7 +204,7 @@ extern "C" int shineon_l2norm_planes(const float* featA, const float* featB, voi
   SHINEON_REQUIRE(featA && featB && a_hi && b_hi && (a_lo == nullptr) == (b_lo == nullptr), "l2norm_planes: null pointer");
   SHINEON_REQUIRE(B > 0 && B <= 65535 && h > 0 && w > 0 && C > 0 && C % 64 == 0, "l2norm_planes: bad shape (C %% 64)");
   SHINEON_REQUIRE(scale > 0.f, "l2norm_planes: scale");
-  l2norm_planes_kernel<<<dim3(cdiv(h * w, 8), 2, B), 256, 0, (cudaStream_t)stream>>>(featA, featB, (plane_t*)a_hi, (plane_t*)a_lo,
+  klaunch(l2norm_planes_kernel, dim3(cdiv(h * w, 8), 2, B), 256, 0, (cudaStream_t)stream, featA, featB, (plane_t*)a_hi, (plane_t*)a_lo,
                                                                                     (plane_t*)b_hi, (plane_t*)b_lo, h, w, C,
                                                                                     plane_fmt, scale);
   return after_launch("l2norm_planes_kernel");

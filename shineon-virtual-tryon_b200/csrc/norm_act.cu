@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256)
     nchw_to_planes_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                           plane_t* __restrict__ yh, plane_t* __restrict__ yl, int HW, int cpad,
                           int act, float act_param, int fmt) {
+  pdl_grid_sync();
   const int n = blockIdx.y;
   const int groups = (C0 + C1 + 7) / 8;
   const long total = (long)HW * groups;
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     planes_to_nchw_kernel(const plane_t* __restrict__ xh, const plane_t* __restrict__ xl, int cstride,
                           float* __restrict__ y, int HW, int C, int fmt) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(256)
     nchw_im2col_planes_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                               plane_t* __restrict__ yh, plane_t* __restrict__ yl, int H, int W, int kh, int kw,
                               int stride, int pad, int Ho, int Wo, int kpad, int act, float act_param) {
+  pdl_grid_sync();
   // grid: x = (pair of k-groups, output column) tiles, y = output row, z = image; output column fastest so
   // neighbouring threads read neighbouring input columns of the same NCHW channel plane.  Each thread produces 16
   // consecutive k (two 16-byte chunks per plane): 16 independent gathers in flight.
@@ -123,6 +126,7 @@ template <int FMT>
 __global__ void __launch_bounds__(256)
     nchw_s2d_planes_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1,
                            plane_t* __restrict__ yh, plane_t* __restrict__ yl, int H, int W, int cpad) {
+  pdl_grid_sync();
   const int n = blockIdx.z, Y = blockIdx.y;
   const int Wz = W / 2 + 1;
   const int groups = cpad >> 3;
@@ -165,6 +169,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     col2im3x3_kernel(const float* __restrict__ t, const float* __restrict__ bias, float* __restrict__ y, int H, int W,
                      int Cout, int tstride) {
+  pdl_grid_sync();
   const int n = blockIdx.y;
   const long total = (long)H * W * Cout;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
@@ -216,6 +221,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
     upconv3x3_gather_kernel(const float* __restrict__ t, const float* __restrict__ bias, float* __restrict__ y, int h,
                             int w, int Cout, int tstride, int gpb, int tile_w, int tiles_x) {
+  pdl_grid_sync();
   const int n = blockIdx.z;
   const int g = blockIdx.y * gpb + (int)threadIdx.x % gpb;
   const int pix = (int)threadIdx.x / gpb;
@@ -301,6 +307,7 @@ __global__ void __launch_bounds__(256)
 template <int CB>  // channels per CTA (power of two <= 32)
 __global__ void __launch_bounds__(256)
     instnorm_stats_kernel(const float* __restrict__ x, double* __restrict__ ws, int HW, int C, int pix_per_cta) {
+  pdl_grid_sync();
   constexpr int PP = 256 / CB;
   __shared__ float s_sum[256], s_sq[256];
   const int n = blockIdx.z;
@@ -339,6 +346,7 @@ __global__ void __launch_bounds__(256)
     instnorm_apply_kernel(const float* __restrict__ x, const double* __restrict__ ws, float* __restrict__ yf,
                           plane_t* __restrict__ yh, plane_t* __restrict__ yl, int HW, int C, int cpad,
                           float eps, int do_norm, int act_rt, float act_param) {
+  pdl_grid_sync();
   extern __shared__ float s_tab[];  // mean[C], rstd[C]
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -447,6 +455,7 @@ __global__ void __launch_bounds__(256)
                           const plane_t* __restrict__ s1h, const plane_t* __restrict__ s1l, int c1pad,
                           plane_t* __restrict__ yh, plane_t* __restrict__ yl, int H, int W, int act,
                           float act_param) {
+  pdl_grid_sync();
   const int n = blockIdx.z, bi = (int)blockIdx.y - 1;
   const int ctot = c0pad + c1pad;
   const int groups = ctot >> 3;
@@ -509,6 +518,7 @@ __device__ __forceinline__ uint8_t image_u8(float x) {
 template <int C>
 __global__ void __launch_bounds__(256)
     image_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int HW) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int p0 = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (p0 >= HW) return;
@@ -526,6 +536,7 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     image_to_u8_scalar_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int HW, int C) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   for (long e = (long)blockIdx.x * 256 + threadIdx.x; e < (long)HW * C; e += (long)gridDim.x * 256) {
     const int c = (int)(e % C);
@@ -543,6 +554,7 @@ __global__ void __launch_bounds__(256)
                        const float* __restrict__ warped_prev, float* __restrict__ p_rend, float* __restrict__ masks,
                        float* __restrict__ p_tryon, float* __restrict__ fmasks, uint8_t* __restrict__ tryon_u8, int HW,
                        int nf, int f, int flow_warp) {
+  pdl_grid_sync();
   constexpr int PX = VEC4 ? 4 : 1;
   const int b = blockIdx.y;
   for (int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX; p0 < HW; p0 += gridDim.x * blockDim.x * PX) {
@@ -629,7 +641,7 @@ extern "C" int shineon_nchw_to_planes(const float* x0, int C0, const float* x1, 
   SHINEON_REQUIRE(cpad % 8 == 0 && cpad >= C0 + C1, "nchw_to_planes: cpad %d too small / not a multiple of 8", cpad);
   const int HW = H * W;
   dim3 grid(grid_x((long)HW * ((C0 + C1 + 7) / 8), 256), N);
-  nchw_to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo,
+  klaunch(nchw_to_planes_kernel, grid, 256, 0, (cudaStream_t)stream, x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo,
                                                                HW, cpad, act, act_param, plane_fmt);
   return after_launch("nchw_to_planes_kernel");
 }
@@ -639,7 +651,7 @@ extern "C" int shineon_planes_to_nchw(const void* x_hi, const void* x_lo, int x_
   SHINEON_REQUIRE_FMT(plane_fmt, "planes_to_nchw");
   SHINEON_REQUIRE(x_hi && y && N > 0 && N <= 65535 && H > 0 && W > 0 && C > 0 && x_cstride >= C, "planes_to_nchw: bad argument");
   dim3 grid(cdiv(H * W, 32), cdiv(C, 32), N);
-  planes_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const plane_t*)x_hi, (const plane_t*)x_lo, x_cstride, y,
+  klaunch(planes_to_nchw_kernel, grid, 256, 0, (cudaStream_t)stream, (const plane_t*)x_hi, (const plane_t*)x_lo, x_cstride, y,
                                                                H * W, C, plane_fmt);
   return after_launch("planes_to_nchw_kernel");
 }
@@ -656,10 +668,10 @@ extern "C" int shineon_nchw_im2col_planes(const float* x0, int C0, const float* 
   SHINEON_REQUIRE(Ho <= 65535, "nchw_im2col_planes: Ho too large");
   dim3 grid(cdiv(Wo * (kpad / 16), 256), Ho, N);
   if (plane_fmt == SHINEON_FMT_FP16)
-    nchw_im2col_planes_kernel<SHINEON_FMT_FP16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    klaunch(nchw_im2col_planes_kernel<SHINEON_FMT_FP16>, grid, 256, 0, (cudaStream_t)stream, 
         x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, kh, kw, stride, pad, Ho, Wo, kpad, act, act_param);
   else
-    nchw_im2col_planes_kernel<SHINEON_FMT_BF16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    klaunch(nchw_im2col_planes_kernel<SHINEON_FMT_BF16>, grid, 256, 0, (cudaStream_t)stream, 
         x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, kh, kw, stride, pad, Ho, Wo, kpad, act, act_param);
   return after_launch("nchw_im2col_planes_kernel");
 }
@@ -672,9 +684,9 @@ extern "C" int shineon_nchw_s2d_planes(const float* x0, int C0, const float* x1,
   SHINEON_REQUIRE(cpad % 8 == 0 && cpad >= 4 * (C0 + C1), "nchw_s2d_planes: cpad %d too small / not a multiple of 8", cpad);
   dim3 grid(cdiv((W / 2 + 1) * (cpad / 8), 256), H / 2 + 1, N);
   if (plane_fmt == SHINEON_FMT_FP16)
-    nchw_s2d_planes_kernel<SHINEON_FMT_FP16><<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad);
+    klaunch(nchw_s2d_planes_kernel<SHINEON_FMT_FP16>, grid, 256, 0, (cudaStream_t)stream, x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad);
   else
-    nchw_s2d_planes_kernel<SHINEON_FMT_BF16><<<grid, 256, 0, (cudaStream_t)stream>>>(x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad);
+    klaunch(nchw_s2d_planes_kernel<SHINEON_FMT_BF16>, grid, 256, 0, (cudaStream_t)stream, x0, C0, x1, C1, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad);
   return after_launch("nchw_s2d_planes_kernel");
 }
 
@@ -683,7 +695,7 @@ extern "C" int shineon_col2im3x3(const float* t, const float* bias, float* y, in
   SHINEON_REQUIRE(t && y, "col2im3x3: null pointer");
   SHINEON_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && Cout > 0 && tstride >= 9 * Cout, "col2im3x3: bad shape");
   dim3 grid(grid_x((long)H * W * Cout, 256), N);
-  col2im3x3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, bias, y, H, W, Cout, tstride);
+  klaunch(col2im3x3_kernel, grid, 256, 0, (cudaStream_t)stream, t, bias, y, H, W, Cout, tstride);
   return after_launch("col2im3x3_kernel");
 }
 
@@ -719,9 +731,9 @@ static int upconv3x3_gather_direct(const float* t, const float* bias, float* y, 
   SHINEON_REQUIRE(cdiv(groups, gpb) <= 65535, "upconv3x3_gather: too many channels");
   dim3 grid(tiles_x * tiles_y, cdiv(groups, gpb), N);
   if (vec == 4)
-    upconv3x3_gather_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(t, bias, y, h, w, Cout, tstride, gpb, tile_w, tiles_x);
+    klaunch(upconv3x3_gather_kernel<4>, grid, 256, 0, (cudaStream_t)stream, t, bias, y, h, w, Cout, tstride, gpb, tile_w, tiles_x);
   else
-    upconv3x3_gather_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(t, bias, y, h, w, Cout, tstride, gpb, tile_w, tiles_x);
+    klaunch(upconv3x3_gather_kernel<1>, grid, 256, 0, (cudaStream_t)stream, t, bias, y, h, w, Cout, tstride, gpb, tile_w, tiles_x);
   return after_launch("upconv3x3_gather_kernel");
 }
 
@@ -734,12 +746,12 @@ int launch_instnorm_stats(const float* x, double* ws, int N, int HW, int C, cuda
   int pix_per_cta = pp * 16;
   dim3 grid(cdiv(HW, pix_per_cta), cdiv(C, cb), N);
   switch (cb) {
-    case 32: instnorm_stats_kernel<32><<<grid, 256, 0, stream>>>(x, ws, HW, C, pix_per_cta); break;
-    case 16: instnorm_stats_kernel<16><<<grid, 256, 0, stream>>>(x, ws, HW, C, pix_per_cta); break;
-    case 8: instnorm_stats_kernel<8><<<grid, 256, 0, stream>>>(x, ws, HW, C, pix_per_cta); break;
-    case 4: instnorm_stats_kernel<4><<<grid, 256, 0, stream>>>(x, ws, HW, C, pix_per_cta); break;
-    case 2: instnorm_stats_kernel<2><<<grid, 256, 0, stream>>>(x, ws, HW, C, pix_per_cta); break;
-    default: instnorm_stats_kernel<1><<<grid, 256, 0, stream>>>(x, ws, HW, C, pix_per_cta); break;
+    case 32: klaunch(instnorm_stats_kernel<32>, grid, 256, 0, stream, x, ws, HW, C, pix_per_cta); break;
+    case 16: klaunch(instnorm_stats_kernel<16>, grid, 256, 0, stream, x, ws, HW, C, pix_per_cta); break;
+    case 8: klaunch(instnorm_stats_kernel<8>, grid, 256, 0, stream, x, ws, HW, C, pix_per_cta); break;
+    case 4: klaunch(instnorm_stats_kernel<4>, grid, 256, 0, stream, x, ws, HW, C, pix_per_cta); break;
+    case 2: klaunch(instnorm_stats_kernel<2>, grid, 256, 0, stream, x, ws, HW, C, pix_per_cta); break;
+    default: klaunch(instnorm_stats_kernel<1>, grid, 256, 0, stream, x, ws, HW, C, pix_per_cta); break;
   }
   return after_launch("instnorm_stats_kernel");
 }
@@ -769,7 +781,7 @@ extern "C" int shineon_instnorm_act(const float* x, float* y_f32, void* y_hi, vo
   const size_t sm = 2 * C * sizeof(float);
   cudaStream_t st = stream;
 #define SHINEON_IN_APPLY(F, A, V)                                                                                   \
-  instnorm_apply_kernel<F, A, V><<<grid, 256, sm, st>>>(x, stats_ws, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, \
+  klaunch(instnorm_apply_kernel<F, A, V>, grid, 256, sm, st, x, stats_ws, y_f32, (plane_t*)y_hi, (plane_t*)y_lo, HW, C, \
                                                          cpad, eps, do_norm, act, act_param)
 #define SHINEON_IN_ACT(F, V)                                              \
   switch (act) {                                                          \
@@ -801,7 +813,7 @@ extern "C" int shineon_upsample2x_cat(const void* s0_hi, const void* s0_lo, int 
   SHINEON_REQUIRE(H + 1 <= 65535, "upsample2x_cat: H too large");
   dim3 grid(cdiv((W + 1) * ((c0pad + c1pad) / 8), 256), H + 1, N);
 #define SHINEON_UP(F, A)                                                                                              \
-  upsample2x_cat_kernel<F, A><<<grid, 256, 0, (cudaStream_t)stream>>>(                                               \
+  klaunch(upsample2x_cat_kernel<F, A>, grid, 256, 0, (cudaStream_t)stream,                                                \
       (const plane_t*)s0_hi, (const plane_t*)s0_lo, c0pad, (const plane_t*)s1_hi, (const plane_t*)s1_lo, c1pad,      \
       (plane_t*)y_hi, (plane_t*)y_lo, H, W, act, act_param)
   if (plane_fmt == SHINEON_FMT_FP16) {
@@ -832,11 +844,11 @@ extern "C" int shineon_tom_compose(const float* unet_out, int Cout, const float*
                     al16(p_tryons) && al16(flow_masks) && (reinterpret_cast<uintptr_t>(p_tryons_u8) & 3) == 0;
   if (vec4) {
     dim3 grid(grid_x((long)HW / 4, 256), B);
-    tom_compose_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(unet_out, Cout, cloth, warped_prev, p_rendereds, tryon_masks,
+    klaunch(tom_compose_kernel<true>, grid, 256, 0, (cudaStream_t)stream, unet_out, Cout, cloth, warped_prev, p_rendereds, tryon_masks,
                                                                    p_tryons, flow_masks, p_tryons_u8, HW, n_frames, frame, flow_warp);
   } else {
     dim3 grid(grid_x((long)HW, 256), B);
-    tom_compose_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(unet_out, Cout, cloth, warped_prev, p_rendereds, tryon_masks,
+    klaunch(tom_compose_kernel<false>, grid, 256, 0, (cudaStream_t)stream, unet_out, Cout, cloth, warped_prev, p_rendereds, tryon_masks,
                                                                     p_tryons, flow_masks, p_tryons_u8, HW, n_frames, frame, flow_warp);
   }
   return after_launch("tom_compose_kernel");
@@ -848,10 +860,10 @@ extern "C" int shineon_image_to_u8(const float* x, unsigned char* y, int B, int 
   const int HW = H * W;
   const bool vec = HW % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 3) == 0;
   if (vec && C == 3)
-    image_to_u8_kernel<3><<<dim3(cdiv(HW / 4, 256), B), 256, 0, (cudaStream_t)stream>>>(x, y, HW);
+    klaunch(image_to_u8_kernel<3>, dim3(cdiv(HW / 4, 256), B), 256, 0, (cudaStream_t)stream, x, y, HW);
   else if (vec && C == 1)
-    image_to_u8_kernel<1><<<dim3(cdiv(HW / 4, 256), B), 256, 0, (cudaStream_t)stream>>>(x, y, HW);
+    klaunch(image_to_u8_kernel<1>, dim3(cdiv(HW / 4, 256), B), 256, 0, (cudaStream_t)stream, x, y, HW);
   else
-    image_to_u8_scalar_kernel<<<dim3(grid_x((long)HW * C, 256), B), 256, 0, (cudaStream_t)stream>>>(x, y, HW, C);
+    klaunch(image_to_u8_scalar_kernel, dim3(grid_x((long)HW * C, 256), B), 256, 0, (cudaStream_t)stream, x, y, HW, C);
   return after_launch("image_to_u8_kernel");
 }

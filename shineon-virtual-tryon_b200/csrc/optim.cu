@@ -9,6 +9,7 @@ __global__ void __launch_bounds__(256)
     adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                      long n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
                      float grad_scale) {
+  pdl_grid_sync();
   const float step_size = lr / bc1;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     float grad = g[i] * grad_scale;
@@ -37,7 +38,7 @@ extern "C" int shineon_adam_step(float* param, const float* grad, float* exp_avg
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  adam_step_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+  klaunch(adam_step_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                  weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale);
   return after_launch("adam_step_kernel");
 }

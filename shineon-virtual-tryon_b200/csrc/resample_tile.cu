@@ -23,6 +23,7 @@ template <int C>
 __global__ void __launch_bounds__(256)
     resample2d_tile_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ in1,
                            const float* __restrict__ flow, float* __restrict__ out, int H, int W, int tiles_x) {
+  pdl_grid_sync();
   extern __shared__ __align__(128) float s_tile[];  // [C][kRsBH][kRsBW]
   __shared__ __align__(8) uint64_t bar;
   const int b = blockIdx.y;
@@ -123,7 +124,7 @@ int shineon_resample2d_tile(const float* in1, const float* flow, float* out, int
       e = cudaFuncSetAttribute(resample2d_tile_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      \
       opted = e == cudaSuccess;                                                                                     \
     }                                                                                                               \
-    if (e == cudaSuccess) resample2d_tile_kernel<CC><<<grid, 256, smem, stream>>>(tm, in1, flow, out, H, W, tiles_x); \
+    if (e == cudaSuccess) klaunch(resample2d_tile_kernel<CC>, grid, 256, smem, stream, tm, in1, flow, out, H, W, tiles_x); \
   }
   switch (C) {
     case 1: SHINEON_RS(1) break;

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256)
                           const float* __restrict__ nshift, const float* __restrict__ gb, int gb_cstride,
                           float* __restrict__ yf, int yf_cstride, plane_t* __restrict__ yh, plane_t* __restrict__ yl,
                           int HW, int C, int cpad, float eps, int norm_mode, int act, float act_param) {
+  pdl_grid_sync();
   extern __shared__ float s_tab[];  // a[C], b[C]: normalized = x * a + b
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -105,6 +106,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
     nearest_resize_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int Hs, int Ws, int H, int W, int C,
                                float scale_h, float scale_w, long total) {
+  pdl_grid_sync();
   const int cg = C / VEC;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
     const int g = (int)(e % cg);
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     nearest_resize_planes_kernel(const float* __restrict__ x, int C, int Hs, int Ws, plane_t* __restrict__ yh,
                                  plane_t* __restrict__ yl, int H, int W, int cpad, float scale_h, float scale_w, int fmt) {
+  pdl_grid_sync();
   const int n = blockIdx.y;
   const int groups = cpad >> 3;
   const long total = (long)H * W * groups;
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     nearest_im2col_planes_kernel(const float* __restrict__ x, int C, int Hs, int Ws, plane_t* __restrict__ yh,
                                  plane_t* __restrict__ yl, int H, int W, int ks, int kpad, float scale_h, float scale_w, int fmt) {
+  pdl_grid_sync();
   const int n = blockIdx.y;
   const int groups = kpad >> 3;
   const int pad = ks / 2, K = ks * ks * C;
@@ -187,6 +191,7 @@ __global__ void __launch_bounds__(256)
 
 // y may alias a or b (every element is read and written by the same thread): no __restrict__, no read-only loads
 __global__ void __launch_bounds__(256) add_nhwc_kernel(const float* a, const float* b, float* y, long n4, long n) {
+  pdl_grid_sync();
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long)gridDim.x * blockDim.x) {
     const float4 u = reinterpret_cast<const float4*>(a)[e], v = reinterpret_cast<const float4*>(b)[e];
     reinterpret_cast<float4*>(y)[e] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
@@ -200,6 +205,7 @@ __global__ void __launch_bounds__(256) add_nhwc_kernel(const float* a, const flo
 __global__ void __launch_bounds__(256)
     sams_flow_blend_kernel(const float* __restrict__ g, int Cg, const float* __restrict__ warped, float* __restrict__ out,
                            long out_bstride, int HW) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= HW) return;
@@ -224,7 +230,7 @@ extern "C" int shineon_sams_flow_blend(const float* gen_out, int Cg, const float
   SHINEON_REQUIRE(Cg == (warped_prev ? 4 : 3), "sams_flow_blend: generator output has %d channels, expected %d", Cg, warped_prev ? 4 : 3);
   SHINEON_REQUIRE(out_bstride >= 3l * H * W, "sams_flow_blend: out_bstride");
   dim3 grid(cdiv(H * W, 256), B);
-  sams_flow_blend_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gen_out, Cg, warped_prev, out, out_bstride, H * W);
+  klaunch(sams_flow_blend_kernel, grid, 256, 0, (cudaStream_t)stream, gen_out, Cg, warped_prev, out, out_bstride, H * W);
   return after_launch("sams_flow_blend_kernel");
 }
 
@@ -259,7 +265,7 @@ extern "C" int shineon_spade_modulate(const float* x, const double* stats_ws, co
   dim3 grid(grid_1d(HW * (C / vec), 256), N);
   const size_t sm = 2 * (size_t)C * sizeof(float);
 #define SHINEON_SPADE(F, V)                                                                                               \
-  spade_modulate_kernel<F, V><<<grid, 256, sm, (cudaStream_t)stream>>>(x, stats_ws, nscale, nshift, gb, gb_cstride, y_f32, \
+  klaunch(spade_modulate_kernel<F, V>, grid, 256, sm, (cudaStream_t)stream, x, stats_ws, nscale, nshift, gb, gb_cstride, y_f32, \
                                                                        y_cstride, (plane_t*)y_hi, (plane_t*)y_lo, (int)HW, C, \
                                                                        cpad, eps, norm_mode, act, act_param)
   if (plane_fmt == SHINEON_FMT_FP16) {
@@ -278,9 +284,9 @@ extern "C" int shineon_nearest_resize_nhwc(const float* x, float* y, int N, int 
   const bool v4 = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
   const long total = (long)N * H * W * (C / (v4 ? 4 : 1));
   if (v4)
-    nearest_resize_nhwc_kernel<4><<<grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, Hs, Ws, H, W, C, scale_h, scale_w, total);
+    klaunch(nearest_resize_nhwc_kernel<4>, grid_1d(total, 256), 256, 0, (cudaStream_t)stream, x, y, Hs, Ws, H, W, C, scale_h, scale_w, total);
   else
-    nearest_resize_nhwc_kernel<1><<<grid_1d(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, Hs, Ws, H, W, C, scale_h, scale_w, total);
+    klaunch(nearest_resize_nhwc_kernel<1>, grid_1d(total, 256), 256, 0, (cudaStream_t)stream, x, y, Hs, Ws, H, W, C, scale_h, scale_w, total);
   return after_launch("nearest_resize_nhwc_kernel");
 }
 
@@ -292,7 +298,7 @@ extern "C" int shineon_nearest_resize_planes(const float* x, int N, int C, int H
   SHINEON_REQUIRE(cpad % 8 == 0 && cpad >= C, "nearest_resize_planes: cpad %d too small / not a multiple of 8", cpad);
   SHINEON_REQUIRE(scale_h > 0.f && scale_w > 0.f, "nearest_resize_planes: bad scale");
   dim3 grid(grid_1d((long)H * W * (cpad >> 3), 256), N);
-  nearest_resize_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, C, Hs, Ws, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad,
+  klaunch(nearest_resize_planes_kernel, grid, 256, 0, (cudaStream_t)stream, x, C, Hs, Ws, (plane_t*)y_hi, (plane_t*)y_lo, H, W, cpad,
                                                                        scale_h, scale_w, plane_fmt);
   return after_launch("nearest_resize_planes_kernel");
 }
@@ -306,7 +312,7 @@ extern "C" int shineon_nearest_im2col_planes(const float* x, int N, int C, int H
   SHINEON_REQUIRE(kpad % 8 == 0 && kpad >= ks * ks * C, "nearest_im2col_planes: kpad %d too small / not a multiple of 8", kpad);
   SHINEON_REQUIRE(scale_h > 0.f && scale_w > 0.f, "nearest_im2col_planes: bad scale");
   dim3 grid(grid_1d((long)H * W * (kpad >> 3), 256), N);
-  nearest_im2col_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, C, Hs, Ws, (plane_t*)y_hi, (plane_t*)y_lo, H, W, ks, kpad,
+  klaunch(nearest_im2col_planes_kernel, grid, 256, 0, (cudaStream_t)stream, x, C, Hs, Ws, (plane_t*)y_hi, (plane_t*)y_lo, H, W, ks, kpad,
                                                                        scale_h, scale_w, plane_fmt);
   return after_launch("nearest_im2col_planes_kernel");
 }
@@ -315,6 +321,6 @@ extern "C" int shineon_add_nhwc(const float* a, const float* b, float* y, long n
   SHINEON_REQUIRE(a && b && y && n > 0, "add_nhwc: bad argument");
   const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
   const long n4 = al ? n / 4 : 0;
-  add_nhwc_kernel<<<grid_1d(n4 > 0 ? n4 : 1, 256), 256, 0, (cudaStream_t)stream>>>(a, b, y, n4, n);
+  klaunch(add_nhwc_kernel, grid_1d(n4 > 0 ? n4 : 1, 256), 256, 0, (cudaStream_t)stream, a, b, y, n4, n);
   return after_launch("add_nhwc_kernel");
 }

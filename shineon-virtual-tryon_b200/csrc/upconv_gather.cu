@@ -32,6 +32,7 @@ __host__ __device__ constexpr bool up3c_has(int f, int p, int a) { return (f + p
 __global__ void __launch_bounds__(256, 3)
     upconv3x3_gather_tma_kernel(const __grid_constant__ CUtensorMap tmV, const float* __restrict__ bias,
                                 float* __restrict__ y, double* __restrict__ stats, int h, int w, int Cout, int tiles_x) {
+  pdl_grid_sync();
   extern __shared__ __align__(128) float sv[];  // [9 taps][TH+2][TW+2][CB]
   __shared__ __align__(8) uint64_t bar;
   __shared__ float s_stat[8][kGatherCB][2];  // per warp: single writer per slot, summed in a fixed order (reproducible)
@@ -184,6 +185,6 @@ int shineon_upconv3x3_gather_tma(const float* t, const float* bias, float* y, do
   }
   const int tiles_x = cdiv(w, kGatherTW), tiles_y = cdiv(h, kGatherTH);
   dim3 grid(tiles_x * tiles_y, Cout / kGatherCB, N);
-  upconv3x3_gather_tma_kernel<<<grid, 256, kGatherSmemBytes, stream>>>(tm, bias, y, stats_ws, h, w, Cout, tiles_x);
+  klaunch(upconv3x3_gather_tma_kernel, grid, 256, kGatherSmemBytes, stream, tm, bias, y, stats_ws, h, w, Cout, tiles_x);
   return after_launch("upconv3x3_gather_tma_kernel");
 }

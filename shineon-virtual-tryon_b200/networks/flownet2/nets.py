@@ -8,6 +8,8 @@ never happen — producers write straight into 64-aligned channel windows of one
 packed weights follow that layout; the small-Cin stems (3/6/11/12 channels, up to 7x7) use the im2col'd 1x1 GEMM;
 the warps / norms / concats between sub-networks are the fused kernels of csrc/flownet_glue.cu.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -81,6 +83,19 @@ class _Concat:
 
 class _Net(nn.Module):
     """Packed-weight cache shared by the four sub-networks."""
+
+    def _concat(self, N, H, W, seg_channels, prec, device):
+        """Concat buffers are kept per (shape, precision): every forward's producers overwrite all real channels of
+        their windows and nothing ever writes the padding channels, so the zero fill happens once per buffer instead
+        of once per forward (it was 78 fill launches = 5 % of a batch-16 FlowNet2 forward)."""
+        cache = self.__dict__.setdefault("_cat_cache", {})
+        key = (N, H, W, tuple(seg_channels), prec, str(device))
+        cat = cache.get(key)
+        if cat is None:
+            if len(cache) >= 16:  # a new batch size / resolution: drop the old set
+                cache.clear()
+            cat = cache[key] = _Concat(N, H, W, seg_channels, prec, device)
+        return cat
 
     def _packs(self, prec):
         sig = (params_signature(self), prec)
@@ -206,13 +221,13 @@ class FlowNetC(_Net):
         """x: f32 NCHW [B,6,H,W] -> flow2 f32 NHWC [B,H/4,W/4,2] (FlowNetC.py:71-128, eval)."""
         B, _, H, W = x.shape
         dev = x.device
-        mk = lambda k, segs: _Concat(B, H // k, W // k, segs, prec, dev)
+        mk = lambda k, segs: self._concat(B, H // k, W // k, segs, prec, dev)
         cat5, cat4, cat3, cat2 = mk(32, (512, 512, 2)), mk(16, (512, 256, 2)), mk(8, (256, 128, 2)), mk(4, (128, 64, 2))
         x1, x2 = x[:, 0:3].contiguous(), x[:, 3:].contiguous()
         c2a = self._c(prec, "conv2", self._stem(prec, "conv1", x1), out=cat2.window(0))
         c3a = self._c(prec, "conv3", c2a)
         c3b = self._c(prec, "conv3", self._c(prec, "conv2", self._stem(prec, "conv1", x2)))
-        in31 = _Concat(B, H // 8, W // 8, (32, 441), prec, dev)
+        in31 = self._concat(B, H // 8, W // 8, (32, 441), prec, dev)
         corr = ops.correlation_planes(c3a, c3b, 256, 20, 20, 2)  # tensor-core cost volume straight from the planes
         ops.nchw_to_planes(corr, act="leaky", act_param=LEAK, out=in31.window(1))  # corr_activation
         self._c(prec, "conv_redir", c3a, out=in31.window(0))
@@ -257,7 +272,7 @@ class FlowNetS(_Net):
         """x: f32 NCHW [B,12,H,W] -> flow2 f32 NHWC [B,H/4,W/4,2] (FlowNetS.py:60-94, eval)."""
         B, _, H, W = x.shape
         dev = x.device
-        mk = lambda k, segs: _Concat(B, H // k, W // k, segs, prec, dev)
+        mk = lambda k, segs: self._concat(B, H // k, W // k, segs, prec, dev)
         cat5, cat4, cat3, cat2 = mk(32, (512, 512, 2)), mk(16, (512, 256, 2)), mk(8, (256, 128, 2)), mk(4, (128, 64, 2))
         c2 = self._c(prec, "conv2", self._stem(prec, "conv1", x), out=cat2.window(0))
         c3 = self._c(prec, "conv3_1", self._c(prec, "conv3", c2), out=cat3.window(0))
@@ -308,7 +323,7 @@ class FlowNetSD(_Net):
         """x: f32 NCHW [B,6,H,W] -> flow2 f32 NHWC [B,H/4,W/4,2] (FlowNetSD.py:66-106, eval)."""
         B, _, H, W = x.shape
         dev = x.device
-        mk = lambda k, segs: _Concat(B, H // k, W // k, segs, prec, dev)
+        mk = lambda k, segs: self._concat(B, H // k, W // k, segs, prec, dev)
         cat5, cat4, cat3, cat2 = mk(32, (512, 512, 2)), mk(16, (512, 256, 2)), mk(8, (256, 128, 2)), mk(4, (128, 64, 2))
         c0 = self._stem(prec, "conv0", x)
         c1 = self._c(prec, "conv1_1", self._c(prec, "conv1", c0))
@@ -352,8 +367,8 @@ class FlowNetFusion(_Net):
         """x: f32 NCHW [B,11,H,W] -> flow0 f32 NHWC [B,H,W,2] (FlowNetFusion.py:47-67)."""
         B, _, H, W = x.shape
         dev = x.device
-        cat1 = _Concat(B, H // 2, W // 2, (128, 32, 2), prec, dev)
-        cat0 = _Concat(B, H, W, (64, 16, 2), prec, dev)
+        cat1 = self._concat(B, H // 2, W // 2, (128, 32, 2), prec, dev)
+        cat0 = self._concat(B, H, W, (64, 16, 2), prec, dev)
         c0 = self._stem(prec, "conv0", x, out=cat0.window(0))
         c1 = self._c(prec, "conv1_1", self._c(prec, "conv1", c0), out=cat1.window(0))
         c2 = self._c(prec, "conv2_1", self._c(prec, "conv2", c1))
@@ -398,6 +413,14 @@ class FlowNet2(nn.Module):
         self.flownetfusion = FlowNetFusion(args, batchNorm=batchNorm)
         _init(self)
         self.precision = None
+        self.parallel_sd = os.environ.get("SHINEON_FLOW_PARALLEL_SD", "1") != "0"
+        self._side = {}
+
+    def _side_stream(self, device):
+        st = self._side.get(device)
+        if st is None:
+            st = self._side[device] = torch.cuda.Stream(device=device)
+        return st
 
     def forward(self, inputs):
         """inputs f32 [B,3,2,H,W] (H, W multiples of 64) -> flow f32 NCHW [B,2,H,W] (models.py:127-192)."""
@@ -407,9 +430,25 @@ class FlowNet2(nn.Module):
         prec = ops.resolve_precision(self.precision)
         df = self.div_flow
         x = ops.flownet_normalize(inputs.contiguous(), self.rgb_max)
+        # FlowNetSD only needs the normalised pair: it runs on a side stream next to the C -> S1 -> S2 chain (most layers
+        # of a try-on sized batch launch fewer CTAs than there are SMs) and joins before the fusion network.  Under
+        # stream capture the fork / join becomes a parallel branch of the graph.
+        cur = torch.cuda.current_stream(x.device)
+        side = self._side_stream(x.device) if self.parallel_sd else None
+        if side is not None:
+            capturing = torch.cuda.is_current_stream_capturing()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                sd_flow = ops.upsample4x_flow(self.flownets_d.run(x, prec), 1.0 / df, bilinear=False)
+            if not capturing:  # inside a capture the graph's private pool is not reused before the join below
+                x.record_stream(side)
+                sd_flow.record_stream(cur)
         c_flow = ops.upsample4x_flow(self.flownetc.run(x, prec), df, bilinear=True)
         s1_flow = ops.upsample4x_flow(self.flownets_1.run(ops.flownet_warp_concat(x, c_flow, df), prec), df, bilinear=True)
         s2_flow = ops.upsample4x_flow(self.flownets_2.run(ops.flownet_warp_concat(x, s1_flow, df), prec), df, bilinear=False)
-        sd_flow = ops.upsample4x_flow(self.flownets_d.run(x, prec), 1.0 / df, bilinear=False)
+        if side is not None:
+            cur.wait_stream(side)
+        else:
+            sd_flow = ops.upsample4x_flow(self.flownets_d.run(x, prec), 1.0 / df, bilinear=False)
         flow0 = self.flownetfusion.run(ops.flownet_fusion_concat(x, sd_flow, s2_flow), prec)
         return flow0.permute(0, 3, 1, 2).contiguous()
