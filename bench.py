@@ -513,12 +513,15 @@ def run_flow(args, rank, world):
         e0.record()
         for i in range(steps):
             fn(i)
+        net.join_lanes()
         e1.record()
         distributed.barrier()
         clocks = sampler.stop() if sampler else None
         return distributed.max_over_ranks(e0.elapsed_time(e1), dev), clocks
 
-    step = lambda i: net(*sets[i % n_sets])
+    # consecutive pair batches are independent: batch i goes to compute lane i % net.lanes (two forwards in flight), each
+    # input set has its own captured graph and output buffers; timed() joins the lanes before the closing event
+    step = lambda i: net(*sets[i % n_sets], lane=i)
 
     def e2e_step(i):
         stage[0].copy_(host[0], non_blocking=True)
@@ -599,7 +602,7 @@ def run_flow(args, rank, world):
                                "FlowNetFusion; Resample2d / ChannelNorm glue) two-frame forward + flow confidence, 256x192",
                    "pairs_per_step_per_gpu": B, "parallelism": f"dp{world} (pairs sharded, no collective)",
                    "weights": "seeded xavier (no checkpoint offline)", "cuda_graph": True, "cpu_binding": numa,
-                   "flownet_sd_on_side_stream": parallel_sd,
+                   "flownet_sd_on_side_stream": parallel_sd, "compute_lanes": net.lanes,
                    "l2": f"{n_sets} input sets cycled; each step streams > 2 GB of activations through HBM (no flush needed)"},
         "e2e": {"value": pps(ms_e2e), "unit": "pairs/s", "h2d_bytes_per_step": 2 * B * 3 * H * W * 4 * world,
                 "d2h_bytes_per_step": B * 3 * H * W * 4 * world, "ms_per_step": ms_e2e / args.steps,
@@ -727,14 +730,16 @@ def run_b200(args, rank, world):
         return distributed.max_over_ranks(e0.elapsed_time(e1), dev), clocks
 
     def step_raw(i):
-        return pipe.run_raw(*raw_sets[i % N_INPUT_SETS], prep)
+        # consecutive steps are independent: step i goes to compute lane i % pipe.lanes (two steps in flight), each input
+        # set has its own captured graph and output buffer; timed() drains the lanes before the closing event
+        return pipe.run_raw(*raw_sets[i % N_INPUT_SETS], prep, lane=i)
 
     def run_mode(precision):
         pipe.set_precision(precision)
         for i in range(max(args.warmup, N_INPUT_SETS)):  # every input set's graph captured before the timed region
             step_raw(i)
         l0 = _lib.launch_count() + pipe.replayed_launches
-        ms, clocks = timed(step_raw, args.steps, ClockSampler(local) if rank == 0 else None)
+        ms, clocks = timed(step_raw, args.steps, ClockSampler(local) if rank == 0 else None, drain=True)
         launches = _lib.launch_count() + pipe.replayed_launches - l0
         torch.cuda.synchronize()
         # roofline of the dominant kernel: the same steps once more, eagerly, with CUDA events around every tensor-core
@@ -747,7 +752,7 @@ def run_b200(args, rank, world):
             # the tensor-core launches bracket back-to-back GPU execution instead of host launch gaps (eager issue of the ~65
             # launches takes longer than the kernels themselves); the spin is outside every event pair
             torch.cuda._sleep(spin_cycles)
-            return step_raw(i)
+            return pipe.run_raw(*raw_sets[i % N_INPUT_SETS], prep)  # one stream: a launch's events see only that launch
 
         spin_cycles = int(12e-3 * 1.9e9)
         ms_prof, _ = timed(step_prof, args.steps)
@@ -796,6 +801,7 @@ def run_b200(args, rank, world):
             "clips_per_step_per_gpu": args.clips, "frames_per_clip": FRAMES_PER_CLIP, "frames_per_step": frames * world,
             "parallelism": f"dp{world} (clips sharded, no collective)", "weights": "seeded random (no checkpoints offline)",
             "cuda_graph": not args.no_graph, "cpu_binding": numa,
+            "compute_lanes": pipe.lanes if not args.no_graph else 1,
             "l2": f"{N_INPUT_SETS} input sets of {frames * 10 * H * W / 1e6:.0f} MB cycled (> 126 MB L2 together); each step also "
                   "moves > 5 GB of activations through HBM (no flush needed)",
         },

@@ -208,6 +208,11 @@ typedef struct shineon_conv2d_params {
    * workspace per concurrently running launch. */
   void* splitk_ws;
   size_t splitk_ws_bytes;
+  /* != 0: ConvTranspose2d(4, 2, 1) in ONE launch (shineon_conv2d_igemm_fwd only).  w_hi/w_lo = all four phase weight sets
+   * [4 (py*2+px)][Cout][2*2][cin_pad] as shineon_pack_deconv4x4s2_weight writes them; kh = kw = 2, stride = 1, Ho = H,
+   * Wo = W, out_H = 2H, out_W = 2W; pad_*, oh_*, ow_* are ignored: phase (py, px) pads (1-py, 1-px) and writes the output
+   * pixels (2*oh + py, 2*ow + px).  Same results as four launches with oh_mul = ow_mul = 2 (submodules.py:34-38). */
+  int deconv_phases;
 } shineon_conv2d_params;
 size_t shineon_conv2d_splitk_workspace_bytes(const shineon_conv2d_params* p);
 

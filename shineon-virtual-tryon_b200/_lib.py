@@ -32,7 +32,7 @@ class Conv2dParams(C.Structure):
         ("out_H", c_i), ("out_W", c_i), ("out_cstride", c_i), ("out_coffset", c_i),
         ("oh_mul", c_i), ("oh_off", c_i), ("ow_mul", c_i), ("ow_off", c_i),
         ("tile_n", c_i), ("stages", c_i), ("stats_ws", c_p), ("acc_chunk_kb", c_i),
-        ("splitk_ws", c_p), ("splitk_ws_bytes", C.c_size_t),
+        ("splitk_ws", c_p), ("splitk_ws_bytes", C.c_size_t), ("deconv_phases", c_i),
     ]
 
 

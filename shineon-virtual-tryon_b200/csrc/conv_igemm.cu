@@ -49,6 +49,12 @@ struct ConvArgs {
   int stage_off;     // byte offset (from the 1024-aligned tile base) of the epilogue transpose buffers, < 0 = direct stores
   int n_tiles, total_tiles;  // channel tiles per pixel tile, pixel tiles * channel tiles
   int w_per_image;           // 1: the B operand is a [N][Cout][K] batch indexed by the tile's image (needs nb == 1)
+  // ConvTranspose2d(4, 2, 1) as ONE launch: the four output-parity phases (py, px) are an extra, slowest tile dimension.
+  // Phase tiles read the weight set [phase] of a [4][Cout][2*2][cin_pad] batch, pad (1 - py, 1 - px) and write the output
+  // lattice (2*oh + py, 2*ow + px).  (Four launches of 8-32 CTAs each left the small pyramid levels of FlowNet2 and the
+  // training step's down-conv input gradients on a sliver of the chip.)
+  int phases;                // 1 or 4
+  int phase_tiles;           // pixel tiles of one phase
   // epilogue
   const float* bias;
   const float* scale;
@@ -273,7 +279,15 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int tile = item / a.ksplit, ks = item - tile * a.ksplit;
         const int kb_lo = ks * a.kb_per_split, kb_hi = min(a.num_kb, kb_lo + a.kb_per_split);
-        const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+        const int nt = tile % a.n_tiles;
+        int mt = tile / a.n_tiles;
+        int pad_h = a.pad_h, pad_w = a.pad_w, phz = 0;
+        if (a.phases > 1) {
+          phz = mt / a.phase_tiles;
+          mt -= phz * a.phase_tiles;
+          pad_h = 1 - (phz >> 1);
+          pad_w = 1 - (phz & 1);
+        }
         const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, tn = mt / tiles_hw;
         const int n0 = tn * a.nb, h0 = th * a.bh, w0 = tw * a.bw, cn0 = nt * BN;
         for (int kb = kb_lo; kb < kb_hi; ++kb, ++g) {
@@ -287,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int tap = kb / a.cin_blocks, cb = kb - tap * a.cin_blocks;
           const int fy = tap / a.kw, fx = tap - fy * a.kw;
           if (a.stride == 1) {
-            const int cx = w0 + fx - a.pad_w, cy = h0 + fy - a.pad_h;
+            const int cx = w0 + fx - pad_w, cy = h0 + fy - pad_h;
             tma_load_4d(sA, &tmAh, full, cb * kBlockK, cx, cy, n0);
             if (SPLIT) tma_load_4d(sA + kABytes, &tmAl, full, cb * kBlockK, cx, cy, n0);
           } else {
@@ -299,9 +313,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             tma_load_5d(sA, &tmAh, full, cc, w0 + ax, py, h0 + ay, n0);
             if (SPLIT) tma_load_5d(sA + kABytes, &tmAl, full, cc, w0 + ax, py, h0 + ay, n0);
           }
-          if (a.w_per_image) {
-            tma_load_3d(sB, &tmBh, full, kb * kBlockK, cn0, n0);
-            if (SPLIT) tma_load_3d(sB + kBBytes, &tmBl, full, kb * kBlockK, cn0, n0);
+          if (a.w_per_image | (a.phases > 1)) {
+            const int wset = a.w_per_image ? n0 : phz;
+            tma_load_3d(sB, &tmBh, full, kb * kBlockK, cn0, wset);
+            if (SPLIT) tma_load_3d(sB + kBBytes, &tmBl, full, kb * kBlockK, cn0, wset);
           } else {
             tma_load_2d(sB, &tmBh, full, kb * kBlockK, cn0);
             if (SPLIT) tma_load_2d(sB + kBBytes, &tmBl, full, kb * kBlockK, cn0);
@@ -377,12 +392,20 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int tile = item / a.ksplit, ks = item - tile * a.ksplit;
       const int kb_lo = ks * a.kb_per_split, kb_hi = min(a.num_kb, kb_lo + a.kb_per_split);
-      const int nt = tile % a.n_tiles, mt = tile / a.n_tiles;
+      const int nt = tile % a.n_tiles;
+      int mt = tile / a.n_tiles;
+      int oh_off = a.oh_off, ow_off = a.ow_off;
+      if (a.phases > 1) {
+        const int phz = mt / a.phase_tiles;
+        mt -= phz * a.phase_tiles;
+        oh_off = phz >> 1;
+        ow_off = phz & 1;
+      }
       const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, tn = mt / tiles_hw;
       const int cn0 = nt * BN;
       const int n = tn * a.nb + ni, oh = th * a.bh + hi_, ow = tw * a.bw + wi;
       const bool row_ok = ni < a.nb && n < a.N && oh < a.Ho && ow < a.Wo;
-      const long pix = ((long)n * a.out_H + (oh * a.oh_mul + a.oh_off)) * a.out_W + (ow * a.ow_mul + a.ow_off);
+      const long pix = ((long)n * a.out_H + (oh * a.oh_mul + oh_off)) * a.out_W + (ow * a.ow_mul + ow_off);
       // coalesced stores: every lane needs the output offsets of the 8 rows it will write (row = it*4 + lane/8)
       const bool co_ok = kChunk == 32 && stage != nullptr && (a.out_cstride & 3) == 0 &&
                          ((a.out_coffset + cn0) & 3) == 0;  // warp-uniform
@@ -1061,12 +1084,23 @@ static int fill_args(const shineon_conv2d_params* p, ConvArgs& a) {
   a.out_cstride = p->out_cstride ? p->out_cstride : p->Cout;
   a.out_coffset = p->out_coffset;
   SHINEON_REQUIRE(a.out_coffset >= 0 && a.out_coffset + a.Cout <= a.out_cstride, "conv2d: output channel window out of range");
-  SHINEON_REQUIRE((a.Ho - 1) * a.oh_mul + a.oh_off < a.out_H && (a.Wo - 1) * a.ow_mul + a.ow_off < a.out_W, "conv2d: output pixel window out of range");
+  SHINEON_REQUIRE(p->deconv_phases || ((a.Ho - 1) * a.oh_mul + a.oh_off < a.out_H && (a.Wo - 1) * a.ow_mul + a.ow_off < a.out_W),
+                  "conv2d: output pixel window out of range");
   a.w_per_image = p->w_per_image ? 1 : 0;
+  a.phases = p->deconv_phases ? 4 : 1;
+  if (a.phases > 1) {
+    SHINEON_REQUIRE(p->kh == 2 && p->kw == 2 && p->stride == 1 && p->Ho == p->H && p->Wo == p->W && !p->w_per_image,
+                    "conv2d: deconv_phases needs the 2x2 / stride 1 phase geometry (Ho = H, Wo = W)");
+    SHINEON_REQUIRE(a.out_H == 2 * p->H && a.out_W == 2 * p->W && p->stats_ws == nullptr,
+                    "conv2d: deconv_phases writes a [N, 2H, 2W] output and has no statistics epilogue");
+    a.oh_mul = 2; a.ow_mul = 2; a.oh_off = 0; a.ow_off = 0;  // the phase of a tile sets the offsets
+    a.pad_h = 1; a.pad_w = 1;
+  }
   pick_tile(a.w_per_image ? 1 : a.N, a.Ho, a.Wo, a.nb, a.bh, a.bw);
   a.stats = nullptr;
   a.tiles_w = cdiv(a.Wo, a.bw);
   a.tiles_h = cdiv(a.Ho, a.bh);
+  a.phase_tiles = a.tiles_w * a.tiles_h * cdiv(a.N, a.nb);
   return SHINEON_OK;
 }
 
@@ -1102,7 +1136,7 @@ extern "C" int shineon_conv2d_igemm_fwd(const shineon_conv2d_params* p, shineon_
 
 extern "C" size_t shineon_conv2d_splitk_workspace_bytes(const shineon_conv2d_params* p) {
   ConvArgs a;
-  if (fill_args(p, a) != SHINEON_OK) return 0;
+  if (fill_args(p, a) != SHINEON_OK || a.phases > 1) return 0;
   int bn = p->tile_n;
   if (bn == 0) bn = a.Cout <= 16 ? 16 : a.Cout <= 32 ? 32 : a.Cout <= 64 ? 64 : 128;
   const long m_tiles = (long)a.tiles_w * a.tiles_h * cdiv(a.N, a.nb);
@@ -1116,8 +1150,8 @@ extern "C" size_t shineon_conv2d_splitk_workspace_bytes(const shineon_conv2d_par
 static int conv2d_igemm_launch(const shineon_conv2d_params* p, ConvArgs& a, cudaStream_t stream) {
   int rc;
   const bool split = p->x_lo != nullptr;
-  const int m_tiles = a.tiles_w * a.tiles_h * cdiv(a.N, a.nb);
-  SHINEON_REQUIRE((long)m_tiles < (1l << 31), "conv2d: too many tiles");
+  SHINEON_REQUIRE((long)a.phases * a.phase_tiles < (1l << 31), "conv2d: too many tiles");
+  const int m_tiles = a.phases * a.phase_tiles;
 
   int bn = p->tile_n;
   if (bn == 0) bn = a.Cout <= 16 ? 16 : a.Cout <= 32 ? 32 : a.Cout <= 64 ? 64 : 128;
@@ -1145,8 +1179,8 @@ static int conv2d_igemm_launch(const shineon_conv2d_params* p, ConvArgs& a, cuda
   }
   {
     const cuuint64_t K = (cuuint64_t)p->kh * p->kw * Cw;
-    const int brank = a.w_per_image ? 3 : 2;
-    cuuint64_t dims[3] = {K, (cuuint64_t)p->Cout, N};
+    const int brank = (a.w_per_image || a.phases > 1) ? 3 : 2;
+    cuuint64_t dims[3] = {K, (cuuint64_t)p->Cout, a.phases > 1 ? (cuuint64_t)a.phases : N};
     cuuint64_t strides[2] = {K * 2, K * 2 * (cuuint64_t)p->Cout};
     cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)bn, 1};
     if ((rc = encode_map(&tBh, p->w_hi, brank, dims, strides, box, "B hi", p->plane_fmt))) return rc;
@@ -1158,7 +1192,7 @@ static int conv2d_igemm_launch(const shineon_conv2d_params* p, ConvArgs& a, cuda
   a.ksplit = 1;
   a.kb_per_split = a.num_kb;
   a.sk_ws = nullptr; a.sk_cnt = nullptr; a.sk_ctot = 0; a.sk_slice = 0;
-  if (p->splitk_ws != nullptr) {
+  if (p->splitk_ws != nullptr && a.phases == 1) {
     const int n_tiles = cdiv(a.Cout, bn);
     int per = a.num_kb;
     const int ks = plan_splitk(m_tiles * n_tiles, a.num_kb, bn, a.chunk_kb, &per);
@@ -1248,7 +1282,7 @@ extern "C" int shineon_conv2d_im2col_fwd(const shineon_conv2d_params* p, const f
   a.cin_pad = p->cin_pad; a.cin_blocks = p->cin_pad / kBlockK; a.x_cstride = p->cin_pad;
   a.num_kb = a.cin_blocks;  // the GEMM is 1x1 over the padded K
   a.chunk_kb = a.num_kb;
-  a.stages = 1; a.w_per_image = 0; a.stats = nullptr;
+  a.stages = 1; a.w_per_image = 0; a.stats = nullptr; a.phases = 1; a.phase_tiles = 0;
   a.ksplit = 1; a.kb_per_split = a.num_kb; a.sk_ws = nullptr; a.sk_cnt = nullptr; a.sk_ctot = 0; a.sk_slice = 0;
   a.bias = p->bias; a.scale = p->scale; a.shift = p->shift;
   a.pre_act = p->pre_act; a.post_act = p->post_act; a.act_param = p->act_param;
@@ -1294,6 +1328,7 @@ extern "C" int shineon_conv2d_direct_fwd(const shineon_conv2d_params* p, shineon
   ConvArgs a;
   int rc = fill_args(p, a);
   if (rc) return rc;
+  SHINEON_REQUIRE(a.phases == 1, "conv2d_direct: deconv_phases is a tcgen05-kernel mode (run the four phases separately)");
   long total = (long)a.N * a.Ho * a.Wo * a.Cout;
   long blocks = (total + 127) / 128;
   if (blocks > 148 * 64) blocks = 148 * 64;

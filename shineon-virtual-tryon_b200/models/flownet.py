@@ -3,6 +3,8 @@
 The reference constructor loads `models/flownet2_pytorch/FlowNet2_checkpoint.pth.tar` and calls `.cuda()`; no
 checkpoint is available offline, so `checkpoint=None` builds the same module tree with its default initialisation
 (load one with `load_state_dict` — the keys are the reference's)."""
+import os
+
 import torch
 from torch import nn
 
@@ -26,32 +28,61 @@ class FlowNet(nn.Module):
         # static outputs, overwritten by the next call on the same input buffers.
         self.cuda_graph = False
         self._graphs = {}
+        # Compute lanes (cuda_graph mode): forward(..., lane=i) replays on stream i % lanes, so two independent pair batches
+        # are in flight and the many small launches of one (pyramid levels of 4x3 ... 16x12 pixels) fill the SMs the other
+        # leaves idle.  The results are then ordered on the lane: join_lanes() before reading them on the caller's stream.
+        self.lanes = int(os.environ.get("SHINEON_FLOW_LANES", "2"))
+        self._lane_streams = {}
 
-    def forward(self, input_A, input_B):
+    def forward(self, input_A, input_B, lane=None):
         with torch.no_grad():
             size = input_A.size()
             assert len(size) == 4 or len(size) == 5
             if len(size) == 5:
                 b, n, c, h, w = size
-                flow, conf = self.compute_flow_and_conf(input_A.reshape(-1, c, h, w), input_B.reshape(-1, c, h, w))
+                flow, conf = self.compute_flow_and_conf(input_A.reshape(-1, c, h, w), input_B.reshape(-1, c, h, w), lane)
                 return flow.view(b, n, 2, h, w), conf.view(b, n, 1, h, w)
-            return self.compute_flow_and_conf(input_A, input_B)
+            return self.compute_flow_and_conf(input_A, input_B, lane)
 
-    def compute_flow_and_conf(self, im1, im2):
+    def join_lanes(self):
+        """Makes the caller's stream wait for every forward issued on a compute lane."""
+        cur = torch.cuda.current_stream()
+        for st in self._lane_streams.values():
+            cur.wait_stream(st)
+
+    def compute_flow_and_conf(self, im1, im2, lane=None):
         if not self.cuda_graph or ops.PROFILE is not None:
             return self._compute_flow_and_conf(im1, im2)
         im1, im2 = im1.contiguous(), im2.contiguous()
-        key = (im1.data_ptr(), im2.data_ptr(), tuple(im1.shape))
+        lane_id = 0 if (lane is None or self.lanes <= 1) else 1 + lane % self.lanes
+        key = (im1.data_ptr(), im2.data_ptr(), tuple(im1.shape), lane_id)
+        if lane_id:
+            cur = torch.cuda.current_stream(im1.device)
+            ls = self._lane_streams.get((str(im1.device), lane_id))
+            if ls is None:
+                ls = self._lane_streams[(str(im1.device), lane_id)] = torch.cuda.Stream(im1.device)
+            ls.wait_stream(cur)
+            with torch.cuda.stream(ls):
+                return self._replay(key, im1, im2, lane_id)
+        return self._replay(key, im1, im2, lane_id)
+
+    def _replay(self, key, im1, im2, lane_id):
+        from ..networks.flownet2 import nets
+
         ent = self._graphs.get(key)
         if ent is None:
             if len(self._graphs) >= 4:
                 self._graphs.clear()
-            for _ in range(2):  # weight packing / allocator warm-up outside the capture
-                self._compute_flow_and_conf(im1, im2)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, capture_error_mode="thread_local"):  # other threads (NCCL watchdog) may poll events
-                out = self._compute_flow_and_conf(im1, im2)
+            nets.CONCAT_LANE[0] = lane_id  # concurrent forwards keep separate concat buffers
+            try:
+                for _ in range(2):  # weight packing / allocator warm-up outside the capture
+                    self._compute_flow_and_conf(im1, im2)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):  # other threads (NCCL watchdog) may poll events
+                    out = self._compute_flow_and_conf(im1, im2)
+            finally:
+                nets.CONCAT_LANE[0] = 0
             ent = self._graphs[key] = (graph, out)
         ent[0].replay()
         return ent[1]

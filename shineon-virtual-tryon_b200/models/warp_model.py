@@ -1,13 +1,19 @@
 """WarpModel — Geometric Matching Module (reference: models/warp_model.py:27-152)."""
 import argparse
+import os
 from argparse import ArgumentParser
 
+import torch
 from torch import nn
 
 from ..networks.cpvton.warp import (FeatureCorrelation, FeatureExtraction, FeatureL2Norm, FeatureRegression,
                                     TpsGridGen)
 from .. import ops
 from .base_model import BaseModel, get_and_cat_inputs, maybe_combine_frames_and_channels
+
+
+# extractionA / extractionB on two streams while a CUDA graph is being captured (parallel graph branches); A/B switch
+PARALLEL_EXTRACTION = os.environ.get("SHINEON_GMM_PARALLEL", "0") == "1"
 
 
 class WarpModel(BaseModel):
@@ -44,8 +50,21 @@ class WarpModel(BaseModel):
 
     def regress_theta(self, inputA, inputB):
         """inputA / inputB: f32 NCHW tensors, or the two stems' operands from ops.frame_prep_planes."""
-        featureA = self.extractionA.forward_nhwc(inputA)
-        featureB = self.extractionB.forward_nhwc(inputB)
+        if PARALLEL_EXTRACTION and torch.cuda.is_current_stream_capturing():
+            # the two towers are independent: inside a graph capture they become parallel branches (the capture's private
+            # pool is not recycled before the join, so no cross-stream allocator bookkeeping is needed)
+            cur = torch.cuda.current_stream()
+            side = self.__dict__.get("_side")
+            if side is None:
+                side = self.__dict__["_side"] = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                featureB = self.extractionB.forward_nhwc(inputB)
+            featureA = self.extractionA.forward_nhwc(inputA)
+            cur.wait_stream(side)
+        else:
+            featureA = self.extractionA.forward_nhwc(inputA)
+            featureB = self.extractionB.forward_nhwc(inputB)
         _, corr = self.correlation.forward_fused(featureA, featureB, prec=ops.resolve_precision(self.precision))
         return self.regression.forward_planes(corr)
 

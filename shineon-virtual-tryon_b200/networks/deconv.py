@@ -5,11 +5,15 @@ FlowNetC.py:59-62.  out[2m+py] = sum over the two taps of that output parity, i.
 2x2 stride-1 convolutions of the *input*, each scattered to its (py, px) output lattice:
   py = 0: x[m-1]*w[3] + x[m]*w[1]   (pad 1 before)      py = 1: x[m]*w[2] + x[m+1]*w[0]   (pad 0)
 """
+import os
+
 import torch
 
 from .. import ops
 
 _TAPS = {0: [3, 1], 1: [2, 0]}
+# True: one launch per transposed conv (phase = a tile dimension of conv_igemm); False: four phase launches (round 1 / 2a)
+MERGE_PHASES = os.environ.get("SHINEON_DECONV_MERGE", "1") != "0"
 
 
 class PackedDeconv4x4s2:
@@ -39,6 +43,13 @@ class PackedDeconv4x4s2:
                                                                   cin_pad, ops._p(cm), fmt, w_scale, ops._stream()),
                   "shineon_pack_deconv4x4s2_weight")
         b = None if bias is None else ops._req(bias.detach().float().contiguous(), name="bias")
+        # all four phases in one launch (the phase is a tile dimension of the kernel): pc_all holds the whole weight batch
+        pa = ops.PackedConv.__new__(ops.PackedConv)
+        pa.fmt, pa.Cout, pa.Cin, pa.kh, pa.kw, pa.stride = fmt, Cout, Cin, 2, 2, 1
+        pa.pad_h, pa.pad_w, pa.cin_pad = 1, 1, cin_pad
+        pa.w_hi, pa.w_lo = w_hi, w_lo
+        pa.acc_scale, pa.bias, pa.transposed = 1.0 / w_scale, b, False
+        self.pc_all = pa
         self.phases = []
         for py in (0, 1):
             for px in (0, 1):
@@ -57,6 +68,10 @@ class PackedDeconv4x4s2:
             out_f32 = torch.empty(N, 2 * H, 2 * W, self.Cout, dtype=torch.float32, device=dev)
         if want_planes and out_planes is None:
             out_planes = ops.Planes(N, 2 * H, 2 * W, self.Cout, prec=x.prec, device=dev)
+        if MERGE_PHASES:
+            ops.conv2d(x, self.pc_all, post_act=post_act, act_param=act_param, out_f32=out_f32, out_planes=out_planes,
+                       out_coffset=out_coffset, out_geom=(2 * H, 2 * W, 2, 0, 2, 0), out_hw=(H, W), deconv_phases=True)
+            return out_f32, out_planes
         for py, px, pc in self.phases:
             ops.conv2d(x, pc, post_act=post_act, act_param=act_param, out_f32=out_f32, out_planes=out_planes,
                        out_coffset=out_coffset, out_geom=(2 * H, 2 * W, 2, py, 2, px), out_hw=(H, W))

@@ -81,6 +81,11 @@ class _Concat:
         return cmap
 
 
+# forwards that may run concurrently (models.flownet.FlowNet compute lanes) must not share concat buffers: the lane id
+# of the forward being issued is part of the cache key
+CONCAT_LANE = [0]
+
+
 class _Net(nn.Module):
     """Packed-weight cache shared by the four sub-networks."""
 
@@ -89,13 +94,34 @@ class _Net(nn.Module):
         their windows and nothing ever writes the padding channels, so the zero fill happens once per buffer instead
         of once per forward (it was 78 fill launches = 5 % of a batch-16 FlowNet2 forward)."""
         cache = self.__dict__.setdefault("_cat_cache", {})
-        key = (N, H, W, tuple(seg_channels), prec, str(device))
+        key = (N, H, W, tuple(seg_channels), prec, str(device), CONCAT_LANE[0])
         cat = cache.get(key)
         if cat is None:
-            if len(cache) >= 16:  # a new batch size / resolution: drop the old set
+            if len(cache) >= 32:  # a new batch size / resolution: drop the old set
                 cache.clear()
             cat = cache[key] = _Concat(N, H, W, seg_channels, prec, device)
         return cat
+
+    # deconv{lvl} of a refinement level does not depend on that level's predict_flow -> upsampled_flow chain: it runs on an
+    # auxiliary stream (a parallel branch under graph capture).  Both chains write windows of the cached concat buffer, so
+    # no allocation crosses streams.
+    parallel = os.environ.get("SHINEON_FLOW_PARALLEL_REFINE", "1") != "0"
+
+    def _fork(self, fn, allocates=False):
+        """Runs fn() on this network's auxiliary stream, forked from the current one; returns the join callable.
+        allocates=True: fn's results are torch allocations that cross back to the forking stream -- only done inside a graph
+        capture (whose private pool is not recycled before the join); eagerly such branches stay on the current stream."""
+        if not self.parallel or ops.PROFILE is not None or (allocates and not torch.cuda.is_current_stream_capturing()):
+            fn()
+            return lambda: None
+        cur = torch.cuda.current_stream()
+        aux = self.__dict__.get("_aux_stream")
+        if aux is None:
+            aux = self.__dict__["_aux_stream"] = torch.cuda.Stream()
+        aux.wait_stream(cur)
+        with torch.cuda.stream(aux):
+            fn()
+        return lambda: cur.wait_stream(aux)
 
     def _packs(self, prec):
         sig = (params_signature(self), prec)
@@ -172,9 +198,11 @@ class _Net(nn.Module):
         src, segs = c6, None
         flow = None
         for lvl, cat in zip((5, 4, 3, 2), cats):
+            join = self._fork(lambda: self._pc(prec, f"deconv{lvl}", segs)(src, post_act="leaky", act_param=LEAK,
+                                                                          out_planes=cat.window(1)))
             flow, flow_pl = self._flow(prec, f"predict_flow{lvl + 1}", src, segs)
             self._pc(prec, f"upsampled_flow{lvl + 1}_to_{lvl}")(flow_pl, out_planes=cat.window(2))
-            self._pc(prec, f"deconv{lvl}", segs)(src, post_act="leaky", act_param=LEAK, out_planes=cat.window(1))
+            join()
             src, segs = cat.buf, cat.seg
         flow2, _ = self._flow(prec, "predict_flow2", src, segs, want_f32=True, want_planes=False)
         return flow2
@@ -224,9 +252,13 @@ class FlowNetC(_Net):
         mk = lambda k, segs: self._concat(B, H // k, W // k, segs, prec, dev)
         cat5, cat4, cat3, cat2 = mk(32, (512, 512, 2)), mk(16, (512, 256, 2)), mk(8, (256, 128, 2)), mk(4, (128, 64, 2))
         x1, x2 = x[:, 0:3].contiguous(), x[:, 3:].contiguous()
+        tower_b = {}
+        join = self._fork(lambda: tower_b.update(c3=self._c(prec, "conv3", self._c(prec, "conv2", self._stem(prec, "conv1", x2)))),
+                          allocates=True)  # the second frame's tower next to the first's
         c2a = self._c(prec, "conv2", self._stem(prec, "conv1", x1), out=cat2.window(0))
         c3a = self._c(prec, "conv3", c2a)
-        c3b = self._c(prec, "conv3", self._c(prec, "conv2", self._stem(prec, "conv1", x2)))
+        join()
+        c3b = tower_b["c3"]
         in31 = self._concat(B, H // 8, W // 8, (32, 441), prec, dev)
         corr = ops.correlation_planes(c3a, c3b, 256, 20, 20, 2)  # tensor-core cost volume straight from the planes
         ops.nchw_to_planes(corr, act="leaky", act_param=LEAK, out=in31.window(1))  # corr_activation
@@ -335,8 +367,10 @@ class FlowNetSD(_Net):
         flow, flow_pl = self._flow(prec, "predict_flow6", c6)
         src, segs = c6, None
         for lvl, cat in zip((5, 4, 3, 2), (cat5, cat4, cat3, cat2)):
+            join = self._fork(lambda: self._pc(prec, f"deconv{lvl}", segs)(src, post_act="leaky", act_param=LEAK,
+                                                                          out_planes=cat.window(1)))
             self._pc(prec, f"upsampled_flow{lvl + 1}_to_{lvl}")(flow_pl, out_planes=cat.window(2))
-            self._pc(prec, f"deconv{lvl}", segs)(src, post_act="leaky", act_param=LEAK, out_planes=cat.window(1))
+            join()
             inter = self._c(prec, f"inter_conv{lvl}", cat.buf, segs=cat.seg, act=False)
             flow, flow_pl = self._flow(prec, f"predict_flow{lvl}", inter, want_f32=lvl == 2, want_planes=lvl != 2)
             src, segs = cat.buf, cat.seg
@@ -372,13 +406,16 @@ class FlowNetFusion(_Net):
         c0 = self._stem(prec, "conv0", x, out=cat0.window(0))
         c1 = self._c(prec, "conv1_1", self._c(prec, "conv1", c0), out=cat1.window(0))
         c2 = self._c(prec, "conv2_1", self._c(prec, "conv2", c1))
+        join = self._fork(lambda: self._pc(prec, "deconv1")(c2, post_act="leaky", act_param=LEAK, out_planes=cat1.window(1)))
         _, flow2_pl = self._flow(prec, "predict_flow2", c2)
         self._pc(prec, "upsampled_flow2_to_1")(flow2_pl, out_planes=cat1.window(2))
-        self._pc(prec, "deconv1")(c2, post_act="leaky", act_param=LEAK, out_planes=cat1.window(1))
+        join()
         i1 = self._c(prec, "inter_conv1", cat1.buf, segs=cat1.seg, act=False)
+        join = self._fork(lambda: self._pc(prec, "deconv0", cat1.seg)(cat1.buf, post_act="leaky", act_param=LEAK,
+                                                                       out_planes=cat0.window(1)))
         _, flow1_pl = self._flow(prec, "predict_flow1", i1)
         self._pc(prec, "upsampled_flow1_to_0")(flow1_pl, out_planes=cat0.window(2))
-        self._pc(prec, "deconv0", cat1.seg)(cat1.buf, post_act="leaky", act_param=LEAK, out_planes=cat0.window(1))
+        join()
         i0 = self._c(prec, "inter_conv0", cat0.buf, segs=cat0.seg, act=False)
         flow0, _ = self._flow(prec, "predict_flow0", i0, want_f32=True, want_planes=False)
         return flow0

@@ -305,11 +305,13 @@ class PackedConv:
 
 def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_param=0.0, out_f32=None,
            out_planes=None, out_coffset=0, want_f32=False, want_planes=False, direct=False, tile_n=0, stages=0,
-           out_geom=None, out_hw=None, stats_ws=None):
+           out_geom=None, out_hw=None, stats_ws=None, deconv_phases=False):
     """Run one convolution layer on planes `x` with packed weights `pc`.
 
     Outputs: f32 NHWC tensor [N,Ho,Wo,Cout] (want_f32 / out_f32) and/or Planes (want_planes / out_planes).
     out_geom = (out_H, out_W, oh_mul, oh_off, ow_mul, ow_off) scatters into a larger output (deconv phases).
+    deconv_phases: `pc` holds the four phase weight sets of a ConvTranspose2d(4, 2, 1) ([4, Cout, 4, cin_pad]); one launch
+    computes all four output parities (networks/deconv.py).
     stats_ws: zeroed f64 [N*Cout*2] buffer; the kernel adds the per-(image, channel) sum / sum of squares of the f32
     output values to it (InstanceNorm statistics for instnorm_act(stats_ready=True)).
     """
@@ -349,6 +351,7 @@ def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_pa
         p.out_cstride, p.out_coffset = out_f32.shape[-1], out_coffset
     p.oh_mul, p.oh_off, p.ow_mul, p.ow_off = ohm, oho, owm, owo
     p.tile_n, p.stages = tile_n, stages
+    p.deconv_phases = int(deconv_phases)
     p.stats_ws = _p(stats_ws)
     p.acc_chunk_kb = ACC_CHUNK_KB
     if SPLIT_K and not direct:
@@ -371,7 +374,7 @@ def conv2d(x, pc, *, scale=None, shift=None, pre_act=None, post_act=None, act_pa
     check(fn(C.byref(p), _stream()), "shineon_conv2d_direct_fwd" if direct else "shineon_conv2d_igemm_fwd")
     if prof is not None and not direct:
         e1.record()
-        prof.append((2.0 * N * Ho * Wo * pc.Cout * pc.kh * pc.kw * pc.Cin, e0, e1,
+        prof.append((2.0 * N * Ho * Wo * pc.Cout * pc.kh * pc.kw * pc.Cin * (4 if deconv_phases else 1), e0, e1,
                      (N, H, W, pc.Cin, x.cpad, pc.Cout, pc.kh, pc.stride)))
     return out_f32, out_planes
 

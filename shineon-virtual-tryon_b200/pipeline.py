@@ -13,6 +13,7 @@ on the device.  Entry points, from the reference's tensors to its file formats:
   pipe.run_host_raw(raw_h, prep)           pinned uint8 host frames in, pinned uint8 host frames out: 10 B/pixel up,
                                            3 B/pixel down (the f32 forms move 112 and 12)
 """
+import os
 from collections import OrderedDict
 
 import torch
@@ -34,6 +35,13 @@ class TryOnPipeline:
         self._graphs = OrderedDict()
         self._tensors = None
         self.replayed_launches = 0  # kernel launches executed through graph replays (not seen by shineon_launch_count)
+        # Compute lanes: consecutive steps are independent (frames / clips never talk to each other), so the host-buffer
+        # entry points and run_raw(lane=...) replay step i on stream i % lanes.  Two steps in flight let the launch-latency
+        # bound parts of one step (the 4x3 ... 16x12 levels, attention, the regression head: kernels of 8-40 CTAs) run next
+        # to the chip-filling layers of the other.  1 (default) = everything on the caller's stream: measured on B200 at 160
+        # frames per step, two lanes gave +1 % device-resident and -4 % end to end (profiles/r02_concurrency.md).
+        self.lanes = int(os.environ.get("SHINEON_LANES", "1"))
+        self._lane_streams = {}
 
     def set_precision(self, precision):
         self.warp_model.set_precision(precision)
@@ -156,12 +164,38 @@ class TryOnPipeline:
 
     RAW_KEYS = ("parse", "cloth", "densepose", "image")
 
+    def _lane(self, i, dev):
+        key = (str(dev), i % max(1, self.lanes))
+        st = self._lane_streams.get(key)
+        if st is None:
+            st = self._lane_streams[key] = torch.cuda.Stream(dev)
+        return st
+
+    def join_lanes(self):
+        """Makes the caller's stream wait for every step issued on a compute lane (run_raw(lane=...))."""
+        cur = torch.cuda.current_stream()
+        for st in self._lane_streams.values():
+            cur.wait_stream(st)
+
     @torch.no_grad()
-    def run_raw(self, parse, cloth, densepose, image, prep, u8_out=True):
+    def run_raw(self, parse, cloth, densepose, image, prep, u8_out=True, lane=None):
         """Decoded 8-bit frames on the device (`image`, `cloth`, `densepose` [F,H,W,3], `parse` [F,H,W], uint8) ->
         try-on frames uint8 [F,H,W,3] exactly as visualization.save_images would encode them (u8_out=False: the f32
-        triple of __call__).  The reference's Dataset.__getitem__ tensor prep runs on the device (ops.FramePrep)."""
-        out = self._graph_call("raw", self._raw_fn(prep, u8_out), (parse, cloth, densepose, image))
+        triple of __call__).  The reference's Dataset.__getitem__ tensor prep runs on the device (ops.FramePrep).
+
+        lane=i (CUDA-graph mode): the step is issued on compute lane i % self.lanes after everything queued on the caller's
+        stream so far; steps on different lanes overlap.  The result is ordered on the lane, not on the caller's stream:
+        call join_lanes() (or synchronise) before reading it, and give concurrent steps distinct input buffers (a graph
+        owns its output buffer)."""
+        fn, args = self._raw_fn(prep, u8_out), (parse, cloth, densepose, image)
+        if lane is None or self.lanes <= 1 or not self.cuda_graph:
+            out = self._graph_call("raw", fn, args)
+        else:
+            cur = torch.cuda.current_stream(parse.device)
+            ls = self._lane(lane, parse.device)
+            ls.wait_stream(cur)
+            with torch.cuda.stream(ls):
+                out = self._graph_call("raw", fn, args)
         return out[0] if u8_out else out
 
     # ------------------------------------------------------------------ host entry points
@@ -217,13 +251,20 @@ class TryOnPipeline:
             for d, h in zip(dev_in, host_tensors):
                 d.copy_(h, non_blocking=True)
             st["in_ready"][slot].record(st["s_in"])
-        cur.wait_event(st["in_ready"][slot])
+        # compute stream of this call: the caller's, or (CUDA-graph mode, lanes > 1) the slot's lane so that two
+        # consecutive calls' kernels overlap; either way the result is ordered by `done_event`
+        comp = cur
+        if self.cuda_graph and self.lanes > 1:
+            comp = self._lane(slot, dev)
+            comp.wait_stream(cur)
+        comp.wait_event(st["in_ready"][slot])
         if self.cuda_graph:
-            cur.wait_event(st["out_done"][slot])  # this slot's graph owns its output buffer: the last D2H of it must be done
-        result = self._graph_call(tag, fn, dev_in)[0]
-        st["in_free"][slot].record(cur)
+            comp.wait_event(st["out_done"][slot])  # this slot's graph owns its output buffer: the last D2H of it must be done
+        with torch.cuda.stream(comp):
+            result = self._graph_call(tag, fn, dev_in)[0]
+        st["in_free"][slot].record(comp)
         computed = torch.cuda.Event()
-        computed.record(cur)
+        computed.record(comp)
         if st["host_out"][slot] is None:
             st["host_out"][slot] = torch.empty(result.shape, dtype=result.dtype).pin_memory()
         out_h = st["host_out"][slot]
@@ -237,10 +278,12 @@ class TryOnPipeline:
 
     def host_streams(self):
         """The copy streams of every host entry point used so far (a caller timing on its own stream waits on these)."""
-        return [s for st in self._host_state.values() for s in (st["s_in"], st["s_out"])]
+        return [s for st in self._host_state.values() for s in (st["s_in"], st["s_out"])] + list(self._lane_streams.values())
 
     def host_sync(self):
         """Wait for every outstanding run_host* call (copies included)."""
         for s in self.host_streams():
+            s.synchronize()
+        for s in self._lane_streams.values():
             s.synchronize()
         torch.cuda.current_stream().synchronize()

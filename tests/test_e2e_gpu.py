@@ -351,6 +351,33 @@ def test_flownet2_batch16_matches_reference_golden(cuda):
         assert agree > 0.999, agree  # thresholded residual: disagreement only within round-off of the 0.02 threshold
 
 
+def test_flownet_compute_lanes_match_single_stream(cuda):
+    """FlowNet(cuda_graph) with compute lanes: two different pair batches in flight on two streams (each lane replays its own
+    graph over its own concat buffers) must return exactly what the single-stream eager forward returns for each batch,
+    repeatedly (a shared buffer between the lanes would show up as cross-talk)."""
+    from oracle import weights
+    from shineon_virtual_tryon_b200.models.flownet import FlowNet
+
+    seed, shapes, _ = load_golden("flownet2")
+    sd = weights.synth_state_dict(shapes, seed)
+    net = FlowNet()
+    net.flowNet.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    g = torch.Generator().manual_seed(77)
+    pairs = [(torch.rand(3, 3, 128, 128, generator=g).cuda(), torch.rand(3, 3, 128, 128, generator=g).cuda()) for _ in range(2)]
+    with torch.no_grad():
+        want = [tuple(t.clone() for t in net(a, b)) for a, b in pairs]
+    net.cuda_graph = True
+    net.lanes = 2
+    for rep in range(4):
+        with torch.no_grad():
+            got = [net(a, b, lane=i) for i, (a, b) in enumerate(pairs)]
+        net.join_lanes()
+        torch.cuda.synchronize()
+        for (wf, wc), (gf, gc) in zip(want, got):
+            assert torch.equal(wf, gf) and torch.equal(wc, gc), f"lane result differs from the eager forward (round {rep})"
+
+
 def test_flownet_resizes_inputs_whose_height_is_not_a_multiple_of_64(cuda):
     """models/flownet.py:46-51,56-58: bilinear resize to the 64-multiple below, FlowNet2, flow resized back and scaled
     by old_h / new_h, confidence resized back (no longer binary).  200x200 -> 192x192."""

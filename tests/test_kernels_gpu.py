@@ -136,7 +136,8 @@ def test_conv2d_epilogue_and_window(ops):
     assert got[:, :64].abs().max().item() == 0 and got[:, 128:].abs().max().item() == 0
 
 
-@pytest.mark.parametrize("cfg", [(2, 22, 64, 48, 64, 4, 2, 1), (2, 3, 32, 32, 64, 7, 2, 3), (1, 10, 64, 48, 64, 4, 2, 1)])
+@pytest.mark.parametrize("cfg", [(2, 22, 64, 48, 64, 4, 2, 1), (2, 3, 32, 32, 64, 7, 2, 3), (1, 10, 64, 48, 64, 4, 2, 1),
+                                 (2, 12, 64, 72, 64, 7, 2, 3), (3, 6, 40, 36, 64, 3, 1, 1), (1, 11, 33, 45, 64, 3, 1, 1)])
 def test_im2col_first_layer(ops, cfg):
     """Small-Cin conv as im2col'd planes + dense 1x1 GEMM (cat of two NCHW inputs fused)."""
     N, Cin, H, W, Cout, k, s, p = cfg
@@ -208,21 +209,44 @@ def test_upsampled_conv3x3_at_low_resolution(ops, shape):
     assert_close(nchw(y), want, atol=3e-5, rtol=1e-4, what="upsample->conv3x3 at low resolution")
 
 
-def test_deconv_as_phase_convs(ops):
-    """ConvTranspose2d(4,2,1) (submodules.py:34-38) = 4 phase-wise 2x2 convolutions scattered into the output."""
+@pytest.mark.parametrize("shape", [(2, 6, 8, 64, 32), (3, 4, 3, 130, 2), (16, 4, 3, 256, 200), (2, 24, 16, 64, 64),
+                                   (5, 9, 7, 64, 144)])
+def test_deconv_as_phase_convs(ops, shape):
+    """ConvTranspose2d(4,2,1) (submodules.py:34-38) = 4 phase-wise 2x2 convolutions scattered into the output: as ONE launch
+    (the phase is a tile dimension of conv_igemm, `deconv_phases`) and as four launches -- the two forms must agree bit for
+    bit (same products, same accumulation order) and match torch within fp32-grade tolerance; f32 and plane outputs,
+    Cout not a multiple of the channel tile (weight boxes run into the next phase's rows / past the tensor), several pixel
+    tiles per phase, a channel window of a wider output buffer."""
+    from shineon_virtual_tryon_b200.networks import deconv as dmod
+
     g = torch.Generator().manual_seed(11)
-    N, H, W, Cin, Cout = 2, 6, 8, 64, 32
+    N, H, W, Cin, Cout = shape
     x = torch.randn(N, Cin, H, W, generator=g)
     w = torch.randn(Cin, Cout, 4, 4, generator=g) * 0.05
     b = torch.randn(Cout, generator=g) * 0.1
     want = F.conv_transpose2d(x, w, b, stride=2, padding=1)
-    from shineon_virtual_tryon_b200.networks.deconv import PackedDeconv4x4s2
-
     xp = _planes_from(ops, x)
-    dc = PackedDeconv4x4s2(w.cuda(), b.cuda())
-    y = dc(xp, want_f32=True)[0]
-    torch.cuda.synchronize()
-    assert_close(nchw(y), want, atol=3e-5, rtol=1e-4, what="deconv")
+    dc = dmod.PackedDeconv4x4s2(w.cuda(), b.cuda())
+    outs = {}
+    saved = dmod.MERGE_PHASES
+    try:
+        for merged in (True, False):
+            dmod.MERGE_PHASES = merged
+            y = dc(xp, want_f32=True)[0]
+            cat = ops.Planes(N, 2 * H, 2 * W, 64 + ops.cpad64(Cout), device="cuda", cpad=64 + ops.cpad64(Cout))
+            cat.hi.zero_()
+            cat.lo.zero_()
+            dc(xp, post_act="leaky", act_param=0.1, out_planes=cat.window(64, Cout))
+            torch.cuda.synchronize()
+            outs[merged] = (y.clone(), cat.hi.clone(), cat.lo.clone())
+    finally:
+        dmod.MERGE_PHASES = saved
+    assert_close(nchw(outs[True][0]), want, atol=3e-5, rtol=1e-4, what="deconv (one launch)")
+    for a, bb, what in zip(outs[True], outs[False], ("f32", "planes hi", "planes lo")):
+        assert torch.equal(a, bb), f"deconv one launch vs four phase launches: {what} differ"
+    got = (outs[True][1].float() + outs[True][2].float())[..., 64:64 + Cout].permute(0, 3, 1, 2).cpu()
+    assert (outs[True][1][..., :64] == 0).all() and (outs[True][1][..., 64 + Cout:] == 0).all(), "wrote outside its window"
+    assert_close(got, F.leaky_relu(want, 0.1), atol=3e-5, rtol=1e-4, what="deconv planes window")
 
 
 # ------------------------------------------------------------------------------------------ gather ops
