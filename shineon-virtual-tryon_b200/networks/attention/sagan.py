@@ -7,7 +7,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from .._engine_util import params_signature, require_cuda
+from .._engine_util import params_signature, require_cuda, side_run
 
 
 class SelfAttention(nn.Module):
@@ -56,15 +56,21 @@ class SelfAttention(nn.Module):
         C, Cq = self.chanel_in, self.chanel_in // 8
         g_qkv = ops.sagan_attention_bwd(qkv, self.gamma.detach(), g_out, Cq, _grad_of(self.gamma), beta_gamma=1.0)
         _, G = ops.instnorm_act(g_qkv, do_norm=False, want_f32=False, want_planes=True, prec=prec)  # f32 -> planes
-        for conv, c0, cn in ((self.query_conv, 0, Cq), (self.key_conv, Cq, Cq), (self.value_conv, 2 * Cq, C)):
-            ops.channel_sum(g_qkv, _grad_of(conv.bias), beta=1.0, coffset=c0)
-            ops.conv2d_wgrad(G, x_planes, _grad_of(conv.weight), Cout=cn, Cin=C, kh=1, kw=1, stride=1, pad=0, beta=1.0,
-                             g_coffset=c0)
+        def proj_wgrad():  # weight / bias gradients of the three projections: next to the input-gradient conv below
+            for conv, c0, cn in ((self.query_conv, 0, Cq), (self.key_conv, Cq, Cq), (self.value_conv, 2 * Cq, C)):
+                ops.channel_sum(g_qkv, _grad_of(conv.bias), beta=1.0, coffset=c0)
+                ops.conv2d_wgrad(G, x_planes, _grad_of(conv.weight), Cout=cn, Cin=C, kh=1, kw=1, stride=1, pad=0, beta=1.0,
+                                 g_coffset=c0)
+
+        from ..cpvton import unet as _unet
+
+        join = side_run(proj_wgrad, _unet.GRAD_READY_HOOK is None)
         sig = (params_signature(self), prec, "dgrad")
         if getattr(self, "_packed_dgrad", None) is None or self._packed_dgrad[0] != sig:
             w = torch.cat([self.query_conv.weight, self.key_conv.weight, self.value_conv.weight], 0)
             self._packed_dgrad = (sig, ops.PackedConv(w, None, stride=1, pad=0, prec=prec, transposed=True))
         g_x, _ = ops.conv2d(G, self._packed_dgrad[1], want_f32=True)
+        join()  # g_qkv / G / x_planes stay referenced until here
         return g_x
 
     def forward(self, x):

@@ -11,7 +11,7 @@ import torch
 from torch import nn
 
 from ... import ops
-from .._engine_util import fold_bn, params_signature, require_cuda
+from .._engine_util import side_run, fold_bn, params_signature, require_cuda
 from ..activation import Sine, Swish, act_name
 from ..attention.sagan import SelfAttention
 
@@ -458,13 +458,21 @@ class UnetSkipConnectionBlock(nn.Module):
         sub = pr["sub"]
         dc, uc = pr["downconv"], pr["upconv"]
         # ---- up path: norm/attn/act -> conv3x3
-        gc, G = self._finish_bwd(tp["up"], g1, g2, prec)
-        if uc.bias is not None:
-            ops.channel_sum(gc, _grad_of(uc.bias), beta=1.0)
-        ops.conv2d_wgrad(G, tp["u"], _grad_of(uc.weight), Cout=uc.out_channels, Cin=uc.in_channels, kh=3, kw=3, stride=1,
-                         pad=1, chan_map=pk["cmap_up"], beta=1.0)
+        # (weight / bias gradients on the auxiliary stream, see _engine_util.side_run; gc_* / G_* / tp stay referenced until
+        # the joins at the end.  With a gradient-ready hook installed -- eager data-parallel overlap -- everything stays on
+        # one stream so that "ready" keeps meaning "enqueued before this point".)
+        par = GRAD_READY_HOOK is None
+        gc_u, G_u = self._finish_bwd(tp["up"], g1, g2, prec)
+
+        def up_wgrad():
+            if uc.bias is not None:
+                ops.channel_sum(gc_u, _grad_of(uc.bias), beta=1.0)
+            ops.conv2d_wgrad(G_u, tp["u"], _grad_of(uc.weight), Cout=uc.out_channels, Cin=uc.in_channels, kh=3, kw=3,
+                             stride=1, pad=1, chan_map=pk["cmap_up"], beta=1.0)
+
+        join_u = side_run(up_wgrad, par)
         _ready(self.up_params())
-        g_u, _ = ops.conv2d(G, pk["up_dgrad"], want_f32=True)  # [N,2H,2W,Cin_up]
+        g_u, _ = ops.conv2d(G_u, pk["up_dgrad"], want_f32=True)  # [N,2H,2W,Cin_up]
         # ---- bilinear x2 + concat
         if sub is None:
             g_skip, _ = ops.upsample2x_cat_bwd(g_u, uc.in_channels, 0)
@@ -474,15 +482,19 @@ class UnetSkipConnectionBlock(nn.Module):
             g_skip, g_xp = ops.upsample2x_cat_bwd(g_u, c_skip, uc.in_channels - c_skip)
             g_child = sub.backward(g_xp, None, prec)
         # ---- down path: norm/attn/act -> conv4x4 s2
-        gc, G = self._finish_bwd(tp["down"], g_skip, g_child, prec)
-        if dc.bias is not None:
-            ops.channel_sum(gc, _grad_of(dc.bias), beta=1.0)
-        ops.conv2d_wgrad(G, tp["a_in"], _grad_of(dc.weight), Cout=dc.out_channels, Cin=dc.in_channels, kh=4, kw=4, stride=2,
-                         pad=1, mode=1 if pk["down_i2c"] is not None else 0, beta=1.0)
+        gc_d, G_d = self._finish_bwd(tp["down"], g_skip, g_child, prec)
+
+        def down_wgrad():
+            if dc.bias is not None:
+                ops.channel_sum(gc_d, _grad_of(dc.bias), beta=1.0)
+            ops.conv2d_wgrad(G_d, tp["a_in"], _grad_of(dc.weight), Cout=dc.out_channels, Cin=dc.in_channels, kh=4, kw=4,
+                             stride=2, pad=1, mode=1 if pk["down_i2c"] is not None else 0, beta=1.0)
+
+        join_d = side_run(down_wgrad, par)
         _ready(self.down_params())
-        if self.outermost:
-            return None
-        g_in, _ = pk["down_dgrad"](G, want_f32=True)
+        g_in = None if self.outermost else pk["down_dgrad"](G_d, want_f32=True)[0]
+        join_u()
+        join_d()
         return g_in
 
     precision = None  # ops.PRECISIONS name for a block used on its own (UnetGenerator passes its own)

@@ -895,7 +895,11 @@ _WGRAD_WS = {}
 
 def _workspace(nbytes, device, key="ws"):
     """Grow-only scratch buffer per (device, key): the C ABI never allocates, the caller owns the workspace."""
-    k = (str(device), key)
+    # one buffer per stream role (main / auxiliary): the weight-gradient branch of the backward runs on an auxiliary stream next to kernels that
+    # use the same kind of scratch on the main one (networks/_engine_util.side_run)
+    from .networks._engine_util import on_aux_stream
+
+    k = (str(device), key, on_aux_stream(device))
     buf = _WGRAD_WS.get(k)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
