@@ -41,6 +41,7 @@ def parse():
                                                          "levels are latency-bound, 16 clips measured 3 % fewer frames/s)")
     ap.add_argument("--fast", action="store_true", help="also report the bf16x3 / fp16 / bf16 modes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flow-warp", action="store_true", help="try-on workload: skip the secondary 5-frame flow-warp clip measurement")
     ap.add_argument("--no-graph", action="store_true", help="try-on workload: launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--workload", default="tryon", choices=["tryon", "train", "flow"],
                     help="tryon = BASELINE configs[2] (the headline; default); train = configs[4]: U-Net stage training step, "
@@ -671,6 +672,70 @@ TRYON_METRIC = "try-on frames/sec @256x192 (GMM warp + U-Net)"
 N_INPUT_SETS = 4  # distinct device-resident input sets cycled by the timed loop: 4 x 39 MB of frames > the 126 MB L2
 
 
+def flow_warp_clips(warp, dev, clips, steps, warmup, peak_tf):
+    """SURVEY 8d config 3, secondary form: the channel-stacked 5-frame U-Net of the reference's `--n_frames_total 5 --flow_warp`
+    recipe (ngf = int(64 (ln 5 + 1)) = 167, 50 input / 25 output channels), each frame blended with the previous try-on frame
+    warped by the clip's optical flow (Resample2d, four sequential blends: unet_mask_model.py:111-131), fed by the same GMM
+    warp per frame.  f32 device tensors in, f32 try-on frames out (the nn.Module surface); flows ~ N(0, 3 px)."""
+    import argparse
+
+    import torch
+
+    from shineon_virtual_tryon_b200.models.unet_mask_model import UnetMaskModel
+    from shineon_virtual_tryon_b200.networks.attention.sagan import SelfAttention
+
+    n = FRAMES_PER_CLIP
+    torch.manual_seed(421)
+    hp = argparse.Namespace(person_inputs=["agnostic", "densepose"], n_frames_total=n, n_frames_now=n, cloth_inputs=["cloth"], ngf=64,
+                            self_attn=True, num_attn=2, flow_warp=True, activation="gelu", is_train=False, grid_size=5,
+                            fine_height=H, fine_width=W)
+    tom5 = UnetMaskModel(hp).eval()
+    with torch.no_grad():
+        for m in tom5.modules():
+            if isinstance(m, SelfAttention):
+                m.gamma.uniform_(0.5, 1.5)
+    tom5 = tom5.to(dev)
+    g = torch.Generator().manual_seed(77)
+    person_gmm = torch.randn(clips * n, 22, H, W, generator=g).to(dev)
+    cloth = (torch.rand(clips * n, 3, H, W, generator=g) * 2 - 1).to(dev)
+    person_tom = torch.randn(clips, 7 * n, H, W, generator=g).to(dev)
+    flows = (torch.randn(clips, 2 * n, H, W, generator=g) * 3).to(dev)
+
+    def step():
+        wc = warp.warp(person_gmm, cloth, cloth)[0]
+        return tom5(person_tom, wc.view(clips, 3 * n, H, W), flows)[2]
+
+    graphed = True
+    with torch.no_grad():
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                out = step()
+            run = graph.replay
+        except RuntimeError:
+            torch.cuda.synchronize()
+            graphed, run = False, step
+        for _ in range(max(1, warmup)):
+            run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    gf_clip = 119.8 + n * 9.333  # SURVEY 8a U1 (n = 5, flow_warp) + G1-G4 per frame
+    return {"workload": "configs[2] secondary: 5 x (GMM + TPS warp) -> channel-stacked 5-frame U-Net (ngf 167) -> flow-warp blend "
+                        "(4 chained Resample2d), f32 device tensors in / out",
+            "clips_per_step": clips, "ms_per_step": ms, "clips_per_s": clips / (ms * 1e-3), "frames_per_s": clips * n / (ms * 1e-3),
+            "cuda_graph": graphed, "algorithmic_gflop_per_clip": gf_clip,
+            "frac_of_tensor_peak": gf_clip * 1e9 * clips / (ms * 1e-3) / 1e12 / peak_tf,
+            "parity": "tests/test_e2e_gpu.py (golden tom_flow5 from the reference's UnetMaskModel)"}
+
+
 def synth_raw_frames(frames, seed, pinned=True):
     """Decoded 8-bit frames as the reference's Dataset.__getitem__ receives them from PIL (channel-last)."""
     import torch
@@ -854,6 +919,12 @@ def run_b200(args, rank, world):
             for m, r in fast.items()}
         line["other_precisions"]["note"] = ("not parity-green at 1e-3 except bf16x3; measured error bounds in "
                                             "tests/test_e2e_gpu.py::test_other_precision_modes")
+    if world == 1 and not args.no_flow_warp:
+        # the metric names "(warp + U-Net + flow)": the flow-warp form of the clip, measured in the same run
+        del raw_sets, a, c, p
+        pipe._graphs.clear()
+        torch.cuda.empty_cache()
+        line["flow_warp_clips"] = flow_warp_clips(warp, dev, 8, max(5, args.steps // 2), args.warmup, peak_tf)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cfps, cores, sample, _ = cpu_tryon_fps(args.cpu_clips)

@@ -1,16 +1,25 @@
 """UnetMaskModel — CP-VTON Try-On Module (reference: models/unet_mask_model.py:27-326)."""
 import argparse
 import math
+import os
 
 import torch
 from torch import nn
 
 from .. import ops
 from ..networks import init_weights
+from ..networks._engine_util import side_run
 from ..networks.cpvton.unet import UnetGenerator
 from ..networks.flownet2.native_ops import Resample2d
 from ..networks.loss import VGGLoss
 from .base_model import BaseModel, get_and_cat_inputs, maybe_combine_frames_and_channels
+
+# VGG features of the target images on the auxiliary stream during the U-Net forward of a training step.  Off: measured on
+# B200 at batch 4, two half-batch passes through the slices (targets early, prediction later) cost more than the overlap
+# returns -- 5.69 ms against 5.43 ms for the one batched pass over [prediction; target] (profiles/r02_concurrency.md).
+PARALLEL_VGG_TARGET = os.environ.get("SHINEON_VGG_TARGET_PARALLEL", "0") == "1"
+# the backward's packed operands prepared on the auxiliary stream while the losses are computed
+PREPACK_BACKWARD = os.environ.get("SHINEON_PREPACK_BACKWARD", "1") != "0"
 
 
 class UnetMaskModel(BaseModel):
@@ -120,6 +129,17 @@ class UnetMaskModel(BaseModel):
         person = get_and_cat_inputs(batch, hp.person_inputs).contiguous()
         cloths = get_and_cat_inputs(batch, hp.cloth_inputs).contiguous()
         dev = person.device
+        # the perceptual loss's target features need nothing from the U-Net: on the auxiliary stream, next to the forward
+        # pass (batch 4 leaves most SMs idle in the lower U-Net levels); joined where the loss reads them
+        used = [(n - 1, 0.5 if n > 1 else 1.0)] + ([(n - 2, 0.5)] if n > 1 else [])
+        tgts = {f: im[:, 3 * f:3 * f + 3].contiguous() for f, _ in used}
+        tgt_feats = {}
+
+        def target_branch():
+            for f, t in tgts.items():
+                tgt_feats[f] = self.criterionVGG.target_features(t)
+
+        join_targets = side_run(target_branch) if PARALLEL_VGG_TARGET else (lambda: None)
         saved_prec = self.unet.precision
         if self.unet.precision is None:
             self.unet.precision = "bf16x3"
@@ -128,6 +148,8 @@ class UnetMaskModel(BaseModel):
                 (person, cloths), ops.resolve_precision(self.unet.precision))
         finally:
             self.unet.precision = saved_prec
+        # the backward's packed operands, on the auxiliary stream while the compose / loss kernels run
+        join_packs = side_run(self.unet.prepack_backward) if (PREPACK_BACKWARD and not val) else (lambda: None)
         B, H, W, Cout = out.shape
         p_rendereds = torch.empty(B, 3 * n, H, W, device=dev)
         tryon_masks = torch.empty(B, n, H, W, device=dev)
@@ -145,15 +167,15 @@ class UnetMaskModel(BaseModel):
 
         # ---- losses (unet_mask_model.py:173-191): last frame (and the one before it, each weighted 0.5, when n > 1)
         acc = torch.zeros(8, device=dev)  # l1, vgg, mask_l1, flow_mask, then per-frame curr/prev copies for the log
-        used = [(n - 1, 0.5 if n > 1 else 1.0)] + ([(n - 2, 0.5)] if n > 1 else [])
         grad = not val
+        join_targets()
         g_tryon = [torch.zeros(B, 3, H, W, device=dev) for _ in range(n)] if grad else [None] * n
         g_mask = [None] * n
         for f, w in used:
             pt = p_tryons[:, 3 * f:3 * f + 3].contiguous()
-            tgt = im[:, 3 * f:3 * f + 3].contiguous()
+            tgt = tgts[f]
             ops.l1_loss(pt, tgt, acc[0:1], g_tryon[f], weight=w, accumulate_grad=True)
-            self.criterionVGG.loss_and_grad(pt, tgt, acc[1:2], g_tryon[f], scale=w)
+            self.criterionVGG.loss_and_grad(pt, tgt, acc[1:2], g_tryon[f], scale=w, y_feats=tgt_feats.get(f))
             tm = tryon_masks[:, f:f + 1].contiguous()
             if grad:
                 g_mask[f] = torch.empty(B, 1, H, W, device=dev)
@@ -175,6 +197,7 @@ class UnetMaskModel(BaseModel):
                                          g_flow_masks=g_fm if f == n - 1 else None, want_g_warped=warped[f] is not None)
                 if warped[f] is not None:  # p_tryon of frame f-1 also feeds frame f through Resample2d
                     ops.resample2d_bwd(prev_gen[f], flows_c[f], gw, grad_in1=g_tryon[f - 1])
+            join_packs()
             self.unet.backward(g_out)
         if not val:
             self.global_step += 1

@@ -48,6 +48,14 @@ class SelfAttention(nn.Module):
         z, _ = ops.sagan_attention(qkv, x_f32, self.gamma.detach(), self.chanel_in // 8, want_f32=True, want_planes=False)
         return z, qkv
 
+    def packed_dgrad(self, prec):
+        """The stacked q/k/v projection weights as the input-gradient conv's operand (re-packed when the weights change)."""
+        sig = (params_signature(self), prec, "dgrad")
+        if getattr(self, "_packed_dgrad", None) is None or self._packed_dgrad[0] != sig:
+            w = torch.cat([self.query_conv.weight, self.key_conv.weight, self.value_conv.weight], 0)
+            self._packed_dgrad = (sig, ops.PackedConv(w, None, stride=1, pad=0, prec=prec, transposed=True))
+        return self._packed_dgrad[1]
+
     def backward(self, x_planes, qkv, g_out, prec):
         """g_out = dL/dz (f32 NHWC).  Accumulates gamma / q,k,v weight and bias gradients; returns the part of dL/dx that
         flows through the projections (the residual branch contributes g_out itself, added by the caller)."""
@@ -65,11 +73,7 @@ class SelfAttention(nn.Module):
         from ..cpvton import unet as _unet
 
         join = side_run(proj_wgrad, _unet.GRAD_READY_HOOK is None)
-        sig = (params_signature(self), prec, "dgrad")
-        if getattr(self, "_packed_dgrad", None) is None or self._packed_dgrad[0] != sig:
-            w = torch.cat([self.query_conv.weight, self.key_conv.weight, self.value_conv.weight], 0)
-            self._packed_dgrad = (sig, ops.PackedConv(w, None, stride=1, pad=0, prec=prec, transposed=True))
-        g_x, _ = ops.conv2d(G, self._packed_dgrad[1], want_f32=True)
+        g_x, _ = ops.conv2d(G, self.packed_dgrad(prec), want_f32=True)
         join()  # g_qkv / G / x_planes stay referenced until here
         return g_x
 

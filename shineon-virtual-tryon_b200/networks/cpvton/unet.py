@@ -71,6 +71,19 @@ class UnetGenerator(nn.Module):
         self._train_prec = prec
         return self.model.run((x0.contiguous(), None if x1 is None else x1.contiguous()), prec, train=True)
 
+    def prepack_backward(self):
+        """Packs the backward pass's conv operands (flipped / transposed 16-bit weights of every block and attention layer)
+        ahead of time; a training step calls it on the auxiliary stream while the losses are being computed, so the first
+        backward after an optimiser step does not stop for ~20 small pack launches.  backward() finds them cached."""
+        prec = self._train_prec
+        blk = self.model
+        while blk is not None:
+            blk._pack_bwd(prec)
+            for a in (blk._parts["attn_up"], blk._parts["attn_down"]):
+                if a is not None:
+                    a.packed_dgrad(prec)
+            blk = blk._parts["sub"]
+
     def backward(self, grad_out_nhwc):
         """Accumulates dL/dparam into every parameter's .grad (allocated on first use) given dL/d(output) as f32 NHWC
         [N,H,W,output_nc].  The input gradient is not produced (the U-Net's inputs are data)."""

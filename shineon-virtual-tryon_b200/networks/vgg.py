@@ -158,19 +158,29 @@ class VGGLoss(nn.Module):
                           "FILE (torchvision vgg19 state_dict) or load a checkpoint that contains criterionVGG.*", stacklevel=3)
             self._warned = True
 
-    def loss_and_grad(self, x, y, loss, grad_x, scale=1.0):
+    def target_features(self, y):
+        """The five feature maps of the (detached) target images, f32 NHWC: they do not depend on the network being trained,
+        so a training step may compute them next to its forward pass and hand them to loss_and_grad(y_feats=...)."""
+        prec = ops.resolve_precision(self.precision if self.precision is not None else "bf16x3")
+        return self.vgg.run(y.contiguous(), prec, keep=False)[0]
+
+    def loss_and_grad(self, x, y, loss, grad_x, scale=1.0, y_feats=None):
         """loss[0] += scale * VGGLoss(x, y); grad_x (f32 NCHW [B,3,H,W], None = value only) += scale * dVGGLoss/dx.
-        x, y: f32 NCHW CUDA images."""
+        x, y: f32 NCHW CUDA images.  y_feats = target_features(y) computed earlier (y is then ignored): only x goes
+        through the slices here; the values are the same either way (every image is convolved on its own)."""
         prec = ops.resolve_precision(self.precision if self.precision is not None else "bf16x3")
         B = x.shape[0]
-        feats, tape = self.vgg.run(torch.cat([x, y], 0).contiguous(), prec, keep=True)
+        if y_feats is None:
+            feats, tape = self.vgg.run(torch.cat([x, y], 0).contiguous(), prec, keep=True)
+        else:
+            feats, tape = self.vgg.run(x.contiguous(), prec, keep=True)
         ids = list(range(len(feats))) if self.layids is None else list(self.layids)
         # L1 terms: features of x are the first B images of the batch, the targets the last B (contiguous halves)
         g_feat = {}
         for i in ids:
             f = feats[i]
             g = torch.empty_like(f[:B]) if grad_x is not None else None
-            ops.l1_loss(f[:B], f[B:], loss, g, weight=scale * self.weights[i], beta_loss=1.0)
+            ops.l1_loss(f[:B], f[B:] if y_feats is None else y_feats[i], loss, g, weight=scale * self.weights[i], beta_loss=1.0)
             g_feat[id(f)] = g
         if grad_x is None:
             return loss
