@@ -18,8 +18,9 @@ from .base_model import BaseModel, get_and_cat_inputs, maybe_combine_frames_and_
 # B200 at batch 4, two half-batch passes through the slices (targets early, prediction later) cost more than the overlap
 # returns -- 5.69 ms against 5.43 ms for the one batched pass over [prediction; target] (profiles/r02_concurrency.md).
 PARALLEL_VGG_TARGET = os.environ.get("SHINEON_VGG_TARGET_PARALLEL", "0") == "1"
-# the backward's packed operands prepared on the auxiliary stream while the losses are computed
-PREPACK_BACKWARD = os.environ.get("SHINEON_PREPACK_BACKWARD", "1") != "0"
+# the backward's packed operands prepared on the auxiliary stream while the losses are computed: measured 5.57 ms against
+# 5.48 ms without (the ~20 pack launches then compete with the loss kernels instead of filling gaps of the backward): off
+PREPACK_BACKWARD = os.environ.get("SHINEON_PREPACK_BACKWARD", "0") == "1"
 
 
 class UnetMaskModel(BaseModel):
