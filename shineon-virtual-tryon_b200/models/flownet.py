@@ -44,6 +44,14 @@ class FlowNet(nn.Module):
                 return flow.view(b, n, 2, h, w), conf.view(b, n, 1, h, w)
             return self.compute_flow_and_conf(input_A, input_B, lane)
 
+    def lane_stream(self, lane, device):
+        """The stream forward(..., lane=lane) issues its work on (callers queue the download of a lane's result there)."""
+        key = (str(torch.device(device)), 1 + lane % max(1, self.lanes))
+        ls = self._lane_streams.get(key)
+        if ls is None:
+            ls = self._lane_streams[key] = torch.cuda.Stream(device)
+        return ls
+
     def join_lanes(self):
         """Makes the caller's stream wait for every forward issued on a compute lane."""
         cur = torch.cuda.current_stream()
@@ -58,9 +66,7 @@ class FlowNet(nn.Module):
         key = (im1.data_ptr(), im2.data_ptr(), tuple(im1.shape), lane_id)
         if lane_id:
             cur = torch.cuda.current_stream(im1.device)
-            ls = self._lane_streams.get((str(im1.device), lane_id))
-            if ls is None:
-                ls = self._lane_streams[(str(im1.device), lane_id)] = torch.cuda.Stream(im1.device)
+            ls = self.lane_stream(lane, im1.device)
             ls.wait_stream(cur)
             with torch.cuda.stream(ls):
                 return self._replay(key, im1, im2, lane_id)
