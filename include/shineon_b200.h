@@ -137,6 +137,12 @@ int shineon_correlation_fwd(const float* in1, const float* in2, float* out, int 
  * kernel gathers the (2*(maxd/s2)+1)^2 displacements, scales by 1/C and zero-fills out-of-image taps. */
 int shineon_correlation_gather(const float* full, float* out, int B, int C, int H, int W, int pad_size,
                                int max_displacement, int stride2, shineon_stream_t stream);
+/* The same gather writing act(cost volume) as NHWC 16-bit planes [B,H,W,y_cstride] (y_hi / y_lo point at the first channel
+ * of the consumer's channel window; channels D*D .. pad8(D*D) are written as zeros) -- FlowNetC.py:86-88: corr ->
+ * corr_activation -> cat, without the NCHW f32 cost volume in between. */
+int shineon_correlation_gather_planes(const float* full, void* y_hi, void* y_lo, int y_cstride, int B, int C, int H, int W,
+                                      int pad_size, int max_displacement, int stride2, int act, float act_param,
+                                      int plane_fmt, shineon_stream_t stream);
 int shineon_correlation_bwd(const float* in1, const float* in2, const float* grad_out, float* grad_in1,
                             float* grad_in2, int B, int C, int H, int W, int pad_size, int kernel_size,
                             int max_displacement, int stride1, int stride2, shineon_stream_t stream);

@@ -84,6 +84,7 @@ SIGNATURES = {
                                       C.POINTER(c_i), C.POINTER(c_i), C.POINTER(c_i)],
     "shineon_correlation_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_correlation_gather": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "shineon_correlation_gather_planes": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_p],
     "shineon_correlation_bwd": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_pack_conv_weight": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_f, c_p],
     "shineon_pack_deconv4x4s2_weight": [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_i, c_f, c_p],

@@ -31,25 +31,28 @@ inline int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-// ---------------------------------------------------------------- programmatic dependent launch (optional, off)
-// Every kernel of the library starts with pdl_grid_sync() and is launched through klaunch().  With SHINEON_PDL=1 the
-// launches carry the programmatic stream-serialisation attribute: the next kernel of the stream (or of the captured
-// graph) is scheduled while this one still runs - its CTAs become resident as SMs free up and block in
-// griddepcontrol.wait until this grid has completed and flushed.  Ordering is unchanged: nothing before the wait touches
-// memory, and the trigger comes after the wait, so at most one dependent grid is ever resident ahead of time (a chain
-// A -> B -> C stays transitive: C passes its wait only after B completed, and B only after it passed its own wait on A).
-// Measured on B200 (profiles/r02_pdl.md): parity suite green, but the graph-replayed steps got SLOWER (try-on 11.93 ->
-// 12.44 ms, training 6.10 -> 6.21 ms, FlowNet2 8.50 -> 8.43 ms), so the default is plain stream ordering; without the attribute
-// the two instructions are no-ops.
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library starts with pdl_grid_sync() (griddepcontrol.wait: returns once every grid this one depends
+// on has completed and flushed; a no-op for a launch without the attribute) and is launched through klaunch(), which adds
+// the programmatic stream-serialisation attribute.  The next kernel of the stream (or of the captured graph) is then set
+// up -- launch processing, CTA rasterisation -- while its predecessor drains, instead of after it.  Ordering is unchanged:
+// nothing before the wait touches memory, and without an explicit trigger a dependent grid becomes resident only when all
+// CTAs of its predecessor have exited (a chain A -> B -> C stays transitive: C passes its wait only after B completed, and B
+// only after it passed its own wait on A).  Measured on B200 (profiles/r02_pdl.md): try-on step 12.03 -> 11.84 ms, FlowNet2
+// 5.58 -> 5.52 ms, training step 5.47 -> 5.44 ms.  The variant that also triggers early (griddepcontrol.launch_dependents
+// right after the wait, -DSHINEON_PDL_EARLY_TRIGGER) makes the successor resident next to the running persistent conv CTAs
+// and was 4 % SLOWER on the try-on step.  SHINEON_PDL=0 launches with plain stream ordering.
 __device__ __forceinline__ void pdl_grid_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef SHINEON_PDL_EARLY_TRIGGER  // the measured-slower variant: successor resident while this grid still runs
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
 
 inline bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("SHINEON_PDL");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
   }();
   return on;
 }

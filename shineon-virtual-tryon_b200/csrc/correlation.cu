@@ -96,6 +96,51 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The same gather for a consumer that wants NHWC 16-bit planes (FlowNetC: LeakyReLU(cost volume) is a channel window of
+// conv3_1's concat input).  One warp per output pixel: the pixel's row of the all-pairs matrix (H*W floats, L2-resident
+// right after the GEMM) is read by the whole warp, and the D*D displacement values leave as contiguous 16-byte chunks of
+// the pixel's channel vector with the activation and the hi/lo split applied -- instead of an NCHW f32 cost volume
+// (element stride H*W between a pixel's displacements) that a second kernel re-reads, transposes and splits.
+template <int FMT>
+__global__ void __launch_bounds__(256)
+    correlation_gather_planes_kernel(const float* __restrict__ full, plane_t* __restrict__ yh, plane_t* __restrict__ yl,
+                                     int C, int H, int W, int shift, int drad, int s2, int cstride, int cpad, int act,
+                                     float act_param, long pixels) {
+  pdl_grid_sync();
+  const int D = 2 * drad + 1, DD = D * D, P = H * W;
+  const float inv = 1.f / (float)C;
+  const int lane = threadIdx.x & 31;
+  for (long wp = (long)blockIdx.x * 8 + (threadIdx.x >> 5); wp < pixels; wp += (long)gridDim.x * 8) {
+    const int p = (int)(wp % P);
+    const int y = p / W, x = p - y * W;
+    const int y1 = y + shift, x1 = x + shift;
+    const bool ok1 = y1 >= 0 && y1 < H && x1 >= 0 && x1 < W;
+    const float* row = full + ((wp - p) + (long)(y1 * W + x1)) * P;  // row of pixel (b, y1, x1)
+    for (int ch = lane; ch < (cpad >> 3); ch += 32) {
+      float v[8];
+      int d = ch * 8;
+      int tj = d / D, ti = d - tj * D;
+#pragma unroll
+      for (int j = 0; j < 8; ++j, ++d) {
+        float t = 0.f;
+        if (d < DD) {
+          const int y2 = y1 + (tj - drad) * s2, x2 = x1 + (ti - drad) * s2;
+          if (ok1 && y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) t = __ldg(row + (y2 * W + x2)) * inv;
+          t = apply_act(t, act, act_param);
+        }
+        v[j] = t;
+        if (++ti == D) { ti = 0; ++tj; }
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split16x2(v[2 * j], v[2 * j + 1], FMT, hi[j], lo[j]);
+      const long o = wp * cstride + ch * 8;
+      *reinterpret_cast<uint4*>(yh + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (yl) *reinterpret_cast<uint4*>(yl + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
 // Backward, one thread per input element, loops follow correlation_cuda_kernel.cu:151-241 / :244-334
 // (integer divisions truncate toward zero exactly like the reference).
 __global__ void __launch_bounds__(256)
@@ -195,6 +240,31 @@ extern "C" int shineon_correlation_gather(const float* full, float* out, int B, 
   klaunch(correlation_gather_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, full, out, C, H, W, max_displacement - pad_size,
                                                                           g.drad, stride2, total);
   return after_launch("correlation_gather_kernel");
+}
+
+extern "C" int shineon_correlation_gather_planes(const float* full, void* y_hi, void* y_lo, int y_cstride, int B, int C, int H,
+                                                 int W, int pad_size, int max_displacement, int stride2, int act, float act_param,
+                                                 int plane_fmt, shineon_stream_t stream) {
+  SHINEON_REQUIRE(full && y_hi, "correlation_gather_planes: null pointer");
+  SHINEON_REQUIRE(plane_fmt == SHINEON_FMT_BF16 || plane_fmt == SHINEON_FMT_FP16, "correlation_gather_planes: plane_fmt %d", plane_fmt);
+  CorrGeom g;
+  if (!corr_geom(C, H, W, pad_size, 1, max_displacement, 1, stride2, g))
+    return fail(SHINEON_ERR_ARG, "correlation_gather_planes: bad geometry");
+  SHINEON_REQUIRE(g.outH == H && g.outW == W, "correlation_gather_planes: needs pad_size == max_displacement (output size == input size)");
+  const int cpad = (g.outC + 7) / 8 * 8;
+  SHINEON_REQUIRE(y_cstride >= cpad && y_cstride % 8 == 0, "correlation_gather_planes: y_cstride %d too small for %d channels / not a multiple of 8", y_cstride, g.outC);
+  SHINEON_REQUIRE((reinterpret_cast<uintptr_t>(y_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_lo) & 15) == 0, "correlation_gather_planes: planes must be 16-byte aligned");
+  const long pixels = (long)B * H * W;
+  if (pixels == 0) return SHINEON_OK;
+  long blocks = (pixels + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (plane_fmt == SHINEON_FMT_FP16)
+    klaunch(correlation_gather_planes_kernel<SHINEON_FMT_FP16>, (int)blocks, 256, 0, (cudaStream_t)stream, full, (plane_t*)y_hi,
+            (plane_t*)y_lo, C, H, W, max_displacement - pad_size, g.drad, stride2, y_cstride, cpad, act, act_param, pixels);
+  else
+    klaunch(correlation_gather_planes_kernel<SHINEON_FMT_BF16>, (int)blocks, 256, 0, (cudaStream_t)stream, full, (plane_t*)y_hi,
+            (plane_t*)y_lo, C, H, W, max_displacement - pad_size, g.drad, stride2, y_cstride, cpad, act, act_param, pixels);
+  return after_launch("correlation_gather_planes_kernel");
 }
 
 extern "C" int shineon_correlation_bwd(const float* in1, const float* in2, const float* grad_out, float* grad_in1,

@@ -260,8 +260,8 @@ class FlowNetC(_Net):
         join()
         c3b = tower_b["c3"]
         in31 = self._concat(B, H // 8, W // 8, (32, 441), prec, dev)
-        corr = ops.correlation_planes(c3a, c3b, 256, 20, 20, 2)  # tensor-core cost volume straight from the planes
-        ops.nchw_to_planes(corr, act="leaky", act_param=LEAK, out=in31.window(1))  # corr_activation
+        # tensor-core cost volume straight from the planes; corr_activation and the layout of conv3_1's input in the gather
+        ops.correlation_planes(c3a, c3b, 256, 20, 20, 2, out_planes=in31.window(1), act="leaky", act_param=LEAK)
         self._c(prec, "conv_redir", c3a, out=in31.window(0))
         c31 = self._c(prec, "conv3_1", in31.buf, out=cat3.window(0), segs=in31.seg)
         c4 = self._c(prec, "conv4_1", self._c(prec, "conv4", c31), out=cat4.window(0))

@@ -233,10 +233,11 @@ def correlation_fwd(in1, in2, pad_size, kernel_size, max_displacement, stride1, 
     return out
 
 
-def correlation_planes(f1, f2, C, pad_size, max_displacement, stride2):
+def correlation_planes(f1, f2, C, pad_size, max_displacement, stride2, out_planes=None, act=None, act_param=0.0):
     """Tensor-core cost volume (kernel_size 1, stride1 1, pad == max_displacement): f1, f2 are Planes [B,H,W,C]
     (e.g. straight out of the conv3 layers).  One per-image tcgen05 GEMM (f2 plays the weights) + a gather.
-    Returns f32 NCHW [B, D*D, H, W]."""
+    Returns f32 NCHW [B, D*D, H, W]; with out_planes (a Planes / channel window of >= D*D channels) the gather writes
+    act(cost volume) there as NHWC planes instead and out_planes is returned."""
     assert f1.prec == f2.prec and f1.cpad == f2.cpad and f1.cstride == f1.cpad and f2.cstride == f2.cpad
     B, H, W = f1.N, f1.H, f1.W
     P = H * W
@@ -246,6 +247,13 @@ def correlation_planes(f1, f2, C, pad_size, max_displacement, stride2):
     pc.cin_pad, pc.w_hi, pc.w_lo, pc.bias, pc.acc_scale, pc.transposed, pc.per_image = f2.cpad, f2.hi, f2.lo, None, 1.0, False, True
     full, _ = conv2d(f1, pc, want_f32=True)  # [B,H,W,P]
     D = 2 * (max_displacement // stride2) + 1
+    if out_planes is not None:
+        assert out_planes.N == B and out_planes.H == H and out_planes.W == W and out_planes.C >= D * D and out_planes.fmt == f1.fmt
+        check(_lib.load().shineon_correlation_gather_planes(_p(full), out_planes._ptr(out_planes.hi), out_planes._ptr(out_planes.lo),
+                                                            out_planes.cstride, B, C, H, W, pad_size, max_displacement, stride2,
+                                                            ACT[act], float(act_param), out_planes.fmt, _stream()),
+              "shineon_correlation_gather_planes")
+        return out_planes
     out = torch.empty(B, D * D, H, W, dtype=torch.float32, device=full.device)
     check(_lib.load().shineon_correlation_gather(_p(full), _p(out), B, C, H, W, pad_size, max_displacement, stride2,
                                                  _stream()), "shineon_correlation_gather")

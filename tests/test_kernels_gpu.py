@@ -349,6 +349,17 @@ def test_correlation(ops, cfg):
     if k == 1 and s1 == 1 and pad == maxd:
         got_tc = ops.correlation_fwd(a.cuda(), b.cuda(), pad, k, maxd, s1, s2, tensor_cores=True)
         assert_close(got_tc, want, atol=1e-5, rtol=1e-4, what="correlation fwd (tcgen05 GEMM + gather)")
+        # the gather writing LeakyReLU(cost volume) as NHWC planes into a channel window (what FlowNetC consumes) must hold
+        # exactly the planes the two-kernel route (NCHW f32 cost volume -> nchw_to_planes) produces, and nothing outside
+        pa, pb = ops.nchw_to_planes(a.cuda()), ops.nchw_to_planes(b.cuda())
+        DD = got_tc.shape[1]
+        cat = ops.Planes(2, H, W, 64 + ops.cpad64(DD), device="cuda", cpad=64 + ops.cpad64(DD))
+        cat.hi.zero_(); cat.lo.zero_()
+        ops.correlation_planes(pa, pb, C, pad, maxd, s2, out_planes=cat.window(64, DD), act="leaky", act_param=0.1)
+        ref = ops.nchw_to_planes(ops.correlation_planes(pa, pb, C, pad, maxd, s2), act="leaky", act_param=0.1)
+        torch.cuda.synchronize()
+        assert torch.equal(cat.hi[..., 64:64 + DD], ref.hi[..., :DD]) and torch.equal(cat.lo[..., 64:64 + DD], ref.lo[..., :DD])
+        assert (cat.hi[..., :64] == 0).all() and (cat.hi[..., 64 + DD:] == 0).all() and (cat.lo[..., 64 + DD:] == 0).all()
     if H * W <= 120:
         go = torch.randn(want.shape, generator=g)
         w1, w2 = fo.correlation_bwd(a, b, go, pad, k, maxd, s1, s2)
