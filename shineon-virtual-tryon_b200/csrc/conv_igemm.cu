@@ -49,7 +49,9 @@ struct ConvArgs {
   int stage_off;     // byte offset (from the 1024-aligned tile base) of the epilogue transpose buffers, < 0 = direct stores
   int n_tiles, total_tiles;  // channel tiles per pixel tile, pixel tiles * channel tiles
   int w_per_image;           // 1: the B operand is a [N][Cout][K] batch indexed by the tile's image (needs nb == 1)
-  // ConvTranspose2d(4, 2, 1) as ONE launch: the four output-parity phases (py, px) are an extra, slowest tile dimension.
+  // ConvTranspose2d(4, 2, 1) as ONE launch: the four output-parity phases (py, px) are an extra tile dimension (tile order:
+  // channel tile, then phase, then pixel tile -- with the phase slowest, FlowNetFusion's deconv0 re-read its 201 MB input from
+  // DRAM once per phase: 600 MB per launch under ncu, profiles/r02_late_kernels.md).
   // Phase tiles read the weight set [phase] of a [4][Cout][2*2][cin_pad] batch, pad (1 - py, 1 - px) and write the output
   // lattice (2*oh + py, 2*ow + px).  (Four launches of 8-32 CTAs each left the small pyramid levels of FlowNet2 and the
   // training step's down-conv input gradients on a sliver of the chip.)
@@ -282,9 +284,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int nt = tile % a.n_tiles;
         int mt = tile / a.n_tiles;
         int pad_h = a.pad_h, pad_w = a.pad_w, phz = 0;
-        if (a.phases > 1) {
-          phz = mt / a.phase_tiles;
-          mt -= phz * a.phase_tiles;
+        if (a.phases > 1) {  // phase fastest: the four phases of a pixel tile run on neighbouring CTAs and share its input in L2
+          phz = mt & 3;
+          mt >>= 2;
           pad_h = 1 - (phz >> 1);
           pad_w = 1 - (phz & 1);
         }
@@ -396,8 +398,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       int mt = tile / a.n_tiles;
       int oh_off = a.oh_off, ow_off = a.ow_off;
       if (a.phases > 1) {
-        const int phz = mt / a.phase_tiles;
-        mt -= phz * a.phase_tiles;
+        const int phz = mt & 3;
+        mt >>= 2;
         oh_off = phz >> 1;
         ow_off = phz & 1;
       }
