@@ -14,6 +14,8 @@ from ..networks.flownet2.nets import FlowNet2
 
 
 class FlowNet(nn.Module):
+    MAX_GRAPHS = 8  # captured forwards kept (one per input-buffer pair and lane)
+
     def __init__(self, checkpoint=None):
         super().__init__()
         self.flowNet = FlowNet2()
@@ -77,8 +79,8 @@ class FlowNet(nn.Module):
 
         ent = self._graphs.get(key)
         if ent is None:
-            if len(self._graphs) >= 4:
-                self._graphs.clear()
+            while len(self._graphs) >= self.MAX_GRAPHS:
+                self._graphs.pop(next(iter(self._graphs)))  # oldest capture first
             nets.CONCAT_LANE[0] = lane_id  # concurrent forwards keep separate concat buffers
             try:
                 for _ in range(2):  # weight packing / allocator warm-up outside the capture
@@ -89,7 +91,10 @@ class FlowNet(nn.Module):
                     out = self._compute_flow_and_conf(im1, im2)
             finally:
                 nets.CONCAT_LANE[0] = 0
-            ent = self._graphs[key] = (graph, out)
+            # the graph holds raw pointers into the sub-networks' cached concat buffers: keep those tensors alive with it
+            # (the caches drop their entries when the batch size / resolution changes)
+            keep = [c for m in self.flowNet.modules() for c in m.__dict__.get("_cat_cache", {}).values()]
+            ent = self._graphs[key] = (graph, out, keep)
         ent[0].replay()
         return ent[1]
 
