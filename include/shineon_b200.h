@@ -363,6 +363,11 @@ int shineon_flownet_normalize(const float* inputs, float* x, double* ws, int B, 
  * times `mul`; dst f32 NCHW [B,2,4h,4w]. */
 int shineon_upsample4x_flow(const float* src, int src_cstride, float* dst, int B, int h, int w, float mul,
                             int bilinear, shineon_stream_t stream);
+/* `upsampled_flow*` = ConvTranspose2d(2, 2, 4, 2, 1) of a predicted flow (FlowNetC.py:59-62): flow f32 NHWC [B,h,w,flow_cstride]
+ * (first two channels), weight f32 [2,2,4,4] (the module's own layout), bias [2] or NULL -> both channels of the consumer's
+ * channel window, NHWC 16-bit planes [B,2h,2w,y_cstride] (y_hi / y_lo at the window's first channel). */
+int shineon_flow_deconv4x4s2_planes(const float* flow, int flow_cstride, const float* weight, const float* bias, void* y_hi,
+                                    void* y_lo, int y_cstride, int B, int h, int w, int plane_fmt, shineon_stream_t stream);
 /* FlowNetS input: out [B,12,H,W] = [x | Resample2d(x[:,3:6], flow) | flow/div_flow | ChannelNorm(x[:,:3]-resampled)]. */
 int shineon_flownet_warp_concat(const float* x, const float* flow, float* out, int B, int H, int W, float div_flow,
                                 shineon_stream_t stream);

@@ -113,6 +113,7 @@ SIGNATURES = {
     "shineon_linear_tanh": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_flownet_normalize": [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p],
     "shineon_upsample4x_flow": [c_p, c_i, c_p, c_i, c_i, c_i, c_f, c_i, c_p],
+    "shineon_flow_deconv4x4s2_planes": [c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p],
     "shineon_flownet_warp_concat": [c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_p],
     "shineon_flownet_fusion_concat": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
     "shineon_bilinear_resize": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p],

@@ -197,6 +197,51 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// `upsampled_flow*`: ConvTranspose2d(2, 2, 4, 2, 1) on a predicted flow (FlowNetC.py:59-62, FlowNetS / SD / Fusion alike).
+// Two channels in, two out: 16 MACs per output value -- on the tensor-core conv this was a launch over a 64-channel padded
+// operand plus a f32 -> planes conversion of the flow in front of it, 18 times per FlowNet2 forward.  One thread per output
+// pixel reads the (at most) 2 x 2 contributing flow vectors and writes both channels of the consumer's concat window as
+// 16-bit hi/lo planes.  out[2*iy - 1 + ky][2*ix - 1 + kx][co] += in[iy][ix][ci] * w[ci][co][ky][kx].
+template <int FMT>
+__global__ void __launch_bounds__(256)
+    flow_deconv4x4s2_planes_kernel(const float* __restrict__ flow, int flow_cstride, const float* __restrict__ weight,
+                                   const float* __restrict__ bias, plane_t* __restrict__ yh, plane_t* __restrict__ yl,
+                                   int cstride, int h, int w, long total) {
+  pdl_grid_sync();
+  __shared__ float s_w[64];  // [ci][co][ky][kx]
+  if (threadIdx.x < 64) s_w[threadIdx.x] = __ldg(weight + threadIdx.x);
+  __syncthreads();
+  const float b0 = bias ? __ldg(bias) : 0.f, b1 = bias ? __ldg(bias + 1) : 0.f;
+  const int W2 = 2 * w, H2 = 2 * h;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(e % W2), oy = (int)((e / W2) % H2);
+    const long b = e / ((long)W2 * H2);
+    float a0 = b0, a1 = b1;
+    const int iy_hi = (oy + 1) >> 1, ix_hi = (ox + 1) >> 1;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int iy = iy_hi - dy, ky = oy + 1 - 2 * iy;  // ky in {0,1} + 2*dy
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ix = ix_hi - dx, kx = ox + 1 - 2 * ix;
+        if (ix < 0 || ix >= w) continue;
+        const float* src = flow + ((b * h + iy) * w + ix) * flow_cstride;
+        const float v0 = __ldg(src), v1 = __ldg(src + 1);
+        const int t = ky * 4 + kx;
+        a0 = fmaf(v0, s_w[t], a0);            // ci 0, co 0
+        a0 = fmaf(v1, s_w[32 + t], a0);       // ci 1, co 0
+        a1 = fmaf(v0, s_w[16 + t], a1);       // ci 0, co 1
+        a1 = fmaf(v1, s_w[48 + t], a1);       // ci 1, co 1
+      }
+    }
+    uint32_t hi, lo;
+    split16x2(a0, a1, FMT, hi, lo);
+    *reinterpret_cast<uint32_t*>(yh + e * cstride) = hi;
+    if (yl) *reinterpret_cast<uint32_t*>(yl + e * cstride) = lo;
+  }
+}
+
 static inline int blocks_for(long total) {
   long b = (total + 255) / 256;
   return (int)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
@@ -263,4 +308,21 @@ extern "C" int shineon_bilinear_resize(const float* x, float* y, int BC, int Hi,
   klaunch(bilinear_resize_kernel, blocks_for(total), 256, 0, (cudaStream_t)stream, x, y, Hi, Wi, Ho, Wo, (float)Hi / (float)Ho,
                                                                             (float)Wi / (float)Wo, mul, total);
   return after_launch("bilinear_resize_kernel");
+}
+
+extern "C" int shineon_flow_deconv4x4s2_planes(const float* flow, int flow_cstride, const float* weight, const float* bias,
+                                               void* y_hi, void* y_lo, int y_cstride, int B, int h, int w, int plane_fmt,
+                                               shineon_stream_t stream) {
+  SHINEON_REQUIRE(flow && weight && y_hi && flow_cstride >= 2, "flow_deconv4x4s2_planes: bad argument");
+  SHINEON_REQUIRE(B > 0 && h > 0 && w > 0 && y_cstride >= 2 && y_cstride % 2 == 0, "flow_deconv4x4s2_planes: bad shape");
+  SHINEON_REQUIRE(plane_fmt == SHINEON_FMT_BF16 || plane_fmt == SHINEON_FMT_FP16, "flow_deconv4x4s2_planes: plane_fmt %d", plane_fmt);
+  SHINEON_REQUIRE((reinterpret_cast<uintptr_t>(y_hi) & 3) == 0 && (reinterpret_cast<uintptr_t>(y_lo) & 3) == 0, "flow_deconv4x4s2_planes: planes must be 4-byte aligned");
+  const long total = (long)B * 4 * h * w;
+  if (plane_fmt == SHINEON_FMT_FP16)
+    klaunch(flow_deconv4x4s2_planes_kernel<SHINEON_FMT_FP16>, blocks_for(total), 256, 0, (cudaStream_t)stream, flow, flow_cstride, weight,
+            bias, (plane_t*)y_hi, (plane_t*)y_lo, y_cstride, h, w, total);
+  else
+    klaunch(flow_deconv4x4s2_planes_kernel<SHINEON_FMT_BF16>, blocks_for(total), 256, 0, (cudaStream_t)stream, flow, flow_cstride, weight,
+            bias, (plane_t*)y_hi, (plane_t*)y_lo, y_cstride, h, w, total);
+  return after_launch("flow_deconv4x4s2_planes_kernel");
 }

@@ -81,6 +81,9 @@ class _Concat:
         return cmap
 
 
+# upsampled_flow* (2 -> 2 channel transposed convs on a predicted flow) on the direct CUDA-core kernel (A/B switch)
+UPFLOW_DIRECT = os.environ.get("SHINEON_UPFLOW_DIRECT", "1") != "0"
+
 # forwards that may run concurrently (models.flownet.FlowNet compute lanes) must not share concat buffers: the lane id
 # of the forward being issued is part of the cache key
 CONCAT_LANE = [0]
@@ -193,6 +196,20 @@ class _Net(nn.Module):
         pl = ops.conv2d(x, pc, want_planes=True)[1] if want_planes else None
         return f32, pl
 
+    def _upflow(self, prec, name, flow_f32, flow_planes, out):
+        """upsampled_flow*: ConvTranspose2d(2, 2, 4, 2, 1) of a predicted flow into `out` (the flow window of the next level's
+        concat buffer).  From the f32 flow on the small CUDA-core kernel (16 MACs per output value); UPFLOW_DIRECT = False keeps
+        the tensor-core transposed conv over the flow's 64-channel padded planes."""
+        if UPFLOW_DIRECT and flow_f32 is not None:
+            pk = self._packs(prec)
+            key = name + "/f32"
+            if key not in pk:
+                m = getattr(self, name)
+                pk[key] = (m.weight.detach().float().contiguous(), None if m.bias is None else m.bias.detach().float().contiguous())
+            wgt, bias = pk[key]
+            return ops.flow_deconv4x4s2_planes(flow_f32, wgt, bias, out)
+        return self._pc(prec, name)(flow_planes, out_planes=out)
+
     def _refine(self, prec, c6, cats, names):
         """Decoder shared by FlowNetC / FlowNetS (FlowNetC.py:100-123): cats = [concat5, concat4, concat3, concat2]."""
         src, segs = c6, None
@@ -200,8 +217,8 @@ class _Net(nn.Module):
         for lvl, cat in zip((5, 4, 3, 2), cats):
             join = self._fork(lambda: self._pc(prec, f"deconv{lvl}", segs)(src, post_act="leaky", act_param=LEAK,
                                                                           out_planes=cat.window(1)))
-            flow, flow_pl = self._flow(prec, f"predict_flow{lvl + 1}", src, segs)
-            self._pc(prec, f"upsampled_flow{lvl + 1}_to_{lvl}")(flow_pl, out_planes=cat.window(2))
+            flow, flow_pl = self._flow(prec, f"predict_flow{lvl + 1}", src, segs, want_f32=True, want_planes=not UPFLOW_DIRECT)
+            self._upflow(prec, f"upsampled_flow{lvl + 1}_to_{lvl}", flow, flow_pl, cat.window(2))
             join()
             src, segs = cat.buf, cat.seg
         flow2, _ = self._flow(prec, "predict_flow2", src, segs, want_f32=True, want_planes=False)
@@ -364,15 +381,16 @@ class FlowNetSD(_Net):
         c4 = self._c(prec, "conv4_1", self._c(prec, "conv4", c3), out=cat4.window(0))
         c5 = self._c(prec, "conv5_1", self._c(prec, "conv5", c4), out=cat5.window(0))
         c6 = self._c(prec, "conv6_1", self._c(prec, "conv6", c5))
-        flow, flow_pl = self._flow(prec, "predict_flow6", c6)
+        flow, flow_pl = self._flow(prec, "predict_flow6", c6, want_f32=True, want_planes=not UPFLOW_DIRECT)
         src, segs = c6, None
         for lvl, cat in zip((5, 4, 3, 2), (cat5, cat4, cat3, cat2)):
             join = self._fork(lambda: self._pc(prec, f"deconv{lvl}", segs)(src, post_act="leaky", act_param=LEAK,
                                                                           out_planes=cat.window(1)))
-            self._pc(prec, f"upsampled_flow{lvl + 1}_to_{lvl}")(flow_pl, out_planes=cat.window(2))
+            self._upflow(prec, f"upsampled_flow{lvl + 1}_to_{lvl}", flow, flow_pl, cat.window(2))
             join()
             inter = self._c(prec, f"inter_conv{lvl}", cat.buf, segs=cat.seg, act=False)
-            flow, flow_pl = self._flow(prec, f"predict_flow{lvl}", inter, want_f32=lvl == 2, want_planes=lvl != 2)
+            flow, flow_pl = self._flow(prec, f"predict_flow{lvl}", inter, want_f32=True,
+                                       want_planes=lvl != 2 and not UPFLOW_DIRECT)
             src, segs = cat.buf, cat.seg
         return flow
 
@@ -407,14 +425,14 @@ class FlowNetFusion(_Net):
         c1 = self._c(prec, "conv1_1", self._c(prec, "conv1", c0), out=cat1.window(0))
         c2 = self._c(prec, "conv2_1", self._c(prec, "conv2", c1))
         join = self._fork(lambda: self._pc(prec, "deconv1")(c2, post_act="leaky", act_param=LEAK, out_planes=cat1.window(1)))
-        _, flow2_pl = self._flow(prec, "predict_flow2", c2)
-        self._pc(prec, "upsampled_flow2_to_1")(flow2_pl, out_planes=cat1.window(2))
+        flow2, flow2_pl = self._flow(prec, "predict_flow2", c2, want_f32=True, want_planes=not UPFLOW_DIRECT)
+        self._upflow(prec, "upsampled_flow2_to_1", flow2, flow2_pl, cat1.window(2))
         join()
         i1 = self._c(prec, "inter_conv1", cat1.buf, segs=cat1.seg, act=False)
         join = self._fork(lambda: self._pc(prec, "deconv0", cat1.seg)(cat1.buf, post_act="leaky", act_param=LEAK,
                                                                        out_planes=cat0.window(1)))
-        _, flow1_pl = self._flow(prec, "predict_flow1", i1)
-        self._pc(prec, "upsampled_flow1_to_0")(flow1_pl, out_planes=cat0.window(2))
+        flow1, flow1_pl = self._flow(prec, "predict_flow1", i1, want_f32=True, want_planes=not UPFLOW_DIRECT)
+        self._upflow(prec, "upsampled_flow1_to_0", flow1, flow1_pl, cat0.window(2))
         join()
         i0 = self._c(prec, "inter_conv0", cat0.buf, segs=cat0.seg, act=False)
         flow0, _ = self._flow(prec, "predict_flow0", i0, want_f32=True, want_planes=False)

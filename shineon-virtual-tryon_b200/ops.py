@@ -847,6 +847,18 @@ def upsample4x_flow(src_nhwc, mul, bilinear):
     return dst
 
 
+def flow_deconv4x4s2_planes(flow_nhwc, weight, bias, out_planes):
+    """ConvTranspose2d(2, 2, 4, 2, 1) of a predicted flow (f32 NHWC [B,h,w,>=2]) written into the first two channels of
+    out_planes (a Planes / channel window [B,2h,2w,.]); weight f32 [2,2,4,4] CUDA (the module's layout), bias [2] or None."""
+    flow_nhwc, weight = _req(flow_nhwc, name="flow"), _req(weight, name="weight")
+    B, h, w, cs = flow_nhwc.shape
+    assert tuple(weight.shape) == (2, 2, 4, 4) and out_planes.N == B and out_planes.H == 2 * h and out_planes.W == 2 * w
+    check(_lib.load().shineon_flow_deconv4x4s2_planes(_p(flow_nhwc), cs, _p(weight), _p(bias), out_planes._ptr(out_planes.hi),
+                                                      out_planes._ptr(out_planes.lo), out_planes.cstride, B, h, w, out_planes.fmt,
+                                                      _stream()), "shineon_flow_deconv4x4s2_planes")
+    return out_planes
+
+
 def flownet_warp_concat(x, flow, div_flow):
     x, flow = _req(x), _req(flow)
     B, _, H, W = x.shape

@@ -249,6 +249,27 @@ def test_deconv_as_phase_convs(ops, shape):
     assert_close(got, F.leaky_relu(want, 0.1), atol=3e-5, rtol=1e-4, what="deconv planes window")
 
 
+@pytest.mark.parametrize("shape", [(2, 4, 3), (3, 16, 12), (1, 7, 5), (2, 64, 48)])
+def test_flow_deconv_direct(ops, shape):
+    """upsampled_flow* = ConvTranspose2d(2, 2, 4, 2, 1) of a predicted flow (FlowNetC.py:59-62) on the direct kernel: f32 NHWC
+    flow in, the two channels of a concat window out (hi/lo planes); against torch, with and without bias, and nothing
+    written outside the two channels."""
+    g = torch.Generator().manual_seed(5)
+    B, h, w = shape
+    flow = torch.randn(B, 2, h, w, generator=g) * 3
+    wt = torch.randn(2, 2, 4, 4, generator=g) * 0.3
+    for bias in (None, torch.randn(2, generator=g)):
+        want = F.conv_transpose2d(flow, wt, bias, stride=2, padding=1)
+        cat = ops.Planes(B, 2 * h, 2 * w, 128, device="cuda", cpad=128)
+        cat.hi.zero_(); cat.lo.zero_()
+        ops.flow_deconv4x4s2_planes(flow.permute(0, 2, 3, 1).contiguous().cuda(), wt.cuda(), None if bias is None else bias.cuda(),
+                                    cat.window(64, 2))
+        torch.cuda.synchronize()
+        got = (cat.hi.float() + cat.lo.float())[..., 64:66].permute(0, 3, 1, 2).cpu()
+        assert_close(got, want, atol=3e-5, rtol=1e-4, what="flow deconv (direct kernel)")
+        assert (cat.hi[..., :64] == 0).all() and (cat.hi[..., 66:] == 0).all() and (cat.lo[..., 66:] == 0).all()
+
+
 # ------------------------------------------------------------------------------------------ gather ops
 def _tps(ops, gs, H, W):
     from oracle.gmm import TpsTables
