@@ -55,34 +55,56 @@ def _init(net):
 
 
 # ------------------------------------------------------------------ engine helpers
-class _Concat:
-    """A concat buffer: segments at 64-aligned channel offsets of one Planes; `chan_map` for the consumers."""
+class _Segs(list):
+    """Segment channel counts of a concat buffer + the alignment of their offsets (64 = every segment readable on its own
+    as a conv input window; 8 = packed for write-only windows)."""
 
-    def __init__(self, N, H, W, seg_channels, prec, device):
+    def __init__(self, seg_channels, align=64):
+        super().__init__(seg_channels)
+        self.align = align
+
+
+def _seg_pad(c, align):
+    return (c + align - 1) // align * align
+
+
+class _Concat:
+    """A concat buffer: segments at aligned channel offsets of one Planes; `chan_map` for the consumers.  align = 8 packs
+    the segments (only the first one is then read on its own): FlowNetFusion's full-resolution concat of 64 + 16 + 2 channels
+    is 128 wide instead of 192, its half-resolution one (128 + 32 + 2) 192 instead of 256 -- a third less operand traffic
+    and K for the memory-bound layers that read them."""
+
+    def __init__(self, N, H, W, seg_channels, prec, device, align=64):
         self.offsets, off = [], 0
         for c in seg_channels:
             self.offsets.append(off)
-            off += ops.cpad64(c)
-        self.seg = list(seg_channels)
+            off += _seg_pad(c, align)
+        off = ops.cpad64(off)
+        self.align = align
+        self.seg = _Segs(seg_channels, align)
         self.buf = ops.Planes(N, H, W, off, prec=prec, device=device, cpad=off)
         self.buf.hi.zero_()
         if self.buf.lo is not None:
             self.buf.lo.zero_()
 
     def window(self, i):
-        return self.buf.window(self.offsets[i], self.seg[i])
+        return self.buf.window(self.offsets[i], self.seg[i], align=self.align)
 
     @staticmethod
     def chan_map(seg_channels):
+        align = getattr(seg_channels, "align", 64)
         cmap, base = [], 0
         for c in seg_channels:
-            cmap += list(range(base, base + c)) + [-1] * (ops.cpad64(c) - c)
+            cmap += list(range(base, base + c)) + [-1] * (_seg_pad(c, align) - c)
             base += c
-        return cmap
+        return cmap + [-1] * (ops.cpad64(len(cmap)) - len(cmap))
 
 
 # upsampled_flow* (2 -> 2 channel transposed convs on a predicted flow) on the direct CUDA-core kernel (A/B switch)
 UPFLOW_DIRECT = os.environ.get("SHINEON_UPFLOW_DIRECT", "1") != "0"
+
+# FlowNetFusion's concat buffers with packed (8-aligned) segments (A/B switch; 64 = one K-block per segment)
+FUSION_CONCAT_ALIGN = 8 if os.environ.get("SHINEON_FUSION_TIGHT_CONCAT", "1") != "0" else 64
 
 # forwards that may run concurrently (models.flownet.FlowNet compute lanes) must not share concat buffers: the lane id
 # of the forward being issued is part of the cache key
@@ -92,17 +114,17 @@ CONCAT_LANE = [0]
 class _Net(nn.Module):
     """Packed-weight cache shared by the four sub-networks."""
 
-    def _concat(self, N, H, W, seg_channels, prec, device):
+    def _concat(self, N, H, W, seg_channels, prec, device, align=64):
         """Concat buffers are kept per (shape, precision): every forward's producers overwrite all real channels of
         their windows and nothing ever writes the padding channels, so the zero fill happens once per buffer instead
         of once per forward (it was 78 fill launches = 5 % of a batch-16 FlowNet2 forward)."""
         cache = self.__dict__.setdefault("_cat_cache", {})
-        key = (N, H, W, tuple(seg_channels), prec, str(device), CONCAT_LANE[0])
+        key = (N, H, W, tuple(seg_channels), prec, str(device), CONCAT_LANE[0], align)
         cat = cache.get(key)
         if cat is None:
             if len(cache) >= 32:  # a new batch size / resolution: drop the old set
                 cache.clear()
-            cat = cache[key] = _Concat(N, H, W, seg_channels, prec, device)
+            cat = cache[key] = _Concat(N, H, W, seg_channels, prec, device, align)
         return cat
 
     # deconv{lvl} of a refinement level does not depend on that level's predict_flow -> upsampled_flow chain: it runs on an
@@ -419,8 +441,8 @@ class FlowNetFusion(_Net):
         """x: f32 NCHW [B,11,H,W] -> flow0 f32 NHWC [B,H,W,2] (FlowNetFusion.py:47-67)."""
         B, _, H, W = x.shape
         dev = x.device
-        cat1 = self._concat(B, H // 2, W // 2, (128, 32, 2), prec, dev)
-        cat0 = self._concat(B, H, W, (64, 16, 2), prec, dev)
+        cat1 = self._concat(B, H // 2, W // 2, (128, 32, 2), prec, dev, align=FUSION_CONCAT_ALIGN)
+        cat0 = self._concat(B, H, W, (64, 16, 2), prec, dev, align=FUSION_CONCAT_ALIGN)
         c0 = self._stem(prec, "conv0", x, out=cat0.window(0))
         c1 = self._c(prec, "conv1_1", self._c(prec, "conv1", c0), out=cat1.window(0))
         c2 = self._c(prec, "conv2_1", self._c(prec, "conv2", c1))

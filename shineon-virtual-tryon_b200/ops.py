@@ -100,11 +100,15 @@ class Planes:
     def cstride(self):
         return self.hi.shape[-1]
 
-    def window(self, c0, C):
-        """View of channels [c0, c0+C) (c0 % 64 == 0) sharing this buffer's storage."""
-        assert c0 % 64 == 0 and c0 + cpad64(C) <= self.hi.shape[-1]
+    def window(self, c0, C, align=64):
+        """View of channels [c0, c0+C) sharing this buffer's storage.  align = 64 (default): the window starts on a K-block
+        and owns whole K-blocks, so it can also be read as a conv input on its own; align = 8: a write-only slot of a packed
+        concat buffer (16-byte aligned stores), whose neighbours start right behind its 8-channel padding."""
+        assert align in (8, 64) and c0 % align == 0
+        wpad = cpad64(C) if align == 64 else (C + 7) // 8 * 8
+        assert c0 + wpad <= self.hi.shape[-1]
         v = Planes.__new__(Planes)
-        v.fmt, v.N, v.H, v.W, v.C, v.cpad = self.fmt, self.N, self.H, self.W, C, cpad64(C)
+        v.fmt, v.N, v.H, v.W, v.C, v.cpad = self.fmt, self.N, self.H, self.W, C, wpad
         v.hi, v.lo, v.coffset = self.hi, self.lo, self.coffset + c0
         return v
 
