@@ -685,7 +685,10 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------- B200 arm
-TRYON_METRIC = "try-on frames/sec @256x192 (GMM warp + U-Net)"
+# BASELINE.json: "try-on frames/sec @256x192 (warp+U-Net+flow)".  `value` / `e2e` are the primary form of SURVEY 8d config 3
+# (5 frames of a clip as a batch through GMM warp + U-Net); the flow-warp form of the same clip (`--n_frames_total 5
+# --flow_warp`, Resample2d blends) is timed in the same run and reported in `flow_warp_clips`, FlowNet2 itself by `--workload flow`.
+TRYON_METRIC = "try-on frames/sec @256x192 (warp+U-Net+flow: GMM warp + U-Net per frame; flow-warp clip form in flow_warp_clips)"
 N_INPUT_SETS = 4  # distinct device-resident input sets cycled by the timed loop: 4 x 39 MB of frames > the 126 MB L2
 
 
